@@ -1,0 +1,246 @@
+/*
+ * mbfea.h -- C ABI of libmbfea.so, the B200-native replacement for the
+ * simulation hot path of IasonManolas/MeshBeamFEA.
+ *
+ * The reference has no FFI: the path sits behind the C++ class BeamSimulator
+ * [REF src/beamsimulator.hpp:78-95], whose executeSimulation() forwards to
+ * fea::solve() of the un-vendored threed-beam-fea library
+ * [REF src/beamsimulator.cpp:40-69].  This header is what a binding for that
+ * seam binds: plain pointers and sizes, no C++/torch types.  The C++17 shim
+ * meshbeamfea_b200/cpp/beamsimulator.hpp re-exposes the reference's own class
+ * and struct names on top of it (INTEGRATION.md shows the two-line swap).
+ *
+ * Conventions
+ *  - Matrices are COLUMN-MAJOR, exactly the memory image of the reference's
+ *    Eigen members (Eigen::MatrixX3d nodes, MatrixX2i elements, MatrixX3d
+ *    elementalNormals, [REF src/beamsimulator.hpp:35-43]).
+ *  - DOF order per vertex: ux,uy,uz,rx,ry,rz; global DOF = 6*vertex+dof
+ *    [REF src/beamsimulator.cpp:139-150].
+ *  - Every function returns an mbfea_status; mbfea_last_error() gives text.
+ *  - There is NO CPU fallback: without a usable CUDA device every compute entry
+ *    point returns MBFEA_ECUDA.
+ */
+#ifndef MBFEA_H
+#define MBFEA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define MBFEA_VERSION 100 /* 0.1.0 */
+
+typedef enum mbfea_status {
+    MBFEA_OK = 0,
+    /* where the reference would hit a GSL Expects() and std::terminate:
+     * empty job [REF src/beamsimulator.cpp:41], size mismatches [:73-75],
+     * element index out of range [:81-83], b,h<=0 or nu outside [-1,0.5]
+     * [REF src/beam.hpp:14,25], dof outside [0,6) [REF src/utilities.hpp:77] */
+    MBFEA_EPRECOND = 1,
+    /* std::runtime_error("Vertex index is outside of valid range.")
+     * [REF src/beamsimulator.cpp:134-137] */
+    MBFEA_ERANGE_FIXED = 2,
+    /* std::range_error("Node index is out of valid range.")
+     * [REF src/beamsimulator.cpp:164-166] */
+    MBFEA_ERANGE_FORCE = 3,
+    MBFEA_ECUDA = 4,      /* CUDA / NCCL runtime failure, or no device        */
+    MBFEA_ESTATE = 5,     /* call order violated (e.g. execute before set_job) */
+    MBFEA_ENOCONV = 6,    /* PCG hit max_iter before reaching tol (results are
+                             still readable; stats carry the residual)         */
+    MBFEA_ESINGULAR = 7,  /* breakdown: non-SPD system (no fixed vertex,
+                             isolated vertex, zero-length beam ...)            */
+    MBFEA_EIO = 8,        /* scenario / PLY / CSV file problem                 */
+    MBFEA_EARG = 9        /* NULL pointer or nonsensical argument              */
+} mbfea_status;
+
+typedef struct mbfea_ctx mbfea_ctx; /* opaque: device buffers, stream, graphs, comm */
+
+typedef struct mbfea_options {
+    int32_t device;        /* CUDA ordinal; -1 = current device                */
+    int32_t verbose;       /* reference sets opts.verbose=true [REF :57]; here
+                              stdout logging is opt-in                         */
+    double  tol;           /* PCG stop: ||r||_2 <= tol*||f||_2   (1e-8)        */
+    int64_t max_iter;      /* 0 = 20*ndof                                       */
+    int32_t check_every;   /* PCG iterations per captured CUDA graph; the host
+                              polls convergence once per graph (0 = auto)      */
+    int32_t spmv_kernel;   /* 0 auto, 1 row-thread LDG kernel, 2 TMA-staged     */
+    int32_t rank;          /* vertex-block partition: this process' rank ...   */
+    int32_t world;         /* ... of `world` processes (1 = single GPU)        */
+    int32_t use_graph;     /* 1 = capture the PCG iteration in a CUDA graph     */
+    int32_t reserved[7];
+} mbfea_options;
+
+typedef struct mbfea_stats {
+    int64_t n_vertices, n_beams, n_fixed;
+    int64_t n_block_rows;       /* free vertices owned by this rank             */
+    int64_t n_block_rows_global;
+    int64_t nnz_blocks;         /* 6x6 blocks stored on this rank               */
+    int64_t n_ghost_blocks;     /* halo x-blocks received per SpMV              */
+    int64_t iterations;
+    double  rel_residual;       /* recurrence residual ||r||/||f|| at exit      */
+    double  true_rel_residual;  /* ||f-Ku||/||f|| recomputed after the solve    */
+    /* host wall-clock, ms */
+    double  ms_host_prep;       /* validate + float props + maps + pattern      */
+    double  ms_h2d;
+    /* device time (CUDA events on the ctx stream), ms */
+    double  ms_pack, ms_assemble, ms_precond, ms_pcg, ms_recover, ms_d2h;
+    double  ms_execute_total;
+    /* algorithmic bytes (DESIGN.md "Algorithmic bytes") for this rank */
+    double  bytes_spmv, bytes_pcg_iter, bytes_assemble, bytes_recover;
+    int64_t kernel_launches;    /* kernels launched by the last execute()       */
+    int32_t converged;
+    int32_t reserved[5];
+} mbfea_stats;
+
+int          mbfea_version(void);
+void         mbfea_options_default(mbfea_options *opts);
+int          mbfea_create(mbfea_ctx **out, const mbfea_options *opts);
+void         mbfea_destroy(mbfea_ctx *ctx);
+const char  *mbfea_last_error(const mbfea_ctx *ctx); /* ctx may be NULL: last create() error */
+const char  *mbfea_status_string(int status);
+
+/* ---- the simulation API: replaces BeamSimulator::setSimulation /
+ *      FeaSimulationJob::{setElements,setNodes,setFixedNodes,setNodalForces}
+ *      [REF src/beamsimulator.cpp:12-14,71-171] -------------------------------
+ * nodes_cm   3V doubles  x[V],y[V],z[V]          (Eigen::MatrixX3d nodes)
+ * elems_cm   2E int32    first[E],second[E]      (Eigen::MatrixX2i elements)
+ * normals_cm 3E doubles                          (MatrixX3d elementalNormals)
+ * dims_bh    2E floats   {b,h} per beam          (std::vector<BeamDimensions>)
+ * mat_nuE    2E floats   {nu,E_GPa} per beam     (std::vector<BeamMaterial>)
+ * fixed      F  int32                            (Eigen::VectorXi fixedNodes)
+ * f_node/f_dof/f_mag  nF entries                 (std::vector<NodalForce>)
+ * All inputs are copied; the caller may free them on return.
+ * Section properties EA,EIz,EIy,GJ are derived here, on the host, in IEEE
+ * float with the reference's promotion rules [REF src/beamsimulator.cpp:173-188].
+ */
+int mbfea_set_job(mbfea_ctx *ctx, int64_t V, int64_t E,
+                  const double *nodes_cm, const int32_t *elems_cm,
+                  const double *normals_cm, const float *dims_bh,
+                  const float *mat_nuE, int64_t F, const int32_t *fixed,
+                  int64_t nF, const int64_t *f_node, const int64_t *f_dof,
+                  const double *f_mag);
+
+/* Replaces only the loads (same mesh, same constraints): the pattern, maps and
+ * device mesh stay resident.  Same checks as FeaSimulationJob::setNodalForces. */
+int mbfea_set_forces(mbfea_ctx *ctx, int64_t nF, const int64_t *f_node,
+                     const int64_t *f_dof, const double *f_mag);
+
+/* ---- replaces BeamSimulator::executeSimulation -> fea::solve
+ *      [REF src/beamsimulator.cpp:40-69]: element stiffness + rotation,
+ *      assembly, elimination, PCG, element-force recovery.  Results stay on
+ *      the device until fetched.  Returns MBFEA_ENOCONV / MBFEA_ESINGULAR with
+ *      results still readable.                                              */
+int mbfea_execute(mbfea_ctx *ctx);
+
+/* the three phases of execute(), separately callable (bench / profiling) */
+int mbfea_assemble(mbfea_ctx *ctx); /* K1+K2 (+block-Jacobi setup K5)        */
+int mbfea_solve(mbfea_ctx *ctx);    /* K4+K6 PCG                              */
+int mbfea_recover(mbfea_ctx *ctx);  /* expand u, K7 element forces            */
+
+/* ---- results: the memory image of SimulationResults
+ *      [REF src/beamsimulator.hpp:45-52; src/beamsimulator.cpp:190-210] -----
+ * U_cm   6V doubles, column-major V x 6 (Eigen::MatrixXd nodalDisplacements);
+ *        rows of fixed vertices are 0.
+ * F6x2E  12E doubles: component c in [0,6) occupies [c*2E,(c+1)*2E);
+ *        entry 2e = end 0 of beam e, 2e+1 = end 1 (std::vector<VectorXd>
+ *        edgeForces), local frame, order N,Ty,Tz,Mx,My,Mz.                   */
+int mbfea_get_displacements(mbfea_ctx *ctx, double *U_cm);
+int mbfea_get_edge_forces(mbfea_ctx *ctx, double *F6x2E);
+int mbfea_get_stats(const mbfea_ctx *ctx, mbfea_stats *out);
+
+/* result files the reference has fea::solve write when a file name is set
+ * [REF src/beamsimulator.cpp:46-54]: V x 6 and E x 12, ',' separated,
+ * precision 14.  Opt-in here.                                               */
+int mbfea_write_displacements_csv(mbfea_ctx *ctx, const char *path);
+int mbfea_write_element_forces_csv(mbfea_ctx *ctx, const char *path);
+
+/* ---- parity / debug taps (tests compare these with the oracle) ----------- */
+int mbfea_get_props(mbfea_ctx *ctx, double *props4 /* E x {EA,EIz,EIy,GJ} */);
+int mbfea_get_dofmap(mbfea_ctx *ctx, int32_t *free_index /* V; -1 = fixed */);
+int mbfea_get_kelem(mbfea_ctx *ctx, double *Ke /* E x 12 x 12 row-major */);
+int mbfea_get_bsr_sizes(mbfea_ctx *ctx, int64_t *n_block_rows, int64_t *nnz_blocks,
+                        int64_t *row_offset /* first global block row owned */,
+                        int64_t *n_ghost);
+/* local BSR of this rank: rowptr nb+1, colidx nnzb (LOCAL column ids: owned
+ * [0,nb) then ghosts), vals nnzb x 36 row-major 6x6; ghost_global n_ghost
+ * global block-row ids of the ghost columns.  Any pointer may be NULL.       */
+int mbfea_get_bsr(mbfea_ctx *ctx, int64_t *rowptr, int32_t *colidx, double *vals,
+                  int64_t *ghost_global);
+int mbfea_get_load(mbfea_ctx *ctx, double *f_reduced /* 6*nb, owned rows */);
+/* y = K x on the owned rows, single-rank contexts only: x,y 6*nb doubles (host) */
+int mbfea_spmv(mbfea_ctx *ctx, const double *x, double *y);
+/* same, with an explicit kernel choice (1 row-thread, 2 TMA-staged) */
+int mbfea_spmv_with(mbfea_ctx *ctx, int32_t kernel, const double *x, double *y);
+/* inject displacements (V x 6 column-major) and run only K7 on them */
+int mbfea_recover_from(mbfea_ctx *ctx, const double *U_cm);
+
+/* ---- measurement helpers (bench.py) --------------------------------------
+ * Runs the SpMV kernel `reps` times on the ctx stream between two CUDA events
+ * (after `warmup` untimed launches) and returns the mean ms per launch.      */
+int mbfea_time_spmv(mbfea_ctx *ctx, int32_t kernel /* as options.spmv_kernel */,
+                    int32_t warmup, int32_t reps, double *ms_per_launch);
+int mbfea_time_assemble(mbfea_ctx *ctx, int32_t warmup, int32_t reps, double *ms_per_launch);
+
+/* ---- multi-GPU (one process per GPU; vertex-block partition) -------------
+ * Rank 0 makes an id, the launcher broadcasts the 128 bytes (torch.distributed
+ * in bench.py), every rank calls comm_init before set_job.  Collectives on the
+ * data path: halo exchange of boundary x-blocks per SpMV and an all-gather of
+ * per-rank dot-product partials (summed in fixed rank order).               */
+int mbfea_comm_unique_id(uint8_t id128[128]);
+int mbfea_comm_init(mbfea_ctx *ctx, const uint8_t id128[128], int32_t rank, int32_t world);
+
+/* Host-only partition plan (no GPU needed; exercised by the gloo CPU tests):
+ * which block rows `rank` owns and which ghost blocks it receives from whom.
+ * Call with NULL arrays to size.  send_* describe what this rank SENDS.      */
+typedef struct mbfea_plan_sizes {
+    int64_t nb_global, row_begin, row_end, nnz_blocks, n_ghost, n_send, n_neighbors;
+} mbfea_plan_sizes;
+int mbfea_plan_partition(int64_t V, int64_t E, const int32_t *elems_cm,
+                         int64_t F, const int32_t *fixed, int32_t rank, int32_t world,
+                         mbfea_plan_sizes *sizes,
+                         int64_t *rowptr /* nb_local+1 */, int32_t *colidx /* nnzb, local ids */,
+                         int64_t *ghost_global /* n_ghost, ascending => grouped by owner */,
+                         int32_t *ghost_owner /* n_ghost */,
+                         int64_t *send_local_rows /* n_send local row ids, grouped by dest */,
+                         int32_t *send_dest /* n_send */);
+
+/* ---- scenario files ("next" row 1): config.json + ASCII PLY edge mesh -----
+ * [REF src/utilities.hpp:50-95; src/edgemesh.cpp:115-135;
+ *      Models/TwoLineSegments.ply].  Loads the scenario and calls set_job.    */
+int mbfea_load_scenario(mbfea_ctx *ctx, const char *config_json_path,
+                        const char *ply_path_override /* NULL = use plyFilename */);
+
+/* The same files parsed into flat arrays without touching a GPU (host-only). */
+typedef struct mbfea_scenario mbfea_scenario;
+int  mbfea_scenario_open(const char *config_json_path, const char *ply_path_override,
+                         mbfea_scenario **out, char *errbuf, int64_t errbuf_len);
+void mbfea_scenario_sizes(const mbfea_scenario *sc, int64_t *V, int64_t *E, int64_t *F, int64_t *nF);
+void mbfea_scenario_copy(const mbfea_scenario *sc, double *nodes_cm, int32_t *elems_cm,
+                         double *normals_cm, float *dims_bh, float *mat_nuE, int32_t *fixed,
+                         int64_t *f_node, int64_t *f_dof, double *f_mag);
+void mbfea_scenario_close(mbfea_scenario *sc);
+
+/* ---- host-only pieces of set_job, callable without a GPU (CPU tests) --------
+ * validate: the checks of set_job in the reference's order, same return codes;
+ *           msg (may be NULL) receives the text mbfea_last_error would give.
+ * props   : EA,EIz,EIy,GJ per beam with the reference's float arithmetic
+ *           [REF src/beamsimulator.cpp:173-188].
+ * free_map: K3 on the host (the device kernel must agree bit for bit).        */
+int mbfea_host_validate(int64_t V, int64_t E, const int32_t *elems_cm, const float *dims_bh,
+                        const float *mat_nuE, int64_t F, const int32_t *fixed, int64_t nF,
+                        const int64_t *f_node, const int64_t *f_dof, char *msg, int64_t msg_len);
+int mbfea_host_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4);
+int mbfea_host_free_map(int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
+                        int64_t *n_free);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBFEA_H */

@@ -1,0 +1,1065 @@
+// libmbfea.so C ABI (include/mbfea.h): context, device residency, the PCG
+// driver with its CUDA-graph batching, multi-GPU plumbing and the parity taps.
+// Host code is C++17; all device work is in kernels.cu.  There is no CPU
+// fallback: without a CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "mbfea_internal.hpp"
+#include "nccl_dl.hpp"
+
+using namespace mbfea;
+using namespace mbfea::dev;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+};
+
+struct CudaFail { cudaError_t e; const char *what; int line; };
+struct NcclFail { int e; const char *what; int line; };
+
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) throw CudaFail{_e, #call, __LINE__};     \
+    } while (0)
+#define NK(call)                                                        \
+    do {                                                                \
+        int _e = (call);                                                \
+        if (_e != 0) throw NcclFail{_e, #call, __LINE__};               \
+    } while (0)
+
+}  // namespace
+
+struct mbfea_ctx {
+    mbfea_options opt{};
+    mutable std::string err;
+    int device = 0, sm_count = 148;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    // job (host)
+    bool have_job = false, assembled = false, solved = false, recovered = false;
+    int64_t V = 0, E = 0, F = 0;
+    HostPlan plan;
+    std::vector<double> props_host;
+    std::vector<int32_t> tile_row_host;
+    bool tma_ok = false;       // pattern fits the TMA tile geometry
+    bool tma_prepared = false;
+
+    // device: mesh
+    DevBuf<Node4> node4;
+    DevBuf<ElemRec> rec;
+    DevBuf<int32_t> free_index, fixed;
+    // device: pattern
+    DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, send_rows;
+    // device: matrix + vectors
+    DevBuf<double> vals, minv, f, x, r, z, p, Ap, sendbuf;
+    DevBuf<double> part_a, part_b, part_c, red, gath;
+    DevBuf<PcgScalars> sc;
+    DevBuf<int> flag;
+    PcgScalars *sc_host = nullptr;  // pinned
+    // device: results
+    DevBuf<double> xg, U_cm, U_rm, F6;
+
+    // multi-GPU
+    const nccl::Api *nc = nullptr;
+    nccl::Comm comm = nullptr;
+
+    // PCG graph cache
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_iters = 0, graph_kernel = 0;
+    int64_t launches = 0;
+
+    mbfea_stats stats{};
+
+    int64_t nb() const { return plan.nb(); }
+    int64_t ng() const { return (int64_t)plan.ghost_global.size(); }
+    int world() const { return opt.world; }
+    int64_t row_begin_of(int q) const { return plan.nb_global * q / opt.world; }
+};
+
+namespace {
+
+int fail(mbfea_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+template <class Fn>
+int guarded(mbfea_ctx *c, Fn fn)
+{
+    try {
+        return fn();
+    } catch (const CudaFail &f) {
+        char buf[512];
+        std::snprintf(buf, sizeof buf, "CUDA error %d (%s) at api.cu:%d in %s", (int)f.e, cudaGetErrorString(f.e),
+                      f.line, f.what);
+        cudaGetLastError();
+        return fail(c, MBFEA_ECUDA, buf);
+    } catch (const NcclFail &f) {
+        char buf[512];
+        std::snprintf(buf, sizeof buf, "NCCL error %d (%s) at api.cu:%d in %s", f.e,
+                      (c && c->nc) ? c->nc->GetErrorString(f.e) : "?", f.line, f.what);
+        return fail(c, MBFEA_ECUDA, buf);
+    } catch (const std::bad_alloc &) {
+        return fail(c, MBFEA_EARG, "host allocation failed");
+    }
+}
+
+template <class T>
+void upload(mbfea_ctx *c, DevBuf<T> &d, const T *h, size_t n)
+{
+    CK(d.alloc(n));
+    if (n) CK(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, c->st));
+}
+
+template <class T>
+void upload(mbfea_ctx *c, DevBuf<T> &d, const std::vector<T> &h) { upload(c, d, h.data(), h.size()); }
+
+void drop_graph(mbfea_ctx *c)
+{
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->graph_exec = nullptr; c->graph_iters = 0; c->graph_kernel = 0;
+}
+
+int pick_spmv(const mbfea_ctx *c, int requested)
+{
+    int k = requested ? requested : c->opt.spmv_kernel;
+    if (k == 0) k = c->tma_ok ? 2 : 1;
+    if (k == 2 && !c->tma_ok) k = 1;
+    return k;
+}
+
+// one SpMV on the ctx stream: y = K x (x has nb + n_ghost blocks)
+void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *partial, const PcgScalars *sc)
+{
+    const int64_t nb = c->nb();
+    if (nb <= 0) return;
+    if (kernel == 2) {
+        if (!c->tma_prepared) {
+            CK((cudaError_t)spmv_tma_prepare());
+            c->tma_prepared = true;
+        }
+        const int64_t ntiles = (int64_t)c->tile_row_host.size() - 1;
+        launch_spmv_tma(c->st, spmv_tma_grid(ntiles, c->sm_count), ntiles, c->tile_row.p, c->rowptr.p, c->colidx.p,
+                        c->vals.p, x, y, partial, sc);
+    } else {
+        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, x, y, partial, sc);
+    }
+    c->launches++;
+}
+
+int spmv_grid(const mbfea_ctx *c, int kernel)
+{
+    if (kernel == 2) return spmv_tma_grid((int64_t)c->tile_row_host.size() - 1, c->sm_count);
+    return spmv_rowthread_grid(c->nb());
+}
+
+// boundary x-blocks -> neighbours' ghost slots (multi-GPU only)
+void halo_exchange(mbfea_ctx *c, double *xvec)
+{
+    if (c->world() <= 1 || c->plan.neighbors.empty()) return;
+    const int64_t nb = c->nb();
+    launch_pack_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, xvec, c->sendbuf.p);
+    c->launches++;
+    NK(c->nc->GroupStart());
+    for (const Neighbor &q : c->plan.neighbors) {
+        if (q.send_count)
+            NK(c->nc->Send(c->sendbuf.p + 6 * q.send_offset, (size_t)(6 * q.send_count), nccl::kFloat64, q.rank,
+                           c->comm, c->st));
+        if (q.recv_count)
+            NK(c->nc->Recv(xvec + 6 * (nb + q.recv_offset), (size_t)(6 * q.recv_count), nccl::kFloat64, q.rank,
+                           c->comm, c->st));
+    }
+    NK(c->nc->GroupEnd());
+}
+
+// One PCG iteration (parity = iteration & 1) enqueued on the stream.
+// Dot products: single GPU -> consumers read the per-CTA partials directly.
+// Multi GPU -> each rank collapses its partials, all-gathers the per-rank
+// values, and every rank sums the W entries in rank order (identical bits on
+// every rank, so all ranks take the same stop decision).
+void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
+{
+    const int64_t nb = c->nb();
+    const int W = c->world();
+    const int gs = spmv_grid(c, kernel), gv = vec_grid(nb);
+    halo_exchange(c, c->p.p);
+    run_spmv(c, kernel, c->p.p, c->Ap.p, c->part_a.p, c->sc.p);
+    PartialRef pAp{c->part_a.p, gs, 1};
+    if (W > 1) {
+        launch_reduce_partials(c->st, c->part_a.p, gs, c->red.p, nullptr, nullptr, c->sc.p);
+        NK(c->nc->AllGather(c->red.p, c->gath.p, 1, nccl::kFloat64, c->comm, c->st));
+        pAp = PartialRef{c->gath.p, W, 1};
+        c->launches++;
+    }
+    launch_pcg_update(c->st, nb, parity, pAp, c->minv.p, c->p.p, c->Ap.p, c->x.p, c->r.p, c->z.p, c->part_b.p,
+                      c->part_c.p, c->sc.p);
+    PartialRef rz{c->part_b.p, gv, 1}, rr{c->part_c.p, gv, 1};
+    if (W > 1) {
+        launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, c->part_c.p, c->red.p + 3, c->sc.p);
+        NK(c->nc->AllGather(c->red.p + 2, c->gath.p + W, 2, nccl::kFloat64, c->comm, c->st));
+        rz = PartialRef{c->gath.p + W, W, 2};
+        rr = PartialRef{c->gath.p + W + 1, W, 2};
+        c->launches++;
+    }
+    launch_pcg_pupdate(c->st, nb, parity, rz, rr, c->z.p, c->p.p, c->sc.p);
+    c->launches += 2;
+}
+
+void do_assemble(mbfea_ctx *c)
+{
+    launch_assemble(c->st, c->plan.nnzb(), c->contrib_ptr.p, c->contrib.p, c->rec.p, c->node4.p, c->vals.p);
+    c->launches++;
+}
+
+void do_precond(mbfea_ctx *c)
+{
+    CK(cudaMemsetAsync(c->flag.p, 0, sizeof(int), c->st));
+    launch_block_jacobi(c->st, c->nb(), c->diag_idx.p, c->vals.p, c->minv.p, c->flag.p);
+    c->launches++;
+}
+
+float elapsed(mbfea_ctx *c, int a, int b)
+{
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]));
+    return ms;
+}
+
+int need_job(mbfea_ctx *c)
+{
+    if (!c) return MBFEA_EARG;
+    if (!c->have_job) return fail(c, MBFEA_ESTATE, "no job: call mbfea_set_job first");
+    return MBFEA_OK;
+}
+
+void upload_forces(mbfea_ctx *c, int64_t nF, const int64_t *f_node, const int64_t *f_dof, const double *f_mag)
+{
+    const int64_t nb = c->nb();
+    CK(cudaMemsetAsync(c->f.p, 0, (size_t)std::max<int64_t>(1, 6 * nb) * sizeof(double), c->st));
+    if (nF > 0) {
+        DevBuf<int64_t> dn, dd;
+        DevBuf<double> dm;
+        upload(c, dn, f_node, (size_t)nF);
+        upload(c, dd, f_dof, (size_t)nF);
+        upload(c, dm, f_mag, (size_t)nF);
+        launch_scatter_forces(c->st, nF, dn.p, dd.p, dm.p, c->free_index.p, c->plan.row_begin, nb, c->f.p);
+        CK(cudaStreamSynchronize(c->st));
+    }
+    c->solved = c->recovered = false;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int mbfea_version(void) { return MBFEA_VERSION; }
+
+void mbfea_options_default(mbfea_options *o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    o->device = -1;
+    o->verbose = 0;
+    o->tol = 1e-8;
+    o->max_iter = 0;
+    o->check_every = 0;
+    o->spmv_kernel = 0;
+    o->rank = 0;
+    o->world = 1;
+    o->use_graph = 1;
+}
+
+const char *mbfea_status_string(int s)
+{
+    switch (s) {
+        case MBFEA_OK: return "ok";
+        case MBFEA_EPRECOND: return "precondition violated (the reference would Expects()-terminate)";
+        case MBFEA_ERANGE_FIXED: return "Vertex index is outside of valid range.";
+        case MBFEA_ERANGE_FORCE: return "Node index is out of valid range.";
+        case MBFEA_ECUDA: return "CUDA/NCCL failure or no device";
+        case MBFEA_ESTATE: return "call order violated";
+        case MBFEA_ENOCONV: return "PCG did not converge within max_iter";
+        case MBFEA_ESINGULAR: return "singular or non-SPD system";
+        case MBFEA_EIO: return "file error";
+        case MBFEA_EARG: return "bad argument";
+        default: return "unknown status";
+    }
+}
+
+const char *mbfea_last_error(const mbfea_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int mbfea_create(mbfea_ctx **out, const mbfea_options *opts)
+{
+    if (!out) return fail(nullptr, MBFEA_EARG, "out is NULL");
+    *out = nullptr;
+    mbfea_options o;
+    if (opts) o = *opts; else mbfea_options_default(&o);
+    if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return fail(nullptr, MBFEA_EARG, "bad rank/world");
+    if (!(o.tol > 0.0)) o.tol = 1e-8;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, MBFEA_ECUDA,
+                    std::string("no usable CUDA device (libmbfea has no CPU fallback): ") + cudaGetErrorString(e));
+    }
+    std::unique_ptr<mbfea_ctx> c(new (std::nothrow) mbfea_ctx);
+    if (!c) return fail(nullptr, MBFEA_EARG, "host allocation failed");
+    c->opt = o;
+    int rc = guarded(nullptr, [&]() -> int {
+        if (o.device >= 0) CK(cudaSetDevice(o.device));
+        CK(cudaGetDevice(&c->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, c->device));
+        if (prop.major < 10) {
+            return fail(nullptr, MBFEA_ECUDA, std::string("device '") + prop.name +
+                                                  "' is not sm_100-class; libmbfea ships sm_100a code only");
+        }
+        c->sm_count = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+        CK(cudaMallocHost(reinterpret_cast<void **>(&c->sc_host), sizeof(PcgScalars)));
+        CK(c->sc.alloc(1));
+        CK(c->flag.alloc(1));
+        CK(c->part_a.alloc(kMaxPartials));
+        CK(c->part_b.alloc(kMaxPartials));
+        CK(c->part_c.alloc(kMaxPartials));
+        CK(c->red.alloc(8));
+        CK(c->gath.alloc((size_t)8 * o.world));
+        return MBFEA_OK;
+    });
+    if (rc != MBFEA_OK) return rc;
+    *out = c.release();
+    return MBFEA_OK;
+}
+
+void mbfea_destroy(mbfea_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    drop_graph(c);
+    if (c->comm && c->nc) c->nc->CommDestroy(c->comm);
+    for (auto &ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->sc_host) cudaFreeHost(c->sc_host);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int mbfea_comm_unique_id(uint8_t id128[128])
+{
+    if (!id128) return MBFEA_EARG;
+    std::string msg;
+    const nccl::Api *nc = nccl::load(msg);
+    if (!nc) return fail(nullptr, MBFEA_ECUDA, msg);
+    nccl::UniqueId id;
+    if (int e = nc->GetUniqueId(&id)) return fail(nullptr, MBFEA_ECUDA, std::string("ncclGetUniqueId: ") + nc->GetErrorString(e));
+    std::memcpy(id128, id.internal, 128);
+    return MBFEA_OK;
+}
+
+int mbfea_comm_init(mbfea_ctx *c, const uint8_t id128[128], int32_t rank, int32_t world)
+{
+    if (!c || !id128) return MBFEA_EARG;
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, MBFEA_EARG, "bad rank/world");
+    if (c->have_job) return fail(c, MBFEA_ESTATE, "comm_init must precede set_job");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        std::string msg;
+        c->nc = nccl::load(msg);
+        if (!c->nc) return fail(c, MBFEA_ECUDA, msg);
+        nccl::UniqueId id;
+        std::memcpy(id.internal, id128, 128);
+        NK(c->nc->CommInitRank(&c->comm, world, id, rank));
+        c->opt.rank = rank; c->opt.world = world;
+        CK(c->gath.alloc((size_t)8 * world));
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm,
+                  const double *normals_cm, const float *dims_bh, const float *mat_nuE, int64_t F,
+                  const int32_t *fixed, int64_t nF, const int64_t *f_node, const int64_t *f_dof,
+                  const double *f_mag)
+{
+    if (!c) return MBFEA_EARG;
+    if (F < 0 || nF < 0) return fail(c, MBFEA_EARG, "negative count");
+    if ((V > 0 && !nodes_cm) || (E > 0 && (!elems_cm || !normals_cm || !dims_bh || !mat_nuE)) || (F > 0 && !fixed) ||
+        (nF > 0 && (!f_node || !f_dof || !f_mag)))
+        return fail(c, MBFEA_EARG, "NULL input array");
+    if (c->world() > 1 && !c->comm) return fail(c, MBFEA_ESTATE, "world > 1 requires mbfea_comm_init first");
+    c->have_job = c->assembled = c->solved = c->recovered = false;
+    std::string msg;
+    if (int rc = validate_job(V, E, elems_cm, dims_bh, mat_nuE, F, fixed, nF, f_node, f_dof, msg)) return fail(c, rc, msg);
+
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        drop_graph(c);
+        std::memset(&c->stats, 0, sizeof c->stats);
+        const double t0 = now_ms();
+        c->V = V; c->E = E; c->F = F;
+        c->props_host.resize((size_t)4 * E);
+        derive_props(E, dims_bh, mat_nuE, c->props_host.data());
+        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan);
+        build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
+        c->tma_ok = true;
+        for (size_t t = 0; t + 1 < c->tile_row_host.size(); ++t)
+            if (c->plan.rowptr[c->tile_row_host[t + 1]] - c->plan.rowptr[c->tile_row_host[t]] > kTmaCapBlocks)
+                c->tma_ok = false;  // a single row longer than a stage: row-thread kernel only
+        const double t1 = now_ms();
+        c->stats.ms_host_prep = t1 - t0;
+
+        const int64_t nb = c->nb(), ng = c->ng(), nnzb = c->plan.nnzb();
+        // mesh -> device, repacked into aligned records
+        {
+            DevBuf<double> d_nodes, d_normals, d_props;
+            DevBuf<int32_t> d_elems, d_scratch;
+            upload(c, d_nodes, nodes_cm, (size_t)3 * V);
+            upload(c, d_elems, elems_cm, (size_t)2 * E);
+            upload(c, d_normals, normals_cm, (size_t)3 * E);
+            upload(c, d_props, c->props_host);
+            upload(c, c->fixed, fixed, (size_t)F);
+            CK(c->node4.alloc((size_t)V));
+            CK(c->rec.alloc((size_t)E));
+            CK(c->free_index.alloc((size_t)V));
+            CK(d_scratch.alloc((size_t)V + (size_t)V / 1024 + 2));
+            launch_pack_nodes(c->st, V, d_nodes.p, c->node4.p);
+            launch_pack_elems(c->st, E, d_elems.p, d_normals.p, d_props.p, c->rec.p);
+            launch_free_map(c->st, V, F, c->fixed.p, c->free_index.p, d_scratch.p);  // K3
+            CK(cudaStreamSynchronize(c->st));
+        }
+        upload(c, c->rowptr, c->plan.rowptr);
+        upload(c, c->colidx, c->plan.colidx);
+        upload(c, c->diag_idx, c->plan.diag_idx);
+        upload(c, c->contrib_ptr, c->plan.contrib_ptr);
+        upload(c, c->contrib, c->plan.contrib);
+        upload(c, c->tile_row, c->tile_row_host);
+        upload(c, c->send_rows, c->plan.send_rows);
+        CK(c->sendbuf.alloc((size_t)6 * c->plan.send_rows.size()));
+        CK(c->vals.alloc((size_t)nnzb * 36));
+        CK(c->minv.alloc((size_t)nb * 36));
+        CK(c->f.alloc((size_t)6 * nb));
+        CK(c->x.alloc((size_t)6 * nb));
+        CK(c->r.alloc((size_t)6 * nb));
+        CK(c->z.alloc((size_t)6 * nb));
+        CK(c->Ap.alloc((size_t)6 * nb));
+        CK(c->p.alloc((size_t)6 * (nb + ng)));
+        CK(cudaMemsetAsync(c->p.p, 0, (size_t)std::max<int64_t>(1, 6 * (nb + ng)) * sizeof(double), c->st));
+        CK(c->xg.alloc((size_t)6 * c->plan.nb_global));
+        CK(c->U_cm.alloc((size_t)6 * V));
+        CK(c->U_rm.alloc((size_t)6 * V));
+        CK(c->F6.alloc((size_t)12 * E));
+        // the contributor lists are only needed on the device from here on
+        c->plan.contrib.clear(); c->plan.contrib.shrink_to_fit();
+        c->plan.contrib_ptr.clear(); c->plan.contrib_ptr.shrink_to_fit();
+        upload_forces(c, nF, f_node, f_dof, f_mag);
+        CK(cudaStreamSynchronize(c->st));
+        c->stats.ms_h2d = now_ms() - t1;
+
+        mbfea_stats &s = c->stats;
+        s.n_vertices = V; s.n_beams = E; s.n_fixed = V - c->plan.nb_global;
+        s.n_block_rows = nb; s.n_block_rows_global = c->plan.nb_global;
+        s.nnz_blocks = nnzb; s.n_ghost_blocks = ng;
+        // algorithmic bytes: SpMV 292/block + 100/row; PCG iteration
+        // adds 10 vector passes (48 B/row each) + the 288 B block-Jacobi inverse
+        s.bytes_spmv = 292.0 * (double)nnzb + 100.0 * (double)nb;
+        s.bytes_pcg_iter = s.bytes_spmv + 768.0 * (double)nb;
+        s.bytes_assemble = 112.0 * (double)E + 288.0 * (double)nnzb;
+        s.bytes_recover = 208.0 * (double)E + 96.0 * (double)E;
+        c->have_job = true;
+        if (c->opt.verbose)
+            std::fprintf(stderr, "[mbfea] rank %d/%d: V=%lld E=%lld free=%lld rows=%lld blocks=%lld ghosts=%lld prep=%.1f ms h2d=%.1f ms\n",
+                         c->opt.rank, c->opt.world, (long long)V, (long long)E, (long long)c->plan.nb_global,
+                         (long long)nb, (long long)nnzb, (long long)ng, s.ms_host_prep, s.ms_h2d);
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_set_forces(mbfea_ctx *c, int64_t nF, const int64_t *f_node, const int64_t *f_dof, const double *f_mag)
+{
+    if (int rc = need_job(c)) return rc;
+    if (nF < 0 || (nF > 0 && (!f_node || !f_dof || !f_mag))) return fail(c, MBFEA_EARG, "bad force arrays");
+    std::string msg;
+    if (int rc = validate_forces(c->V, nF, f_node, f_dof, msg)) return fail(c, rc, msg);
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        upload_forces(c, nF, f_node, f_dof, f_mag);
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_assemble(mbfea_ctx *c)
+{
+    if (int rc = need_job(c)) return rc;
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaEventRecord(c->ev[0], c->st));
+        do_assemble(c);
+        CK(cudaEventRecord(c->ev[1], c->st));
+        do_precond(c);
+        CK(cudaEventRecord(c->ev[2], c->st));
+        int flag = 0;
+        CK(cudaMemcpyAsync(&flag, c->flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->stats.ms_assemble = elapsed(c, 0, 1);
+        c->stats.ms_precond = elapsed(c, 1, 2);
+        c->assembled = true; c->solved = c->recovered = false;
+        if (flag) return fail(c, MBFEA_ESINGULAR,
+                              "a diagonal 6x6 block is not positive definite (isolated vertex, zero-length or zero-stiffness beam)");
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_solve(mbfea_ctx *c)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!c->assembled) return fail(c, MBFEA_ESTATE, "solve before assemble");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const int64_t nb = c->nb();
+        const int W = c->world();
+        const int kernel = pick_spmv(c, 0);
+        const int gv = vec_grid(nb);
+        long long max_iter = c->opt.max_iter;
+        if (max_iter <= 0) max_iter = std::min<long long>(20LL * 6 * std::max<int64_t>(1, c->plan.nb_global), 5000000LL);
+        int check = c->opt.check_every;
+        if (check <= 0) {
+            // aim at ~5 ms of device work between host polls
+            const double est_us = c->stats.bytes_pcg_iter / 4.0e6 + 8.0;
+            check = (int)std::min(200.0, std::max(2.0, 5000.0 / est_us));
+        }
+        check += check & 1;  // parity alternates: keep batches even
+
+        CK(cudaEventRecord(c->ev[0], c->st));
+        launch_pcg_init(c->st, nb, c->f.p, c->minv.p, c->x.p, c->r.p, c->z.p, c->p.p, c->part_b.p, c->part_c.p);
+        PartialRef rz{c->part_b.p, gv, 1}, ff{c->part_c.p, gv, 1};
+        if (W > 1) {
+            launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, c->part_c.p, c->red.p + 3, nullptr);
+            NK(c->nc->AllGather(c->red.p + 2, c->gath.p + W, 2, nccl::kFloat64, c->comm, c->st));
+            rz = PartialRef{c->gath.p + W, W, 2};
+            ff = PartialRef{c->gath.p + W + 1, W, 2};
+        }
+        launch_pcg_init_finish(c->st, rz, ff, c->sc.p, c->opt.tol, max_iter);
+        c->launches += 2;
+
+        bool use_graph = c->opt.use_graph != 0;
+        if (use_graph && (c->graph_exec == nullptr || c->graph_iters != check || c->graph_kernel != kernel)) {
+            drop_graph(c);
+            if (kernel == 2 && !c->tma_prepared) { CK((cudaError_t)spmv_tma_prepare()); c->tma_prepared = true; }
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = c->launches;
+            CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+            try {
+                for (int i = 0; i < check; ++i) enqueue_iteration(c, kernel, i & 1);
+            } catch (...) {
+                cudaStreamEndCapture(c->st, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            CK(cudaStreamEndCapture(c->st, &g));
+            c->launches = l0;
+            cudaError_t e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            CK(e);
+            c->graph_iters = check; c->graph_kernel = kernel;
+        }
+        const int64_t per_iter = (W > 1) ? 6 : 3;
+        for (;;) {
+            if (use_graph) {
+                CK(cudaGraphLaunch(c->graph_exec, c->st));
+                c->launches += per_iter * check;
+            } else {
+                for (int i = 0; i < check; ++i) enqueue_iteration(c, kernel, i & 1);
+            }
+            CK(cudaMemcpyAsync(c->sc_host, c->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            if (c->sc_host->done != 0) break;
+        }
+        CK(cudaEventRecord(c->ev[1], c->st));
+        // true residual ||f - K x|| / ||f||, recomputed
+        CK(cudaMemcpyAsync(c->p.p, c->x.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        halo_exchange(c, c->p.p);
+        run_spmv(c, kernel, c->p.p, c->Ap.p, nullptr, nullptr);
+        launch_residual(c->st, nb, c->f.p, c->Ap.p, c->part_a.p);
+        launch_reduce_partials(c->st, c->part_a.p, gv, c->red.p, nullptr, nullptr, nullptr);
+        c->launches += 2;
+        double rr_true = 0.0;
+        if (W > 1) {
+            NK(c->nc->AllGather(c->red.p, c->gath.p, 1, nccl::kFloat64, c->comm, c->st));
+            std::vector<double> g((size_t)W);
+            CK(cudaMemcpyAsync(g.data(), c->gath.p, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            for (double v : g) rr_true += v;
+        } else {
+            CK(cudaMemcpyAsync(&rr_true, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        }
+        const PcgScalars &h = *c->sc_host;
+        mbfea_stats &s = c->stats;
+        s.ms_pcg = elapsed(c, 0, 1);
+        s.iterations = h.iter;
+        s.rel_residual = h.ff > 0 ? std::sqrt(h.rr / h.ff) : 0.0;
+        s.true_rel_residual = h.ff > 0 ? std::sqrt(rr_true / h.ff) : 0.0;
+        s.converged = h.done == 1;
+        c->solved = true; c->recovered = false;
+        if (c->opt.verbose)
+            std::fprintf(stderr, "[mbfea] rank %d: PCG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d, batch %d\n",
+                         c->opt.rank, (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel, check);
+        if (h.done == 3) return fail(c, MBFEA_ESINGULAR, "PCG breakdown: p.Ap <= 0 or non-finite (system not SPD: is any vertex fixed?)");
+        if (h.done == 2) return fail(c, MBFEA_ENOCONV, "PCG reached max_iter before the requested tolerance");
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_recover(mbfea_ctx *c)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!c->solved) return fail(c, MBFEA_ESTATE, "recover before solve");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const int64_t nb = c->nb();
+        CK(cudaEventRecord(c->ev[0], c->st));
+        if (c->world() > 1) {
+            for (int q = 0; q < c->world(); ++q) {
+                const int64_t b = c->row_begin_of(q), e = c->row_begin_of(q + 1);
+                if (e > b)
+                    NK(c->nc->Broadcast(c->x.p, c->xg.p + 6 * b, (size_t)(6 * (e - b)), nccl::kFloat64, q, c->comm, c->st));
+            }
+        } else if (nb > 0) {
+            CK(cudaMemcpyAsync(c->xg.p, c->x.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        }
+        launch_expand(c->st, c->V, c->free_index.p, c->xg.p, c->U_cm.p, c->U_rm.p);
+        launch_element_forces(c->st, c->E, c->rec.p, c->node4.p, c->U_rm.p, c->F6.p);
+        c->launches += 2;
+        CK(cudaEventRecord(c->ev[1], c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->stats.ms_recover = elapsed(c, 0, 1);
+        c->recovered = true;
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_execute(mbfea_ctx *c)
+{
+    if (int rc = need_job(c)) return rc;
+    const double t0 = now_ms();
+    c->launches = 0;
+    int rc = mbfea_assemble(c);
+    if (rc != MBFEA_OK) return rc;
+    int rs = mbfea_solve(c);
+    if (rs != MBFEA_OK && rs != MBFEA_ENOCONV && rs != MBFEA_ESINGULAR) return rs;
+    const std::string keep = c->err;
+    rc = mbfea_recover(c);
+    if (rc != MBFEA_OK) return rc;
+    c->stats.ms_execute_total = now_ms() - t0;
+    c->stats.kernel_launches = c->launches;
+    if (rs != MBFEA_OK) c->err = keep;
+    return rs;
+}
+
+int mbfea_get_displacements(mbfea_ctx *c, double *U_cm)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!U_cm) return fail(c, MBFEA_EARG, "U_cm is NULL");
+    if (!c->recovered) return fail(c, MBFEA_ESTATE, "no results: call mbfea_execute first");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const double t0 = now_ms();
+        CK(cudaMemcpyAsync(U_cm, c->U_cm.p, (size_t)6 * c->V * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->stats.ms_d2h += now_ms() - t0;
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_get_edge_forces(mbfea_ctx *c, double *F6x2E)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!F6x2E) return fail(c, MBFEA_EARG, "F6x2E is NULL");
+    if (!c->recovered) return fail(c, MBFEA_ESTATE, "no results: call mbfea_execute first");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const double t0 = now_ms();
+        CK(cudaMemcpyAsync(F6x2E, c->F6.p, (size_t)12 * c->E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->stats.ms_d2h += now_ms() - t0;
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_get_stats(const mbfea_ctx *c, mbfea_stats *out)
+{
+    if (!c || !out) return MBFEA_EARG;
+    *out = c->stats;
+    return MBFEA_OK;
+}
+
+// ---- result files ----------------------------------------------------------
+static int write_csv(mbfea_ctx *c, const char *path, const std::vector<double> &rowmajor, int64_t rows, int cols)
+{
+    std::FILE *fp = std::fopen(path, "w");
+    if (!fp) return fail(c, MBFEA_EIO, std::string("cannot open ") + path);
+    for (int64_t r = 0; r < rows; ++r) {
+        for (int j = 0; j < cols; ++j)
+            std::fprintf(fp, j + 1 < cols ? "%.14g," : "%.14g\n", rowmajor[(size_t)r * cols + j]);
+    }
+    std::fclose(fp);
+    return MBFEA_OK;
+}
+
+int mbfea_write_displacements_csv(mbfea_ctx *c, const char *path)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!path) return fail(c, MBFEA_EARG, "path is NULL");
+    if (!c->recovered) return fail(c, MBFEA_ESTATE, "no results");
+    std::vector<double> U((size_t)6 * c->V);
+    int rc = guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(U.data(), c->U_rm.p, U.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return MBFEA_OK;
+    });
+    if (rc) return rc;
+    return write_csv(c, path, U, c->V, 6);
+}
+
+int mbfea_write_element_forces_csv(mbfea_ctx *c, const char *path)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!path) return fail(c, MBFEA_EARG, "path is NULL");
+    if (!c->recovered) return fail(c, MBFEA_ESTATE, "no results");
+    const int64_t E = c->E;
+    std::vector<double> F((size_t)12 * E), rows((size_t)12 * E);
+    int rc = guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(F.data(), c->F6.p, F.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return MBFEA_OK;
+    });
+    if (rc) return rc;
+    for (int64_t e = 0; e < E; ++e)
+        for (int k = 0; k < 6; ++k) {
+            rows[(size_t)e * 12 + k] = F[(size_t)k * 2 * E + 2 * e];
+            rows[(size_t)e * 12 + 6 + k] = F[(size_t)k * 2 * E + 2 * e + 1];
+        }
+    return write_csv(c, path, rows, E, 12);
+}
+
+// ---- parity / debug taps ---------------------------------------------------
+int mbfea_get_props(mbfea_ctx *c, double *props4)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!props4) return fail(c, MBFEA_EARG, "NULL");
+    std::memcpy(props4, c->props_host.data(), c->props_host.size() * sizeof(double));
+    return MBFEA_OK;
+}
+
+int mbfea_get_dofmap(mbfea_ctx *c, int32_t *free_index)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!free_index) return fail(c, MBFEA_EARG, "NULL");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(free_index, c->free_index.p, (size_t)c->V * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_get_kelem(mbfea_ctx *c, double *Ke)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!Ke) return fail(c, MBFEA_EARG, "NULL");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        DevBuf<double> d;
+        CK(d.alloc((size_t)144 * c->E));
+        launch_kelem(c->st, c->E, c->rec.p, c->node4.p, d.p);
+        CK(cudaMemcpyAsync(Ke, d.p, (size_t)144 * c->E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_get_bsr_sizes(mbfea_ctx *c, int64_t *nbr, int64_t *nnzb, int64_t *row_offset, int64_t *n_ghost)
+{
+    if (int rc = need_job(c)) return rc;
+    if (nbr) *nbr = c->nb();
+    if (nnzb) *nnzb = c->plan.nnzb();
+    if (row_offset) *row_offset = c->plan.row_begin;
+    if (n_ghost) *n_ghost = c->ng();
+    return MBFEA_OK;
+}
+
+int mbfea_get_bsr(mbfea_ctx *c, int64_t *rowptr, int32_t *colidx, double *vals, int64_t *ghost_global)
+{
+    if (int rc = need_job(c)) return rc;
+    if (vals && !c->assembled) return fail(c, MBFEA_ESTATE, "values requested before assemble");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const int64_t nb = c->nb(), nnzb = c->plan.nnzb();
+        if (rowptr) {
+            std::vector<int32_t> rp((size_t)nb + 1);
+            CK(cudaMemcpyAsync(rp.data(), c->rowptr.p, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            for (int64_t i = 0; i <= nb; ++i) rowptr[i] = rp[(size_t)i];
+        }
+        if (colidx) CK(cudaMemcpyAsync(colidx, c->colidx.p, (size_t)nnzb * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+        if (vals) CK(cudaMemcpyAsync(vals, c->vals.p, (size_t)nnzb * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if (ghost_global) std::copy(c->plan.ghost_global.begin(), c->plan.ghost_global.end(), ghost_global);
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_get_load(mbfea_ctx *c, double *f_reduced)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!f_reduced) return fail(c, MBFEA_EARG, "NULL");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(f_reduced, c->f.p, (size_t)6 * c->nb() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_spmv_with(mbfea_ctx *c, int32_t kernel, const double *x, double *y)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!x || !y) return fail(c, MBFEA_EARG, "NULL");
+    if (!c->assembled) return fail(c, MBFEA_ESTATE, "spmv before assemble");
+    if (c->world() > 1) return fail(c, MBFEA_ESTATE, "mbfea_spmv is a single-rank tap");
+    if (kernel == 2 && !c->tma_ok) return fail(c, MBFEA_EARG, "pattern has a row longer than a TMA stage");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const size_t n = (size_t)6 * c->nb() * sizeof(double);
+        CK(cudaMemcpyAsync(c->p.p, x, n, cudaMemcpyHostToDevice, c->st));
+        run_spmv(c, pick_spmv(c, kernel), c->p.p, c->Ap.p, nullptr, nullptr);
+        CK(cudaMemcpyAsync(y, c->Ap.p, n, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->solved = c->recovered = false;  // p / Ap were overwritten
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_spmv(mbfea_ctx *c, const double *x, double *y) { return mbfea_spmv_with(c, 0, x, y); }
+
+int mbfea_recover_from(mbfea_ctx *c, const double *U_cm)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!U_cm) return fail(c, MBFEA_EARG, "NULL");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(c->U_cm.p, U_cm, (size_t)6 * c->V * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        launch_colmajor_to_rowmajor(c->st, c->V, c->U_cm.p, c->U_rm.p);
+        launch_element_forces(c->st, c->E, c->rec.p, c->node4.p, c->U_rm.p, c->F6.p);
+        CK(cudaStreamSynchronize(c->st));
+        c->recovered = true;
+        return MBFEA_OK;
+    });
+}
+
+// ---- measurement helpers -----------------------------------------------------
+int mbfea_time_spmv(mbfea_ctx *c, int32_t kernel, int32_t warmup, int32_t reps, double *ms_per_launch)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!ms_per_launch || reps <= 0) return fail(c, MBFEA_EARG, "bad arguments");
+    if (!c->assembled) return fail(c, MBFEA_ESTATE, "time_spmv before assemble");
+    if (kernel == 2 && !c->tma_ok) return fail(c, MBFEA_EARG, "pattern has a row longer than a TMA stage");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const int k = pick_spmv(c, kernel);
+        launch_fill(c->st, 6 * (c->nb() + c->ng()), c->p.p, 0.5, 0.03125, 17);
+        for (int i = 0; i < warmup; ++i) run_spmv(c, k, c->p.p, c->Ap.p, c->part_a.p, nullptr);
+        CK(cudaEventRecord(c->ev[4], c->st));
+        for (int i = 0; i < reps; ++i) run_spmv(c, k, c->p.p, c->Ap.p, c->part_a.p, nullptr);
+        CK(cudaEventRecord(c->ev[5], c->st));
+        CK(cudaStreamSynchronize(c->st));
+        *ms_per_launch = (double)elapsed(c, 4, 5) / reps;
+        c->solved = c->recovered = false;
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_time_assemble(mbfea_ctx *c, int32_t warmup, int32_t reps, double *ms_per_launch)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!ms_per_launch || reps <= 0) return fail(c, MBFEA_EARG, "bad arguments");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        for (int i = 0; i < warmup; ++i) do_assemble(c);
+        CK(cudaEventRecord(c->ev[4], c->st));
+        for (int i = 0; i < reps; ++i) do_assemble(c);
+        CK(cudaEventRecord(c->ev[5], c->st));
+        CK(cudaStreamSynchronize(c->st));
+        *ms_per_launch = (double)elapsed(c, 4, 5) / reps;
+        return MBFEA_OK;
+    });
+}
+
+// ---- host-only partition plan --------------------------------------------------
+int mbfea_plan_partition(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
+                         int32_t rank, int32_t world, mbfea_plan_sizes *sizes, int64_t *rowptr, int32_t *colidx,
+                         int64_t *ghost_global, int32_t *ghost_owner, int64_t *send_local_rows, int32_t *send_dest)
+{
+    if (V <= 0 || E <= 0 || !elems_cm || (F > 0 && !fixed) || world < 1 || rank < 0 || rank >= world) return MBFEA_EARG;
+    for (int64_t e = 0; e < 2 * E; ++e)
+        if (elems_cm[e] < 0 || elems_cm[e] >= V) return MBFEA_EPRECOND;
+    for (int64_t i = 0; i < F; ++i)
+        if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
+    HostPlan P;
+    try {
+        build_plan(V, E, elems_cm, F, fixed, rank, world, false, P);
+    } catch (const std::bad_alloc &) {
+        return MBFEA_EARG;
+    }
+    if (sizes) {
+        sizes->nb_global = P.nb_global; sizes->row_begin = P.row_begin; sizes->row_end = P.row_end;
+        sizes->nnz_blocks = P.nnzb(); sizes->n_ghost = (int64_t)P.ghost_global.size();
+        sizes->n_send = (int64_t)P.send_rows.size(); sizes->n_neighbors = (int64_t)P.neighbors.size();
+    }
+    if (rowptr) for (size_t i = 0; i < P.rowptr.size(); ++i) rowptr[i] = P.rowptr[i];
+    if (colidx) std::copy(P.colidx.begin(), P.colidx.end(), colidx);
+    if (ghost_global) std::copy(P.ghost_global.begin(), P.ghost_global.end(), ghost_global);
+    if (ghost_owner) std::copy(P.ghost_owner.begin(), P.ghost_owner.end(), ghost_owner);
+    if (send_local_rows) for (size_t i = 0; i < P.send_rows.size(); ++i) send_local_rows[i] = P.send_rows[i];
+    if (send_dest) std::copy(P.send_dest.begin(), P.send_dest.end(), send_dest);
+    return MBFEA_OK;
+}
+
+// ---- scenario files ------------------------------------------------------------
+int mbfea_load_scenario(mbfea_ctx *c, const char *config_json_path, const char *ply_path_override)
+{
+    if (!c || !config_json_path) return MBFEA_EARG;
+    Scenario sc;
+    std::string msg;
+    if (int rc = load_scenario_files(config_json_path, ply_path_override, sc, msg)) return fail(c, rc, msg);
+    return mbfea_set_job(c, sc.V, sc.E, sc.nodes_cm.data(), sc.elems_cm.data(), sc.normals_cm.data(),
+                         sc.dims_bh.data(), sc.mat_nuE.data(), (int64_t)sc.fixed.size(), sc.fixed.data(),
+                         (int64_t)sc.f_node.size(), sc.f_node.data(), sc.f_dof.data(), sc.f_mag.data());
+}
+
+struct mbfea_scenario { Scenario sc; };
+
+int mbfea_scenario_open(const char *config_json_path, const char *ply_path_override, mbfea_scenario **out,
+                        char *errbuf, int64_t errbuf_len)
+{
+    if (!config_json_path || !out) return MBFEA_EARG;
+    *out = nullptr;
+    std::unique_ptr<mbfea_scenario> h(new (std::nothrow) mbfea_scenario);
+    if (!h) return MBFEA_EARG;
+    std::string msg;
+    const int rc = load_scenario_files(config_json_path, ply_path_override, h->sc, msg);
+    if (errbuf && errbuf_len > 0) std::snprintf(errbuf, (size_t)errbuf_len, "%s", msg.c_str());
+    if (rc != MBFEA_OK) return rc;
+    *out = h.release();
+    return MBFEA_OK;
+}
+
+void mbfea_scenario_sizes(const mbfea_scenario *h, int64_t *V, int64_t *E, int64_t *F, int64_t *nF)
+{
+    if (!h) return;
+    if (V) *V = h->sc.V;
+    if (E) *E = h->sc.E;
+    if (F) *F = (int64_t)h->sc.fixed.size();
+    if (nF) *nF = (int64_t)h->sc.f_node.size();
+}
+
+void mbfea_scenario_copy(const mbfea_scenario *h, double *nodes_cm, int32_t *elems_cm, double *normals_cm,
+                         float *dims_bh, float *mat_nuE, int32_t *fixed, int64_t *f_node, int64_t *f_dof,
+                         double *f_mag)
+{
+    if (!h) return;
+    const Scenario &s = h->sc;
+    if (nodes_cm) std::copy(s.nodes_cm.begin(), s.nodes_cm.end(), nodes_cm);
+    if (elems_cm) std::copy(s.elems_cm.begin(), s.elems_cm.end(), elems_cm);
+    if (normals_cm) std::copy(s.normals_cm.begin(), s.normals_cm.end(), normals_cm);
+    if (dims_bh) std::copy(s.dims_bh.begin(), s.dims_bh.end(), dims_bh);
+    if (mat_nuE) std::copy(s.mat_nuE.begin(), s.mat_nuE.end(), mat_nuE);
+    if (fixed) std::copy(s.fixed.begin(), s.fixed.end(), fixed);
+    if (f_node) std::copy(s.f_node.begin(), s.f_node.end(), f_node);
+    if (f_dof) std::copy(s.f_dof.begin(), s.f_dof.end(), f_dof);
+    if (f_mag) std::copy(s.f_mag.begin(), s.f_mag.end(), f_mag);
+}
+
+void mbfea_scenario_close(mbfea_scenario *h) { delete h; }
+
+// ---- host-only pieces ----------------------------------------------------------
+int mbfea_host_validate(int64_t V, int64_t E, const int32_t *elems_cm, const float *dims_bh, const float *mat_nuE,
+                        int64_t F, const int32_t *fixed, int64_t nF, const int64_t *f_node, const int64_t *f_dof,
+                        char *msg, int64_t msg_len)
+{
+    std::string m;
+    const int rc = validate_job(V, E, elems_cm, dims_bh, mat_nuE, F, fixed, nF, f_node, f_dof, m);
+    if (msg && msg_len > 0) std::snprintf(msg, (size_t)msg_len, "%s", m.c_str());
+    return rc;
+}
+
+int mbfea_host_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4)
+{
+    if (E < 0 || (E > 0 && (!dims_bh || !mat_nuE || !props4))) return MBFEA_EARG;
+    derive_props(E, dims_bh, mat_nuE, props4);
+    return MBFEA_OK;
+}
+
+int mbfea_host_free_map(int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index, int64_t *n_free)
+{
+    if (V <= 0 || !free_index || (F > 0 && !fixed)) return MBFEA_EARG;
+    for (int64_t i = 0; i < F; ++i)
+        if (fixed[i] < 0 || fixed[i] > V - 1) return MBFEA_ERANGE_FIXED;
+    std::vector<int32_t> fm;
+    const int64_t n = build_free_map(V, F, fixed, fm);
+    std::copy(fm.begin(), fm.end(), free_index);
+    if (n_free) *n_free = n;
+    return MBFEA_OK;
+}
+
+}  // extern "C"

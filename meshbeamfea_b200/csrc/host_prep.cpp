@@ -1,0 +1,328 @@
+// Host-side preparation: validation in the reference's order, the float
+// section-property quirk, the constraint map, the 6x6-block CSR pattern with
+// per-block contributor lists (ascending element order => deterministic,
+// scatter-free assembly on the device) and the vertex-block partition plan.
+// Pure C++17: nothing here touches CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "mbfea_internal.hpp"
+
+namespace mbfea {
+
+// ---------------------------------------------------------------------------
+// Validation.  Order follows FeaSimulationJob(job): setElements() first, then
+// setNodes() -> setFixedNodes() -> setNodalForces()
+// [REF src/beamsimulator.cpp:107-111].
+// ---------------------------------------------------------------------------
+int validate_forces(int64_t V, int64_t nF, const int64_t *f_node, const int64_t *f_dof,
+                    std::string &msg)
+{
+    for (int64_t i = 0; i < nF; ++i) {
+        // `force.index > nodes.size() - 1` compares a ptrdiff_t with a size_t, so a
+        // negative index wraps and throws as well [REF src/beamsimulator.cpp:164-166]
+        if (f_node[i] < 0 || f_node[i] > V - 1) {
+            msg = "Node index is out of valid range.";
+            return MBFEA_ERANGE_FORCE;
+        }
+    }
+    for (int64_t i = 0; i < nF; ++i) {
+        // the scenario loader Expects(dof in [0,6)) [REF src/utilities.hpp:77]
+        if (f_dof[i] < 0 || f_dof[i] > 5) {
+            msg = "precondition violated: force dof must be in [0,6)";
+            return MBFEA_EPRECOND;
+        }
+    }
+    return MBFEA_OK;
+}
+
+int validate_job(int64_t V, int64_t E, const int32_t *elems_cm, const float *dims_bh,
+                 const float *mat_nuE, int64_t F, const int32_t *fixed, int64_t nF,
+                 const int64_t *f_node, const int64_t *f_dof, std::string &msg)
+{
+    // Expects(!simulationJob.isEmpty()) [REF src/beamsimulator.cpp:41,113-115]
+    if (V <= 0 || E <= 0) {
+        msg = "precondition violated: empty simulation job (no nodes or no elements)";
+        return MBFEA_EPRECOND;
+    }
+    if (V > (int64_t)INT32_MAX / 8 || E > (int64_t)(1u << 29) - 1) {
+        msg = "job too large for 32-bit block indices";
+        return MBFEA_EARG;
+    }
+    for (int64_t e = 0; e < E; ++e) {
+        const int32_t a = elems_cm[e], b = elems_cm[E + e];
+        // the reference's range check [REF :81-83] compares against 3V and lets
+        // negatives through; anything it would let through out of [0,V) is UB
+        // there, so this build rejects it as the same class of error.
+        if (a < 0 || b < 0 || a >= V || b >= V) {
+            msg = "precondition violated: element node index out of range";
+            return MBFEA_EPRECOND;
+        }
+        if (a == b) {
+            msg = "precondition violated: zero-length beam (both ends on one vertex)";
+            return MBFEA_EPRECOND;
+        }
+        // BeamDimensions / BeamMaterial constructors [REF src/beam.hpp:14,25]
+        const float bb = dims_bh[2 * e], hh = dims_bh[2 * e + 1];
+        const float nu = mat_nuE[2 * e];
+        if (!(bb > 0 && hh > 0)) {
+            msg = "precondition violated: beam dimensions must be positive";
+            return MBFEA_EPRECOND;
+        }
+        if (!(nu <= 0.5f && nu >= -1.0f)) {
+            msg = "precondition violated: Poisson's ratio outside [-1, 0.5]";
+            return MBFEA_EPRECOND;
+        }
+    }
+    for (int64_t i = 0; i < F; ++i) {
+        if (fixed[i] < 0 || (int64_t)fixed[i] > V - 1) {
+            msg = "Vertex index is outside of valid range.";  // [REF :134-137]
+            return MBFEA_ERANGE_FIXED;
+        }
+    }
+    return validate_forces(V, nF, f_node, f_dof, msg);
+}
+
+// ---------------------------------------------------------------------------
+// Section properties.  Every member of BeamSimulationProperties is `float`
+// [REF src/beamsimulator.hpp:13-27]; the expressions below keep the reference's
+// promotions: std::pow(float,int) -> double, float*double -> double, result
+// narrowed to float on assignment [REF src/beamsimulator.cpp:173-188].
+// ---------------------------------------------------------------------------
+static inline void props_one(float b, float h, float nu, float Egpa, double *out)
+{
+    const float crossArea = b * h;
+    const float I2 = static_cast<float>(b * std::pow(static_cast<double>(h), 3) / 12);
+    const float I3 = static_cast<float>(h * std::pow(static_cast<double>(b), 3) / 12);
+    const float polarInertia = I2 + I3;
+    const float youngsModulusPascal = static_cast<float>(Egpa * std::pow(10.0, 9));
+    const float G = youngsModulusPascal / (2 * (1 + nu));
+    const float EA = youngsModulusPascal * crossArea;
+    const float EIy = youngsModulusPascal * I3;
+    const float EIz = youngsModulusPascal * I2;
+    const float GJ = G * polarInertia;
+    out[0] = EA;   // fea::Props(EA, EIz, EIy, GJ, normal) [REF :89-90]
+    out[1] = EIz;
+    out[2] = EIy;
+    out[3] = GJ;
+}
+
+template <class Fn>
+static void parallel_ranges(int64_t n, int64_t min_per_thread, Fn fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int64_t nt = std::max<int64_t>(1, std::min<int64_t>(hw ? hw : 1, n / std::max<int64_t>(1, min_per_thread)));
+    nt = std::min<int64_t>(nt, 32);
+    if (nt <= 1) { fn(0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int64_t t = 0; t < nt; ++t)
+        th.emplace_back([=] { fn(n * t / nt, n * (t + 1) / nt, (int)t); });
+    for (auto &x : th) x.join();
+}
+
+void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4)
+{
+    parallel_ranges(E, 1 << 16, [=](int64_t lo, int64_t hi, int) {
+        // most meshes repeat one section: memoise the last one
+        float lb = NAN, lh = NAN, ln = NAN, le = NAN;
+        double last[4] = {0, 0, 0, 0};
+        for (int64_t e = lo; e < hi; ++e) {
+            const float b = dims_bh[2 * e], h = dims_bh[2 * e + 1], nu = mat_nuE[2 * e], Eg = mat_nuE[2 * e + 1];
+            if (!(b == lb && h == lh && nu == ln && Eg == le)) {
+                props_one(b, h, nu, Eg, last);
+                lb = b; lh = h; ln = nu; le = Eg;
+            }
+            std::memcpy(props4 + 4 * e, last, sizeof last);
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------
+// K3 (host copy): all six DOFs of a fixed vertex are removed
+// [REF src/beamsimulator.cpp:139-150], so elimination is a vertex renumbering.
+// ---------------------------------------------------------------------------
+int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<int32_t> &fm)
+{
+    fm.assign((size_t)V, 0);
+    for (int64_t i = 0; i < F; ++i) fm[fixed[i]] = -1;
+    int32_t k = 0;
+    for (int64_t v = 0; v < V; ++v)
+        if (fm[v] == 0) fm[v] = k++;
+    return k;
+}
+
+static inline int32_t owner_of(int64_t g, int64_t nb_global, int32_t world)
+{
+    // inverse of row_begin(r) = nb_global*r/world
+    int32_t r = (int32_t)(((g + 1) * world - 1) / std::max<int64_t>(nb_global, 1));
+    if (r >= world) r = world - 1;
+    while (r > 0 && nb_global * r / world > g) --r;
+    while (r + 1 < world && nb_global * (r + 1) / world <= g) ++r;
+    return r;
+}
+
+void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
+                int32_t rank, int32_t world, bool with_contrib, HostPlan &P)
+{
+    P.V = V; P.E = E; P.rank = rank; P.world = world;
+    P.nb_global = build_free_map(V, F, fixed, P.free_index);
+    const int64_t nbg = P.nb_global;
+    P.row_begin = nbg * rank / world;
+    P.row_end = nbg * (rank + 1) / world;
+    const int64_t r0 = P.row_begin, nb = P.row_end - P.row_begin;
+    const int32_t *fm = P.free_index.data();
+
+    // pass 1: entries per owned row (diagonal contributions + off-diagonal ones)
+    std::vector<int32_t> cnt((size_t)nb + 1, 0);
+    for (int64_t e = 0; e < E; ++e) {
+        const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
+        if (fa >= 0 && fa >= r0 && fa < r0 + nb) cnt[fa - r0] += (fb >= 0) ? 2 : 1;
+        if (fb >= 0 && fb >= r0 && fb < r0 + nb) cnt[fb - r0] += (fa >= 0) ? 2 : 1;
+    }
+    std::vector<int64_t> start((size_t)nb + 1, 0);
+    for (int64_t r = 0; r < nb; ++r) start[r + 1] = start[r] + cnt[r];
+    const int64_t nent = start[nb];
+    struct Ent { int32_t col; int32_t code; };  // global column, (e<<2)|which
+    std::vector<Ent> ent((size_t)nent);
+    {
+        std::vector<int64_t> pos(start.begin(), start.end() - 1);
+        for (int64_t e = 0; e < E; ++e) {  // ascending element order
+            const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
+            const int32_t code = (int32_t)(e << 2);
+            if (fa >= 0 && fa >= r0 && fa < r0 + nb) {
+                ent[pos[fa - r0]++] = {(int32_t)fa, code | SUB_00};
+                if (fb >= 0) ent[pos[fa - r0]++] = {(int32_t)fb, code | SUB_01};
+            }
+            if (fb >= 0 && fb >= r0 && fb < r0 + nb) {
+                if (fa >= 0) ent[pos[fb - r0]++] = {(int32_t)fa, code | SUB_10};
+                ent[pos[fb - r0]++] = {(int32_t)fb, code | SUB_11};
+            }
+        }
+    }
+    // a free vertex with no beam still owns a (zero) diagonal block so that the
+    // row exists; the solver reports it as singular.
+    // per row: stable sort by column (keeps ascending element order), count blocks
+    P.rowptr.assign((size_t)nb + 1, 0);
+    std::vector<int32_t> nblk((size_t)nb, 0);
+    parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t r = lo; r < hi; ++r) {
+            Ent *b = ent.data() + start[r], *e2 = ent.data() + start[r + 1];
+            if (e2 - b <= 24) {
+                for (Ent *i = b + 1; i < e2; ++i) {
+                    Ent x = *i; Ent *j = i - 1;
+                    while (j >= b && j->col > x.col) { j[1] = *j; --j; }
+                    j[1] = x;
+                }
+            } else {
+                std::stable_sort(b, e2, [](const Ent &x, const Ent &y) { return x.col < y.col; });
+            }
+            int32_t n = 0; bool has_diag = false;
+            for (Ent *i = b; i < e2; ++i) {
+                if (i == b || i->col != i[-1].col) ++n;
+                if (i->col == r0 + r) has_diag = true;
+            }
+            nblk[r] = n + (has_diag ? 0 : 1);
+        }
+    });
+    for (int64_t r = 0; r < nb; ++r) P.rowptr[r + 1] = P.rowptr[r] + nblk[r];
+    const int64_t nnzb = P.rowptr[nb];
+    P.colidx.assign((size_t)nnzb, 0);
+    P.diag_idx.assign((size_t)nb, 0);
+    std::vector<int32_t> gcol((size_t)nnzb);  // global column ids first
+    if (with_contrib) { P.contrib_ptr.assign((size_t)nnzb + 1, 0); P.contrib.assign((size_t)nent, 0); }
+    else { P.contrib_ptr.clear(); P.contrib.clear(); }
+    parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t r = lo; r < hi; ++r) {
+            const Ent *b = ent.data() + start[r], *e2 = ent.data() + start[r + 1];
+            int64_t k = P.rowptr[r] - 1;
+            const int32_t me = (int32_t)(r0 + r);
+            bool diag_done = false;
+            // number of contributions before this row == start[r] (every entry is one)
+            int64_t c = start[r];
+            for (const Ent *i = b; i < e2; ++i) {
+                if (i == b || i->col != i[-1].col) {
+                    if (!diag_done && i->col > me) {  // isolated vertex: empty diagonal block
+                        ++k; gcol[k] = me; P.diag_idx[r] = (int32_t)k; diag_done = true;
+                        if (with_contrib) P.contrib_ptr[k] = (int32_t)c;
+                    }
+                    ++k; gcol[k] = i->col;
+                    if (i->col == me) { P.diag_idx[r] = (int32_t)k; diag_done = true; }
+                    if (with_contrib) P.contrib_ptr[k] = (int32_t)c;
+                }
+                if (with_contrib) P.contrib[c] = i->code;
+                ++c;
+            }
+            if (!diag_done) {
+                ++k; gcol[k] = me; P.diag_idx[r] = (int32_t)k;
+                if (with_contrib) P.contrib_ptr[k] = (int32_t)c;
+            }
+        }
+    });
+    if (with_contrib) P.contrib_ptr[nnzb] = (int32_t)nent;
+
+    // ghosts: global columns outside the owned range, ascending
+    P.ghost_global.clear();
+    for (int64_t k = 0; k < nnzb; ++k)
+        if (gcol[k] < r0 || gcol[k] >= r0 + nb) P.ghost_global.push_back(gcol[k]);
+    std::sort(P.ghost_global.begin(), P.ghost_global.end());
+    P.ghost_global.erase(std::unique(P.ghost_global.begin(), P.ghost_global.end()), P.ghost_global.end());
+    const int64_t ng = (int64_t)P.ghost_global.size();
+    P.ghost_owner.resize((size_t)ng);
+    for (int64_t i = 0; i < ng; ++i) P.ghost_owner[i] = owner_of(P.ghost_global[i], nbg, world);
+    for (int64_t k = 0; k < nnzb; ++k) {
+        const int64_t g = gcol[k];
+        if (g >= r0 && g < r0 + nb) P.colidx[k] = (int32_t)(g - r0);
+        else {
+            const auto it = std::lower_bound(P.ghost_global.begin(), P.ghost_global.end(), g);
+            P.colidx[k] = (int32_t)(nb + (it - P.ghost_global.begin()));
+        }
+    }
+    // sends: the pattern is symmetric, so rank q needs owned row i from us iff
+    // row i has a column owned by q.  Sorted by (dest, row) == the order in which
+    // q lists them among its ghosts (ascending global id).
+    std::vector<std::pair<int32_t, int32_t>> snd;  // (dest, local row)
+    for (int64_t r = 0; r < nb; ++r) {
+        int32_t last = -1;
+        for (int64_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
+            if (P.colidx[k] < nb) continue;
+            const int32_t q = P.ghost_owner[P.colidx[k] - nb];
+            if (q != last) { snd.emplace_back(q, (int32_t)r); last = q; }
+        }
+    }
+    std::sort(snd.begin(), snd.end());
+    snd.erase(std::unique(snd.begin(), snd.end()), snd.end());
+    P.send_rows.resize(snd.size()); P.send_dest.resize(snd.size());
+    for (size_t i = 0; i < snd.size(); ++i) { P.send_dest[i] = snd[i].first; P.send_rows[i] = snd[i].second; }
+    // neighbour table
+    P.neighbors.clear();
+    for (int32_t q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        Neighbor nbq{q, 0, 0, 0, 0};
+        const auto gl = std::lower_bound(P.ghost_owner.begin(), P.ghost_owner.end(), q);
+        const auto gh = std::upper_bound(P.ghost_owner.begin(), P.ghost_owner.end(), q);
+        nbq.recv_offset = gl - P.ghost_owner.begin(); nbq.recv_count = gh - gl;
+        const auto sl = std::lower_bound(P.send_dest.begin(), P.send_dest.end(), q);
+        const auto sh = std::upper_bound(P.send_dest.begin(), P.send_dest.end(), q);
+        nbq.send_offset = sl - P.send_dest.begin(); nbq.send_count = sh - sl;
+        if (nbq.recv_count || nbq.send_count) P.neighbors.push_back(nbq);
+    }
+}
+
+void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
+                 std::vector<int32_t> &tile_row)
+{
+    const int64_t nb = (int64_t)rowptr.size() - 1;
+    tile_row.clear();
+    tile_row.push_back(0);
+    int64_t r = 0;
+    while (r < nb) {
+        int64_t r1 = r + 1;  // a tile always holds at least one row (long rows are chunked)
+        while (r1 < nb && r1 - r < max_rows && rowptr[r1 + 1] - rowptr[r] <= cap_blocks) ++r1;
+        tile_row.push_back((int32_t)r1);
+        r = r1;
+    }
+}
+
+}  // namespace mbfea

@@ -1,0 +1,909 @@
+// Hand-written sm_100a kernels of libmbfea.so.
+//
+//   pack_*          input repacking (column-major Eigen images -> 32/64-byte records)
+//   K3 free_map     constraint elimination as a vertex renumbering (flag + scan)
+//   K1 kelem        12x12 element stiffness in global axes (parity tap)
+//   K1+K2 assemble  deterministic scatter-free assembly into 6x6-block BSR
+//   K5 block_jacobi inverse of every diagonal block
+//   K4 spmv_*       y = K x with the p.Ap partial dot in the epilogue
+//                   (row-thread LDG kernel and TMA bulk-copy staged kernel)
+//   K6 pcg_*        fused PCG vector kernels, device-resident scalars
+//   K7 element_forces  beam end forces in the SimulationResults layout
+//
+// Everything is FP64; tensor cores are not used (0.25 flop/byte sparse work).
+// Reductions are two-level and fixed-order: per-CTA partials written to a
+// buffer, then summed in a fixed order by every consumer CTA, so a solve is
+// bit-reproducible run to run for a given grid.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace mbfea { namespace dev {
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the CTA in a fixed order; result valid in thread 0 (and broadcast
+// to all threads when BCAST).  scratch: >= 33 doubles of shared memory.
+template <bool BCAST>
+__device__ __forceinline__ double block_sum(double v, double *scratch)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (lane < nw) ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (BCAST && lane == 0) scratch[32] = t;
+    }
+    if (BCAST) {
+        __syncthreads();
+        t = scratch[32];
+    }
+    return t;
+}
+
+// Every CTA sums the same partials in the same order -> identical value.
+__device__ __forceinline__ double sum_partials(PartialRef ref, double *scratch)
+{
+    double s = 0.0;
+    for (int i = threadIdx.x; i < ref.n; i += blockDim.x) s += ref.buf[(size_t)i * ref.stride];
+    return block_sum<true>(s, scratch);
+}
+
+__device__ __forceinline__ double2 ldg2(const double *p)
+{
+    return __ldg(reinterpret_cast<const double2 *>(p));
+}
+
+// streaming 16-byte load: matrix values are touched once per SpMV
+__device__ __forceinline__ double2 ld_stream2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------
+__global__ void k_pack_nodes(int64_t V, const double *__restrict__ nodes_cm, Node4 *__restrict__ node4)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    Node4 n{nodes_cm[v], nodes_cm[V + v], nodes_cm[2 * V + v], 0.0};
+    double2 *o = reinterpret_cast<double2 *>(node4 + v);
+    o[0] = make_double2(n.x, n.y);
+    o[1] = make_double2(n.z, 0.0);
+}
+
+__global__ void k_pack_elems(int64_t E, const int32_t *__restrict__ elems_cm,
+                             const double *__restrict__ normals_cm, const double *__restrict__ props4,
+                             ElemRec *__restrict__ rec)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const double2 p01 = ldg2(props4 + 4 * e), p23 = ldg2(props4 + 4 * e + 2);
+    const uint32_t a = (uint32_t)elems_cm[e], b = (uint32_t)elems_cm[E + e];
+    const long long ab = (long long)(((unsigned long long)b << 32) | a);
+    double2 *o = reinterpret_cast<double2 *>(rec + e);
+    o[0] = make_double2(normals_cm[e], normals_cm[E + e]);
+    o[1] = make_double2(normals_cm[2 * E + e], p01.x);
+    o[2] = make_double2(p01.y, p23.x);
+    o[3] = make_double2(p23.y, __longlong_as_double(ab));
+}
+
+void launch_pack_nodes(cudaStream_t st, int64_t V, const double *nodes_cm, Node4 *node4)
+{
+    if (V <= 0) return;
+    k_pack_nodes<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, nodes_cm, node4);
+}
+
+void launch_pack_elems(cudaStream_t st, int64_t E, const int32_t *elems_cm, const double *normals_cm,
+                       const double *props4, ElemRec *rec)
+{
+    if (E <= 0) return;
+    k_pack_elems<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(E, elems_cm, normals_cm, props4, rec);
+}
+
+// ---------------------------------------------------------------------------
+// K3: constraint map.  All six DOFs of a fixed vertex go
+// [REF src/beamsimulator.cpp:139-150], so elimination is the vertex map
+// free_index[v] = -1 (fixed) | rank of v among free vertices; the reduced DOF
+// of (v,d) is 6*free_index[v]+d.  Integer only => bit-exact vs the oracle.
+// ---------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void k_fill_i32(int64_t n, int32_t *a, int32_t v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+__global__ void k_mark_fixed(int64_t F, const int32_t *__restrict__ fixed, int32_t *flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) flag[fixed[i]] = 0;  // duplicates write the same value
+}
+
+// per-tile exclusive scan of the flags (in place) + tile totals
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(int64_t V, int32_t *flag_scan, int32_t *tile_sum,
+                                                             int32_t *flag_keep)
+{
+    __shared__ int32_t wsum[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        v[j] = (base + j < V) ? flag_scan[base + j] : 0;
+        s += v[j];
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int32_t woff = 0;
+    for (int j = 0; j < w; ++j) woff += wsum[j];
+    int32_t run = woff + inc - s;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if (base + j < V) {
+            flag_keep[base + j] = v[j];
+            flag_scan[base + j] = run;
+        }
+        run += v[j];
+    }
+    if (threadIdx.x == kScanThreads - 1) tile_sum[blockIdx.x] = woff + inc;
+}
+
+// exclusive scan of the tile totals, one CTA, fixed order
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(int64_t ntiles, int32_t *tile_sum)
+{
+    __shared__ int32_t wsum[kScanThreads / 32];
+    __shared__ int32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < ntiles; base += kScanThreads) {
+        const int64_t i = base + threadIdx.x;
+        const int32_t v = (i < ntiles) ? tile_sum[i] : 0;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        int32_t woff = 0;
+        for (int j = 0; j < w; ++j) woff += wsum[j];
+        const int32_t carry = carry_s;
+        if (i < ntiles) tile_sum[i] = carry + woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == kScanThreads - 1) carry_s = carry + woff + inc;
+        __syncthreads();
+    }
+}
+
+__global__ void k_scan_finish(int64_t V, int32_t *free_index, const int32_t *__restrict__ tile_sum,
+                              const int32_t *__restrict__ flag_keep)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    free_index[v] = flag_keep[v] ? free_index[v] + tile_sum[v / kScanTile] : -1;
+}
+
+void launch_free_map(cudaStream_t st, int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
+                     int32_t *scratch)
+{
+    if (V <= 0) return;
+    const int64_t ntiles = (V + kScanTile - 1) / kScanTile;
+    int32_t *flag_keep = scratch;          // V ints
+    int32_t *tile_sum = scratch + V;       // ntiles ints
+    k_fill_i32<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, free_index, 1);
+    if (F > 0) k_mark_fixed<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(F, fixed, free_index);
+    k_scan_tiles<<<(unsigned)ntiles, kScanThreads, 0, st>>>(V, free_index, tile_sum, flag_keep);
+    k_scan_tile_sums<<<1, kScanThreads, 0, st>>>(ntiles, tile_sum);
+    k_scan_finish<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, free_index, tile_sum, flag_keep);
+}
+
+// ---------------------------------------------------------------------------
+// K1: element stiffness in global axes, one thread per (beam, row of 12).
+// Debug/parity tap: the production path never stores K_e (see k_assemble).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) k_kelem(int64_t E, const ElemRec *__restrict__ rec,
+                                               const Node4 *__restrict__ node4, double *__restrict__ Ke)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / 12;
+    const int r = (int)(t - e * 12);
+    if (e >= E) return;
+    Frame f; Stiff s; int32_t a, b;
+    load_elem(rec, node4, e, f, s, a, b);
+    const int half = r / 6, rr = r - 6 * half;
+    double lo[6], hi[6];
+    kelem_row(f, s, half * 2 + 0, rr, lo);
+    kelem_row(f, s, half * 2 + 1, rr, hi);
+    double2 *o = reinterpret_cast<double2 *>(Ke + e * 144 + r * 12);
+    o[0] = make_double2(lo[0], lo[1]); o[1] = make_double2(lo[2], lo[3]); o[2] = make_double2(lo[4], lo[5]);
+    o[3] = make_double2(hi[0], hi[1]); o[4] = make_double2(hi[2], hi[3]); o[5] = make_double2(hi[4], hi[5]);
+}
+
+void launch_kelem(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4, double *Ke)
+{
+    if (E <= 0) return;
+    const int64_t n = E * 12;
+    k_kelem<<<(unsigned)((n + 191) / 192), 192, 0, st>>>(E, rec, node4, Ke);
+}
+
+// ---------------------------------------------------------------------------
+// K1+K2 fused: one 6-lane slice per OUTPUT block, lane = row of the 6x6 block.
+// The slice walks the block's contributor list (element, sub-block), which the
+// host sorted by ascending element index -- the order in which the reference's
+// setFromTriplets sums duplicates -- recomputes the element's frame and
+// coefficients in registers and accumulates its row.  No atomics, no scatter:
+// every block is written exactly once, by one slice, in a fixed order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) k_assemble(int64_t nnzb, const int32_t *__restrict__ contrib_ptr,
+                                                  const int32_t *__restrict__ contrib,
+                                                  const ElemRec *__restrict__ rec,
+                                                  const Node4 *__restrict__ node4, double *__restrict__ vals)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = t / 6;
+    const int r = (int)(t - k * 6);
+    if (k >= nnzb) return;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const int32_t c0 = __ldg(contrib_ptr + k), c1 = __ldg(contrib_ptr + k + 1);
+    for (int32_t c = c0; c < c1; ++c) {
+        const int32_t code = __ldg(contrib + c);
+        Frame f; Stiff s; int32_t a, b;
+        load_elem(rec, node4, (int64_t)(code >> 2), f, s, a, b);
+        double row[6];
+        kelem_row(f, s, code & 3, r, row);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[j] = ADD(acc[j], row[j]);
+    }
+    double2 *o = reinterpret_cast<double2 *>(vals + k * 36 + r * 6);
+    o[0] = make_double2(acc[0], acc[1]);
+    o[1] = make_double2(acc[2], acc[3]);
+    o[2] = make_double2(acc[4], acc[5]);
+}
+
+void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, const int32_t *contrib,
+                     const ElemRec *rec, const Node4 *node4, double *vals)
+{
+    if (nnzb <= 0) return;
+    const int64_t n = nnzb * 6;
+    k_assemble<<<(unsigned)((n + 191) / 192), 192, 0, st>>>(nnzb, contrib_ptr, contrib, rec, node4, vals);
+}
+
+// ---------------------------------------------------------------------------
+// K5: 6x6 block-Jacobi.  One thread per block row: Gauss-Jordan on the SPD
+// diagonal block (no pivoting needed); a non-positive pivot raises *flag.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_block_jacobi(int64_t nb, const int32_t *__restrict__ diag_idx,
+                                                      const double *__restrict__ vals,
+                                                      double *__restrict__ minv, int *flag)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nb) return;
+    const double *D = vals + (int64_t)__ldg(diag_idx + r) * 36;
+    double M[6][6], I[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            const double2 v = ldg2(D + 6 * i + j);
+            M[i][j] = v.x; M[i][j + 1] = v.y;
+            I[i][j] = (i == j) ? 1.0 : 0.0; I[i][j + 1] = (i == j + 1) ? 1.0 : 0.0;
+        }
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double piv = M[k][k];
+        if (!(piv > 0.0)) bad = true;
+        const double p = 1.0 / piv;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { M[k][j] *= p; I[k][j] *= p; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i == k) continue;
+            const double f = M[i][k];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { M[i][j] -= f * M[k][j]; I[i][j] -= f * I[k][j]; }
+        }
+    }
+    if (bad) atomicOr(flag, 1);
+    double2 *o = reinterpret_cast<double2 *>(minv + r * 36);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) o[3 * i + j / 2] = make_double2(I[i][j], I[i][j + 1]);
+}
+
+void launch_block_jacobi(cudaStream_t st, int64_t nb, const int32_t *diag_idx, const double *vals,
+                         double *minv, int *flag)
+{
+    if (nb <= 0) return;
+    k_block_jacobi<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, diag_idx, vals, minv, flag);
+}
+
+// ---------------------------------------------------------------------------
+// K4 (a): row-thread SpMV.  192 threads = 32 block rows x 6 scalar rows; a
+// thread owns one scalar row and streams its 48-byte slice of every block in
+// the row (3 x LDG.128), gathering the 48-byte x-block through the read-only
+// path.  Consecutive threads read consecutive 48-byte slices, so a warp's
+// three loads together cover a contiguous span of the value stream.
+// Epilogue: partial[blockIdx] = sum over the CTA's rows of x_r . y_r.
+// ---------------------------------------------------------------------------
+constexpr int kRowsPerCta = 32;
+constexpr int kSpmvThreads = kRowsPerCta * 6;
+
+__global__ void __launch_bounds__(kSpmvThreads) k_spmv_rowthread(
+    int64_t nb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+    const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+    double *__restrict__ partial, const PcgScalars *sc)
+{
+    __shared__ double red[33];
+    if (sc != nullptr && sc->done != 0) return;
+    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+    double dot = 0.0;
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+        const int64_t row = r0 + lr;
+        if (row < nb) {
+            const int32_t kb = __ldg(rowptr + row), ke = __ldg(rowptr + row + 1);
+            double acc = 0.0;
+            for (int32_t k = kb; k < ke; ++k) {
+                const int32_t c = __ldg(colidx + k);
+                const double *v = vals + (int64_t)k * 36 + i * 6;
+                const double *xx = x + (int64_t)c * 6;
+                const double2 v0 = ldg2(v), v1 = ldg2(v + 2), v2 = ldg2(v + 4);
+                const double2 x0 = ldg2(xx), x1 = ldg2(xx + 2), x2 = ldg2(xx + 4);
+                acc = fma(v0.x, x0.x, acc); acc = fma(v0.y, x0.y, acc);
+                acc = fma(v1.x, x1.x, acc); acc = fma(v1.y, x1.y, acc);
+                acc = fma(v2.x, x2.x, acc); acc = fma(v2.y, x2.y, acc);
+            }
+            y[row * 6 + i] = acc;
+            dot = fma(__ldg(x + row * 6 + i), acc, dot);
+        }
+    }
+    if (partial != nullptr) {
+        const double s = block_sum<false>(dot, red);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
+int spmv_rowthread_grid(int64_t nb)
+{
+    const int64_t tiles = (nb + kRowsPerCta - 1) / kRowsPerCta;
+    return (int)(tiles < 1 ? 1 : (tiles > kMaxPartials ? kMaxPartials : tiles));
+}
+
+void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx,
+                           const double *vals, const double *x, double *y, double *partial,
+                           const PcgScalars *sc)
+{
+    k_spmv_rowthread<<<spmv_rowthread_grid(nb), kSpmvThreads, 0, st>>>(nb, rowptr, colidx, vals, x, y, partial, sc);
+}
+
+// ---------------------------------------------------------------------------
+// K4 (b): TMA-staged SpMV.  The values of a tile of consecutive block rows are
+// ONE contiguous span of the value stream, so a single elected producer thread
+// moves each tile with one cp.async.bulk (1-D TMA, SASS UBLKCP) into a ring of
+// kTmaStages shared-memory stages, completion signalled on an mbarrier.  Six
+// consumer warps (one thread per scalar row) read their 48-byte slices from
+// shared memory, gather x through the read-only path, and hand the stage back
+// through a second mbarrier.  Persistent CTAs, static tile -> CTA assignment
+// (tile t to CTA t mod grid), so the partial dot products are reproducible.
+// ---------------------------------------------------------------------------
+constexpr int kTmaConsumers = kTmaMaxRows * 6;       // 192
+constexpr int kTmaThreads = kTmaConsumers + 32;      // + producer warp
+constexpr int kTmaStageBytes = kTmaCapBlocks * 288;  // 64512
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1) k_spmv_tma(
+    int64_t ntiles, const int32_t *__restrict__ tile_row, const int32_t *__restrict__ rowptr,
+    const int32_t *__restrict__ colidx, const double *__restrict__ vals, const double *__restrict__ x,
+    double *__restrict__ y, double *__restrict__ partial, const PcgScalars *sc)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kTmaStages], empty_bar[kTmaStages];
+    __shared__ double red[33];
+    if (sc != nullptr && sc->done != 0) return;
+    double *stage_buf = reinterpret_cast<double *>(smem_raw);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTmaStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kTmaConsumers / 32);  // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5;
+    double dot = 0.0;
+    if (warp == kTmaConsumers / 32) {
+        // ---- producer warp: one elected lane issues the bulk copies ----
+        if ((threadIdx.x & 31) == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int32_t r0 = __ldg(tile_row + t), r1 = __ldg(tile_row + t + 1);
+                const int32_t kb = __ldg(rowptr + r0), ke = __ldg(rowptr + r1);
+                const uint32_t bytes = (uint32_t)(ke - kb) * 288u;
+                if (bytes > 0) {
+                    mbar_expect_tx(&full_bar[stage], bytes);
+                    tma_bulk_g2s(stage_buf + (size_t)stage * (kTmaStageBytes / 8), vals + (int64_t)kb * 36, bytes,
+                                 &full_bar[stage]);
+                } else {
+                    mbar_arrive(&full_bar[stage]);
+                }
+                if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ---- consumers: thread = (local block row, scalar row) ----
+        const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int32_t r0 = __ldg(tile_row + t), r1 = __ldg(tile_row + t + 1);
+            const int32_t row = r0 + lr;
+            const bool live = row < r1;
+            int32_t kb = 0, ke = 0, k0 = 0;
+            if (live) { kb = __ldg(rowptr + row); ke = __ldg(rowptr + row + 1); }
+            k0 = __ldg(rowptr + r0);
+            mbar_wait(&full_bar[stage], phase);
+            if (live) {
+                const double *sv = stage_buf + (size_t)stage * (kTmaStageBytes / 8) + (size_t)(kb - k0) * 36 + i * 6;
+                double acc = 0.0;
+                for (int32_t k = kb; k < ke; ++k, sv += 36) {
+                    const int32_t c = __ldg(colidx + k);
+                    const double *xx = x + (int64_t)c * 6;
+                    const double2 x0 = ldg2(xx), x1 = ldg2(xx + 2), x2 = ldg2(xx + 4);
+                    const double2 v0 = *reinterpret_cast<const double2 *>(sv);
+                    const double2 v1 = *reinterpret_cast<const double2 *>(sv + 2);
+                    const double2 v2 = *reinterpret_cast<const double2 *>(sv + 4);
+                    acc = fma(v0.x, x0.x, acc); acc = fma(v0.y, x0.y, acc);
+                    acc = fma(v1.x, x1.x, acc); acc = fma(v1.y, x1.y, acc);
+                    acc = fma(v2.x, x2.x, acc); acc = fma(v2.y, x2.y, acc);
+                }
+                y[(int64_t)row * 6 + i] = acc;
+                dot = fma(__ldg(x + (int64_t)row * 6 + i), acc, dot);
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
+        }
+    }
+    if (partial != nullptr) {
+        const double s = block_sum<false>(dot, red);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
+int spmv_tma_grid(int64_t ntiles, int sm_count)
+{
+    int64_t g = ntiles < sm_count ? ntiles : sm_count;
+    if (g > kMaxPartials) g = kMaxPartials;
+    return (int)(g < 1 ? 1 : g);
+}
+
+size_t spmv_tma_smem_bytes() { return (size_t)kTmaStages * kTmaStageBytes; }
+
+int spmv_tma_prepare()
+{
+    return (int)cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)spmv_tma_smem_bytes());
+}
+
+void launch_spmv_tma(cudaStream_t st, int grid, int64_t ntiles, const int32_t *tile_row,
+                     const int32_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
+                     double *y, double *partial, const PcgScalars *sc)
+{
+    k_spmv_tma<<<grid, kTmaThreads, spmv_tma_smem_bytes(), st>>>(ntiles, tile_row, rowptr, colidx, vals, x, y,
+                                                                 partial, sc);
+}
+
+// ---------------------------------------------------------------------------
+// K6: fused PCG vector kernels.  192 threads = 32 block rows x 6 DOFs; the
+// block-Jacobi apply needs the 6 residuals of a row, exchanged through shared
+// memory.  All scalars (alpha, beta, iteration count, stop flag) live on the
+// device so a whole batch of iterations is one CUDA graph with no host sync.
+// ---------------------------------------------------------------------------
+int vec_grid(int64_t nb)
+{
+    const int64_t tiles = (nb + kRowsPerCta - 1) / kRowsPerCta;
+    return (int)(tiles < 1 ? 1 : (tiles > kMaxPartials ? kMaxPartials : tiles));
+}
+
+// z_i = sum_j Minv[row][i][j] * rs[j]
+__device__ __forceinline__ double apply_minv_row(const double *__restrict__ minv, int64_t row, int i,
+                                                 const double *rs)
+{
+    const double *m = minv + row * 36 + i * 6;
+    const double2 m0 = ldg2(m), m1 = ldg2(m + 2), m2 = ldg2(m + 4);
+    double z = m0.x * rs[0];
+    z = fma(m0.y, rs[1], z); z = fma(m1.x, rs[2], z); z = fma(m1.y, rs[3], z);
+    z = fma(m2.x, rs[4], z); z = fma(m2.y, rs[5], z);
+    return z;
+}
+
+__global__ void __launch_bounds__(kSpmvThreads) k_pcg_init(
+    int64_t nb, const double *__restrict__ f, const double *__restrict__ minv, double *__restrict__ x,
+    double *__restrict__ r, double *__restrict__ z, double *__restrict__ p, double *__restrict__ part_rz,
+    double *__restrict__ part_ff)
+{
+    __shared__ double rs[kSpmvThreads];
+    __shared__ double red[33];
+    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+    double rz = 0.0, ff = 0.0;
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+        const int64_t row = r0 + lr;
+        const bool live = row < nb;
+        double fv = 0.0;
+        if (live) fv = f[row * 6 + i];
+        __syncthreads();
+        rs[threadIdx.x] = fv;
+        __syncthreads();
+        if (live) {
+            const double zv = apply_minv_row(minv, row, i, rs + lr * 6);
+            x[row * 6 + i] = 0.0;
+            r[row * 6 + i] = fv;
+            z[row * 6 + i] = zv;
+            p[row * 6 + i] = zv;
+            rz = fma(fv, zv, rz);
+            ff = fma(fv, fv, ff);
+        }
+    }
+    const double a = block_sum<false>(rz, red);
+    const double b = block_sum<false>(ff, red);
+    if (threadIdx.x == 0) { part_rz[blockIdx.x] = a; part_ff[blockIdx.x] = b; }
+}
+
+__global__ void __launch_bounds__(256) k_pcg_init_finish(PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
+                                                         long long max_iter)
+{
+    __shared__ double red[33];
+    const double a = sum_partials(rz, red);
+    const double b = sum_partials(ff, red);
+    if (threadIdx.x == 0) {
+        sc->rz[0] = a; sc->rz[1] = 0.0;
+        sc->ff = b; sc->rr = b; sc->pAp = 1.0;
+        sc->iter = 0; sc->max_iter = max_iter; sc->tol2 = tol * tol;
+        // f == 0 -> u == 0 is the solution; a non-finite load is a breakdown
+        sc->done = (b == 0.0) ? 1 : ((isfinite(a) && isfinite(b)) ? 0 : 3);
+        sc->pad = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kSpmvThreads) k_pcg_update(
+    int64_t nb, int parity, PartialRef pAp_ref, const double *__restrict__ minv, const double *__restrict__ p,
+    const double *__restrict__ Ap, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
+    double *__restrict__ part_rz, double *__restrict__ part_rr, PcgScalars *sc)
+{
+    __shared__ double rs[kSpmvThreads];
+    __shared__ double red[33];
+    if (sc->done != 0) return;
+    const double pAp = sum_partials(pAp_ref, red);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->pAp = pAp;
+    if (!(pAp > 0.0) || !isfinite(pAp)) return;  // breakdown: k_pcg_pupdate raises the flag
+    const double alpha = sc->rz[parity] / pAp;
+    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+    double rz = 0.0, rr = 0.0;
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+        const int64_t row = r0 + lr;
+        const bool live = row < nb;
+        double rv = 0.0;
+        if (live) {
+            const int64_t j = row * 6 + i;
+            x[j] = fma(alpha, p[j], x[j]);
+            rv = fma(-alpha, Ap[j], r[j]);
+            r[j] = rv;
+        }
+        __syncthreads();
+        rs[threadIdx.x] = rv;
+        __syncthreads();
+        if (live) {
+            const double zv = apply_minv_row(minv, row, i, rs + lr * 6);
+            z[row * 6 + i] = zv;
+            rz = fma(rv, zv, rz);
+            rr = fma(rv, rv, rr);
+        }
+    }
+    const double a = block_sum<false>(rz, red);
+    const double b = block_sum<false>(rr, red);
+    if (threadIdx.x == 0) { part_rz[blockIdx.x] = a; part_rr[blockIdx.x] = b; }
+}
+
+__global__ void __launch_bounds__(kSpmvThreads) k_pcg_pupdate(
+    int64_t nb, int parity, PartialRef rz_ref, PartialRef rr_ref, const double *__restrict__ z,
+    double *__restrict__ p, PcgScalars *sc)
+{
+    __shared__ double red[33];
+    if (sc->done != 0) return;
+    const double pAp = sc->pAp;
+    if (!(pAp > 0.0) || !isfinite(pAp)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->done = 3;
+        return;
+    }
+    const double rz_new = sum_partials(rz_ref, red);
+    const double rr = sum_partials(rr_ref, red);
+    const double beta = rz_new / sc->rz[parity];
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb * 6;
+         j += (int64_t)gridDim.x * blockDim.x)
+        p[j] = fma(beta, p[j], z[j]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rz[parity ^ 1] = rz_new;
+        sc->rr = rr;
+        const long long it = sc->iter + 1;
+        sc->iter = it;
+        int done = 0;
+        if (!isfinite(rr) || !isfinite(rz_new)) done = 3;
+        else if (rr <= sc->tol2 * sc->ff) done = 1;
+        else if (it >= sc->max_iter) done = 2;
+        sc->done = done;
+    }
+}
+
+void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double *minv, double *x,
+                     double *r, double *z, double *p, double *part_rz, double *part_ff)
+{
+    k_pcg_init<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, f, minv, x, r, z, p, part_rz, part_ff);
+}
+
+void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
+                            long long max_iter)
+{
+    k_pcg_init_finish<<<1, 256, 0, st>>>(rz, ff, sc, tol, max_iter);
+}
+
+void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
+                       const double *p, const double *Ap, double *x, double *r, double *z,
+                       double *part_rz, double *part_rr, PcgScalars *sc)
+{
+    k_pcg_update<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, pAp, minv, p, Ap, x, r, z, part_rz, part_rr, sc);
+}
+
+void launch_pcg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rz, PartialRef rr,
+                        const double *z, double *p, PcgScalars *sc)
+{
+    k_pcg_pupdate<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, rz, rr, z, p, sc);
+}
+
+// collapse partial sums to one value each (fixed order); multi-GPU path
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *a, int n, double *out_a, const double *b,
+                                                         double *out_b, const PcgScalars *sc)
+{
+    __shared__ double red[33];
+    if (sc != nullptr && sc->done != 0) return;
+    const double sa = sum_partials(PartialRef{a, n, 1}, red);
+    if (threadIdx.x == 0) *out_a = sa;
+    if (b != nullptr) {
+        const double sb = sum_partials(PartialRef{b, n, 1}, red);
+        if (threadIdx.x == 0) *out_b = sb;
+    }
+}
+
+void launch_reduce_partials(cudaStream_t st, const double *a, int n, double *out_a, const double *b,
+                            double *out_b, const PcgScalars *sc)
+{
+    k_reduce_partials<<<1, 256, 0, st>>>(a, n, out_a, b, out_b, sc);
+}
+
+__global__ void k_pack_halo(int64_t n_send, const int32_t *__restrict__ send_rows, const double *__restrict__ x,
+                            double *__restrict__ sendbuf)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = t / 6;
+    const int i = (int)(t - s * 6);
+    if (s >= n_send) return;
+    sendbuf[t] = x[(int64_t)__ldg(send_rows + s) * 6 + i];
+}
+
+void launch_pack_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, const double *x, double *sendbuf)
+{
+    if (n_send <= 0) return;
+    const int64_t n = n_send * 6;
+    k_pack_halo<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_send, send_rows, x, sendbuf);
+}
+
+__global__ void __launch_bounds__(kSpmvThreads) k_residual(int64_t nb, const double *__restrict__ f,
+                                                           const double *__restrict__ y,
+                                                           double *__restrict__ part_rr)
+{
+    __shared__ double red[33];
+    double rr = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb * 6;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        const double d = f[j] - y[j];
+        rr = fma(d, d, rr);
+    }
+    const double s = block_sum<false>(rr, red);
+    if (threadIdx.x == 0) part_rr[blockIdx.x] = s;
+}
+
+void launch_residual(cudaStream_t st, int64_t nb, const double *f, const double *y, double *part_rr)
+{
+    k_residual<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, f, y, part_rr);
+}
+
+__global__ void k_fill_f64(int64_t n, double *a, double v0, double dv, int period)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v0 + dv * (double)(i % period);
+}
+
+void launch_fill(cudaStream_t st, int64_t n, double *a, double v0, double dv, int period)
+{
+    if (n <= 0) return;
+    k_fill_f64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, v0, dv, period);
+}
+
+// load vector of the reduced system: f[6*free_index[node]+dof] += magnitude.
+// One thread, fixed order: duplicates accumulate in input order (deterministic)
+// and nF is tiny next to the mesh.  Forces on fixed vertices are dropped, as
+// elimination drops their equations.
+__global__ void k_scatter_forces(int64_t nF, const int64_t *__restrict__ node, const int64_t *__restrict__ dof,
+                                 const double *__restrict__ mag, const int32_t *__restrict__ free_index,
+                                 int64_t row_begin, int64_t nb, double *f)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int64_t i = 0; i < nF; ++i) {
+        const int64_t g = free_index[node[i]];
+        if (g < row_begin || g >= row_begin + nb) continue;
+        f[(g - row_begin) * 6 + dof[i]] += mag[i];
+    }
+}
+
+void launch_scatter_forces(cudaStream_t st, int64_t nF, const int64_t *node, const int64_t *dof, const double *mag,
+                           const int32_t *free_index, int64_t row_begin, int64_t nb, double *f)
+{
+    if (nF <= 0) return;
+    k_scatter_forces<<<1, 32, 0, st>>>(nF, node, dof, mag, free_index, row_begin, nb, f);
+}
+
+// ---------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------
+// U_cm: V x 6 column-major (Eigen::MatrixXd nodalDisplacements
+// [REF src/beamsimulator.cpp:192]); U_rm: the same row-major for the K7 gather.
+__global__ void k_expand(int64_t V, const int32_t *__restrict__ free_index, const double *__restrict__ xg,
+                         double *__restrict__ U_cm, double *__restrict__ U_rm)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t v = t / 6;
+    const int d = (int)(t - v * 6);
+    if (v >= V) return;
+    const int32_t fi = __ldg(free_index + v);
+    const double u = fi >= 0 ? xg[(int64_t)fi * 6 + d] : 0.0;
+    U_rm[t] = u;
+    U_cm[(int64_t)d * V + v] = u;
+}
+
+void launch_expand(cudaStream_t st, int64_t V, const int32_t *free_index, const double *x_global,
+                   double *U_cm, double *U_rm)
+{
+    if (V <= 0) return;
+    const int64_t n = V * 6;
+    k_expand<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V, free_index, x_global, U_cm, U_rm);
+}
+
+__global__ void k_cm_to_rm(int64_t V, const double *__restrict__ U_cm, double *__restrict__ U_rm)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t v = t / 6;
+    const int d = (int)(t - v * 6);
+    if (v >= V) return;
+    U_rm[t] = U_cm[(int64_t)d * V + v];
+}
+
+void launch_colmajor_to_rowmajor(cudaStream_t st, int64_t V, const double *U_cm, double *U_rm)
+{
+    if (V <= 0) return;
+    const int64_t n = V * 6;
+    k_cm_to_rm<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V, U_cm, U_rm);
+}
+
+// K7: f_e = K_l (A u_e), one thread per beam, K_l and A rebuilt in registers.
+// Output layout of SimulationResults::edgeForces [REF src/beamsimulator.cpp:198-207]:
+// F[c*2E + 2e] = f_e[c], F[c*2E + 2e+1] = f_e[6+c]  -> one 16-byte store per component.
+__global__ void __launch_bounds__(128) k_element_forces(int64_t E, const ElemRec *__restrict__ rec,
+                                                        const Node4 *__restrict__ node4,
+                                                        const double *__restrict__ U_rm,
+                                                        double *__restrict__ F6x2E)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    Frame f; Stiff s; int32_t a, b;
+    load_elem(rec, node4, e, f, s, a, b);
+    double ue[12], ul[12], fe[12];
+    const double *ua = U_rm + (int64_t)a * 6, *ub = U_rm + (int64_t)b * 6;
+#pragma unroll
+    for (int j = 0; j < 6; j += 2) {
+        const double2 va = ldg2(ua + j), vb = ldg2(ub + j);
+        ue[j] = va.x; ue[j + 1] = va.y; ue[6 + j] = vb.x; ue[6 + j + 1] = vb.y;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const double *u3 = ue + 3 * g;
+        ul[3 * g + 0] = ADD(ADD(MUL(f.nx[0], u3[0]), MUL(f.nx[1], u3[1])), MUL(f.nx[2], u3[2]));
+        ul[3 * g + 1] = ADD(ADD(MUL(f.ny[0], u3[0]), MUL(f.ny[1], u3[1])), MUL(f.ny[2], u3[2]));
+        ul[3 * g + 2] = ADD(ADD(MUL(f.nz[0], u3[0]), MUL(f.nz[1], u3[1])), MUL(f.nz[2], u3[2]));
+    }
+    local_forces(s, ul, fe);
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+        *reinterpret_cast<double2 *>(F6x2E + (int64_t)c * 2 * E + 2 * e) = make_double2(fe[c], fe[6 + c]);
+}
+
+void launch_element_forces(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4,
+                           const double *U_rm, double *F6x2E)
+{
+    if (E <= 0) return;
+    k_element_forces<<<(unsigned)((E + 127) / 128), 128, 0, st>>>(E, rec, node4, U_rm, F6x2E);
+}
+
+}}  // namespace mbfea::dev

@@ -1,0 +1,91 @@
+// Launch wrappers of the hand-written sm_100a kernels (definitions in
+// kernels.cu).  All launches go to the caller's stream; none synchronises.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "element.cuh"
+
+namespace mbfea { namespace dev {
+
+constexpr int kVecThreads = 256;
+constexpr int kMaxPartials = 148 * 8;  // fixed upper bound of reduction grids
+
+// TMA-staged SpMV tile geometry (see kernels.cu)
+constexpr int kTmaCapBlocks = 224;  // 6x6 blocks per stage: 224*288 B = 63 KB
+constexpr int kTmaMaxRows = 32;     // block rows per tile  -> 192 consumer threads
+constexpr int kTmaStages = 3;
+
+struct PcgScalars {
+    double rz[2];        // r.z, double-buffered by iteration parity
+    double ff;           // f.f
+    double rr;           // r.r of the last finished iteration
+    double pAp;          // last p.Ap (diagnostic)
+    long long iter;      // finished iterations
+    long long max_iter;
+    double tol2;         // tol^2
+    int done;            // 0 running, 1 converged, 2 max_iter, 3 breakdown
+    int pad;
+};
+
+// where a kernel finds the partial sums of a dot product: n values, stride apart
+struct PartialRef { const double *buf; int n; int stride; };
+
+void launch_pack_nodes(cudaStream_t st, int64_t V, const double *nodes_cm, Node4 *node4);
+void launch_pack_elems(cudaStream_t st, int64_t E, const int32_t *elems_cm, const double *normals_cm,
+                       const double *props4, ElemRec *rec);
+// K3: device constraint map (flags -> exclusive scan)
+void launch_free_map(cudaStream_t st, int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
+                     int32_t *scratch /* >= V + V/1024 + 1 ints */);
+// K1: E x 12 x 12 element matrices (parity tap)
+void launch_kelem(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4, double *Ke);
+// K1+K2 fused: deterministic scatter-free BSR assembly
+void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, const int32_t *contrib,
+                     const ElemRec *rec, const Node4 *node4, double *vals);
+// K5: inverse of every diagonal block; *flag |= 1 on a non-positive pivot
+void launch_block_jacobi(cudaStream_t st, int64_t nb, const int32_t *diag_idx, const double *vals,
+                         double *minv, int *flag);
+// K4: y = A x (x has nb + n_ghost blocks), partial[blockIdx] = sum x_own . y
+int  spmv_rowthread_grid(int64_t nb);
+void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx,
+                           const double *vals, const double *x, double *y, double *partial,
+                           const PcgScalars *sc);
+int  spmv_tma_grid(int64_t ntiles, int sm_count);
+size_t spmv_tma_smem_bytes();
+int  spmv_tma_prepare();  // opt in to the large dynamic shared memory; returns cudaError
+void launch_spmv_tma(cudaStream_t st, int grid, int64_t ntiles, const int32_t *tile_row,
+                     const int32_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
+                     double *y, double *partial, const PcgScalars *sc);
+// K6: fused PCG vector kernels
+int  vec_grid(int64_t nb);
+void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double *minv, double *x,
+                     double *r, double *z, double *p, double *part_rz, double *part_ff);
+void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
+                            long long max_iter);
+void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
+                       const double *p, const double *Ap, double *x, double *r, double *z,
+                       double *part_rz, double *part_rr, PcgScalars *sc);
+void launch_pcg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rz, PartialRef rr,
+                        const double *z, double *p, PcgScalars *sc);
+// collapse `n` partials to out[0] in fixed order (multi-GPU path, before the all-gather)
+void launch_reduce_partials(cudaStream_t st, const double *a, int n, double *out_a, const double *b,
+                            double *out_b, const PcgScalars *sc);
+// halo: pack owned boundary blocks into the send buffer
+void launch_pack_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, const double *x, double *sendbuf);
+// deterministic test pattern a[i] = v0 + dv*(i % period)  (SpMV timing input)
+void launch_fill(cudaStream_t st, int64_t n, double *a, double v0, double dv, int period);
+// load vector of the reduced system (owned rows), duplicates accumulate in input order
+void launch_scatter_forces(cudaStream_t st, int64_t nF, const int64_t *node, const int64_t *dof, const double *mag,
+                           const int32_t *free_index, int64_t row_begin, int64_t nb, double *f);
+// residual check: r = f - y, partial r.r
+void launch_residual(cudaStream_t st, int64_t nb, const double *f, const double *y, double *part_rr);
+// results
+void launch_expand(cudaStream_t st, int64_t V, const int32_t *free_index, const double *x_global,
+                   double *U_cm, double *U_rm);
+void launch_colmajor_to_rowmajor(cudaStream_t st, int64_t V, const double *U_cm, double *U_rm);
+// K7: element end forces in the SimulationResults layout (6 x 2E)
+void launch_element_forces(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4,
+                           const double *U_rm, double *F6x2E);
+
+}}  // namespace mbfea::dev

@@ -1,0 +1,80 @@
+// Internal declarations shared by the host-prep, kernel, solver and C-ABI
+// translation units of libmbfea.so.  Not installed; the public surface is
+// include/mbfea.h.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/mbfea.h"
+
+namespace mbfea {
+
+// ---------------------------------------------------------------------------
+// Host-side plan: everything derived from connectivity + fixed set.  Pure C++,
+// usable without a GPU (mbfea_plan_partition, gloo tests).
+// ---------------------------------------------------------------------------
+struct Neighbor {
+    int32_t rank;
+    int64_t recv_offset, recv_count;  // in ghost blocks (ghost region of x)
+    int64_t send_offset, send_count;  // in send_rows
+};
+
+struct HostPlan {
+    int64_t V = 0, E = 0;
+    int32_t rank = 0, world = 1;
+    int64_t nb_global = 0;            // free vertices
+    int64_t row_begin = 0, row_end = 0;
+    std::vector<int32_t> free_index;  // V, -1 fixed  (K3 map, host copy)
+    std::vector<int32_t> rowptr;      // nb+1
+    std::vector<int32_t> colidx;      // nnzb, LOCAL ids: owned [0,nb), ghosts after
+    std::vector<int32_t> diag_idx;    // nb: position of the diagonal block
+    std::vector<int32_t> contrib_ptr; // nnzb+1
+    std::vector<int32_t> contrib;     // (element<<2)|which, ascending element per block
+    std::vector<int64_t> ghost_global;// ascending => grouped by owner
+    std::vector<int32_t> ghost_owner;
+    std::vector<int32_t> send_rows;   // local row ids grouped by destination rank
+    std::vector<int32_t> send_dest;   // parallel to send_rows
+    std::vector<Neighbor> neighbors;
+    int64_t nb() const { return row_end - row_begin; }
+    int64_t nnzb() const { return (int64_t)colidx.size(); }
+};
+
+// Which 6x6 sub-block of the 12x12 element matrix a contribution is.
+enum : int { SUB_00 = 0, SUB_01 = 1, SUB_10 = 2, SUB_11 = 3 };
+
+// Validation in the reference's order; returns MBFEA_* and fills msg.
+int validate_job(int64_t V, int64_t E, const int32_t *elems_cm, const float *dims_bh,
+                 const float *mat_nuE, int64_t F, const int32_t *fixed, int64_t nF,
+                 const int64_t *f_node, const int64_t *f_dof, std::string &msg);
+int validate_forces(int64_t V, int64_t nF, const int64_t *f_node, const int64_t *f_dof,
+                    std::string &msg);
+
+// float-quirk section properties [REF src/beamsimulator.cpp:173-188]
+void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4);
+
+// free_index + nb_global.  fixed must be validated already.
+int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<int32_t> &free_index);
+
+// Block pattern, contributor lists, halo plan for `rank` of `world`.
+// with_contrib=false skips the contributor lists (plan-only callers).
+void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
+                int32_t rank, int32_t world, bool with_contrib, HostPlan &plan);
+
+// Row tiles for the TMA-staged SpMV: tile t covers rows [tile_row[t], tile_row[t+1]).
+void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
+                 std::vector<int32_t> &tile_row);
+
+// Scenario files (config.json + ASCII PLY).
+struct Scenario {
+    int64_t V = 0, E = 0;
+    std::vector<double> nodes_cm, normals_cm;
+    std::vector<int32_t> elems_cm, fixed;
+    std::vector<float> dims_bh, mat_nuE;
+    std::vector<int64_t> f_node, f_dof;
+    std::vector<double> f_mag;
+};
+int load_scenario_files(const char *json_path, const char *ply_override, Scenario &sc, std::string &msg);
+int load_ply_edge_mesh(const char *ply_path, Scenario &sc, std::string &msg);
+
+}  // namespace mbfea
