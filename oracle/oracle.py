@@ -187,7 +187,20 @@ def element_forces(job: Job, U_rowmajor: np.ndarray, props=None):
     return F, Fe
 
 
-def solve(job: Job, form: str = "eliminate"):
+def _lu_solve(A, rhs, refine: int):
+    """SuperLU solve + `refine` steps of iterative refinement (residual in
+    long double).  refine=0 is the raw factorisation the reference would use."""
+    import scipy.sparse.linalg as spla
+    lu = spla.splu(A.tocsc())
+    x = lu.solve(rhs)
+    Ac = A.tocsr()
+    for _ in range(refine):
+        r = (rhs.astype(np.longdouble) - (Ac @ x).astype(np.longdouble)).astype(np.float64)
+        x = x + lu.solve(r)
+    return x
+
+
+def solve(job: Job, form: str = "eliminate", refine: int = 2):
     """Full pipeline with a sparse direct solve.
 
     Returns (U (V,6), edge_forces (6, 2E)) in the layout of the reference's
@@ -204,7 +217,7 @@ def solve(job: Job, form: str = "eliminate"):
         free_dofs = (6 * np.nonzero(fm >= 0)[0][:, None] + np.arange(6)[None, :]).ravel()
         Kr = K[free_dofs][:, free_dofs].tocsc()
         u = np.zeros(6 * V)
-        u[free_dofs] = spla.splu(Kr).solve(f[free_dofs])
+        u[free_dofs] = _lu_solve(Kr, f[free_dofs], refine)
     elif form == "kkt":
         # one Lagrange row/col per BC, 6 per fixed vertex in the order the
         # reference emits them [REF src/beamsimulator.cpp:139-150]
@@ -214,7 +227,7 @@ def solve(job: Job, form: str = "eliminate"):
         Cmat = sp.csr_matrix((np.ones(m), (np.arange(m), bc)), shape=(m, 6 * V))
         KKT = sp.bmat([[K, Cmat.T], [Cmat, None]], format="csc")
         rhs = np.concatenate([f, np.zeros(m)])
-        u = spla.splu(KKT).solve(rhs)[:6 * V]
+        u = _lu_solve(KKT, rhs, refine)[:6 * V]
     else:
         raise ValueError(form)
     U = u.reshape(V, 6)

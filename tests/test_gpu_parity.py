@@ -1,0 +1,311 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/mbfea.h),
+against the CPU oracle on the same seeded inputs, against the committed golden
+fixtures, and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Bars (BASELINE.json north_star): DOF numbering, block pattern and
+constraint map bit-exact; assembled K entries within 1e-12 relative (to the
+block's largest entry; in fact they are bit-identical); displacements and beam
+forces within 1e-8 relative L2."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import meshbeamfea_b200 as mb
+from meshbeamfea_b200 import _lib as L
+from meshbeamfea_b200 import synthetic as syn
+from oracle import oracle as orc
+from helpers import to_oracle, rel_l2, block_rel, write_scenario, forces_list
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+TOL_K = 1e-12     # K entries, relative to the block maximum
+TOL_U = 1e-8      # displacements / forces, relative L2
+
+
+def ctx_for(job, **kw):
+    kw.setdefault("tol", 1e-12)   # parity runs converge well below the 1e-8 bar (hard part 5)
+    c = mb.Context(device=0, **kw)
+    c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job.beamMaterial,
+              job.fixedNodes, job.nodalForces)
+    return c
+
+
+def oracle_bsr(O):
+    V = O.nodes.shape[0]
+    props = orc.beam_props(O.dims, O.material)
+    fm = orc.free_map(V, O.fixed)
+    rp, col = orc.bsr_pattern(O, fm)
+    vals = orc.bsr_assemble(O, fm, rp, col, props)
+    return props, fm, rp, col, vals
+
+
+def oracle_spmv(rp, col, vals, x):
+    y = np.empty_like(x)
+    colc = np.ascontiguousarray(col, np.int32)
+    orc.lib().orc_bsr_spmv(C.c_int64(rp.size - 1), rp.ctypes.data_as(orc._pi64), colc.ctypes.data_as(orc._pi32),
+                           vals.ctypes.data_as(orc._pd), x.ctypes.data_as(orc._pd), y.ctypes.data_as(orc._pd))
+    return y
+
+
+SMALL = {
+    "two_segments": lambda: syn.two_line_segments(),
+    "cantilever5_rot": lambda: syn.cantilever(5, *list(syn.tester_rotation_cases())[14][3:5]),
+    "planar_grid_24": lambda: syn.planar_grid(24),
+    "lattice_9": lambda: syn.cubic_lattice(9),
+    "gridshell_17": lambda: syn.gridshell(17),
+    "random_1234": lambda: syn.random_mesh(1234),
+    "random_batch_8": lambda: syn.merge_jobs([syn.random_mesh(1234 + m, V=60) for m in range(8)]),
+}
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_stage_by_stage_parity(built, name):
+    job = SMALL[name]()
+    O = to_oracle(job)
+    props, fm, rp, col, vals = oracle_bsr(O)
+    with ctx_for(job) as c:
+        # section properties: float arithmetic of the reference, bit-exact
+        assert np.array_equal(c.props(), props)
+        # K3 constraint map (device kernel), bit-exact
+        assert np.array_equal(c.dofmap(), fm)
+        # K1 element matrices
+        Ke = orc.kelem_all(O, props)
+        Kg = c.kelem()
+        assert block_rel(Kg.reshape(-1, 12, 12), Ke.reshape(-1, 12, 12)) <= TOL_K
+        assert np.array_equal(Kg, Ke)                      # bit-identical (same IEEE operation order)
+        # K2 pattern + values
+        c.assemble()
+        rp2, col2, vals2, ghosts = c.bsr()
+        assert np.array_equal(rp2, rp) and np.array_equal(col2, col) and ghosts.size == 0
+        assert block_rel(vals2, vals) <= TOL_K
+        assert np.array_equal(vals2, vals)                 # deterministic element-order sums
+        # load vector of the reduced system
+        f = orc.load_vector(O.nodes.shape[0], O.forces)
+        free_dofs = (6 * np.nonzero(fm >= 0)[0][:, None] + np.arange(6)[None, :]).ravel()
+        assert np.array_equal(c.load(), f[free_dofs])
+        # K4 both SpMV kernels
+        x = np.random.default_rng(0).standard_normal(free_dofs.size)
+        y0 = oracle_spmv(rp, col, vals, x)
+        for kernel in (1, 2):
+            assert rel_l2(c.spmv(x, kernel=kernel), y0) < 1e-14
+        # the whole path vs the oracle's sparse direct solve
+        c.execute()
+        U, F = orc.solve(O)
+        st = c.stats()
+        assert st["converged"] == 1 and st["rel_residual"] <= 1e-12
+        assert rel_l2(c.displacements(), U) < TOL_U
+        assert rel_l2(c.edge_forces(), F) < TOL_U
+        assert np.all(c.displacements()[np.asarray(job.fixedNodes)] == 0.0)
+        # K7 alone, on the oracle's displacements: bit-identical
+        c.recover_from(U)
+        assert np.array_equal(c.edge_forces(), F)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_both_spmv_kernels_give_the_same_solution(built, kernel):
+    job = syn.cubic_lattice(14)
+    O = to_oracle(job)
+    U, F = orc.solve(O)
+    with ctx_for(job, spmv_kernel=kernel) as c:
+        c.execute()
+        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
+
+
+def test_reference_fixture_and_screenshot_golden(built):
+    sim = mb.BeamSimulator(device=0, tol=1e-13)
+    sim.setSimulation(syn.two_line_segments())
+    res = sim.executeSimulation()
+    assert np.allclose(res.edgeForces[5], [-200.0, 100.0, -100.0, 0.0], rtol=0, atol=1e-7)
+    assert res.nodalDisplacements[2, 1] == pytest.approx(0.40000006103516, abs=1e-12)
+    assert res.nodalDisplacements.shape == (3, 6) and len(res.edgeForces) == 6 and res.edgeForces[0].shape == (4,)
+    assert sim.getResults() is res
+    sim.setSimulation(syn.two_line_segments(fixed=(1, 2), forces=((0, 0, 1000.0),)))
+    res = sim.executeSimulation()
+    assert res.nodalDisplacements[0, 0] == pytest.approx(1.25e-05, rel=1e-12)
+    assert np.allclose(res.edgeForces[0], [1000.0, -1000.0, 0.0, 0.0], atol=1e-7)
+
+
+def test_tester_rotation_cases(built):
+    """The 45 runs of BeamSimulatorTester::launchRotationTest
+    [REF src/beamsimulatortester.cpp:8-41] through the mirrored API."""
+    sim = mb.BeamSimulator(device=0, tol=1e-13)
+    for axis, step, nbeams, xa, ya in syn.tester_rotation_cases():
+        sim.setSimulation(syn.cantilever(nbeams, xa, ya))
+        res = sim.executeSimulation()
+        tip = res.nodalDisplacements[-1]
+        za = np.cross(xa, ya)
+        assert tip[:3] @ ya == pytest.approx(2.380952380952381e-05, rel=1e-9)
+        assert tip[3:] @ za == pytest.approx(3.571428571428572e-05, rel=1e-9)
+        assert res.edgeForces[5][0] == pytest.approx(-1000.0, rel=1e-9)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))), ids=os.path.basename)
+def test_committed_golden_fixtures(built, path):
+    g = np.load(path)
+    with mb.Context(device=0, tol=1e-13) as c:
+        c.set_job(g["nodes"], g["elements"], g["normals"], g["dims"], g["material"], g["fixed"],
+                  [(int(a), int(b), float(v)) for a, b, v in g["forces"]])
+        c.execute()
+        assert np.array_equal(c.props(), g["props"]) and np.array_equal(c.dofmap(), g["free_index"])
+        assert rel_l2(c.displacements(), g["U"]) < TOL_U
+        assert rel_l2(c.edge_forces(), g["F"]) < TOL_U
+
+
+def test_error_conventions_through_the_abi(built, tmp_path):
+    sim = mb.BeamSimulator(device=0)
+    with pytest.raises(mb.ContractViolation):          # Expects(!simulationJob.isEmpty())
+        sim.executeSimulation()
+    job = syn.two_line_segments(fixed=(1, 2, 3), forces=((0, 0, 1000.0),))   # config.json as shipped
+    with pytest.raises(RuntimeError, match="Vertex index is outside of valid range."):
+        sim.setSimulation(job)
+    with pytest.raises(mb.ContractViolation):          # job stays empty after a failed setSimulation
+        sim.executeSimulation()
+    with pytest.raises(mb.RangeError, match="Node index is out of valid range."):
+        sim.setSimulation(syn.two_line_segments(forces=((3, 1, 100.0),)))
+    bad = syn.two_line_segments(); bad.elementalNormals = bad.elementalNormals[:1]
+    with pytest.raises(mb.ContractViolation):          # Expects(sizes match) [REF src/beamsimulator.cpp:73-75]
+        sim.setSimulation(bad)
+    # no fixed vertex: the reduced matrix is singular -> reported, not silently wrong
+    with pytest.raises((mb.SingularSystem, mb.NotConverged)):
+        s2 = mb.BeamSimulator(device=0, max_iter=500)
+        s2.setSimulation(syn.two_line_segments(fixed=()))
+        s2.executeSimulation()
+    # call order
+    with mb.Context(device=0) as c:
+        with pytest.raises(mb.MbfeaError):
+            c.execute()
+    # scenario files end to end [REF src/utilities.hpp:50-95]
+    cfg, ply = write_scenario(tmp_path, [0], [[2, 1, 100]])
+    with mb.Context(device=0, tol=1e-13) as c:
+        c.load_scenario(cfg)
+        c.execute()
+        assert np.allclose(c.edge_forces()[5], [-200.0, 100.0, -100.0, 0.0], atol=1e-7)
+        nd, ef = os.path.join(str(tmp_path), "nd.csv"), os.path.join(str(tmp_path), "ef.csv")
+        c.write_displacements_csv(nd); c.write_element_forces_csv(ef)
+        ndv = np.loadtxt(nd, delimiter=","); efv = np.loadtxt(ef, delimiter=",")
+        assert ndv.shape == (3, 6) and efv.shape == (2, 12)
+        assert np.allclose(ndv, c.displacements(), rtol=1e-13, atol=0)
+        assert np.allclose(efv[:, 5], [-200.0, -100.0], atol=1e-6) and np.allclose(efv[:, 11], [100.0, 0.0], atol=1e-6)
+    cfg2, _ = write_scenario(tmp_path, [1, 2, 3], [[0, 0, 1000]])
+    with mb.Context(device=0) as c:
+        with pytest.raises(RuntimeError, match="Vertex index is outside of valid range."):
+            c.load_scenario(cfg2)
+
+
+def test_forces_on_fixed_vertices_duplicates_and_reload(built):
+    job = syn.planar_grid(10)
+    O = to_oracle(job)
+    with ctx_for(job) as c:
+        c.execute()
+        U1 = c.displacements().copy()
+        # duplicates accumulate; forces on fixed vertices are dropped by elimination
+        forces = forces_list(job)
+        doubled = forces + forces + [(0, 2, 123.0)]
+        c.set_forces(doubled)
+        c.solve(); c.recover()
+        assert rel_l2(c.displacements(), 2 * U1) < 1e-9
+        c.set_forces(forces)
+        c.solve(); c.recover()
+        assert rel_l2(c.displacements(), U1) < 1e-9
+        # zero load -> zero solution, zero iterations
+        c.set_forces([])
+        c.solve(); c.recover()
+        assert c.stats()["iterations"] == 0 and np.all(c.displacements() == 0)
+
+
+def test_run_to_run_bitwise_determinism(built):
+    job = syn.cubic_lattice(12)
+    outs = []
+    for _ in range(2):
+        with ctx_for(job, tol=1e-10) as c:
+            c.execute()
+            outs.append((c.displacements().copy(), c.edge_forces().copy(), c.stats()["iterations"]))
+    assert outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_graph_and_plain_launch_agree(built):
+    job = syn.planar_grid(16)
+    with ctx_for(job, use_graph=True) as a, ctx_for(job, use_graph=False, check_every=10) as b:
+        a.execute(); b.execute()
+        assert a.stats()["iterations"] == b.stats()["iterations"]
+        assert np.array_equal(a.displacements(), b.displacements())
+
+
+def test_max_iter_reports_not_converged(built):
+    job = syn.cubic_lattice(12)
+    with ctx_for(job, tol=1e-12, max_iter=10) as c:
+        rc = c.execute(allow_unconverged=True)
+        st = c.stats()
+        assert rc == L.ENOCONV and st["converged"] == 0 and st["iterations"] == 10
+        assert c.displacements().shape == (12 ** 3, 6)       # results still readable
+    with ctx_for(job, tol=1e-12, max_iter=10) as c:
+        with pytest.raises(mb.NotConverged):
+            c.execute()
+
+
+def test_full_size_properties_lattice_100(built):
+    """BASELINE config 3 at full size (2.97 M beams, 5.94 M free DOF): the oracle
+    cannot solve this in seconds, so parity is checked through size-independent
+    properties of the assembled operator and of the recovered forces."""
+    n = 100
+    job = syn.cubic_lattice(n)
+    with ctx_for(job, tol=1e-8, max_iter=40) as c:
+        st0 = c.stats()
+        assert st0["n_beams"] == 2970000 and st0["n_block_rows"] == 990000
+        assert st0["nnz_blocks"] == 990000 + 2 * (2970000 - 10000)   # nb + 2*E_free
+        fm = c.dofmap()
+        ref = np.arange(n ** 3, dtype=np.int32).reshape(n, n, n)
+        exp = np.full(n ** 3, -1, np.int32)
+        free = (ref % n != 0).ravel()
+        exp[free] = np.arange(free.sum(), dtype=np.int32)
+        assert np.array_equal(fm, exp)                       # constraint map, closed form
+        c.assemble()
+        nb = st0["n_block_rows"]
+        rng = np.random.default_rng(1)
+        x, y = rng.standard_normal(6 * nb), rng.standard_normal(6 * nb)
+        for kernel in (1, 2):
+            Kx, Ky = c.spmv(x, kernel), c.spmv(y, kernel)
+            # symmetry: y.(Kx) == x.(Ky); linearity: K(2x-3y) == 2Kx-3Ky
+            assert abs(y @ Kx - x @ Ky) <= 1e-12 * (np.linalg.norm(Kx) * np.linalg.norm(y))
+            assert rel_l2(c.spmv(2 * x - 3 * y, kernel), 2 * Kx - 3 * Ky) < 1e-14
+            assert x @ Kx > 0                                  # positive definite on a random vector
+        assert np.array_equal(c.spmv(x, 1), c.spmv(x, 1))
+        assert rel_l2(c.spmv(x, 2), c.spmv(x, 1)) < 1e-15
+        # rigid translation of the whole lattice: K t = 0 on every row whose vertex
+        # has no fixed neighbour (layer k >= 2), and != 0 next to the clamped layer
+        t = np.zeros((nb, 6)); t[:, 0] = 1.0
+        Kt = c.spmv(t.ravel(), 1).reshape(nb, 6)
+        kk = (np.nonzero(free)[0] % n)
+        scale = np.abs(Kt[kk == 1]).max()
+        assert scale > 0 and np.abs(Kt[kk >= 2]).max() <= 1e-9 * scale
+        # the same rows of the block matrix vs the oracle on a 6^3 corner is covered
+        # by the small cases; here check the element forces of a rigid motion vanish
+        U = np.zeros((n ** 3, 6)); U[:, 0] = 1e-3; U[:, 1] = -2e-3; U[:, 2] = 5e-4
+        c.recover_from(U)
+        F = c.edge_forces()
+        assert np.abs(F).max() <= 1e-9 * 2.1e11 * 1e-4 * 1e-3 / 0.1 * 10
+        # equilibrium of recovered forces after a (truncated) solve: N at end0 == -N at end1
+        c.execute(allow_unconverged=True)
+        F = c.edge_forces()
+        assert np.abs(F[0][0::2] + F[0][1::2]).max() <= 1e-9 * max(1.0, np.abs(F[0]).max())
+        assert np.abs(F[3][0::2] + F[3][1::2]).max() <= 1e-9 * max(1.0, np.abs(F[3]).max())
+
+
+def test_batched_small_meshes_block_diagonal(built):
+    """BASELINE config 5 in miniature: many independent small meshes solved as one
+    block-diagonal job must equal the meshes solved one at a time."""
+    jobs = [syn.random_mesh(1234 + m, V=50) for m in range(16)]
+    merged = syn.merge_jobs(jobs)
+    with ctx_for(merged, tol=1e-13) as c:
+        c.execute()
+        U = c.displacements()
+    off = 0
+    for jb in jobs:
+        Uo, _ = orc.solve(to_oracle(jb))
+        V = jb.nodes.shape[0]
+        assert rel_l2(U[off:off + V], Uo) < TOL_U
+        off += V

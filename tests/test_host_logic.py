@@ -1,0 +1,253 @@
+"""CPU-only tests of the host side of libmbfea.so: the library loads and exports
+every symbol include/mbfea.h declares, validation/error conventions, the float
+section-property arithmetic, the constraint map, the block pattern and the
+vertex-block partition plan, and the scenario (config.json + PLY) reader.
+No compute entry point is called here (there is no GPU and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import meshbeamfea_b200 as mb
+from meshbeamfea_b200 import _lib as L
+from meshbeamfea_b200 import synthetic as syn
+from oracle import oracle as orc
+from helpers import to_oracle, write_scenario
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "mbfea.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mbfea_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    names = header_functions()
+    assert len(names) >= 35
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (mbfea_[a-z0-9_]+)", out))
+    assert set(names) <= exported, sorted(set(names) - exported)
+    assert set(names) == set(L.SIGNATURES), sorted(set(names) ^ set(L.SIGNATURES))
+    lib = L.lib()
+    assert lib.mbfea_version() == 100
+    assert lib.mbfea_status_string(2) == b"Vertex index is outside of valid range."
+    assert lib.mbfea_status_string(3) == b"Node index is out of valid range."
+
+
+def test_no_silent_cpu_fallback(built):
+    """Without a GPU the product must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mb.MbfeaError, match="no usable CUDA device"):
+        mb.Context()
+    with pytest.raises(mb.MbfeaError):
+        mb.BeamSimulator()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under meshbeamfea_b200/ or
+    include/ may import, link, load or call it."""
+    banned = re.compile(r"import\s+oracle|from\s+oracle|libmbfea_oracle|\borc_[a-z]|oracle\.py|oracle/oracle")
+    for top in ("meshbeamfea_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not banned.search(text), (dirpath, f)
+
+
+def _validate(job, fixed=None, forces=None):
+    lib = L.lib()
+    nodes = np.asarray(job.nodes, np.float64); el = np.ascontiguousarray(np.asarray(job.elements, np.int32).T).ravel()
+    dims = np.ascontiguousarray(job.beamDimensions, np.float32); mat = np.ascontiguousarray(job.beamMaterial, np.float32)
+    fixed = np.ascontiguousarray(job.fixedNodes if fixed is None else fixed, np.int32)
+    forces = [(f.index, f.dof, f.magnitude) for f in job.nodalForces] if forces is None else forces
+    fn = np.array([f[0] for f in forces], np.int64); fd = np.array([f[1] for f in forces], np.int64)
+    msg = C.create_string_buffer(256)
+    rc = lib.mbfea_host_validate(nodes.shape[0], job.elements.shape[0], L.ptr(el, L._pi32), L.ptr(dims, L._pf),
+                                 L.ptr(mat, L._pf), fixed.size, L.ptr(fixed, L._pi32), fn.size, L.ptr(fn, L._pi64),
+                                 L.ptr(fd, L._pi64), msg, 256)
+    return rc, msg.value.decode()
+
+
+def test_validation_error_conventions(built):
+    job = syn.two_line_segments()
+    assert _validate(job) == (L.OK, "")
+    # config.json as shipped fixes vertex 3 of a 3-vertex mesh [REF src/beamsimulator.cpp:134-137]
+    assert _validate(job, fixed=[1, 2, 3]) == (L.ERANGE_FIXED, "Vertex index is outside of valid range.")
+    assert _validate(job, fixed=[-1])[0] == L.ERANGE_FIXED
+    # [REF src/beamsimulator.cpp:164-166]
+    assert _validate(job, forces=[(3, 0, 1.0)]) == (L.ERANGE_FORCE, "Node index is out of valid range.")
+    assert _validate(job, forces=[(0, 6, 1.0)])[0] == L.EPRECOND      # [REF src/utilities.hpp:77]
+    bad = syn.two_line_segments(); bad.beamDimensions[1, 0] = 0.0     # [REF src/beam.hpp:14]
+    assert _validate(bad)[0] == L.EPRECOND
+    bad = syn.two_line_segments(); bad.beamMaterial[0, 0] = 0.51      # [REF src/beam.hpp:25]
+    assert _validate(bad)[0] == L.EPRECOND
+    bad = syn.two_line_segments(); bad.elements[0, 1] = 7
+    assert _validate(bad)[0] == L.EPRECOND
+    # the reference orders the checks elements -> fixed -> forces [REF src/beamsimulator.cpp:107-111]
+    assert _validate(job, fixed=[9], forces=[(9, 0, 1.0)])[0] == L.ERANGE_FIXED
+    with pytest.raises(mb.ContractViolation):
+        mb.BeamDimensions(0.0, 1.0)
+    with pytest.raises(mb.ContractViolation):
+        mb.BeamMaterial(0.6, 210)
+    assert (mb.BeamDimensions().b, mb.BeamDimensions().h) == (1.0, 1.0)           # [REF src/beam.hpp:16]
+    assert (mb.BeamMaterial().poissonsRatio, mb.BeamMaterial().youngsModulusGPascal) == (0.3, 210.0)  # [:27]
+
+
+def test_host_props_bit_exact_vs_oracle(built):
+    rng = np.random.default_rng(5)
+    E = 20000
+    dims = rng.uniform(0.001, 0.5, (E, 2)).astype(np.float32)
+    mat = np.stack([rng.uniform(-1, 0.5, E), rng.uniform(1, 1000, E)], 1).astype(np.float32)
+    out = np.empty((E, 4))
+    assert L.lib().mbfea_host_props(E, L.ptr(dims, L._pf), L.ptr(mat, L._pf), L.ptr(out, L._pd)) == L.OK
+    assert np.array_equal(out, orc.beam_props(dims, mat))
+    one = np.empty((1, 4))
+    L.lib().mbfea_host_props(1, L.ptr(np.array([[0.01, 0.01]], np.float32), L._pf),
+                             L.ptr(np.array([[0.3, 800]], np.float32), L._pf), L.ptr(one, L._pd))
+    assert list(one[0]) == [80000000.0, 666.6665649414062, 666.6665649414062, 512.8204345703125]
+
+
+def test_host_free_map_bit_exact_vs_oracle(built):
+    rng = np.random.default_rng(3)
+    for V, F in ((3, 1), (1000, 17), (50000, 7000)):
+        fixed = rng.integers(0, V, F).astype(np.int32)  # duplicates on purpose
+        fm = np.empty(V, np.int32); n = C.c_int64()
+        assert L.lib().mbfea_host_free_map(V, F, L.ptr(fixed, L._pi32), L.ptr(fm, L._pi32), C.byref(n)) == L.OK
+        ref = orc.free_map(V, fixed)
+        assert np.array_equal(fm, ref) and n.value == (ref >= 0).sum()
+    fm = np.empty(3, np.int32)
+    assert L.lib().mbfea_host_free_map(3, 3, L.ptr(np.array([1, 2, 3], np.int32), L._pi32), L.ptr(fm, L._pi32), None) == L.ERANGE_FIXED
+
+
+@pytest.mark.parametrize("job", [syn.two_line_segments(), syn.planar_grid(9), syn.cubic_lattice(5), syn.gridshell(7),
+                                 syn.random_mesh(21, V=80)], ids=["2seg", "grid9", "lat5", "shell7", "rand80"])
+def test_block_pattern_bit_exact_vs_oracle(built, job):
+    O = to_oracle(job)
+    V = O.nodes.shape[0]
+    fm = orc.free_map(V, O.fixed)
+    rp, col = orc.bsr_pattern(O, fm)
+    p = mb.plan_partition(V, job.elements, job.fixedNodes, 0, 1)
+    assert p["nb_global"] == (fm >= 0).sum() and p["row_begin"] == 0 and p["row_end"] == p["nb_global"]
+    assert np.array_equal(p["rowptr"], rp) and np.array_equal(p["colidx"], col)
+    assert p["ghost_global"].size == 0 and p["send_rows"].size == 0
+
+
+def test_pattern_with_multi_edges_and_isolated_vertex(built):
+    # two beams between the same pair of vertices share one block; a free vertex
+    # without beams still owns an (empty) diagonal block
+    elements = np.array([[0, 1], [1, 0], [1, 2]], np.int32)
+    p = mb.plan_partition(4, elements, np.array([0], np.int32), 0, 1)
+    assert p["nb_global"] == 3
+    assert list(p["rowptr"]) == [0, 2, 4, 5] and list(p["colidx"]) == [0, 1, 0, 1, 2]
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partition_plan_is_consistent(built, world):
+    job = syn.cubic_lattice(7)
+    V = job.nodes.shape[0]
+    full = mb.plan_partition(V, job.elements, job.fixedNodes, 0, 1)
+    plans = [mb.plan_partition(V, job.elements, job.fixedNodes, r, world) for r in range(world)]
+    nbg = full["nb_global"]
+    assert plans[0]["row_begin"] == 0 and plans[-1]["row_end"] == nbg
+    for r, p in enumerate(plans):
+        assert p["row_begin"] == nbg * r // world and p["row_end"] == nbg * (r + 1) // world
+        if r:
+            assert p["row_begin"] == plans[r - 1]["row_end"]
+        nb = p["row_end"] - p["row_begin"]
+        # local pattern, mapped back to global columns, equals the rows of the global pattern
+        lo, hi = full["rowptr"][p["row_begin"]], full["rowptr"][p["row_end"]]
+        assert np.array_equal(p["rowptr"], full["rowptr"][p["row_begin"]:p["row_end"] + 1] - lo)
+        gcol = np.where(p["colidx"] < nb, p["colidx"] + p["row_begin"],
+                        p["ghost_global"][np.maximum(p["colidx"] - nb, 0)] if p["ghost_global"].size else 0)
+        assert np.array_equal(gcol, full["colidx"][lo:hi])
+        # ghosts ascending, owned by someone else, owner consistent with the row split
+        gg = p["ghost_global"]
+        assert np.all(np.diff(gg) > 0)
+        assert np.all((gg < p["row_begin"]) | (gg >= p["row_end"]))
+        for g, o in zip(gg, p["ghost_owner"]):
+            assert plans[o]["row_begin"] <= g < plans[o]["row_end"]
+    # what q receives from r (in order) is exactly what r sends to q (in order)
+    for r, p in enumerate(plans):
+        for q, pq in enumerate(plans):
+            if q == r:
+                continue
+            sent = p["send_rows"][p["send_dest"] == q] + p["row_begin"]
+            recv = pq["ghost_global"][pq["ghost_owner"] == r]
+            assert np.array_equal(sent, recv)
+
+
+def test_scenario_reader_fixture_and_error_path(built, tmp_path):
+    cfg, ply = write_scenario(tmp_path, [0], [[2, 1, 100]])
+    job = mb.read_scenario(cfg)
+    ref = syn.two_line_segments()
+    assert np.array_equal(job.nodes, ref.nodes) and np.array_equal(job.elements, ref.elements)
+    assert np.array_equal(job.elementalNormals, ref.elementalNormals)
+    assert np.array_equal(job.beamDimensions, ref.beamDimensions) and np.array_equal(job.beamMaterial, ref.beamMaterial)
+    assert list(job.fixedNodes) == [0]
+    assert [(f.index, f.dof, f.magnitude) for f in job.nodalForces] == [(2, 1, 100.0)]
+    # absolute plyFilename that does not exist (config.json as shipped) -> IO error, override works
+    cfg2 = os.path.join(str(tmp_path), "shipped.json")
+    with open(cfg2, "w") as f:
+        f.write('{\n\t"plyFilename": "/home/iason/Coding/spiralEdgeMesh.ply",\n\t"fixedVertices": [1,2,3],\n\t"forces": [[0,0,1000]]\n}\n')
+    with pytest.raises(OSError):
+        mb.read_scenario(cfg2)
+    job = mb.read_scenario(cfg2, ply)
+    assert list(job.fixedNodes) == [1, 2, 3]  # vertex 3 is out of range: set_job must raise (GPU test)
+    # Expects(dof in [0,6) && index >= 0 && magnitude >= 0) [REF src/utilities.hpp:77]
+    cfg3, _ = write_scenario(tmp_path, [0], [[2, 1, -5]])
+    with pytest.raises(mb.ContractViolation):
+        mb.read_scenario(cfg3)
+    cfg4, _ = write_scenario(tmp_path, [0], [[2, 6, 5]])
+    with pytest.raises(mb.ContractViolation):
+        mb.read_scenario(cfg4)
+
+
+def test_ply_reader_defaults_and_double_types(built, tmp_path):
+    ply = """ply
+format ascii 1.0
+comment no custom attributes: defaults of VCGEdgeMesh::setDefaultAttributes
+element vertex 2
+property double x
+property double y
+property double z
+element edge 1
+property int vertex1
+property int vertex2
+end_header
+0.1 0 0
+0.30000000000000004 0 0
+0 1
+"""
+    cfg, _ = write_scenario(tmp_path, [0], [[1, 2, 1.5]], ply_text=ply, ply_name="plain.ply")
+    job = mb.read_scenario(cfg)
+    assert job.nodes[0, 0] == 0.1 and job.nodes[1, 0] == 0.30000000000000004
+    assert np.array_equal(job.elementalNormals, [[0, 0, 1]])          # [REF src/edgemesh.cpp:226-232]
+    assert np.array_equal(job.beamDimensions, np.array([[0.01, 0.01]], np.float32))
+    assert np.array_equal(job.beamMaterial, np.array([[0.3, 210]], np.float32))
+
+
+def test_synthetic_configs_have_the_surveyed_sizes():
+    g = syn.planar_grid(100)
+    assert g.nodes.shape[0] == 10000 and g.elements.shape[0] == 19800 and g.fixedNodes.size == 100
+    l = syn.cubic_lattice(10)
+    assert l.elements.shape[0] == 3 * 10 * 10 * 9 and l.fixedNodes.size == 100
+    # per vertex: +i (normal y), +j (normal z), +k (normal x)
+    assert list(l.elements[0]) == [0, 100] and list(l.elementalNormals[0]) == [0, 1, 0]
+    assert list(l.elements[1]) == [0, 10] and list(l.elementalNormals[1]) == [0, 0, 1]
+    assert list(l.elements[2]) == [0, 1] and list(l.elementalNormals[2]) == [1, 0, 0]
+    s = syn.gridshell(12)
+    t = s.nodes[s.elements[:, 1]] - s.nodes[s.elements[:, 0]]
+    assert np.abs((t * s.elementalNormals).sum(1)).max() < 1e-14      # normals exactly perpendicular
+    assert np.allclose(np.linalg.norm(s.elementalNormals, axis=1), 1.0, atol=1e-15)
+    r = syn.random_mesh(1234)
+    assert r.nodes.shape[0] == 200 and 450 <= r.elements.shape[0] <= 700
+    cases = list(syn.tester_rotation_cases())
+    assert len(cases) == 45                                            # [REF src/beamsimulatortester.cpp:21-40]
