@@ -67,7 +67,7 @@ typedef struct mbfea_options {
     int64_t max_iter;      /* 0 = 20*ndof                                       */
     int32_t check_every;   /* PCG iterations per captured CUDA graph; the host
                               polls convergence once per graph (0 = auto)      */
-    int32_t spmv_kernel;   /* 0 auto, 1 row-thread LDG kernel, 2 TMA-staged     */
+    int32_t spmv_kernel;   /* 0 auto (= 1), 1 row-thread LDG kernel, 2 TMA-staged */
     int32_t rank;          /* vertex-block partition: this process' rank ...   */
     int32_t world;         /* ... of `world` processes (1 = single GPU)        */
     int32_t use_graph;     /* 1 = capture the PCG iteration in a CUDA graph     */

@@ -32,6 +32,11 @@ struct __align__(32) Node4 { double x, y, z, w; };
 
 struct Frame { double nx[3], ny[3], nz[3]; double L; };
 
+// K1 output: the local frame and the ten stiffness coefficients of one beam,
+// computed once per beam and consumed by the assembly slices (160 B, 32-B aligned).
+struct __align__(32) ElemGeom { double v[20]; };
+static_assert(sizeof(ElemGeom) == 160, "ElemGeom must be 160 bytes");
+
 struct Stiff {  // the ten coefficients of K_l
     double ea, gj, z12, z6, z1x4, z1x2, y12, y6, y1x4, y1x2;
 };
@@ -150,6 +155,29 @@ __device__ __forceinline__ void load_elem(const ElemRec *__restrict__ rec, const
     Node4 P0{a0.x, a0.y, a1.x, 0.0}, P1{b0.x, b0.y, b1.x, 0.0};
     make_frame(P0, P1, nr, f);
     make_stiff(pr, f.L, s);
+}
+
+__device__ __forceinline__ void store_geom(ElemGeom *__restrict__ geom, int64_t e, const Frame &f, const Stiff &s,
+                                           int32_t a, int32_t b)
+{
+    double2 *o = reinterpret_cast<double2 *>(geom + e);
+    const long long ab = (long long)(((unsigned long long)(uint32_t)b << 32) | (uint32_t)a);
+    o[0] = make_double2(f.nx[0], f.nx[1]); o[1] = make_double2(f.nx[2], f.ny[0]);
+    o[2] = make_double2(f.ny[1], f.ny[2]); o[3] = make_double2(f.nz[0], f.nz[1]);
+    o[4] = make_double2(f.nz[2], s.ea);    o[5] = make_double2(s.gj, s.z12);
+    o[6] = make_double2(s.z6, s.z1x4);     o[7] = make_double2(s.z1x2, s.y12);
+    o[8] = make_double2(s.y6, s.y1x4);     o[9] = make_double2(s.y1x2, __longlong_as_double(ab));
+}
+
+__device__ __forceinline__ void load_geom(const ElemGeom *__restrict__ geom, int64_t e, Frame &f, Stiff &s)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(geom + e);
+    const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4),
+                  q5 = __ldg(q + 5), q6 = __ldg(q + 6), q7 = __ldg(q + 7), q8 = __ldg(q + 8), q9 = __ldg(q + 9);
+    f.nx[0] = q0.x; f.nx[1] = q0.y; f.nx[2] = q1.x; f.ny[0] = q1.y; f.ny[1] = q2.x; f.ny[2] = q2.y;
+    f.nz[0] = q3.x; f.nz[1] = q3.y; f.nz[2] = q4.x; f.L = 0.0;
+    s.ea = q4.y; s.gj = q5.x; s.z12 = q5.y; s.z6 = q6.x; s.z1x4 = q6.y; s.z1x2 = q7.x; s.y12 = q7.y;
+    s.y6 = q8.x; s.y1x4 = q8.y; s.y1x2 = q9.x;
 }
 
 }}  // namespace mbfea::dev

@@ -257,17 +257,40 @@ void launch_kelem(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *n
 }
 
 // ---------------------------------------------------------------------------
-// K1+K2 fused: one 6-lane slice per OUTPUT block, lane = row of the 6x6 block.
-// The slice walks the block's contributor list (element, sub-block), which the
+// K1 (production): one thread per beam computes the local frame and the ten
+// stiffness coefficients ONCE, register-resident from two 32-byte vertex
+// records and one 64-byte beam record (vectorised 16-byte loads), and stores
+// them as one 160-byte ElemGeom record.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_elem_geom(int64_t E, const ElemRec *__restrict__ rec,
+                                                   const Node4 *__restrict__ node4, ElemGeom *__restrict__ geom)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    Frame f; Stiff s; int32_t a, b;
+    load_elem(rec, node4, e, f, s, a, b);
+    store_geom(geom, e, f, s, a, b);
+}
+
+void launch_elem_geom(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4, ElemGeom *geom)
+{
+    if (E <= 0) return;
+    k_elem_geom<<<(unsigned)((E + 127) / 128), 128, 0, st>>>(E, rec, node4, geom);
+}
+
+// ---------------------------------------------------------------------------
+// K2: one 6-lane slice per OUTPUT block, lane = row of the 6x6 block.  The
+// slice walks the block's contributor list (element, sub-block), which the
 // host sorted by ascending element index -- the order in which the reference's
-// setFromTriplets sums duplicates -- recomputes the element's frame and
-// coefficients in registers and accumulates its row.  No atomics, no scatter:
-// every block is written exactly once, by one slice, in a fixed order.
+// setFromTriplets sums duplicates -- forms its row of Q^T S Q from the beam's
+// ElemGeom record (L1/L2-resident: the 6 lanes of a slice and the slices of
+// the same block row read the same records) and accumulates it.  No atomics,
+// no scatter: every block is written exactly once, by one slice, in a fixed
+// order, so the assembled matrix is bit-reproducible.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(192) k_assemble(int64_t nnzb, const int32_t *__restrict__ contrib_ptr,
                                                   const int32_t *__restrict__ contrib,
-                                                  const ElemRec *__restrict__ rec,
-                                                  const Node4 *__restrict__ node4, double *__restrict__ vals)
+                                                  const ElemGeom *__restrict__ geom, double *__restrict__ vals)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t k = t / 6;
@@ -277,8 +300,8 @@ __global__ void __launch_bounds__(192) k_assemble(int64_t nnzb, const int32_t *_
     const int32_t c0 = __ldg(contrib_ptr + k), c1 = __ldg(contrib_ptr + k + 1);
     for (int32_t c = c0; c < c1; ++c) {
         const int32_t code = __ldg(contrib + c);
-        Frame f; Stiff s; int32_t a, b;
-        load_elem(rec, node4, (int64_t)(code >> 2), f, s, a, b);
+        Frame f; Stiff s;
+        load_geom(geom, (int64_t)(code >> 2), f, s);
         double row[6];
         kelem_row(f, s, code & 3, r, row);
 #pragma unroll
@@ -291,11 +314,11 @@ __global__ void __launch_bounds__(192) k_assemble(int64_t nnzb, const int32_t *_
 }
 
 void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, const int32_t *contrib,
-                     const ElemRec *rec, const Node4 *node4, double *vals)
+                     const ElemGeom *geom, double *vals)
 {
     if (nnzb <= 0) return;
     const int64_t n = nnzb * 6;
-    k_assemble<<<(unsigned)((n + 191) / 192), 192, 0, st>>>(nnzb, contrib_ptr, contrib, rec, node4, vals);
+    k_assemble<<<(unsigned)((n + 191) / 192), 192, 0, st>>>(nnzb, contrib_ptr, contrib, geom, vals);
 }
 
 // ---------------------------------------------------------------------------

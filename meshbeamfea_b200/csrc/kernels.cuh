@@ -40,9 +40,11 @@ void launch_free_map(cudaStream_t st, int64_t V, int64_t F, const int32_t *fixed
                      int32_t *scratch /* >= V + V/1024 + 1 ints */);
 // K1: E x 12 x 12 element matrices (parity tap)
 void launch_kelem(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4, double *Ke);
-// K1+K2 fused: deterministic scatter-free BSR assembly
+// K1: frame + stiffness coefficients of every beam -> ElemGeom records
+void launch_elem_geom(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4, ElemGeom *geom);
+// K2: deterministic scatter-free BSR assembly from the ElemGeom records
 void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, const int32_t *contrib,
-                     const ElemRec *rec, const Node4 *node4, double *vals);
+                     const ElemGeom *geom, double *vals);
 // K5: inverse of every diagonal block; *flag |= 1 on a non-positive pivot
 void launch_block_jacobi(cudaStream_t st, int64_t nb, const int32_t *diag_idx, const double *vals,
                          double *minv, int *flag);

@@ -256,7 +256,8 @@ def test_full_size_properties_lattice_100(built):
     with ctx_for(job, tol=1e-8, max_iter=40) as c:
         st0 = c.stats()
         assert st0["n_beams"] == 2970000 and st0["n_block_rows"] == 990000
-        assert st0["nnz_blocks"] == 990000 + 2 * (2970000 - 10000)   # nb + 2*E_free
+        # nb + 2*E_free; beams with a clamped end: n^2 columns k=0->1 plus 2n(n-1) inside the clamped layer
+        assert st0["nnz_blocks"] == 990000 + 2 * (2970000 - 10000 - 19800)
         fm = c.dofmap()
         ref = np.arange(n ** 3, dtype=np.int32).reshape(n, n, n)
         exp = np.full(n ** 3, -1, np.int32)
