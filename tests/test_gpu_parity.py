@@ -310,3 +310,13 @@ def test_batched_small_meshes_block_diagonal(built):
         V = jb.nodes.shape[0]
         assert rel_l2(U[off:off + V], Uo) < TOL_U
         off += V
+
+
+def test_cpp_dropin_runs_the_reference_tester_harness(built):
+    """meshbeamfea_b200/cpp/tester_main: BeamSimulatorTester::launchRotationTest
+    [REF src/beamsimulatortester.cpp:8-41] through the C++17 drop-in header."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(HERE), "meshbeamfea_b200", "cpp", "tester_main")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "46 runs, 0 failures" in r.stdout

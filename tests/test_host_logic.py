@@ -251,3 +251,16 @@ def test_synthetic_configs_have_the_surveyed_sizes():
     assert r.nodes.shape[0] == 200 and 450 <= r.elements.shape[0] <= 700
     cases = list(syn.tester_rotation_cases())
     assert len(cases) == 45                                            # [REF src/beamsimulatortester.cpp:21-40]
+
+
+def test_cpp_dropin_header_builds_and_fails_loudly_without_gpu(built):
+    """The C++17 shim (same type/method names as the reference's beamsimulator.hpp)
+    compiles and links against libmbfea.so; without a GPU it must throw, not compute."""
+    exe = os.path.join(ROOT, "meshbeamfea_b200", "cpp", "tester_main")
+    assert os.path.exists(exe)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no usable CUDA device" in (r.stderr + r.stdout)
