@@ -71,7 +71,10 @@ typedef struct mbfea_options {
     int32_t rank;          /* vertex-block partition: this process' rank ...   */
     int32_t world;         /* ... of `world` processes (1 = single GPU)        */
     int32_t use_graph;     /* 1 = capture the PCG iteration in a CUDA graph     */
-    int32_t reserved[7];
+    int32_t comm_mode;     /* world > 1: 0 auto (NVLink peer memory when every
+                              peer is reachable, else NCCL), 1 NCCL send/recv +
+                              all-gather, 2 peer memory required               */
+    int32_t reserved[6];
 } mbfea_options;
 
 typedef struct mbfea_stats {

@@ -105,6 +105,15 @@ struct mbfea_ctx {
     // multi-GPU
     const nccl::Api *nc = nullptr;
     nccl::Comm comm = nullptr;
+    // NVLink peer-memory path (comm_mode 0/2): mailbox + ghost regions mapped through CUDA IPC
+    bool p2p = false;
+    DevBuf<Mailbox> mailbox;
+    DevBuf<PeerCtx> peerctx;
+    DevBuf<unsigned int> tickets;
+    DevBuf<double *> push_dst;
+    std::vector<Mailbox *> peer_mailbox;   // [world]; own entry = mailbox.p
+    std::vector<double *> peer_p;          // [world]; peers' p vectors (IPC mappings), own = p.p
+    unsigned long long epoch = 0;
 
     // PCG graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -186,7 +195,7 @@ void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *part
         launch_spmv_tma(c->st, spmv_tma_grid(ntiles, c->sm_count), ntiles, c->tile_row.p, c->rowptr.p, c->colidx.p,
                         c->vals.p, x, y, partial, sc);
     } else {
-        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, x, y, partial, sc);
+        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, x, y, partial, sc, nullptr);
     }
     c->launches++;
 }
@@ -216,6 +225,119 @@ void halo_exchange(mbfea_ctx *c, double *xvec)
     NK(c->nc->GroupEnd());
 }
 
+// all-gather of `bytes` (multiple of 8) host bytes per rank through NCCL (setup paths only)
+void allgather_host(mbfea_ctx *c, const void *in, void *out, size_t bytes)
+{
+    const int W = c->world();
+    DevBuf<unsigned char> din, dout;
+    CK(din.alloc(bytes));
+    CK(dout.alloc(bytes * W));
+    CK(cudaMemcpyAsync(din.p, in, bytes, cudaMemcpyHostToDevice, c->st));
+    NK(c->nc->AllGather(din.p, dout.p, bytes / 8, nccl::kInt64, c->comm, c->st));
+    CK(cudaMemcpyAsync(out, dout.p, bytes * W, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+}
+
+void close_peer_vectors(mbfea_ctx *c)
+{
+    for (size_t q = 0; q < c->peer_p.size(); ++q)
+        if ((int)q != c->opt.rank && c->peer_p[q]) cudaIpcCloseMemHandle(c->peer_p[q]);
+    c->peer_p.clear();
+}
+
+// comm_init: decide whether every peer is reachable over NVLink peer memory and map the mailboxes
+void setup_p2p_mailboxes(mbfea_ctx *c)
+{
+    const int W = c->world(), me = c->opt.rank;
+    c->p2p = false;
+    if (W <= 1 || c->opt.comm_mode == 1 || W > kMaxWorld) return;
+    // (device ordinal, pid-independent) of every rank; all must be peer-accessible from here
+    std::vector<int64_t> devs((size_t)W);
+    int64_t mine = c->device;
+    allgather_host(c, &mine, devs.data(), sizeof(int64_t));
+    int64_t ok = 1;
+    for (int q = 0; q < W; ++q) {
+        if (q == me) continue;
+        int can = 0;
+        if (devs[q] == c->device || cudaDeviceCanAccessPeer(&can, c->device, (int)devs[q]) != cudaSuccess || !can) ok = 0;
+    }
+    cudaGetLastError();
+    CK(c->mailbox.alloc(1));
+    CK(c->tickets.alloc(4));
+    CK(c->peerctx.alloc(1));
+    CK(cudaMemsetAsync(c->mailbox.p, 0, sizeof(Mailbox), c->st));
+    CK(cudaMemsetAsync(c->tickets.p, 0, 4 * sizeof(unsigned int), c->st));
+    CK(cudaStreamSynchronize(c->st));
+    struct Rec { cudaIpcMemHandle_t h; int64_t ok; };
+    static_assert(sizeof(Rec) % 8 == 0, "IPC record must be a multiple of 8 bytes");
+    Rec r;
+    std::memset(&r, 0, sizeof r);
+    if (ok && cudaIpcGetMemHandle(&r.h, c->mailbox.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    r.ok = ok;
+    std::vector<Rec> all((size_t)W);
+    allgather_host(c, &r, all.data(), sizeof(Rec));
+    for (int q = 0; q < W; ++q) ok = ok && all[q].ok;
+    c->peer_mailbox.assign((size_t)W, nullptr);
+    if (ok) {
+        for (int q = 0; q < W && ok; ++q) {
+            if (q == me) { c->peer_mailbox[q] = c->mailbox.p; continue; }
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            c->peer_mailbox[q] = static_cast<Mailbox *>(ptr);
+        }
+    }
+    // every rank must take the same path
+    int64_t okl = ok;
+    std::vector<int64_t> oks((size_t)W);
+    allgather_host(c, &okl, oks.data(), sizeof(int64_t));
+    for (int q = 0; q < W; ++q) ok = ok && oks[q];
+    c->p2p = ok != 0;
+    if (!c->p2p && c->opt.comm_mode == 2) throw CudaFail{cudaErrorPeerAccessUnsupported, "comm_mode 2: peer memory not available on every rank", __LINE__};
+    if (c->opt.verbose)
+        std::fprintf(stderr, "[mbfea] rank %d/%d: PCG data path over %s\n", me, W,
+                     c->p2p ? "NVLink peer memory (CUDA IPC mailboxes, no NCCL calls per iteration)" : "NCCL send/recv + all-gather");
+}
+
+// set_job: map the peers' p vectors and build the push list (where each owned boundary block goes)
+void setup_p2p_halo(mbfea_ctx *c)
+{
+    if (!c->p2p) return;
+    const int W = c->world(), me = c->opt.rank;
+    const int64_t nb = c->nb();
+    struct Rec { cudaIpcMemHandle_t h; int64_t nb; int64_t recv_off[kMaxWorld]; };
+    static_assert(sizeof(Rec) % 8 == 0, "IPC record must be a multiple of 8 bytes");
+    Rec r;
+    std::memset(&r, 0, sizeof r);
+    CK(cudaIpcGetMemHandle(&r.h, c->p.p));
+    r.nb = nb;
+    for (int q = 0; q < W; ++q) r.recv_off[q] = -1;
+    for (const Neighbor &n : c->plan.neighbors) r.recv_off[n.rank] = n.recv_offset;
+    std::vector<Rec> all((size_t)W);
+    allgather_host(c, &r, all.data(), sizeof(Rec));
+    c->peer_p.assign((size_t)W, nullptr);
+    for (int q = 0; q < W; ++q) {
+        if (q == me) { c->peer_p[q] = c->p.p; continue; }
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_p[q] = static_cast<double *>(ptr);
+    }
+    // what rank q receives from me occupies q's ghost slots [recv_off_q[me], ...) in my send order
+    std::vector<double *> dst(c->plan.send_rows.size());
+    for (const Neighbor &n : c->plan.neighbors)
+        for (int64_t j = 0; j < n.send_count; ++j)
+            dst[(size_t)(n.send_offset + j)] = c->peer_p[n.rank] + 6 * (all[n.rank].nb + all[n.rank].recv_off[me] + j);
+    upload(c, c->push_dst, dst);
+    PeerCtx pc;
+    std::memset(&pc, 0, sizeof pc);
+    pc.rank = me; pc.world = W; pc.n_neighbors = (int)c->plan.neighbors.size();
+    for (int j = 0; j < pc.n_neighbors; ++j) pc.neighbor[j] = c->plan.neighbors[(size_t)j].rank;
+    pc.mine = c->mailbox.p;
+    for (int q = 0; q < W; ++q) pc.peer[q] = c->peer_mailbox[(size_t)q];
+    pc.tickets = c->tickets.p;
+    CK(cudaMemcpyAsync(c->peerctx.p, &pc, sizeof pc, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+}
+
 // One PCG iteration (parity = iteration & 1) enqueued on the stream.
 // Dot products: single GPU -> consumers read the per-CTA partials directly.
 // Multi GPU -> each rank collapses its partials, all-gathers the per-rank
@@ -226,6 +348,22 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
     const int64_t nb = c->nb();
     const int W = c->world();
     const int gs = spmv_grid(c, kernel), gv = vec_grid(nb);
+    if (c->p2p) {
+        // NVLink peer-memory path: 4 kernels, no NCCL call.  The SpMV waits for the neighbours'
+        // pushed ghost blocks and its last CTA all-gathers p.Ap through the mailboxes; update and
+        // pupdate do the same for r.z / r.r; push_halo stores the new boundary blocks of p into
+        // the neighbours' ghost regions.
+        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, c->p.p, c->Ap.p, c->part_a.p, c->sc.p,
+                              c->peerctx.p);
+        launch_pcg_update(c->st, nb, parity, PartialRef{c->part_a.p, gs, 1}, c->minv.p, c->p.p, c->Ap.p, c->x.p, c->r.p,
+                          c->z.p, c->part_b.p, c->part_c.p, c->sc.p, c->peerctx.p);
+        launch_pcg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, PartialRef{c->part_c.p, gv, 1}, c->z.p,
+                           c->p.p, c->sc.p, c->peerctx.p);
+        launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst.p, c->p.p, c->sc.p,
+                         c->peerctx.p);
+        c->launches += 4;
+        return;
+    }
     halo_exchange(c, c->p.p);
     run_spmv(c, kernel, c->p.p, c->Ap.p, c->part_a.p, c->sc.p);
     PartialRef pAp{c->part_a.p, gs, 1};
@@ -236,7 +374,7 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         c->launches++;
     }
     launch_pcg_update(c->st, nb, parity, pAp, c->minv.p, c->p.p, c->Ap.p, c->x.p, c->r.p, c->z.p, c->part_b.p,
-                      c->part_c.p, c->sc.p);
+                      c->part_c.p, c->sc.p, nullptr);
     PartialRef rz{c->part_b.p, gv, 1}, rr{c->part_c.p, gv, 1};
     if (W > 1) {
         launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, c->part_c.p, c->red.p + 3, c->sc.p);
@@ -245,7 +383,7 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         rr = PartialRef{c->gath.p + W + 1, W, 2};
         c->launches++;
     }
-    launch_pcg_pupdate(c->st, nb, parity, rz, rr, c->z.p, c->p.p, c->sc.p);
+    launch_pcg_pupdate(c->st, nb, parity, rz, rr, c->z.p, c->p.p, c->sc.p, nullptr);
     c->launches += 2;
 }
 
@@ -387,6 +525,9 @@ void mbfea_destroy(mbfea_ctx *c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     drop_graph(c);
+    close_peer_vectors(c);
+    for (size_t q = 0; q < c->peer_mailbox.size(); ++q)
+        if ((int)q != c->opt.rank && c->peer_mailbox[q]) cudaIpcCloseMemHandle(c->peer_mailbox[q]);
     if (c->comm && c->nc) c->nc->CommDestroy(c->comm);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -422,6 +563,7 @@ int mbfea_comm_init(mbfea_ctx *c, const uint8_t id128[128], int32_t rank, int32_
         NK(c->nc->CommInitRank(&c->comm, world, id, rank));
         c->opt.rank = rank; c->opt.world = world;
         CK(c->gath.alloc((size_t)8 * world));
+        setup_p2p_mailboxes(c);
         return MBFEA_OK;
     });
 }
@@ -444,6 +586,13 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         drop_graph(c);
+        if (c->p2p) {
+            // peers unmap my old p before I free it (the all-gather is the rendezvous)
+            close_peer_vectors(c);
+            int64_t token = 0;
+            std::vector<int64_t> tokens((size_t)c->world());
+            allgather_host(c, &token, tokens.data(), sizeof token);
+        }
         std::memset(&c->stats, 0, sizeof c->stats);
         const double t0 = now_ms();
         c->V = V; c->E = E; c->F = F;
@@ -504,6 +653,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         c->plan.contrib_ptr.clear(); c->plan.contrib_ptr.shrink_to_fit();
         upload_forces(c, nF, f_node, f_dof, f_mag);
         CK(cudaStreamSynchronize(c->st));
+        setup_p2p_halo(c);
         c->stats.ms_h2d = now_ms() - t1;
 
         mbfea_stats &s = c->stats;
@@ -568,8 +718,9 @@ int mbfea_solve(mbfea_ctx *c)
         CK(cudaSetDevice(c->device));
         const int64_t nb = c->nb();
         const int W = c->world();
-        const int kernel = pick_spmv(c, 0);
+        const int kernel = c->p2p ? 1 : pick_spmv(c, 0);
         const int gv = vec_grid(nb);
+        c->epoch++;
         long long max_iter = c->opt.max_iter;
         if (max_iter <= 0) max_iter = std::min<long long>(20LL * 6 * std::max<int64_t>(1, c->plan.nb_global), 5000000LL);
         int check = c->opt.check_every;
@@ -589,8 +740,13 @@ int mbfea_solve(mbfea_ctx *c)
             rz = PartialRef{c->gath.p + W, W, 2};
             ff = PartialRef{c->gath.p + W + 1, W, 2};
         }
-        launch_pcg_init_finish(c->st, rz, ff, c->sc.p, c->opt.tol, max_iter);
+        launch_pcg_init_finish(c->st, rz, ff, c->sc.p, c->opt.tol, max_iter, c->epoch);
         c->launches += 2;
+        if (c->p2p) {  // ghost blocks of p for iteration 0
+            launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst.p, c->p.p, c->sc.p,
+                             c->peerctx.p);
+            c->launches++;
+        }
 
         bool use_graph = c->opt.use_graph != 0;
         if (use_graph && (c->graph_exec == nullptr || c->graph_iters != check || c->graph_kernel != kernel)) {
@@ -613,7 +769,7 @@ int mbfea_solve(mbfea_ctx *c)
             CK(e);
             c->graph_iters = check; c->graph_kernel = kernel;
         }
-        const int64_t per_iter = (W > 1) ? 6 : 3;
+        const int64_t per_iter = c->p2p ? 4 : ((W > 1) ? 6 : 3);
         for (;;) {
             if (use_graph) {
                 CK(cudaGraphLaunch(c->graph_exec, c->st));
@@ -655,6 +811,8 @@ int mbfea_solve(mbfea_ctx *c)
         if (c->opt.verbose)
             std::fprintf(stderr, "[mbfea] rank %d: PCG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d, batch %d\n",
                          c->opt.rank, (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel, check);
+        if (c->p2p && peer_timeout_flag())
+            return fail(c, MBFEA_ECUDA, "a peer rank stopped signalling during the PCG loop (NVLink mailbox wait timed out)");
         if (h.done == 3) return fail(c, MBFEA_ESINGULAR, "PCG breakdown: p.Ap <= 0 or non-finite (system not SPD: is any vertex fixed?)");
         if (h.done == 2) return fail(c, MBFEA_ENOCONV, "PCG reached max_iter before the requested tolerance");
         return MBFEA_OK;

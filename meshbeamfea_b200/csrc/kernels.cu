@@ -64,6 +64,45 @@ __device__ __forceinline__ double sum_partials(PartialRef ref, double *scratch)
     return block_sum<true>(s, scratch);
 }
 
+// ---- peer-memory signalling ---------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Bounded: a peer that never signals (a crashed rank) must not hang the GPU.  After ~10 s the
+// waiter gives up and raises *timeout_flag; the host reports it as a failed solve.
+__device__ int g_peer_timeout = 0;
+__device__ __forceinline__ void spin_until(const unsigned long long *p, unsigned long long want)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) != want) {
+        __nanosleep(40);
+        if (clock64() - t0 > 20000000000LL) { atomicExch(&g_peer_timeout, 1); break; }
+    }
+}
+// true in every thread of exactly one CTA of the grid: the last one to get here.
+// Call after the CTA's global writes; resets the ticket for the next launch.
+__device__ __forceinline__ bool last_cta_done(unsigned int *ticket)
+{
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *ticket = 0u;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last != 0;
+}
+
 __device__ __forceinline__ double2 ldg2(const double *p)
 {
     return __ldg(reinterpret_cast<const double2 *>(p));
@@ -279,46 +318,48 @@ void launch_elem_geom(cudaStream_t st, int64_t E, const ElemRec *rec, const Node
 }
 
 // ---------------------------------------------------------------------------
-// K2: one 6-lane slice per OUTPUT block, lane = row of the 6x6 block.  The
-// slice walks the block's contributor list (element, sub-block), which the
-// host sorted by ascending element index -- the order in which the reference's
-// setFromTriplets sums duplicates -- forms its row of Q^T S Q from the beam's
-// ElemGeom record (L1/L2-resident: the 6 lanes of a slice and the slices of
-// the same block row read the same records) and accumulates it.  No atomics,
-// no scatter: every block is written exactly once, by one slice, in a fixed
-// order, so the assembled matrix is bit-reproducible.
+// K2: one thread per OUTPUT block.  The thread walks the block's contributor
+// list (element, sub-block), which the host sorted by ascending element index
+// -- the order in which the reference's setFromTriplets sums duplicates --
+// forms the 6x6 sub-block Q^T S Q from the beam's 160-byte ElemGeom record
+// with every row index a compile-time constant (no divergent row dispatch)
+// and accumulates it in 36 registers.  No atomics, no scatter: every block is
+// written exactly once, by one thread, in a fixed order, so the assembled
+// matrix is bit-reproducible and bit-identical to the oracle's.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(192) k_assemble(int64_t nnzb, const int32_t *__restrict__ contrib_ptr,
+__global__ void __launch_bounds__(128) k_assemble(int64_t nnzb, const int32_t *__restrict__ contrib_ptr,
                                                   const int32_t *__restrict__ contrib,
                                                   const ElemGeom *__restrict__ geom, double *__restrict__ vals)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t k = t / 6;
-    const int r = (int)(t - k * 6);
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnzb) return;
-    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double acc[36];
+#pragma unroll
+    for (int j = 0; j < 36; ++j) acc[j] = 0.0;
     const int32_t c0 = __ldg(contrib_ptr + k), c1 = __ldg(contrib_ptr + k + 1);
     for (int32_t c = c0; c < c1; ++c) {
         const int32_t code = __ldg(contrib + c);
         Frame f; Stiff s;
         load_geom(geom, (int64_t)(code >> 2), f, s);
-        double row[6];
-        kelem_row(f, s, code & 3, r, row);
+        const int which = code & 3;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) acc[j] = ADD(acc[j], row[j]);
+        for (int r = 0; r < 6; ++r) {
+            double row[6];
+            kelem_row(f, s, which, r, row);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[6 * r + j] = ADD(acc[6 * r + j], row[j]);
+        }
     }
-    double2 *o = reinterpret_cast<double2 *>(vals + k * 36 + r * 6);
-    o[0] = make_double2(acc[0], acc[1]);
-    o[1] = make_double2(acc[2], acc[3]);
-    o[2] = make_double2(acc[4], acc[5]);
+    double2 *o = reinterpret_cast<double2 *>(vals + k * 36);
+#pragma unroll
+    for (int j = 0; j < 18; ++j) o[j] = make_double2(acc[2 * j], acc[2 * j + 1]);
 }
 
 void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, const int32_t *contrib,
                      const ElemGeom *geom, double *vals)
 {
     if (nnzb <= 0) return;
-    const int64_t n = nnzb * 6;
-    k_assemble<<<(unsigned)((n + 191) / 192), 192, 0, st>>>(nnzb, contrib_ptr, contrib, geom, vals);
+    k_assemble<<<(unsigned)((nnzb + 127) / 128), 128, 0, st>>>(nnzb, contrib_ptr, contrib, geom, vals);
 }
 
 // ---------------------------------------------------------------------------
@@ -386,10 +427,17 @@ constexpr int kSpmvThreads = kRowsPerCta * 6;
 __global__ void __launch_bounds__(kSpmvThreads) k_spmv_rowthread(
     int64_t nb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
     const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-    double *__restrict__ partial, const PcgScalars *sc)
+    double *__restrict__ partial, const PcgScalars *sc, const PeerCtx *pc)
 {
     __shared__ double red[33];
     if (sc != nullptr && sc->done != 0) return;
+    unsigned long long tag = 0;
+    if (pc != nullptr) {
+        // this iteration's ghost x-blocks were pushed into x[nb..) by the neighbours
+        tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
+        if ((int)threadIdx.x < pc->n_neighbors) spin_until(&pc->mine->halo_tag[pc->neighbor[threadIdx.x]], tag);
+        __syncthreads();
+    }
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
     double dot = 0.0;
     for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
@@ -415,6 +463,17 @@ __global__ void __launch_bounds__(kSpmvThreads) k_spmv_rowthread(
         const double s = block_sum<false>(dot, red);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
     }
+    if (pc != nullptr && partial != nullptr && last_cta_done(pc->tickets + 0)) {
+        // fused reduction + all-gather: the last CTA sums the partials in fixed order and
+        // stores p.Ap of this rank into every rank's mailbox over NVLink
+        const double s = sum_partials(PartialRef{partial, (int)gridDim.x, 1}, red);
+        if ((int)threadIdx.x < pc->world) {
+            Mailbox *m = pc->peer[threadIdx.x];
+            m->dot_val[0][pc->rank] = s;
+            __threadfence_system();
+            st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);
+        }
+    }
 }
 
 int spmv_rowthread_grid(int64_t nb)
@@ -425,9 +484,9 @@ int spmv_rowthread_grid(int64_t nb)
 
 void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx,
                            const double *vals, const double *x, double *y, double *partial,
-                           const PcgScalars *sc)
+                           const PcgScalars *sc, const PeerCtx *pc)
 {
-    k_spmv_rowthread<<<spmv_rowthread_grid(nb), kSpmvThreads, 0, st>>>(nb, rowptr, colidx, vals, x, y, partial, sc);
+    k_spmv_rowthread<<<spmv_rowthread_grid(nb), kSpmvThreads, 0, st>>>(nb, rowptr, colidx, vals, x, y, partial, sc, pc);
 }
 
 // ---------------------------------------------------------------------------
@@ -647,7 +706,7 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_init(
 }
 
 __global__ void __launch_bounds__(256) k_pcg_init_finish(PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                                                         long long max_iter)
+                                                         long long max_iter, unsigned long long epoch)
 {
     __shared__ double red[33];
     const double a = sum_partials(rz, red);
@@ -659,19 +718,32 @@ __global__ void __launch_bounds__(256) k_pcg_init_finish(PartialRef rz, PartialR
         // f == 0 -> u == 0 is the solution; a non-finite load is a breakdown
         sc->done = (b == 0.0) ? 1 : ((isfinite(a) && isfinite(b)) ? 0 : 3);
         sc->pad = 0;
+        sc->epoch = epoch;
+        sc->tag_cur = 0;
     }
 }
 
 __global__ void __launch_bounds__(kSpmvThreads) k_pcg_update(
     int64_t nb, int parity, PartialRef pAp_ref, const double *__restrict__ minv, const double *__restrict__ p,
     const double *__restrict__ Ap, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
-    double *__restrict__ part_rz, double *__restrict__ part_rr, PcgScalars *sc)
+    double *__restrict__ part_rz, double *__restrict__ part_rr, PcgScalars *sc, const PeerCtx *pc)
 {
     __shared__ double rs[kSpmvThreads];
     __shared__ double red[33];
     if (sc->done != 0) return;
-    const double pAp = sum_partials(pAp_ref, red);
-    if (blockIdx.x == 0 && threadIdx.x == 0) sc->pAp = pAp;
+    double pAp;
+    unsigned long long tag = 0;
+    if (pc != nullptr) {
+        // every rank's p.Ap arrives in my mailbox; summed in rank order => same bits on all ranks
+        tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter) + 1;
+        if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[0][threadIdx.x], tag);
+        __syncthreads();
+        pAp = 0.0;
+        for (int q = 0; q < pc->world; ++q) pAp += __ldcv(&pc->mine->dot_val[0][q]);
+    } else {
+        pAp = sum_partials(pAp_ref, red);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->pAp = pAp; sc->tag_cur = tag; }
     if (!(pAp > 0.0) || !isfinite(pAp)) return;  // breakdown: k_pcg_pupdate raises the flag
     const double alpha = sc->rz[parity] / pAp;
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
@@ -699,11 +771,22 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_update(
     const double a = block_sum<false>(rz, red);
     const double b = block_sum<false>(rr, red);
     if (threadIdx.x == 0) { part_rz[blockIdx.x] = a; part_rr[blockIdx.x] = b; }
+    if (pc != nullptr && last_cta_done(pc->tickets + 1)) {
+        const double sa = sum_partials(PartialRef{part_rz, (int)gridDim.x, 1}, red);
+        const double sb = sum_partials(PartialRef{part_rr, (int)gridDim.x, 1}, red);
+        if ((int)threadIdx.x < pc->world) {
+            Mailbox *m = pc->peer[threadIdx.x];
+            m->dot_val[1][pc->rank] = sa;
+            m->dot_val[2][pc->rank] = sb;
+            __threadfence_system();
+            st_release_sys(&m->dot_tag[1][pc->rank], tag);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kSpmvThreads) k_pcg_pupdate(
     int64_t nb, int parity, PartialRef rz_ref, PartialRef rr_ref, const double *__restrict__ z,
-    double *__restrict__ p, PcgScalars *sc)
+    double *__restrict__ p, PcgScalars *sc, const PeerCtx *pc)
 {
     __shared__ double red[33];
     if (sc->done != 0) return;
@@ -712,8 +795,20 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_pupdate(
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->done = 3;
         return;
     }
-    const double rz_new = sum_partials(rz_ref, red);
-    const double rr = sum_partials(rr_ref, red);
+    double rz_new, rr;
+    if (pc != nullptr) {
+        const unsigned long long tag = sc->tag_cur;   // written by k_pcg_update, stable here
+        if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[1][threadIdx.x], tag);
+        __syncthreads();
+        rz_new = 0.0; rr = 0.0;
+        for (int q = 0; q < pc->world; ++q) {
+            rz_new += __ldcv(&pc->mine->dot_val[1][q]);
+            rr += __ldcv(&pc->mine->dot_val[2][q]);
+        }
+    } else {
+        rz_new = sum_partials(rz_ref, red);
+        rr = sum_partials(rr_ref, red);
+    }
     const double beta = rz_new / sc->rz[parity];
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb * 6;
          j += (int64_t)gridDim.x * blockDim.x)
@@ -738,22 +833,63 @@ void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double 
 }
 
 void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                            long long max_iter)
+                            long long max_iter, unsigned long long epoch)
 {
-    k_pcg_init_finish<<<1, 256, 0, st>>>(rz, ff, sc, tol, max_iter);
+    k_pcg_init_finish<<<1, 256, 0, st>>>(rz, ff, sc, tol, max_iter, epoch);
 }
 
 void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
                        const double *p, const double *Ap, double *x, double *r, double *z,
-                       double *part_rz, double *part_rr, PcgScalars *sc)
+                       double *part_rz, double *part_rr, PcgScalars *sc, const PeerCtx *pc)
 {
-    k_pcg_update<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, pAp, minv, p, Ap, x, r, z, part_rz, part_rr, sc);
+    k_pcg_update<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, pAp, minv, p, Ap, x, r, z, part_rz, part_rr, sc, pc);
 }
 
 void launch_pcg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rz, PartialRef rr,
-                        const double *z, double *p, PcgScalars *sc)
+                        const double *z, double *p, PcgScalars *sc, const PeerCtx *pc)
 {
-    k_pcg_pupdate<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, rz, rr, z, p, sc);
+    k_pcg_pupdate<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, rz, rr, z, p, sc, pc);
+}
+
+// P2P halo exchange: every owned boundary x-block is stored straight into its
+// slot of the destination rank's ghost region (NVLink peer stores, fire and
+// forget); the last CTA then publishes the tag to every neighbour's mailbox.
+__global__ void __launch_bounds__(256) k_push_halo(int64_t n_send, const int32_t *__restrict__ send_rows,
+                                                   double *const *__restrict__ dst, const double *__restrict__ x,
+                                                   const PcgScalars *sc, const PeerCtx *pc)
+{
+    if (sc->done != 0) return;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_send * 3;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = t / 3;
+        const int j = (int)(t - s * 3) * 2;
+        const double2 v = *reinterpret_cast<const double2 *>(x + (int64_t)__ldg(send_rows + s) * 6 + j);
+        *reinterpret_cast<double2 *>(dst[s] + j) = v;
+    }
+    __threadfence_system();
+    if (last_cta_done(pc->tickets + 2)) {
+        const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
+        if ((int)threadIdx.x < pc->n_neighbors) {
+            __threadfence_system();
+            st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
+        }
+    }
+}
+
+int peer_timeout_flag()
+{
+    int v = 0;
+    cudaMemcpyFromSymbol(&v, g_peer_timeout, sizeof(int));
+    return v;
+}
+
+void launch_push_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, double *const *dst,
+                      const double *x, const PcgScalars *sc, const PeerCtx *pc)
+{
+    int64_t g = (n_send * 3 + 255) / 256;
+    if (g < 1) g = 1;
+    if (g > 148) g = 148;
+    k_push_halo<<<(unsigned)g, 256, 0, st>>>(n_send, send_rows, dst, x, sc, pc);
 }
 
 // collapse partial sums to one value each (fixed order); multi-GPU path

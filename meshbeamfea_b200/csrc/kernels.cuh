@@ -17,6 +17,27 @@ constexpr int kTmaCapBlocks = 224;  // 6x6 blocks per stage: 224*288 B = 63 KB
 constexpr int kTmaMaxRows = 32;     // block rows per tile  -> 192 consumer threads
 constexpr int kTmaStages = 3;
 
+constexpr int kMaxWorld = 16;
+
+// ---- multi-GPU over NVLink peer memory (no NCCL on the PCG data path) --------
+// One Mailbox per rank, in device memory that every peer maps through CUDA IPC.
+// Producers write values into the CONSUMER's mailbox with plain peer stores,
+// fence at system scope, then store a tag; consumers spin on their own (local)
+// mailbox with acquire loads.  tag = (solve epoch << 32) | iteration stamp.
+struct Mailbox {
+    unsigned long long halo_tag[kMaxWorld];    // [q]: rank q's boundary x-blocks have landed in my ghost region
+    unsigned long long dot_tag[2][kMaxWorld];  // [0]: p.Ap   [1]: r.z and r.r
+    double dot_val[3][kMaxWorld];              // [0] p.Ap  [1] r.z  [2] r.r   (per source rank)
+};
+
+struct PeerCtx {          // device-resident, local memory
+    int rank, world, n_neighbors, pad;
+    int neighbor[kMaxWorld];
+    Mailbox *mine;
+    Mailbox *peer[kMaxWorld];   // peer[rank] == mine
+    unsigned int *tickets;      // last-CTA-done tickets: [0] spmv [1] update [2] push_halo
+};
+
 struct PcgScalars {
     double rz[2];        // r.z, double-buffered by iteration parity
     double ff;           // f.f
@@ -27,6 +48,8 @@ struct PcgScalars {
     double tol2;         // tol^2
     int done;            // 0 running, 1 converged, 2 max_iter, 3 breakdown
     int pad;
+    unsigned long long epoch;    // solve counter (multi-GPU tags)
+    unsigned long long tag_cur;  // tag of the values produced in the current iteration
 };
 
 // where a kernel finds the partial sums of a dot product: n values, stride apart
@@ -52,7 +75,7 @@ void launch_block_jacobi(cudaStream_t st, int64_t nb, const int32_t *diag_idx, c
 int  spmv_rowthread_grid(int64_t nb);
 void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx,
                            const double *vals, const double *x, double *y, double *partial,
-                           const PcgScalars *sc);
+                           const PcgScalars *sc, const PeerCtx *pc);
 int  spmv_tma_grid(int64_t ntiles, int sm_count);
 size_t spmv_tma_smem_bytes();
 int  spmv_tma_prepare();  // opt in to the large dynamic shared memory; returns cudaError
@@ -64,12 +87,16 @@ int  vec_grid(int64_t nb);
 void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double *minv, double *x,
                      double *r, double *z, double *p, double *part_rz, double *part_ff);
 void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                            long long max_iter);
+                            long long max_iter, unsigned long long epoch);
 void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
                        const double *p, const double *Ap, double *x, double *r, double *z,
-                       double *part_rz, double *part_rr, PcgScalars *sc);
+                       double *part_rz, double *part_rr, PcgScalars *sc, const PeerCtx *pc);
 void launch_pcg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rz, PartialRef rr,
-                        const double *z, double *p, PcgScalars *sc);
+                        const double *z, double *p, PcgScalars *sc, const PeerCtx *pc);
+int peer_timeout_flag();  // 1 once any peer wait gave up (a rank died)
+// P2P halo: owned boundary x-blocks -> the neighbours' ghost slots (peer stores), then the tag
+void launch_push_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, double *const *dst,
+                      const double *x, const PcgScalars *sc, const PeerCtx *pc);
 // collapse `n` partials to out[0] in fixed order (multi-GPU path, before the all-gather)
 void launch_reduce_partials(cudaStream_t st, const double *a, int n, double *out_a, const double *b,
                             double *out_b, const PcgScalars *sc);

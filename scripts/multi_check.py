@@ -19,13 +19,14 @@ from meshbeamfea_b200 import synthetic as syn  # noqa: E402
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-uid = [mb.Context.comm_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(uid, src=0)
 
 
-def run(n, tol, use_graph=True, max_iter=0):
+def run(n, tol, use_graph=True, max_iter=0, comm_mode=0):
     job = syn.cubic_lattice(n)
-    c = mb.Context(device=local, tol=tol, verbose=(rank == 0), use_graph=use_graph, max_iter=max_iter)
+    c = mb.Context(device=local, tol=tol, verbose=(rank == 0), use_graph=use_graph, max_iter=max_iter,
+                   comm_mode=comm_mode)
+    uid = [mb.Context.comm_unique_id() if rank == 0 else None]   # one fresh NCCL id per communicator
+    dist.broadcast_object_list(uid, src=0)
     c.comm_init(uid[0], rank, world)
     c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job.beamMaterial,
               job.fixedNodes, job.nodalForces)
@@ -35,20 +36,21 @@ def run(n, tol, use_graph=True, max_iter=0):
     return job, c, dt
 
 
-job, c, dt = run(12, 1e-12)
-U, F = c.displacements(), c.edge_forces()
-if rank == 0:
-    from oracle import oracle as orc
-    from helpers import to_oracle, rel_l2
-    Uo, Fo = orc.solve(to_oracle(job))
-    print(f"[multi] world={world} lattice12: its={c.stats()['iterations']} err u={rel_l2(U, Uo):.2e} "
-          f"F={rel_l2(F, Fo):.2e}", flush=True)
-c.close()
-for graph in (True, False):
-    job, c, dt = run(int(os.environ.get("MBFEA_N", "100")), 1e-8, use_graph=graph)
+for mode in (0, 1):
+    job, c, dt = run(12, 1e-12, comm_mode=mode)
+    U, F = c.displacements(), c.edge_forces()
+    if rank == 0:
+        from oracle import oracle as orc
+        from helpers import to_oracle, rel_l2
+        Uo, Fo = orc.solve(to_oracle(job))
+        print(f"[multi] world={world} comm_mode={mode} lattice12: its={c.stats()['iterations']} "
+              f"err u={rel_l2(U, Uo):.2e} F={rel_l2(F, Fo):.2e}", flush=True)
+    c.close()
+for mode, graph in ((0, True), (0, False), (1, True)):
+    job, c, dt = run(int(os.environ.get("MBFEA_N", "100")), 1e-8, use_graph=graph, comm_mode=mode)
     st = c.stats()
     if rank == 0:
-        print(f"[multi] world={world} graph={graph} lattice: its={st['iterations']} relres={st['rel_residual']:.2e} "
+        print(f"[multi] world={world} comm_mode={mode} graph={graph} lattice: its={st['iterations']} relres={st['rel_residual']:.2e} "
               f"true={st['true_rel_residual']:.2e} pcg={st['ms_pcg']:.1f} ms "
               f"({st['ms_pcg'] / max(1, st['iterations']):.4f} ms/it) asm={st['ms_assemble']:.2f} wall={dt:.3f}s "
               f"ghosts={st['n_ghost_blocks']}", flush=True)
