@@ -188,6 +188,13 @@ int mbfea_time_spmv(mbfea_ctx *ctx, int32_t kernel /* as options.spmv_kernel */,
                     int32_t warmup, int32_t reps, double *ms_per_launch);
 int mbfea_time_assemble(mbfea_ctx *ctx, int32_t warmup, int32_t reps, double *ms_per_launch);
 
+/* Tracing (opt-in: environment MBFEA_TRACE=1 at mbfea_solve): device globaltimer
+ * stamps (ns) of the first 256 PCG iterations, *slots_per_iter (= 8) per iteration:
+ * 0 SpMV entry, 1 SpMV past the halo wait, 2 update entry, 3 update past the dot wait,
+ * 4 p-update entry, 5 p-update past the dot wait, 6 halo push entry, 7 halo push done.
+ * Slots 1,3,5,6,7 are only written on the multi-GPU peer-memory path.            */
+int mbfea_debug_trace(mbfea_ctx *ctx, uint64_t *stamps, int64_t max_iters, int64_t *slots_per_iter);
+
 /* ---- multi-GPU (one process per GPU; vertex-block partition) -------------
  * Rank 0 makes an id, the launcher broadcasts the 128 bytes (torch.distributed
  * in bench.py), every rank calls comm_init before set_job.  Collectives on the

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -34,7 +35,7 @@ double now_ms()
 template <class T>
 struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -42,14 +43,17 @@ struct DevBuf {
     void release()
     {
         if (p) cudaFree(p);
-        p = nullptr; n = 0;
+        p = nullptr; n = 0; cap = 0;
     }
+    // keeps the allocation when it is large enough (and not wastefully so): a second
+    // set_job on a same-sized mesh costs no cudaFree/cudaMalloc round trips
     cudaError_t alloc(size_t count)
     {
-        release();
         if (count == 0) count = 1;
+        if (p && cap >= count && cap <= 2 * count + 1024) { n = count; return cudaSuccess; }
+        release();
         cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
-        if (e == cudaSuccess) n = count; else p = nullptr;
+        if (e == cudaSuccess) { n = count; cap = count; } else p = nullptr;
         return e;
     }
 };
@@ -114,6 +118,7 @@ struct mbfea_ctx {
     std::vector<Mailbox *> peer_mailbox;   // [world]; own entry = mailbox.p
     std::vector<double *> peer_p;          // [world]; peers' p vectors (IPC mappings), own = p.p
     unsigned long long epoch = 0;
+    DevBuf<unsigned long long> trace;  // MBFEA_TRACE=1: globaltimer stamps of the first iterations
 
     // PCG graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -740,7 +745,13 @@ int mbfea_solve(mbfea_ctx *c)
             rz = PartialRef{c->gath.p + W, W, 2};
             ff = PartialRef{c->gath.p + W + 1, W, 2};
         }
-        launch_pcg_init_finish(c->st, rz, ff, c->sc.p, c->opt.tol, max_iter, c->epoch);
+        unsigned long long *trace = nullptr;
+        if (const char *tr = std::getenv("MBFEA_TRACE"); tr && *tr == '1') {
+            CK(c->trace.alloc((size_t)kTraceSlots * kTraceIters));
+            CK(cudaMemsetAsync(c->trace.p, 0, sizeof(unsigned long long) * kTraceSlots * kTraceIters, c->st));
+            trace = c->trace.p;
+        }
+        launch_pcg_init_finish(c->st, rz, ff, c->sc.p, c->opt.tol, max_iter, c->epoch, trace);
         c->launches += 2;
         if (c->p2p) {  // ghost blocks of p for iteration 0
             launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst.p, c->p.p, c->sc.p,
@@ -1102,6 +1113,20 @@ int mbfea_time_assemble(mbfea_ctx *c, int32_t warmup, int32_t reps, double *ms_p
         CK(cudaEventRecord(c->ev[5], c->st));
         CK(cudaStreamSynchronize(c->st));
         *ms_per_launch = (double)elapsed(c, 4, 5) / reps;
+        return MBFEA_OK;
+    });
+}
+
+// stamps[iteration][slot], kTraceSlots per iteration, ns (globaltimer); see kernels.cuh
+int mbfea_debug_trace(mbfea_ctx *c, uint64_t *stamps, int64_t max_iters, int64_t *slots_per_iter)
+{
+    if (!c || !stamps) return MBFEA_EARG;
+    if (slots_per_iter) *slots_per_iter = kTraceSlots;
+    if (!c->trace.p) return fail(c, MBFEA_ESTATE, "no trace: set MBFEA_TRACE=1 before mbfea_solve");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        const int64_t n = std::min<int64_t>(max_iters, kTraceIters);
+        CK(cudaMemcpy(stamps, c->trace.p, (size_t)n * kTraceSlots * sizeof(uint64_t), cudaMemcpyDeviceToHost));
         return MBFEA_OK;
     });
 }

@@ -86,6 +86,15 @@ __device__ __forceinline__ void spin_until(const unsigned long long *p, unsigned
         if (clock64() - t0 > 20000000000LL) { atomicExch(&g_peer_timeout, 1); break; }
     }
 }
+__device__ __forceinline__ void trace_stamp(const PcgScalars *sc, long long iter, int slot)
+{
+    if (sc != nullptr && sc->trace != nullptr && iter < kTraceIters && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sc->trace[iter * kTraceSlots + slot] = t;
+    }
+}
+
 // true in every thread of exactly one CTA of the grid: the last one to get here.
 // Call after the CTA's global writes; resets the ticket for the next launch.
 __device__ __forceinline__ bool last_cta_done(unsigned int *ticket)
@@ -431,12 +440,14 @@ __global__ void __launch_bounds__(kSpmvThreads) k_spmv_rowthread(
 {
     __shared__ double red[33];
     if (sc != nullptr && sc->done != 0) return;
+    if (sc != nullptr) trace_stamp(sc, sc->iter, 0);
     unsigned long long tag = 0;
     if (pc != nullptr) {
         // this iteration's ghost x-blocks were pushed into x[nb..) by the neighbours
         tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
         if ((int)threadIdx.x < pc->n_neighbors) spin_until(&pc->mine->halo_tag[pc->neighbor[threadIdx.x]], tag);
         __syncthreads();
+        trace_stamp(sc, sc->iter, 1);
     }
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
     double dot = 0.0;
@@ -706,7 +717,8 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_init(
 }
 
 __global__ void __launch_bounds__(256) k_pcg_init_finish(PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                                                         long long max_iter, unsigned long long epoch)
+                                                         long long max_iter, unsigned long long epoch,
+                                                         unsigned long long *trace)
 {
     __shared__ double red[33];
     const double a = sum_partials(rz, red);
@@ -720,6 +732,7 @@ __global__ void __launch_bounds__(256) k_pcg_init_finish(PartialRef rz, PartialR
         sc->pad = 0;
         sc->epoch = epoch;
         sc->tag_cur = 0;
+        sc->trace = trace;
     }
 }
 
@@ -731,6 +744,7 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_update(
     __shared__ double rs[kSpmvThreads];
     __shared__ double red[33];
     if (sc->done != 0) return;
+    trace_stamp(sc, sc->iter, 2);
     double pAp;
     unsigned long long tag = 0;
     if (pc != nullptr) {
@@ -738,6 +752,7 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_update(
         tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter) + 1;
         if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[0][threadIdx.x], tag);
         __syncthreads();
+        trace_stamp(sc, sc->iter, 3);
         pAp = 0.0;
         for (int q = 0; q < pc->world; ++q) pAp += __ldcv(&pc->mine->dot_val[0][q]);
     } else {
@@ -795,12 +810,15 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_pupdate(
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->done = 3;
         return;
     }
+    const long long it0 = sc->iter;   // only block 0 stamps, and it bumps iter after this read
+    trace_stamp(sc, it0, 4);
     double rz_new, rr;
     if (pc != nullptr) {
         const unsigned long long tag = sc->tag_cur;   // written by k_pcg_update, stable here
         if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[1][threadIdx.x], tag);
         __syncthreads();
         rz_new = 0.0; rr = 0.0;
+        trace_stamp(sc, it0, 5);
         for (int q = 0; q < pc->world; ++q) {
             rz_new += __ldcv(&pc->mine->dot_val[1][q]);
             rr += __ldcv(&pc->mine->dot_val[2][q]);
@@ -833,9 +851,9 @@ void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double 
 }
 
 void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                            long long max_iter, unsigned long long epoch)
+                            long long max_iter, unsigned long long epoch, unsigned long long *trace)
 {
-    k_pcg_init_finish<<<1, 256, 0, st>>>(rz, ff, sc, tol, max_iter, epoch);
+    k_pcg_init_finish<<<1, 256, 0, st>>>(rz, ff, sc, tol, max_iter, epoch, trace);
 }
 
 void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
@@ -859,6 +877,7 @@ __global__ void __launch_bounds__(256) k_push_halo(int64_t n_send, const int32_t
                                                    const PcgScalars *sc, const PeerCtx *pc)
 {
     if (sc->done != 0) return;
+    if (sc->iter > 0) trace_stamp(sc, sc->iter - 1, 6);
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_send * 3;
          t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = t / 3;
@@ -872,6 +891,11 @@ __global__ void __launch_bounds__(256) k_push_halo(int64_t n_send, const int32_t
         if ((int)threadIdx.x < pc->n_neighbors) {
             __threadfence_system();
             st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
+        }
+        if (sc->iter > 0 && sc->trace != nullptr && sc->iter - 1 < kTraceIters && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            sc->trace[(sc->iter - 1) * kTraceSlots + 7] = t;
         }
     }
 }

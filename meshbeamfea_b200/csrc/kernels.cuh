@@ -50,7 +50,11 @@ struct PcgScalars {
     int pad;
     unsigned long long epoch;    // solve counter (multi-GPU tags)
     unsigned long long tag_cur;  // tag of the values produced in the current iteration
+    unsigned long long *trace;   // optional: kTraceSlots globaltimer stamps per iteration (first kTraceIters)
 };
+constexpr int kTraceSlots = 8;   // 0 spmv in, 1 spmv past halo wait, 2 update in, 3 update past wait,
+                                 // 4 pupdate in, 5 pupdate past wait, 6 push in, 7 push out (last CTA)
+constexpr int kTraceIters = 256;
 
 // where a kernel finds the partial sums of a dot product: n values, stride apart
 struct PartialRef { const double *buf; int n; int stride; };
@@ -87,7 +91,7 @@ int  vec_grid(int64_t nb);
 void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double *minv, double *x,
                      double *r, double *z, double *p, double *part_rz, double *part_ff);
 void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                            long long max_iter, unsigned long long epoch);
+                            long long max_iter, unsigned long long epoch, unsigned long long *trace);
 void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
                        const double *p, const double *Ap, double *x, double *r, double *z,
                        double *part_rz, double *part_rr, PcgScalars *sc, const PeerCtx *pc);

@@ -321,6 +321,13 @@ class Context:
         U_cm = np.ascontiguousarray(np.asarray(U, np.float64).reshape(self.V, 6).T).ravel()
         self._ck(self._lib.mbfea_recover_from(self._h, ptr(U_cm, _pd)))
 
+    def trace(self, iters: int = 256) -> np.ndarray:
+        """(iters, 8) device globaltimer stamps in ns (needs MBFEA_TRACE=1 during solve)."""
+        out = np.zeros((iters, 8), np.uint64)
+        n = C.c_int64()
+        self._ck(self._lib.mbfea_debug_trace(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), iters, C.byref(n)))
+        return out
+
     def time_spmv(self, kernel: int = 0, warmup: int = 3, reps: int = 20) -> float:
         ms = C.c_double()
         self._ck(self._lib.mbfea_time_spmv(self._h, kernel, warmup, reps, C.byref(ms)))

@@ -1,0 +1,45 @@
+"""Per-phase device-timer breakdown of the PCG iteration (MBFEA_TRACE=1).
+Run directly (1 GPU) or under torchrun (N GPUs)."""
+import os
+import sys
+
+import numpy as np
+
+os.environ["MBFEA_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import meshbeamfea_b200 as mb  # noqa: E402
+from meshbeamfea_b200 import synthetic as syn  # noqa: E402
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+job = syn.cubic_lattice(int(os.environ.get("MBFEA_N", "100")))
+c = mb.Context(device=local, tol=1e-8, max_iter=300)
+if world > 1:
+    uid = [mb.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    c.comm_init(uid[0], rank, world)
+c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job.beamMaterial, job.fixedNodes, job.nodalForces)
+c.execute(allow_unconverged=True)
+t = c.trace(256).astype(np.int64)
+st = c.stats()
+sel = t[20:250]
+names = ["spmv_in", "spmv_go", "upd_in", "upd_go", "pupd_in", "pupd_go", "push_in", "push_out"]
+nxt = t[21:251, 0]
+if world > 1:
+    segs = {"spmv wait halo": sel[:, 1] - sel[:, 0], "spmv body+tail": sel[:, 2] - sel[:, 1], "update wait pAp": sel[:, 3] - sel[:, 2],
+            "update body+tail": sel[:, 4] - sel[:, 3], "pupdate wait rz": sel[:, 5] - sel[:, 4], "pupdate body+tail": sel[:, 6] - sel[:, 5],
+            "push body": sel[:, 7] - sel[:, 6], "push_out -> next spmv": nxt - sel[:, 7], "whole iteration": nxt - sel[:, 0]}
+else:
+    segs = {"spmv": sel[:, 2] - sel[:, 0], "update": sel[:, 4] - sel[:, 2], "pupdate": nxt - sel[:, 4], "whole iteration": nxt - sel[:, 0]}
+msg = [f"[trace] rank {rank}/{world}: ms/it (stats) {st['ms_pcg'] / max(1, st['iterations']):.4f}"]
+for k, v in segs.items():
+    msg.append(f"   {k:24s} median {np.median(v) / 1e3:8.2f} us   mean {np.mean(v) / 1e3:8.2f} us   max {np.max(v) / 1e3:8.2f} us")
+print("\n".join(msg), flush=True)
+c.close()
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()
