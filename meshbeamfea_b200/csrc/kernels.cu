@@ -433,7 +433,7 @@ void launch_block_jacobi(cudaStream_t st, int64_t nb, const int32_t *diag_idx, c
 constexpr int kRowsPerCta = 32;
 constexpr int kSpmvThreads = kRowsPerCta * 6;
 
-__global__ void __launch_bounds__(kSpmvThreads) k_spmv_rowthread(
+__global__ void __launch_bounds__(kSpmvThreads, 8) k_spmv_rowthread(
     int64_t nb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
     const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
     double *__restrict__ partial, const PcgScalars *sc, const PeerCtx *pc)
@@ -441,10 +441,9 @@ __global__ void __launch_bounds__(kSpmvThreads) k_spmv_rowthread(
     __shared__ double red[33];
     if (sc != nullptr && sc->done != 0) return;
     if (sc != nullptr) trace_stamp(sc, sc->iter, 0);
-    unsigned long long tag = 0;
     if (pc != nullptr) {
         // this iteration's ghost x-blocks were pushed into x[nb..) by the neighbours
-        tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
+        const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
         if ((int)threadIdx.x < pc->n_neighbors) spin_until(&pc->mine->halo_tag[pc->neighbor[threadIdx.x]], tag);
         __syncthreads();
         trace_stamp(sc, sc->iter, 1);
@@ -479,6 +478,7 @@ __global__ void __launch_bounds__(kSpmvThreads) k_spmv_rowthread(
         // stores p.Ap of this rank into every rank's mailbox over NVLink
         const double s = sum_partials(PartialRef{partial, (int)gridDim.x, 1}, red);
         if ((int)threadIdx.x < pc->world) {
+            const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
             Mailbox *m = pc->peer[threadIdx.x];
             m->dot_val[0][pc->rank] = s;
             __threadfence_system();
