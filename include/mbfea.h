@@ -74,7 +74,10 @@ typedef struct mbfea_options {
     int32_t comm_mode;     /* world > 1: 0 auto (NVLink peer memory when every
                               peer is reachable, else NCCL), 1 NCCL send/recv +
                               all-gather, 2 peer memory required               */
-    int32_t reserved[6];
+    int32_t storage;       /* solver matrix: 0 auto, 1 every off-diagonal block in
+                              its own row, 2 symmetric half (each block pair
+                              stored once, reached transposed from the other row) */
+    int32_t reserved[5];
 } mbfea_options;
 
 typedef struct mbfea_stats {

@@ -86,7 +86,8 @@ struct mbfea_ctx {
     int64_t V = 0, E = 0, F = 0;
     HostPlan plan;
     std::vector<double> props_host;
-    std::vector<int32_t> tile_row_host;
+    std::vector<int32_t> tile_row_host;    // TMA tiles over the full pattern (K, parity tap)
+    std::vector<int32_t> tile_row_s_host;  // TMA tiles over the solver format (full-row storage only)
     bool tma_ok = false;       // pattern fits the TMA tile geometry
     bool tma_prepared = false;
 
@@ -96,9 +97,11 @@ struct mbfea_ctx {
     DevBuf<ElemGeom> geom;
     DevBuf<int32_t> free_index, fixed;
     // device: pattern
-    DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, send_rows;
-    // device: matrix + vectors
-    DevBuf<double> vals, minv, f, x, r, z, p, Ap, sendbuf;
+    DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, tile_row_s, send_rows;
+    DevBuf<int32_t> uptr, ucol, usrc, lptr, lcol, lblk;   // solver format (HostPlan::uptr ...)
+    // device: matrix + vectors.  vals = assembled K (full pattern); vals_s = stored blocks of
+    // K~ = S K S^T; lfac/sinv = Cholesky factor of the diagonal blocks and its inverse
+    DevBuf<double> vals, vals_s, lfac, sinv, f, ft, x, y, rt, p, Ap, sendbuf;
     DevBuf<double> part_a, part_b, part_c, red, gath;
     DevBuf<PcgScalars> sc;
     DevBuf<int> flag;
@@ -123,7 +126,7 @@ struct mbfea_ctx {
     // PCG graph cache
     cudaGraphExec_t graph_exec = nullptr;
     int graph_iters = 0, graph_kernel = 0;
-    int64_t launches = 0;
+    int64_t launches = 0, graph_launches = 0;
 
     mbfea_stats stats{};
 
@@ -186,46 +189,73 @@ int pick_spmv(const mbfea_ctx *c, int requested)
     return k;
 }
 
-// one SpMV on the ctx stream: y = K x (x has nb + n_ghost blocks)
-void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *partial, const PcgScalars *sc)
+void prepare_tma(mbfea_ctx *c)
+{
+    if (!c->tma_prepared) {
+        CK((cudaError_t)spmv_tma_prepare());
+        c->tma_prepared = true;
+    }
+}
+
+// parity tap: y = K x with the assembled (unscaled) matrix in its full pattern
+void run_spmv_full(mbfea_ctx *c, int kernel, const double *x, double *y)
 {
     const int64_t nb = c->nb();
     if (nb <= 0) return;
     if (kernel == 2) {
-        if (!c->tma_prepared) {
-            CK((cudaError_t)spmv_tma_prepare());
-            c->tma_prepared = true;
-        }
+        prepare_tma(c);
         const int64_t ntiles = (int64_t)c->tile_row_host.size() - 1;
         launch_spmv_tma(c->st, spmv_tma_grid(ntiles, c->sm_count), ntiles, c->tile_row.p, c->rowptr.p, c->colidx.p,
-                        c->vals.p, x, y, partial, sc);
+                        c->vals.p, 0, x, y, nullptr, nullptr);
     } else {
-        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, x, y, partial, sc, nullptr);
+        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, nullptr, nullptr, nullptr, 0, x, y,
+                              nullptr, nullptr, nullptr);
+    }
+    c->launches++;
+}
+
+// the solver's SpMV: y = K~ x (unit diagonal implied; x has nb + n_ghost blocks)
+void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *partial, const PcgScalars *sc,
+              const PeerCtx *pc)
+{
+    const int64_t nb = c->nb();
+    if (nb <= 0) return;
+    if (kernel == 2 && !c->plan.sym_half && pc == nullptr) {
+        prepare_tma(c);
+        const int64_t ntiles = (int64_t)c->tile_row_s_host.size() - 1;
+        launch_spmv_tma(c->st, spmv_tma_grid(ntiles, c->sm_count), ntiles, c->tile_row_s.p, c->uptr.p, c->ucol.p,
+                        c->vals_s.p, 1, x, y, partial, sc);
+    } else {
+        const bool sym = c->plan.sym_half;
+        launch_spmv_rowthread(c->st, nb, c->uptr.p, c->ucol.p, c->vals_s.p, sym ? c->lptr.p : nullptr,
+                              sym ? c->lcol.p : nullptr, sym ? c->lblk.p : nullptr, 1, x, y, partial, sc, pc);
     }
     c->launches++;
 }
 
 int spmv_grid(const mbfea_ctx *c, int kernel)
 {
-    if (kernel == 2) return spmv_tma_grid((int64_t)c->tile_row_host.size() - 1, c->sm_count);
-    return spmv_rowthread_grid(c->nb());
+    if (kernel == 2 && !c->plan.sym_half && !c->p2p)
+        return spmv_tma_grid((int64_t)c->tile_row_s_host.size() - 1, c->sm_count);
+    return spmv_rowthread_grid(c->nb(), c->plan.sym_half);
 }
 
 // boundary x-blocks -> neighbours' ghost slots (multi-GPU only)
-void halo_exchange(mbfea_ctx *c, double *xvec)
+// `width` doubles per block row: 6 for vectors, 36 for the S factors
+void halo_exchange(mbfea_ctx *c, double *xvec, int width = 6)
 {
     if (c->world() <= 1 || c->plan.neighbors.empty()) return;
     const int64_t nb = c->nb();
-    launch_pack_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, xvec, c->sendbuf.p);
+    launch_pack_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, xvec, c->sendbuf.p, width);
     c->launches++;
     NK(c->nc->GroupStart());
     for (const Neighbor &q : c->plan.neighbors) {
         if (q.send_count)
-            NK(c->nc->Send(c->sendbuf.p + 6 * q.send_offset, (size_t)(6 * q.send_count), nccl::kFloat64, q.rank,
-                           c->comm, c->st));
+            NK(c->nc->Send(c->sendbuf.p + width * q.send_offset, (size_t)(width * q.send_count), nccl::kFloat64,
+                           q.rank, c->comm, c->st));
         if (q.recv_count)
-            NK(c->nc->Recv(xvec + 6 * (nb + q.recv_offset), (size_t)(6 * q.recv_count), nccl::kFloat64, q.rank,
-                           c->comm, c->st));
+            NK(c->nc->Recv(xvec + width * (nb + q.recv_offset), (size_t)(width * q.recv_count), nccl::kFloat64,
+                           q.rank, c->comm, c->st));
     }
     NK(c->nc->GroupEnd());
 }
@@ -343,34 +373,30 @@ void setup_p2p_halo(mbfea_ctx *c)
     CK(cudaStreamSynchronize(c->st));
 }
 
-// One PCG iteration (parity = iteration & 1) enqueued on the stream.
+// One CG iteration (parity = iteration & 1) enqueued on the stream.
 // Dot products: single GPU -> consumers read the per-CTA partials directly.
-// Multi GPU -> each rank collapses its partials, all-gathers the per-rank
-// values, and every rank sums the W entries in rank order (identical bits on
-// every rank, so all ranks take the same stop decision).
+// NVLink peer-memory path -> 4 kernels, no NCCL call: the SpMV waits for the neighbours' pushed
+// ghost blocks and its last CTA all-gathers p.Ap through the mailboxes; update does the same for
+// rho; push_halo stores the new boundary blocks of p into the neighbours' ghost regions.
+// NCCL path -> each rank collapses its partials, all-gathers the per-rank values, and every rank
+// sums the W entries in rank order (identical bits on every rank => same stop decision).
 void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
 {
     const int64_t nb = c->nb();
     const int W = c->world();
-    const int gs = spmv_grid(c, kernel), gv = vec_grid(nb);
+    const int gs = spmv_grid(c, kernel), gv = cg_vec_grid(nb);
     if (c->p2p) {
-        // NVLink peer-memory path: 4 kernels, no NCCL call.  The SpMV waits for the neighbours'
-        // pushed ghost blocks and its last CTA all-gathers p.Ap through the mailboxes; update and
-        // pupdate do the same for r.z / r.r; push_halo stores the new boundary blocks of p into
-        // the neighbours' ghost regions.
-        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, c->p.p, c->Ap.p, c->part_a.p, c->sc.p,
-                              c->peerctx.p);
-        launch_pcg_update(c->st, nb, parity, PartialRef{c->part_a.p, gs, 1}, c->minv.p, c->p.p, c->Ap.p, c->x.p, c->r.p,
-                          c->z.p, c->part_b.p, c->part_c.p, c->sc.p, c->peerctx.p);
-        launch_pcg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, PartialRef{c->part_c.p, gv, 1}, c->z.p,
-                           c->p.p, c->sc.p, c->peerctx.p);
+        run_spmv(c, 1, c->p.p, c->Ap.p, c->part_a.p, c->sc.p, c->peerctx.p);
+        launch_cg_update(c->st, nb, parity, PartialRef{c->part_a.p, gs, 1}, c->p.p, c->Ap.p, c->y.p, c->rt.p,
+                         c->part_b.p, c->sc.p, c->peerctx.p);
+        launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, c->rt.p, c->p.p, c->sc.p, c->peerctx.p);
         launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst.p, c->p.p, c->sc.p,
                          c->peerctx.p);
-        c->launches += 4;
+        c->launches += 3;
         return;
     }
     halo_exchange(c, c->p.p);
-    run_spmv(c, kernel, c->p.p, c->Ap.p, c->part_a.p, c->sc.p);
+    run_spmv(c, kernel, c->p.p, c->Ap.p, c->part_a.p, c->sc.p, nullptr);
     PartialRef pAp{c->part_a.p, gs, 1};
     if (W > 1) {
         launch_reduce_partials(c->st, c->part_a.p, gs, c->red.p, nullptr, nullptr, c->sc.p);
@@ -378,17 +404,39 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         pAp = PartialRef{c->gath.p, W, 1};
         c->launches++;
     }
-    launch_pcg_update(c->st, nb, parity, pAp, c->minv.p, c->p.p, c->Ap.p, c->x.p, c->r.p, c->z.p, c->part_b.p,
-                      c->part_c.p, c->sc.p, nullptr);
-    PartialRef rz{c->part_b.p, gv, 1}, rr{c->part_c.p, gv, 1};
+    launch_cg_update(c->st, nb, parity, pAp, c->p.p, c->Ap.p, c->y.p, c->rt.p, c->part_b.p, c->sc.p, nullptr);
+    PartialRef rho{c->part_b.p, gv, 1};
     if (W > 1) {
-        launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, c->part_c.p, c->red.p + 3, c->sc.p);
-        NK(c->nc->AllGather(c->red.p + 2, c->gath.p + W, 2, nccl::kFloat64, c->comm, c->st));
-        rz = PartialRef{c->gath.p + W, W, 2};
-        rr = PartialRef{c->gath.p + W + 1, W, 2};
+        launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, nullptr, nullptr, c->sc.p);
+        NK(c->nc->AllGather(c->red.p + 2, c->gath.p + W, 1, nccl::kFloat64, c->comm, c->st));
+        rho = PartialRef{c->gath.p + W, W, 1};
         c->launches++;
     }
-    launch_pcg_pupdate(c->st, nb, parity, rz, rr, c->z.p, c->p.p, c->sc.p, nullptr);
+    launch_cg_pupdate(c->st, nb, parity, rho, c->rt.p, c->p.p, c->sc.p, nullptr);
+    c->launches += 2;
+}
+
+// Once per batch: the unscaled residual norm ||L r~||^2 and the stop test (never skipped, so
+// sc->rr is current when the loop ends).
+void enqueue_check(mbfea_ctx *c)
+{
+    const int64_t nb = c->nb();
+    const int W = c->world();
+    const int gv = vec_grid(nb);
+    if (c->p2p) {
+        launch_cg_check(c->st, nb, c->lfac.p, c->rt.p, nullptr, c->part_a.p, c->sc.p, c->peerctx.p);
+        launch_cg_check_finish(c->st, PartialRef{c->part_a.p, gv, 1}, c->sc.p, c->peerctx.p);
+    } else {
+        launch_cg_check(c->st, nb, c->lfac.p, c->rt.p, nullptr, c->part_a.p, c->sc.p, nullptr);
+        PartialRef rr{c->part_a.p, gv, 1};
+        if (W > 1) {
+            launch_reduce_partials(c->st, c->part_a.p, gv, c->red.p + 4, nullptr, nullptr, nullptr);
+            NK(c->nc->AllGather(c->red.p + 4, c->gath.p + 2 * W, 1, nccl::kFloat64, c->comm, c->st));
+            rr = PartialRef{c->gath.p + 2 * W, W, 1};
+            c->launches++;
+        }
+        launch_cg_check_finish(c->st, rr, c->sc.p, nullptr);
+    }
     c->launches += 2;
 }
 
@@ -399,11 +447,15 @@ void do_assemble(mbfea_ctx *c)
     c->launches += 2;
 }
 
+// K5: block-Jacobi as a symmetric scaling: factor the diagonal blocks, fetch the ghost rows'
+// factors (multi-GPU, once), and form the stored blocks of K~ = S K S^T.
 void do_precond(mbfea_ctx *c)
 {
     CK(cudaMemsetAsync(c->flag.p, 0, sizeof(int), c->st));
-    launch_block_jacobi(c->st, c->nb(), c->diag_idx.p, c->vals.p, c->minv.p, c->flag.p);
-    c->launches++;
+    launch_block_chol(c->st, c->nb(), c->diag_idx.p, c->vals.p, c->lfac.p, c->sinv.p, c->flag.p);
+    halo_exchange(c, c->sinv.p, 36);
+    launch_scale_blocks(c->st, c->nb(), c->uptr.p, c->ucol.p, c->usrc.p, c->vals.p, c->sinv.p, c->vals_s.p);
+    c->launches += 2;
 }
 
 float elapsed(mbfea_ctx *c, int a, int b)
@@ -604,7 +656,12 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         c->props_host.resize((size_t)4 * E);
         derive_props(E, dims_bh, mat_nuE, c->props_host.data());
         build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan);
+        // solver format: symmetric-half storage unless full rows are asked for (the TMA kernel
+        // streams whole rows and has no transposed-reference path)
+        const bool half = c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2);
+        build_solver_format(c->plan, half);
         build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
+        build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
         c->tma_ok = true;
         for (size_t t = 0; t + 1 < c->tile_row_host.size(); ++t)
             if (c->plan.rowptr[c->tile_row_host[t + 1]] - c->plan.rowptr[c->tile_row_host[t]] > kTmaCapBlocks)
@@ -638,14 +695,24 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         upload(c, c->contrib_ptr, c->plan.contrib_ptr);
         upload(c, c->contrib, c->plan.contrib);
         upload(c, c->tile_row, c->tile_row_host);
+        upload(c, c->tile_row_s, c->tile_row_s_host);
+        upload(c, c->uptr, c->plan.uptr);
+        upload(c, c->ucol, c->plan.ucol);
+        upload(c, c->usrc, c->plan.usrc);
+        upload(c, c->lptr, c->plan.lptr);
+        upload(c, c->lcol, c->plan.lcol);
+        upload(c, c->lblk, c->plan.lblk);
         upload(c, c->send_rows, c->plan.send_rows);
-        CK(c->sendbuf.alloc((size_t)6 * c->plan.send_rows.size()));
+        CK(c->sendbuf.alloc((size_t)36 * c->plan.send_rows.size()));
         CK(c->vals.alloc((size_t)nnzb * 36));
-        CK(c->minv.alloc((size_t)nb * 36));
+        CK(c->vals_s.alloc((size_t)c->plan.ucol.size() * 36));
+        CK(c->lfac.alloc((size_t)nb * 36));
+        CK(c->sinv.alloc((size_t)(nb + ng) * 36));
         CK(c->f.alloc((size_t)6 * nb));
         CK(c->x.alloc((size_t)6 * nb));
-        CK(c->r.alloc((size_t)6 * nb));
-        CK(c->z.alloc((size_t)6 * nb));
+        CK(c->y.alloc((size_t)6 * nb));
+        CK(c->rt.alloc((size_t)6 * nb));
+        CK(c->ft.alloc((size_t)6 * nb));
         CK(c->Ap.alloc((size_t)6 * nb));
         CK(c->p.alloc((size_t)6 * (nb + ng)));
         CK(cudaMemsetAsync(c->p.p, 0, (size_t)std::max<int64_t>(1, 6 * (nb + ng)) * sizeof(double), c->st));
@@ -667,8 +734,11 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         s.nnz_blocks = nnzb; s.n_ghost_blocks = ng;
         // algorithmic bytes: SpMV 292/block + 100/row; PCG iteration
         // adds 10 vector passes (48 B/row each) + the 288 B block-Jacobi inverse
-        s.bytes_spmv = 292.0 * (double)nnzb + 100.0 * (double)nb;
-        s.bytes_pcg_iter = s.bytes_spmv + 768.0 * (double)nb;
+        // algorithmic bytes: the solver SpMV streams 288 B + a 4 B column id per STORED
+        // block, 8 B per transposed reference, and per row 48 B x + 48 B y + two 4 B row pointers;
+        // a CG iteration adds 9 vector passes of 48 B per row
+        s.bytes_spmv = 292.0 * (double)c->plan.ucol.size() + 8.0 * (double)c->plan.lcol.size() + 104.0 * (double)nb;
+        s.bytes_pcg_iter = s.bytes_spmv + 432.0 * (double)nb;
         s.bytes_assemble = 112.0 * (double)E + 288.0 * (double)nnzb;
         s.bytes_recover = 208.0 * (double)E + 96.0 * (double)E;
         c->have_job = true;
@@ -730,19 +800,20 @@ int mbfea_solve(mbfea_ctx *c)
         if (max_iter <= 0) max_iter = std::min<long long>(20LL * 6 * std::max<int64_t>(1, c->plan.nb_global), 5000000LL);
         int check = c->opt.check_every;
         if (check <= 0) {
-            // aim at ~5 ms of device work between host polls
-            const double est_us = c->stats.bytes_pcg_iter / 4.0e6 + 8.0;
-            check = (int)std::min(200.0, std::max(2.0, 5000.0 / est_us));
+            // aim at ~4 ms of device work between residual checks / host polls
+            const double est_us = c->stats.bytes_pcg_iter / 5.0e6 + 8.0;
+            check = (int)std::min(32.0, std::max(2.0, 4000.0 / est_us));
         }
         check += check & 1;  // parity alternates: keep batches even
 
         CK(cudaEventRecord(c->ev[0], c->st));
-        launch_pcg_init(c->st, nb, c->f.p, c->minv.p, c->x.p, c->r.p, c->z.p, c->p.p, c->part_b.p, c->part_c.p);
-        PartialRef rz{c->part_b.p, gv, 1}, ff{c->part_c.p, gv, 1};
+        // f~ = S f, y = 0, r~ = p = f~  (CG on K~ = S K S^T  ==  block-Jacobi PCG on K)
+        launch_cg_init(c->st, nb, c->f.p, c->sinv.p, c->y.p, c->rt.p, c->ft.p, c->p.p, c->part_b.p, c->part_c.p);
+        PartialRef rho{c->part_b.p, gv, 1}, ff{c->part_c.p, gv, 1};
         if (W > 1) {
             launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, c->part_c.p, c->red.p + 3, nullptr);
             NK(c->nc->AllGather(c->red.p + 2, c->gath.p + W, 2, nccl::kFloat64, c->comm, c->st));
-            rz = PartialRef{c->gath.p + W, W, 2};
+            rho = PartialRef{c->gath.p + W, W, 2};
             ff = PartialRef{c->gath.p + W + 1, W, 2};
         }
         unsigned long long *trace = nullptr;
@@ -751,7 +822,7 @@ int mbfea_solve(mbfea_ctx *c)
             CK(cudaMemsetAsync(c->trace.p, 0, sizeof(unsigned long long) * kTraceSlots * kTraceIters, c->st));
             trace = c->trace.p;
         }
-        launch_pcg_init_finish(c->st, rz, ff, c->sc.p, c->opt.tol, max_iter, c->epoch, trace);
+        launch_cg_init_finish(c->st, rho, ff, c->sc.p, c->opt.tol, max_iter, c->epoch, trace);
         c->launches += 2;
         if (c->p2p) {  // ghost blocks of p for iteration 0
             launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst.p, c->p.p, c->sc.p,
@@ -762,44 +833,47 @@ int mbfea_solve(mbfea_ctx *c)
         bool use_graph = c->opt.use_graph != 0;
         if (use_graph && (c->graph_exec == nullptr || c->graph_iters != check || c->graph_kernel != kernel)) {
             drop_graph(c);
-            if (kernel == 2 && !c->tma_prepared) { CK((cudaError_t)spmv_tma_prepare()); c->tma_prepared = true; }
+            if (kernel == 2) prepare_tma(c);
             cudaGraph_t g = nullptr;
             const int64_t l0 = c->launches;
             CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
             try {
                 for (int i = 0; i < check; ++i) enqueue_iteration(c, kernel, i & 1);
+                enqueue_check(c);
             } catch (...) {
                 cudaStreamEndCapture(c->st, &g);
                 if (g) cudaGraphDestroy(g);
                 throw;
             }
             CK(cudaStreamEndCapture(c->st, &g));
+            c->graph_launches = c->launches - l0;
             c->launches = l0;
             cudaError_t e = cudaGraphInstantiate(&c->graph_exec, g, 0);
             cudaGraphDestroy(g);
             CK(e);
             c->graph_iters = check; c->graph_kernel = kernel;
         }
-        const int64_t per_iter = c->p2p ? 4 : ((W > 1) ? 6 : 3);
         for (;;) {
             if (use_graph) {
                 CK(cudaGraphLaunch(c->graph_exec, c->st));
-                c->launches += per_iter * check;
+                c->launches += c->graph_launches;
             } else {
                 for (int i = 0; i < check; ++i) enqueue_iteration(c, kernel, i & 1);
+                enqueue_check(c);
             }
             CK(cudaMemcpyAsync(c->sc_host, c->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->st));
             CK(cudaStreamSynchronize(c->st));
             if (c->sc_host->done != 0) break;
         }
+        launch_unscale(c->st, nb, c->sinv.p, c->y.p, c->x.p);   // x = S^T y
         CK(cudaEventRecord(c->ev[1], c->st));
-        // true residual ||f - K x|| / ||f||, recomputed
-        CK(cudaMemcpyAsync(c->p.p, c->x.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        // true residual ||f - K x|| / ||f|| = ||L (f~ - K~ y)|| / ||f||, recomputed from y
+        CK(cudaMemcpyAsync(c->p.p, c->y.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
         halo_exchange(c, c->p.p);
-        run_spmv(c, kernel, c->p.p, c->Ap.p, nullptr, nullptr);
-        launch_residual(c->st, nb, c->f.p, c->Ap.p, c->part_a.p);
+        run_spmv(c, kernel, c->p.p, c->Ap.p, nullptr, nullptr, nullptr);
+        launch_cg_check(c->st, nb, c->lfac.p, c->ft.p, c->Ap.p, c->part_a.p, nullptr, nullptr);
         launch_reduce_partials(c->st, c->part_a.p, gv, c->red.p, nullptr, nullptr, nullptr);
-        c->launches += 2;
+        c->launches += 3;
         double rr_true = 0.0;
         if (W > 1) {
             NK(c->nc->AllGather(c->red.p, c->gath.p, 1, nccl::kFloat64, c->comm, c->st));
@@ -817,15 +891,20 @@ int mbfea_solve(mbfea_ctx *c)
         s.iterations = h.iter;
         s.rel_residual = h.ff > 0 ? std::sqrt(h.rr / h.ff) : 0.0;
         s.true_rel_residual = h.ff > 0 ? std::sqrt(rr_true / h.ff) : 0.0;
-        s.converged = h.done == 1;
+        // done == 1 is either the residual test or exact convergence (rho below FP64 resolution):
+        // either way the recurrence residual at exit decides
+        const bool met = h.ff == 0.0 || h.rr <= h.tol2 * h.ff;
+        s.converged = (h.done == 1 && met) ? 1 : 0;
         c->solved = true; c->recovered = false;
         if (c->opt.verbose)
-            std::fprintf(stderr, "[mbfea] rank %d: PCG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d, batch %d\n",
-                         c->opt.rank, (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel, check);
+            std::fprintf(stderr, "[mbfea] rank %d: CG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d (%s storage), batch %d\n",
+                         c->opt.rank, (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel,
+                         c->plan.sym_half ? "symmetric-half" : "full-row", check);
         if (c->p2p && peer_timeout_flag())
             return fail(c, MBFEA_ECUDA, "a peer rank stopped signalling during the PCG loop (NVLink mailbox wait timed out)");
-        if (h.done == 3) return fail(c, MBFEA_ESINGULAR, "PCG breakdown: p.Ap <= 0 or non-finite (system not SPD: is any vertex fixed?)");
-        if (h.done == 2) return fail(c, MBFEA_ENOCONV, "PCG reached max_iter before the requested tolerance");
+        if (h.done == 3) return fail(c, MBFEA_ESINGULAR, "CG breakdown: p.Ap <= 0 or non-finite (system not SPD: is any vertex fixed?)");
+        if (h.done == 2) return fail(c, MBFEA_ENOCONV, "CG reached max_iter before the requested tolerance");
+        if (!s.converged) return fail(c, MBFEA_ENOCONV, "CG stagnated above the requested tolerance (residual at FP64 resolution)");
         return MBFEA_OK;
     });
 }
@@ -1054,7 +1133,7 @@ int mbfea_spmv_with(mbfea_ctx *c, int32_t kernel, const double *x, double *y)
         CK(cudaSetDevice(c->device));
         const size_t n = (size_t)6 * c->nb() * sizeof(double);
         CK(cudaMemcpyAsync(c->p.p, x, n, cudaMemcpyHostToDevice, c->st));
-        run_spmv(c, pick_spmv(c, kernel), c->p.p, c->Ap.p, nullptr, nullptr);
+        run_spmv_full(c, pick_spmv(c, kernel), c->p.p, c->Ap.p);
         CK(cudaMemcpyAsync(y, c->Ap.p, n, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         c->solved = c->recovered = false;  // p / Ap were overwritten
@@ -1086,13 +1165,15 @@ int mbfea_time_spmv(mbfea_ctx *c, int32_t kernel, int32_t warmup, int32_t reps, 
     if (!ms_per_launch || reps <= 0) return fail(c, MBFEA_EARG, "bad arguments");
     if (!c->assembled) return fail(c, MBFEA_ESTATE, "time_spmv before assemble");
     if (kernel == 2 && !c->tma_ok) return fail(c, MBFEA_EARG, "pattern has a row longer than a TMA stage");
+    if (kernel == 2 && c->plan.sym_half)
+        return fail(c, MBFEA_EARG, "the TMA kernel streams whole rows: create the context with options.storage = 1 (or spmv_kernel = 2)");
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         const int k = pick_spmv(c, kernel);
         launch_fill(c->st, 6 * (c->nb() + c->ng()), c->p.p, 0.5, 0.03125, 17);
-        for (int i = 0; i < warmup; ++i) run_spmv(c, k, c->p.p, c->Ap.p, c->part_a.p, nullptr);
+        for (int i = 0; i < warmup; ++i) run_spmv(c, k, c->p.p, c->Ap.p, c->part_a.p, nullptr, nullptr);
         CK(cudaEventRecord(c->ev[4], c->st));
-        for (int i = 0; i < reps; ++i) run_spmv(c, k, c->p.p, c->Ap.p, c->part_a.p, nullptr);
+        for (int i = 0; i < reps; ++i) run_spmv(c, k, c->p.p, c->Ap.p, c->part_a.p, nullptr, nullptr);
         CK(cudaEventRecord(c->ev[5], c->st));
         CK(cudaStreamSynchronize(c->st));
         *ms_per_launch = (double)elapsed(c, 4, 5) / reps;

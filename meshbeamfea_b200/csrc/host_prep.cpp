@@ -310,6 +310,50 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     }
 }
 
+void build_solver_format(HostPlan &P, bool half)
+{
+    const int64_t nb = P.nb();
+    P.sym_half = half;
+    P.uptr.assign((size_t)nb + 1, 0);
+    P.lptr.assign((size_t)nb + 1, 0);
+    // pass 1: counts.  (r,c) is stored in row r unless it is a local column below the
+    // diagonal under half storage; then it is reached through row c's block (c,r).
+    for (int64_t r = 0; r < nb; ++r) {
+        int32_t nu = 0, nl = 0;
+        for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
+            const int32_t c = P.colidx[k];
+            if (c == r) continue;
+            if (half && c < nb && c < r) ++nl; else ++nu;
+        }
+        P.uptr[r + 1] = P.uptr[r] + nu;
+        P.lptr[r + 1] = P.lptr[r] + nl;
+    }
+    P.ucol.resize((size_t)P.uptr[nb]);
+    P.usrc.resize((size_t)P.uptr[nb]);
+    P.lcol.resize((size_t)P.lptr[nb]);
+    P.lblk.resize((size_t)P.lptr[nb]);
+    parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t r = lo; r < hi; ++r) {
+            int32_t u = P.uptr[r];
+            for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
+                const int32_t c = P.colidx[k];
+                if (c == r) continue;
+                if (half && c < nb && c < r) continue;
+                P.ucol[u] = c; P.usrc[u] = k; ++u;
+            }
+        }
+    });
+    if (!half) return;
+    // pass 2: transposed references, rows c ascending => each row's list is ascending in c
+    std::vector<int32_t> cur(P.lptr.begin(), P.lptr.end() - 1);
+    for (int64_t c = 0; c < nb; ++c)
+        for (int32_t b = P.uptr[c]; b < P.uptr[c + 1]; ++b) {
+            const int32_t r = P.ucol[b];
+            if (r >= nb) continue;  // ghost column: the owner of r stores its own copy
+            P.lcol[cur[r]] = (int32_t)c; P.lblk[cur[r]] = b; ++cur[r];
+        }
+}
+
 void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
                  std::vector<int32_t> &tile_row)
 {

@@ -372,70 +372,168 @@ void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, 
 }
 
 // ---------------------------------------------------------------------------
-// K5: 6x6 block-Jacobi.  One thread per block row: Gauss-Jordan on the SPD
-// diagonal block (no pivoting needed); a non-positive pivot raises *flag.
+// K5: block-Jacobi as a symmetric scaling.  One thread per block row factors the
+// SPD diagonal block D_r = L_r L_r^T (Cholesky, registers) and stores L_r and
+// S_r = L_r^{-1}.  The solver then runs plain CG on K~ = S K S^T, whose diagonal
+// blocks are the identity -- the same iterates as block-Jacobi PCG on K, without
+// reading a 288-byte inverse per row per iteration and without a z vector.
+// A non-positive pivot raises *flag (isolated vertex, zero-stiffness beam...).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_block_jacobi(int64_t nb, const int32_t *__restrict__ diag_idx,
-                                                      const double *__restrict__ vals,
-                                                      double *__restrict__ minv, int *flag)
+__global__ void __launch_bounds__(128) k_block_chol(int64_t nb, const int32_t *__restrict__ diag_idx,
+                                                    const double *__restrict__ vals, double *__restrict__ lfac,
+                                                    double *__restrict__ sinv, int *flag)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
     const double *D = vals + (int64_t)__ldg(diag_idx + r) * 36;
-    double M[6][6], I[6][6];
+    double L[6][6], S[6][6];
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j < 6; j += 2) {
             const double2 v = ldg2(D + 6 * i + j);
-            M[i][j] = v.x; M[i][j + 1] = v.y;
-            I[i][j] = (i == j) ? 1.0 : 0.0; I[i][j + 1] = (i == j + 1) ? 1.0 : 0.0;
+            L[i][j] = v.x; L[i][j + 1] = v.y;
         }
     bool bad = false;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const double piv = M[k][k];
-        if (!(piv > 0.0)) bad = true;
-        const double p = 1.0 / piv;
+    for (int j = 0; j < 6; ++j) {
+        double d = L[j][j];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) { M[k][j] *= p; I[k][j] *= p; }
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+        const double ljj = sqrt(d), inv = 1.0 / ljj;
+        L[j][j] = ljj;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            if (i == k) continue;
-            const double f = M[i][k];
+        for (int i = j + 1; i < 6; ++i) {
+            double v = L[i][j];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) { M[i][j] -= f * M[k][j]; I[i][j] -= f * I[k][j]; }
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+            L[i][j] = v * inv;
         }
     }
-    if (bad) atomicOr(flag, 1);
-    double2 *o = reinterpret_cast<double2 *>(minv + r * 36);
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; j += 2) o[3 * i + j / 2] = make_double2(I[i][j], I[i][j + 1]);
+        for (int j = i + 1; j < 6; ++j) L[i][j] = 0.0;
+    // S = L^{-1}, lower triangular, column by column
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i < j) { S[i][j] = 0.0; continue; }
+            if (i == j) { S[i][j] = 1.0 / L[j][j]; continue; }
+            double v = 0.0;
+#pragma unroll
+            for (int k = j; k < i; ++k) v -= L[i][k] * S[k][j];
+            S[i][j] = v / L[i][i];
+        }
+    }
+    if (bad) atomicOr(flag, 1);
+    double2 *ol = reinterpret_cast<double2 *>(lfac + r * 36), *os = reinterpret_cast<double2 *>(sinv + r * 36);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            ol[3 * i + j / 2] = make_double2(L[i][j], L[i][j + 1]);
+            os[3 * i + j / 2] = make_double2(S[i][j], S[i][j + 1]);
+        }
 }
 
-void launch_block_jacobi(cudaStream_t st, int64_t nb, const int32_t *diag_idx, const double *vals,
-                         double *minv, int *flag)
+void launch_block_chol(cudaStream_t st, int64_t nb, const int32_t *diag_idx, const double *vals, double *lfac,
+                       double *sinv, int *flag)
 {
     if (nb <= 0) return;
-    k_block_jacobi<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, diag_idx, vals, minv, flag);
+    k_block_chol<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, diag_idx, vals, lfac, sinv, flag);
+}
+
+// K~_rc = S_r K_rc S_c^T for every block the solver format stores (one thread per block
+// row; sinv holds the owned rows followed by the ghost rows).
+__global__ void __launch_bounds__(128) k_scale_blocks(int64_t nb, const int32_t *__restrict__ uptr,
+                                                      const int32_t *__restrict__ ucol,
+                                                      const int32_t *__restrict__ usrc,
+                                                      const double *__restrict__ vals,
+                                                      const double *__restrict__ sinv, double *__restrict__ vals_s)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nb) return;
+    double Sr[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            const double2 v = ldg2(sinv + r * 36 + 6 * i + j);
+            Sr[i][j] = v.x; Sr[i][j + 1] = v.y;
+        }
+    for (int32_t b = __ldg(uptr + r); b < __ldg(uptr + r + 1); ++b) {
+        const double *K = vals + (int64_t)__ldg(usrc + b) * 36;
+        const double *Sc = sinv + (int64_t)__ldg(ucol + b) * 36;
+        double T[6][6];
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            double2 col[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) col[k] = ldg2(K + 6 * k + j);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double a = 0.0, c = 0.0;
+#pragma unroll
+                for (int k = 0; k <= i; ++k) { a = fma(Sr[i][k], col[k].x, a); c = fma(Sr[i][k], col[k].y, c); }
+                T[i][j] = a; T[i][j + 1] = c;
+            }
+        }
+        double out[6][6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double sc[6];
+#pragma unroll
+            for (int k = 0; k < 6; k += 2) { const double2 v = ldg2(Sc + 6 * j + k); sc[k] = v.x; sc[k + 1] = v.y; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k <= j; ++k) a = fma(T[i][k], sc[k], a);
+                out[i][j] = a;
+            }
+        }
+        double2 *o = reinterpret_cast<double2 *>(vals_s + (int64_t)b * 36);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) o[3 * i + j / 2] = make_double2(out[i][j], out[i][j + 1]);
+    }
+}
+
+void launch_scale_blocks(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const int32_t *usrc,
+                         const double *vals, const double *sinv, double *vals_s)
+{
+    if (nb <= 0) return;
+    k_scale_blocks<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, uptr, ucol, usrc, vals, sinv, vals_s);
 }
 
 // ---------------------------------------------------------------------------
 // K4 (a): row-thread SpMV.  192 threads = 32 block rows x 6 scalar rows; a
-// thread owns one scalar row and streams its 48-byte slice of every block in
-// the row (3 x LDG.128), gathering the 48-byte x-block through the read-only
+// thread owns one scalar row and streams its 48-byte slice of every block its
+// row stores (3 x LDG.128), gathering the 48-byte x-block through the read-only
 // path.  Consecutive threads read consecutive 48-byte slices, so a warp's
 // three loads together cover a contiguous span of the value stream.
+//   identity != 0 : a unit diagonal block is implied (scaled solver matrix)
+//   lptr != null  : symmetric-half storage -- the row's remaining neighbours are
+//                   TRANSPOSED references into other rows' stored blocks (thread
+//                   i reads column i of the block: the 6 threads of a row
+//                   together read the whole 288-byte block, which the owning
+//                   row streamed from HBM moments before/after => L2 hit).
 // Epilogue: partial[blockIdx] = sum over the CTA's rows of x_r . y_r.
+// Multi-GPU (pc != null): waits for the neighbours' pushed ghost blocks first,
+// and the last CTA all-gathers the rank's p.Ap through the NVLink mailboxes.
 // ---------------------------------------------------------------------------
 constexpr int kRowsPerCta = 32;
 constexpr int kSpmvThreads = kRowsPerCta * 6;
 
-__global__ void __launch_bounds__(kSpmvThreads, 8) k_spmv_rowthread(
-    int64_t nb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-    const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+template <bool SYM>
+__global__ void __launch_bounds__(kSpmvThreads, SYM ? 7 : 8) k_spmv_rowthread(
+    int64_t nb, const int32_t *__restrict__ uptr, const int32_t *__restrict__ ucol,
+    const double *__restrict__ vals, const int32_t *__restrict__ lptr, const int32_t *__restrict__ lcol,
+    const int32_t *__restrict__ lblk, int identity, const double *__restrict__ x, double *__restrict__ y,
     double *__restrict__ partial, const PcgScalars *sc, const PeerCtx *pc)
 {
     __shared__ double red[33];
@@ -453,10 +551,11 @@ __global__ void __launch_bounds__(kSpmvThreads, 8) k_spmv_rowthread(
     for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
         const int64_t row = r0 + lr;
         if (row < nb) {
-            const int32_t kb = __ldg(rowptr + row), ke = __ldg(rowptr + row + 1);
-            double acc = 0.0;
+            const double xi = __ldg(x + row * 6 + i);
+            double acc = identity ? xi : 0.0;
+            const int32_t kb = __ldg(uptr + row), ke = __ldg(uptr + row + 1);
             for (int32_t k = kb; k < ke; ++k) {
-                const int32_t c = __ldg(colidx + k);
+                const int32_t c = __ldg(ucol + k);
                 const double *v = vals + (int64_t)k * 36 + i * 6;
                 const double *xx = x + (int64_t)c * 6;
                 const double2 v0 = ldg2(v), v1 = ldg2(v + 2), v2 = ldg2(v + 4);
@@ -465,8 +564,21 @@ __global__ void __launch_bounds__(kSpmvThreads, 8) k_spmv_rowthread(
                 acc = fma(v1.x, x1.x, acc); acc = fma(v1.y, x1.y, acc);
                 acc = fma(v2.x, x2.x, acc); acc = fma(v2.y, x2.y, acc);
             }
+            if (SYM) {
+                const int32_t lb = __ldg(lptr + row), le = __ldg(lptr + row + 1);
+                for (int32_t l = lb; l < le; ++l) {
+                    const double *v = vals + (int64_t)__ldg(lblk + l) * 36 + i;   // column i of the block
+                    const double *xx = x + (int64_t)__ldg(lcol + l) * 6;
+                    const double t0 = __ldg(v), t1 = __ldg(v + 6), t2 = __ldg(v + 12), t3 = __ldg(v + 18),
+                                 t4 = __ldg(v + 24), t5 = __ldg(v + 30);
+                    const double2 x0 = ldg2(xx), x1 = ldg2(xx + 2), x2 = ldg2(xx + 4);
+                    acc = fma(t0, x0.x, acc); acc = fma(t1, x0.y, acc);
+                    acc = fma(t2, x1.x, acc); acc = fma(t3, x1.y, acc);
+                    acc = fma(t4, x2.x, acc); acc = fma(t5, x2.y, acc);
+                }
+            }
             y[row * 6 + i] = acc;
-            dot = fma(__ldg(x + row * 6 + i), acc, dot);
+            dot = fma(xi, acc, dot);
         }
     }
     if (partial != nullptr) {
@@ -487,17 +599,24 @@ __global__ void __launch_bounds__(kSpmvThreads, 8) k_spmv_rowthread(
     }
 }
 
-int spmv_rowthread_grid(int64_t nb)
+// one full wave: 148 SMs x resident CTAs per SM (8 at 40 registers, 7 for the symmetric variant)
+int spmv_rowthread_grid(int64_t nb, bool sym)
 {
     const int64_t tiles = (nb + kRowsPerCta - 1) / kRowsPerCta;
-    return (int)(tiles < 1 ? 1 : (tiles > kMaxPartials ? kMaxPartials : tiles));
+    const int64_t cap = sym ? 148 * 7 : 148 * 8;
+    return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
-void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx,
-                           const double *vals, const double *x, double *y, double *partial,
-                           const PcgScalars *sc, const PeerCtx *pc)
+void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const double *vals,
+                           const int32_t *lptr, const int32_t *lcol, const int32_t *lblk, int identity,
+                           const double *x, double *y, double *partial, const PcgScalars *sc, const PeerCtx *pc)
 {
-    k_spmv_rowthread<<<spmv_rowthread_grid(nb), kSpmvThreads, 0, st>>>(nb, rowptr, colidx, vals, x, y, partial, sc, pc);
+    if (lptr != nullptr)
+        k_spmv_rowthread<true><<<spmv_rowthread_grid(nb, true), kSpmvThreads, 0, st>>>(
+            nb, uptr, ucol, vals, lptr, lcol, lblk, identity, x, y, partial, sc, pc);
+    else
+        k_spmv_rowthread<false><<<spmv_rowthread_grid(nb, false), kSpmvThreads, 0, st>>>(
+            nb, uptr, ucol, vals, lptr, lcol, lblk, identity, x, y, partial, sc, pc);
 }
 
 // ---------------------------------------------------------------------------
@@ -556,8 +675,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 __global__ void __launch_bounds__(kTmaThreads, 1) k_spmv_tma(
     int64_t ntiles, const int32_t *__restrict__ tile_row, const int32_t *__restrict__ rowptr,
-    const int32_t *__restrict__ colidx, const double *__restrict__ vals, const double *__restrict__ x,
-    double *__restrict__ y, double *__restrict__ partial, const PcgScalars *sc)
+    const int32_t *__restrict__ colidx, const double *__restrict__ vals, int identity,
+    const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partial, const PcgScalars *sc)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kTmaStages], empty_bar[kTmaStages];
@@ -611,7 +730,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_spmv_tma(
             mbar_wait(&full_bar[stage], phase);
             if (live) {
                 const double *sv = stage_buf + (size_t)stage * (kTmaStageBytes / 8) + (size_t)(kb - k0) * 36 + i * 6;
-                double acc = 0.0;
+                const double xi = __ldg(x + (int64_t)row * 6 + i);
+                double acc = identity ? xi : 0.0;
                 for (int32_t k = kb; k < ke; ++k, sv += 36) {
                     const int32_t c = __ldg(colidx + k);
                     const double *xx = x + (int64_t)c * 6;
@@ -624,7 +744,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_spmv_tma(
                     acc = fma(v2.x, x2.x, acc); acc = fma(v2.y, x2.y, acc);
                 }
                 y[(int64_t)row * 6 + i] = acc;
-                dot = fma(__ldg(x + (int64_t)row * 6 + i), acc, dot);
+                dot = fma(xi, acc, dot);
             }
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[stage]);
@@ -653,18 +773,20 @@ int spmv_tma_prepare()
 }
 
 void launch_spmv_tma(cudaStream_t st, int grid, int64_t ntiles, const int32_t *tile_row,
-                     const int32_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
-                     double *y, double *partial, const PcgScalars *sc)
+                     const int32_t *rowptr, const int32_t *colidx, const double *vals, int identity,
+                     const double *x, double *y, double *partial, const PcgScalars *sc)
 {
-    k_spmv_tma<<<grid, kTmaThreads, spmv_tma_smem_bytes(), st>>>(ntiles, tile_row, rowptr, colidx, vals, x, y,
-                                                                 partial, sc);
+    k_spmv_tma<<<grid, kTmaThreads, spmv_tma_smem_bytes(), st>>>(ntiles, tile_row, rowptr, colidx, vals, identity, x,
+                                                                 y, partial, sc);
 }
 
 // ---------------------------------------------------------------------------
-// K6: fused PCG vector kernels.  192 threads = 32 block rows x 6 DOFs; the
-// block-Jacobi apply needs the 6 residuals of a row, exchanged through shared
-// memory.  All scalars (alpha, beta, iteration count, stop flag) live on the
-// device so a whole batch of iterations is one CUDA graph with no host sync.
+// K6: CG vector kernels on the scaled system (unit block diagonal => no
+// preconditioner apply, no z vector): 9 vector passes per iteration.  All
+// scalars (alpha, beta, iteration count, stop flag) live on the device so a whole
+// batch of iterations is one CUDA graph with no host sync.  The stop test
+// ||f - K x||_2 <= tol ||f||_2 is evaluated on the UNSCALED residual r = L r~
+// once per batch (k_cg_check), so the per-iteration kernels never read L.
 // ---------------------------------------------------------------------------
 int vec_grid(int64_t nb)
 {
@@ -672,59 +794,58 @@ int vec_grid(int64_t nb)
     return (int)(tiles < 1 ? 1 : (tiles > kMaxPartials ? kMaxPartials : tiles));
 }
 
-// z_i = sum_j Minv[row][i][j] * rs[j]
-__device__ __forceinline__ double apply_minv_row(const double *__restrict__ minv, int64_t row, int i,
-                                                 const double *rs)
+// out_i = sum_{j<=i} M[row][i][j] * v[j]   (M lower triangular, full 6x6 storage)
+__device__ __forceinline__ double lower_row_times(const double *__restrict__ M, int64_t row, int i, const double *v)
 {
-    const double *m = minv + row * 36 + i * 6;
+    const double *m = M + row * 36 + i * 6;
     const double2 m0 = ldg2(m), m1 = ldg2(m + 2), m2 = ldg2(m + 4);
-    double z = m0.x * rs[0];
-    z = fma(m0.y, rs[1], z); z = fma(m1.x, rs[2], z); z = fma(m1.y, rs[3], z);
-    z = fma(m2.x, rs[4], z); z = fma(m2.y, rs[5], z);
-    return z;
+    double s = m0.x * v[0];
+    s = fma(m0.y, v[1], s); s = fma(m1.x, v[2], s); s = fma(m1.y, v[3], s);
+    s = fma(m2.x, v[4], s); s = fma(m2.y, v[5], s);
+    return s;  // entries above the diagonal are stored as exact zeros
 }
 
-__global__ void __launch_bounds__(kSpmvThreads) k_pcg_init(
-    int64_t nb, const double *__restrict__ f, const double *__restrict__ minv, double *__restrict__ x,
-    double *__restrict__ r, double *__restrict__ z, double *__restrict__ p, double *__restrict__ part_rz,
+// f~ = S f; y = 0; r~ = f~; p = f~; partials of rho = r~.r~ and of ||f||^2
+__global__ void __launch_bounds__(kSpmvThreads) k_cg_init(
+    int64_t nb, const double *__restrict__ f, const double *__restrict__ sinv, double *__restrict__ y,
+    double *__restrict__ rt, double *__restrict__ ft, double *__restrict__ p, double *__restrict__ part_rho,
     double *__restrict__ part_ff)
 {
-    __shared__ double rs[kSpmvThreads];
+    __shared__ double vs[kSpmvThreads];
     __shared__ double red[33];
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
-    double rz = 0.0, ff = 0.0;
+    double rho = 0.0, ff = 0.0;
     for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
         const int64_t row = r0 + lr;
         const bool live = row < nb;
-        double fv = 0.0;
-        if (live) fv = f[row * 6 + i];
+        const double fv = live ? f[row * 6 + i] : 0.0;
         __syncthreads();
-        rs[threadIdx.x] = fv;
+        vs[threadIdx.x] = fv;
         __syncthreads();
         if (live) {
-            const double zv = apply_minv_row(minv, row, i, rs + lr * 6);
-            x[row * 6 + i] = 0.0;
-            r[row * 6 + i] = fv;
-            z[row * 6 + i] = zv;
-            p[row * 6 + i] = zv;
-            rz = fma(fv, zv, rz);
+            const double t = lower_row_times(sinv, row, i, vs + lr * 6);
+            y[row * 6 + i] = 0.0;
+            rt[row * 6 + i] = t;
+            ft[row * 6 + i] = t;
+            p[row * 6 + i] = t;
+            rho = fma(t, t, rho);
             ff = fma(fv, fv, ff);
         }
     }
-    const double a = block_sum<false>(rz, red);
+    const double a = block_sum<false>(rho, red);
     const double b = block_sum<false>(ff, red);
-    if (threadIdx.x == 0) { part_rz[blockIdx.x] = a; part_ff[blockIdx.x] = b; }
+    if (threadIdx.x == 0) { part_rho[blockIdx.x] = a; part_ff[blockIdx.x] = b; }
 }
 
-__global__ void __launch_bounds__(256) k_pcg_init_finish(PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                                                         long long max_iter, unsigned long long epoch,
-                                                         unsigned long long *trace)
+__global__ void __launch_bounds__(256) k_cg_init_finish(PartialRef rho, PartialRef ff, PcgScalars *sc, double tol,
+                                                        long long max_iter, unsigned long long epoch,
+                                                        unsigned long long *trace)
 {
     __shared__ double red[33];
-    const double a = sum_partials(rz, red);
+    const double a = sum_partials(rho, red);
     const double b = sum_partials(ff, red);
     if (threadIdx.x == 0) {
-        sc->rz[0] = a; sc->rz[1] = 0.0;
+        sc->rz[0] = a; sc->rz[1] = 0.0; sc->rho0 = a;
         sc->ff = b; sc->rr = b; sc->pAp = 1.0;
         sc->iter = 0; sc->max_iter = max_iter; sc->tol2 = tol * tol;
         // f == 0 -> u == 0 is the solution; a non-finite load is a breakdown
@@ -732,16 +853,16 @@ __global__ void __launch_bounds__(256) k_pcg_init_finish(PartialRef rz, PartialR
         sc->pad = 0;
         sc->epoch = epoch;
         sc->tag_cur = 0;
+        sc->checks = 0;
         sc->trace = trace;
     }
 }
 
-__global__ void __launch_bounds__(kSpmvThreads) k_pcg_update(
-    int64_t nb, int parity, PartialRef pAp_ref, const double *__restrict__ minv, const double *__restrict__ p,
-    const double *__restrict__ Ap, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
-    double *__restrict__ part_rz, double *__restrict__ part_rr, PcgScalars *sc, const PeerCtx *pc)
+__global__ void __launch_bounds__(256, 4) k_cg_update(
+    int64_t n, int parity, PartialRef pAp_ref, const double *__restrict__ p, const double *__restrict__ Ap,
+    double *__restrict__ y, double *__restrict__ rt, double *__restrict__ part_rho, PcgScalars *sc,
+    const PeerCtx *pc)
 {
-    __shared__ double rs[kSpmvThreads];
     __shared__ double red[33];
     if (sc->done != 0) return;
     trace_stamp(sc, sc->iter, 2);
@@ -759,49 +880,35 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_update(
         pAp = sum_partials(pAp_ref, red);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc->pAp = pAp; sc->tag_cur = tag; }
-    if (!(pAp > 0.0) || !isfinite(pAp)) return;  // breakdown: k_pcg_pupdate raises the flag
+    if (!(pAp > 0.0) || !isfinite(pAp)) return;  // breakdown: k_cg_pupdate raises the flag
     const double alpha = sc->rz[parity] / pAp;
-    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
-    double rz = 0.0, rr = 0.0;
-    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
-        const int64_t row = r0 + lr;
-        const bool live = row < nb;
-        double rv = 0.0;
-        if (live) {
-            const int64_t j = row * 6 + i;
-            x[j] = fma(alpha, p[j], x[j]);
-            rv = fma(-alpha, Ap[j], r[j]);
-            r[j] = rv;
-        }
-        __syncthreads();
-        rs[threadIdx.x] = rv;
-        __syncthreads();
-        if (live) {
-            const double zv = apply_minv_row(minv, row, i, rs + lr * 6);
-            z[row * 6 + i] = zv;
-            rz = fma(rv, zv, rz);
-            rr = fma(rv, rv, rr);
-        }
+    double rho = 0.0;
+    const int64_t n2 = n >> 1;  // n = 6*nb is even
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += (int64_t)gridDim.x * blockDim.x) {
+        const double2 pv = reinterpret_cast<const double2 *>(p)[j], av = reinterpret_cast<const double2 *>(Ap)[j];
+        double2 yv = reinterpret_cast<double2 *>(y)[j], rv = reinterpret_cast<double2 *>(rt)[j];
+        yv.x = fma(alpha, pv.x, yv.x); yv.y = fma(alpha, pv.y, yv.y);
+        rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+        reinterpret_cast<double2 *>(y)[j] = yv;
+        reinterpret_cast<double2 *>(rt)[j] = rv;
+        rho = fma(rv.x, rv.x, rho); rho = fma(rv.y, rv.y, rho);
     }
-    const double a = block_sum<false>(rz, red);
-    const double b = block_sum<false>(rr, red);
-    if (threadIdx.x == 0) { part_rz[blockIdx.x] = a; part_rr[blockIdx.x] = b; }
+    const double a = block_sum<false>(rho, red);
+    if (threadIdx.x == 0) part_rho[blockIdx.x] = a;
     if (pc != nullptr && last_cta_done(pc->tickets + 1)) {
-        const double sa = sum_partials(PartialRef{part_rz, (int)gridDim.x, 1}, red);
-        const double sb = sum_partials(PartialRef{part_rr, (int)gridDim.x, 1}, red);
+        const double sa = sum_partials(PartialRef{part_rho, (int)gridDim.x, 1}, red);
         if ((int)threadIdx.x < pc->world) {
             Mailbox *m = pc->peer[threadIdx.x];
             m->dot_val[1][pc->rank] = sa;
-            m->dot_val[2][pc->rank] = sb;
             __threadfence_system();
             st_release_sys(&m->dot_tag[1][pc->rank], tag);
         }
     }
 }
 
-__global__ void __launch_bounds__(kSpmvThreads) k_pcg_pupdate(
-    int64_t nb, int parity, PartialRef rz_ref, PartialRef rr_ref, const double *__restrict__ z,
-    double *__restrict__ p, PcgScalars *sc, const PeerCtx *pc)
+__global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, PartialRef rho_ref,
+                                                       const double *__restrict__ rt, double *__restrict__ p,
+                                                       PcgScalars *sc, const PeerCtx *pc)
 {
     __shared__ double red[33];
     if (sc->done != 0) return;
@@ -812,62 +919,167 @@ __global__ void __launch_bounds__(kSpmvThreads) k_pcg_pupdate(
     }
     const long long it0 = sc->iter;   // only block 0 stamps, and it bumps iter after this read
     trace_stamp(sc, it0, 4);
-    double rz_new, rr;
+    double rho_new;
     if (pc != nullptr) {
-        const unsigned long long tag = sc->tag_cur;   // written by k_pcg_update, stable here
+        const unsigned long long tag = sc->tag_cur;   // written by k_cg_update, stable here
         if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[1][threadIdx.x], tag);
         __syncthreads();
-        rz_new = 0.0; rr = 0.0;
         trace_stamp(sc, it0, 5);
-        for (int q = 0; q < pc->world; ++q) {
-            rz_new += __ldcv(&pc->mine->dot_val[1][q]);
-            rr += __ldcv(&pc->mine->dot_val[2][q]);
-        }
+        rho_new = 0.0;
+        for (int q = 0; q < pc->world; ++q) rho_new += __ldcv(&pc->mine->dot_val[1][q]);
     } else {
-        rz_new = sum_partials(rz_ref, red);
-        rr = sum_partials(rr_ref, red);
+        rho_new = sum_partials(rho_ref, red);
     }
-    const double beta = rz_new / sc->rz[parity];
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb * 6;
-         j += (int64_t)gridDim.x * blockDim.x)
-        p[j] = fma(beta, p[j], z[j]);
+    const double beta = rho_new / sc->rz[parity];
+    const int64_t n2 = n >> 1;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += (int64_t)gridDim.x * blockDim.x) {
+        const double2 rv = reinterpret_cast<const double2 *>(rt)[j];
+        double2 pv = reinterpret_cast<double2 *>(p)[j];
+        pv.x = fma(beta, pv.x, rv.x); pv.y = fma(beta, pv.y, rv.y);
+        reinterpret_cast<double2 *>(p)[j] = pv;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->rz[parity ^ 1] = rz_new;
-        sc->rr = rr;
+        sc->rz[parity ^ 1] = rho_new;
         const long long it = sc->iter + 1;
         sc->iter = it;
         int done = 0;
-        if (!isfinite(rr) || !isfinite(rz_new)) done = 3;
-        else if (rr <= sc->tol2 * sc->ff) done = 1;
+        if (!isfinite(rho_new)) done = 3;
+        else if (rho_new <= 1e-32 * sc->rho0) done = 1;   // below anything FP64 can resolve: exact convergence
         else if (it >= sc->max_iter) done = 2;
         sc->done = done;
     }
 }
 
-void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double *minv, double *x,
-                     double *r, double *z, double *p, double *part_rz, double *part_ff)
+// per batch: partial sums of ||L (a - b)||^2 (b may be null): the unscaled residual norm
+__global__ void __launch_bounds__(kSpmvThreads) k_cg_check(int64_t nb, const double *__restrict__ lfac,
+                                                           const double *__restrict__ a, const double *__restrict__ b,
+                                                           double *__restrict__ part, const PcgScalars *sc,
+                                                           const PeerCtx *pc)
 {
-    k_pcg_init<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, f, minv, x, r, z, p, part_rz, part_ff);
+    __shared__ double vs[kSpmvThreads];
+    __shared__ double red[33];
+    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+    double rr = 0.0;
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+        const int64_t row = r0 + lr;
+        const bool live = row < nb;
+        double v = 0.0;
+        if (live) v = a[row * 6 + i] - (b != nullptr ? b[row * 6 + i] : 0.0);
+        __syncthreads();
+        vs[threadIdx.x] = v;
+        __syncthreads();
+        if (live) {
+            const double t = lower_row_times(lfac, row, i, vs + lr * 6);
+            rr = fma(t, t, rr);
+        }
+    }
+    const double s = block_sum<false>(rr, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+    if (pc != nullptr && last_cta_done(pc->tickets + 3)) {
+        const double sa = sum_partials(PartialRef{part, (int)gridDim.x, 1}, red);
+        if ((int)threadIdx.x < pc->world) {
+            const unsigned long long tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)sc->checks) + 1;
+            Mailbox *m = pc->peer[threadIdx.x];
+            m->dot_val[2][pc->rank] = sa;
+            __threadfence_system();
+            st_release_sys(&m->dot_tag[2][pc->rank], tag);
+        }
+    }
 }
 
-void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                            long long max_iter, unsigned long long epoch, unsigned long long *trace)
+// one CTA: total of the check partials -> sc->rr; converged => done = 1
+__global__ void __launch_bounds__(256) k_cg_check_finish(PartialRef part, PcgScalars *sc, const PeerCtx *pc)
 {
-    k_pcg_init_finish<<<1, 256, 0, st>>>(rz, ff, sc, tol, max_iter, epoch, trace);
+    __shared__ double red[33];
+    double rr;
+    if (pc != nullptr) {
+        const unsigned long long tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)sc->checks) + 1;
+        if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[2][threadIdx.x], tag);
+        __syncthreads();
+        rr = 0.0;
+        for (int q = 0; q < pc->world; ++q) rr += __ldcv(&pc->mine->dot_val[2][q]);
+    } else {
+        rr = sum_partials(part, red);
+    }
+    if (threadIdx.x == 0) {
+        sc->rr = rr;
+        sc->checks = sc->checks + 1;
+        if (sc->done == 0 && rr <= sc->tol2 * sc->ff) sc->done = 1;
+        if (sc->done == 0 && !isfinite(rr)) sc->done = 3;
+    }
 }
 
-void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
-                       const double *p, const double *Ap, double *x, double *r, double *z,
-                       double *part_rz, double *part_rr, PcgScalars *sc, const PeerCtx *pc)
+// x = S^T y  (back to the unscaled unknowns)
+__global__ void __launch_bounds__(kSpmvThreads) k_unscale(int64_t nb, const double *__restrict__ sinv,
+                                                          const double *__restrict__ y, double *__restrict__ x)
 {
-    k_pcg_update<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, pAp, minv, p, Ap, x, r, z, part_rz, part_rr, sc, pc);
+    __shared__ double vs[kSpmvThreads];
+    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+        const int64_t row = r0 + lr;
+        const bool live = row < nb;
+        __syncthreads();
+        vs[threadIdx.x] = live ? y[row * 6 + i] : 0.0;
+        __syncthreads();
+        if (live) {
+            const double *S = sinv + row * 36;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s = fma(__ldg(S + 6 * j + i), vs[lr * 6 + j], s);  // column i of S
+            x[row * 6 + i] = s;
+        }
+    }
 }
 
-void launch_pcg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rz, PartialRef rr,
-                        const double *z, double *p, PcgScalars *sc, const PeerCtx *pc)
+void launch_cg_init(cudaStream_t st, int64_t nb, const double *f, const double *sinv, double *y, double *rt,
+                    double *ft, double *p, double *part_rho, double *part_ff)
 {
-    k_pcg_pupdate<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, parity, rz, rr, z, p, sc, pc);
+    k_cg_init<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, f, sinv, y, rt, ft, p, part_rho, part_ff);
 }
+
+void launch_cg_init_finish(cudaStream_t st, PartialRef rho, PartialRef ff, PcgScalars *sc, double tol,
+                           long long max_iter, unsigned long long epoch, unsigned long long *trace)
+{
+    k_cg_init_finish<<<1, 256, 0, st>>>(rho, ff, sc, tol, max_iter, epoch, trace);
+}
+
+int cg_vec_grid(int64_t nb)
+{
+    const int64_t blocks = (3 * nb + 255) / 256;   // one double2 per thread and trip
+    const int64_t cap = 148 * 4;                    // one full wave at 4 CTAs of 256 threads per SM
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *p, const double *Ap,
+                      double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc)
+{
+    k_cg_update<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, parity, pAp, p, Ap, y, rt, part_rho, sc, pc);
+}
+
+void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
+                       PcgScalars *sc, const PeerCtx *pc)
+{
+    k_cg_pupdate<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, parity, rho, rt, p, sc, pc);
+}
+
+void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
+                     const PcgScalars *sc, const PeerCtx *pc)
+{
+    k_cg_check<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, lfac, a, b, part, sc, pc);
+}
+
+void launch_cg_check_finish(cudaStream_t st, PartialRef part, PcgScalars *sc, const PeerCtx *pc)
+{
+    k_cg_check_finish<<<1, 256, 0, st>>>(part, sc, pc);
+}
+
+void launch_unscale(cudaStream_t st, int64_t nb, const double *sinv, const double *y, double *x)
+{
+    if (nb <= 0) return;
+    k_unscale<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, sinv, y, x);
+}
+
+
 
 // P2P halo exchange: every owned boundary x-block is stored straight into its
 // slot of the destination rank's ghost region (NVLink peer stores, fire and
@@ -937,40 +1149,21 @@ void launch_reduce_partials(cudaStream_t st, const double *a, int n, double *out
 }
 
 __global__ void k_pack_halo(int64_t n_send, const int32_t *__restrict__ send_rows, const double *__restrict__ x,
-                            double *__restrict__ sendbuf)
+                            double *__restrict__ sendbuf, int width)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = t / 6;
-    const int i = (int)(t - s * 6);
+    const int64_t s = t / width;
+    const int i = (int)(t - s * width);
     if (s >= n_send) return;
-    sendbuf[t] = x[(int64_t)__ldg(send_rows + s) * 6 + i];
+    sendbuf[t] = x[(int64_t)__ldg(send_rows + s) * width + i];
 }
 
-void launch_pack_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, const double *x, double *sendbuf)
+void launch_pack_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, const double *x, double *sendbuf,
+                      int width)
 {
     if (n_send <= 0) return;
-    const int64_t n = n_send * 6;
-    k_pack_halo<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_send, send_rows, x, sendbuf);
-}
-
-__global__ void __launch_bounds__(kSpmvThreads) k_residual(int64_t nb, const double *__restrict__ f,
-                                                           const double *__restrict__ y,
-                                                           double *__restrict__ part_rr)
-{
-    __shared__ double red[33];
-    double rr = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb * 6;
-         j += (int64_t)gridDim.x * blockDim.x) {
-        const double d = f[j] - y[j];
-        rr = fma(d, d, rr);
-    }
-    const double s = block_sum<false>(rr, red);
-    if (threadIdx.x == 0) part_rr[blockIdx.x] = s;
-}
-
-void launch_residual(cudaStream_t st, int64_t nb, const double *f, const double *y, double *part_rr)
-{
-    k_residual<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, f, y, part_rr);
+    const int64_t n = n_send * width;
+    k_pack_halo<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_send, send_rows, x, sendbuf, width);
 }
 
 __global__ void k_fill_f64(int64_t n, double *a, double v0, double dv, int period)

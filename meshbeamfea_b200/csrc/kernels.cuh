@@ -26,8 +26,8 @@ constexpr int kMaxWorld = 16;
 // mailbox with acquire loads.  tag = (solve epoch << 32) | iteration stamp.
 struct Mailbox {
     unsigned long long halo_tag[kMaxWorld];    // [q]: rank q's boundary x-blocks have landed in my ghost region
-    unsigned long long dot_tag[2][kMaxWorld];  // [0]: p.Ap   [1]: r.z and r.r
-    double dot_val[3][kMaxWorld];              // [0] p.Ap  [1] r.z  [2] r.r   (per source rank)
+    unsigned long long dot_tag[3][kMaxWorld];  // [0]: p.Ap   [1]: rho = r~.r~   [2]: per-batch ||r||^2
+    double dot_val[3][kMaxWorld];              // same slots, one value per source rank
 };
 
 struct PeerCtx {          // device-resident, local memory
@@ -35,7 +35,7 @@ struct PeerCtx {          // device-resident, local memory
     int neighbor[kMaxWorld];
     Mailbox *mine;
     Mailbox *peer[kMaxWorld];   // peer[rank] == mine
-    unsigned int *tickets;      // last-CTA-done tickets: [0] spmv [1] update [2] push_halo
+    unsigned int *tickets;      // last-CTA-done tickets: [0] spmv [1] update [2] push_halo [3] check
 };
 
 struct PcgScalars {
@@ -51,6 +51,8 @@ struct PcgScalars {
     unsigned long long epoch;    // solve counter (multi-GPU tags)
     unsigned long long tag_cur;  // tag of the values produced in the current iteration
     unsigned long long *trace;   // optional: kTraceSlots globaltimer stamps per iteration (first kTraceIters)
+    double rho0;                 // r~.r~ at iteration 0
+    long long checks;            // residual checks done (multi-GPU tag of the per-batch check)
 };
 constexpr int kTraceSlots = 8;   // 0 spmv in, 1 spmv past halo wait, 2 update in, 3 update past wait,
                                  // 4 pupdate in, 5 pupdate past wait, 6 push in, 7 push out (last CTA)
@@ -72,31 +74,40 @@ void launch_elem_geom(cudaStream_t st, int64_t E, const ElemRec *rec, const Node
 // K2: deterministic scatter-free BSR assembly from the ElemGeom records
 void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, const int32_t *contrib,
                      const ElemGeom *geom, double *vals);
-// K5: inverse of every diagonal block; *flag |= 1 on a non-positive pivot
-void launch_block_jacobi(cudaStream_t st, int64_t nb, const int32_t *diag_idx, const double *vals,
-                         double *minv, int *flag);
+// K5: Cholesky factor L and S = L^-1 of every diagonal block; *flag |= 1 on a non-positive pivot
+void launch_block_chol(cudaStream_t st, int64_t nb, const int32_t *diag_idx, const double *vals, double *lfac,
+                       double *sinv, int *flag);
+// solver matrix K~ = S K S^T, stored blocks only (sinv: owned rows then ghost rows)
+void launch_scale_blocks(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const int32_t *usrc,
+                         const double *vals, const double *sinv, double *vals_s);
 // K4: y = A x (x has nb + n_ghost blocks), partial[blockIdx] = sum x_own . y
-int  spmv_rowthread_grid(int64_t nb);
-void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx,
-                           const double *vals, const double *x, double *y, double *partial,
-                           const PcgScalars *sc, const PeerCtx *pc);
+//     identity: unit diagonal implied; lptr/lcol/lblk: transposed references (may be null)
+int  spmv_rowthread_grid(int64_t nb, bool sym);
+void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const double *vals,
+                           const int32_t *lptr, const int32_t *lcol, const int32_t *lblk, int identity,
+                           const double *x, double *y, double *partial, const PcgScalars *sc, const PeerCtx *pc);
 int  spmv_tma_grid(int64_t ntiles, int sm_count);
 size_t spmv_tma_smem_bytes();
 int  spmv_tma_prepare();  // opt in to the large dynamic shared memory; returns cudaError
 void launch_spmv_tma(cudaStream_t st, int grid, int64_t ntiles, const int32_t *tile_row,
-                     const int32_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
-                     double *y, double *partial, const PcgScalars *sc);
-// K6: fused PCG vector kernels
+                     const int32_t *rowptr, const int32_t *colidx, const double *vals, int identity,
+                     const double *x, double *y, double *partial, const PcgScalars *sc);
+// K6: CG vector kernels on the scaled system
 int  vec_grid(int64_t nb);
-void launch_pcg_init(cudaStream_t st, int64_t nb, const double *f, const double *minv, double *x,
-                     double *r, double *z, double *p, double *part_rz, double *part_ff);
-void launch_pcg_init_finish(cudaStream_t st, PartialRef rz, PartialRef ff, PcgScalars *sc, double tol,
-                            long long max_iter, unsigned long long epoch, unsigned long long *trace);
-void launch_pcg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *minv,
-                       const double *p, const double *Ap, double *x, double *r, double *z,
-                       double *part_rz, double *part_rr, PcgScalars *sc, const PeerCtx *pc);
-void launch_pcg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rz, PartialRef rr,
-                        const double *z, double *p, PcgScalars *sc, const PeerCtx *pc);
+int  cg_vec_grid(int64_t nb);
+void launch_cg_init(cudaStream_t st, int64_t nb, const double *f, const double *sinv, double *y, double *rt,
+                    double *ft, double *p, double *part_rho, double *part_ff);
+void launch_cg_init_finish(cudaStream_t st, PartialRef rho, PartialRef ff, PcgScalars *sc, double tol,
+                           long long max_iter, unsigned long long epoch, unsigned long long *trace);
+void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *p, const double *Ap,
+                      double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc);
+void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
+                       PcgScalars *sc, const PeerCtx *pc);
+// unscaled residual norm ||L (a - b)||^2 (b may be null) -> partials; finish: total -> sc->rr, stop test
+void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
+                     const PcgScalars *sc, const PeerCtx *pc);
+void launch_cg_check_finish(cudaStream_t st, PartialRef part, PcgScalars *sc, const PeerCtx *pc);
+void launch_unscale(cudaStream_t st, int64_t nb, const double *sinv, const double *y, double *x);
 int peer_timeout_flag();  // 1 once any peer wait gave up (a rank died)
 // P2P halo: owned boundary x-blocks -> the neighbours' ghost slots (peer stores), then the tag
 void launch_push_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, double *const *dst,
@@ -104,15 +115,14 @@ void launch_push_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows,
 // collapse `n` partials to out[0] in fixed order (multi-GPU path, before the all-gather)
 void launch_reduce_partials(cudaStream_t st, const double *a, int n, double *out_a, const double *b,
                             double *out_b, const PcgScalars *sc);
-// halo: pack owned boundary blocks into the send buffer
-void launch_pack_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, const double *x, double *sendbuf);
+// halo: pack owned boundary blocks (width doubles each) into the send buffer
+void launch_pack_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, const double *x, double *sendbuf,
+                      int width);
 // deterministic test pattern a[i] = v0 + dv*(i % period)  (SpMV timing input)
 void launch_fill(cudaStream_t st, int64_t n, double *a, double v0, double dv, int period);
 // load vector of the reduced system (owned rows), duplicates accumulate in input order
 void launch_scatter_forces(cudaStream_t st, int64_t nF, const int64_t *node, const int64_t *dof, const double *mag,
                            const int32_t *free_index, int64_t row_begin, int64_t nb, double *f);
-// residual check: r = f - y, partial r.r
-void launch_residual(cudaStream_t st, int64_t nb, const double *f, const double *y, double *part_rr);
 // results
 void launch_expand(cudaStream_t st, int64_t V, const int32_t *free_index, const double *x_global,
                    double *U_cm, double *U_rm);

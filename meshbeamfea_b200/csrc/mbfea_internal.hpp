@@ -31,6 +31,13 @@ struct HostPlan {
     std::vector<int32_t> diag_idx;    // nb: position of the diagonal block
     std::vector<int32_t> contrib_ptr; // nnzb+1
     std::vector<int32_t> contrib;     // (element<<2)|which, ascending element per block
+    // Solver format (off-diagonal blocks of the block-Jacobi-scaled matrix, unit diagonal implied):
+    // row r stores the blocks [uptr[r], uptr[r+1]) itself -- its ghost columns and, with
+    // symmetric-half storage, only its local columns c > r -- and reaches the remaining local
+    // columns c < r as TRANSPOSED references [lptr[r], lptr[r+1]) into row c's stored blocks.
+    std::vector<int32_t> uptr, ucol, usrc;  // usrc: index of the block in the full pattern
+    std::vector<int32_t> lptr, lcol, lblk;  // lblk: stored-block index holding (lcol, r)
+    bool sym_half = false;
     std::vector<int64_t> ghost_global;// ascending => grouped by owner
     std::vector<int32_t> ghost_owner;
     std::vector<int32_t> send_rows;   // local row ids grouped by destination rank
@@ -60,6 +67,10 @@ int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<i
 // with_contrib=false skips the contributor lists (plan-only callers).
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                 int32_t rank, int32_t world, bool with_contrib, HostPlan &plan);
+
+// Solver format from the full pattern (see HostPlan::uptr).  half=false keeps every
+// off-diagonal block in its own row (no transposed references).
+void build_solver_format(HostPlan &plan, bool half);
 
 // Row tiles for the TMA-staged SpMV: tile t covers rows [tile_row[t], tile_row[t+1]).
 void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
