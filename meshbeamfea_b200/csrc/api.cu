@@ -117,7 +117,9 @@ struct mbfea_ctx {
     DevBuf<Mailbox> mailbox;
     DevBuf<PeerCtx> peerctx;
     DevBuf<unsigned int> tickets;
-    DevBuf<double *> push_dst;
+    DevBuf<double *> push_dst;   // destination of every (boundary row, neighbour) pair, grouped by row
+    DevBuf<double *> push_dst_send;  // the same in send-list order (standalone push kernel, iteration 0)
+    DevBuf<int32_t> push_idx;    // per owned row: first entry in push_dst | count << 28, or -1
     std::vector<Mailbox *> peer_mailbox;   // [world]; own entry = mailbox.p
     std::vector<double *> peer_p;          // [world]; peers' p vectors (IPC mappings), own = p.p
     unsigned long long epoch = 0;
@@ -361,7 +363,21 @@ void setup_p2p_halo(mbfea_ctx *c)
     for (const Neighbor &n : c->plan.neighbors)
         for (int64_t j = 0; j < n.send_count; ++j)
             dst[(size_t)(n.send_offset + j)] = c->peer_p[n.rank] + 6 * (all[n.rank].nb + all[n.rank].recv_off[me] + j);
-    upload(c, c->push_dst, dst);
+    upload(c, c->push_dst_send, dst);
+    // the same destinations grouped by row, for the push fused into k_cg_pupdate
+    {
+        std::vector<int32_t> cnt((size_t)nb, 0), idx((size_t)nb, -1);
+        for (int32_t r : c->plan.send_rows) cnt[(size_t)r]++;
+        std::vector<int32_t> first((size_t)nb + 1, 0);
+        for (int64_t r = 0; r < nb; ++r) first[(size_t)r + 1] = first[(size_t)r] + cnt[(size_t)r];
+        std::vector<double *> byrow(dst.size());
+        std::vector<int32_t> cur(first.begin(), first.end() - 1);
+        for (size_t i = 0; i < dst.size(); ++i) byrow[(size_t)cur[(size_t)c->plan.send_rows[i]]++] = dst[i];
+        for (int64_t r = 0; r < nb; ++r)
+            if (cnt[(size_t)r]) idx[(size_t)r] = first[(size_t)r] | (cnt[(size_t)r] << 28);
+        upload(c, c->push_dst, byrow);
+        upload(c, c->push_idx, idx);
+    }
     PeerCtx pc;
     std::memset(&pc, 0, sizeof pc);
     pc.rank = me; pc.world = W; pc.n_neighbors = (int)c->plan.neighbors.size();
@@ -389,10 +405,9 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         run_spmv(c, 1, c->p.p, c->Ap.p, c->part_a.p, c->sc.p, c->peerctx.p);
         launch_cg_update(c->st, nb, parity, PartialRef{c->part_a.p, gs, 1}, c->p.p, c->Ap.p, c->y.p, c->rt.p,
                          c->part_b.p, c->sc.p, c->peerctx.p);
-        launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, c->rt.p, c->p.p, c->sc.p, c->peerctx.p);
-        launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst.p, c->p.p, c->sc.p,
-                         c->peerctx.p);
-        c->launches += 3;
+        launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, c->rt.p, c->p.p, c->sc.p, c->peerctx.p,
+                          c->push_idx.p, c->push_dst.p);
+        c->launches += 2;
         return;
     }
     halo_exchange(c, c->p.p);
@@ -412,7 +427,7 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         rho = PartialRef{c->gath.p + W, W, 1};
         c->launches++;
     }
-    launch_cg_pupdate(c->st, nb, parity, rho, c->rt.p, c->p.p, c->sc.p, nullptr);
+    launch_cg_pupdate(c->st, nb, parity, rho, c->rt.p, c->p.p, c->sc.p, nullptr, nullptr, nullptr);
     c->launches += 2;
 }
 
@@ -825,8 +840,8 @@ int mbfea_solve(mbfea_ctx *c)
         launch_cg_init_finish(c->st, rho, ff, c->sc.p, c->opt.tol, max_iter, c->epoch, trace);
         c->launches += 2;
         if (c->p2p) {  // ghost blocks of p for iteration 0
-            launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst.p, c->p.p, c->sc.p,
-                             c->peerctx.p);
+            launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst_send.p, c->p.p,
+                             c->sc.p, c->peerctx.p);
             c->launches++;
         }
 

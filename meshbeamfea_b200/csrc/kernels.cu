@@ -906,9 +906,15 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
     }
 }
 
+// p = r~ + beta p.  Multi-GPU: the thread that produces a boundary block's entries also stores
+// them straight into the neighbours' ghost regions (push_idx[row] = first entry of the row in
+// push_dst | count << 28, or -1), and the last CTA publishes the halo tag -- the halo exchange
+// costs no extra kernel and its NVLink stores overlap the rest of the update.
 __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, PartialRef rho_ref,
                                                        const double *__restrict__ rt, double *__restrict__ p,
-                                                       PcgScalars *sc, const PeerCtx *pc)
+                                                       PcgScalars *sc, const PeerCtx *pc,
+                                                       const int32_t *__restrict__ push_idx,
+                                                       double *const *__restrict__ push_dst)
 {
     __shared__ double red[33];
     if (sc->done != 0) return;
@@ -937,6 +943,25 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
         double2 pv = reinterpret_cast<double2 *>(p)[j];
         pv.x = fma(beta, pv.x, rv.x); pv.y = fma(beta, pv.y, rv.y);
         reinterpret_cast<double2 *>(p)[j] = pv;
+        if (push_idx != nullptr) {
+            const int64_t row = j / 3;
+            const int32_t code = __ldg(push_idx + row);
+            if (code >= 0) {
+                const int off = (int)(j - row * 3) * 2;
+                const int32_t first = code & 0x0fffffff, cnt = code >> 28;
+                for (int32_t q = 0; q < cnt; ++q) *reinterpret_cast<double2 *>(push_dst[first + q] + off) = pv;
+            }
+        }
+    }
+    if (push_idx != nullptr) {
+        __threadfence_system();
+        if (last_cta_done(pc->tickets + 2)) {
+            if ((int)threadIdx.x < pc->n_neighbors) {
+                __threadfence_system();
+                // tag_cur = (epoch << 32 | k) + 1: exactly the halo tag iteration k+1 waits for
+                st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], sc->tag_cur);
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->rz[parity ^ 1] = rho_new;
@@ -1057,9 +1082,9 @@ void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, c
 }
 
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
-                       PcgScalars *sc, const PeerCtx *pc)
+                       PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst)
 {
-    k_cg_pupdate<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, parity, rho, rt, p, sc, pc);
+    k_cg_pupdate<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, parity, rho, rt, p, sc, pc, push_idx, push_dst);
 }
 
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,

@@ -102,7 +102,7 @@ void launch_cg_init_finish(cudaStream_t st, PartialRef rho, PartialRef ff, PcgSc
 void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *p, const double *Ap,
                       double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc);
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
-                       PcgScalars *sc, const PeerCtx *pc);
+                       PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst);
 // unscaled residual norm ||L (a - b)||^2 (b may be null) -> partials; finish: total -> sc->rr, stop test
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
                      const PcgScalars *sc, const PeerCtx *pc);
