@@ -910,6 +910,10 @@ int mbfea_solve(mbfea_ctx *c)
         // either way the recurrence residual at exit decides
         const bool met = h.ff == 0.0 || h.rr <= h.tol2 * h.ff;
         s.converged = (h.done == 1 && met) ? 1 : 0;
+        // On a singular (under-constrained) system the iterates blow up while the recurrence
+        // residual keeps shrinking; the recomputed residual exposes it.
+        const bool diverged = s.converged && !(s.true_rel_residual <= std::max(1e3 * c->opt.tol, 1e-6));
+        if (diverged) s.converged = 0;
         c->solved = true; c->recovered = false;
         if (c->opt.verbose)
             std::fprintf(stderr, "[mbfea] rank %d: CG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d (%s storage), batch %d\n",
@@ -918,6 +922,9 @@ int mbfea_solve(mbfea_ctx *c)
         if (c->p2p && peer_timeout_flag())
             return fail(c, MBFEA_ECUDA, "a peer rank stopped signalling during the PCG loop (NVLink mailbox wait timed out)");
         if (h.done == 3) return fail(c, MBFEA_ESINGULAR, "CG breakdown: p.Ap <= 0 or non-finite (system not SPD: is any vertex fixed?)");
+        if (diverged)
+            return fail(c, MBFEA_ESINGULAR, "recomputed residual ||f - K u|| disagrees with the CG recurrence: the system is singular "
+                                            "(is every connected component held by a fixed vertex?)");
         if (h.done == 2) return fail(c, MBFEA_ENOCONV, "CG reached max_iter before the requested tolerance");
         if (!s.converged) return fail(c, MBFEA_ENOCONV, "CG stagnated above the requested tolerance (residual at FP64 resolution)");
         return MBFEA_OK;
