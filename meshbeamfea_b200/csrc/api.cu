@@ -98,7 +98,7 @@ struct mbfea_ctx {
     DevBuf<int32_t> free_index, fixed;
     // device: pattern
     DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, tile_row_s, send_rows;
-    DevBuf<int32_t> uptr, ucol, usrc, lptr, lcol, lblk;   // solver format (HostPlan::uptr ...)
+    DevBuf<int32_t> uptr, ucol, usrc, lptr, lcol, lofs, ilv_base;   // solver format (HostPlan::uptr ...)
     // device: matrix + vectors.  vals = assembled K (full pattern); vals_s = stored blocks of
     // K~ = S K S^T; lfac/sinv = Cholesky factor of the diagonal blocks and its inverse
     DevBuf<double> vals, vals_s, lfac, sinv, f, ft, x, y, rt, p, Ap, sendbuf;
@@ -210,8 +210,8 @@ void run_spmv_full(mbfea_ctx *c, int kernel, const double *x, double *y)
         launch_spmv_tma(c->st, spmv_tma_grid(ntiles, c->sm_count), ntiles, c->tile_row.p, c->rowptr.p, c->colidx.p,
                         c->vals.p, 0, x, y, nullptr, nullptr);
     } else {
-        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, nullptr, nullptr, nullptr, 0, x, y,
-                              nullptr, nullptr, nullptr);
+        launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, nullptr, nullptr, nullptr, nullptr, 0, x,
+                              y, nullptr, nullptr, nullptr);
     }
     c->launches++;
 }
@@ -230,7 +230,8 @@ void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *part
     } else {
         const bool sym = c->plan.sym_half;
         launch_spmv_rowthread(c->st, nb, c->uptr.p, c->ucol.p, c->vals_s.p, sym ? c->lptr.p : nullptr,
-                              sym ? c->lcol.p : nullptr, sym ? c->lblk.p : nullptr, 1, x, y, partial, sc, pc);
+                              sym ? c->lcol.p : nullptr, sym ? c->lofs.p : nullptr, sym ? c->ilv_base.p : nullptr, 1, x,
+                              y, partial, sc, pc);
     }
     c->launches++;
 }
@@ -469,7 +470,8 @@ void do_precond(mbfea_ctx *c)
     CK(cudaMemsetAsync(c->flag.p, 0, sizeof(int), c->st));
     launch_block_chol(c->st, c->nb(), c->diag_idx.p, c->vals.p, c->lfac.p, c->sinv.p, c->flag.p);
     halo_exchange(c, c->sinv.p, 36);
-    launch_scale_blocks(c->st, c->nb(), c->uptr.p, c->ucol.p, c->usrc.p, c->vals.p, c->sinv.p, c->vals_s.p);
+    launch_scale_blocks(c->st, c->nb(), c->uptr.p, c->ucol.p, c->usrc.p, c->vals.p, c->sinv.p, c->vals_s.p,
+                        c->plan.sym_half ? c->ilv_base.p : nullptr);
     c->launches += 2;
 }
 
@@ -716,11 +718,13 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         upload(c, c->usrc, c->plan.usrc);
         upload(c, c->lptr, c->plan.lptr);
         upload(c, c->lcol, c->plan.lcol);
-        upload(c, c->lblk, c->plan.lblk);
+        upload(c, c->lofs, c->plan.lofs);
+        upload(c, c->ilv_base, c->plan.tile_base);
         upload(c, c->send_rows, c->plan.send_rows);
         CK(c->sendbuf.alloc((size_t)36 * c->plan.send_rows.size()));
         CK(c->vals.alloc((size_t)nnzb * 36));
-        CK(c->vals_s.alloc((size_t)c->plan.ucol.size() * 36));
+        // symmetric-half: interleaved tiles (16-byte units, padded to the longest row of each tile)
+        CK(c->vals_s.alloc(c->plan.sym_half ? (size_t)c->plan.tile_base.back() * 2 : (size_t)c->plan.ucol.size() * 36));
         CK(c->lfac.alloc((size_t)nb * 36));
         CK(c->sinv.alloc((size_t)(nb + ng) * 36));
         CK(c->f.alloc((size_t)6 * nb));

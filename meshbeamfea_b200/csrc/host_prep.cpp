@@ -4,6 +4,7 @@
 // scatter-free assembly on the device) and the vertex-block partition plan.
 // Pure C++17: nothing here touches CUDA.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <thread>
@@ -343,14 +344,28 @@ void build_solver_format(HostPlan &P, bool half)
             }
         }
     });
+    P.tile_base.clear(); P.lofs.clear();
     if (!half) return;
+    // interleaved layout: every tile of 32 rows reserves max-row-length block slots per row
+    const int64_t ntiles = (nb + 31) / 32;
+    P.tile_base.assign((size_t)ntiles + 1, 0);
+    for (int64_t t = 0; t < ntiles; ++t) {
+        int32_t mx = 0;
+        for (int64_t r = t * 32; r < std::min<int64_t>(nb, t * 32 + 32); ++r) mx = std::max(mx, P.uptr[r + 1] - P.uptr[r]);
+        const int64_t next = (int64_t)P.tile_base[t] + (int64_t)mx * 3 * 192;
+        if (next > INT32_MAX) { P.tile_base.clear(); P.sym_half = false; build_solver_format(P, false); return; }
+        P.tile_base[t + 1] = (int32_t)next;
+    }
     // pass 2: transposed references, rows c ascending => each row's list is ascending in c
+    P.lofs.resize(P.lcol.size());
     std::vector<int32_t> cur(P.lptr.begin(), P.lptr.end() - 1);
     for (int64_t c = 0; c < nb; ++c)
         for (int32_t b = P.uptr[c]; b < P.uptr[c + 1]; ++b) {
             const int32_t r = P.ucol[b];
             if (r >= nb) continue;  // ghost column: the owner of r stores its own copy
-            P.lcol[cur[r]] = (int32_t)c; P.lblk[cur[r]] = b; ++cur[r];
+            P.lcol[cur[r]] = (int32_t)c; P.lblk[cur[r]] = b;
+            P.lofs[cur[r]] = P.tile_base[c / 32] + (b - P.uptr[c]) * 3 * 192 + (int32_t)(c % 32) * 6;
+            ++cur[r];
         }
 }
 

@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(128) k_scale_blocks(int64_t nb, const int32_t 
                                                       const int32_t *__restrict__ ucol,
                                                       const int32_t *__restrict__ usrc,
                                                       const double *__restrict__ vals,
-                                                      const double *__restrict__ sinv, double *__restrict__ vals_s)
+                                                      const double *__restrict__ sinv, double *__restrict__ vals_s,
+                                                      const int32_t *__restrict__ tile_base)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
@@ -495,19 +496,28 @@ __global__ void __launch_bounds__(128) k_scale_blocks(int64_t nb, const int32_t 
                 out[i][j] = a;
             }
         }
-        double2 *o = reinterpret_cast<double2 *>(vals_s + (int64_t)b * 36);
+        if (tile_base == nullptr) {   // plain BSR order
+            double2 *o = reinterpret_cast<double2 *>(vals_s + (int64_t)b * 36);
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+            for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = 0; j < 6; j += 2) o[3 * i + j / 2] = make_double2(out[i][j], out[i][j + 1]);
+                for (int j = 0; j < 6; j += 2) o[3 * i + j / 2] = make_double2(out[i][j], out[i][j + 1]);
+        } else {                      // interleaved per 32-row tile (see HostPlan::tile_base)
+            const int64_t k = b - __ldg(uptr + r);
+            double2 *o = reinterpret_cast<double2 *>(vals_s) + (int64_t)__ldg(tile_base + (r >> 5)) + k * 576 + (r & 31) * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int m = 0; m < 3; ++m) o[m * 192 + i] = make_double2(out[i][2 * m], out[i][2 * m + 1]);
+        }
     }
 }
 
 void launch_scale_blocks(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const int32_t *usrc,
-                         const double *vals, const double *sinv, double *vals_s)
+                         const double *vals, const double *sinv, double *vals_s, const int32_t *tile_base)
 {
     if (nb <= 0) return;
-    k_scale_blocks<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, uptr, ucol, usrc, vals, sinv, vals_s);
+    k_scale_blocks<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(nb, uptr, ucol, usrc, vals, sinv, vals_s, tile_base);
 }
 
 // ---------------------------------------------------------------------------
@@ -533,8 +543,9 @@ template <bool SYM>
 __global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
     int64_t nb, const int32_t *__restrict__ uptr, const int32_t *__restrict__ ucol,
     const double *__restrict__ vals, const int32_t *__restrict__ lptr, const int32_t *__restrict__ lcol,
-    const int32_t *__restrict__ lblk, int identity, const double *__restrict__ x, double *__restrict__ y,
-    double *__restrict__ partial, const PcgScalars *sc, const PeerCtx *pc)
+    const int32_t *__restrict__ lofs, const int32_t *__restrict__ tile_base, int identity,
+    const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partial, const PcgScalars *sc,
+    const PeerCtx *pc)
 {
     __shared__ double red[33];
     __shared__ double ts[SYM ? kSpmvThreads * 6 : 1];
@@ -558,11 +569,20 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
             acc = identity ? xi : 0.0;
             // blocks this row stores: thread i streams ROW i of the block, y_r[i] += M[i][:] . x_c
             const int32_t kb = __ldg(uptr + row), ke = __ldg(uptr + row + 1);
+            // SYM: interleaved tile layout -- the CTA's 192 threads read 192 consecutive 16-byte chunks
+            const double2 *vt = SYM ? reinterpret_cast<const double2 *>(vals) + __ldg(tile_base + (r0 >> 5)) + threadIdx.x
+                                    : nullptr;
             for (int32_t k = kb; k < ke; ++k) {
                 const int32_t c = __ldg(ucol + k);
-                const double *v = vals + (int64_t)k * 36 + i * 6;
                 const double *xx = x + (int64_t)c * 6;
-                const double2 v0 = ldg2(v), v1 = ldg2(v + 2), v2 = ldg2(v + 4);
+                double2 v0, v1, v2;
+                if (SYM) {
+                    const double2 *v = vt + (int64_t)(k - kb) * 576;
+                    v0 = __ldg(v); v1 = __ldg(v + 192); v2 = __ldg(v + 384);
+                } else {
+                    const double *v = vals + (int64_t)k * 36 + i * 6;
+                    v0 = ldg2(v); v1 = ldg2(v + 2); v2 = ldg2(v + 4);
+                }
                 const double2 x0 = ldg2(xx), x1 = ldg2(xx + 2), x2 = ldg2(xx + 4);
                 acc = fma(v0.x, x0.x, acc); acc = fma(v0.y, x0.y, acc);
                 acc = fma(v1.x, x1.x, acc); acc = fma(v1.y, x1.y, acc);
@@ -579,9 +599,9 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
             if (live) {
                 const int32_t lb = __ldg(lptr + row), le = __ldg(lptr + row + 1);
                 for (int32_t l = lb; l < le; ++l) {
-                    const double *v = vals + (int64_t)__ldg(lblk + l) * 36 + i * 6;
+                    const double2 *v = reinterpret_cast<const double2 *>(vals) + __ldg(lofs + l) + i;
                     const double xj = __ldg(x + (int64_t)__ldg(lcol + l) * 6 + i);
-                    const double2 v0 = ldg2(v), v1 = ldg2(v + 2), v2 = ldg2(v + 4);
+                    const double2 v0 = __ldg(v), v1 = __ldg(v + 192), v2 = __ldg(v + 384);
                     t0 = fma(v0.x, xj, t0); t1 = fma(v0.y, xj, t1);
                     t2 = fma(v1.x, xj, t2); t3 = fma(v1.y, xj, t3);
                     t4 = fma(v2.x, xj, t4); t5 = fma(v2.y, xj, t5);
@@ -626,15 +646,16 @@ int spmv_rowthread_grid(int64_t nb, bool sym)
 }
 
 void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const double *vals,
-                           const int32_t *lptr, const int32_t *lcol, const int32_t *lblk, int identity,
-                           const double *x, double *y, double *partial, const PcgScalars *sc, const PeerCtx *pc)
+                           const int32_t *lptr, const int32_t *lcol, const int32_t *lofs, const int32_t *tile_base,
+                           int identity, const double *x, double *y, double *partial, const PcgScalars *sc,
+                           const PeerCtx *pc)
 {
     if (lptr != nullptr)
         k_spmv_rowthread<true><<<spmv_rowthread_grid(nb, true), kSpmvThreads, 0, st>>>(
-            nb, uptr, ucol, vals, lptr, lcol, lblk, identity, x, y, partial, sc, pc);
+            nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base, identity, x, y, partial, sc, pc);
     else
         k_spmv_rowthread<false><<<spmv_rowthread_grid(nb, false), kSpmvThreads, 0, st>>>(
-            nb, uptr, ucol, vals, lptr, lcol, lblk, identity, x, y, partial, sc, pc);
+            nb, uptr, ucol, vals, nullptr, nullptr, nullptr, nullptr, identity, x, y, partial, sc, pc);
 }
 
 // ---------------------------------------------------------------------------

@@ -79,13 +79,14 @@ void launch_block_chol(cudaStream_t st, int64_t nb, const int32_t *diag_idx, con
                        double *sinv, int *flag);
 // solver matrix K~ = S K S^T, stored blocks only (sinv: owned rows then ghost rows)
 void launch_scale_blocks(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const int32_t *usrc,
-                         const double *vals, const double *sinv, double *vals_s);
+                         const double *vals, const double *sinv, double *vals_s, const int32_t *tile_base);
 // K4: y = A x (x has nb + n_ghost blocks), partial[blockIdx] = sum x_own . y
 //     identity: unit diagonal implied; lptr/lcol/lblk: transposed references (may be null)
 int  spmv_rowthread_grid(int64_t nb, bool sym);
 void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const double *vals,
-                           const int32_t *lptr, const int32_t *lcol, const int32_t *lblk, int identity,
-                           const double *x, double *y, double *partial, const PcgScalars *sc, const PeerCtx *pc);
+                           const int32_t *lptr, const int32_t *lcol, const int32_t *lofs, const int32_t *tile_base,
+                           int identity, const double *x, double *y, double *partial, const PcgScalars *sc,
+                           const PeerCtx *pc);
 int  spmv_tma_grid(int64_t ntiles, int sm_count);
 size_t spmv_tma_smem_bytes();
 int  spmv_tma_prepare();  // opt in to the large dynamic shared memory; returns cudaError

@@ -38,6 +38,13 @@ struct HostPlan {
     std::vector<int32_t> uptr, ucol, usrc;  // usrc: index of the block in the full pattern
     std::vector<int32_t> lptr, lcol, lblk;  // lblk: stored-block index holding (lcol, r)
     bool sym_half = false;
+    // Symmetric-half values are stored INTERLEAVED per tile of 32 block rows (sliced ELL): the
+    // 16-byte chunk m (0..2) of scalar row i of the k-th stored block of local row lr sits at
+    // 16-byte unit  tile_base[tile] + (3k + m) * 192 + 6 lr + i,  so the 192 threads of a CTA
+    // read 192 consecutive chunks per load instruction.  lofs[l] = unit of (m = 0, i = 0) of the
+    // block a transposed reference points to.  Plain BSR order is kept for full-row storage.
+    std::vector<int32_t> tile_base;         // #tiles + 1, in 16-byte units
+    std::vector<int32_t> lofs;
     std::vector<int64_t> ghost_global;// ascending => grouped by owner
     std::vector<int32_t> ghost_owner;
     std::vector<int32_t> send_rows;   // local row ids grouped by destination rank

@@ -27,16 +27,19 @@ c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job
 c.execute(allow_unconverged=True)
 t = c.trace(256).astype(np.int64)
 st = c.stats()
+# batches end with the residual check: keep iterations whose successor is in the same batch
 sel = t[20:250]
 names = ["spmv_in", "spmv_go", "upd_in", "upd_go", "pupd_in", "pupd_go", "push_in", "push_out"]
 nxt = t[21:251, 0]
 if world > 1:
     segs = {"spmv wait halo": sel[:, 1] - sel[:, 0], "spmv body+tail": sel[:, 2] - sel[:, 1], "update wait pAp": sel[:, 3] - sel[:, 2],
-            "update body+tail": sel[:, 4] - sel[:, 3], "pupdate wait rz": sel[:, 5] - sel[:, 4], "pupdate body+tail": sel[:, 6] - sel[:, 5],
-            "push body": sel[:, 7] - sel[:, 6], "push_out -> next spmv": nxt - sel[:, 7], "whole iteration": nxt - sel[:, 0]}
+            "update body+tail": sel[:, 4] - sel[:, 3], "pupdate wait rho": sel[:, 5] - sel[:, 4],
+            "pupdate+push+tail": nxt - sel[:, 5], "whole iteration": nxt - sel[:, 0]}
 else:
     segs = {"spmv": sel[:, 2] - sel[:, 0], "update": sel[:, 4] - sel[:, 2], "pupdate": nxt - sel[:, 4], "whole iteration": nxt - sel[:, 0]}
 msg = [f"[trace] rank {rank}/{world}: ms/it (stats) {st['ms_pcg'] / max(1, st['iterations']):.4f}"]
+ok = (nxt - sel[:, 0]) < 3 * np.median(nxt - sel[:, 0])
+segs = {k: v[ok] for k, v in segs.items()}
 for k, v in segs.items():
     msg.append(f"   {k:24s} median {np.median(v) / 1e3:8.2f} us   mean {np.mean(v) / 1e3:8.2f} us   max {np.max(v) / 1e3:8.2f} us")
 print("\n".join(msg), flush=True)

@@ -104,14 +104,15 @@ def test_stage_by_stage_parity(built, name):
         assert np.array_equal(c.edge_forces(), F)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
-def test_both_spmv_kernels_give_the_same_solution(built, kernel):
-    job = syn.cubic_lattice(14)
-    O = to_oracle(job)
-    U, F = orc.solve(O)
-    with ctx_for(job, spmv_kernel=kernel) as c:
-        c.execute()
-        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
+@pytest.mark.parametrize("storage,kernel", [(2, 1), (1, 1), (1, 2)],
+                         ids=["symmetric_half-rowthread", "full_rows-rowthread", "full_rows-tma"])
+def test_every_solver_format_and_kernel_gives_the_same_solution(built, storage, kernel):
+    for job in (syn.cubic_lattice(14), syn.random_mesh(77), syn.gridshell(21)):
+        O = to_oracle(job)
+        U, F = orc.solve(O)
+        with ctx_for(job, spmv_kernel=kernel, storage=storage) as c:
+            c.execute()
+            assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
 
 
 def test_reference_fixture_and_screenshot_golden(built):
@@ -229,7 +230,7 @@ def test_run_to_run_bitwise_determinism(built):
 
 def test_graph_and_plain_launch_agree(built):
     job = syn.planar_grid(16)
-    with ctx_for(job, use_graph=True) as a, ctx_for(job, use_graph=False, check_every=10) as b:
+    with ctx_for(job, use_graph=True, check_every=10) as a, ctx_for(job, use_graph=False, check_every=10) as b:
         a.execute(); b.execute()
         assert a.stats()["iterations"] == b.stats()["iterations"]
         assert np.array_equal(a.displacements(), b.displacements())
