@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmbfea.so")
+# MBFEA_LIB selects an alternative build of the same ABI (kernel-tuning A/B runs)
+LIB_PATH = os.environ.get("MBFEA_LIB") or os.path.join(_HERE, "libmbfea.so")
 
 # mbfea_status
 OK, EPRECOND, ERANGE_FIXED, ERANGE_FORCE, ECUDA, ESTATE, ENOCONV, ESINGULAR, EIO, EARG = range(10)

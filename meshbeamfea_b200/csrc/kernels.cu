@@ -539,8 +539,26 @@ void launch_scale_blocks(cudaStream_t st, int64_t nb, const int32_t *uptr, const
 constexpr int kRowsPerCta = 32;
 constexpr int kSpmvThreads = kRowsPerCta * 6;
 
+// tuning knobs of the symmetric-half variant (A/B-tested on B200, see profiles/)
+#ifndef MBFEA_SYM_MINB
+#define MBFEA_SYM_MINB 6      // resident CTAs per SM the register allocation is pinned to
+#endif
+#ifndef MBFEA_SYM_UNROLL
+#define MBFEA_SYM_UNROLL 0    // explicit unroll factor of the block loops (0: leave it to the compiler)
+#endif
+#define MBFEA_PRAGMA_(x) _Pragma(#x)
+#define MBFEA_UNROLL_(n) MBFEA_PRAGMA_(unroll n)
+#if MBFEA_SYM_UNROLL > 0
+#define MBFEA_UNROLL(n) MBFEA_UNROLL_(n)
+#else
+#define MBFEA_UNROLL(n)
+#endif
+#ifndef MBFEA_SYM_PREFETCH
+#define MBFEA_SYM_PREFETCH 0  // fetch the next tile's row pointers while working on this one
+#endif
+
 template <bool SYM>
-__global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
+__global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv_rowthread(
     int64_t nb, const int32_t *__restrict__ uptr, const int32_t *__restrict__ ucol,
     const double *__restrict__ vals, const int32_t *__restrict__ lptr, const int32_t *__restrict__ lcol,
     const int32_t *__restrict__ lofs, const int32_t *__restrict__ tile_base, int identity,
@@ -560,18 +578,36 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
     }
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
     double dot = 0.0;
-    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+    const int64_t stride = (int64_t)gridDim.x * kRowsPerCta;
+    // row pointers of the current tile; with MBFEA_SYM_PREFETCH the next tile's are requested before
+    // this tile's blocks, so the pointer -> column -> x chain of the next tile is one level shorter
+    int32_t kb = 0, ke = 0, lb = 0, le = 0, tb = 0;
+    {
+        const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + lr;
+        if (row < nb) {
+            kb = __ldg(uptr + row); ke = __ldg(uptr + row + 1);
+            if (SYM) { lb = __ldg(lptr + row); le = __ldg(lptr + row + 1); tb = __ldg(tile_base + (row >> 5)); }
+        }
+    }
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += stride) {
         const int64_t row = r0 + lr;
         const bool live = row < nb;
+        int32_t nkb = 0, nke = 0, nlb = 0, nle = 0, ntb = 0;
+        if (MBFEA_SYM_PREFETCH) {
+            const int64_t nrow = row + stride;
+            if (nrow < nb) {
+                nkb = __ldg(uptr + nrow); nke = __ldg(uptr + nrow + 1);
+                if (SYM) { nlb = __ldg(lptr + nrow); nle = __ldg(lptr + nrow + 1); ntb = __ldg(tile_base + (nrow >> 5)); }
+            }
+        }
         double xi = 0.0, acc = 0.0;
         if (live) {
             xi = __ldg(x + row * 6 + i);
             acc = identity ? xi : 0.0;
             // blocks this row stores: thread i streams ROW i of the block, y_r[i] += M[i][:] . x_c
-            const int32_t kb = __ldg(uptr + row), ke = __ldg(uptr + row + 1);
             // SYM: interleaved tile layout -- the CTA's 192 threads read 192 consecutive 16-byte chunks
-            const double2 *vt = SYM ? reinterpret_cast<const double2 *>(vals) + __ldg(tile_base + (r0 >> 5)) + threadIdx.x
-                                    : nullptr;
+            const double2 *vt = SYM ? reinterpret_cast<const double2 *>(vals) + tb + threadIdx.x : nullptr;
+MBFEA_UNROLL(MBFEA_SYM_UNROLL)
             for (int32_t k = kb; k < ke; ++k) {
                 const int32_t c = __ldg(ucol + k);
                 const double *xx = x + (int64_t)c * 6;
@@ -591,13 +627,13 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
         }
         if (SYM) {
             // transposed references: block M = K~(c, r) lives in row c's storage and y_r += M^T x_c.
-            // Thread i again streams ROW i of M (same coalesced 48-byte slices) but needs only the
+            // Thread i again streams ROW i of M (coalesced chunks of row c's tile) but needs only the
             // single entry x_c[i]: it accumulates M[i][k] * x_c[i] for all six outputs k, and the
             // six threads of the row exchange their partial vectors once per tile through shared
             // memory.  Half the register-fill traffic of gathering columns.
             double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
             if (live) {
-                const int32_t lb = __ldg(lptr + row), le = __ldg(lptr + row + 1);
+MBFEA_UNROLL(MBFEA_SYM_UNROLL)
                 for (int32_t l = lb; l < le; ++l) {
                     const double2 *v = reinterpret_cast<const double2 *>(vals) + __ldg(lofs + l) + i;
                     const double xj = __ldg(x + (int64_t)__ldg(lcol + l) * 6 + i);
@@ -617,6 +653,15 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
         if (live) {
             y[row * 6 + i] = acc;
             dot = fma(xi, acc, dot);
+        }
+        if (MBFEA_SYM_PREFETCH) {
+            kb = nkb; ke = nke; lb = nlb; le = nle; tb = ntb;
+        } else {
+            const int64_t nrow = row + stride;
+            if (nrow < nb) {
+                kb = __ldg(uptr + nrow); ke = __ldg(uptr + nrow + 1);
+                if (SYM) { lb = __ldg(lptr + nrow); le = __ldg(lptr + nrow + 1); tb = __ldg(tile_base + (nrow >> 5)); }
+            }
         }
     }
     if (partial != nullptr) {
@@ -641,7 +686,7 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? 6 : 8) k_spmv_rowthread(
 int spmv_rowthread_grid(int64_t nb, bool sym)
 {
     const int64_t tiles = (nb + kRowsPerCta - 1) / kRowsPerCta;
-    const int64_t cap = sym ? 148 * 6 : 148 * 8;
+    const int64_t cap = sym ? 148 * MBFEA_SYM_MINB : 148 * 8;
     return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
