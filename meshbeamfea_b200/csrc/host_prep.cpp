@@ -4,9 +4,13 @@
 // scatter-free assembly on the device) and the vertex-block partition plan.
 // Pure C++17: nothing here touches CUDA.
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 #include "mbfea_internal.hpp"
@@ -164,9 +168,27 @@ static inline int32_t owner_of(int64_t g, int64_t nb_global, int32_t world)
     return r;
 }
 
+static double wall_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+struct PrepTrace {
+    bool on = std::getenv("MBFEA_PREP_TRACE") != nullptr;
+    double t = wall_ms();
+    void lap(const char *what)
+    {
+        if (!on) return;
+        const double n = wall_ms();
+        std::fprintf(stderr, "[mbfea prep] %-28s %8.2f ms\n", what, n - t);
+        t = n;
+    }
+};
+
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                 int32_t rank, int32_t world, bool with_contrib, HostPlan &P)
 {
+    PrepTrace tr;
     P.V = V; P.E = E; P.rank = rank; P.world = world;
     P.nb_global = build_free_map(V, F, fixed, P.free_index);
     const int64_t nbg = P.nb_global;
@@ -174,34 +196,48 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     P.row_end = nbg * (rank + 1) / world;
     const int64_t r0 = P.row_begin, nb = P.row_end - P.row_begin;
     const int32_t *fm = P.free_index.data();
+    tr.lap("free map");
 
-    // pass 1: entries per owned row (diagonal contributions + off-diagonal ones)
+    // pass 1: entries per owned row (diagonal contributions + off-diagonal ones).  Rows are split
+    // into one range per thread; every thread scans all beams in ascending order and handles the
+    // end points that fall into its range, so each row's entries stay in ascending element order.
     std::vector<int32_t> cnt((size_t)nb + 1, 0);
-    for (int64_t e = 0; e < E; ++e) {
-        const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
-        if (fa >= 0 && fa >= r0 && fa < r0 + nb) cnt[fa - r0] += (fb >= 0) ? 2 : 1;
-        if (fb >= 0 && fb >= r0 && fb < r0 + nb) cnt[fb - r0] += (fa >= 0) ? 2 : 1;
-    }
+    auto scan = [&](int64_t lo, int64_t hi, auto &&visit) {
+        for (int64_t e = 0; e < E; ++e) {
+            const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
+            const int64_t la = fa - r0, lb2 = fb - r0;
+            if (fa >= 0 && la >= lo && la < hi) visit(la, e, true, fa, fb);
+            if (fb >= 0 && lb2 >= lo && lb2 < hi) visit(lb2, e, false, fa, fb);
+        }
+    };
+    parallel_ranges(nb, 1 << 15, [&](int64_t lo, int64_t hi, int) {
+        scan(lo, hi, [&](int64_t lrow, int64_t, bool first, int64_t fa, int64_t fb) {
+            cnt[lrow] += ((first ? fb : fa) >= 0) ? 2 : 1;
+        });
+    });
+    tr.lap("count pass");
     std::vector<int64_t> start((size_t)nb + 1, 0);
     for (int64_t r = 0; r < nb; ++r) start[r + 1] = start[r] + cnt[r];
     const int64_t nent = start[nb];
     struct Ent { int32_t col; int32_t code; };  // global column, (e<<2)|which
-    std::vector<Ent> ent((size_t)nent);
+    std::unique_ptr<Ent[]> ent_store(new Ent[(size_t)nent + 1]);  // uninitialised: first touched by its own thread
+    Ent *const ent = ent_store.get();
     {
         std::vector<int64_t> pos(start.begin(), start.end() - 1);
-        for (int64_t e = 0; e < E; ++e) {  // ascending element order
-            const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
-            const int32_t code = (int32_t)(e << 2);
-            if (fa >= 0 && fa >= r0 && fa < r0 + nb) {
-                ent[pos[fa - r0]++] = {(int32_t)fa, code | SUB_00};
-                if (fb >= 0) ent[pos[fa - r0]++] = {(int32_t)fb, code | SUB_01};
-            }
-            if (fb >= 0 && fb >= r0 && fb < r0 + nb) {
-                if (fa >= 0) ent[pos[fb - r0]++] = {(int32_t)fa, code | SUB_10};
-                ent[pos[fb - r0]++] = {(int32_t)fb, code | SUB_11};
-            }
-        }
+        parallel_ranges(nb, 1 << 15, [&](int64_t lo, int64_t hi, int) {
+            scan(lo, hi, [&](int64_t lrow, int64_t e, bool first, int64_t fa, int64_t fb) {
+                const int32_t code = (int32_t)(e << 2);
+                if (first) {
+                    ent[pos[lrow]++] = {(int32_t)fa, code | SUB_00};
+                    if (fb >= 0) ent[pos[lrow]++] = {(int32_t)fb, code | SUB_01};
+                } else {
+                    if (fa >= 0) ent[pos[lrow]++] = {(int32_t)fa, code | SUB_10};
+                    ent[pos[lrow]++] = {(int32_t)fb, code | SUB_11};
+                }
+            });
+        });
     }
+    tr.lap("fill pass");
     // a free vertex with no beam still owns a (zero) diagonal block so that the
     // row exists; the solver reports it as singular.
     // per row: stable sort by column (keeps ascending element order), count blocks
@@ -209,7 +245,7 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     std::vector<int32_t> nblk((size_t)nb, 0);
     parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
         for (int64_t r = lo; r < hi; ++r) {
-            Ent *b = ent.data() + start[r], *e2 = ent.data() + start[r + 1];
+            Ent *b = ent + start[r], *e2 = ent + start[r + 1];
             if (e2 - b <= 24) {
                 for (Ent *i = b + 1; i < e2; ++i) {
                     Ent x = *i; Ent *j = i - 1;
@@ -227,16 +263,18 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
             nblk[r] = n + (has_diag ? 0 : 1);
         }
     });
+    tr.lap("row sort + count");
     for (int64_t r = 0; r < nb; ++r) P.rowptr[r + 1] = P.rowptr[r] + nblk[r];
     const int64_t nnzb = P.rowptr[nb];
     P.colidx.assign((size_t)nnzb, 0);
     P.diag_idx.assign((size_t)nb, 0);
-    std::vector<int32_t> gcol((size_t)nnzb);  // global column ids first
+    std::unique_ptr<int32_t[]> gcol_store(new int32_t[(size_t)nnzb + 1]);  // global column ids first
+    int32_t *const gcol = gcol_store.get();
     if (with_contrib) { P.contrib_ptr.assign((size_t)nnzb + 1, 0); P.contrib.assign((size_t)nent, 0); }
     else { P.contrib_ptr.clear(); P.contrib.clear(); }
     parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
         for (int64_t r = lo; r < hi; ++r) {
-            const Ent *b = ent.data() + start[r], *e2 = ent.data() + start[r + 1];
+            const Ent *b = ent + start[r], *e2 = ent + start[r + 1];
             int64_t k = P.rowptr[r] - 1;
             const int32_t me = (int32_t)(r0 + r);
             bool diag_done = false;
@@ -262,29 +300,34 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
         }
     });
     if (with_contrib) P.contrib_ptr[nnzb] = (int32_t)nent;
+    tr.lap("pattern + contributor fill");
 
     // ghosts: global columns outside the owned range, ascending
     P.ghost_global.clear();
-    for (int64_t k = 0; k < nnzb; ++k)
-        if (gcol[k] < r0 || gcol[k] >= r0 + nb) P.ghost_global.push_back(gcol[k]);
+    if (world > 1)
+        for (int64_t k = 0; k < nnzb; ++k)
+            if (gcol[k] < r0 || gcol[k] >= r0 + nb) P.ghost_global.push_back(gcol[k]);
     std::sort(P.ghost_global.begin(), P.ghost_global.end());
     P.ghost_global.erase(std::unique(P.ghost_global.begin(), P.ghost_global.end()), P.ghost_global.end());
     const int64_t ng = (int64_t)P.ghost_global.size();
     P.ghost_owner.resize((size_t)ng);
     for (int64_t i = 0; i < ng; ++i) P.ghost_owner[i] = owner_of(P.ghost_global[i], nbg, world);
-    for (int64_t k = 0; k < nnzb; ++k) {
-        const int64_t g = gcol[k];
-        if (g >= r0 && g < r0 + nb) P.colidx[k] = (int32_t)(g - r0);
-        else {
-            const auto it = std::lower_bound(P.ghost_global.begin(), P.ghost_global.end(), g);
-            P.colidx[k] = (int32_t)(nb + (it - P.ghost_global.begin()));
+    parallel_ranges(nnzb, 1 << 18, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t k = lo; k < hi; ++k) {
+            const int64_t g = gcol[k];
+            if (g >= r0 && g < r0 + nb) P.colidx[k] = (int32_t)(g - r0);
+            else {
+                const auto it = std::lower_bound(P.ghost_global.begin(), P.ghost_global.end(), g);
+                P.colidx[k] = (int32_t)(nb + (it - P.ghost_global.begin()));
+            }
         }
-    }
+    });
+    tr.lap("ghosts + local column ids");
     // sends: the pattern is symmetric, so rank q needs owned row i from us iff
     // row i has a column owned by q.  Sorted by (dest, row) == the order in which
     // q lists them among its ghosts (ascending global id).
     std::vector<std::pair<int32_t, int32_t>> snd;  // (dest, local row)
-    for (int64_t r = 0; r < nb; ++r) {
+    for (int64_t r = 0; world > 1 && r < nb; ++r) {
         int32_t last = -1;
         for (int64_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
             if (P.colidx[k] < nb) continue;
@@ -309,10 +352,12 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
         nbq.send_offset = sl - P.send_dest.begin(); nbq.send_count = sh - sl;
         if (nbq.recv_count || nbq.send_count) P.neighbors.push_back(nbq);
     }
+    tr.lap("send lists");
 }
 
 void build_solver_format(HostPlan &P, bool half)
 {
+    PrepTrace tr;
     const int64_t nb = P.nb();
     P.sym_half = half;
     P.uptr.assign((size_t)nb + 1, 0);
@@ -345,6 +390,7 @@ void build_solver_format(HostPlan &P, bool half)
         }
     });
     P.tile_base.clear(); P.lofs.clear();
+    tr.lap("solver format: stored blocks");
     if (!half) return;
     // interleaved layout: every tile of 32 rows reserves max-row-length block slots per row
     const int64_t ntiles = (nb + 31) / 32;
@@ -367,6 +413,7 @@ void build_solver_format(HostPlan &P, bool half)
             P.lofs[cur[r]] = P.tile_base[c / 32] + (b - P.uptr[c]) * 3 * 192 + (int32_t)(c % 32) * 6;
             ++cur[r];
         }
+    tr.lap("solver format: transposed refs");
 }
 
 void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
