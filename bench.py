@@ -327,8 +327,13 @@ def main():
             set_job(); ctx.execute(); ctx.displacements_into(U); ctx.edge_forces_into(F)
         barrier()
         t0 = time.perf_counter()
+        parts = [0.0, 0.0, 0.0]
         for _ in range(args.steps):
-            set_job(); ctx.execute(); ctx.displacements_into(U); ctx.edge_forces_into(F)
+            ta = time.perf_counter(); set_job()
+            tb = time.perf_counter(); ctx.execute()
+            tc = time.perf_counter(); ctx.displacements_into(U); ctx.edge_forces_into(F)
+            td = time.perf_counter()
+            parts[0] += tb - ta; parts[1] += tc - tb; parts[2] += td - tc
         barrier()
         dte = time.perf_counter() - t0
         if world > 1:
@@ -338,6 +343,8 @@ def main():
         s2 = ctx.stats()
         e2e = {"value": E / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dte / args.steps,
+               "ms_set_job": 1e3 * parts[0] / args.steps, "ms_execute": 1e3 * parts[1] / args.steps,
+               "ms_fetch_results": 1e3 * parts[2] / args.steps,
                "ms_host_prep": s2["ms_host_prep"], "ms_h2d_incl_plan": s2["ms_h2d"], "ms_d2h": s2["ms_d2h"]}
 
     out = None

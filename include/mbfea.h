@@ -158,6 +158,14 @@ int mbfea_get_displacements(mbfea_ctx *ctx, double *U_cm);
 int mbfea_get_edge_forces(mbfea_ctx *ctx, double *F6x2E);
 int mbfea_get_stats(const mbfea_ctx *ctx, mbfea_stats *out);
 
+/* ---- colour-mapping pre-pass: what the reference recomputes on the CPU right
+ *      after the solve for its viewer and colour bar -- per force component the
+ *      min / max over the 2E beam-end values (Colormap's labels
+ *      [REF src/colorbar.cpp:79-111]) and the values normalised to [0,1]
+ *      (igl::colormap(..., normalize = true) [REF src/gui.cpp:514-526]).      */
+int mbfea_get_force_ranges(mbfea_ctx *ctx, double mins6[6], double maxs6[6]);
+int mbfea_get_edge_forces_normalized(mbfea_ctx *ctx, double *T6x2E);
+
 /* result files the reference has fea::solve write when a file name is set
  * [REF src/beamsimulator.cpp:46-54]: V x 6 and E x 12, ',' separated,
  * precision 14.  Opt-in here.                                               */

@@ -77,6 +77,8 @@ SIGNATURES = {
     "mbfea_get_displacements": (C.c_int, [_vp, _pd]),
     "mbfea_get_edge_forces": (C.c_int, [_vp, _pd]),
     "mbfea_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "mbfea_get_force_ranges": (C.c_int, [_vp, _pd, _pd]),
+    "mbfea_get_edge_forces_normalized": (C.c_int, [_vp, _pd]),
     "mbfea_write_displacements_csv": (C.c_int, [_vp, C.c_char_p]),
     "mbfea_write_element_forces_csv": (C.c_int, [_vp, C.c_char_p]),
     "mbfea_get_props": (C.c_int, [_vp, _pd]),

@@ -96,6 +96,9 @@ struct mbfea_ctx {
     DevBuf<ElemRec> rec;
     DevBuf<ElemGeom> geom;
     DevBuf<int32_t> free_index, fixed;
+    // staging for set_job (kept: a re-submitted mesh of the same size costs no cudaMalloc/cudaFree)
+    DevBuf<double> stg_nodes, stg_normals, stg_props;
+    DevBuf<int32_t> stg_elems, stg_scratch;
     // device: pattern
     DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, tile_row_s, send_rows;
     DevBuf<int32_t> uptr, ucol, usrc, lptr, lcol, lofs, ilv_base;   // solver format (HostPlan::uptr ...)
@@ -685,12 +688,21 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                 c->tma_ok = false;  // a single row longer than a stage: row-thread kernel only
         const double t1 = now_ms();
         c->stats.ms_host_prep = t1 - t0;
+        const bool ptrace = std::getenv("MBFEA_PREP_TRACE") != nullptr;
+        double tl = t1;
+        auto lap = [&](const char *what) {
+            if (!ptrace) return;
+            cudaStreamSynchronize(c->st);
+            const double n = now_ms();
+            std::fprintf(stderr, "[mbfea set_job] %-28s %8.2f ms\n", what, n - tl);
+            tl = n;
+        };
 
         const int64_t nb = c->nb(), ng = c->ng(), nnzb = c->plan.nnzb();
         // mesh -> device, repacked into aligned records
         {
-            DevBuf<double> d_nodes, d_normals, d_props;
-            DevBuf<int32_t> d_elems, d_scratch;
+            DevBuf<double> &d_nodes = c->stg_nodes, &d_normals = c->stg_normals, &d_props = c->stg_props;
+            DevBuf<int32_t> &d_elems = c->stg_elems, &d_scratch = c->stg_scratch;
             upload(c, d_nodes, nodes_cm, (size_t)3 * V);
             upload(c, d_elems, elems_cm, (size_t)2 * E);
             upload(c, d_normals, normals_cm, (size_t)3 * E);
@@ -705,7 +717,9 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             launch_pack_elems(c->st, E, d_elems.p, d_normals.p, d_props.p, c->rec.p);
             launch_free_map(c->st, V, F, c->fixed.p, c->free_index.p, d_scratch.p);  // K3
             CK(cudaStreamSynchronize(c->st));
+            lap("mesh upload + pack + K3");
         }
+        lap("free temporaries");
         upload(c, c->rowptr, c->plan.rowptr);
         upload(c, c->colidx, c->plan.colidx);
         upload(c, c->diag_idx, c->plan.diag_idx);
@@ -721,6 +735,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         upload(c, c->lofs, c->plan.lofs);
         upload(c, c->ilv_base, c->plan.tile_base);
         upload(c, c->send_rows, c->plan.send_rows);
+        lap("plan upload");
         CK(c->sendbuf.alloc((size_t)36 * c->plan.send_rows.size()));
         CK(c->vals.alloc((size_t)nnzb * 36));
         // symmetric-half: interleaved tiles (16-byte units, padded to the longest row of each tile)
@@ -742,8 +757,10 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         // the contributor lists are only needed on the device from here on
         c->plan.contrib.clear(); c->plan.contrib.shrink_to_fit();
         c->plan.contrib_ptr.clear(); c->plan.contrib_ptr.shrink_to_fit();
+        lap("matrix/vector allocation");
         upload_forces(c, nF, f_node, f_dof, f_mag);
         CK(cudaStreamSynchronize(c->st));
+        lap("load vector");
         setup_p2p_halo(c);
         c->stats.ms_h2d = now_ms() - t1;
 
@@ -1007,6 +1024,53 @@ int mbfea_get_edge_forces(mbfea_ctx *c, double *F6x2E)
         CK(cudaMemcpyAsync(F6x2E, c->F6.p, (size_t)12 * c->E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         c->stats.ms_d2h += now_ms() - t0;
+        return MBFEA_OK;
+    });
+}
+
+// ---- colour-mapping pre-pass ------------------------------------
+static int force_ranges_device(mbfea_ctx *c, DevBuf<double> &range)
+{
+    const int64_t n = 2 * c->E;
+    DevBuf<double> pmin, pmax;
+    CK(pmin.alloc((size_t)6 * force_minmax_parts(n)));
+    CK(pmax.alloc((size_t)6 * force_minmax_parts(n)));
+    CK(range.alloc(12));
+    launch_force_ranges(c->st, n, c->F6.p, pmin.p, pmax.p, range.p);
+    CK(cudaStreamSynchronize(c->st));
+    return MBFEA_OK;
+}
+
+int mbfea_get_force_ranges(mbfea_ctx *c, double mins6[6], double maxs6[6])
+{
+    if (int rc = need_job(c)) return rc;
+    if (!mins6 || !maxs6) return fail(c, MBFEA_EARG, "NULL");
+    if (!c->recovered) return fail(c, MBFEA_ESTATE, "no results: call mbfea_execute first");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        DevBuf<double> range;
+        force_ranges_device(c, range);
+        double h[12];
+        CK(cudaMemcpy(h, range.p, sizeof h, cudaMemcpyDeviceToHost));
+        std::copy(h, h + 6, mins6);
+        std::copy(h + 6, h + 12, maxs6);
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_get_edge_forces_normalized(mbfea_ctx *c, double *T6x2E)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!T6x2E) return fail(c, MBFEA_EARG, "NULL");
+    if (!c->recovered) return fail(c, MBFEA_ESTATE, "no results: call mbfea_execute first");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        DevBuf<double> range, out;
+        force_ranges_device(c, range);
+        CK(out.alloc((size_t)12 * c->E));
+        launch_force_normalize(c->st, 2 * c->E, c->F6.p, range.p, out.p);
+        CK(cudaMemcpyAsync(T6x2E, out.p, (size_t)12 * c->E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
         return MBFEA_OK;
     });
 }

@@ -1384,6 +1384,75 @@ __global__ void __launch_bounds__(128) k_element_forces(int64_t E, const ElemRec
         *reinterpret_cast<double2 *>(F6x2E + (int64_t)c * 2 * E + 2 * e) = make_double2(fe[c], fe[6 + c]);
 }
 
+// ---------------------------------------------------------------------------
+// Colour-mapping pre-pass (the step right after the hot path in the reference:
+// igl::colormap(..., normalize=true) + the colour bar's min/max
+// [REF src/gui.cpp:514-526; src/colorbar.cpp:79-87]): per force component the
+// minimum and maximum over the 2E beam-end values, two-level, order-independent.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_force_minmax(int64_t n, const double *__restrict__ F, double *__restrict__ pmin,
+                                                      double *__restrict__ pmax)
+{
+    __shared__ double smin[8], smax[8];
+    const int c = blockIdx.y;
+    const double *v = F + (int64_t)c * n;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[j];
+        lo = fmin(lo, x); hi = fmax(hi, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fmin(lo, smin[w]); hi = fmax(hi, smax[w]); }
+        pmin[c * gridDim.x + blockIdx.x] = lo; pmax[c * gridDim.x + blockIdx.x] = hi;
+    }
+}
+
+__global__ void k_force_minmax_finish(int nparts, const double *__restrict__ pmin, const double *__restrict__ pmax,
+                                      double *__restrict__ out /* 6 mins then 6 maxs */)
+{
+    const int c = threadIdx.x;
+    if (c >= 6) return;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int j = 0; j < nparts; ++j) { lo = fmin(lo, pmin[c * nparts + j]); hi = fmax(hi, pmax[c * nparts + j]); }
+    out[c] = lo; out[6 + c] = hi;
+}
+
+// t = (v - min) / (max - min) per component (0 when the component is constant)
+__global__ void k_force_normalize(int64_t n, const double *__restrict__ F, const double *__restrict__ range,
+                                  double *__restrict__ out)
+{
+    const int c = blockIdx.y;
+    const double lo = range[c], hi = range[6 + c];
+    const double inv = hi > lo ? 1.0 / (hi - lo) : 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)c * n + j] = (F[(int64_t)c * n + j] - lo) * inv;
+}
+
+int force_minmax_parts(int64_t n)
+{
+    const int64_t b = (n + 255) / 256;
+    return (int)(b < 1 ? 1 : (b > 148 ? 148 : b));
+}
+
+void launch_force_ranges(cudaStream_t st, int64_t n, const double *F, double *pmin, double *pmax, double *range)
+{
+    const int parts = force_minmax_parts(n);
+    k_force_minmax<<<dim3((unsigned)parts, 6), 256, 0, st>>>(n, F, pmin, pmax);
+    k_force_minmax_finish<<<1, 32, 0, st>>>(parts, pmin, pmax, range);
+}
+
+void launch_force_normalize(cudaStream_t st, int64_t n, const double *F, const double *range, double *out)
+{
+    k_force_normalize<<<dim3((unsigned)force_minmax_parts(n), 6), 256, 0, st>>>(n, F, range, out);
+}
+
 void launch_element_forces(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4,
                            const double *U_rm, double *F6x2E)
 {

@@ -132,4 +132,9 @@ void launch_colmajor_to_rowmajor(cudaStream_t st, int64_t V, const double *U_cm,
 void launch_element_forces(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4,
                            const double *U_rm, double *F6x2E);
 
+// colour-mapping pre-pass: per-component min/max of the 6 x n force table, and its normalisation
+int  force_minmax_parts(int64_t n);
+void launch_force_ranges(cudaStream_t st, int64_t n, const double *F, double *pmin, double *pmax, double *range);
+void launch_force_normalize(cudaStream_t st, int64_t n, const double *F, const double *range, double *out);
+
 }}  // namespace mbfea::dev

@@ -259,6 +259,18 @@ class Context:
         self._ck(self._lib.mbfea_get_edge_forces(self._h, ptr(F, _pd)))
         return F
 
+    def force_ranges(self):
+        """(min[6], max[6]) of the beam-end forces per component (colour-bar labels)."""
+        lo, hi = np.empty(6), np.empty(6)
+        self._ck(self._lib.mbfea_get_force_ranges(self._h, ptr(lo, _pd), ptr(hi, _pd)))
+        return lo, hi
+
+    def edge_forces_normalized(self) -> np.ndarray:
+        """6 x 2E, each component mapped to [0,1] by its own min/max."""
+        T = np.empty((6, 2 * self.E), np.float64)
+        self._ck(self._lib.mbfea_get_edge_forces_normalized(self._h, ptr(T, _pd)))
+        return T
+
     def displacements_into(self, U_flat: np.ndarray):
         self._ck(self._lib.mbfea_get_displacements(self._h, ptr(U_flat, _pd)))
 

@@ -196,6 +196,25 @@ def test_error_conventions_through_the_abi(built, tmp_path):
             c.load_scenario(cfg2)
 
 
+def test_colour_mapping_prepass(built):
+    """min/max per force component (colour-bar labels: the README screenshot shows Mz in
+    [-200, 100]) and the normalised table, against numpy on the fetched forces."""
+    with ctx_for(syn.two_line_segments(), tol=1e-13) as c:
+        c.execute()
+        lo, hi = c.force_ranges()
+        assert lo[5] == pytest.approx(-200.0, abs=1e-7) and hi[5] == pytest.approx(100.0, abs=1e-7)
+    job = syn.gridshell(23)
+    with ctx_for(job) as c:
+        c.execute()
+        F = c.edge_forces()
+        lo, hi = c.force_ranges()
+        assert np.array_equal(lo, F.min(axis=1)) and np.array_equal(hi, F.max(axis=1))
+        T = c.edge_forces_normalized()
+        span = np.where(hi > lo, hi - lo, 1.0)
+        assert np.allclose(T, (F - lo[:, None]) / span[:, None], rtol=1e-14, atol=1e-15)
+        assert T.min() >= 0.0 and T.max() <= 1.0
+
+
 def test_forces_on_fixed_vertices_duplicates_and_reload(built):
     job = syn.planar_grid(10)
     O = to_oracle(job)
