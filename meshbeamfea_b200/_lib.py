@@ -23,7 +23,7 @@ class Options(C.Structure):
         ("device", C.c_int32), ("verbose", C.c_int32), ("tol", C.c_double), ("max_iter", C.c_int64),
         ("check_every", C.c_int32), ("spmv_kernel", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("use_graph", C.c_int32), ("comm_mode", C.c_int32), ("storage", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("cg_variant", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -104,7 +104,7 @@ struct mbfea_ctx {
     DevBuf<int32_t> uptr, ucol, usrc, lptr, lcol, lofs, ilv_base;   // solver format (HostPlan::uptr ...)
     // device: matrix + vectors.  vals = assembled K (full pattern); vals_s = stored blocks of
     // K~ = S K S^T; lfac/sinv = Cholesky factor of the diagonal blocks and its inverse
-    DevBuf<double> vals, vals_s, lfac, sinv, f, ft, x, y, rt, p, Ap, sendbuf;
+    DevBuf<double> vals, vals_s, lfac, sinv, f, ft, x, y, rt, p, Ap, sdir, sendbuf;
     DevBuf<double> part_a, part_b, part_c, red, gath;
     DevBuf<PcgScalars> sc;
     DevBuf<int> flag;
@@ -214,18 +214,18 @@ void run_spmv_full(mbfea_ctx *c, int kernel, const double *x, double *y)
                         c->vals.p, 0, x, y, nullptr, nullptr);
     } else {
         launch_spmv_rowthread(c->st, nb, c->rowptr.p, c->colidx.p, c->vals.p, nullptr, nullptr, nullptr, nullptr, 0, x,
-                              y, nullptr, nullptr, nullptr);
+                              y, nullptr, nullptr, nullptr, nullptr);
     }
     c->launches++;
 }
 
 // the solver's SpMV: y = K~ x (unit diagonal implied; x has nb + n_ghost blocks)
 void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *partial, const PcgScalars *sc,
-              const PeerCtx *pc)
+              const PeerCtx *pc, double *partial2 = nullptr)
 {
     const int64_t nb = c->nb();
     if (nb <= 0) return;
-    if (kernel == 2 && !c->plan.sym_half && pc == nullptr) {
+    if (kernel == 2 && !c->plan.sym_half && pc == nullptr && partial2 == nullptr) {
         prepare_tma(c);
         const int64_t ntiles = (int64_t)c->tile_row_s_host.size() - 1;
         launch_spmv_tma(c->st, spmv_tma_grid(ntiles, c->sm_count), ntiles, c->tile_row_s.p, c->uptr.p, c->ucol.p,
@@ -234,14 +234,16 @@ void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *part
         const bool sym = c->plan.sym_half;
         launch_spmv_rowthread(c->st, nb, c->uptr.p, c->ucol.p, c->vals_s.p, sym ? c->lptr.p : nullptr,
                               sym ? c->lcol.p : nullptr, sym ? c->lofs.p : nullptr, sym ? c->ilv_base.p : nullptr, 1, x,
-                              y, partial, sc, pc);
+                              y, partial, partial2, sc, pc);
     }
     c->launches++;
 }
 
+int cg_variant(const mbfea_ctx *c) { return c->opt.cg_variant == 2 ? 2 : 1; }
+
 int spmv_grid(const mbfea_ctx *c, int kernel)
 {
-    if (kernel == 2 && !c->plan.sym_half && !c->p2p)
+    if (kernel == 2 && !c->plan.sym_half && !c->p2p && cg_variant(c) == 1)
         return spmv_tma_grid((int64_t)c->tile_row_s_host.size() - 1, c->sm_count);
     return spmv_rowthread_grid(c->nb(), c->plan.sym_half);
 }
@@ -435,6 +437,39 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
     c->launches += 2;
 }
 
+// Single-reduction CG (cg_variant 2): c->p holds the RESIDUAL (ghosted, peer-mapped: it is the SpMV
+// input), c->rt the direction d, c->sdir = K~ d, c->Ap = w = K~ r.  Dots of the SpMV that produced w
+// (delta = r.w in part_a, gamma = r.r in part_b) are consumed by the next step kernel.
+void enqueue_spmv2(mbfea_ctx *c, int kernel)
+{
+    const int W = c->world();
+    const int gs = spmv_grid(c, kernel);
+    if (c->p2p) {
+        run_spmv(c, 1, c->p.p, c->Ap.p, c->part_a.p, c->sc.p, c->peerctx.p, c->part_b.p);
+        return;
+    }
+    halo_exchange(c, c->p.p);
+    run_spmv(c, kernel, c->p.p, c->Ap.p, c->part_a.p, c->sc.p, nullptr, c->part_b.p);
+    if (W > 1) {
+        launch_reduce_partials(c->st, c->part_a.p, gs, c->red.p, c->part_b.p, c->red.p + 1, c->sc.p);
+        NK(c->nc->AllGather(c->red.p, c->gath.p, 2, nccl::kFloat64, c->comm, c->st));
+        c->launches++;
+    }
+}
+
+void enqueue_iteration2(mbfea_ctx *c, int kernel)
+{
+    const int64_t nb = c->nb();
+    const int W = c->world();
+    const int gs = spmv_grid(c, kernel);
+    PartialRef delta{c->part_a.p, gs, 1}, gamma{c->part_b.p, gs, 1};
+    if (W > 1 && !c->p2p) { delta = PartialRef{c->gath.p, W, 2}; gamma = PartialRef{c->gath.p + 1, W, 2}; }
+    launch_cg2_step(c->st, nb, delta, gamma, c->p.p, c->Ap.p, c->rt.p, c->sdir.p, c->y.p, c->sc.p,
+                    c->p2p ? c->peerctx.p : nullptr, c->p2p ? c->push_idx.p : nullptr, c->p2p ? c->push_dst.p : nullptr);
+    c->launches++;
+    enqueue_spmv2(c, kernel);
+}
+
 // Once per batch: the unscaled residual norm ||L r~||^2 and the stop test (never skipped, so
 // sc->rr is current when the loop ends).
 void enqueue_check(mbfea_ctx *c)
@@ -442,14 +477,16 @@ void enqueue_check(mbfea_ctx *c)
     const int64_t nb = c->nb();
     const int W = c->world();
     const int gv = vec_grid(nb);
+    const double *res = cg_variant(c) == 2 ? c->p.p : c->rt.p;   // where the scaled residual lives
+    double *part = c->part_c.p;   // part_a / part_b may hold dots the next step still needs
     if (c->p2p) {
-        launch_cg_check(c->st, nb, c->lfac.p, c->rt.p, nullptr, c->part_a.p, c->sc.p, c->peerctx.p);
-        launch_cg_check_finish(c->st, PartialRef{c->part_a.p, gv, 1}, c->sc.p, c->peerctx.p);
+        launch_cg_check(c->st, nb, c->lfac.p, res, nullptr, part, c->sc.p, c->peerctx.p);
+        launch_cg_check_finish(c->st, PartialRef{part, gv, 1}, c->sc.p, c->peerctx.p);
     } else {
-        launch_cg_check(c->st, nb, c->lfac.p, c->rt.p, nullptr, c->part_a.p, c->sc.p, nullptr);
-        PartialRef rr{c->part_a.p, gv, 1};
+        launch_cg_check(c->st, nb, c->lfac.p, res, nullptr, part, c->sc.p, nullptr);
+        PartialRef rr{part, gv, 1};
         if (W > 1) {
-            launch_reduce_partials(c->st, c->part_a.p, gv, c->red.p + 4, nullptr, nullptr, nullptr);
+            launch_reduce_partials(c->st, part, gv, c->red.p + 4, nullptr, nullptr, nullptr);
             NK(c->nc->AllGather(c->red.p + 4, c->gath.p + 2 * W, 1, nccl::kFloat64, c->comm, c->st));
             rr = PartialRef{c->gath.p + 2 * W, W, 1};
             c->launches++;
@@ -747,6 +784,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         CK(c->y.alloc((size_t)6 * nb));
         CK(c->rt.alloc((size_t)6 * nb));
         CK(c->ft.alloc((size_t)6 * nb));
+        CK(c->sdir.alloc((size_t)6 * nb));
         CK(c->Ap.alloc((size_t)6 * nb));
         CK(c->p.alloc((size_t)6 * (nb + ng)));
         CK(cudaMemsetAsync(c->p.p, 0, (size_t)std::max<int64_t>(1, 6 * (nb + ng)) * sizeof(double), c->st));
@@ -842,9 +880,15 @@ int mbfea_solve(mbfea_ctx *c)
         }
         check += check & 1;  // parity alternates: keep batches even
 
+        const int variant = cg_variant(c);
         CK(cudaEventRecord(c->ev[0], c->st));
         // f~ = S f, y = 0, r~ = p = f~  (CG on K~ = S K S^T  ==  block-Jacobi PCG on K)
-        launch_cg_init(c->st, nb, c->f.p, c->sinv.p, c->y.p, c->rt.p, c->ft.p, c->p.p, c->part_b.p, c->part_c.p);
+        if (variant == 2) {
+            launch_cg2_init(c->st, nb, c->f.p, c->sinv.p, c->y.p, c->p.p, c->ft.p, c->rt.p, c->sdir.p, c->part_c.p);
+            CK(cudaMemsetAsync(c->part_b.p, 0, sizeof(double) * kMaxPartials, c->st));
+        } else {
+            launch_cg_init(c->st, nb, c->f.p, c->sinv.p, c->y.p, c->rt.p, c->ft.p, c->p.p, c->part_b.p, c->part_c.p);
+        }
         PartialRef rho{c->part_b.p, gv, 1}, ff{c->part_c.p, gv, 1};
         if (W > 1) {
             launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, c->part_c.p, c->red.p + 3, nullptr);
@@ -865,16 +909,19 @@ int mbfea_solve(mbfea_ctx *c)
                              c->sc.p, c->peerctx.p);
             c->launches++;
         }
+        if (variant == 2) enqueue_spmv2(c, kernel);   // w0 = K~ r0, gamma0, delta0
 
         bool use_graph = c->opt.use_graph != 0;
-        if (use_graph && (c->graph_exec == nullptr || c->graph_iters != check || c->graph_kernel != kernel)) {
+        if (use_graph && (c->graph_exec == nullptr || c->graph_iters != check || c->graph_kernel != kernel + 16 * variant)) {
             drop_graph(c);
             if (kernel == 2) prepare_tma(c);
             cudaGraph_t g = nullptr;
             const int64_t l0 = c->launches;
             CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
             try {
-                for (int i = 0; i < check; ++i) enqueue_iteration(c, kernel, i & 1);
+                for (int i = 0; i < check; ++i) {
+                    if (variant == 2) enqueue_iteration2(c, kernel); else enqueue_iteration(c, kernel, i & 1);
+                }
                 enqueue_check(c);
             } catch (...) {
                 cudaStreamEndCapture(c->st, &g);
@@ -887,14 +934,16 @@ int mbfea_solve(mbfea_ctx *c)
             cudaError_t e = cudaGraphInstantiate(&c->graph_exec, g, 0);
             cudaGraphDestroy(g);
             CK(e);
-            c->graph_iters = check; c->graph_kernel = kernel;
+            c->graph_iters = check; c->graph_kernel = kernel + 16 * variant;
         }
         for (;;) {
             if (use_graph) {
                 CK(cudaGraphLaunch(c->graph_exec, c->st));
                 c->launches += c->graph_launches;
             } else {
-                for (int i = 0; i < check; ++i) enqueue_iteration(c, kernel, i & 1);
+                for (int i = 0; i < check; ++i) {
+                    if (variant == 2) enqueue_iteration2(c, kernel); else enqueue_iteration(c, kernel, i & 1);
+                }
                 enqueue_check(c);
             }
             CK(cudaMemcpyAsync(c->sc_host, c->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->st));

@@ -562,8 +562,8 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
     int64_t nb, const int32_t *__restrict__ uptr, const int32_t *__restrict__ ucol,
     const double *__restrict__ vals, const int32_t *__restrict__ lptr, const int32_t *__restrict__ lcol,
     const int32_t *__restrict__ lofs, const int32_t *__restrict__ tile_base, int identity,
-    const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partial, const PcgScalars *sc,
-    const PeerCtx *pc)
+    const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partial,
+    double *__restrict__ partial2, const PcgScalars *sc, const PeerCtx *pc)
 {
     __shared__ double red[33];
     __shared__ double ts[SYM ? kSpmvThreads * 6 : 1];
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
         trace_stamp(sc, sc->iter, 1);
     }
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
-    double dot = 0.0;
+    double dot = 0.0, dot2 = 0.0;
     const int64_t stride = (int64_t)gridDim.x * kRowsPerCta;
     // row pointers of the current tile; with MBFEA_SYM_PREFETCH the next tile's are requested before
     // this tile's blocks, so the pointer -> column -> x chain of the next tile is one level shorter
@@ -653,6 +653,7 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
         if (live) {
             y[row * 6 + i] = acc;
             dot = fma(xi, acc, dot);
+            dot2 = fma(xi, xi, dot2);
         }
         if (MBFEA_SYM_PREFETCH) {
             kb = nkb; ke = nke; lb = nlb; le = nle; tb = ntb;
@@ -668,14 +669,20 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
         const double s = block_sum<false>(dot, red);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
     }
+    if (partial2 != nullptr) {   // single-reduction CG: x.x rides along with x.Ax
+        const double s = block_sum<false>(dot2, red);
+        if (threadIdx.x == 0) partial2[blockIdx.x] = s;
+    }
     if (pc != nullptr && partial != nullptr && last_cta_done(pc->tickets + 0)) {
         // fused reduction + all-gather: the last CTA sums the partials in fixed order and
-        // stores p.Ap of this rank into every rank's mailbox over NVLink
+        // stores this rank's dot product(s) into every rank's mailbox over NVLink
         const double s = sum_partials(PartialRef{partial, (int)gridDim.x, 1}, red);
+        const double s2 = partial2 != nullptr ? sum_partials(PartialRef{partial2, (int)gridDim.x, 1}, red) : 0.0;
         if ((int)threadIdx.x < pc->world) {
             const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
             Mailbox *m = pc->peer[threadIdx.x];
             m->dot_val[0][pc->rank] = s;
+            if (partial2 != nullptr) m->dot_val[1][pc->rank] = s2;
             __threadfence_system();
             st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);
         }
@@ -692,15 +699,15 @@ int spmv_rowthread_grid(int64_t nb, bool sym)
 
 void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const double *vals,
                            const int32_t *lptr, const int32_t *lcol, const int32_t *lofs, const int32_t *tile_base,
-                           int identity, const double *x, double *y, double *partial, const PcgScalars *sc,
-                           const PeerCtx *pc)
+                           int identity, const double *x, double *y, double *partial, double *partial2,
+                           const PcgScalars *sc, const PeerCtx *pc)
 {
     if (lptr != nullptr)
         k_spmv_rowthread<true><<<spmv_rowthread_grid(nb, true), kSpmvThreads, 0, st>>>(
-            nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base, identity, x, y, partial, sc, pc);
+            nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base, identity, x, y, partial, partial2, sc, pc);
     else
         k_spmv_rowthread<false><<<spmv_rowthread_grid(nb, false), kSpmvThreads, 0, st>>>(
-            nb, uptr, ucol, vals, nullptr, nullptr, nullptr, nullptr, identity, x, y, partial, sc, pc);
+            nb, uptr, ucol, vals, nullptr, nullptr, nullptr, nullptr, identity, x, y, partial, partial2, sc, pc);
 }
 
 // ---------------------------------------------------------------------------
@@ -1057,6 +1064,136 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
         else if (it >= sc->max_iter) done = 2;
         sc->done = done;
     }
+}
+
+// ---- single-reduction CG (Chronopoulos-Gear): ONE exchange per iteration ----------------
+// The SpMV runs on the residual: w = K~ r, and its epilogue yields both gamma = r.r and
+// delta = r.w.  One elementwise kernel then does everything else:
+//   beta = gamma_i / gamma_{i-1};  alpha = gamma_i / (delta_i - beta gamma_i / alpha_{i-1})
+//   d = r + beta d;  s = w + beta s (= K~ d);  y += alpha d;  r -= alpha s
+// Two kernels and one cross-GPU exchange per iteration instead of three and two.
+__global__ void __launch_bounds__(kSpmvThreads) k_cg2_init(int64_t nb, const double *__restrict__ f,
+                                                           const double *__restrict__ sinv, double *__restrict__ y,
+                                                           double *__restrict__ r, double *__restrict__ ft,
+                                                           double *__restrict__ d, double *__restrict__ s,
+                                                           double *__restrict__ part_ff)
+{
+    __shared__ double vs[kSpmvThreads];
+    __shared__ double red[33];
+    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+    double ff = 0.0;
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+        const int64_t row = r0 + lr;
+        const bool live = row < nb;
+        const double fv = live ? f[row * 6 + i] : 0.0;
+        __syncthreads();
+        vs[threadIdx.x] = fv;
+        __syncthreads();
+        if (live) {
+            const double t = lower_row_times(sinv, row, i, vs + lr * 6);
+            y[row * 6 + i] = 0.0; r[row * 6 + i] = t; ft[row * 6 + i] = t;
+            d[row * 6 + i] = 0.0; s[row * 6 + i] = 0.0;
+            ff = fma(fv, fv, ff);
+        }
+    }
+    const double b = block_sum<false>(ff, red);
+    if (threadIdx.x == 0) part_ff[blockIdx.x] = b;
+}
+
+__global__ void __launch_bounds__(256, 4) k_cg2_step(
+    int64_t n, PartialRef delta_ref, PartialRef gamma_ref, double *__restrict__ r, const double *__restrict__ w,
+    double *__restrict__ d, double *__restrict__ s, double *__restrict__ y, PcgScalars *sc, const PeerCtx *pc,
+    const int32_t *__restrict__ push_idx, double *const *__restrict__ push_dst)
+{
+    __shared__ double red[33];
+    if (sc->done != 0) return;
+    const long long it = sc->iter;    // stable: only block 0 bumps it, after its own reads
+    trace_stamp(sc, it, 2);
+    double delta, gamma;
+    unsigned long long tag = 0;
+    if (pc != nullptr) {
+        tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)it) + 1;
+        if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[0][threadIdx.x], tag);
+        __syncthreads();
+        trace_stamp(sc, it, 3);
+        delta = 0.0; gamma = 0.0;
+        for (int q = 0; q < pc->world; ++q) {
+            delta += __ldcv(&pc->mine->dot_val[0][q]);
+            gamma += __ldcv(&pc->mine->dot_val[1][q]);
+        }
+    } else {
+        delta = sum_partials(delta_ref, red);
+        gamma = sum_partials(gamma_ref, red);
+    }
+    const int par = (int)(it & 1);
+    double beta = 0.0, den = delta;
+    if (it > 0) {
+        beta = gamma / sc->rz[par ^ 1];              // gamma_{i-1}
+        den = delta - beta * gamma / sc->alpha[par ^ 1];
+    }
+    const bool exact = (it == 0) ? (gamma == 0.0) : (gamma <= 1e-32 * sc->rho0);
+    const bool bad = !exact && (!(den > 0.0) || !isfinite(den) || !isfinite(gamma));
+    const double alpha = (exact || bad) ? 0.0 : gamma / den;
+    if (!exact && !bad) {
+        const int64_t n2 = n >> 1;
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += (int64_t)gridDim.x * blockDim.x) {
+            double2 rv = reinterpret_cast<double2 *>(r)[j];
+            const double2 wv = reinterpret_cast<const double2 *>(w)[j];
+            double2 dv = reinterpret_cast<double2 *>(d)[j], sv = reinterpret_cast<double2 *>(s)[j];
+            double2 yv = reinterpret_cast<double2 *>(y)[j];
+            dv.x = fma(beta, dv.x, rv.x); dv.y = fma(beta, dv.y, rv.y);
+            sv.x = fma(beta, sv.x, wv.x); sv.y = fma(beta, sv.y, wv.y);
+            yv.x = fma(alpha, dv.x, yv.x); yv.y = fma(alpha, dv.y, yv.y);
+            rv.x = fma(-alpha, sv.x, rv.x); rv.y = fma(-alpha, sv.y, rv.y);
+            reinterpret_cast<double2 *>(d)[j] = dv;
+            reinterpret_cast<double2 *>(s)[j] = sv;
+            reinterpret_cast<double2 *>(y)[j] = yv;
+            reinterpret_cast<double2 *>(r)[j] = rv;
+            if (push_idx != nullptr) {
+                const int64_t row = j / 3;
+                const int32_t code = __ldg(push_idx + row);
+                if (code >= 0) {
+                    const int off = (int)(j - row * 3) * 2;
+                    const int32_t first = code & 0x0fffffff, cnt = code >> 28;
+                    for (int32_t q = 0; q < cnt; ++q) *reinterpret_cast<double2 *>(push_dst[first + q] + off) = rv;
+                }
+            }
+        }
+    }
+    if (push_idx != nullptr) {   // the halo tag must be published even when nothing moved (peers wait on it)
+        __threadfence_system();
+        if (last_cta_done(pc->tickets + 2)) {
+            if ((int)threadIdx.x < pc->n_neighbors) {
+                __threadfence_system();
+                st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rz[par] = gamma;
+        sc->alpha[par] = alpha;
+        sc->pAp = den;
+        if (it == 0) sc->rho0 = gamma;
+        sc->iter = it + 1;
+        int done = 0;
+        if (bad) done = 3;
+        else if (exact) done = 1;
+        else if (it + 1 >= sc->max_iter) done = 2;
+        sc->done = done;
+    }
+}
+
+void launch_cg2_init(cudaStream_t st, int64_t nb, const double *f, const double *sinv, double *y, double *r, double *ft,
+                     double *d, double *s, double *part_ff)
+{
+    k_cg2_init<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, f, sinv, y, r, ft, d, s, part_ff);
+}
+
+void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef gamma, double *r, const double *w,
+                     double *d, double *s, double *y, PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx,
+                     double *const *push_dst)
+{
+    k_cg2_step<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, delta, gamma, r, w, d, s, y, sc, pc, push_idx, push_dst);
 }
 
 // per batch: partial sums of ||L (a - b)||^2 (b may be null): the unscaled residual norm

@@ -52,6 +52,7 @@ struct PcgScalars {
     unsigned long long tag_cur;  // tag of the values produced in the current iteration
     unsigned long long *trace;   // optional: kTraceSlots globaltimer stamps per iteration (first kTraceIters)
     double rho0;                 // r~.r~ at iteration 0
+    double alpha[2];             // single-reduction CG: alpha of the last two iterations (by parity)
     long long checks;            // residual checks done (multi-GPU tag of the per-batch check)
 };
 constexpr int kTraceSlots = 8;   // 0 spmv in, 1 spmv past halo wait, 2 update in, 3 update past wait,
@@ -85,8 +86,8 @@ void launch_scale_blocks(cudaStream_t st, int64_t nb, const int32_t *uptr, const
 int  spmv_rowthread_grid(int64_t nb, bool sym);
 void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const double *vals,
                            const int32_t *lptr, const int32_t *lcol, const int32_t *lofs, const int32_t *tile_base,
-                           int identity, const double *x, double *y, double *partial, const PcgScalars *sc,
-                           const PeerCtx *pc);
+                           int identity, const double *x, double *y, double *partial, double *partial2,
+                           const PcgScalars *sc, const PeerCtx *pc);
 int  spmv_tma_grid(int64_t ntiles, int sm_count);
 size_t spmv_tma_smem_bytes();
 int  spmv_tma_prepare();  // opt in to the large dynamic shared memory; returns cudaError
@@ -104,6 +105,12 @@ void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, c
                       double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc);
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
                        PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst);
+// single-reduction (Chronopoulos-Gear) CG: SpMV on the residual yields r.r and r.K~r, one step kernel does the rest
+void launch_cg2_init(cudaStream_t st, int64_t nb, const double *f, const double *sinv, double *y, double *r, double *ft,
+                     double *d, double *s, double *part_ff);
+void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef gamma, double *r, const double *w,
+                     double *d, double *s, double *y, PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx,
+                     double *const *push_dst);
 // unscaled residual norm ||L (a - b)||^2 (b may be null) -> partials; finish: total -> sc->rr, stop test
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
                      const PcgScalars *sc, const PeerCtx *pc);

@@ -18,7 +18,7 @@ if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 job = syn.cubic_lattice(int(os.environ.get("MBFEA_N", "100")))
-c = mb.Context(device=local, tol=1e-8, max_iter=300)
+c = mb.Context(device=local, tol=1e-8, max_iter=300, cg_variant=int(os.environ.get("MBFEA_CG", "0")))
 if world > 1:
     uid = [mb.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)

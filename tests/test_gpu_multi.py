@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, uid_path, out_dir, n, comm_mode):
+def _worker(rank, world, uid_path, out_dir, n, comm_mode, variant):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import time
     import meshbeamfea_b200 as mb
@@ -31,7 +31,7 @@ def _worker(rank, world, uid_path, out_dir, n, comm_mode):
             time.sleep(0.05)
         uid = open(uid_path, "rb").read()
     job = syn.cubic_lattice(n)
-    c = mb.Context(device=rank, tol=1e-12, comm_mode=comm_mode)
+    c = mb.Context(device=rank, tol=1e-12, comm_mode=comm_mode, cg_variant=variant)
     c.comm_init(uid, rank, world)
     c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job.beamMaterial,
               job.fixedNodes, job.nodalForces)
@@ -43,9 +43,10 @@ def _worker(rank, world, uid_path, out_dir, n, comm_mode):
     c.close()
 
 
-@pytest.mark.parametrize("comm_mode", [0, 1], ids=["nvlink_peer_memory", "nccl"])
+@pytest.mark.parametrize("comm_mode,variant", [(0, 1), (1, 1), (0, 2), (1, 2)],
+                         ids=["nvlink_peer_memory", "nccl", "nvlink_single_reduction_cg", "nccl_single_reduction_cg"])
 @pytest.mark.parametrize("world", [2])
-def test_two_rank_solve_matches_single_and_oracle(built, tmp_path, world, comm_mode):
+def test_two_rank_solve_matches_single_and_oracle(built, tmp_path, world, comm_mode, variant):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import meshbeamfea_b200 as mb
@@ -53,7 +54,7 @@ def test_two_rank_solve_matches_single_and_oracle(built, tmp_path, world, comm_m
     from oracle import oracle as orc
     from helpers import to_oracle, rel_l2
     n = 14
-    mp.spawn(_worker, args=(world, os.path.join(str(tmp_path), "uid"), str(tmp_path), n, comm_mode), nprocs=world,
+    mp.spawn(_worker, args=(world, os.path.join(str(tmp_path), "uid"), str(tmp_path), n, comm_mode, variant), nprocs=world,
              join=True)
     job = syn.cubic_lattice(n)
     with mb.Context(device=0, tol=1e-12) as c:

@@ -104,13 +104,14 @@ def test_stage_by_stage_parity(built, name):
         assert np.array_equal(c.edge_forces(), F)
 
 
-@pytest.mark.parametrize("storage,kernel", [(2, 1), (1, 1), (1, 2)],
-                         ids=["symmetric_half-rowthread", "full_rows-rowthread", "full_rows-tma"])
-def test_every_solver_format_and_kernel_gives_the_same_solution(built, storage, kernel):
-    for job in (syn.cubic_lattice(14), syn.random_mesh(77), syn.gridshell(21)):
+@pytest.mark.parametrize("storage,kernel,variant", [(2, 1, 1), (1, 1, 1), (1, 2, 1), (2, 1, 2), (1, 1, 2)],
+                         ids=["symmetric_half-rowthread", "full_rows-rowthread", "full_rows-tma",
+                              "symmetric_half-single_reduction_cg", "full_rows-single_reduction_cg"])
+def test_every_solver_format_and_kernel_gives_the_same_solution(built, storage, kernel, variant):
+    for job in (syn.cubic_lattice(14), syn.random_mesh(77), syn.gridshell(21), syn.two_line_segments()):
         O = to_oracle(job)
         U, F = orc.solve(O)
-        with ctx_for(job, spmv_kernel=kernel, storage=storage) as c:
+        with ctx_for(job, spmv_kernel=kernel, storage=storage, cg_variant=variant) as c:
             c.execute()
             assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
 
