@@ -101,8 +101,11 @@ typedef struct mbfea_stats {
     /* algorithmic bytes (DESIGN.md "Algorithmic bytes") for this rank */
     double  bytes_spmv, bytes_pcg_iter, bytes_assemble, bytes_recover;
     int64_t kernel_launches;    /* kernels launched by the last execute()       */
-    int32_t converged;
-    int32_t reserved[5];
+    int32_t converged;          /* 1: recomputed residual <= tol; 2: recurrence met tol,
+                                   recomputed residual stalls just above (FP64 limit of
+                                   this system); 0: not converged                      */
+    int32_t restarts;           /* residual replacements done by the solve             */
+    int32_t reserved[4];
 } mbfea_stats;
 
 int          mbfea_version(void);

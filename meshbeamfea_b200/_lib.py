@@ -39,7 +39,8 @@ class Stats(C.Structure):
         ("ms_execute_total", C.c_double),
         ("bytes_spmv", C.c_double), ("bytes_pcg_iter", C.c_double), ("bytes_assemble", C.c_double),
         ("bytes_recover", C.c_double),
-        ("kernel_launches", C.c_int64), ("converged", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("kernel_launches", C.c_int64), ("converged", C.c_int32), ("restarts", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
     def as_dict(self):

@@ -936,40 +936,69 @@ int mbfea_solve(mbfea_ctx *c)
             CK(e);
             c->graph_iters = check; c->graph_kernel = kernel + 16 * variant;
         }
+        // Outer loop: run batches until the recurrence says "converged", then RECOMPUTE the residual
+        // r~ = f~ - K~ y.  If the recomputed residual misses the tolerance (CG's residual gap on
+        // ill-conditioned systems) replace the recurrence residual by it and resume -- so the tolerance
+        // holds for the true residual ||f - K u||, as far as FP64 allows.
+        double rr_true = 0.0, prev_true = INFINITY;
+        int restarts = 0;
         for (;;) {
-            if (use_graph) {
-                CK(cudaGraphLaunch(c->graph_exec, c->st));
-                c->launches += c->graph_launches;
-            } else {
-                for (int i = 0; i < check; ++i) {
-                    if (variant == 2) enqueue_iteration2(c, kernel); else enqueue_iteration(c, kernel, i & 1);
+            for (;;) {
+                if (use_graph) {
+                    CK(cudaGraphLaunch(c->graph_exec, c->st));
+                    c->launches += c->graph_launches;
+                } else {
+                    for (int i = 0; i < check; ++i) {
+                        if (variant == 2) enqueue_iteration2(c, kernel); else enqueue_iteration(c, kernel, i & 1);
+                    }
+                    enqueue_check(c);
                 }
-                enqueue_check(c);
+                CK(cudaMemcpyAsync(c->sc_host, c->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->st));
+                CK(cudaStreamSynchronize(c->st));
+                if (c->sc_host->done != 0) break;
             }
-            CK(cudaMemcpyAsync(c->sc_host, c->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            if (c->sc_host->done != 0) break;
+            // K~ y through the ghosted buffer (its previous content -- direction or residual -- is
+            // rebuilt by the replacement below if the iteration resumes)
+            CK(cudaMemcpyAsync(c->p.p, c->y.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            halo_exchange(c, c->p.p);
+            run_spmv(c, kernel, c->p.p, c->Ap.p, nullptr, nullptr, nullptr);
+            if (variant == 2)
+                launch_cg_restart(c->st, nb, c->lfac.p, c->ft.p, c->Ap.p, c->p.p, c->rt.p, 0.0, c->sdir.p, c->part_a.p, c->part_b.p);
+            else
+                launch_cg_restart(c->st, nb, c->lfac.p, c->ft.p, c->Ap.p, c->rt.p, c->p.p, 1.0, nullptr, c->part_a.p, c->part_b.p);
+            launch_reduce_partials(c->st, c->part_a.p, gv, c->red.p, c->part_b.p, c->red.p + 1, nullptr);
+            c->launches += 3;
+            PartialRef trr{c->red.p, 1, 1}, trho{c->red.p + 1, 1, 1};
+            rr_true = 0.0;
+            if (W > 1) {
+                NK(c->nc->AllGather(c->red.p, c->gath.p, 2, nccl::kFloat64, c->comm, c->st));
+                trr = PartialRef{c->gath.p, W, 2}; trho = PartialRef{c->gath.p + 1, W, 2};
+                std::vector<double> g((size_t)2 * W);
+                CK(cudaMemcpyAsync(g.data(), c->gath.p, g.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+                CK(cudaStreamSynchronize(c->st));
+                for (int q = 0; q < W; ++q) rr_true += g[(size_t)2 * q];
+            } else {
+                CK(cudaMemcpyAsync(&rr_true, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+                CK(cudaStreamSynchronize(c->st));
+            }
+            const PcgScalars &hh = *c->sc_host;
+            const bool met_true = rr_true <= hh.tol2 * hh.ff;
+            if (hh.done != 1 || met_true || restarts >= 6 || !(rr_true < 0.25 * prev_true) || hh.iter >= hh.max_iter) break;
+            prev_true = rr_true;
+            ++restarts;
+            c->epoch++;
+            launch_cg_restart_finish(c->st, trr, trho, c->sc.p, c->epoch, 1);
+            c->launches++;
+            if (c->p2p) {
+                launch_push_halo(c->st, (int64_t)c->plan.send_rows.size(), c->send_rows.p, c->push_dst_send.p, c->p.p,
+                                 c->sc.p, c->peerctx.p);
+                c->launches++;
+            }
+            if (variant == 2) enqueue_spmv2(c, kernel);
         }
         launch_unscale(c->st, nb, c->sinv.p, c->y.p, c->x.p);   // x = S^T y
         CK(cudaEventRecord(c->ev[1], c->st));
-        // true residual ||f - K x|| / ||f|| = ||L (f~ - K~ y)|| / ||f||, recomputed from y
-        CK(cudaMemcpyAsync(c->p.p, c->y.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-        halo_exchange(c, c->p.p);
-        run_spmv(c, kernel, c->p.p, c->Ap.p, nullptr, nullptr, nullptr);
-        launch_cg_check(c->st, nb, c->lfac.p, c->ft.p, c->Ap.p, c->part_a.p, nullptr, nullptr);
-        launch_reduce_partials(c->st, c->part_a.p, gv, c->red.p, nullptr, nullptr, nullptr);
-        c->launches += 3;
-        double rr_true = 0.0;
-        if (W > 1) {
-            NK(c->nc->AllGather(c->red.p, c->gath.p, 1, nccl::kFloat64, c->comm, c->st));
-            std::vector<double> g((size_t)W);
-            CK(cudaMemcpyAsync(g.data(), c->gath.p, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            for (double v : g) rr_true += v;
-        } else {
-            CK(cudaMemcpyAsync(&rr_true, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-        }
+        CK(cudaStreamSynchronize(c->st));
         const PcgScalars &h = *c->sc_host;
         mbfea_stats &s = c->stats;
         s.ms_pcg = elapsed(c, 0, 1);
@@ -978,17 +1007,23 @@ int mbfea_solve(mbfea_ctx *c)
         s.true_rel_residual = h.ff > 0 ? std::sqrt(rr_true / h.ff) : 0.0;
         // done == 1 is either the residual test or exact convergence (rho below FP64 resolution):
         // either way the recurrence residual at exit decides
-        const bool met = h.ff == 0.0 || h.rr <= h.tol2 * h.ff;
-        s.converged = (h.done == 1 && met) ? 1 : 0;
-        // On a singular (under-constrained) system the iterates blow up while the recurrence
-        // residual keeps shrinking; the recomputed residual exposes it.
-        const bool diverged = s.converged && !(s.true_rel_residual <= std::max(1e3 * c->opt.tol, 1e-6));
-        if (diverged) s.converged = 0;
+        // converged = 1: the RECOMPUTED residual meets the tolerance.  2: the recurrence met it but the
+        // recomputed residual stalls slightly above (attainable FP64 accuracy of this system).
+        // On a singular (under-constrained) system the iterates blow up while the recurrence residual
+        // keeps shrinking; the recomputed residual exposes it.
+        const bool met_rec = h.ff == 0.0 || h.rr <= h.tol2 * h.ff || restarts > 0;
+        const bool met_true = h.ff == 0.0 || rr_true <= h.tol2 * h.ff;
+        const bool near_true = s.true_rel_residual <= std::max(1e3 * c->opt.tol, 1e-6);
+        s.converged = (h.done == 1 && met_true) ? 1 : ((h.done == 1 && met_rec && near_true) ? 2 : 0);
+        const bool diverged = h.done == 1 && met_rec && !near_true;
+        s.restarts = restarts;
         c->solved = true; c->recovered = false;
         if (c->opt.verbose)
             std::fprintf(stderr, "[mbfea] rank %d: CG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d (%s storage), batch %d\n",
                          c->opt.rank, (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel,
                          c->plan.sym_half ? "symmetric-half" : "full-row", check);
+        if (c->opt.verbose && restarts)
+            std::fprintf(stderr, "[mbfea] rank %d: %d residual replacement(s)\n", c->opt.rank, restarts);
         if (c->p2p && peer_timeout_flag())
             return fail(c, MBFEA_ECUDA, "a peer rank stopped signalling during the PCG loop (NVLink mailbox wait timed out)");
         if (h.done == 3) return fail(c, MBFEA_ESINGULAR, "CG breakdown: p.Ap <= 0 or non-finite (system not SPD: is any vertex fixed?)");

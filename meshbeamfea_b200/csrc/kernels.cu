@@ -945,6 +945,7 @@ __global__ void __launch_bounds__(256) k_cg_init_finish(PartialRef rho, PartialR
         sc->epoch = epoch;
         sc->tag_cur = 0;
         sc->checks = 0;
+        sc->restart_iter = 0;
         sc->trace = trace;
     }
 }
@@ -1127,11 +1128,12 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
     }
     const int par = (int)(it & 1);
     double beta = 0.0, den = delta;
-    if (it > 0) {
+    if (it > sc->restart_iter) {
         beta = gamma / sc->rz[par ^ 1];              // gamma_{i-1}
         den = delta - beta * gamma / sc->alpha[par ^ 1];
     }
     const bool exact = (it == 0) ? (gamma == 0.0) : (gamma <= 1e-32 * sc->rho0);
+    // (rho0 is the very first gamma of the solve, kept across restarts)
     const bool bad = !exact && (!(den > 0.0) || !isfinite(den) || !isfinite(gamma));
     const double alpha = (exact || bad) ? 0.0 : gamma / den;
     if (!exact && !bad) {
@@ -1231,6 +1233,71 @@ __global__ void __launch_bounds__(kSpmvThreads) k_cg_check(int64_t nb, const dou
             st_release_sys(&m->dot_tag[2][pc->rank], tag);
         }
     }
+}
+
+// Residual replacement (restart): r~ := f~ - K~ y (the recomputed residual), direction := r~ (classic)
+// or 0 (single-reduction); partials of ||L r~||^2 and of rho = r~.r~
+__global__ void __launch_bounds__(kSpmvThreads) k_cg_restart(int64_t nb, const double *__restrict__ lfac,
+                                                             const double *__restrict__ ft,
+                                                             const double *__restrict__ Ky, double *__restrict__ res,
+                                                             double *__restrict__ dir, double dir_scale,
+                                                             double *__restrict__ aux_zero,
+                                                             double *__restrict__ part_rr, double *__restrict__ part_rho)
+{
+    __shared__ double vs[kSpmvThreads];
+    __shared__ double red[33];
+    const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
+    double rr = 0.0, rho = 0.0;
+    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
+        const int64_t row = r0 + lr;
+        const bool live = row < nb;
+        double v = 0.0;
+        if (live) v = ft[row * 6 + i] - Ky[row * 6 + i];
+        __syncthreads();
+        vs[threadIdx.x] = v;
+        __syncthreads();
+        if (live) {
+            const double t = lower_row_times(lfac, row, i, vs + lr * 6);
+            rr = fma(t, t, rr);
+            rho = fma(v, v, rho);
+            if (res != nullptr) res[row * 6 + i] = v;
+            if (dir != nullptr) dir[row * 6 + i] = dir_scale * v;
+            if (aux_zero != nullptr) aux_zero[row * 6 + i] = 0.0;
+        }
+    }
+    const double a = block_sum<false>(rr, red);
+    const double b = block_sum<false>(rho, red);
+    if (threadIdx.x == 0) { part_rr[blockIdx.x] = a; part_rho[blockIdx.x] = b; }
+}
+
+// one CTA: resume the iteration from the replaced residual under a new epoch
+__global__ void __launch_bounds__(256) k_cg_restart_finish(PartialRef rr, PartialRef rho, PcgScalars *sc,
+                                                           unsigned long long epoch, int clear_done)
+{
+    __shared__ double red[33];
+    const double a = sum_partials(rr, red);
+    const double b = sum_partials(rho, red);
+    if (threadIdx.x == 0) {
+        sc->rr = a;
+        if (clear_done) {
+            sc->rz[0] = b; sc->rz[1] = b;   // whichever parity the next iteration reads
+            sc->restart_iter = sc->iter;     // single-reduction CG: next step runs with beta = 0
+            sc->epoch = epoch;               // new tags: the halo / dot slots of this iteration index were used already
+            sc->done = 0;
+        }
+    }
+}
+
+void launch_cg_restart(cudaStream_t st, int64_t nb, const double *lfac, const double *ft, const double *Ky, double *res,
+                       double *dir, double dir_scale, double *aux_zero, double *part_rr, double *part_rho)
+{
+    k_cg_restart<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, lfac, ft, Ky, res, dir, dir_scale, aux_zero, part_rr, part_rho);
+}
+
+void launch_cg_restart_finish(cudaStream_t st, PartialRef rr, PartialRef rho, PcgScalars *sc, unsigned long long epoch,
+                              int clear_done)
+{
+    k_cg_restart_finish<<<1, 256, 0, st>>>(rr, rho, sc, epoch, clear_done);
 }
 
 // one CTA: total of the check partials -> sc->rr; converged => done = 1

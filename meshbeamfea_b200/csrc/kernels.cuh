@@ -53,6 +53,7 @@ struct PcgScalars {
     unsigned long long *trace;   // optional: kTraceSlots globaltimer stamps per iteration (first kTraceIters)
     double rho0;                 // r~.r~ at iteration 0
     double alpha[2];             // single-reduction CG: alpha of the last two iterations (by parity)
+    long long restart_iter;      // iteration index of the last residual replacement (its step uses beta = 0)
     long long checks;            // residual checks done (multi-GPU tag of the per-batch check)
 };
 constexpr int kTraceSlots = 8;   // 0 spmv in, 1 spmv past halo wait, 2 update in, 3 update past wait,
@@ -115,6 +116,11 @@ void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef g
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
                      const PcgScalars *sc, const PeerCtx *pc);
 void launch_cg_check_finish(cudaStream_t st, PartialRef part, PcgScalars *sc, const PeerCtx *pc);
+// residual replacement: res := ft - Ky, dir := dir_scale * res, aux_zero := 0; partials of ||L res||^2 and res.res
+void launch_cg_restart(cudaStream_t st, int64_t nb, const double *lfac, const double *ft, const double *Ky, double *res,
+                       double *dir, double dir_scale, double *aux_zero, double *part_rr, double *part_rho);
+void launch_cg_restart_finish(cudaStream_t st, PartialRef rr, PartialRef rho, PcgScalars *sc, unsigned long long epoch,
+                              int clear_done);
 void launch_unscale(cudaStream_t st, int64_t nb, const double *sinv, const double *y, double *x);
 int peer_timeout_flag();  // 1 once any peer wait gave up (a rank died)
 // P2P halo: owned boundary x-blocks -> the neighbours' ghost slots (peer stores), then the tag

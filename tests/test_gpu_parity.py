@@ -95,7 +95,8 @@ def test_stage_by_stage_parity(built, name):
         c.execute()
         U, F = orc.solve(O)
         st = c.stats()
-        assert st["converged"] == 1 and st["rel_residual"] <= 1e-12
+        # 1: the recomputed residual meets 1e-12; 2: it stalls just above (FP64 limit of the system)
+        assert st["converged"] in (1, 2) and st["rel_residual"] <= 1e-12 and st["true_rel_residual"] <= 1e-9
         assert rel_l2(c.displacements(), U) < TOL_U
         assert rel_l2(c.edge_forces(), F) < TOL_U
         assert np.all(c.displacements()[np.asarray(job.fixedNodes)] == 0.0)
@@ -254,6 +255,23 @@ def test_graph_and_plain_launch_agree(built):
         a.execute(); b.execute()
         assert a.stats()["iterations"] == b.stats()["iterations"]
         assert np.array_equal(a.displacements(), b.displacements())
+
+
+def test_tolerance_holds_for_the_recomputed_residual(built):
+    """CG's recurrence residual drifts from f - K u on ill-conditioned systems (long cantilevered
+    grid: at 1e-8 the recomputed residual was 2.5e-7).  The solver recomputes, replaces and resumes,
+    so the tolerance holds for the true residual and the displacements meet the 1e-8 parity bar."""
+    job = syn.planar_grid(60)
+    U, F = orc.solve(to_oracle(job))
+    with ctx_for(job, tol=1e-8) as c:
+        c.execute()
+        st = c.stats()
+        assert st["converged"] == 1 and st["true_rel_residual"] <= 1e-8
+    with ctx_for(job, tol=1e-11) as c:
+        c.execute()
+        st = c.stats()
+        assert st["converged"] in (1, 2)
+        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
 
 
 def test_max_iter_reports_not_converged(built):
