@@ -956,6 +956,8 @@ int mbfea_solve(mbfea_ctx *c)
                 CK(cudaMemcpyAsync(c->sc_host, c->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->st));
                 CK(cudaStreamSynchronize(c->st));
                 if (c->sc_host->done != 0) break;
+                if (c->p2p && peer_timeout_flag())
+                    return fail(c, MBFEA_ECUDA, "a peer rank stopped signalling during the CG loop (NVLink mailbox wait timed out)");
             }
             // K~ y through the ghosted buffer (its previous content -- direction or residual -- is
             // rebuilt by the replacement below if the iteration resumes)

@@ -681,10 +681,17 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
         if ((int)threadIdx.x < pc->world) {
             const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
             Mailbox *m = pc->peer[threadIdx.x];
-            m->dot_val[0][pc->rank] = s;
-            if (partial2 != nullptr) m->dot_val[1][pc->rank] = s2;
-            __threadfence_system();
-            st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);
+            if (partial2 == nullptr) {
+                m->dot_val[0][pc->rank] = s;
+                __threadfence_system();
+                st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);
+            } else {   // single-reduction CG: slots double-buffered by iteration parity
+                const int par = (int)(sc->iter & 1);
+                m->dot_val[3 + 2 * par][pc->rank] = s;
+                m->dot_val[4 + 2 * par][pc->rank] = s2;
+                __threadfence_system();
+                st_release_sys(&m->dot_tag[3 + par][pc->rank], tag + 1);
+            }
         }
     }
 }
@@ -1114,13 +1121,14 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
     unsigned long long tag = 0;
     if (pc != nullptr) {
         tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)it) + 1;
-        if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[0][threadIdx.x], tag);
+        const int mp = (int)(it & 1);
+        if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[3 + mp][threadIdx.x], tag);
         __syncthreads();
         trace_stamp(sc, it, 3);
         delta = 0.0; gamma = 0.0;
         for (int q = 0; q < pc->world; ++q) {
-            delta += __ldcv(&pc->mine->dot_val[0][q]);
-            gamma += __ldcv(&pc->mine->dot_val[1][q]);
+            delta += __ldcv(&pc->mine->dot_val[3 + 2 * mp][q]);
+            gamma += __ldcv(&pc->mine->dot_val[4 + 2 * mp][q]);
         }
     } else {
         delta = sum_partials(delta_ref, red);

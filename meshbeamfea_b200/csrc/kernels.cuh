@@ -26,8 +26,12 @@ constexpr int kMaxWorld = 16;
 // mailbox with acquire loads.  tag = (solve epoch << 32) | iteration stamp.
 struct Mailbox {
     unsigned long long halo_tag[kMaxWorld];    // [q]: rank q's boundary x-blocks have landed in my ghost region
-    unsigned long long dot_tag[3][kMaxWorld];  // [0]: p.Ap   [1]: rho = r~.r~   [2]: per-batch ||r||^2
-    double dot_val[3][kMaxWorld];              // same slots, one value per source rank
+    // classic CG: [0] p.Ap, [1] rho = r~.r~, [2] per-batch ||r||^2 -- two all-to-all exchanges per
+    // iteration interlock, so one slot each is safe.  Single-reduction CG has ONE exchange per
+    // iteration and a rank may run one exchange ahead of a non-neighbour's consumption: its slots are
+    // double-buffered by iteration parity: tag [3 + par], values [3 + 2 par] (r.K~r) and [4 + 2 par] (r.r)
+    unsigned long long dot_tag[5][kMaxWorld];
+    double dot_val[7][kMaxWorld];
 };
 
 struct PeerCtx {          // device-resident, local memory
