@@ -77,7 +77,7 @@ typedef struct mbfea_options {
     int32_t storage;       /* solver matrix: 0 auto, 1 every off-diagonal block in
                               its own row, 2 symmetric half (each block pair
                               stored once, reached transposed from the other row) */
-    int32_t cg_variant;    /* 0 auto, 1 classic CG (two dot-product exchanges per
+    int32_t cg_variant;    /* 0 auto (1 on one GPU, 2 on several), 1 classic CG (two dot-product exchanges per
                               iteration), 2 single-reduction CG (Chronopoulos-Gear:
                               SpMV on the residual, one exchange per iteration)  */
     int32_t reserved[4];

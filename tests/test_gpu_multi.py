@@ -45,7 +45,7 @@ def _worker(rank, world, uid_path, out_dir, n, comm_mode, variant):
 
 @pytest.mark.parametrize("comm_mode,variant", [(0, 1), (1, 1), (0, 2), (1, 2)],
                          ids=["nvlink_peer_memory", "nccl", "nvlink_single_reduction_cg", "nccl_single_reduction_cg"])
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_two_rank_solve_matches_single_and_oracle(built, tmp_path, world, comm_mode, variant):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
