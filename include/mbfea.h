@@ -80,7 +80,11 @@ typedef struct mbfea_options {
     int32_t cg_variant;    /* 0 auto (1 on one GPU, 2 on several), 1 classic CG (two dot-product exchanges per
                               iteration), 2 single-reduction CG (Chronopoulos-Gear:
                               SpMV on the residual, one exchange per iteration)  */
-    int32_t reserved[4];
+    int32_t batch_mode;    /* a job that is a batch of >= 32 independent small meshes
+                              (connected components with contiguous vertex ranges, each
+                              <= 1024 free vertices) is solved one CTA per mesh, each
+                              with its own iteration count: 0 auto, 1 never            */
+    int32_t reserved[3];
 } mbfea_options;
 
 typedef struct mbfea_stats {
@@ -105,7 +109,9 @@ typedef struct mbfea_stats {
                                    recomputed residual stalls just above (FP64 limit of
                                    this system); 0: not converged                      */
     int32_t restarts;           /* residual replacements done by the solve             */
-    int32_t reserved[4];
+    int32_t n_components;       /* > 0: batched solve, one CTA per mesh; iterations = the
+                                   slowest mesh's count                                 */
+    int32_t reserved[3];
 } mbfea_stats;
 
 int          mbfea_version(void);

@@ -23,7 +23,7 @@ class Options(C.Structure):
         ("device", C.c_int32), ("verbose", C.c_int32), ("tol", C.c_double), ("max_iter", C.c_int64),
         ("check_every", C.c_int32), ("spmv_kernel", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("use_graph", C.c_int32), ("comm_mode", C.c_int32), ("storage", C.c_int32),
-        ("cg_variant", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("cg_variant", C.c_int32), ("batch_mode", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -40,7 +40,7 @@ class Stats(C.Structure):
         ("bytes_spmv", C.c_double), ("bytes_pcg_iter", C.c_double), ("bytes_assemble", C.c_double),
         ("bytes_recover", C.c_double),
         ("kernel_launches", C.c_int64), ("converged", C.c_int32), ("restarts", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("n_components", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
     def as_dict(self):

@@ -126,6 +126,9 @@ struct mbfea_ctx {
     std::vector<Mailbox *> peer_mailbox;   // [world]; own entry = mailbox.p
     std::vector<double *> peer_p;          // [world]; peers' p vectors (IPC mappings), own = p.p
     unsigned long long epoch = 0;
+    // batched solve (one CTA per connected component)
+    DevBuf<int32_t> comp_ptr, comp_iters, comp_status;
+    DevBuf<double> comp_rr, comp_ff;
     DevBuf<unsigned long long> trace;  // MBFEA_TRACE=1: globaltimer stamps of the first iterations
 
     // PCG graph cache
@@ -721,7 +724,10 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan);
         // solver format: symmetric-half storage unless full rows are asked for (the TMA kernel
         // streams whole rows and has no transposed-reference path)
-        const bool half = c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2);
+        if (c->opt.batch_mode != 1) find_components(c->plan, 1024, 32);
+        else { c->plan.comp_ptr.clear(); c->plan.comp_max_rows = 0; }
+        const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
+        const bool half = !batched && (c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2));
         build_solver_format(c->plan, half);
         build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
         build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
@@ -778,6 +784,12 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         upload(c, c->lofs, c->plan.lofs);
         upload(c, c->ilv_base, c->plan.tile_base);
         upload(c, c->send_rows, c->plan.send_rows);
+        if (batched) {
+            const size_t nc = c->plan.comp_ptr.size() - 1;
+            upload(c, c->comp_ptr, c->plan.comp_ptr);
+            CK(c->comp_iters.alloc(nc)); CK(c->comp_status.alloc(nc));
+            CK(c->comp_rr.alloc(nc)); CK(c->comp_ff.alloc(nc));
+        }
         lap("plan upload");
         CK(c->sendbuf.alloc((size_t)36 * c->plan.send_rows.size()));
         CK(c->vals.alloc((size_t)nnzb * 36));
@@ -812,6 +824,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         s.n_vertices = V; s.n_beams = E; s.n_fixed = V - c->plan.nb_global;
         s.n_block_rows = nb; s.n_block_rows_global = c->plan.nb_global;
         s.nnz_blocks = nnzb; s.n_ghost_blocks = ng;
+        s.n_components = batched ? (int32_t)(c->plan.comp_ptr.size() - 1) : 0;
         // algorithmic bytes: SpMV 292/block + 100/row; PCG iteration
         // adds 10 vector passes (48 B/row each) + the 288 B block-Jacobi inverse
         // algorithmic bytes: the solver SpMV streams 288 B + a 4 B column id per STORED
@@ -886,6 +899,60 @@ int mbfea_solve(mbfea_ctx *c)
         }
         check += check & 1;  // parity alternates: keep batches even
 
+        if (!c->plan.comp_ptr.empty()) {
+            // ---- batched path: one CTA per mesh, own iteration count, own stop test ----
+            const int nc = (int)c->plan.comp_ptr.size() - 1;
+            const size_t smem = (size_t)c->plan.comp_max_rows * 6 * 4 * sizeof(double);
+            CK((cudaError_t)cg_batched_prepare(smem));
+            CK(cudaEventRecord(c->ev[0], c->st));
+            launch_cg_batched(c->st, nc, smem, c->comp_ptr.p, c->uptr.p, c->ucol.p, c->vals_s.p, c->f.p, c->sinv.p,
+                              c->lfac.p, c->y.p, c->opt.tol, (int)std::min<long long>(max_iter, INT32_MAX), 16,
+                              c->comp_iters.p, c->comp_rr.p, c->comp_ff.p, c->comp_status.p);
+            launch_unscale(c->st, nb, c->sinv.p, c->y.p, c->x.p);
+            CK(cudaEventRecord(c->ev[1], c->st));
+            c->launches += 2;
+            // recomputed residual over the whole job: f~ = S f into ft first
+            launch_cg_init(c->st, nb, c->f.p, c->sinv.p, c->rt.p, c->rt.p, c->ft.p, c->p.p, c->part_b.p, c->part_c.p);
+            CK(cudaMemcpyAsync(c->p.p, c->y.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            run_spmv(c, 1, c->p.p, c->Ap.p, nullptr, nullptr, nullptr);
+            launch_cg_check(c->st, nb, c->lfac.p, c->ft.p, c->Ap.p, c->part_a.p, nullptr, nullptr);
+            launch_reduce_partials(c->st, c->part_a.p, gv, c->red.p, nullptr, nullptr, nullptr);
+            c->launches += 4;
+            std::vector<int32_t> its((size_t)nc), stat((size_t)nc);
+            std::vector<double> crr((size_t)nc), cff((size_t)nc);
+            double rr_true = 0.0;
+            CK(cudaMemcpyAsync(its.data(), c->comp_iters.p, its.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(stat.data(), c->comp_status.p, stat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(crr.data(), c->comp_rr.p, crr.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(cff.data(), c->comp_ff.p, cff.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(&rr_true, c->red.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            long long it_max = 0, it_sum = 0;
+            double rr = 0.0, ff = 0.0, worst = 0.0;
+            int n_bad = 0, n_max = 0;
+            for (int b = 0; b < nc; ++b) {
+                it_max = std::max<long long>(it_max, its[(size_t)b]); it_sum += its[(size_t)b];
+                rr += crr[(size_t)b]; ff += cff[(size_t)b];
+                if (cff[(size_t)b] > 0) worst = std::max(worst, std::sqrt(crr[(size_t)b] / cff[(size_t)b]));
+                n_bad += stat[(size_t)b] == 3; n_max += stat[(size_t)b] == 2;
+            }
+            mbfea_stats &s = c->stats;
+            s.ms_pcg = elapsed(c, 0, 1);
+            s.iterations = it_max;
+            s.rel_residual = worst;   // the worst mesh's own ||r|| / ||f||
+            s.true_rel_residual = ff > 0 ? std::sqrt(rr_true / ff) : 0.0;
+            s.restarts = 0;
+            s.converged = (n_bad == 0 && n_max == 0) ? 1 : 0;
+            c->solved = true; c->recovered = false;
+            if (c->opt.verbose)
+                std::fprintf(stderr, "[mbfea] batched CG: %d meshes, iterations max %lld mean %.1f, worst rel res %.3e, job true rel res %.3e, %.2f ms\n",
+                             nc, it_max, (double)it_sum / nc, worst, s.true_rel_residual, s.ms_pcg);
+            if (n_bad) return fail(c, MBFEA_ESINGULAR, "CG breakdown in " + std::to_string(n_bad) + " mesh(es) of the batch (not SPD: is every mesh held by a fixed vertex?)");
+            if (n_max) return fail(c, MBFEA_ENOCONV, std::to_string(n_max) + " mesh(es) of the batch reached max_iter before the requested tolerance");
+            if (!(s.true_rel_residual <= std::max(1e3 * c->opt.tol, 1e-6)))
+                return fail(c, MBFEA_ESINGULAR, "recomputed residual disagrees with the CG recurrence: a mesh of the batch is singular");
+            return MBFEA_OK;
+        }
         const int variant = cg_variant(c);
         CK(cudaEventRecord(c->ev[0], c->st));
         // f~ = S f, y = 0, r~ = p = f~  (CG on K~ = S K S^T  ==  block-Jacobi PCG on K)

@@ -1330,6 +1330,131 @@ __global__ void __launch_bounds__(256) k_cg_check_finish(PartialRef part, PcgSca
     }
 }
 
+// ---------------------------------------------------------------------------
+// Batched CG: many small independent meshes (connected components with contiguous block rows)
+// solved concurrently, ONE CTA PER COMPONENT.  The component's four CG vectors live in shared
+// memory, its K~ rows (full-row storage, plain BSR) stream from L2; every component runs its own
+// iteration count and stops on its own residual ||L r~|| <= tol ||f||.  No grid-wide
+// synchronisation, no host polling: a mesh that needs 300 iterations does not wait for one that
+// needs 30 000.
+// ---------------------------------------------------------------------------
+constexpr int kBatchThreads = 384;
+
+__device__ __forceinline__ double batch_block_sum(double v, double *scratch)
+{
+    // all threads get the result; fixed order
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBatchThreads / 32; ++k) t += scratch[k];
+    return t;
+}
+
+__global__ void __launch_bounds__(kBatchThreads) k_cg_batched(
+    int ncomp, const int32_t *__restrict__ comp_ptr, const int32_t *__restrict__ uptr,
+    const int32_t *__restrict__ ucol, const double *__restrict__ vals, const double *__restrict__ f,
+    const double *__restrict__ sinv, const double *__restrict__ lfac, double *__restrict__ y_out,
+    double tol, int max_iter, int check_every, int32_t *__restrict__ comp_iters, double *__restrict__ comp_rr,
+    double *__restrict__ comp_ff, int32_t *__restrict__ comp_status)
+{
+    extern __shared__ double sm[];
+    __shared__ double red[kBatchThreads / 32];
+    const int b = blockIdx.x;
+    if (b >= ncomp) return;
+    const int r0 = comp_ptr[b], r1 = comp_ptr[b + 1];
+    const int n = (r1 - r0) * 6;
+    double *y = sm, *r = sm + n, *p = sm + 2 * n, *Ap = sm + 3 * n;
+    // f~ = S f (row-local), ||f||^2
+    double ff = 0.0, rho = 0.0;
+    for (int j = threadIdx.x; j < n; j += kBatchThreads) {
+        const int row = r0 + j / 6, i = j % 6;
+        const double *fr = f + (int64_t)row * 6;
+        const double fv[6] = {fr[0], fr[1], fr[2], fr[3], fr[4], fr[5]};
+        const double t = lower_row_times(sinv, row, i, fv);
+        y[j] = 0.0; r[j] = t; p[j] = t;
+        rho = fma(t, t, rho);
+        ff = fma(fv[i], fv[i], ff);
+    }
+    rho = batch_block_sum(rho, red);
+    ff = batch_block_sum(ff, red);
+    const double tol2ff = tol * tol * ff;
+    int it = 0, status = (ff == 0.0) ? 1 : 0;
+    double rr = ff;
+    const double rho0 = rho;
+    while (status == 0) {
+        // Ap = K~ p (unit diagonal + the row's stored blocks; columns are inside the component)
+        for (int j = threadIdx.x; j < n; j += kBatchThreads) {
+            const int lrow = j / 6, i = j - 6 * lrow;
+            const int row = r0 + lrow;
+            double acc = p[j];
+            const int32_t kb = __ldg(uptr + row), ke = __ldg(uptr + row + 1);
+            for (int32_t k = kb; k < ke; ++k) {
+                const double *xx = p + (__ldg(ucol + k) - r0) * 6;
+                const double *v = vals + (int64_t)k * 36 + i * 6;
+                const double2 v0 = ldg2(v), v1 = ldg2(v + 2), v2 = ldg2(v + 4);
+                acc = fma(v0.x, xx[0], acc); acc = fma(v0.y, xx[1], acc);
+                acc = fma(v1.x, xx[2], acc); acc = fma(v1.y, xx[3], acc);
+                acc = fma(v2.x, xx[4], acc); acc = fma(v2.y, xx[5], acc);
+            }
+            Ap[j] = acc;
+        }
+        __syncthreads();
+        double pAp = 0.0;
+        for (int j = threadIdx.x; j < n; j += kBatchThreads) pAp = fma(p[j], Ap[j], pAp);
+        pAp = batch_block_sum(pAp, red);
+        if (!(pAp > 0.0) || !isfinite(pAp)) { status = 3; break; }
+        const double alpha = rho / pAp;
+        double rho_new = 0.0;
+        for (int j = threadIdx.x; j < n; j += kBatchThreads) {
+            y[j] = fma(alpha, p[j], y[j]);
+            const double rv = fma(-alpha, Ap[j], r[j]);
+            r[j] = rv;
+            rho_new = fma(rv, rv, rho_new);
+        }
+        rho_new = batch_block_sum(rho_new, red);   // (also orders the writes of r before the reads below)
+        ++it;
+        if (it % check_every == 0 || rho_new <= 1e-32 * rho0 || it >= max_iter) {
+            double t2 = 0.0;
+            for (int j = threadIdx.x; j < n; j += kBatchThreads) {
+                const int lrow = j / 6, i = j - 6 * lrow;
+                const double t = lower_row_times(lfac, r0 + lrow, i, r + lrow * 6);
+                t2 = fma(t, t, t2);
+            }
+            rr = batch_block_sum(t2, red);
+            if (rr <= tol2ff) { status = 1; break; }
+            if (rho_new <= 1e-32 * rho0) { status = 1; break; }
+            if (!isfinite(rr)) { status = 3; break; }
+            if (it >= max_iter) { status = 2; break; }
+        }
+        const double beta = rho_new / rho;
+        rho = rho_new;
+        for (int j = threadIdx.x; j < n; j += kBatchThreads) p[j] = fma(beta, p[j], r[j]);
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += kBatchThreads) y_out[(int64_t)r0 * 6 + j] = y[j];
+    if (threadIdx.x == 0) { comp_iters[b] = it; comp_rr[b] = rr; comp_ff[b] = ff; comp_status[b] = status; }
+}
+
+int cg_batched_prepare(size_t smem_bytes)
+{
+    return (int)cudaFuncSetAttribute(k_cg_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+void launch_cg_batched(cudaStream_t st, int ncomp, size_t smem_bytes, const int32_t *comp_ptr, const int32_t *uptr,
+                       const int32_t *ucol, const double *vals, const double *f, const double *sinv, const double *lfac,
+                       double *y, double tol, int max_iter, int check_every, int32_t *comp_iters, double *comp_rr,
+                       double *comp_ff, int32_t *comp_status)
+{
+    if (ncomp <= 0) return;
+    k_cg_batched<<<ncomp, kBatchThreads, smem_bytes, st>>>(ncomp, comp_ptr, uptr, ucol, vals, f, sinv, lfac, y, tol,
+                                                          max_iter, check_every, comp_iters, comp_rr, comp_ff, comp_status);
+}
+
 // x = S^T y  (back to the unscaled unknowns)
 __global__ void __launch_bounds__(kSpmvThreads) k_unscale(int64_t nb, const double *__restrict__ sinv,
                                                           const double *__restrict__ y, double *__restrict__ x)

@@ -125,6 +125,12 @@ void launch_cg_restart(cudaStream_t st, int64_t nb, const double *lfac, const do
                        double *dir, double dir_scale, double *aux_zero, double *part_rr, double *part_rho);
 void launch_cg_restart_finish(cudaStream_t st, PartialRef rr, PartialRef rho, PcgScalars *sc, unsigned long long epoch,
                               int clear_done);
+// batched CG: one CTA per connected component (contiguous block rows), vectors in shared memory
+int  cg_batched_prepare(size_t smem_bytes);
+void launch_cg_batched(cudaStream_t st, int ncomp, size_t smem_bytes, const int32_t *comp_ptr, const int32_t *uptr,
+                       const int32_t *ucol, const double *vals, const double *f, const double *sinv, const double *lfac,
+                       double *y, double tol, int max_iter, int check_every, int32_t *comp_iters, double *comp_rr,
+                       double *comp_ff, int32_t *comp_status);
 void launch_unscale(cudaStream_t st, int64_t nb, const double *sinv, const double *y, double *x);
 int peer_timeout_flag();  // 1 once any peer wait gave up (a rank died)
 // P2P halo: owned boundary x-blocks -> the neighbours' ghost slots (peer stores), then the tag

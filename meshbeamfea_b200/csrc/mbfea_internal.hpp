@@ -45,6 +45,11 @@ struct HostPlan {
     // block a transposed reference points to.  Plain BSR order is kept for full-row storage.
     std::vector<int32_t> tile_base;         // #tiles + 1, in 16-byte units
     std::vector<int32_t> lofs;
+    // Connected components of the reduced system when each occupies a contiguous range of block
+    // rows (a batch of independent meshes submitted as one job): comp_ptr[b]..comp_ptr[b+1].
+    // Empty when the job is one mesh, the ranges interleave, or a component is too large.
+    std::vector<int32_t> comp_ptr;
+    int32_t comp_max_rows = 0;
     std::vector<int64_t> ghost_global;// ascending => grouped by owner
     std::vector<int32_t> ghost_owner;
     std::vector<int32_t> send_rows;   // local row ids grouped by destination rank
@@ -78,6 +83,10 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
 // Solver format from the full pattern (see HostPlan::uptr).  half=false keeps every
 // off-diagonal block in its own row (no transposed references).
 void build_solver_format(HostPlan &plan, bool half);
+
+// Fills plan.comp_ptr when the job is a batch of >= min_components independent meshes whose block
+// rows are contiguous and no larger than max_rows (single rank only).
+void find_components(HostPlan &plan, int32_t max_rows, int32_t min_components);
 
 // Row tiles for the TMA-staged SpMV: tile t covers rows [tile_row[t], tile_row[t+1]).
 void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,

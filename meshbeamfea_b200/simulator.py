@@ -141,7 +141,7 @@ class Context:
     """One ``mbfea_ctx``: device buffers, stream, PCG graph, optional NCCL comm."""
 
     def __init__(self, device: int = -1, tol: float = 1e-8, max_iter: int = 0, verbose: bool = False,
-                 spmv_kernel: int = 0, check_every: int = 0, use_graph: bool = True, comm_mode: int = 0, storage: int = 0, cg_variant: int = 0):
+                 spmv_kernel: int = 0, check_every: int = 0, use_graph: bool = True, comm_mode: int = 0, storage: int = 0, cg_variant: int = 0, batch_mode: int = 0):
         self._lib = L.lib()
         o = Options()
         self._lib.mbfea_options_default(C.byref(o))
@@ -150,6 +150,7 @@ class Context:
         o.comm_mode = comm_mode
         o.storage = storage
         o.cg_variant = cg_variant
+        o.batch_mode = batch_mode
         self._h = C.c_void_p()
         rc = self._lib.mbfea_create(C.byref(self._h), C.byref(o))
         if rc != L.OK:

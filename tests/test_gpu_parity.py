@@ -351,6 +351,37 @@ def test_batched_small_meshes_block_diagonal(built):
         off += V
 
 
+def test_batched_solver_one_cta_per_mesh(built):
+    """BASELINE config 5: a job that is a batch of independent small meshes is solved one CTA per
+    mesh (own iteration count, own stop test).  Must equal the per-mesh oracle solutions and the
+    global solver on the same job; meshes converge at different iteration counts."""
+    jobs = [syn.random_mesh(500 + m, V=40 + (m % 5) * 10) for m in range(48)]
+    merged = syn.merge_jobs(jobs)
+    with ctx_for(merged, tol=1e-12) as c, ctx_for(merged, tol=1e-12, batch_mode=1) as g:
+        c.execute(); g.execute()
+        sb, sg = c.stats(), g.stats()
+        assert sb["n_components"] == 48 and sg["n_components"] == 0
+        assert sb["converged"] == 1 and sb["rel_residual"] <= 1e-12
+        U, F = c.displacements(), c.edge_forces()
+        assert rel_l2(U, g.displacements()) < 1e-9 and rel_l2(F, g.edge_forces()) < 1e-9
+        # a second execute reproduces the first bit for bit
+        c.execute()
+        assert np.array_equal(U, c.displacements())
+    off = eoff = 0
+    for jb in jobs:
+        Uo, Fo = orc.solve(to_oracle(jb))
+        V, E = jb.nodes.shape[0], jb.elements.shape[0]
+        assert rel_l2(U[off:off + V], Uo) < TOL_U
+        assert rel_l2(F[:, 2 * eoff:2 * (eoff + E)], Fo) < TOL_U
+        off += V; eoff += E
+    # a mesh of the batch without any fixed vertex is reported, not silently wrong
+    bad = [syn.random_mesh(900 + m, V=40) for m in range(40)]
+    bad[7].fixedNodes = np.zeros(0, np.int32)
+    with ctx_for(syn.merge_jobs(bad), tol=1e-10, max_iter=3000) as c:
+        with pytest.raises((mb.SingularSystem, mb.NotConverged)):
+            c.execute()
+
+
 def test_cpp_dropin_runs_the_reference_tester_harness(built):
     """meshbeamfea_b200/cpp/tester_main: BeamSimulatorTester::launchRotationTest
     [REF src/beamsimulatortester.cpp:8-41] through the C++17 drop-in header."""
