@@ -421,35 +421,21 @@ void find_components(HostPlan &P, int32_t max_rows, int32_t min_components)
     P.comp_ptr.clear(); P.comp_max_rows = 0;
     const int64_t nb = P.nb();
     if (P.world != 1 || nb < min_components) return;
-    // union-find over the block pattern (path halving, union by smaller root id => root = min row)
-    std::vector<int32_t> parent((size_t)nb);
-    for (int64_t r = 0; r < nb; ++r) parent[r] = (int32_t)r;
-    auto find = [&](int32_t u) {
-        while (parent[u] != u) { parent[u] = parent[parent[u]]; u = parent[u]; }
-        return u;
-    };
-    for (int64_t r = 0; r < nb; ++r)
-        for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
-            const int32_t c = P.colidx[k];
-            if (c >= r) continue;
-            const int32_t a = find((int32_t)r), b = find(c);
-            if (a != b) parent[std::max(a, b)] = std::min(a, b);
-        }
-    // contiguous ranges: walking the rows in order, the root may only ever change to the current row
-    std::vector<int32_t> starts;
-    int32_t cur = -1;
+    // Independent row ranges: sweep the rows keeping the furthest column reached so far; a range
+    // closes at row r when nothing in it couples beyond r (the pattern is symmetric, so nothing
+    // later couples back into it either).  A range may hold several connected components (a mesh
+    // whose free vertices fall apart once its fixed vertices are removed stays one range).
+    std::vector<int32_t> starts{0};
+    int32_t reach = 0, mx = 0;
     for (int64_t r = 0; r < nb; ++r) {
-        const int32_t root = find((int32_t)r);
-        if (root == cur) continue;
-        if (root != (int32_t)r) return;  // a component seen before resumes: ranges interleave
-        starts.push_back((int32_t)r);
-        cur = root;
+        if (P.rowptr[r + 1] > P.rowptr[r]) reach = std::max(reach, P.colidx[P.rowptr[r + 1] - 1]);  // columns ascending
+        if (reach <= (int32_t)r) {
+            mx = std::max(mx, (int32_t)(r + 1) - starts.back());
+            starts.push_back((int32_t)(r + 1));
+        }
     }
-    if ((int64_t)starts.size() < min_components) return;
-    starts.push_back((int32_t)nb);
-    int32_t mx = 0;
-    for (size_t b = 0; b + 1 < starts.size(); ++b) mx = std::max(mx, starts[b + 1] - starts[b]);
-    if (mx > max_rows) return;
+    if (starts.back() != (int32_t)nb) return;   // cannot happen for a symmetric pattern
+    if ((int64_t)starts.size() - 1 < min_components || mx > max_rows) return;
     P.comp_ptr = std::move(starts);
     P.comp_max_rows = mx;
 }
