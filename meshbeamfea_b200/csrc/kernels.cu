@@ -683,13 +683,11 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
             Mailbox *m = pc->peer[threadIdx.x];
             if (partial2 == nullptr) {
                 m->dot_val[0][pc->rank] = s;
-                __threadfence_system();
-                st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);
+                st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);   // release orders this thread's value store first
             } else {   // single-reduction CG: slots double-buffered by iteration parity
                 const int par = (int)(sc->iter & 1);
                 m->dot_val[3 + 2 * par][pc->rank] = s;
                 m->dot_val[4 + 2 * par][pc->rank] = s2;
-                __threadfence_system();
                 st_release_sys(&m->dot_tag[3 + par][pc->rank], tag + 1);
             }
         }
@@ -999,7 +997,6 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
         if ((int)threadIdx.x < pc->world) {
             Mailbox *m = pc->peer[threadIdx.x];
             m->dot_val[1][pc->rank] = sa;
-            __threadfence_system();
             st_release_sys(&m->dot_tag[1][pc->rank], tag);
         }
     }
@@ -1037,6 +1034,7 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
     }
     const double beta = rho_new / sc->rz[parity];
     const int64_t n2 = n >> 1;
+    bool pushed = false;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += (int64_t)gridDim.x * blockDim.x) {
         const double2 rv = reinterpret_cast<const double2 *>(rt)[j];
         double2 pv = reinterpret_cast<double2 *>(p)[j];
@@ -1049,14 +1047,14 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
                 const int off = (int)(j - row * 3) * 2;
                 const int32_t first = code & 0x0fffffff, cnt = code >> 28;
                 for (int32_t q = 0; q < cnt; ++q) *reinterpret_cast<double2 *>(push_dst[first + q] + off) = pv;
+                pushed = true;
             }
         }
     }
     if (push_idx != nullptr) {
-        __threadfence_system();
+        if (pushed) __threadfence_system();   // this thread's peer stores land before its CTA takes a ticket
         if (last_cta_done(pc->tickets + 2)) {
             if ((int)threadIdx.x < pc->n_neighbors) {
-                __threadfence_system();
                 // tag_cur = (epoch << 32 | k) + 1: exactly the halo tag iteration k+1 waits for
                 st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], sc->tag_cur);
             }
@@ -1144,6 +1142,7 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
     // (rho0 is the very first gamma of the solve, kept across restarts)
     const bool bad = !exact && (!(den > 0.0) || !isfinite(den) || !isfinite(gamma));
     const double alpha = (exact || bad) ? 0.0 : gamma / den;
+    bool pushed = false;
     if (!exact && !bad) {
         const int64_t n2 = n >> 1;
         for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += (int64_t)gridDim.x * blockDim.x) {
@@ -1166,15 +1165,15 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
                     const int off = (int)(j - row * 3) * 2;
                     const int32_t first = code & 0x0fffffff, cnt = code >> 28;
                     for (int32_t q = 0; q < cnt; ++q) *reinterpret_cast<double2 *>(push_dst[first + q] + off) = rv;
+                    pushed = true;
                 }
             }
         }
     }
     if (push_idx != nullptr) {   // the halo tag must be published even when nothing moved (peers wait on it)
-        __threadfence_system();
+        if (pushed) __threadfence_system();
         if (last_cta_done(pc->tickets + 2)) {
             if ((int)threadIdx.x < pc->n_neighbors) {
-                __threadfence_system();
                 st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
             }
         }
@@ -1237,7 +1236,6 @@ __global__ void __launch_bounds__(kSpmvThreads) k_cg_check(int64_t nb, const dou
             const unsigned long long tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)sc->checks) + 1;
             Mailbox *m = pc->peer[threadIdx.x];
             m->dot_val[2][pc->rank] = sa;
-            __threadfence_system();
             st_release_sys(&m->dot_tag[2][pc->rank], tag);
         }
     }
