@@ -342,10 +342,11 @@ __global__ void __launch_bounds__(128, 6) k_assemble(int64_t nnzb, const int32_t
                                                      const ElemGeom *__restrict__ geom, double *__restrict__ vals)
 {
     // two threads per output block: rows 0-2 and rows 3-5 (18 register accumulators each, so six
-    // CTAs of 128 threads stay resident per SM); the pair writes 288 contiguous bytes
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t k = t >> 1;
-    const int h = (int)(t & 1);
+    // CTAs of 128 threads stay resident per SM).  The half is warp-uniform (even warps take rows
+    // 0-2, odd warps rows 3-5 of the same 32 blocks), so no warp executes both branches.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * 64 + (warp >> 1) * 32 + lane;
+    const int h = warp & 1;
     if (k >= nnzb) return;
     double acc[18];
 #pragma unroll
@@ -383,8 +384,7 @@ void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, 
                      const ElemGeom *geom, double *vals)
 {
     if (nnzb <= 0) return;
-    const int64_t n = nnzb * 2;
-    k_assemble<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(nnzb, contrib_ptr, contrib, geom, vals);
+    k_assemble<<<(unsigned)((nnzb + 63) / 64), 128, 0, st>>>(nnzb, contrib_ptr, contrib, geom, vals);
 }
 
 // ---------------------------------------------------------------------------
