@@ -390,3 +390,23 @@ def test_cpp_dropin_runs_the_reference_tester_harness(built):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "46 runs, 0 failures" in r.stdout
+
+
+def test_mbfea_run_cli_on_reference_scenario_files(built, tmp_path):
+    """meshbeamfea_b200/cpp/mbfea_run: config.json + PLY of the reference in, the two result CSVs
+    of GUI::setSimulation [REF src/gui.cpp:363-370] out (the reference has no CLI)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(HERE), "meshbeamfea_b200", "cpp", "mbfea_run")
+    cfg, ply = write_scenario(tmp_path, [0], [[2, 1, 100]])
+    out = os.path.join(str(tmp_path), "Results")
+    r = subprocess.run([exe, cfg, "--out", out, "--tol", "1e-13"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Mz in [-200, 100]" in r.stdout
+    nd = np.loadtxt(os.path.join(out, "nodal_displacements.csv"), delimiter=",")
+    ef = np.loadtxt(os.path.join(out, "elemental_displacements.csv"), delimiter=",")
+    assert nd.shape == (3, 6) and ef.shape == (2, 12)
+    assert nd[2, 1] == pytest.approx(0.40000006103516, abs=1e-12)
+    # config.json as shipped with the reference: vertex 3 does not exist in the fixture
+    cfg2, _ = write_scenario(tmp_path, [1, 2, 3], [[0, 0, 1000]])
+    r = subprocess.run([exe, cfg2, "--out", out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Vertex index is outside of valid range." in r.stderr
