@@ -231,6 +231,9 @@ int mbfea_comm_init(mbfea_ctx *ctx, const uint8_t id128[128], int32_t rank, int3
  * Call with NULL arrays to size.  send_* describe what this rank SENDS.      */
 typedef struct mbfea_plan_sizes {
     int64_t nb_global, row_begin, row_end, nnz_blocks, n_ghost, n_send, n_neighbors;
+    /* batch detection (world == 1): independent block-row ranges of the reduced system when the
+     * job is a batch of >= 32 small meshes (each <= 1024 rows), else 0                        */
+    int64_t n_components, max_component_rows;
 } mbfea_plan_sizes;
 int mbfea_plan_partition(int64_t V, int64_t E, const int32_t *elems_cm,
                          int64_t F, const int32_t *fixed, int32_t rank, int32_t world,

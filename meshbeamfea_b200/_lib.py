@@ -49,7 +49,8 @@ class Stats(C.Structure):
 
 class PlanSizes(C.Structure):
     _fields_ = [(k, C.c_int64) for k in
-                ("nb_global", "row_begin", "row_end", "nnz_blocks", "n_ghost", "n_send", "n_neighbors")]
+                ("nb_global", "row_begin", "row_end", "nnz_blocks", "n_ghost", "n_send", "n_neighbors",
+                 "n_components", "max_component_rows")]
 
 
 _lib = None

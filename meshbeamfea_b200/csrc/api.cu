@@ -1481,6 +1481,9 @@ int mbfea_plan_partition(int64_t V, int64_t E, const int32_t *elems_cm, int64_t 
         sizes->nb_global = P.nb_global; sizes->row_begin = P.row_begin; sizes->row_end = P.row_end;
         sizes->nnz_blocks = P.nnzb(); sizes->n_ghost = (int64_t)P.ghost_global.size();
         sizes->n_send = (int64_t)P.send_rows.size(); sizes->n_neighbors = (int64_t)P.neighbors.size();
+        find_components(P, 1024, 32);
+        sizes->n_components = P.comp_ptr.empty() ? 0 : (int64_t)P.comp_ptr.size() - 1;
+        sizes->max_component_rows = P.comp_max_rows;
     }
     if (rowptr) for (size_t i = 0; i < P.rowptr.size(); ++i) rowptr[i] = P.rowptr[i];
     if (colidx) std::copy(P.colidx.begin(), P.colidx.end(), colidx);

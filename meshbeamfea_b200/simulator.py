@@ -379,7 +379,8 @@ def plan_partition(V: int, elements: np.ndarray, fixed: np.ndarray, rank: int, w
         _raise(rc, lib.mbfea_status_string(rc).decode())
     return dict(nb_global=sz.nb_global, row_begin=sz.row_begin, row_end=sz.row_end, rowptr=rowptr,
                 colidx=col[:sz.nnz_blocks], ghost_global=gg[:sz.n_ghost], ghost_owner=go[:sz.n_ghost],
-                send_rows=sr[:sz.n_send], send_dest=sd[:sz.n_send], n_neighbors=sz.n_neighbors)
+                send_rows=sr[:sz.n_send], send_dest=sd[:sz.n_send], n_neighbors=sz.n_neighbors,
+                n_components=sz.n_components, max_component_rows=sz.max_component_rows)
 
 
 def read_scenario(config_json: str, ply_override: Optional[str] = None):

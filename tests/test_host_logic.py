@@ -149,6 +149,30 @@ def test_pattern_with_multi_edges_and_isolated_vertex(built):
     assert list(p["rowptr"]) == [0, 2, 4, 5] and list(p["colidx"]) == [0, 1, 0, 1, 2]
 
 
+def test_batch_detection(built):
+    """A job that is a batch of independent small meshes is recognised by its independent block-row
+    ranges (a mesh may fall into several connected components once its fixed vertices go)."""
+    jobs = [syn.random_mesh(300 + m, V=30 + (m % 4) * 10) for m in range(40)]
+    merged = syn.merge_jobs(jobs)
+    p = mb.plan_partition(merged.nodes.shape[0], merged.elements, merged.fixedNodes, 0, 1)
+    assert p["n_components"] == 40
+    assert p["max_component_rows"] == max(j.nodes.shape[0] - np.unique(j.fixedNodes).size for j in jobs)
+    # one connected mesh, too few meshes, or a partitioned job: not a batch
+    g = syn.planar_grid(12)
+    assert mb.plan_partition(g.nodes.shape[0], g.elements, g.fixedNodes, 0, 1)["n_components"] == 0
+    few = syn.merge_jobs(jobs[:8])
+    assert mb.plan_partition(few.nodes.shape[0], few.elements, few.fixedNodes, 0, 1)["n_components"] == 0
+    assert mb.plan_partition(merged.nodes.shape[0], merged.elements, merged.fixedNodes, 0, 2)["n_components"] == 0
+    # interleaved vertex numbering of two meshes couples the ranges: falls back to the global solver
+    a, b = syn.random_mesh(1, V=40), syn.random_mesh(2, V=40)
+    two = syn.merge_jobs([a, b] * 20)
+    perm = np.arange(two.nodes.shape[0]); perm[[3, 45]] = perm[[45, 3]]      # swap a vertex of mesh 0 with one of mesh 1
+    inv = np.argsort(perm)
+    el = inv[two.elements]
+    fx = inv[two.fixedNodes]
+    assert mb.plan_partition(two.nodes.shape[0], el, fx, 0, 1)["n_components"] == 39   # meshes 0 and 1 merge into one range
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_partition_plan_is_consistent(built, world):
     job = syn.cubic_lattice(7)
