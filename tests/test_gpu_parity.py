@@ -410,3 +410,62 @@ def test_mbfea_run_cli_on_reference_scenario_files(built, tmp_path):
     cfg2, _ = write_scenario(tmp_path, [1, 2, 3], [[0, 0, 1000]])
     r = subprocess.run([exe, cfg2, "--out", out], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Vertex index is outside of valid range." in r.stderr
+
+
+def test_edge_cases(built):
+    """Empty / degenerate inputs the reference's adapter would meet: every vertex fixed (nothing to
+    solve), one beam, duplicated fixed indices, two beams between the same vertices, a free vertex
+    without beams (reported singular), non-perpendicular normals (same frame formulas as upstream)."""
+    # every vertex fixed: zero displacements, zero forces, no iterations
+    job = syn.two_line_segments(fixed=(0, 1, 2))
+    with ctx_for(job) as c:
+        c.execute()
+        assert c.stats()["n_block_rows"] == 0 and c.stats()["iterations"] == 0
+        assert np.all(c.displacements() == 0) and np.all(c.edge_forces() == 0)
+    # one beam, one end clamped, duplicated fixed index
+    one = mb.SimulationJob(np.array([[0, 0, 0], [0, 0, 2.0]]), np.array([[1, 0]], np.int32), np.array([[1.0, 0, 0]]),
+                           np.array([0, 0, 0], np.int32), [mb.NodalForce(1, 0, 5.0), mb.NodalForce(1, 2, -7.0)],
+                           [mb.BeamDimensions(0.02, 0.03)], [mb.BeamMaterial(0.25, 70.0)])
+    U, F = orc.solve(to_oracle(syn.merge_jobs([_as_arrays(one)])))
+    with ctx_for(_as_arrays(one), tol=1e-13) as c:
+        c.execute()
+        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
+    # two beams between the same pair of vertices share one block (contributions summed in element order)
+    multi = syn.two_line_segments()
+    multi.elements = np.array([[0, 1], [1, 2], [2, 1]], np.int32)
+    multi.elementalNormals = np.array([[0, 1, 0], [0, 1, 0], [0, 0, 1.0]])
+    multi.beamDimensions = np.array([[0.01, 0.01], [0.01, 0.02], [0.03, 0.01]], np.float32)
+    multi.beamMaterial = np.array([[0.3, 800], [0.3, 210], [0.2, 70]], np.float32)
+    O = to_oracle(multi)
+    U, F = orc.solve(O)
+    with ctx_for(multi, tol=1e-13) as c:
+        c.assemble()
+        props, fm, rp, col, vals = oracle_bsr(O)
+        assert np.array_equal(c.bsr()[2], vals)
+        c.execute()
+        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
+    # a free vertex no beam touches: its diagonal block is zero -> singular, reported at assembly
+    iso = syn.two_line_segments()
+    iso.nodes = np.vstack([iso.nodes, [[5.0, 5.0, 5.0]]])
+    with ctx_for(iso) as c:
+        with pytest.raises(mb.SingularSystem):
+            c.execute()
+    # skewed (non-perpendicular, non-unit) normals: the frame is what the upstream formulas give
+    skew = syn.cubic_lattice(4)
+    rng = np.random.default_rng(9)
+    skew.elementalNormals = skew.elementalNormals * 2.5 + 0.3 * rng.standard_normal(skew.elementalNormals.shape)
+    O = to_oracle(skew)
+    with ctx_for(skew, tol=1e-13) as c:
+        assert np.array_equal(c.kelem(), orc.kelem_all(O))
+        c.execute()
+        U, F = orc.solve(O)
+        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
+
+
+def _as_arrays(job):
+    """SimulationJob with list-typed sections/forces -> the array-typed form merge_jobs expects."""
+    dims = np.array([[d.b, d.h] for d in job.beamDimensions], np.float32) if not isinstance(job.beamDimensions, np.ndarray) else job.beamDimensions
+    mat = np.array([[m.poissonsRatio, m.youngsModulusGPascal] for m in job.beamMaterial], np.float32) if not isinstance(job.beamMaterial, np.ndarray) else job.beamMaterial
+    return mb.SimulationJob(np.asarray(job.nodes, np.float64), np.asarray(job.elements, np.int32),
+                            np.asarray(job.elementalNormals, np.float64), np.asarray(job.fixedNodes, np.int32),
+                            job.nodalForces, dims, mat)
