@@ -560,7 +560,7 @@ constexpr int kSpmvThreads = kRowsPerCta * 6;
 #define MBFEA_SYM_PREFETCH 0  // fetch the next tile's row pointers while working on this one
 #endif
 
-template <bool SYM>
+template <bool SYM, bool DOT2>
 __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv_rowthread(
     int64_t nb, const int32_t *__restrict__ uptr, const int32_t *__restrict__ ucol,
     const double *__restrict__ vals, const int32_t *__restrict__ lptr, const int32_t *__restrict__ lcol,
@@ -656,7 +656,7 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
         if (live) {
             y[row * 6 + i] = acc;
             dot = fma(xi, acc, dot);
-            dot2 = fma(xi, xi, dot2);
+            if (DOT2) dot2 = fma(xi, xi, dot2);
         }
         if (MBFEA_SYM_PREFETCH) {
             kb = nkb; ke = nke; lb = nlb; le = nle; tb = ntb;
@@ -672,7 +672,7 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
         const double s = block_sum<false>(dot, red);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
     }
-    if (partial2 != nullptr) {   // single-reduction CG: x.x rides along with x.Ax
+    if (DOT2) {   // single-reduction CG: x.x rides along with x.Ax
         const double s = block_sum<false>(dot2, red);
         if (threadIdx.x == 0) partial2[blockIdx.x] = s;
     }
@@ -680,11 +680,11 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
         // fused reduction + all-gather: the last CTA sums the partials in fixed order and
         // stores this rank's dot product(s) into every rank's mailbox over NVLink
         const double s = sum_partials(PartialRef{partial, (int)gridDim.x, 1}, red);
-        const double s2 = partial2 != nullptr ? sum_partials(PartialRef{partial2, (int)gridDim.x, 1}, red) : 0.0;
+        const double s2 = DOT2 ? sum_partials(PartialRef{partial2, (int)gridDim.x, 1}, red) : 0.0;
         if ((int)threadIdx.x < pc->world) {
             const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
             Mailbox *m = pc->peer[threadIdx.x];
-            if (partial2 == nullptr) {
+            if (!DOT2) {
                 m->dot_val[0][pc->rank] = s;
                 st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);   // release orders this thread's value store first
             } else {   // single-reduction CG: slots double-buffered by iteration parity
@@ -710,12 +710,19 @@ void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, con
                            int identity, const double *x, double *y, double *partial, double *partial2,
                            const PcgScalars *sc, const PeerCtx *pc)
 {
-    if (lptr != nullptr)
-        k_spmv_rowthread<true><<<spmv_rowthread_grid(nb, true), kSpmvThreads, 0, st>>>(
-            nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base, identity, x, y, partial, partial2, sc, pc);
+    const int gs = spmv_rowthread_grid(nb, lptr != nullptr);
+    if (lptr != nullptr && partial2 != nullptr)
+        k_spmv_rowthread<true, true><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+                                                                  identity, x, y, partial, partial2, sc, pc);
+    else if (lptr != nullptr)
+        k_spmv_rowthread<true, false><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+                                                                   identity, x, y, partial, nullptr, sc, pc);
+    else if (partial2 != nullptr)
+        k_spmv_rowthread<false, true><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, nullptr, nullptr, nullptr,
+                                                                   nullptr, identity, x, y, partial, partial2, sc, pc);
     else
-        k_spmv_rowthread<false><<<spmv_rowthread_grid(nb, false), kSpmvThreads, 0, st>>>(
-            nb, uptr, ucol, vals, nullptr, nullptr, nullptr, nullptr, identity, x, y, partial, partial2, sc, pc);
+        k_spmv_rowthread<false, false><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, nullptr, nullptr, nullptr,
+                                                                    nullptr, identity, x, y, partial, nullptr, sc, pc);
 }
 
 // ---------------------------------------------------------------------------
