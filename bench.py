@@ -48,6 +48,8 @@ def make_job(workload: str):
     from meshbeamfea_b200 import synthetic as syn
     if workload.startswith("lattice"):
         return syn.cubic_lattice(int(workload[len("lattice"):]))
+    if workload.startswith("batch"):   # BASELINE config 5: N independent ~500-beam random meshes as one job
+        return syn.merge_jobs([syn.random_mesh(1234 + m) for m in range(int(workload[len("batch"):]))])
     if workload.startswith("gridshell"):
         return syn.gridshell(int(workload[len("gridshell"):]))
     if workload.startswith("grid"):

@@ -115,6 +115,9 @@ typedef struct mbfea_stats {
 } mbfea_stats;
 
 int          mbfea_version(void);
+/* sizeof(mbfea_options), sizeof(mbfea_stats), sizeof(mbfea_plan_sizes) as compiled into the
+ * library: lets a binding in another language verify its struct layouts at load time.       */
+void         mbfea_abi_sizes(int64_t sizes3[3]);
 void         mbfea_options_default(mbfea_options *opts);
 int          mbfea_create(mbfea_ctx **out, const mbfea_options *opts);
 void         mbfea_destroy(mbfea_ctx *ctx);

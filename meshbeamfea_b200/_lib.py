@@ -65,6 +65,7 @@ _i32 = C.c_int32
 # name -> (restype, argtypes); also the list the export test checks against the header
 SIGNATURES = {
     "mbfea_version": (C.c_int, []),
+    "mbfea_abi_sizes": (None, [_pi64]),
     "mbfea_options_default": (None, [C.POINTER(Options)]),
     "mbfea_create": (C.c_int, [C.POINTER(_vp), C.POINTER(Options)]),
     "mbfea_destroy": (None, [_vp]),
@@ -123,6 +124,11 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        sizes = (C.c_int64 * 3)()
+        L.mbfea_abi_sizes(sizes)
+        mine = (C.sizeof(Options), C.sizeof(Stats), C.sizeof(PlanSizes))
+        if tuple(sizes) != mine:
+            raise ImportError(f"{LIB_PATH}: struct layouts {tuple(sizes)} do not match this binding {mine}; rebuild the library")
         _lib = L
     return _lib
 

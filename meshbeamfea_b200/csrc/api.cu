@@ -563,6 +563,14 @@ extern "C" {
 
 int mbfea_version(void) { return MBFEA_VERSION; }
 
+void mbfea_abi_sizes(int64_t sizes3[3])
+{
+    if (!sizes3) return;
+    sizes3[0] = (int64_t)sizeof(mbfea_options);
+    sizes3[1] = (int64_t)sizeof(mbfea_stats);
+    sizes3[2] = (int64_t)sizeof(mbfea_plan_sizes);
+}
+
 void mbfea_options_default(mbfea_options *o)
 {
     if (!o) return;

@@ -33,7 +33,10 @@ def test_library_exports_every_declared_symbol(built):
     exported = set(re.findall(r" T (mbfea_[a-z0-9_]+)", out))
     assert set(names) <= exported, sorted(set(names) - exported)
     assert set(names) == set(L.SIGNATURES), sorted(set(names) ^ set(L.SIGNATURES))
-    lib = L.lib()
+    lib = L.lib()   # also verifies sizeof(mbfea_options / mbfea_stats / mbfea_plan_sizes) against the ctypes mirrors
+    sizes = (C.c_int64 * 3)()
+    lib.mbfea_abi_sizes(sizes)
+    assert tuple(sizes) == (C.sizeof(L.Options), C.sizeof(L.Stats), C.sizeof(L.PlanSizes))
     assert lib.mbfea_version() == 100
     assert lib.mbfea_status_string(2) == b"Vertex index is outside of valid range."
     assert lib.mbfea_status_string(3) == b"Node index is out of valid range."
