@@ -549,6 +549,9 @@ constexpr int kSpmvThreads = kRowsPerCta * 6;
 #ifndef MBFEA_SYM_UNROLL
 #define MBFEA_SYM_UNROLL 0    // explicit unroll factor of the block loops (0: leave it to the compiler)
 #endif
+#ifndef MBFEA_SYM_L2PF
+#define MBFEA_SYM_L2PF 0      // prefetch.global.L2 the value range of the CTA's tile after next (measured: slower)
+#endif
 #define MBFEA_PRAGMA_(x) _Pragma(#x)
 #define MBFEA_UNROLL_(n) MBFEA_PRAGMA_(unroll n)
 #if MBFEA_SYM_UNROLL > 0
@@ -585,11 +588,20 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
     // row pointers of the current tile; with MBFEA_SYM_PREFETCH the next tile's are requested before
     // this tile's blocks, so the pointer -> column -> x chain of the next tile is one level shorter
     int32_t kb = 0, ke = 0, lb = 0, le = 0, tb = 0;
+    // [pb, pe): 16-byte units of the tile this CTA will process after the next one.  Its whole value
+    // range is contiguous (interleaved layout), so the CTA can pull it into L2 a full tile ahead with
+    // fire-and-forget prefetches: by the time the loads are issued they are L2 hits, not HBM misses.
+    int32_t pb = 0, pe = 0;
+    const int64_t ntiles = (nb + kRowsPerCta - 1) / kRowsPerCta;
     {
         const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + lr;
         if (row < nb) {
             kb = __ldg(uptr + row); ke = __ldg(uptr + row + 1);
             if (SYM) { lb = __ldg(lptr + row); le = __ldg(lptr + row + 1); tb = __ldg(tile_base + (row >> 5)); }
+        }
+        if (SYM && MBFEA_SYM_L2PF) {
+            const int64_t t1 = (int64_t)blockIdx.x + gridDim.x;
+            if (t1 < ntiles) { pb = __ldg(tile_base + t1); pe = __ldg(tile_base + t1 + 1); }
         }
     }
     for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += stride) {
@@ -602,6 +614,11 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
                 nkb = __ldg(uptr + nrow); nke = __ldg(uptr + nrow + 1);
                 if (SYM) { nlb = __ldg(lptr + nrow); nle = __ldg(lptr + nrow + 1); ntb = __ldg(tile_base + (nrow >> 5)); }
             }
+        }
+        if (SYM && MBFEA_SYM_L2PF) {
+            const char *base = reinterpret_cast<const char *>(vals);
+            for (int64_t u = (int64_t)pb * 16 + (int64_t)threadIdx.x * 128; u < (int64_t)pe * 16; u += kSpmvThreads * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + u));
         }
         double xi = 0.0, acc = 0.0;
         if (live) {
@@ -666,6 +683,11 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
                 kb = __ldg(uptr + nrow); ke = __ldg(uptr + nrow + 1);
                 if (SYM) { lb = __ldg(lptr + nrow); le = __ldg(lptr + nrow + 1); tb = __ldg(tile_base + (nrow >> 5)); }
             }
+        }
+        if (SYM && MBFEA_SYM_L2PF) {
+            const int64_t t2 = (r0 >> 5) + 2 * (int64_t)gridDim.x;   // the tile after next
+            pb = pe = 0;
+            if (t2 < ntiles) { pb = __ldg(tile_base + t2); pe = __ldg(tile_base + t2 + 1); }
         }
     }
     if (partial != nullptr) {
