@@ -633,6 +633,7 @@ int mbfea_create(mbfea_ctx **out, const mbfea_options *opts)
                                                   "' is not sm_100-class; libmbfea ships sm_100a code only");
         }
         c->sm_count = prop.multiProcessorCount;
+        if (const char *e = std::getenv("MBFEA_PDL")) set_pdl(*e != '0');
         CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
         for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
         CK(cudaMallocHost(reinterpret_cast<void **>(&c->sc_host), sizeof(PcgScalars)));

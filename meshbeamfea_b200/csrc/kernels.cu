@@ -64,6 +64,30 @@ __device__ __forceinline__ double sum_partials(PartialRef ref, double *scratch)
     return block_sum<true>(s, scratch);
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The kernels of the CG loop are launched with programmatic stream serialisation: a kernel lets
+// its successor start launching at once (pdl_trigger) and itself waits for its predecessor's
+// results with pdl_wait before touching them.  The successor's CTAs become resident as this
+// kernel's CTAs retire, so launch latency and ramp-up overlap the previous kernel's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static bool g_use_pdl = true;
+void set_pdl(bool on) { g_use_pdl = on; }
+
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- peer-memory signalling ---------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -573,6 +597,8 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
 {
     __shared__ double red[33];
     __shared__ double ts[SYM ? kSpmvThreads * 6 : 1];
+    pdl_wait();      // the previous kernel's results (and sc) are visible from here
+    pdl_trigger();   // the next kernel may start launching
     if (sc != nullptr && sc->done != 0) return;
     if (sc != nullptr) trace_stamp(sc, sc->iter, 0);
     if (pc != nullptr) {
@@ -734,17 +760,19 @@ void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, con
 {
     const int gs = spmv_rowthread_grid(nb, lptr != nullptr);
     if (lptr != nullptr && partial2 != nullptr)
-        k_spmv_rowthread<true, true><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
-                                                                  identity, x, y, partial, partial2, sc, pc);
+        launch_pdl(k_spmv_rowthread<true, true>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+                   identity, x, y, partial, partial2, sc, pc);
     else if (lptr != nullptr)
-        k_spmv_rowthread<true, false><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
-                                                                   identity, x, y, partial, nullptr, sc, pc);
+        launch_pdl(k_spmv_rowthread<true, false>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+                   identity, x, y, partial, (double *)nullptr, sc, pc);
     else if (partial2 != nullptr)
-        k_spmv_rowthread<false, true><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, nullptr, nullptr, nullptr,
-                                                                   nullptr, identity, x, y, partial, partial2, sc, pc);
+        launch_pdl(k_spmv_rowthread<false, true>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, (const int32_t *)nullptr,
+                   (const int32_t *)nullptr, (const int32_t *)nullptr, (const int32_t *)nullptr, identity, x, y, partial,
+                   partial2, sc, pc);
     else
-        k_spmv_rowthread<false, false><<<gs, kSpmvThreads, 0, st>>>(nb, uptr, ucol, vals, nullptr, nullptr, nullptr,
-                                                                    nullptr, identity, x, y, partial, nullptr, sc, pc);
+        launch_pdl(k_spmv_rowthread<false, false>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, (const int32_t *)nullptr,
+                   (const int32_t *)nullptr, (const int32_t *)nullptr, (const int32_t *)nullptr, identity, x, y, partial,
+                   (double *)nullptr, sc, pc);
 }
 
 // ---------------------------------------------------------------------------
@@ -993,6 +1021,8 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
     const PeerCtx *pc)
 {
     __shared__ double red[33];
+    pdl_wait();      // the previous kernel's results (and sc) are visible from here
+    pdl_trigger();   // the next kernel may start launching
     if (sc->done != 0) return;
     trace_stamp(sc, sc->iter, 2);
     double pAp;
@@ -1045,6 +1075,8 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
                                                        double *const *__restrict__ push_dst)
 {
     __shared__ double red[33];
+    pdl_wait();      // the previous kernel's results (and sc) are visible from here
+    pdl_trigger();   // the next kernel may start launching
     if (sc->done != 0) return;
     const double pAp = sc->pAp;
     if (!(pAp > 0.0) || !isfinite(pAp)) {
@@ -1144,6 +1176,8 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
     const int32_t *__restrict__ push_idx, double *const *__restrict__ push_dst)
 {
     __shared__ double red[33];
+    pdl_wait();      // the previous kernel's results (and sc) are visible from here
+    pdl_trigger();   // the next kernel may start launching
     if (sc->done != 0) return;
     const long long it = sc->iter;    // stable: only block 0 bumps it, after its own reads
     trace_stamp(sc, it, 2);
@@ -1234,7 +1268,7 @@ void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef g
                      double *d, double *s, double *y, PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx,
                      double *const *push_dst)
 {
-    k_cg2_step<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, delta, gamma, r, w, d, s, y, sc, pc, push_idx, push_dst);
+    launch_pdl(k_cg2_step, cg_vec_grid(nb), 256, 0, st, 6 * nb, delta, gamma, r, w, d, s, y, sc, pc, push_idx, push_dst);
 }
 
 // per batch: partial sums of ||L (a - b)||^2 (b may be null): the unscaled residual norm
@@ -1245,6 +1279,8 @@ __global__ void __launch_bounds__(kSpmvThreads) k_cg_check(int64_t nb, const dou
 {
     __shared__ double vs[kSpmvThreads];
     __shared__ double red[33];
+    pdl_wait();
+    pdl_trigger();
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
     double rr = 0.0;
     for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
@@ -1342,6 +1378,8 @@ void launch_cg_restart_finish(cudaStream_t st, PartialRef rr, PartialRef rho, Pc
 __global__ void __launch_bounds__(256) k_cg_check_finish(PartialRef part, PcgScalars *sc, const PeerCtx *pc)
 {
     __shared__ double red[33];
+    pdl_wait();
+    pdl_trigger();
     double rr;
     if (pc != nullptr) {
         const unsigned long long tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)sc->checks) + 1;
@@ -1529,24 +1567,24 @@ int cg_vec_grid(int64_t nb)
 void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *p, const double *Ap,
                       double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc)
 {
-    k_cg_update<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, parity, pAp, p, Ap, y, rt, part_rho, sc, pc);
+    launch_pdl(k_cg_update, cg_vec_grid(nb), 256, 0, st, 6 * nb, parity, pAp, p, Ap, y, rt, part_rho, sc, pc);
 }
 
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
                        PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst)
 {
-    k_cg_pupdate<<<cg_vec_grid(nb), 256, 0, st>>>(6 * nb, parity, rho, rt, p, sc, pc, push_idx, push_dst);
+    launch_pdl(k_cg_pupdate, cg_vec_grid(nb), 256, 0, st, 6 * nb, parity, rho, rt, p, sc, pc, push_idx, push_dst);
 }
 
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
                      const PcgScalars *sc, const PeerCtx *pc)
 {
-    k_cg_check<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, lfac, a, b, part, sc, pc);
+    launch_pdl(k_cg_check, vec_grid(nb), kSpmvThreads, 0, st, nb, lfac, a, b, part, sc, pc);
 }
 
 void launch_cg_check_finish(cudaStream_t st, PartialRef part, PcgScalars *sc, const PeerCtx *pc)
 {
-    k_cg_check_finish<<<1, 256, 0, st>>>(part, sc, pc);
+    launch_pdl(k_cg_check_finish, 1, 256, 0, st, part, sc, pc);
 }
 
 void launch_unscale(cudaStream_t st, int64_t nb, const double *sinv, const double *y, double *x)
