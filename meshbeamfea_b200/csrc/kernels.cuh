@@ -132,7 +132,7 @@ void launch_cg_batched(cudaStream_t st, int ncomp, size_t smem_bytes, const int3
                        double *y, double tol, int max_iter, int check_every, int32_t *comp_iters, double *comp_rr,
                        double *comp_ff, int32_t *comp_status);
 void launch_unscale(cudaStream_t st, int64_t nb, const double *sinv, const double *y, double *x);
-void set_pdl(bool on);    // programmatic dependent launch of the CG-loop kernels (default on; MBFEA_PDL=0 turns it off)
+void set_pdl(bool on);    // programmatic dependent launch of the CG-loop kernels (default off; MBFEA_PDL=1 turns it on)
 int peer_timeout_flag();  // 1 once any peer wait gave up (a rank died)
 // P2P halo: owned boundary x-blocks -> the neighbours' ghost slots (peer stores), then the tag
 void launch_push_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, double *const *dst,
