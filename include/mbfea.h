@@ -63,10 +63,12 @@ typedef struct mbfea_options {
     int32_t device;        /* CUDA ordinal; -1 = current device                */
     int32_t verbose;       /* reference sets opts.verbose=true [REF :57]; here
                               stdout logging is opt-in                         */
-    double  tol;           /* PCG stop: ||r||_2 <= tol*||f||_2   (1e-8)        */
+    double  tol;           /* PCG stop: ||f - K u||_2 <= tol*||f||_2 (1e-8); tested on
+                              the recurrence once per batch, verified on the
+                              recomputed residual at the end                   */
     int64_t max_iter;      /* 0 = 20*ndof                                       */
-    int32_t check_every;   /* PCG iterations per captured CUDA graph; the host
-                              polls convergence once per graph (0 = auto)      */
+    int32_t check_every;   /* PCG iterations per captured CUDA graph = per residual
+                              check; the host polls once per graph (0 = auto)  */
     int32_t spmv_kernel;   /* 0 auto (= 1), 1 row-thread LDG kernel, 2 TMA-staged */
     int32_t rank;          /* vertex-block partition: this process' rank ...   */
     int32_t world;         /* ... of `world` processes (1 = single GPU)        */

@@ -1,5 +1,6 @@
-// libmbfea.so C ABI (include/mbfea.h): context, device residency, the PCG
-// driver with its CUDA-graph batching, multi-GPU plumbing and the parity taps.
+// libmbfea.so C ABI (include/mbfea.h): context, device residency, the CG driver
+// (CUDA-graph batches, residual verification/replacement, batched small meshes),
+// multi-GPU plumbing (NCCL bootstrap, CUDA-IPC peer memory) and the parity taps.
 // Host code is C++17; all device work is in kernels.cu.  There is no CPU
 // fallback: without a CUDA device every compute entry point fails.
 #include <cuda_runtime.h>
@@ -834,8 +835,6 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         s.n_block_rows = nb; s.n_block_rows_global = c->plan.nb_global;
         s.nnz_blocks = nnzb; s.n_ghost_blocks = ng;
         s.n_components = batched ? (int32_t)(c->plan.comp_ptr.size() - 1) : 0;
-        // algorithmic bytes: SpMV 292/block + 100/row; PCG iteration
-        // adds 10 vector passes (48 B/row each) + the 288 B block-Jacobi inverse
         // algorithmic bytes: the solver SpMV streams 288 B + a 4 B column id per STORED
         // block, 8 B per transposed reference, and per row 48 B x + 48 B y + two 4 B row pointers;
         // a CG iteration adds 9 vector passes of 48 B per row

@@ -1,14 +1,18 @@
 // Hand-written sm_100a kernels of libmbfea.so.
 //
-//   pack_*          input repacking (column-major Eigen images -> 32/64-byte records)
-//   K3 free_map     constraint elimination as a vertex renumbering (flag + scan)
-//   K1 kelem        12x12 element stiffness in global axes (parity tap)
-//   K1+K2 assemble  deterministic scatter-free assembly into 6x6-block BSR
-//   K5 block_jacobi inverse of every diagonal block
-//   K4 spmv_*       y = K x with the p.Ap partial dot in the epilogue
-//                   (row-thread LDG kernel and TMA bulk-copy staged kernel)
-//   K6 pcg_*        fused PCG vector kernels, device-resident scalars
-//   K7 element_forces  beam end forces in the SimulationResults layout
+//   pack_*            input repacking (column-major Eigen images -> 32/64-byte records)
+//   K3 free_map       constraint elimination as a vertex renumbering (flag + scan)
+//   K1 elem_geom      local frame + stiffness coefficients of every beam (kelem: parity tap)
+//   K2 assemble       deterministic scatter-free assembly into 6x6-block BSR
+//   K5 block_chol     block-Jacobi as a symmetric scaling: L_r, S_r = L_r^-1 per diagonal block
+//      scale_blocks   K~ = S K S^T in the solver layout (symmetric-half interleaved / full rows)
+//   K4 spmv_*         y = K~ x with the dot-product partials in the epilogue
+//                     (row-thread kernel <SYM, DOT2>; TMA bulk-copy staged kernel)
+//   K6 cg_*           CG vector kernels on the scaled system, device-resident scalars,
+//                     classic (update/pupdate) and single-reduction (cg2_step) recurrences,
+//                     per-batch residual check, residual replacement, batched one-CTA-per-mesh CG
+//   K7 element_forces beam end forces in the SimulationResults layout; colour-map pre-pass
+//   multi-GPU         NVLink peer-memory mailboxes: halo push, dot all-gather (last-CTA pattern)
 //
 // Everything is FP64; tensor cores are not used (0.25 flop/byte sparse work).
 // Reductions are two-level and fixed-order: per-CTA partials written to a
