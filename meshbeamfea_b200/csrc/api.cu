@@ -820,9 +820,6 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         CK(c->U_cm.alloc((size_t)6 * V));
         CK(c->U_rm.alloc((size_t)6 * V));
         CK(c->F6.alloc((size_t)12 * E));
-        // the contributor lists are only needed on the device from here on
-        c->plan.contrib.clear(); c->plan.contrib.shrink_to_fit();
-        c->plan.contrib_ptr.clear(); c->plan.contrib_ptr.shrink_to_fit();
         lap("matrix/vector allocation");
         upload_forces(c, nF, f_node, f_dof, f_mag);
         CK(cudaStreamSynchronize(c->st));

@@ -266,11 +266,12 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     tr.lap("row sort + count");
     for (int64_t r = 0; r < nb; ++r) P.rowptr[r + 1] = P.rowptr[r] + nblk[r];
     const int64_t nnzb = P.rowptr[nb];
-    P.colidx.assign((size_t)nnzb, 0);
-    P.diag_idx.assign((size_t)nb, 0);
+    // every entry of these is overwritten below: resize (no refill when the size is unchanged)
+    P.colidx.resize((size_t)nnzb);
+    P.diag_idx.resize((size_t)nb);
     std::unique_ptr<int32_t[]> gcol_store(new int32_t[(size_t)nnzb + 1]);  // global column ids first
     int32_t *const gcol = gcol_store.get();
-    if (with_contrib) { P.contrib_ptr.assign((size_t)nnzb + 1, 0); P.contrib.assign((size_t)nent, 0); }
+    if (with_contrib) { P.contrib_ptr.resize((size_t)nnzb + 1); P.contrib.resize((size_t)nent); }
     else { P.contrib_ptr.clear(); P.contrib.clear(); }
     parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
         for (int64_t r = lo; r < hi; ++r) {
@@ -364,16 +365,18 @@ void build_solver_format(HostPlan &P, bool half)
     P.lptr.assign((size_t)nb + 1, 0);
     // pass 1: counts.  (r,c) is stored in row r unless it is a local column below the
     // diagonal under half storage; then it is reached through row c's block (c,r).
-    for (int64_t r = 0; r < nb; ++r) {
-        int32_t nu = 0, nl = 0;
-        for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
-            const int32_t c = P.colidx[k];
-            if (c == r) continue;
-            if (half && c < nb && c < r) ++nl; else ++nu;
+    parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t r = lo; r < hi; ++r) {
+            int32_t nu = 0, nl = 0;
+            for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
+                const int32_t c = P.colidx[k];
+                if (c == r) continue;
+                if (half && c < nb && c < r) ++nl; else ++nu;
+            }
+            P.uptr[r + 1] = nu; P.lptr[r + 1] = nl;   // counts first, prefix sums below
         }
-        P.uptr[r + 1] = P.uptr[r] + nu;
-        P.lptr[r + 1] = P.lptr[r] + nl;
-    }
+    });
+    for (int64_t r = 0; r < nb; ++r) { P.uptr[r + 1] += P.uptr[r]; P.lptr[r + 1] += P.lptr[r]; }
     P.ucol.resize((size_t)P.uptr[nb]);
     P.usrc.resize((size_t)P.uptr[nb]);
     P.lcol.resize((size_t)P.lptr[nb]);
