@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-alt-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -327,11 +328,28 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "BSR 6x6 FP64 SpMV (k_spmv_*)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "BSR 6x6 FP64 SpMV, production format (symmetric-half interleaved unless a batch): k_spmv_rowthread",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
                 "traffic": traffic, "algorithmic_bytes_per_launch": st["bytes_spmv"], "ms_per_launch": ms_spmv,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---- the same SpMV family on the full-row format (every block in its own row): more bytes, higher
+    #      fraction of peak, slower in wall time -- reported beside the production format for context ----
+    roofline_alt = None
+    if world == 1 and rank == 0 and not args.no_alt_roofline:
+        alt = mb.Context(device=local, tol=args.tol, storage=1)
+        alt.set_job_raw(V, E, A["nodes_cm"], A["elems_cm"], A["normals_cm"], A["dims"], A["mat"], A["fixed"],
+                        A["fn"], A["fd"], A["fm"])
+        if alt.stats()["n_components"] == 0:
+            alt.assemble()
+            ms_alt = alt.time_spmv(kernel=1, warmup=3, reps=50)
+            b_alt = alt.stats()["bytes_spmv"]
+            roofline_alt = {"format": "full rows (storage=1), k_spmv_rowthread<false>", "achieved": b_alt / (ms_alt * 1e-3) / 1e9,
+                            "peak": peak, "unit": "GB/s", "frac": b_alt / (ms_alt * 1e-3) / 1e9 / peak,
+                            "algorithmic_bytes_per_launch": b_alt, "ms_per_launch": ms_alt}
+        alt.close()
 
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
@@ -374,7 +392,8 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-               "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+               "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_full_row_format": roofline_alt,
+               "cpu_baseline": cpu,
                "pcg_iterations": int(st["iterations"]), "rel_residual": st["rel_residual"],
                "true_rel_residual": st["true_rel_residual"], "converged": bool(st["converged"]),
                "time_to_solve_s": st["ms_pcg"] / 1e3, "device_ms_per_step": dev_ms / args.steps,
