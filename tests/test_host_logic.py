@@ -291,3 +291,17 @@ def test_cpp_dropin_header_builds_and_fails_loudly_without_gpu(built):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode != 0
     assert "no usable CUDA device" in (r.stderr + r.stdout)
+
+
+def test_bench_reference_arm_runs_on_cpu(built):
+    """bench.py --impl reference: the CPU oracle timed on this host, one JSON line with the contract keys."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "lattice8",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "beams/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"] == "lattice8"
