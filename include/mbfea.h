@@ -86,7 +86,10 @@ typedef struct mbfea_options {
                               (connected components with contiguous vertex ranges, each
                               <= 1024 free vertices) is solved one CTA per mesh, each
                               with its own iteration count: 0 auto, 1 never            */
-    int32_t reserved[3];
+    int32_t reorder;       /* internal breadth-first renumbering of the reduced system (results
+                              and taps stay in vertex / canonical numbering): 0 auto (only when
+                              the input vertex order has no locality), 1 never, 2 always       */
+    int32_t reserved[2];
 } mbfea_options;
 
 typedef struct mbfea_stats {
@@ -196,13 +199,15 @@ int mbfea_get_kelem(mbfea_ctx *ctx, double *Ke /* E x 12 x 12 row-major */);
 int mbfea_get_bsr_sizes(mbfea_ctx *ctx, int64_t *n_block_rows, int64_t *nnz_blocks,
                         int64_t *row_offset /* first global block row owned */,
                         int64_t *n_ghost);
-/* local BSR of this rank: rowptr nb+1, colidx nnzb (LOCAL column ids: owned
- * [0,nb) then ghosts), vals nnzb x 36 row-major 6x6; ghost_global n_ghost
- * global block-row ids of the ghost columns.  Any pointer may be NULL.       */
+/* The block rows this rank owns, in CANONICAL reduced numbering (rank of the vertex among the
+ * free vertices, what the reference / oracle use) whatever the internal renumbering: rows in
+ * ascending canonical id (row_ids[nb]), rowptr nb+1, colidx nnzb GLOBAL canonical column ids,
+ * ascending within a row, vals nnzb x 36 row-major 6x6.  Any pointer may be NULL.
+ * On a single rank row_ids is 0..nb-1 and this is the reduced matrix of the whole job.   */
 int mbfea_get_bsr(mbfea_ctx *ctx, int64_t *rowptr, int32_t *colidx, double *vals,
-                  int64_t *ghost_global);
-int mbfea_get_load(mbfea_ctx *ctx, double *f_reduced /* 6*nb, owned rows */);
-/* y = K x on the owned rows, single-rank contexts only: x,y 6*nb doubles (host) */
+                  int64_t *row_ids);
+int mbfea_get_load(mbfea_ctx *ctx, double *f_reduced /* 6*nb, owned rows, same row order */);
+/* y = K x, single-rank contexts only: x,y 6*nb doubles (host), canonical numbering */
 int mbfea_spmv(mbfea_ctx *ctx, const double *x, double *y);
 /* same, with an explicit kernel choice (1 row-thread, 2 TMA-staged) */
 int mbfea_spmv_with(mbfea_ctx *ctx, int32_t kernel, const double *x, double *y);
@@ -277,6 +282,11 @@ int mbfea_host_validate(int64_t V, int64_t E, const int32_t *elems_cm, const flo
 int mbfea_host_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4);
 int mbfea_host_free_map(int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
                         int64_t *n_free);
+/* renumber: the internal breadth-first renumbering set_job would use (mode as options.reorder:
+ *           0 auto, 1 never, 2 always).  perm[n_free]: canonical reduced id -> internal block row
+ *           (identity when the canonical order is kept); *reordered says which.                */
+int mbfea_host_renumber(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
+                        int32_t mode, int32_t *perm, int32_t *reordered);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -23,7 +23,8 @@ class Options(C.Structure):
         ("device", C.c_int32), ("verbose", C.c_int32), ("tol", C.c_double), ("max_iter", C.c_int64),
         ("check_every", C.c_int32), ("spmv_kernel", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("use_graph", C.c_int32), ("comm_mode", C.c_int32), ("storage", C.c_int32),
-        ("cg_variant", C.c_int32), ("batch_mode", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("cg_variant", C.c_int32), ("batch_mode", C.c_int32), ("reorder", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -108,6 +109,7 @@ SIGNATURES = {
     "mbfea_host_validate": (C.c_int, [_i64, _i64, _pi32, _pf, _pf, _i64, _pi32, _i64, _pi64, _pi64, C.c_char_p, _i64]),
     "mbfea_host_props": (C.c_int, [_i64, _pf, _pf, _pd]),
     "mbfea_host_free_map": (C.c_int, [_i64, _i64, _pi32, _pi32, _pi64]),
+    "mbfea_host_renumber": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _pi32, _pi32]),
 }
 
 

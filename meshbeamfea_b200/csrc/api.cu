@@ -96,7 +96,7 @@ struct mbfea_ctx {
     DevBuf<Node4> node4;
     DevBuf<ElemRec> rec;
     DevBuf<ElemGeom> geom;
-    DevBuf<int32_t> free_index, fixed;
+    DevBuf<int32_t> free_index, free_canon, fixed;   // free_canon: the K3 scan (canonical); free_index: composed with the internal renumbering
     // staging for set_job (kept: a re-submitted mesh of the same size costs no cudaMalloc/cudaFree)
     DevBuf<double> stg_nodes, stg_normals, stg_props;
     DevBuf<int32_t> stg_elems, stg_scratch;
@@ -731,7 +731,9 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         c->V = V; c->E = E; c->F = F;
         c->props_host.resize((size_t)4 * E);
         derive_props(E, dims_bh, mat_nuE, c->props_host.data());
-        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan);
+        // internal renumbering: 0 auto (only when the input vertex order has no locality), 1 never, 2 always
+        const int reorder = c->opt.reorder == 1 ? 0 : (c->opt.reorder == 2 ? 2 : 1);
+        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan, reorder);
         // solver format: symmetric-half storage unless full rows are asked for (the TMA kernel
         // streams whole rows and has no transposed-reference path)
         if (c->opt.batch_mode != 1) find_components(c->plan, 1024, 32);
@@ -771,10 +773,19 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             CK(c->rec.alloc((size_t)E));
             CK(c->geom.alloc((size_t)E));
             CK(c->free_index.alloc((size_t)V));
+            CK(c->free_canon.alloc((size_t)V));
             CK(d_scratch.alloc((size_t)V + (size_t)V / 1024 + 2));
             launch_pack_nodes(c->st, V, d_nodes.p, c->node4.p);
             launch_pack_elems(c->st, E, d_elems.p, d_normals.p, d_props.p, c->rec.p);
-            launch_free_map(c->st, V, F, c->fixed.p, c->free_index.p, d_scratch.p);  // K3
+            launch_free_map(c->st, V, F, c->fixed.p, c->free_canon.p, d_scratch.p);  // K3 (canonical map)
+            if (c->plan.perm.empty()) {
+                CK(cudaMemcpyAsync(c->free_index.p, c->free_canon.p, (size_t)V * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->st));
+            } else {
+                DevBuf<int32_t> d_perm;
+                upload(c, d_perm, c->plan.perm);
+                launch_apply_perm(c->st, V, c->free_canon.p, d_perm.p, c->free_index.p);
+                CK(cudaStreamSynchronize(c->st));
+            }
             CK(cudaStreamSynchronize(c->st));
             lap("mesh upload + pack + K3");
         }
@@ -1312,7 +1323,7 @@ int mbfea_get_dofmap(mbfea_ctx *c, int32_t *free_index)
     if (!free_index) return fail(c, MBFEA_EARG, "NULL");
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
-        CK(cudaMemcpyAsync(free_index, c->free_index.p, (size_t)c->V * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(free_index, c->free_canon.p, (size_t)c->V * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         return MBFEA_OK;
     });
@@ -1343,23 +1354,60 @@ int mbfea_get_bsr_sizes(mbfea_ctx *c, int64_t *nbr, int64_t *nnzb, int64_t *row_
     return MBFEA_OK;
 }
 
-int mbfea_get_bsr(mbfea_ctx *c, int64_t *rowptr, int32_t *colidx, double *vals, int64_t *ghost_global)
+// canonical reduced id of an internal global row / of a local column id
+static inline int64_t canon_of(const mbfea_ctx *c, int64_t internal_global)
+{
+    return c->plan.inv.empty() ? internal_global : (int64_t)c->plan.inv[(size_t)internal_global];
+}
+
+// owned rows in ascending canonical order: order[j] = local row
+static std::vector<int32_t> canonical_row_order(const mbfea_ctx *c)
+{
+    const int64_t nb = c->nb();
+    std::vector<int32_t> order((size_t)nb);
+    for (int64_t r = 0; r < nb; ++r) order[(size_t)r] = (int32_t)r;
+    if (!c->plan.inv.empty())
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            return c->plan.inv[(size_t)(c->plan.row_begin + a)] < c->plan.inv[(size_t)(c->plan.row_begin + b)];
+        });
+    return order;
+}
+
+int mbfea_get_bsr(mbfea_ctx *c, int64_t *rowptr, int32_t *colidx, double *vals, int64_t *row_ids)
 {
     if (int rc = need_job(c)) return rc;
     if (vals && !c->assembled) return fail(c, MBFEA_ESTATE, "values requested before assemble");
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
-        const int64_t nb = c->nb(), nnzb = c->plan.nnzb();
-        if (rowptr) {
-            std::vector<int32_t> rp((size_t)nb + 1);
-            CK(cudaMemcpyAsync(rp.data(), c->rowptr.p, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+        const int64_t nb = c->nb(), nnzb = c->plan.nnzb(), r0 = c->plan.row_begin;
+        const std::vector<int32_t> &rp = c->plan.rowptr, &ci = c->plan.colidx;
+        std::vector<double> v;
+        if (vals) {
+            v.resize((size_t)nnzb * 36);
+            CK(cudaMemcpyAsync(v.data(), c->vals.p, v.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
             CK(cudaStreamSynchronize(c->st));
-            for (int64_t i = 0; i <= nb; ++i) rowptr[i] = rp[(size_t)i];
         }
-        if (colidx) CK(cudaMemcpyAsync(colidx, c->colidx.p, (size_t)nnzb * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
-        if (vals) CK(cudaMemcpyAsync(vals, c->vals.p, (size_t)nnzb * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        if (ghost_global) std::copy(c->plan.ghost_global.begin(), c->plan.ghost_global.end(), ghost_global);
+        const std::vector<int32_t> order = canonical_row_order(c);
+        int64_t out = 0;
+        std::vector<std::pair<int64_t, int32_t>> cols;   // (canonical column, position)
+        for (int64_t j = 0; j < nb; ++j) {
+            const int32_t r = order[(size_t)j];
+            if (rowptr) rowptr[j] = out;
+            if (row_ids) row_ids[j] = canon_of(c, r0 + r);
+            cols.clear();
+            for (int32_t k = rp[(size_t)r]; k < rp[(size_t)r + 1]; ++k) {
+                const int32_t lc = ci[(size_t)k];
+                const int64_t g = lc < nb ? r0 + lc : c->plan.ghost_global[(size_t)(lc - nb)];
+                cols.emplace_back(canon_of(c, g), k);
+            }
+            std::sort(cols.begin(), cols.end());
+            for (const auto &pc : cols) {
+                if (colidx) colidx[out] = (int32_t)pc.first;
+                if (vals) std::memcpy(vals + out * 36, v.data() + (size_t)pc.second * 36, 36 * sizeof(double));
+                ++out;
+            }
+        }
+        if (rowptr) rowptr[nb] = out;
         return MBFEA_OK;
     });
 }
@@ -1370,8 +1418,12 @@ int mbfea_get_load(mbfea_ctx *c, double *f_reduced)
     if (!f_reduced) return fail(c, MBFEA_EARG, "NULL");
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
-        CK(cudaMemcpyAsync(f_reduced, c->f.p, (size_t)6 * c->nb() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        const int64_t nb = c->nb();
+        std::vector<double> f((size_t)6 * nb);
+        CK(cudaMemcpyAsync(f.data(), c->f.p, f.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
+        const std::vector<int32_t> order = canonical_row_order(c);
+        for (int64_t j = 0; j < nb; ++j) std::memcpy(f_reduced + 6 * j, f.data() + 6 * (size_t)order[(size_t)j], 6 * sizeof(double));
         return MBFEA_OK;
     });
 }
@@ -1385,11 +1437,22 @@ int mbfea_spmv_with(mbfea_ctx *c, int32_t kernel, const double *x, double *y)
     if (kernel == 2 && !c->tma_ok) return fail(c, MBFEA_EARG, "pattern has a row longer than a TMA stage");
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
-        const size_t n = (size_t)6 * c->nb() * sizeof(double);
-        CK(cudaMemcpyAsync(c->p.p, x, n, cudaMemcpyHostToDevice, c->st));
+        const int64_t nb = c->nb();
+        const size_t n = (size_t)6 * nb * sizeof(double);
+        // x and y are in canonical reduced numbering; the device works on the internal one
+        std::vector<double> xi, yi;
+        const double *src = x;
+        if (!c->plan.perm.empty()) {
+            xi.resize((size_t)6 * nb); yi.resize((size_t)6 * nb);
+            for (int64_t i = 0; i < nb; ++i) std::memcpy(xi.data() + 6 * (size_t)c->plan.perm[(size_t)i], x + 6 * i, 6 * sizeof(double));
+            src = xi.data();
+        }
+        CK(cudaMemcpyAsync(c->p.p, src, n, cudaMemcpyHostToDevice, c->st));
         run_spmv_full(c, pick_spmv(c, kernel), c->p.p, c->Ap.p);
-        CK(cudaMemcpyAsync(y, c->Ap.p, n, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(c->plan.perm.empty() ? y : yi.data(), c->Ap.p, n, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
+        if (!c->plan.perm.empty())
+            for (int64_t i = 0; i < nb; ++i) std::memcpy(y + 6 * i, yi.data() + 6 * (size_t)c->plan.perm[(size_t)i], 6 * sizeof(double));
         c->solved = c->recovered = false;  // p / Ap were overwritten
         return MBFEA_OK;
     });
@@ -1583,6 +1646,25 @@ int mbfea_host_free_map(int64_t V, int64_t F, const int32_t *fixed, int32_t *fre
     const int64_t n = build_free_map(V, F, fixed, fm);
     std::copy(fm.begin(), fm.end(), free_index);
     if (n_free) *n_free = n;
+    return MBFEA_OK;
+}
+
+int mbfea_host_renumber(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed, int32_t mode,
+                        int32_t *perm, int32_t *reordered)
+{
+    if (V <= 0 || E <= 0 || !elems_cm || !perm || (F > 0 && !fixed)) return MBFEA_EARG;
+    for (int64_t e = 0; e < 2 * E; ++e)
+        if (elems_cm[e] < 0 || elems_cm[e] >= V) return MBFEA_EPRECOND;
+    for (int64_t i = 0; i < F; ++i)
+        if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
+    HostPlan P;
+    try {
+        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, P, mode == 1 ? 0 : (mode == 2 ? 2 : 1));
+    } catch (const std::bad_alloc &) {
+        return MBFEA_EARG;
+    }
+    if (reordered) *reordered = P.perm.empty() ? 0 : 1;
+    for (int64_t i = 0; i < P.nb_global; ++i) perm[i] = P.perm.empty() ? (int32_t)i : P.perm[(size_t)i];
     return MBFEA_OK;
 }
 

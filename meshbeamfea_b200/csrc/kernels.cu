@@ -289,6 +289,22 @@ __global__ void k_scan_finish(int64_t V, int32_t *free_index, const int32_t *__r
     free_index[v] = flag_keep[v] ? free_index[v] + tile_sum[v / kScanTile] : -1;
 }
 
+// free_index[v] = perm[canonical rank] (internal block row), -1 stays -1
+__global__ void k_apply_perm(int64_t V, const int32_t *__restrict__ canon, const int32_t *__restrict__ perm,
+                             int32_t *__restrict__ out)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int32_t c = canon[v];
+    out[v] = c >= 0 ? __ldg(perm + c) : -1;
+}
+
+void launch_apply_perm(cudaStream_t st, int64_t V, const int32_t *canon, const int32_t *perm, int32_t *out)
+{
+    if (V <= 0) return;
+    k_apply_perm<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, canon, perm, out);
+}
+
 void launch_free_map(cudaStream_t st, int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
                      int32_t *scratch)
 {

@@ -73,6 +73,8 @@ void launch_pack_elems(cudaStream_t st, int64_t E, const int32_t *elems_cm, cons
 // K3: device constraint map (flags -> exclusive scan)
 void launch_free_map(cudaStream_t st, int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
                      int32_t *scratch /* >= V + V/1024 + 1 ints */);
+// composes the canonical map with the internal renumbering of the reduced system
+void launch_apply_perm(cudaStream_t st, int64_t V, const int32_t *canon, const int32_t *perm, int32_t *out);
 // K1: E x 12 x 12 element matrices (parity tap)
 void launch_kelem(cudaStream_t st, int64_t E, const ElemRec *rec, const Node4 *node4, double *Ke);
 // K1: frame + stiffness coefficients of every beam -> ElemGeom records

@@ -25,7 +25,13 @@ struct HostPlan {
     int32_t rank = 0, world = 1;
     int64_t nb_global = 0;            // free vertices
     int64_t row_begin = 0, row_end = 0;
-    std::vector<int32_t> free_index;  // V, -1 fixed  (K3 map, host copy)
+    std::vector<int32_t> free_index;  // V, -1 fixed: INTERNAL block row of each vertex (K3 map composed with perm)
+    // Internal renumbering of the reduced system (empty = identity).  The K3 map ranks free vertices
+    // in vertex order ("canonical" reduced numbering, what the oracle and the reference use); when
+    // that numbering has no locality (vertex ids in arbitrary order) the solver works on a breadth-
+    // first renumbering instead: perm[canonical] = internal row, inv[internal] = canonical.  Purely
+    // internal: every tap and result is reported in canonical / vertex numbering.
+    std::vector<int32_t> perm, inv;
     std::vector<int32_t> rowptr;      // nb+1
     std::vector<int32_t> colidx;      // nnzb, LOCAL ids: owned [0,nb), ghosts after
     std::vector<int32_t> diag_idx;    // nb: position of the diagonal block
@@ -77,8 +83,9 @@ int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<i
 
 // Block pattern, contributor lists, halo plan for `rank` of `world`.
 // with_contrib=false skips the contributor lists (plan-only callers).
+// reorder: 0 never, 1 when the canonical numbering has poor locality (auto), 2 always
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
-                int32_t rank, int32_t world, bool with_contrib, HostPlan &plan);
+                int32_t rank, int32_t world, bool with_contrib, HostPlan &plan, int reorder = 0);
 
 // Solver format from the full pattern (see HostPlan::uptr).  half=false keeps every
 // off-diagonal block in its own row (no transposed references).

@@ -141,7 +141,7 @@ class Context:
     """One ``mbfea_ctx``: device buffers, stream, PCG graph, optional NCCL comm."""
 
     def __init__(self, device: int = -1, tol: float = 1e-8, max_iter: int = 0, verbose: bool = False,
-                 spmv_kernel: int = 0, check_every: int = 0, use_graph: bool = True, comm_mode: int = 0, storage: int = 0, cg_variant: int = 0, batch_mode: int = 0):
+                 spmv_kernel: int = 0, check_every: int = 0, use_graph: bool = True, comm_mode: int = 0, storage: int = 0, cg_variant: int = 0, batch_mode: int = 0, reorder: int = 0):
         self._lib = L.lib()
         o = Options()
         self._lib.mbfea_options_default(C.byref(o))
@@ -151,6 +151,7 @@ class Context:
         o.storage = storage
         o.cg_variant = cg_variant
         o.batch_mode = batch_mode
+        o.reorder = reorder
         self._h = C.c_void_p()
         rc = self._lib.mbfea_create(C.byref(self._h), C.byref(o))
         if rc != L.OK:
@@ -312,13 +313,15 @@ class Context:
         return a.value, b.value, c.value, d.value
 
     def bsr(self, values: bool = True):
+        """(rowptr, colidx, vals, row_ids): the owned block rows in canonical reduced numbering
+        (ascending row_ids; global canonical column ids).  On one rank row_ids == arange(nb)."""
         nb, nnzb, row0, ng = self.bsr_sizes()
         rowptr = np.empty(nb + 1, np.int64)
         col = np.empty(max(nnzb, 1), np.int32)
         vals = np.empty((max(nnzb, 1), 6, 6), np.float64) if values else None
-        ghosts = np.empty(max(ng, 1), np.int64)
-        self._ck(self._lib.mbfea_get_bsr(self._h, ptr(rowptr, _pi64), ptr(col, _pi32), ptr(vals, _pd), ptr(ghosts, _pi64)))
-        return rowptr, col[:nnzb], (vals[:nnzb] if values else None), ghosts[:ng]
+        rows = np.empty(max(nb, 1), np.int64)
+        self._ck(self._lib.mbfea_get_bsr(self._h, ptr(rowptr, _pi64), ptr(col, _pi32), ptr(vals, _pd), ptr(rows, _pi64)))
+        return rowptr, col[:nnzb], (vals[:nnzb] if values else None), rows[:nb]
 
     def load(self) -> np.ndarray:
         nb = self.bsr_sizes()[0]
@@ -381,6 +384,22 @@ def plan_partition(V: int, elements: np.ndarray, fixed: np.ndarray, rank: int, w
                 colidx=col[:sz.nnz_blocks], ghost_global=gg[:sz.n_ghost], ghost_owner=go[:sz.n_ghost],
                 send_rows=sr[:sz.n_send], send_dest=sd[:sz.n_send], n_neighbors=sz.n_neighbors,
                 n_components=sz.n_components, max_component_rows=sz.max_component_rows)
+
+
+def host_renumber(V: int, elements: np.ndarray, fixed: np.ndarray, mode: int = 0):
+    """The internal breadth-first renumbering set_job would use (host only): (perm, reordered)."""
+    lib = L.lib()
+    elements = np.asarray(elements, np.int32).reshape(-1, 2)
+    elems_cm = np.ascontiguousarray(elements.T).ravel()
+    fixed = np.ascontiguousarray(np.asarray(fixed, np.int32).ravel())
+    n_free = V - np.unique(fixed).size
+    perm = np.empty(max(n_free, 1), np.int32)
+    flag = C.c_int32()
+    rc = lib.mbfea_host_renumber(V, elements.shape[0], ptr(elems_cm, _pi32), fixed.size, ptr(fixed, _pi32), mode,
+                                 ptr(perm, _pi32), C.byref(flag))
+    if rc != L.OK:
+        _raise(rc, lib.mbfea_status_string(rc).decode())
+    return perm[:n_free], bool(flag.value)
 
 
 def read_scenario(config_json: str, ply_override: Optional[str] = None):

@@ -78,8 +78,8 @@ def test_stage_by_stage_parity(built, name):
         assert np.array_equal(Kg, Ke)                      # bit-identical (same IEEE operation order)
         # K2 pattern + values
         c.assemble()
-        rp2, col2, vals2, ghosts = c.bsr()
-        assert np.array_equal(rp2, rp) and np.array_equal(col2, col) and ghosts.size == 0
+        rp2, col2, vals2, rows = c.bsr()
+        assert np.array_equal(rp2, rp) and np.array_equal(col2, col) and np.array_equal(rows, np.arange(rp.size - 1))
         assert block_rel(vals2, vals) <= TOL_K
         assert np.array_equal(vals2, vals)                 # deterministic element-order sums
         # load vector of the reduced system
@@ -115,6 +115,41 @@ def test_every_solver_format_and_kernel_gives_the_same_solution(built, storage, 
         with ctx_for(job, spmv_kernel=kernel, storage=storage, cg_variant=variant) as c:
             c.execute()
             assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
+
+
+@pytest.mark.parametrize("reorder", [0, 2], ids=["auto", "always"])
+def test_arbitrary_vertex_numbering(built, reorder):
+    """Vertex ids in random order: the solver renumbers internally (breadth-first) but every tap and
+    result stays in the reference's numbering -- constraint map, pattern and K values bit-exact,
+    displacements and forces within the parity bar, equal to the well-numbered mesh un-shuffled."""
+    base = syn.cubic_lattice(11)
+    V = base.nodes.shape[0]
+    vperm = np.random.default_rng(5).permutation(V)
+    inv = np.argsort(vperm)
+    fn, fd, fm_ = base.nodalForces
+    job = mb.SimulationJob(base.nodes[inv], vperm[base.elements].astype(np.int32), base.elementalNormals,
+                           vperm[base.fixedNodes].astype(np.int32), (vperm[fn], fd, fm_), base.beamDimensions,
+                           base.beamMaterial)
+    O = to_oracle(job)
+    props, fm, rp, col, vals = oracle_bsr(O)
+    with ctx_for(job, reorder=reorder) as c:
+        assert np.array_equal(c.dofmap(), fm)
+        c.assemble()
+        rp2, col2, vals2, rows = c.bsr()
+        assert np.array_equal(rp2, rp) and np.array_equal(col2, col) and np.array_equal(rows, np.arange(rp.size - 1))
+        assert np.array_equal(vals2, vals)
+        f = orc.load_vector(V, O.forces)
+        free_dofs = (6 * np.nonzero(fm >= 0)[0][:, None] + np.arange(6)[None, :]).ravel()
+        assert np.array_equal(c.load(), f[free_dofs])
+        x = np.random.default_rng(0).standard_normal(free_dofs.size)
+        assert rel_l2(c.spmv(x, kernel=1), oracle_spmv(rp, col, vals, x)) < 1e-14
+        c.execute()
+        U, F = orc.solve(O)
+        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
+        Ushuf = c.displacements()
+    with ctx_for(base) as c:
+        c.execute()
+        assert rel_l2(Ushuf[vperm], c.displacements()) < 1e-9     # same physical solution
 
 
 def test_reference_fixture_and_screenshot_golden(built):

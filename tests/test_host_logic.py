@@ -176,6 +176,47 @@ def test_batch_detection(built):
     assert mb.plan_partition(two.nodes.shape[0], el, fx, 0, 1)["n_components"] == 39   # meshes 0 and 1 merge into one range
 
 
+def _shuffle_vertices(job, seed):
+    V = job.nodes.shape[0]
+    perm = np.random.default_rng(seed).permutation(V)      # new id of old vertex v
+    inv = np.argsort(perm)
+    fn, fd, fm = job.nodalForces
+    return mb.SimulationJob(job.nodes[inv], perm[job.elements].astype(np.int32), job.elementalNormals,
+                            perm[job.fixedNodes].astype(np.int32), (perm[fn], fd, fm), job.beamDimensions,
+                            job.beamMaterial)
+
+
+def test_internal_renumbering(built):
+    """A mesh whose vertex ids are in arbitrary order gets a breadth-first internal numbering
+    (neighbouring rows close together); a mesh that already has locality keeps its order."""
+    lat = syn.cubic_lattice(40)      # 62 400 block rows: more than the ~16 MB locality window of the heuristic
+    V = lat.nodes.shape[0]
+    perm, reordered = mb.host_renumber(V, lat.elements, lat.fixedNodes, 0)
+    assert not reordered and np.array_equal(perm, np.arange(perm.size))
+    shuf = _shuffle_vertices(lat, 3)
+    perm, reordered = mb.host_renumber(V, shuf.elements, shuf.fixedNodes, 0)
+    assert reordered and np.array_equal(np.sort(perm), np.arange(perm.size))        # a permutation
+    fm = orc.free_map(V, shuf.fixedNodes)
+    a, b = fm[shuf.elements[:, 0]], fm[shuf.elements[:, 1]]
+    both = (a >= 0) & (b >= 0)
+    span_before = np.abs(a[both] - b[both]).mean()
+    span_after = np.abs(perm[a[both]] - perm[b[both]]).mean()
+    assert span_after < 0.2 * span_before and span_after < 3 * 40 * 40            # ~ one BFS level
+    small = _shuffle_vertices(syn.cubic_lattice(10), 4)                              # L2-resident anyway: left alone
+    assert not mb.host_renumber(1000, small.elements, small.fixedNodes, 0)[1]
+    assert not mb.host_renumber(V, shuf.elements, shuf.fixedNodes, 1)[1]           # never
+    assert mb.host_renumber(V, lat.elements, lat.fixedNodes, 2)[1]                # always
+    # a batch of independent meshes stays a sequence of contiguous row ranges after renumbering
+    jobs = [syn.random_mesh(700 + m, V=30) for m in range(12)]
+    merged = syn.merge_jobs(jobs)
+    perm, reordered = mb.host_renumber(merged.nodes.shape[0], merged.elements, merged.fixedNodes, 2)
+    assert reordered
+    fm = orc.free_map(merged.nodes.shape[0], merged.fixedNodes)
+    owner = np.repeat(np.arange(12), 30)[fm >= 0]          # mesh of each canonical free row
+    by_internal = owner[np.argsort(perm)]
+    assert np.all(np.diff(by_internal) >= 0)
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_partition_plan_is_consistent(built, world):
     job = syn.cubic_lattice(7)
