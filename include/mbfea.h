@@ -88,7 +88,9 @@ typedef struct mbfea_options {
                               with its own iteration count: 0 auto, 1 never            */
     int32_t reorder;       /* internal breadth-first renumbering of the reduced system (results
                               and taps stay in vertex / canonical numbering): 0 auto (only when
-                              the input vertex order has no locality), 1 never, 2 always       */
+                              the input vertex order has no locality), 1 never, 2 always,
+                              3 Morton (Z-order) numbering from the vertex coordinates: 32-row
+                              tiles become compact bricks of the mesh                          */
     int32_t reserved[2];
 } mbfea_options;
 

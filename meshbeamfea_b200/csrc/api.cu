@@ -732,8 +732,8 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         c->props_host.resize((size_t)4 * E);
         derive_props(E, dims_bh, mat_nuE, c->props_host.data());
         // internal renumbering: 0 auto (only when the input vertex order has no locality), 1 never, 2 always
-        const int reorder = c->opt.reorder == 1 ? 0 : (c->opt.reorder == 2 ? 2 : 1);
-        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan, reorder);
+        const int reorder = c->opt.reorder == 1 ? 0 : (c->opt.reorder == 2 ? 2 : (c->opt.reorder == 3 ? 3 : 1));
+        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan, reorder, nodes_cm);
         // solver format: symmetric-half storage unless full rows are asked for (the TMA kernel
         // streams whole rows and has no transposed-reference path)
         if (c->opt.batch_mode != 1) find_components(c->plan, 1024, 32);
@@ -1112,7 +1112,7 @@ int mbfea_solve(mbfea_ctx *c)
         if (c->opt.verbose)
             std::fprintf(stderr, "[mbfea] rank %d: CG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d (%s storage), batch %d\n",
                          c->opt.rank, (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel,
-                         c->plan.sym_half ? "symmetric-half" : "full-row", check);
+                         c->plan.sym_half ? (c->plan.balanced ? "symmetric-half, balanced" : "symmetric-half") : "full-row", check);
         if (c->opt.verbose && restarts)
             std::fprintf(stderr, "[mbfea] rank %d: %d residual replacement(s)\n", c->opt.rank, restarts);
         if (c->p2p && peer_timeout_flag())
@@ -1659,7 +1659,7 @@ int mbfea_host_renumber(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F
         if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
     HostPlan P;
     try {
-        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, P, mode == 1 ? 0 : (mode == 2 ? 2 : 1));
+        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, P, mode == 1 ? 0 : (mode == 2 ? 2 : (mode == 3 ? 3 : 1)));
     } catch (const std::bad_alloc &) {
         return MBFEA_EARG;
     }

@@ -190,23 +190,82 @@ struct PrepTrace {
 // x-gathers land in recently streamed (L2-resident) memory whatever the input vertex ids were.
 // Components are exhausted one after the other, so a batch of independent meshes stays a sequence
 // of contiguous row ranges.  Returns false (perm left empty) when the canonical order is kept.
+// Morton (Z-order) renumbering from the vertex coordinates: consecutive 32 rows form a compact brick
+// of the mesh, so both rows of most pairs share an SpMV tile (the pair's second use hits L1) while
+// the curve keeps the remaining neighbours within L2 reach.  10 bits per axis, LSD radix sort.
+static void morton_renumber(int64_t V, const double *nodes_cm, const std::vector<int32_t> &fc, int64_t nbg,
+                            std::vector<int32_t> &perm, std::vector<int32_t> &inv)
+{
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+    for (int64_t v = 0; v < V; ++v)
+        if (fc[v] >= 0)
+            for (int a = 0; a < 3; ++a) {
+                const double x = nodes_cm[(size_t)a * V + v];
+                lo[a] = std::min(lo[a], x); hi[a] = std::max(hi[a], x);
+            }
+    const double span = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-300));
+    auto spread = [](uint32_t x) {   // 10 bits -> every third bit
+        x &= 0x3ffu;
+        x = (x | (x << 16)) & 0x030000ffu;
+        x = (x | (x << 8)) & 0x0300f00fu;
+        x = (x | (x << 4)) & 0x030c30c3u;
+        x = (x | (x << 2)) & 0x09249249u;
+        return x;
+    };
+    std::vector<uint32_t> key((size_t)nbg), key2((size_t)nbg);
+    std::vector<int32_t> id((size_t)nbg), id2((size_t)nbg);
+    for (int64_t v = 0; v < V; ++v) {
+        const int32_t c = fc[v];
+        if (c < 0) continue;
+        uint32_t k = 0;
+        for (int a = 0; a < 3; ++a) {
+            const double t = (nodes_cm[(size_t)a * V + v] - lo[a]) / span;
+            const uint32_t q = (uint32_t)std::min(1023.0, std::max(0.0, t * 1023.0 + 0.5));
+            k |= spread(q) << a;
+        }
+        key[(size_t)c] = k; id[(size_t)c] = c;
+    }
+    for (int pass = 0; pass < 4; ++pass) {   // stable LSD radix sort, 8 bits per pass
+        const int sh = 8 * pass;
+        size_t cnt[257] = {0};
+        for (int64_t i = 0; i < nbg; ++i) cnt[((key[(size_t)i] >> sh) & 0xff) + 1]++;
+        for (int b = 0; b < 256; ++b) cnt[b + 1] += cnt[b];
+        for (int64_t i = 0; i < nbg; ++i) {
+            const size_t d = cnt[(key[(size_t)i] >> sh) & 0xff]++;
+            key2[d] = key[(size_t)i]; id2[d] = id[(size_t)i];
+        }
+        key.swap(key2); id.swap(id2);
+    }
+    perm.resize((size_t)nbg); inv.resize((size_t)nbg);
+    for (int64_t i = 0; i < nbg; ++i) { inv[(size_t)i] = id[(size_t)i]; perm[(size_t)id[(size_t)i]] = (int32_t)i; }
+}
+
 static bool bfs_renumber(int64_t V, int64_t E, const int32_t *elems_cm, const std::vector<int32_t> &fc, int64_t nbg,
-                         int mode, std::vector<int32_t> &perm, std::vector<int32_t> &inv)
+                         int mode, const double *nodes_cm, std::vector<int32_t> &perm, std::vector<int32_t> &inv)
 {
     perm.clear(); inv.clear();
     if (mode == 0 || nbg < 2) return false;
+    if (mode == 3 && nodes_cm != nullptr) { morton_renumber(V, nodes_cm, fc, nbg, perm, inv); return true; }
+    if (mode == 3) mode = 2;
     if (mode == 1) {
-        // locality of the canonical numbering: share of beams whose two rows are further apart than
-        // ~16 MB of the value stream (~900 B per row)
+        // locality of a numbering: share of beams whose two rows are further apart than ~16 MB of
+        // the value stream (~900 B per row)
         const int64_t window = std::max<int64_t>(4096, (int64_t)(16e6 / 900.0));
-        int64_t far = 0, tot = 0;
-        for (int64_t e = 0; e < E; ++e) {
-            const int32_t a = fc[elems_cm[e]], b = fc[elems_cm[E + e]];
-            if (a < 0 || b < 0) continue;
-            ++tot;
-            far += std::llabs((long long)a - (long long)b) > window;
-        }
-        if (tot == 0 || far * 20 < tot) return false;   // < 5 % far pairs: keep the input order
+        auto poor = [&](const int32_t *pm) {
+            int64_t far = 0, tot = 0;
+            for (int64_t e = 0; e < E; ++e) {
+                int32_t a = fc[elems_cm[e]], b = fc[elems_cm[E + e]];
+                if (a < 0 || b < 0) continue;
+                if (pm) { a = pm[a]; b = pm[b]; }
+                ++tot;
+                far += std::llabs((long long)a - (long long)b) > window;
+            }
+            return tot != 0 && far * 20 >= tot;   // >= 5 % far pairs
+        };
+        if (!poor(nullptr)) return false;   // keep the input order
+        // (Z-order, mode 3, costs a fifth of the traversal on the host but its SpMV measured 5 % slower
+        // than breadth-first + balanced storage on B200: profiles/README.md -- so auto stays breadth-first)
     }
     (void)V;
     // adjacency of the free-vertex graph (CSR)
@@ -241,16 +300,16 @@ static bool bfs_renumber(int64_t V, int64_t E, const int32_t *elems_cm, const st
 }
 
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
-                int32_t rank, int32_t world, bool with_contrib, HostPlan &P, int reorder)
+                int32_t rank, int32_t world, bool with_contrib, HostPlan &P, int reorder, const double *nodes_cm)
 {
     PrepTrace tr;
     P.V = V; P.E = E; P.rank = rank; P.world = world;
     P.nb_global = build_free_map(V, F, fixed, P.free_index);
     const int64_t nbg = P.nb_global;
-    if (bfs_renumber(V, E, elems_cm, P.free_index, nbg, reorder, P.perm, P.inv)) {
+    if (bfs_renumber(V, E, elems_cm, P.free_index, nbg, reorder, nodes_cm, P.perm, P.inv)) {
         for (int64_t v = 0; v < V; ++v)
             if (P.free_index[v] >= 0) P.free_index[v] = P.perm[P.free_index[v]];
-        tr.lap("breadth-first renumbering");
+        tr.lap("internal renumbering");
     }
     P.row_begin = nbg * rank / world;
     P.row_end = nbg * (rank + 1) / world;
@@ -423,15 +482,55 @@ void build_solver_format(HostPlan &P, bool half)
     P.sym_half = half;
     P.uptr.assign((size_t)nb + 1, 0);
     P.lptr.assign((size_t)nb + 1, 0);
-    // pass 1: counts.  (r,c) is stored in row r unless it is a local column below the
-    // diagonal under half storage; then it is reached through row c's block (c,r).
+    // Which row stores the block of a local pair {r, c}?  Default: the upper one (r < c) -- on
+    // translation-invariant numberings (lattices, grids in scan order) every row then stores the
+    // same number of blocks and the transposed references of a tile stay coalesced.  On irregular
+    // numberings the upper counts vary row by row and the 32-row tiles of the interleaved layout
+    // pad to their longest row; there the pairs are oriented greedily towards the emptier row
+    // (rows ascending, ties to the upper row), which brings every row to ~deg/2 stored blocks.
+    std::vector<uint8_t> own;   // per BSR entry: 1 = stored in its own row (balanced orientation only)
+    P.balanced = false;
+    if (half) {
+        int64_t stored = 0, slots = 0;
+        for (int64_t t = 0; t * 32 < nb; ++t) {
+            int32_t mx = 0;
+            for (int64_t r = t * 32; r < std::min<int64_t>(nb, t * 32 + 32); ++r) {
+                int32_t nu = 0;
+                for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) nu += P.colidx[k] > r;
+                stored += nu; mx = std::max(mx, nu);
+            }
+            slots += 32 * (int64_t)mx;
+        }
+        static const bool no_balance = std::getenv("MBFEA_NO_BALANCE") != nullptr;   // A/B knob
+        if (slots * 20 > stored * 21 && !no_balance) {   // > 5 % padding under the upper rule
+            P.balanced = true;
+            own.assign(P.colidx.size(), 1);
+            std::vector<int32_t> cnt((size_t)nb, 0), cursor(P.rowptr.begin(), P.rowptr.end() - 1);
+            for (int64_t r = 0; r < nb; ++r)
+                for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
+                    const int32_t c = P.colidx[k];
+                    if (c >= nb) { ++cnt[r]; continue; }   // ghost column: always stored here
+                    if (c <= r) continue;
+                    // the mirrored entry (c, r): row c's local lower entries are met in ascending r
+                    const int32_t m = cursor[c]++;
+                    const bool mine = cnt[r] <= cnt[c];
+                    own[(size_t)k] = mine; own[(size_t)m] = !mine;
+                    ++cnt[mine ? r : c];
+                }
+        }
+    }
+    auto stored_here = [&](int64_t r, int32_t k, int32_t c) {
+        if (!half || c >= nb) return true;
+        return P.balanced ? own[(size_t)k] != 0 : c > r;
+    };
+    // pass 1: counts.  (r,c) is stored in row r, or reached through row c's block (c,r).
     parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
         for (int64_t r = lo; r < hi; ++r) {
             int32_t nu = 0, nl = 0;
             for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
                 const int32_t c = P.colidx[k];
                 if (c == r) continue;
-                if (half && c < nb && c < r) ++nl; else ++nu;
+                if (stored_here(r, k, c)) ++nu; else ++nl;
             }
             P.uptr[r + 1] = nu; P.lptr[r + 1] = nl;   // counts first, prefix sums below
         }
@@ -447,7 +546,7 @@ void build_solver_format(HostPlan &P, bool half)
             for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
                 const int32_t c = P.colidx[k];
                 if (c == r) continue;
-                if (half && c < nb && c < r) continue;
+                if (!stored_here(r, k, c)) continue;
                 P.ucol[u] = c; P.usrc[u] = k; ++u;
             }
         }

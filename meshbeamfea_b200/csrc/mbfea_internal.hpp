@@ -39,11 +39,13 @@ struct HostPlan {
     std::vector<int32_t> contrib;     // (element<<2)|which, ascending element per block
     // Solver format (off-diagonal blocks of the block-Jacobi-scaled matrix, unit diagonal implied):
     // row r stores the blocks [uptr[r], uptr[r+1]) itself -- its ghost columns and, with
-    // symmetric-half storage, only its local columns c > r -- and reaches the remaining local
-    // columns c < r as TRANSPOSED references [lptr[r], lptr[r+1]) into row c's stored blocks.
+    // symmetric-half storage, one of every local pair {r, c} (the upper one, c > r, unless
+    // `balanced`) -- and reaches the remaining local
+    // columns as TRANSPOSED references [lptr[r], lptr[r+1]) into row c's stored blocks.
     std::vector<int32_t> uptr, ucol, usrc;  // usrc: index of the block in the full pattern
     std::vector<int32_t> lptr, lcol, lblk;  // lblk: stored-block index holding (lcol, r)
     bool sym_half = false;
+    bool balanced = false;   // pairs oriented towards the emptier row instead of the upper one (irregular numberings)
     // Symmetric-half values are stored INTERLEAVED per tile of 32 block rows (sliced ELL): the
     // 16-byte chunk m (0..2) of scalar row i of the k-th stored block of local row lr sits at
     // 16-byte unit  tile_base[tile] + (3k + m) * 192 + 6 lr + i,  so the 192 threads of a CTA
@@ -83,9 +85,11 @@ int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<i
 
 // Block pattern, contributor lists, halo plan for `rank` of `world`.
 // with_contrib=false skips the contributor lists (plan-only callers).
-// reorder: 0 never, 1 when the canonical numbering has poor locality (auto), 2 always
+// reorder: 0 never, 1 breadth-first when the canonical numbering has poor locality (auto), 2 breadth-first
+// always, 3 Morton order of the vertex coordinates (needs nodes_cm; falls back to 2 without)
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
-                int32_t rank, int32_t world, bool with_contrib, HostPlan &plan, int reorder = 0);
+                int32_t rank, int32_t world, bool with_contrib, HostPlan &plan, int reorder = 0,
+                const double *nodes_cm = nullptr);
 
 // Solver format from the full pattern (see HostPlan::uptr).  half=false keeps every
 // off-diagonal block in its own row (no transposed references).

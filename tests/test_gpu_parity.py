@@ -117,7 +117,7 @@ def test_every_solver_format_and_kernel_gives_the_same_solution(built, storage, 
             assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
 
 
-@pytest.mark.parametrize("reorder", [0, 2], ids=["auto", "always"])
+@pytest.mark.parametrize("reorder", [0, 2, 3], ids=["auto", "always", "morton"])
 def test_arbitrary_vertex_numbering(built, reorder):
     """Vertex ids in random order: the solver renumbers internally (breadth-first) but every tap and
     result stays in the reference's numbering -- constraint map, pattern and K values bit-exact,
