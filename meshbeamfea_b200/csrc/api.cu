@@ -124,6 +124,7 @@ struct mbfea_ctx {
     DevBuf<double *> push_dst;   // destination of every (boundary row, neighbour) pair, grouped by row
     DevBuf<double *> push_dst_send;  // the same in send-list order (standalone push kernel, iteration 0)
     DevBuf<int32_t> push_idx;    // per owned row: first entry in push_dst | count << 28, or -1
+    DevBuf<int32_t> push_rows;   // the owned rows with push_idx >= 0, ascending (boundary-first pass of the step kernel)
     std::vector<Mailbox *> peer_mailbox;   // [world]; own entry = mailbox.p
     std::vector<double *> peer_p;          // [world]; peers' p vectors (IPC mappings), own = p.p
     unsigned long long epoch = 0;
@@ -391,8 +392,12 @@ void setup_p2p_halo(mbfea_ctx *c)
         for (size_t i = 0; i < dst.size(); ++i) byrow[(size_t)cur[(size_t)c->plan.send_rows[i]]++] = dst[i];
         for (int64_t r = 0; r < nb; ++r)
             if (cnt[(size_t)r]) idx[(size_t)r] = first[(size_t)r] | (cnt[(size_t)r] << 28);
+        std::vector<int32_t> rows;
+        for (int64_t r = 0; r < nb; ++r)
+            if (cnt[(size_t)r]) rows.push_back((int32_t)r);
         upload(c, c->push_dst, byrow);
         upload(c, c->push_idx, idx);
+        upload(c, c->push_rows, rows);
     }
     PeerCtx pc;
     std::memset(&pc, 0, sizeof pc);
@@ -475,7 +480,8 @@ void enqueue_iteration2(mbfea_ctx *c, int kernel)
     PartialRef delta{c->part_a.p, gs, 1}, gamma{c->part_b.p, gs, 1};
     if (W > 1 && !c->p2p) { delta = PartialRef{c->gath.p, W, 2}; gamma = PartialRef{c->gath.p + 1, W, 2}; }
     launch_cg2_step(c->st, nb, delta, gamma, c->p.p, c->Ap.p, c->rt.p, c->sdir.p, c->y.p, c->sc.p,
-                    c->p2p ? c->peerctx.p : nullptr, c->p2p ? c->push_idx.p : nullptr, c->p2p ? c->push_dst.p : nullptr);
+                    c->p2p ? c->peerctx.p : nullptr, c->p2p ? c->push_idx.p : nullptr, c->p2p ? c->push_dst.p : nullptr,
+                    c->p2p ? c->push_rows.p : nullptr, c->p2p ? (int)c->push_rows.n : 0);
     c->launches++;
     enqueue_spmv2(c, kernel);
 }

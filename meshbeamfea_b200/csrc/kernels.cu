@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -68,6 +69,15 @@ __device__ __forceinline__ double sum_partials(PartialRef ref, double *scratch)
     return block_sum<true>(s, scratch);
 }
 
+// two sums in one pass over the partials (same fixed order as sum_partials)
+__device__ __forceinline__ void sum_partials2(PartialRef a, PartialRef b, double *scratch, double &sa, double &sb)
+{
+    double s = 0.0, t = 0.0;
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) { s += a.buf[(size_t)i * a.stride]; t += b.buf[(size_t)i * b.stride]; }
+    sa = block_sum<true>(s, scratch);
+    sb = block_sum<true>(t, scratch);
+}
+
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------
 // (Opt-in, MBFEA_PDL=1.)  The kernels of the CG loop can be launched with programmatic stream serialisation: a kernel lets
 // its successor start launching at once (pdl_trigger) and itself waits for its predecessor's
@@ -103,6 +113,27 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// flag of the fence-free exchange (Mailbox::ll): never 0, distinct from the slot's previous use (two iterations back)
+__device__ __forceinline__ unsigned int ll_flag(unsigned long long epoch, long long iter)
+{
+    return 0x80000000u | (((unsigned int)epoch & 0x3fu) << 25) | ((unsigned int)(iter + 1) & 0x1ffffffu);
+}
+__device__ __forceinline__ void ll_store(unsigned long long *lo, unsigned long long *hi, double v, unsigned int flag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), f = (unsigned long long)flag << 32;
+    st_relaxed_sys(lo, f | (b & 0xffffffffull));
+    st_relaxed_sys(hi, f | (b >> 32));
+}
 // Bounded: a peer that never signals (a crashed rank) must not hang the GPU.  After ~10 s the
 // waiter gives up and raises *timeout_flag; the host reports it as a failed solve.
 __device__ int g_peer_timeout = 0;
@@ -114,9 +145,31 @@ __device__ __forceinline__ void spin_until(const unsigned long long *p, unsigned
         if (clock64() - t0 > 20000000000LL) { atomicExch(&g_peer_timeout, 1); break; }
     }
 }
+__device__ __forceinline__ double ll_wait(const unsigned long long *lo, const unsigned long long *hi, unsigned int flag)
+{
+    const long long t0 = clock64();
+    unsigned long long a, b;
+    for (;;) {
+        a = ld_relaxed_sys(lo); b = ld_relaxed_sys(hi);
+        if ((unsigned int)(a >> 32) == flag && (unsigned int)(b >> 32) == flag) break;
+        __nanosleep(20);
+        if (clock64() - t0 > 20000000000LL) { atomicExch(&g_peer_timeout, 1); break; }
+    }
+    return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+}
 __device__ __forceinline__ void trace_stamp(const PcgScalars *sc, long long iter, int slot)
 {
     if (sc != nullptr && sc->trace != nullptr && iter < kTraceIters && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sc->trace[iter * kTraceSlots + slot] = t;
+    }
+}
+
+// stamp from whichever CTA calls it (thread 0): end-of-kernel events of the last CTA
+__device__ __forceinline__ void trace_stamp_cta(const PcgScalars *sc, long long iter, int slot)
+{
+    if (sc != nullptr && sc->trace != nullptr && iter < kTraceIters && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         sc->trace[iter * kTraceSlots + slot] = t;
@@ -607,16 +660,20 @@ constexpr int kSpmvThreads = kRowsPerCta * 6;
 #define MBFEA_SYM_PREFETCH 0  // fetch the next tile's row pointers while working on this one
 #endif
 
-template <bool SYM, bool DOT2>
-__global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv_rowthread(
+// ROWS (32 or 16) block rows per CTA: the symmetric variant runs half-tiles on small systems (a rank's
+// share on 8 GPUs is ~4 tiles per resident CTA: whole tiles quantise the makespan to 5 and leave too few
+// independent load chains per SM); the interleaved layout is addressed by (row & 31) either way.
+template <bool SYM, bool DOT2, int ROWS>
+__global__ void __launch_bounds__(ROWS * 6, (SYM ? MBFEA_SYM_MINB : 8) * (32 / ROWS)) k_spmv_rowthread(
     int64_t nb, const int32_t *__restrict__ uptr, const int32_t *__restrict__ ucol,
     const double *__restrict__ vals, const int32_t *__restrict__ lptr, const int32_t *__restrict__ lcol,
     const int32_t *__restrict__ lofs, const int32_t *__restrict__ tile_base, int identity,
     const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partial,
     double *__restrict__ partial2, const PcgScalars *sc, const PeerCtx *pc)
 {
+    constexpr int kThreads = ROWS * 6;
     __shared__ double red[33];
-    __shared__ double ts[SYM ? kSpmvThreads * 6 : 1];
+    __shared__ double ts[SYM ? kThreads * 6 : 1];
     pdl_wait();      // the previous kernel's results (and sc) are visible from here
     pdl_trigger();   // the next kernel may start launching
     if (sc != nullptr && sc->done != 0) return;
@@ -630,7 +687,7 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
     }
     const int lr = threadIdx.x / 6, i = threadIdx.x - 6 * lr;
     double dot = 0.0, dot2 = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * kRowsPerCta;
+    const int64_t stride = (int64_t)gridDim.x * ROWS;
     // row pointers of the current tile; with MBFEA_SYM_PREFETCH the next tile's are requested before
     // this tile's blocks, so the pointer -> column -> x chain of the next tile is one level shorter
     int32_t kb = 0, ke = 0, lb = 0, le = 0, tb = 0;
@@ -638,9 +695,9 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
     // range is contiguous (interleaved layout), so the CTA can pull it into L2 a full tile ahead with
     // fire-and-forget prefetches: by the time the loads are issued they are L2 hits, not HBM misses.
     int32_t pb = 0, pe = 0;
-    const int64_t ntiles = (nb + kRowsPerCta - 1) / kRowsPerCta;
+    const int64_t ntiles = (nb + ROWS - 1) / ROWS;
     {
-        const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + lr;
+        const int64_t row = (int64_t)blockIdx.x * ROWS + lr;
         if (row < nb) {
             kb = __ldg(uptr + row); ke = __ldg(uptr + row + 1);
             if (SYM) { lb = __ldg(lptr + row); le = __ldg(lptr + row + 1); tb = __ldg(tile_base + (row >> 5)); }
@@ -650,7 +707,7 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
             if (t1 < ntiles) { pb = __ldg(tile_base + t1); pe = __ldg(tile_base + t1 + 1); }
         }
     }
-    for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += stride) {
+    for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < nb; r0 += stride) {
         const int64_t row = r0 + lr;
         const bool live = row < nb;
         int32_t nkb = 0, nke = 0, nlb = 0, nle = 0, ntb = 0;
@@ -663,7 +720,7 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
         }
         if (SYM && MBFEA_SYM_L2PF) {
             const char *base = reinterpret_cast<const char *>(vals);
-            for (int64_t u = (int64_t)pb * 16 + (int64_t)threadIdx.x * 128; u < (int64_t)pe * 16; u += kSpmvThreads * 128)
+            for (int64_t u = (int64_t)pb * 16 + (int64_t)threadIdx.x * 128; u < (int64_t)pe * 16; u += kThreads * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + u));
         }
         double xi = 0.0, acc = 0.0;
@@ -672,7 +729,7 @@ __global__ void __launch_bounds__(kSpmvThreads, SYM ? MBFEA_SYM_MINB : 8) k_spmv
             acc = identity ? xi : 0.0;
             // blocks this row stores: thread i streams ROW i of the block, y_r[i] += M[i][:] . x_c
             // SYM: interleaved tile layout -- the CTA's 192 threads read 192 consecutive 16-byte chunks
-            const double2 *vt = SYM ? reinterpret_cast<const double2 *>(vals) + tb + threadIdx.x : nullptr;
+            const double2 *vt = SYM ? reinterpret_cast<const double2 *>(vals) + tb + (int)(row & 31) * 6 + i : nullptr;
 MBFEA_UNROLL(MBFEA_SYM_UNROLL)
             for (int32_t k = kb; k < ke; ++k) {
                 const int32_t c = __ldg(ucol + k);
@@ -747,29 +804,45 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
     if (pc != nullptr && partial != nullptr && last_cta_done(pc->tickets + 0)) {
         // fused reduction + all-gather: the last CTA sums the partials in fixed order and
         // stores this rank's dot product(s) into every rank's mailbox over NVLink
-        const double s = sum_partials(PartialRef{partial, (int)gridDim.x, 1}, red);
-        const double s2 = DOT2 ? sum_partials(PartialRef{partial2, (int)gridDim.x, 1}, red) : 0.0;
-        if ((int)threadIdx.x < pc->world) {
-            const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
-            Mailbox *m = pc->peer[threadIdx.x];
-            if (!DOT2) {
+        double s, s2 = 0.0;
+        if (DOT2) sum_partials2(PartialRef{partial, (int)gridDim.x, 1}, PartialRef{partial2, (int)gridDim.x, 1}, red, s, s2);
+        else s = sum_partials(PartialRef{partial, (int)gridDim.x, 1}, red);
+        if (!DOT2) {
+            if ((int)threadIdx.x < pc->world) {
+                const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
+                Mailbox *m = pc->peer[threadIdx.x];
                 m->dot_val[0][pc->rank] = s;
                 st_release_sys(&m->dot_tag[0][pc->rank], tag + 1);   // release orders this thread's value store first
-            } else {   // single-reduction CG: slots double-buffered by iteration parity
-                const int par = (int)(sc->iter & 1);
-                m->dot_val[3 + 2 * par][pc->rank] = s;
-                m->dot_val[4 + 2 * par][pc->rank] = s2;
-                st_release_sys(&m->dot_tag[3 + par][pc->rank], tag + 1);
             }
+        } else if ((int)threadIdx.x < 2 * pc->world) {
+            // single-reduction CG: fence-free words, slots double-buffered by iteration parity;
+            // thread q sends r.K~r to rank q, thread world + q sends r.r
+            const int q = (int)threadIdx.x % pc->world, which = (int)threadIdx.x / pc->world;
+            const int par = (int)(sc->iter & 1);
+            Mailbox *m = pc->peer[q];
+            ll_store(&m->ll[par][2 * which][pc->rank], &m->ll[par][2 * which + 1][pc->rank], which ? s2 : s,
+                     ll_flag(sc->epoch, sc->iter));
         }
+        if (DOT2) trace_stamp_cta(sc, sc->iter, 4);
     }
+}
+
+// rows per CTA: half-tiles when whole tiles would give a resident CTA fewer than kHalfTileBelow tiles
+static int spmv_rows(int64_t nb, bool sym)
+{
+    static const int forced = [] { const char *e = std::getenv("MBFEA_SPMV_ROWS"); return e ? std::atoi(e) : 0; }();
+    if (!sym) return 32;
+    if (forced == 16 || forced == 32) return forced;
+    constexpr int64_t kHalfTileBelow = 12;
+    return (nb + 31) / 32 < (int64_t)148 * MBFEA_SYM_MINB * kHalfTileBelow ? 16 : 32;
 }
 
 // one full wave: 148 SMs x resident CTAs per SM (8 at 40 registers, 6 at 56 for the symmetric variant)
 int spmv_rowthread_grid(int64_t nb, bool sym)
 {
-    const int64_t tiles = (nb + kRowsPerCta - 1) / kRowsPerCta;
-    const int64_t cap = sym ? 148 * MBFEA_SYM_MINB : 148 * 8;
+    const int rows = spmv_rows(nb, sym);
+    const int64_t tiles = (nb + rows - 1) / rows;
+    const int64_t cap = (sym ? 148 * MBFEA_SYM_MINB : 148 * 8) * (32 / rows);
     return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
@@ -779,20 +852,27 @@ void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, con
                            const PcgScalars *sc, const PeerCtx *pc)
 {
     const int gs = spmv_rowthread_grid(nb, lptr != nullptr);
-    if (lptr != nullptr && partial2 != nullptr)
-        launch_pdl(k_spmv_rowthread<true, true>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+    const bool half_tiles = spmv_rows(nb, lptr != nullptr) == 16;
+    const int32_t *null32 = nullptr;
+    double *nulld = nullptr;
+    if (lptr != nullptr && partial2 != nullptr && half_tiles)
+        launch_pdl(k_spmv_rowthread<true, true, 16>, gs, 96, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
                    identity, x, y, partial, partial2, sc, pc);
+    else if (lptr != nullptr && partial2 != nullptr)
+        launch_pdl(k_spmv_rowthread<true, true, 32>, gs, 192, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+                   identity, x, y, partial, partial2, sc, pc);
+    else if (lptr != nullptr && half_tiles)
+        launch_pdl(k_spmv_rowthread<true, false, 16>, gs, 96, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+                   identity, x, y, partial, nulld, sc, pc);
     else if (lptr != nullptr)
-        launch_pdl(k_spmv_rowthread<true, false>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
-                   identity, x, y, partial, (double *)nullptr, sc, pc);
+        launch_pdl(k_spmv_rowthread<true, false, 32>, gs, 192, 0, st, nb, uptr, ucol, vals, lptr, lcol, lofs, tile_base,
+                   identity, x, y, partial, nulld, sc, pc);
     else if (partial2 != nullptr)
-        launch_pdl(k_spmv_rowthread<false, true>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, (const int32_t *)nullptr,
-                   (const int32_t *)nullptr, (const int32_t *)nullptr, (const int32_t *)nullptr, identity, x, y, partial,
-                   partial2, sc, pc);
+        launch_pdl(k_spmv_rowthread<false, true, 32>, gs, 192, 0, st, nb, uptr, ucol, vals, null32, null32, null32, null32,
+                   identity, x, y, partial, partial2, sc, pc);
     else
-        launch_pdl(k_spmv_rowthread<false, false>, gs, kSpmvThreads, 0, st, nb, uptr, ucol, vals, (const int32_t *)nullptr,
-                   (const int32_t *)nullptr, (const int32_t *)nullptr, (const int32_t *)nullptr, identity, x, y, partial,
-                   (double *)nullptr, sc, pc);
+        launch_pdl(k_spmv_rowthread<false, false, 32>, gs, 192, 0, st, nb, uptr, ucol, vals, null32, null32, null32, null32,
+                   identity, x, y, partial, nulld, sc, pc);
 }
 
 // ---------------------------------------------------------------------------
@@ -1193,9 +1273,11 @@ __global__ void __launch_bounds__(kSpmvThreads) k_cg2_init(int64_t nb, const dou
 __global__ void __launch_bounds__(256, 4) k_cg2_step(
     int64_t n, PartialRef delta_ref, PartialRef gamma_ref, double *__restrict__ r, const double *__restrict__ w,
     double *__restrict__ d, double *__restrict__ s, double *__restrict__ y, PcgScalars *sc, const PeerCtx *pc,
-    const int32_t *__restrict__ push_idx, double *const *__restrict__ push_dst)
+    const int32_t *__restrict__ push_idx, double *const *__restrict__ push_dst,
+    const int32_t *__restrict__ push_rows, int n_push)
 {
     __shared__ double red[33];
+    __shared__ double dots[2][kMaxWorld];
     pdl_wait();      // the previous kernel's results (and sc) are visible from here
     pdl_trigger();   // the next kernel may start launching
     if (sc->done != 0) return;
@@ -1206,14 +1288,15 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
     if (pc != nullptr) {
         tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)it) + 1;
         const int mp = (int)(it & 1);
-        if ((int)threadIdx.x < pc->world) spin_until(&pc->mine->dot_tag[3 + mp][threadIdx.x], tag);
+        if ((int)threadIdx.x < 2 * pc->world) {   // thread q waits for rank q's r.K~r, thread world + q for its r.r
+            const int q = (int)threadIdx.x % pc->world, which = (int)threadIdx.x / pc->world;
+            const Mailbox *m = pc->mine;
+            dots[which][q] = ll_wait(&m->ll[mp][2 * which][q], &m->ll[mp][2 * which + 1][q], ll_flag(sc->epoch, it));
+        }
         __syncthreads();
         trace_stamp(sc, it, 3);
         delta = 0.0; gamma = 0.0;
-        for (int q = 0; q < pc->world; ++q) {
-            delta += __ldcv(&pc->mine->dot_val[3 + 2 * mp][q]);
-            gamma += __ldcv(&pc->mine->dot_val[4 + 2 * mp][q]);
-        }
+        for (int q = 0; q < pc->world; ++q) { delta += dots[0][q]; gamma += dots[1][q]; }   // rank order: same bits everywhere
     } else {
         delta = sum_partials(delta_ref, red);
         gamma = sum_partials(gamma_ref, red);
@@ -1230,8 +1313,8 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
     const double alpha = (exact || bad) ? 0.0 : gamma / den;
     bool pushed = false;
     if (!exact && !bad) {
-        const int64_t n2 = n >> 1;
-        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += (int64_t)gridDim.x * blockDim.x) {
+        // d = r + beta d; s = w + beta s; y += alpha d; r -= alpha s on 16-byte chunk j; returns the new r
+        auto step = [&](int64_t j) {
             double2 rv = reinterpret_cast<double2 *>(r)[j];
             const double2 wv = reinterpret_cast<const double2 *>(w)[j];
             double2 dv = reinterpret_cast<double2 *>(d)[j], sv = reinterpret_cast<double2 *>(s)[j];
@@ -1244,16 +1327,25 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
             reinterpret_cast<double2 *>(s)[j] = sv;
             reinterpret_cast<double2 *>(y)[j] = yv;
             reinterpret_cast<double2 *>(r)[j] = rv;
-            if (push_idx != nullptr) {
-                const int64_t row = j / 3;
-                const int32_t code = __ldg(push_idx + row);
-                if (code >= 0) {
-                    const int off = (int)(j - row * 3) * 2;
-                    const int32_t first = code & 0x0fffffff, cnt = code >> 28;
-                    for (int32_t q = 0; q < cnt; ++q) *reinterpret_cast<double2 *>(push_dst[first + q] + off) = rv;
-                    pushed = true;
-                }
-            }
+            return rv;
+        };
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+        // boundary blocks first: their stores into the neighbours' ghost regions cross NVLink while the
+        // interior is updated, so the system-scope fence below finds them already acknowledged
+        for (int64_t k = tid; k < 3 * (int64_t)n_push; k += nthr) {
+            const int64_t kr = k / 3;
+            const int32_t row = __ldg(push_rows + kr);
+            const int off = (int)(k - kr * 3);
+            const double2 rv = step((int64_t)row * 3 + off);
+            const int32_t code = __ldg(push_idx + row);
+            const int32_t first = code & 0x0fffffff, cnt = code >> 28;
+            for (int32_t q = 0; q < cnt; ++q) *reinterpret_cast<double2 *>(push_dst[first + q] + 2 * off) = rv;
+            pushed = true;
+        }
+        const int64_t n2 = n >> 1;
+        for (int64_t j = tid; j < n2; j += nthr) {
+            if (push_idx != nullptr && __ldg(push_idx + j / 3) >= 0) continue;   // done above
+            step(j);
         }
     }
     if (push_idx != nullptr) {   // the halo tag must be published even when nothing moved (peers wait on it)
@@ -1262,6 +1354,7 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
             if ((int)threadIdx.x < pc->n_neighbors) {
                 st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
             }
+            trace_stamp_cta(sc, it, 5);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1286,9 +1379,10 @@ void launch_cg2_init(cudaStream_t st, int64_t nb, const double *f, const double 
 
 void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef gamma, double *r, const double *w,
                      double *d, double *s, double *y, PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx,
-                     double *const *push_dst)
+                     double *const *push_dst, const int32_t *push_rows, int n_push)
 {
-    launch_pdl(k_cg2_step, cg_vec_grid(nb), 256, 0, st, 6 * nb, delta, gamma, r, w, d, s, y, sc, pc, push_idx, push_dst);
+    launch_pdl(k_cg2_step, cg_vec_grid(nb), 256, 0, st, 6 * nb, delta, gamma, r, w, d, s, y, sc, pc, push_idx, push_dst,
+               push_rows, push_idx != nullptr ? n_push : 0);
 }
 
 // per batch: partial sums of ||L (a - b)||^2 (b may be null): the unscaled residual norm

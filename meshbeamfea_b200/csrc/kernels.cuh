@@ -10,7 +10,7 @@
 namespace mbfea { namespace dev {
 
 constexpr int kVecThreads = 256;
-constexpr int kMaxPartials = 148 * 8;  // fixed upper bound of reduction grids
+constexpr int kMaxPartials = 148 * 16;  // fixed upper bound of reduction grids
 
 // TMA-staged SpMV tile geometry (see kernels.cu)
 constexpr int kTmaCapBlocks = 224;  // 6x6 blocks per stage: 224*288 B = 63 KB
@@ -32,6 +32,11 @@ struct Mailbox {
     // double-buffered by iteration parity: tag [3 + par], values [3 + 2 par] (r.K~r) and [4 + 2 par] (r.r)
     unsigned long long dot_tag[5][kMaxWorld];
     double dot_val[7][kMaxWorld];
+    // single-reduction CG, fence-free exchange: each double travels as two 8-byte words
+    // (flag << 32 | half of the bit pattern); an 8-byte store is never torn, so a word whose flag
+    // matches carries valid data and the sender needs no fence (and no round trip) before signalling.
+    // [iteration parity][0 r.K~r low, 1 r.K~r high, 2 r.r low, 3 r.r high][rank]
+    unsigned long long ll[2][4][kMaxWorld];
 };
 
 struct PeerCtx {          // device-resident, local memory
@@ -117,7 +122,7 @@ void launch_cg2_init(cudaStream_t st, int64_t nb, const double *f, const double 
                      double *d, double *s, double *part_ff);
 void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef gamma, double *r, const double *w,
                      double *d, double *s, double *y, PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx,
-                     double *const *push_dst);
+                     double *const *push_dst, const int32_t *push_rows, int n_push);
 // unscaled residual norm ||L (a - b)||^2 (b may be null) -> partials; finish: total -> sc->rr, stop test
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
                      const PcgScalars *sc, const PeerCtx *pc);

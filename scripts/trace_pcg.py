@@ -31,7 +31,14 @@ st = c.stats()
 sel = t[20:250]
 names = ["spmv_in", "spmv_go", "upd_in", "upd_go", "pupd_in", "pupd_go", "push_in", "push_out"]
 nxt = t[21:251, 0]
-if world > 1:
+variant = int(os.environ.get("MBFEA_CG", "0")) or (2 if world > 1 else 1)
+if variant == 2:   # single-reduction CG: SpMV on the residual (stamps 0, 1), then one step kernel (stamps 2, 3)
+    segs = {"spmv wait halo": sel[:, 1] - sel[:, 0], "spmv body+tail+launch": sel[:, 2] - sel[:, 1], "step wait dots": sel[:, 3] - sel[:, 2],
+            "step body+push+tail+launch": nxt - sel[:, 3], "whole iteration": nxt - sel[:, 0]}
+    if world > 1:   # end-of-kernel stamps of the last CTA (slots 4, 5)
+        segs.update({"  spmv go -> last CTA published dots": sel[:, 4] - sel[:, 1], "  dots published -> step kernel starts": sel[:, 2] - sel[:, 4],
+                     "  step go -> last CTA published halo tag": sel[:, 5] - sel[:, 3], "  halo tag -> next spmv starts": nxt - sel[:, 5]})
+elif world > 1:
     segs = {"spmv wait halo": sel[:, 1] - sel[:, 0], "spmv body+tail": sel[:, 2] - sel[:, 1], "update wait pAp": sel[:, 3] - sel[:, 2],
             "update body+tail": sel[:, 4] - sel[:, 3], "pupdate wait rho": sel[:, 5] - sel[:, 4],
             "pupdate+push+tail": nxt - sel[:, 5], "whole iteration": nxt - sel[:, 0]}
@@ -41,7 +48,7 @@ msg = [f"[trace] rank {rank}/{world}: ms/it (stats) {st['ms_pcg'] / max(1, st['i
 ok = (nxt - sel[:, 0]) < 3 * np.median(nxt - sel[:, 0])
 segs = {k: v[ok] for k, v in segs.items()}
 for k, v in segs.items():
-    msg.append(f"   {k:24s} median {np.median(v) / 1e3:8.2f} us   mean {np.mean(v) / 1e3:8.2f} us   max {np.max(v) / 1e3:8.2f} us")
+    msg.append(f"   {k:44s} median {np.median(v) / 1e3:8.2f} us   mean {np.mean(v) / 1e3:8.2f} us   max {np.max(v) / 1e3:8.2f} us")
 print("\n".join(msg), flush=True)
 c.close()
 if world > 1:
