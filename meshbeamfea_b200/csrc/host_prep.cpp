@@ -517,6 +517,11 @@ void build_solver_format(HostPlan &P, bool half)
                     own[(size_t)k] = mine; own[(size_t)m] = !mine;
                     ++cnt[mine ? r : c];
                 }
+            // keep it only when it pays (a small regular mesh pads at its faces under either rule)
+            int64_t slots_bal = 0;
+            for (int64_t t = 0; t * 32 < nb; ++t)
+                slots_bal += 32 * (int64_t)*std::max_element(cnt.begin() + t * 32, cnt.begin() + std::min<int64_t>(nb, t * 32 + 32));
+            if (slots_bal * 100 > slots * 97) { P.balanced = false; own.clear(); }
         }
     }
     auto stored_here = [&](int64_t r, int32_t k, int32_t c) {

@@ -346,3 +346,65 @@ def test_bench_reference_arm_runs_on_cpu(built):
     assert d["impl"] == "reference" and d["unit"] == "beams/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"] == "lattice8"
+
+
+def _shuffled(job, seed):
+    V = job.nodes.shape[0]
+    vperm = np.random.default_rng(seed).permutation(V)
+    inv = np.argsort(vperm)
+    return job.nodes[inv], vperm[job.elements].astype(np.int32), vperm[job.fixedNodes].astype(np.int32)
+
+
+def _check_solver_format(fmt, elements, fixed, V):
+    """Every off-diagonal pair of the reduced pattern is stored exactly once, its other direction is a
+    transposed reference to exactly that stored block, and the tiles hold their longest row."""
+    nb = fmt["n_block_rows"]
+    isfixed = np.zeros(V, bool); isfixed[fixed] = True
+    fc = np.full(V, -1, np.int64); fc[~isfixed] = np.arange(nb)
+    a, b = fc[elements[:, 0]], fc[elements[:, 1]]
+    m = (a >= 0) & (b >= 0) & (a != b)
+    pa, pb = fmt["perm"][a[m]].astype(np.int64), fmt["perm"][b[m]].astype(np.int64)
+    pairs = np.unique(np.minimum(pa, pb) * nb + np.maximum(pa, pb))
+    uptr, ucol, lptr, lcol, lofs, tb = (fmt[k].astype(np.int64) for k in ("uptr", "ucol", "lptr", "lcol", "lofs", "tile_base"))
+    urow = np.repeat(np.arange(nb), np.diff(uptr)); lrow = np.repeat(np.arange(nb), np.diff(lptr))
+    assert fmt["n_stored"] == fmt["n_refs"] == pairs.size and fmt["n_offdiag"] == 2 * pairs.size
+    assert np.array_equal(np.sort(np.minimum(urow, ucol) * nb + np.maximum(urow, ucol)), pairs)     # stored once
+    assert np.array_equal(np.sort(lrow * nb + lcol), np.sort(ucol * nb + urow))                      # refs = transposes
+    # a reference points at the first 16-byte chunk of scalar row 0 of the block stored in row lcol
+    slot = np.arange(ucol.size) - uptr[urow]
+    first_chunk = tb[urow // 32] + slot * 576 + (urow % 32) * 6
+    where = {(int(r), int(c)): int(u) for r, c, u in zip(urow, ucol, first_chunk)}
+    assert all(where[(int(c), int(r))] == int(o) for r, c, o in zip(lrow, lcol, lofs))
+    rows_len = np.diff(uptr)
+    padded = np.zeros((nb + 31) // 32 * 32, np.int64); padded[:nb] = rows_len
+    assert np.array_equal(np.diff(tb), padded.reshape(-1, 32).max(1) * 576)
+    assert fmt["value_units"] == tb[-1] and fmt["longest_row"] == rows_len.max()
+    return tb[-1] / (576.0 / 32 * pairs.size)    # slots per stored block: 1.0 = no padding
+
+
+def test_solver_format_upper_rule_on_regular_numbering():
+    lat = syn.cubic_lattice(12)
+    fmt = mb.host_solver_format(lat.nodes, lat.elements, lat.fixedNodes)
+    assert not fmt["renumbered"] and not fmt["balanced"] and fmt["longest_row"] == 3
+    assert np.all(fmt["ucol"] > np.repeat(np.arange(fmt["n_block_rows"]), np.diff(fmt["uptr"])))   # upper blocks only
+    assert _check_solver_format(fmt, lat.elements, lat.fixedNodes, lat.nodes.shape[0]) < 1.10   # face rows store fewer than 3
+
+
+@pytest.mark.parametrize("mode", [2, 3], ids=["breadth_first", "morton"])
+def test_solver_format_balanced_on_irregular_numbering(mode):
+    """Shuffled vertex ids: internal renumbering (either kind) + pairs oriented towards the emptier row
+    keep the interleaved tiles almost free of padding."""
+    lat = syn.cubic_lattice(14)
+    nodes, elements, fixed = _shuffled(lat, 3)
+    fmt = mb.host_solver_format(nodes, elements, fixed, mode=mode)
+    assert fmt["renumbered"] and np.array_equal(np.sort(fmt["perm"]), np.arange(fmt["n_block_rows"]))
+    pad = _check_solver_format(fmt, elements, fixed, nodes.shape[0])
+    if mode == 2:
+        assert fmt["balanced"] and fmt["longest_row"] <= 4 and pad < 1.12
+    else:   # the Z-order is monotone along every axis of a lattice: three upper neighbours per row, nothing to balance
+        assert fmt["longest_row"] == 3 and pad < 1.12
+    shell = syn.gridshell(40)
+    nodes, elements, fixed = _shuffled(shell, 4)
+    fmt = mb.host_solver_format(nodes, elements, fixed, mode=mode)
+    assert fmt["balanced"]
+    assert _check_solver_format(fmt, elements, fixed, nodes.shape[0]) < 1.25   # upper rule: 1.36-1.45 on this mesh
