@@ -73,7 +73,10 @@ __device__ __forceinline__ double sum_partials(PartialRef ref, double *scratch)
 __device__ __forceinline__ void sum_partials2(PartialRef a, PartialRef b, double *scratch, double &sa, double &sb)
 {
     double s = 0.0, t = 0.0;
-    for (int i = threadIdx.x; i < a.n; i += blockDim.x) { s += a.buf[(size_t)i * a.stride]; t += b.buf[(size_t)i * b.stride]; }
+#pragma unroll 8
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) {   // loads batched by the unroll, adds in order
+        s += __ldcg(a.buf + (size_t)i * a.stride); t += __ldcg(b.buf + (size_t)i * b.stride);
+    }
     sa = block_sum<true>(s, scratch);
     sb = block_sum<true>(t, scratch);
 }
@@ -176,14 +179,17 @@ __device__ __forceinline__ void trace_stamp_cta(const PcgScalars *sc, long long 
     }
 }
 
-// true in every thread of exactly one CTA of the grid: the last one to get here.
-// Call after the CTA's global writes; resets the ticket for the next launch.
-__device__ __forceinline__ bool last_cta_done(unsigned int *ticket)
+// true in every thread of exactly one CTA of the grid: the last one to get here.  Call after the CTA's
+// global writes; resets the ticket for the next launch.  ONE fence per CTA: the barrier orders every
+// thread's writes before thread 0's fence, which is cumulative (the grid-sync pattern; a fence in every
+// thread cost the step kernel 5 us per iteration on two GPUs).  sys: some thread of the CTA stored into
+// peer memory, so the fence must reach system scope before the ticket is taken.
+__device__ __forceinline__ bool last_cta_done(unsigned int *ticket, bool sys)
 {
     __shared__ int is_last;
-    __threadfence();
-    __syncthreads();
+    const int any_sys = __syncthreads_or(sys ? 1 : 0);
     if (threadIdx.x == 0) {
+        if (any_sys) __threadfence_system(); else __threadfence();
         const unsigned int t = atomicAdd(ticket, 1u);
         is_last = (t == gridDim.x - 1);
         if (is_last) *ticket = 0u;
@@ -801,7 +807,7 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
         const double s = block_sum<false>(dot2, red);
         if (threadIdx.x == 0) partial2[blockIdx.x] = s;
     }
-    if (pc != nullptr && partial != nullptr && last_cta_done(pc->tickets + 0)) {
+    if (pc != nullptr && partial != nullptr && last_cta_done(pc->tickets + 0, false)) {
         // fused reduction + all-gather: the last CTA sums the partials in fixed order and
         // stores this rank's dot product(s) into every rank's mailbox over NVLink
         double s, s2 = 0.0;
@@ -1154,7 +1160,7 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
     }
     const double a = block_sum<false>(rho, red);
     if (threadIdx.x == 0) part_rho[blockIdx.x] = a;
-    if (pc != nullptr && last_cta_done(pc->tickets + 1)) {
+    if (pc != nullptr && last_cta_done(pc->tickets + 1, false)) {
         const double sa = sum_partials(PartialRef{part_rho, (int)gridDim.x, 1}, red);
         if ((int)threadIdx.x < pc->world) {
             Mailbox *m = pc->peer[threadIdx.x];
@@ -1216,8 +1222,7 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
         }
     }
     if (push_idx != nullptr) {
-        if (pushed) __threadfence_system();   // this thread's peer stores land before its CTA takes a ticket
-        if (last_cta_done(pc->tickets + 2)) {
+        if (last_cta_done(pc->tickets + 2, pushed)) {   // peer stores land (system-scope fence) before the ticket
             if ((int)threadIdx.x < pc->n_neighbors) {
                 // tag_cur = (epoch << 32 | k) + 1: exactly the halo tag iteration k+1 waits for
                 st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], sc->tag_cur);
@@ -1349,8 +1354,7 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
         }
     }
     if (push_idx != nullptr) {   // the halo tag must be published even when nothing moved (peers wait on it)
-        if (pushed) __threadfence_system();
-        if (last_cta_done(pc->tickets + 2)) {
+        if (last_cta_done(pc->tickets + 2, pushed)) {
             if ((int)threadIdx.x < pc->n_neighbors) {
                 st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
             }
@@ -1412,7 +1416,7 @@ __global__ void __launch_bounds__(kSpmvThreads) k_cg_check(int64_t nb, const dou
     }
     const double s = block_sum<false>(rr, red);
     if (threadIdx.x == 0) part[blockIdx.x] = s;
-    if (pc != nullptr && last_cta_done(pc->tickets + 3)) {
+    if (pc != nullptr && last_cta_done(pc->tickets + 3, false)) {
         const double sa = sum_partials(PartialRef{part, (int)gridDim.x, 1}, red);
         if ((int)threadIdx.x < pc->world) {
             const unsigned long long tag = ((sc->epoch << 32) | (unsigned long long)(unsigned int)sc->checks) + 1;
@@ -1725,11 +1729,9 @@ __global__ void __launch_bounds__(256) k_push_halo(int64_t n_send, const int32_t
         const double2 v = *reinterpret_cast<const double2 *>(x + (int64_t)__ldg(send_rows + s) * 6 + j);
         *reinterpret_cast<double2 *>(dst[s] + j) = v;
     }
-    __threadfence_system();
-    if (last_cta_done(pc->tickets + 2)) {
+    if (last_cta_done(pc->tickets + 2, true)) {
         const unsigned long long tag = (sc->epoch << 32) | (unsigned long long)(unsigned int)sc->iter;
         if ((int)threadIdx.x < pc->n_neighbors) {
-            __threadfence_system();
             st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
         }
         if (sc->iter > 0 && sc->trace != nullptr && sc->iter - 1 < kTraceIters && threadIdx.x == 0) {
