@@ -256,7 +256,7 @@ int spmv_grid(const mbfea_ctx *c, int kernel)
 {
     if (kernel == 2 && !c->plan.sym_half && !c->p2p && cg_variant(c) == 1)
         return spmv_tma_grid((int64_t)c->tile_row_s_host.size() - 1, c->sm_count);
-    return spmv_rowthread_grid(c->nb(), c->plan.sym_half);
+    return spmv_rowthread_grid(c->nb(), c->plan.sym_half, c->p2p);
 }
 
 // boundary x-blocks -> neighbours' ghost slots (multi-GPU only)

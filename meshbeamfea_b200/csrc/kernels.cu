@@ -69,13 +69,14 @@ __device__ __forceinline__ double sum_partials(PartialRef ref, double *scratch)
     return block_sum<true>(s, scratch);
 }
 
-// two sums in one pass over the partials (same fixed order as sum_partials)
-__device__ __forceinline__ void sum_partials2(PartialRef a, PartialRef b, double *scratch, double &sa, double &sb)
+// sums of n (a, b) pairs in a fixed order; one 16-byte load per pair, loads batched by the unroll
+__device__ __forceinline__ void sum_partial_pairs(const double2 *pairs, int n, double *scratch, double &sa, double &sb)
 {
     double s = 0.0, t = 0.0;
 #pragma unroll 8
-    for (int i = threadIdx.x; i < a.n; i += blockDim.x) {   // loads batched by the unroll, adds in order
-        s += __ldcg(a.buf + (size_t)i * a.stride); t += __ldcg(b.buf + (size_t)i * b.stride);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 v = __ldcg(pairs + i);
+        s += v.x; t += v.y;
     }
     sa = block_sum<true>(s, scratch);
     sb = block_sum<true>(t, scratch);
@@ -799,19 +800,27 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
             if (t2 < ntiles) { pb = __ldg(tile_base + t2); pe = __ldg(tile_base + t2 + 1); }
         }
     }
-    if (partial != nullptr) {
-        const double s = block_sum<false>(dot, red);
-        if (threadIdx.x == 0) partial[blockIdx.x] = s;
-    }
-    if (DOT2) {   // single-reduction CG: x.x rides along with x.Ax
-        const double s = block_sum<false>(dot2, red);
-        if (threadIdx.x == 0) partial2[blockIdx.x] = s;
+    if (DOT2 && pc != nullptr) {
+        // multi-GPU single-reduction CG: both partials in one 16-byte slot of `partial`, so the last
+        // CTA's serial reduction below needs half the loads (partial2 is not used on this path)
+        const double s = block_sum<false>(dot, red), s2 = block_sum<false>(dot2, red);
+        if (threadIdx.x == 0) reinterpret_cast<double2 *>(partial)[blockIdx.x] = make_double2(s, s2);
+    } else {
+        if (partial != nullptr) {
+            const double s = block_sum<false>(dot, red);
+            if (threadIdx.x == 0) partial[blockIdx.x] = s;
+        }
+        if (DOT2) {   // single-reduction CG: x.x rides along with x.Ax
+            const double s = block_sum<false>(dot2, red);
+            if (threadIdx.x == 0) partial2[blockIdx.x] = s;
+        }
     }
     if (pc != nullptr && partial != nullptr && last_cta_done(pc->tickets + 0, false)) {
         // fused reduction + all-gather: the last CTA sums the partials in fixed order and
         // stores this rank's dot product(s) into every rank's mailbox over NVLink
+        if (DOT2) trace_stamp_cta(sc, sc->iter, 6);
         double s, s2 = 0.0;
-        if (DOT2) sum_partials2(PartialRef{partial, (int)gridDim.x, 1}, PartialRef{partial2, (int)gridDim.x, 1}, red, s, s2);
+        if (DOT2) sum_partial_pairs(reinterpret_cast<const double2 *>(partial), (int)gridDim.x, red, s, s2);
         else s = sum_partials(PartialRef{partial, (int)gridDim.x, 1}, red);
         if (!DOT2) {
             if ((int)threadIdx.x < pc->world) {
@@ -834,19 +843,22 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
 }
 
 // rows per CTA: half-tiles when whole tiles would give a resident CTA fewer than kHalfTileBelow tiles
-static int spmv_rows(int64_t nb, bool sym)
+static int spmv_rows(int64_t nb, bool sym, bool peer)
 {
     static const int forced = [] { const char *e = std::getenv("MBFEA_SPMV_ROWS"); return e ? std::atoi(e) : 0; }();
     if (!sym) return 32;
+    // NVLink peer path: the last CTA reduces one partial per CTA serially -- twice the CTAs cost more there
+    // (7.6 vs 2.8 us on two GPUs) than the finer tiles gain (and the paired partials fill `partial` at 148 * 8)
+    if (peer) return 32;
     if (forced == 16 || forced == 32) return forced;
     constexpr int64_t kHalfTileBelow = 12;
     return (nb + 31) / 32 < (int64_t)148 * MBFEA_SYM_MINB * kHalfTileBelow ? 16 : 32;
 }
 
 // one full wave: 148 SMs x resident CTAs per SM (8 at 40 registers, 6 at 56 for the symmetric variant)
-int spmv_rowthread_grid(int64_t nb, bool sym)
+int spmv_rowthread_grid(int64_t nb, bool sym, bool peer)
 {
-    const int rows = spmv_rows(nb, sym);
+    const int rows = spmv_rows(nb, sym, peer);
     const int64_t tiles = (nb + rows - 1) / rows;
     const int64_t cap = (sym ? 148 * MBFEA_SYM_MINB : 148 * 8) * (32 / rows);
     return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
@@ -857,8 +869,8 @@ void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, con
                            int identity, const double *x, double *y, double *partial, double *partial2,
                            const PcgScalars *sc, const PeerCtx *pc)
 {
-    const int gs = spmv_rowthread_grid(nb, lptr != nullptr);
-    const bool half_tiles = spmv_rows(nb, lptr != nullptr) == 16;
+    const int gs = spmv_rowthread_grid(nb, lptr != nullptr, pc != nullptr);
+    const bool half_tiles = spmv_rows(nb, lptr != nullptr, pc != nullptr) == 16;
     const int32_t *null32 = nullptr;
     double *nulld = nullptr;
     if (lptr != nullptr && partial2 != nullptr && half_tiles)

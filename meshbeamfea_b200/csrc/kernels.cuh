@@ -95,7 +95,7 @@ void launch_scale_blocks(cudaStream_t st, int64_t nb, const int32_t *uptr, const
                          const double *vals, const double *sinv, double *vals_s, const int32_t *tile_base);
 // K4: y = A x (x has nb + n_ghost blocks), partial[blockIdx] = sum x_own . y
 //     identity: unit diagonal implied; lptr/lcol/lblk: transposed references (may be null)
-int  spmv_rowthread_grid(int64_t nb, bool sym);
+int  spmv_rowthread_grid(int64_t nb, bool sym, bool peer = false);   // peer: launched with a PeerCtx
 void launch_spmv_rowthread(cudaStream_t st, int64_t nb, const int32_t *uptr, const int32_t *ucol, const double *vals,
                            const int32_t *lptr, const int32_t *lcol, const int32_t *lofs, const int32_t *tile_base,
                            int identity, const double *x, double *y, double *partial, double *partial2,

@@ -36,7 +36,8 @@ if variant == 2:   # single-reduction CG: SpMV on the residual (stamps 0, 1), th
     segs = {"spmv wait halo": sel[:, 1] - sel[:, 0], "spmv body+tail+launch": sel[:, 2] - sel[:, 1], "step wait dots": sel[:, 3] - sel[:, 2],
             "step body+push+tail+launch": nxt - sel[:, 3], "whole iteration": nxt - sel[:, 0]}
     if world > 1:   # end-of-kernel stamps of the last CTA (slots 4, 5)
-        segs.update({"  spmv go -> last CTA published dots": sel[:, 4] - sel[:, 1], "  dots published -> step kernel starts": sel[:, 2] - sel[:, 4],
+        segs.update({"  spmv go -> all CTAs done (ticket won)": sel[:, 6] - sel[:, 1], "  ticket won -> dots published": sel[:, 4] - sel[:, 6],
+                     "  spmv go -> last CTA published dots": sel[:, 4] - sel[:, 1], "  dots published -> step kernel starts": sel[:, 2] - sel[:, 4],
                      "  step go -> last CTA published halo tag": sel[:, 5] - sel[:, 3], "  halo tag -> next spmv starts": nxt - sel[:, 5]})
 elif world > 1:
     segs = {"spmv wait halo": sel[:, 1] - sel[:, 0], "spmv body+tail": sel[:, 2] - sel[:, 1], "update wait pAp": sel[:, 3] - sel[:, 2],
