@@ -492,14 +492,23 @@ void build_solver_format(HostPlan &P, bool half)
     P.balanced = false;
     if (half) {
         int64_t stored = 0, slots = 0;
-        for (int64_t t = 0; t * 32 < nb; ++t) {
-            int32_t mx = 0;
-            for (int64_t r = t * 32; r < std::min<int64_t>(nb, t * 32 + 32); ++r) {
-                int32_t nu = 0;
-                for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) nu += P.colidx[k] > r;
-                stored += nu; mx = std::max(mx, nu);
-            }
-            slots += 32 * (int64_t)mx;
+        {
+            const int64_t nt32 = (nb + 31) / 32;
+            std::vector<int64_t> part_stored(64, 0), part_slots(64, 0);   // per thread (parallel_ranges uses <= 32)
+            parallel_ranges(nt32, 1 << 9, [&](int64_t lo, int64_t hi, int th) {
+                int64_t st = 0, sl = 0;
+                for (int64_t t = lo; t < hi; ++t) {
+                    int32_t mx = 0;
+                    for (int64_t r = t * 32; r < std::min<int64_t>(nb, t * 32 + 32); ++r) {
+                        int32_t nu = 0;
+                        for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) nu += P.colidx[k] > r;
+                        st += nu; mx = std::max(mx, nu);
+                    }
+                    sl += 32 * (int64_t)mx;
+                }
+                part_stored[(size_t)th] = st; part_slots[(size_t)th] = sl;
+            });
+            for (int t = 0; t < 64; ++t) { stored += part_stored[(size_t)t]; slots += part_slots[(size_t)t]; }
         }
         static const bool no_balance = std::getenv("MBFEA_NO_BALANCE") != nullptr;   // A/B knob
         if (slots * 20 > stored * 21 && !no_balance) {   // > 5 % padding under the upper rule
@@ -569,17 +578,24 @@ void build_solver_format(HostPlan &P, bool half)
         if (next > INT32_MAX) { P.tile_base.clear(); P.sym_half = false; build_solver_format(P, false); return; }
         P.tile_base[t + 1] = (int32_t)next;
     }
-    // pass 2: transposed references, rows c ascending => each row's list is ascending in c
+    // pass 2: transposed references.  Row r's list holds its local neighbours whose block lives in the
+    // other row, ascending in c (the order of the pattern row); the slot of (c, r) inside row c's
+    // short stored list is found by scanning it.
     P.lofs.resize(P.lcol.size());
-    std::vector<int32_t> cur(P.lptr.begin(), P.lptr.end() - 1);
-    for (int64_t c = 0; c < nb; ++c)
-        for (int32_t b = P.uptr[c]; b < P.uptr[c + 1]; ++b) {
-            const int32_t r = P.ucol[b];
-            if (r >= nb) continue;  // ghost column: the owner of r stores its own copy
-            P.lcol[cur[r]] = (int32_t)c; P.lblk[cur[r]] = b;
-            P.lofs[cur[r]] = P.tile_base[c / 32] + (b - P.uptr[c]) * 3 * 192 + (int32_t)(c % 32) * 6;
-            ++cur[r];
+    parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t r = lo; r < hi; ++r) {
+            int32_t l = P.lptr[r];
+            for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
+                const int32_t c = P.colidx[k];
+                if (c == r || stored_here(r, k, c)) continue;
+                int32_t b = P.uptr[c];
+                while (P.ucol[b] != (int32_t)r) ++b;   // present by symmetry of the local pattern
+                P.lcol[l] = c; P.lblk[l] = b;
+                P.lofs[l] = P.tile_base[c / 32] + (b - P.uptr[c]) * 3 * 192 + (int32_t)(c % 32) * 6;
+                ++l;
+            }
         }
+    });
     tr.lap("solver format: transposed refs");
 }
 
