@@ -285,7 +285,7 @@ int mbfea_host_props(int64_t E, const float *dims_bh, const float *mat_nuE, doub
 int mbfea_host_free_map(int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
                         int64_t *n_free);
 /* renumber: the internal breadth-first renumbering set_job would use (mode as options.reorder:
- *           0 auto, 1 never, 2 always).  perm[n_free]: canonical reduced id -> internal block row
+ *           0 auto, 1 never, 2 always; 3 needs coordinates and acts as 2 here).  perm[n_free]: canonical reduced id -> internal block row
  *           (identity when the canonical order is kept); *reordered says which.                */
 int mbfea_host_renumber(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                         int32_t mode, int32_t *perm, int32_t *reordered);

@@ -450,7 +450,8 @@ def test_mbfea_run_cli_on_reference_scenario_files(built, tmp_path):
 def test_edge_cases(built):
     """Empty / degenerate inputs the reference's adapter would meet: every vertex fixed (nothing to
     solve), one beam, duplicated fixed indices, two beams between the same vertices, a free vertex
-    without beams (reported singular), non-perpendicular normals (same frame formulas as upstream)."""
+    without beams (reported singular), degenerate beam geometry (reported singular), non-perpendicular
+    normals (same frame formulas as upstream)."""
     # every vertex fixed: zero displacements, zero forces, no iterations
     job = syn.two_line_segments(fixed=(0, 1, 2))
     with ctx_for(job) as c:
@@ -485,6 +486,18 @@ def test_edge_cases(built):
     with ctx_for(iso) as c:
         with pytest.raises(mb.SingularSystem):
             c.execute()
+    # degenerate geometry: a zero-length beam (L = 0) and a normal parallel to its beam (nz = nx x ny = 0)
+    # make K non-finite; the reference would factorise NaNs, here the diagonal-block Cholesky reports it
+    for what in ("zero_length", "parallel_normal"):
+        bad = syn.two_line_segments()
+        if what == "zero_length":
+            bad.nodes = bad.nodes.copy(); bad.nodes[2] = bad.nodes[1]
+        else:
+            bad.elementalNormals = bad.elementalNormals.copy()
+            bad.elementalNormals[1] = bad.nodes[2] - bad.nodes[1]
+        with ctx_for(bad) as c:
+            with pytest.raises(mb.SingularSystem):
+                c.execute()
     # skewed (non-perpendicular, non-unit) normals: the frame is what the upstream formulas give
     skew = syn.cubic_lattice(4)
     rng = np.random.default_rng(9)
