@@ -114,12 +114,26 @@ static inline void props_one(float b, float h, float nu, float Egpa, double *out
     out[3] = GJ;
 }
 
+// Host threads of this process: the node's cores divided by the ranks that share it (one process per GPU, all on
+// one node: 8 ranks x 16 threads on 16 cores made set_job slower on 8 GPUs than on one).  MBFEA_HOST_THREADS overrides.
+static thread_local int tl_rank_share = 1;
+struct RankShare {
+    int saved;
+    explicit RankShare(int world) : saved(tl_rank_share) { tl_rank_share = std::max(1, world); }
+    ~RankShare() { tl_rank_share = saved; }
+};
+static int64_t host_threads()
+{
+    static const int forced = [] { const char *e = std::getenv("MBFEA_HOST_THREADS"); return e ? std::atoi(e) : 0; }();
+    if (forced > 0) return std::min(forced, 32);
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max<int64_t>(1, std::min<int64_t>(32, (int64_t)(hw ? hw : 1) / tl_rank_share));
+}
+
 template <class Fn>
 static void parallel_ranges(int64_t n, int64_t min_per_thread, Fn fn)
 {
-    unsigned hw = std::thread::hardware_concurrency();
-    int64_t nt = std::max<int64_t>(1, std::min<int64_t>(hw ? hw : 1, n / std::max<int64_t>(1, min_per_thread)));
-    nt = std::min<int64_t>(nt, 32);
+    const int64_t nt = std::max<int64_t>(1, std::min<int64_t>(host_threads(), n / std::max<int64_t>(1, min_per_thread)));
     if (nt <= 1) { fn(0, n, 0); return; }
     std::vector<std::thread> th;
     for (int64_t t = 0; t < nt; ++t)
@@ -303,6 +317,7 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
                 int32_t rank, int32_t world, bool with_contrib, HostPlan &P, int reorder, const double *nodes_cm)
 {
     PrepTrace tr;
+    RankShare share(world);
     P.V = V; P.E = E; P.rank = rank; P.world = world;
     P.nb_global = build_free_map(V, F, fixed, P.free_index);
     const int64_t nbg = P.nb_global;
@@ -321,8 +336,29 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     // into one range per thread; every thread scans all beams in ascending order and handles the
     // end points that fall into its range, so each row's entries stay in ascending element order.
     std::vector<int32_t> cnt((size_t)nb + 1, 0);
+    // several ranks: the beams with an owned end point, ascending (found once, in parallel), so that the
+    // per-thread scans below cost E / world instead of E
+    std::vector<int32_t> rel;
+    const bool filtered = world > 1 && E <= INT32_MAX;
+    if (filtered) {
+        std::vector<std::vector<int32_t>> chunk(64);
+        parallel_ranges(E, 1 << 16, [&](int64_t lo, int64_t hi, int th) {
+            std::vector<int32_t> &out = chunk[(size_t)th];
+            for (int64_t e = lo; e < hi; ++e) {
+                const int64_t la = (int64_t)fm[elems_cm[e]] - r0, lb2 = (int64_t)fm[elems_cm[E + e]] - r0;
+                if ((la >= 0 && la < nb) || (lb2 >= 0 && lb2 < nb)) out.push_back((int32_t)e);
+            }
+        });
+        size_t tot = 0;
+        for (const auto &cvec : chunk) tot += cvec.size();
+        rel.reserve(tot);
+        for (const auto &cvec : chunk) rel.insert(rel.end(), cvec.begin(), cvec.end());   // thread ranges ascend
+        tr.lap("beams with an owned end");
+    }
+    const int64_t nrel = filtered ? (int64_t)rel.size() : E;
     auto scan = [&](int64_t lo, int64_t hi, auto &&visit) {
-        for (int64_t e = 0; e < E; ++e) {
+        for (int64_t j = 0; j < nrel; ++j) {
+            const int64_t e = filtered ? rel[(size_t)j] : j;
             const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
             const int64_t la = fa - r0, lb2 = fb - r0;
             if (fa >= 0 && la >= lo && la < hi) visit(la, e, true, fa, fb);
@@ -478,6 +514,7 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
 void build_solver_format(HostPlan &P, bool half)
 {
     PrepTrace tr;
+    RankShare share(P.world);
     const int64_t nb = P.nb();
     P.sym_half = half;
     P.uptr.assign((size_t)nb + 1, 0);

@@ -217,9 +217,10 @@ def test_internal_renumbering(built):
     assert np.all(np.diff(by_internal) >= 0)
 
 
-@pytest.mark.parametrize("world", [2, 3, 8])
-def test_partition_plan_is_consistent(built, world):
-    job = syn.cubic_lattice(7)
+@pytest.mark.parametrize("world,n", [(2, 7), (3, 7), (8, 7), (3, 40)], ids=["w2", "w3", "w8", "w3_threaded"])
+def test_partition_plan_is_consistent(built, world, n):
+    """(n = 40: large enough for the multi-threaded host passes and the owned-beam filter of world > 1.)"""
+    job = syn.cubic_lattice(n)
     V = job.nodes.shape[0]
     full = mb.plan_partition(V, job.elements, job.fixedNodes, 0, 1)
     plans = [mb.plan_partition(V, job.elements, job.fixedNodes, r, world) for r in range(world)]
