@@ -335,7 +335,8 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     // pass 1: entries per owned row (diagonal contributions + off-diagonal ones).  Rows are split
     // into one range per thread; every thread scans all beams in ascending order and handles the
     // end points that fall into its range, so each row's entries stay in ascending element order.
-    std::vector<int32_t> cnt((size_t)nb + 1, 0);
+    std::vector<int32_t> &cnt = P.scratch_cnt;
+    cnt.assign((size_t)nb + 1, 0);
     // several ranks: the beams with an owned end point, ascending (found once, in parallel), so that the
     // per-thread scans below cost E / world instead of E
     std::vector<int32_t> rel;
@@ -371,14 +372,18 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
         });
     });
     tr.lap("count pass");
-    std::vector<int64_t> start((size_t)nb + 1, 0);
+    std::vector<int64_t> &start = P.scratch_start;
+    start.resize((size_t)nb + 1);
+    start[0] = 0;
     for (int64_t r = 0; r < nb; ++r) start[r + 1] = start[r] + cnt[r];
     const int64_t nent = start[nb];
     struct Ent { int32_t col; int32_t code; };  // global column, (e<<2)|which
-    std::unique_ptr<Ent[]> ent_store(new Ent[(size_t)nent + 1]);  // uninitialised: first touched by its own thread
-    Ent *const ent = ent_store.get();
+    static_assert(sizeof(Ent) == sizeof(int64_t), "Ent is stored in the int64 scratch");
+    if (P.scratch_ent.size() < (size_t)nent + 1) P.scratch_ent.resize((size_t)nent + 1);
+    Ent *const ent = reinterpret_cast<Ent *>(P.scratch_ent.data());
     {
-        std::vector<int64_t> pos(start.begin(), start.end() - 1);
+        std::vector<int64_t> &pos = P.scratch_pos;
+        pos.assign(start.begin(), start.end() - 1);
         parallel_ranges(nb, 1 << 15, [&](int64_t lo, int64_t hi, int) {
             scan(lo, hi, [&](int64_t lrow, int64_t e, bool first, int64_t fa, int64_t fb) {
                 const int32_t code = (int32_t)(e << 2);
@@ -397,7 +402,8 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     // row exists; the solver reports it as singular.
     // per row: stable sort by column (keeps ascending element order), count blocks
     P.rowptr.assign((size_t)nb + 1, 0);
-    std::vector<int32_t> nblk((size_t)nb, 0);
+    std::vector<int32_t> &nblk = P.scratch_nblk;
+    nblk.assign((size_t)nb, 0);
     parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
         for (int64_t r = lo; r < hi; ++r) {
             Ent *b = ent + start[r], *e2 = ent + start[r + 1];
@@ -424,8 +430,8 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     // every entry of these is overwritten below: resize (no refill when the size is unchanged)
     P.colidx.resize((size_t)nnzb);
     P.diag_idx.resize((size_t)nb);
-    std::unique_ptr<int32_t[]> gcol_store(new int32_t[(size_t)nnzb + 1]);  // global column ids first
-    int32_t *const gcol = gcol_store.get();
+    if (P.scratch_gcol.size() < (size_t)nnzb + 1) P.scratch_gcol.resize((size_t)nnzb + 1);   // global column ids first
+    int32_t *const gcol = P.scratch_gcol.data();
     if (with_contrib) { P.contrib_ptr.resize((size_t)nnzb + 1); P.contrib.resize((size_t)nent); }
     else { P.contrib_ptr.clear(); P.contrib.clear(); }
     parallel_ranges(nb, 1 << 14, [&](int64_t lo, int64_t hi, int) {
