@@ -332,42 +332,57 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     const int32_t *fm = P.free_index.data();
     tr.lap("free map");
 
-    // pass 1: entries per owned row (diagonal contributions + off-diagonal ones).  Rows are split
-    // into one range per thread; every thread scans all beams in ascending order and handles the
-    // end points that fall into its range, so each row's entries stay in ascending element order.
+    // pass 1: entries per owned row (diagonal contributions + off-diagonal ones).  The owned rows are
+    // split into one range per thread.  Every end point that falls into an owned row is first dropped
+    // into the bucket (element chunk, row range) it belongs to -- one parallel sweep over the beams -- and
+    // each row-range thread then walks its buckets in chunk order, i.e. in ascending element order, so
+    // each row's entries stay in the order Eigen's setFromTriplets would sum them.  O(E) work in total
+    // (O(E / world) after the sweep on several ranks) instead of one full scan of the beams per thread.
     std::vector<int32_t> &cnt = P.scratch_cnt;
     cnt.assign((size_t)nb + 1, 0);
-    // several ranks: the beams with an owned end point, ascending (found once, in parallel), so that the
-    // per-thread scans below cost E / world instead of E
-    std::vector<int32_t> rel;
-    const bool filtered = world > 1 && E <= INT32_MAX;
-    if (filtered) {
-        std::vector<std::vector<int32_t>> chunk(64);
-        parallel_ranges(E, 1 << 16, [&](int64_t lo, int64_t hi, int th) {
-            std::vector<int32_t> &out = chunk[(size_t)th];
-            for (int64_t e = lo; e < hi; ++e) {
-                const int64_t la = (int64_t)fm[elems_cm[e]] - r0, lb2 = (int64_t)fm[elems_cm[E + e]] - r0;
-                if ((la >= 0 && la < nb) || (lb2 >= 0 && lb2 < nb)) out.push_back((int32_t)e);
-            }
-        });
-        size_t tot = 0;
-        for (const auto &cvec : chunk) tot += cvec.size();
-        rel.reserve(tot);
-        for (const auto &cvec : chunk) rel.insert(rel.end(), cvec.begin(), cvec.end());   // thread ranges ascend
-        tr.lap("beams with an owned end");
-    }
-    const int64_t nrel = filtered ? (int64_t)rel.size() : E;
-    auto scan = [&](int64_t lo, int64_t hi, auto &&visit) {
-        for (int64_t j = 0; j < nrel; ++j) {
-            const int64_t e = filtered ? rel[(size_t)j] : j;
-            const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
-            const int64_t la = fa - r0, lb2 = fb - r0;
-            if (fa >= 0 && la >= lo && la < hi) visit(la, e, true, fa, fb);
-            if (fb >= 0 && lb2 >= lo && lb2 < hi) visit(lb2, e, false, fa, fb);
-        }
+    const int64_t n_ranges = std::max<int64_t>(1, std::min<int64_t>(host_threads(), nb >> 15));
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(host_threads(), E >> 16));
+    int64_t bound[34];   // row range t = [bound[t], bound[t + 1])
+    for (int64_t t = 0; t <= n_ranges; ++t) bound[t] = nb * t / n_ranges;
+    const double to_range = (double)n_ranges / (double)std::max<int64_t>(1, nb);
+    auto range_of = [&](int64_t lrow) {   // estimate by multiplication, settle against the bounds
+        int64_t t = std::min<int64_t>(n_ranges - 1, (int64_t)((double)lrow * to_range));
+        while (lrow >= bound[t + 1]) ++t;
+        while (lrow < bound[t]) --t;
+        return t;
     };
-    parallel_ranges(nb, 1 << 15, [&](int64_t lo, int64_t hi, int) {
-        scan(lo, hi, [&](int64_t lrow, int64_t, bool first, int64_t fa, int64_t fb) {
+    std::vector<std::vector<int32_t>> &bucket = P.scratch_bucket;   // (e << 1) | (0: first end, 1: second end)
+    if (bucket.size() < (size_t)(n_chunks * n_ranges)) bucket.resize((size_t)(n_chunks * n_ranges));
+    auto run_threads = [](int64_t n, auto &&body) {
+        if (n == 1) { body((int64_t)0); return; }
+        std::vector<std::thread> th;
+        for (int64_t t = 0; t < n; ++t) th.emplace_back([&body, t] { body(t); });
+        for (auto &x : th) x.join();
+    };
+    run_threads(n_chunks, [&](int64_t ch) {
+        const int64_t lo = E * ch / n_chunks, hi = E * (ch + 1) / n_chunks;
+        std::vector<int32_t> *mine = &bucket[(size_t)(ch * n_ranges)];
+        for (int64_t t = 0; t < n_ranges; ++t) mine[t].clear();   // capacity survives between jobs
+        for (int64_t e = lo; e < hi; ++e) {
+            const int64_t la = (int64_t)fm[elems_cm[e]] - r0, lb2 = (int64_t)fm[elems_cm[E + e]] - r0;
+            if (la >= 0 && la < nb) mine[range_of(la)].push_back((int32_t)(e << 1));
+            if (lb2 >= 0 && lb2 < nb) mine[range_of(lb2)].push_back((int32_t)((e << 1) | 1));
+        }
+    });
+    tr.lap("end points -> buckets");
+    // visit(local row, element, is first end, free row of first end, of second end) for every owned end
+    // point of row range t, ascending in the element index
+    auto scan = [&](int64_t t, auto &&visit) {
+        for (int64_t ch = 0; ch < n_chunks; ++ch)
+            for (const int32_t code : bucket[(size_t)(ch * n_ranges + t)]) {
+                const int64_t e = code >> 1;
+                const int64_t fa = fm[elems_cm[e]], fb = fm[elems_cm[E + e]];
+                if (code & 1) visit(fb - r0, e, false, fa, fb);
+                else visit(fa - r0, e, true, fa, fb);
+            }
+    };
+    run_threads(n_ranges, [&](int64_t t) {
+        scan(t, [&](int64_t lrow, int64_t, bool first, int64_t fa, int64_t fb) {
             cnt[lrow] += ((first ? fb : fa) >= 0) ? 2 : 1;
         });
     });
@@ -384,8 +399,8 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     {
         std::vector<int64_t> &pos = P.scratch_pos;
         pos.assign(start.begin(), start.end() - 1);
-        parallel_ranges(nb, 1 << 15, [&](int64_t lo, int64_t hi, int) {
-            scan(lo, hi, [&](int64_t lrow, int64_t e, bool first, int64_t fa, int64_t fb) {
+        run_threads(n_ranges, [&](int64_t t) {
+            scan(t, [&](int64_t lrow, int64_t e, bool first, int64_t fa, int64_t fb) {
                 const int32_t code = (int32_t)(e << 2);
                 if (first) {
                     ent[pos[lrow]++] = {(int32_t)fa, code | SUB_00};

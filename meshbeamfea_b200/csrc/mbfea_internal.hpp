@@ -48,6 +48,7 @@ struct HostPlan {
     // build_plan scratch, kept between jobs: re-submitting a mesh of the same size then touches no fresh pages
     std::vector<int64_t> scratch_ent, scratch_start, scratch_pos;
     std::vector<int32_t> scratch_gcol, scratch_cnt, scratch_nblk;
+    std::vector<std::vector<int32_t>> scratch_bucket;   // owned end points per (element chunk, row range)
     bool balanced = false;   // pairs oriented towards the emptier row instead of the upper one (irregular numberings)
     // Symmetric-half values are stored INTERLEAVED per tile of 32 block rows (sliced ELL): the
     // 16-byte chunk m (0..2) of scalar row i of the k-th stored block of local row lr sits at
