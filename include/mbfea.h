@@ -289,6 +289,14 @@ int mbfea_host_free_map(int64_t V, int64_t F, const int32_t *fixed, int32_t *fre
  *           (identity when the canonical order is kept); *reordered says which.                */
 int mbfea_host_renumber(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                         int32_t mode, int32_t *perm, int32_t *reordered);
+/* contributors: the assembly plan of rank `rank` of `world` -- for block k of the rank's pattern
+ *           (the order of mbfea_plan_partition's colidx) the entries [contrib_ptr[k], contrib_ptr[k+1])
+ *           of contrib are (beam << 2) | sub-block (0: (a,a), 1: (a,b), 2: (b,a), 3: (b,b)) in ascending
+ *           beam order = the order Eigen's setFromTriplets sums duplicates in.  sizes[2] = {blocks,
+ *           entries}; arrays may be NULL (sizes only): contrib_ptr[blocks+1], contrib[entries].   */
+int mbfea_host_contributors(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
+                            int32_t rank, int32_t world, int64_t sizes[2], int32_t *contrib_ptr,
+                            int32_t *contrib);
 /* solver_format: the symmetric-half solver format set_job would build for a one-rank job, in the
  *           INTERNAL numbering (mode as options.reorder; nodes_cm may be NULL unless mode == 3).
  *           sizes[8] = {block rows nb, off-diagonal blocks of the full pattern, stored blocks,

@@ -1568,6 +1568,26 @@ int mbfea_plan_partition(int64_t V, int64_t E, const int32_t *elems_cm, int64_t 
     return MBFEA_OK;
 }
 
+int mbfea_host_contributors(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
+                            int32_t rank, int32_t world, int64_t sizes[2], int32_t *contrib_ptr, int32_t *contrib)
+{
+    if (V <= 0 || E <= 0 || !elems_cm || !sizes || (F > 0 && !fixed) || world < 1 || rank < 0 || rank >= world) return MBFEA_EARG;
+    for (int64_t e = 0; e < 2 * E; ++e)
+        if (elems_cm[e] < 0 || elems_cm[e] >= V) return MBFEA_EPRECOND;
+    for (int64_t i = 0; i < F; ++i)
+        if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
+    HostPlan P;
+    try {
+        build_plan(V, E, elems_cm, F, fixed, rank, world, true, P);
+    } catch (const std::bad_alloc &) {
+        return MBFEA_EARG;
+    }
+    sizes[0] = P.nnzb(); sizes[1] = (int64_t)P.contrib.size();
+    if (contrib_ptr) std::copy(P.contrib_ptr.begin(), P.contrib_ptr.end(), contrib_ptr);
+    if (contrib) std::copy(P.contrib.begin(), P.contrib.end(), contrib);
+    return MBFEA_OK;
+}
+
 // ---- scenario files ------------------------------------------------------------
 int mbfea_load_scenario(mbfea_ctx *c, const char *config_json_path, const char *ply_path_override)
 {

@@ -402,6 +402,25 @@ def host_renumber(V: int, elements: np.ndarray, fixed: np.ndarray, mode: int = 0
     return perm[:n_free], bool(flag.value)
 
 
+def host_contributors(V: int, elements: np.ndarray, fixed: np.ndarray, rank: int = 0, world: int = 1):
+    """Assembly plan of one rank (host only): (contrib_ptr, contrib) per block of the rank's pattern."""
+    lib = L.lib()
+    elements = np.asarray(elements, np.int32).reshape(-1, 2)
+    elems_cm = np.ascontiguousarray(elements.T).ravel()
+    fixed = np.ascontiguousarray(np.asarray(fixed, np.int32).ravel())
+    sizes = np.zeros(2, np.int64)
+    args = (V, elements.shape[0], ptr(elems_cm, _pi32), fixed.size, ptr(fixed, _pi32), rank, world, ptr(sizes, _pi64))
+    rc = lib.mbfea_host_contributors(*args, None, None)
+    if rc != L.OK:
+        _raise(rc, lib.mbfea_status_string(rc).decode())
+    cptr = np.zeros(int(sizes[0]) + 1, np.int32)
+    contrib = np.zeros(max(int(sizes[1]), 1), np.int32)
+    rc = lib.mbfea_host_contributors(*args, ptr(cptr, _pi32), ptr(contrib, _pi32))
+    if rc != L.OK:
+        _raise(rc, lib.mbfea_status_string(rc).decode())
+    return cptr, contrib[:int(sizes[1])]
+
+
 def host_solver_format(nodes: Optional[np.ndarray], elements: np.ndarray, fixed: np.ndarray, V: Optional[int] = None,
                        mode: int = 0) -> dict:
     """The symmetric-half solver format set_job would build for a one-rank job (host only, internal

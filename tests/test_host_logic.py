@@ -253,6 +253,27 @@ def test_partition_plan_is_consistent(built, world, n):
             assert np.array_equal(sent, recv)
 
 
+@pytest.mark.parametrize("world,n", [(2, 9), (3, 40)], ids=["w2", "w3_threaded"])
+def test_partitioned_assembly_plan_equals_the_single_rank_plan(built, world, n):
+    """Every rank's contributor lists (which beams' sub-blocks are summed into a block, in which order)
+    are the single-rank lists of the same rows: K rows are bit-identical for any number of GPUs.  The
+    single-rank lists are ascending in the beam index = the order setFromTriplets sums duplicates in."""
+    job = syn.cubic_lattice(n)
+    V = job.nodes.shape[0]
+    full = mb.plan_partition(V, job.elements, job.fixedNodes, 0, 1)
+    fptr, fcon = mb.host_contributors(V, job.elements, job.fixedNodes)
+    assert fptr[-1] == fcon.size and fptr.size == full["colidx"].size + 1
+    seg = np.repeat(np.arange(fptr.size - 1), np.diff(fptr))
+    same_block = seg[1:] == seg[:-1]
+    assert np.all((fcon[1:] >> 2)[same_block] >= (fcon[:-1] >> 2)[same_block])          # ascending beams per block
+    for r in range(world):
+        p = mb.plan_partition(V, job.elements, job.fixedNodes, r, world)
+        cptr, con = mb.host_contributors(V, job.elements, job.fixedNodes, r, world)
+        k0, k1 = full["rowptr"][p["row_begin"]], full["rowptr"][p["row_end"]]
+        assert np.array_equal(cptr - cptr[0], fptr[k0:k1 + 1] - fptr[k0])
+        assert np.array_equal(con, fcon[fptr[k0]:fptr[k1]])
+
+
 def test_scenario_reader_fixture_and_error_path(built, tmp_path):
     cfg, ply = write_scenario(tmp_path, [0], [[2, 1, 100]])
     job = mb.read_scenario(cfg)
