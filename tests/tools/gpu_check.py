@@ -1,7 +1,7 @@
 """First-contact GPU check: every stage against the oracle, verbose, no early exit."""
 import os, sys, time, traceback
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import meshbeamfea_b200 as mb
 from meshbeamfea_b200 import synthetic as syn

@@ -1,7 +1,7 @@
 """torchrun-able multi-GPU check: partitioned solve vs oracle on a small lattice,
 then a timed strong-scaling run.  Usage (on the GPU box):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29511 scripts/multi_check.py
+      --master-port 29511 tests/tools/multi_check.py
 """
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402

@@ -1,7 +1,7 @@
 """Runs the BASELINE.json configs on one GPU and prints one JSON line per config
 (parity where an oracle answer exists, throughput and solver statistics otherwise).
 
-  python scripts/run_configs.py [1 2 3 3b 4 5]      (default: all)
+  python tests/tools/run_configs.py [1 2 3 3b 4 5]      (default: all)
     1   Models/TwoLineSegments.ply-equivalent fixture, three scenarios (golden vectors)
     2   planar 100x100 grid, cantilever load            (vs the oracle's direct solve)
     3   cubic lattice 100^3
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import meshbeamfea_b200 as mb  # noqa: E402
 from meshbeamfea_b200 import synthetic as syn  # noqa: E402
