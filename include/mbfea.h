@@ -297,17 +297,17 @@ int mbfea_host_renumber(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F
 int mbfea_host_contributors(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                             int32_t rank, int32_t world, int64_t sizes[2], int32_t *contrib_ptr,
                             int32_t *contrib);
-/* solver_format: the symmetric-half solver format set_job would build for a one-rank job, in the
- *           INTERNAL numbering (mode as options.reorder; nodes_cm may be NULL unless mode == 3).
+/* solver_format: the symmetric-half solver format set_job would build on rank `rank` of `world`, in the
+ *           INTERNAL numbering (local block rows; ghost columns have ids >= nb and are always stored) (mode as options.reorder; nodes_cm may be NULL unless mode == 3).
  *           sizes[8] = {block rows nb, off-diagonal blocks of the full pattern, stored blocks,
  *           transposed references, 16-byte units of the interleaved value array, balanced 0/1,
  *           longest stored row, renumbered 0/1}.  Arrays may be NULL (sizes only); otherwise
  *           uptr[nb+1], ucol[stored], lptr[nb+1], lcol[refs], lofs[refs] (16-byte unit of the
  *           referenced block's first chunk), tile_base[ceil(nb/32)+1], perm[nb].               */
 int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
-                             const int32_t *fixed, int32_t mode, int64_t sizes[8], int32_t *uptr,
-                             int32_t *ucol, int32_t *lptr, int32_t *lcol, int32_t *lofs, int32_t *tile_base,
-                             int32_t *perm);
+                             const int32_t *fixed, int32_t mode, int32_t rank, int32_t world, int64_t sizes[8],
+                             int32_t *uptr, int32_t *ucol, int32_t *lptr, int32_t *lcol, int32_t *lofs,
+                             int32_t *tile_base, int32_t *perm);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -111,8 +111,8 @@ SIGNATURES = {
     "mbfea_host_free_map": (C.c_int, [_i64, _i64, _pi32, _pi32, _pi64]),
     "mbfea_host_renumber": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _pi32, _pi32]),
     "mbfea_host_contributors": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _i32, _pi64, _pi32, _pi32]),
-    "mbfea_host_solver_format": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, _i32, _pi64, _pi32, _pi32, _pi32,
-                                           _pi32, _pi32, _pi32, _pi32]),
+    "mbfea_host_solver_format": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, _i32, _i32, _i32, _pi64, _pi32, _pi32,
+                                           _pi32, _pi32, _pi32, _pi32, _pi32]),
 }
 
 

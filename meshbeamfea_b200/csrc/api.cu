@@ -1695,17 +1695,18 @@ int mbfea_host_renumber(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F
 }
 
 int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
-                             const int32_t *fixed, int32_t mode, int64_t sizes[8], int32_t *uptr, int32_t *ucol,
-                             int32_t *lptr, int32_t *lcol, int32_t *lofs, int32_t *tile_base, int32_t *perm)
+                             const int32_t *fixed, int32_t mode, int32_t rank, int32_t world, int64_t sizes[8],
+                             int32_t *uptr, int32_t *ucol, int32_t *lptr, int32_t *lcol, int32_t *lofs,
+                             int32_t *tile_base, int32_t *perm)
 {
-    if (V <= 0 || E <= 0 || !elems_cm || !sizes || (F > 0 && !fixed)) return MBFEA_EARG;
+    if (V <= 0 || E <= 0 || !elems_cm || !sizes || (F > 0 && !fixed) || world < 1 || rank < 0 || rank >= world) return MBFEA_EARG;
     for (int64_t e = 0; e < 2 * E; ++e)
         if (elems_cm[e] < 0 || elems_cm[e] >= V) return MBFEA_EPRECOND;
     for (int64_t i = 0; i < F; ++i)
         if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
     HostPlan P;
     try {
-        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, P, mode == 1 ? 0 : (mode == 2 ? 2 : (mode == 3 ? 3 : 1)), nodes_cm);
+        build_plan(V, E, elems_cm, F, fixed, rank, world, false, P, mode == 1 ? 0 : (mode == 2 ? 2 : (mode == 3 ? 3 : 1)), nodes_cm);
         build_solver_format(P, true);
     } catch (const std::bad_alloc &) {
         return MBFEA_EARG;
@@ -1719,7 +1720,7 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
     if (!P.sym_half) return MBFEA_EARG;   // value array beyond 2^31 units: full rows (not reachable at host-test sizes)
     auto put = [](int32_t *dst, const std::vector<int32_t> &src) { if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(int32_t)); };
     put(uptr, P.uptr); put(ucol, P.ucol); put(lptr, P.lptr); put(lcol, P.lcol); put(lofs, P.lofs); put(tile_base, P.tile_base);
-    if (perm) for (int64_t i = 0; i < nb; ++i) perm[i] = P.perm.empty() ? (int32_t)i : P.perm[(size_t)i];
+    if (perm) for (int64_t i = 0; i < P.nb_global; ++i) perm[i] = P.perm.empty() ? (int32_t)i : P.perm[(size_t)i];
     return MBFEA_OK;
 }
 

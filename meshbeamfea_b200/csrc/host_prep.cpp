@@ -573,6 +573,9 @@ void build_solver_format(HostPlan &P, bool half)
             P.balanced = true;
             own.assign(P.colidx.size(), 1);
             std::vector<int32_t> cnt((size_t)nb, 0), cursor(P.rowptr.begin(), P.rowptr.end() - 1);
+            // a row lists its columns in GLOBAL order: ghosts owned by lower ranks (local ids >= nb) come first
+            for (int64_t r = 0; r < nb; ++r)
+                while (cursor[r] < P.rowptr[r + 1] && P.colidx[cursor[r]] >= nb) ++cursor[r];
             for (int64_t r = 0; r < nb; ++r)
                 for (int32_t k = P.rowptr[r]; k < P.rowptr[r + 1]; ++k) {
                     const int32_t c = P.colidx[k];

@@ -422,9 +422,9 @@ def host_contributors(V: int, elements: np.ndarray, fixed: np.ndarray, rank: int
 
 
 def host_solver_format(nodes: Optional[np.ndarray], elements: np.ndarray, fixed: np.ndarray, V: Optional[int] = None,
-                       mode: int = 0) -> dict:
-    """The symmetric-half solver format set_job would build for a one-rank job (host only, internal
-    numbering): which row stores each pair's block, the transposed references and the tile layout."""
+                       mode: int = 0, rank: int = 0, world: int = 1) -> dict:
+    """The symmetric-half solver format set_job would build on one rank (host only, internal numbering,
+    local block rows): which row stores each pair's block, the transposed references and the tile layout."""
     lib = L.lib()
     elements = np.asarray(elements, np.int32).reshape(-1, 2)
     elems_cm = np.ascontiguousarray(elements.T).ravel()
@@ -436,18 +436,19 @@ def host_solver_format(nodes: Optional[np.ndarray], elements: np.ndarray, fixed:
         nodes_cm = np.ascontiguousarray(nodes.T).ravel()
     sizes = np.zeros(8, np.int64)
     args = (V, elements.shape[0], ptr(nodes_cm, _pd) if nodes_cm is not None else None, ptr(elems_cm, _pi32), fixed.size,
-            ptr(fixed, _pi32), mode, ptr(sizes, _pi64))
+            ptr(fixed, _pi32), mode, rank, world, ptr(sizes, _pi64))
     rc = lib.mbfea_host_solver_format(*args, None, None, None, None, None, None, None)
     if rc != L.OK:
         _raise(rc, lib.mbfea_status_string(rc).decode())
     nb, _, stored, refs = (int(v) for v in sizes[:4])
     out = {k: np.zeros(max(n, 1), np.int32) for k, n in (("uptr", nb + 1), ("ucol", stored), ("lptr", nb + 1), ("lcol", refs),
-                                                          ("lofs", refs), ("tile_base", (nb + 31) // 32 + 1), ("perm", nb))}
+                                                          ("lofs", refs), ("tile_base", (nb + 31) // 32 + 1),
+                                                          ("perm", V - np.unique(fixed).size))}
     rc = lib.mbfea_host_solver_format(*args, *(ptr(out[k], _pi32) for k in ("uptr", "ucol", "lptr", "lcol", "lofs", "tile_base", "perm")))
     if rc != L.OK:
         _raise(rc, lib.mbfea_status_string(rc).decode())
     out = {"uptr": out["uptr"][:nb + 1], "ucol": out["ucol"][:stored], "lptr": out["lptr"][:nb + 1], "lcol": out["lcol"][:refs],
-           "lofs": out["lofs"][:refs], "tile_base": out["tile_base"][:(nb + 31) // 32 + 1], "perm": out["perm"][:nb]}
+           "lofs": out["lofs"][:refs], "tile_base": out["tile_base"][:(nb + 31) // 32 + 1], "perm": out["perm"]}
     out.update(n_block_rows=nb, n_offdiag=int(sizes[1]), n_stored=stored, n_refs=refs, value_units=int(sizes[4]),
                balanced=bool(sizes[5]), longest_row=int(sizes[6]), renumbered=bool(sizes[7]))
     return out

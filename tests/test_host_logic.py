@@ -430,3 +430,44 @@ def test_solver_format_balanced_on_irregular_numbering(mode):
     fmt = mb.host_solver_format(nodes, elements, fixed, mode=mode)
     assert fmt["balanced"]
     assert _check_solver_format(fmt, elements, fixed, nodes.shape[0]) < 1.25   # upper rule: 1.36-1.45 on this mesh
+
+
+@pytest.mark.parametrize("mode", [2, 3], ids=["breadth_first", "morton"])
+def test_solver_format_on_every_rank_of_a_partition(built, mode):
+    """Several ranks, irregular numbering: a rank's rows list ghost columns of lower ranks FIRST (global column
+    order), which the pair orientation must skip.  Per rank: every local pair is stored exactly once and
+    referenced from its other row, ghost columns are always stored, references point at the stored block."""
+    nodes, elements, fixed = _shuffled(syn.gridshell(60), 11)   # balanced orientation on ranks 1 and 2 in both modes
+    V = nodes.shape[0]
+    world = 3
+    saw_balanced = False
+    for rank in range(world):
+        fmt = mb.host_solver_format(nodes, elements, fixed, mode=mode, rank=rank, world=world)
+        nb = fmt["n_block_rows"]
+        uptr, ucol, lptr, lcol, lofs, tb = (fmt[k].astype(np.int64) for k in ("uptr", "ucol", "lptr", "lcol", "lofs", "tile_base"))
+        urow = np.repeat(np.arange(nb), np.diff(uptr)); lrow = np.repeat(np.arange(nb), np.diff(lptr))
+        # the rank's rows of the (internally renumbered) reduced pattern, from the beams
+        isfixed = np.zeros(V, bool); isfixed[fixed] = True
+        fc = np.full(V, -1, np.int64); fc[~isfixed] = np.arange((~isfixed).sum())
+        nbg = fmt["perm"].size
+        r0 = nbg * rank // world
+        assert nb == nbg * (rank + 1) // world - r0
+        a, b = fc[elements[:, 0]], fc[elements[:, 1]]
+        m = (a >= 0) & (b >= 0) & (a != b)
+        ga, gb = fmt["perm"][a[m]].astype(np.int64), fmt["perm"][b[m]].astype(np.int64)
+        own_a, own_b = (ga >= r0) & (ga < r0 + nb), (gb >= r0) & (gb < r0 + nb)
+        local = own_a & own_b
+        pairs = np.unique(np.minimum(ga[local], gb[local]) * nbg + np.maximum(ga[local], gb[local]))
+        ghost_entries = np.unique(np.concatenate([ga[own_a & ~own_b] * nbg + gb[own_a & ~own_b],
+                                                  gb[own_b & ~own_a] * nbg + ga[own_b & ~own_a]]))
+        is_ghost = ucol >= nb
+        assert is_ghost.sum() == ghost_entries.size                       # every (owned row, foreign column) stored here
+        lu, lc = urow[~is_ghost] + r0, ucol[~is_ghost] + r0
+        assert np.array_equal(np.sort(np.minimum(lu, lc) * nbg + np.maximum(lu, lc)), pairs)   # each local pair once
+        assert np.array_equal(np.sort((lrow + r0) * nbg + lcol + r0), np.sort(lc * nbg + lu))    # refs = their transposes
+        slot = np.arange(ucol.size) - uptr[urow]
+        first_chunk = tb[urow // 32] + slot * 576 + (urow % 32) * 6
+        where = {(int(r), int(c)): int(u) for r, c, u in zip(urow, ucol, first_chunk)}
+        assert all(where[(int(c), int(r))] == int(o) for r, c, o in zip(lrow, lcol, lofs))
+        saw_balanced |= bool(fmt["balanced"]) and rank > 0
+    assert saw_balanced
