@@ -1594,7 +1594,11 @@ int mbfea_load_scenario(mbfea_ctx *c, const char *config_json_path, const char *
     if (!c || !config_json_path) return MBFEA_EARG;
     Scenario sc;
     std::string msg;
-    if (int rc = load_scenario_files(config_json_path, ply_path_override, sc, msg)) return fail(c, rc, msg);
+    try {
+        if (int rc = load_scenario_files(config_json_path, ply_path_override, sc, msg)) return fail(c, rc, msg);
+    } catch (const std::exception &e) {   // e.g. bad_alloc: nothing may unwind through the C ABI
+        return fail(c, MBFEA_EIO, std::string("scenario reader: ") + e.what());
+    }
     return mbfea_set_job(c, sc.V, sc.E, sc.nodes_cm.data(), sc.elems_cm.data(), sc.normals_cm.data(),
                          sc.dims_bh.data(), sc.mat_nuE.data(), (int64_t)sc.fixed.size(), sc.fixed.data(),
                          (int64_t)sc.f_node.size(), sc.f_node.data(), sc.f_dof.data(), sc.f_mag.data());
@@ -1610,7 +1614,12 @@ int mbfea_scenario_open(const char *config_json_path, const char *ply_path_overr
     std::unique_ptr<mbfea_scenario> h(new (std::nothrow) mbfea_scenario);
     if (!h) return MBFEA_EARG;
     std::string msg;
-    const int rc = load_scenario_files(config_json_path, ply_path_override, h->sc, msg);
+    int rc;
+    try {
+        rc = load_scenario_files(config_json_path, ply_path_override, h->sc, msg);
+    } catch (const std::exception &e) {   // e.g. bad_alloc: nothing may unwind through the C ABI
+        rc = MBFEA_EIO; msg = std::string("scenario reader: ") + e.what();
+    }
     if (errbuf && errbuf_len > 0) std::snprintf(errbuf, (size_t)errbuf_len, "%s", msg.c_str());
     if (rc != MBFEA_OK) return rc;
     *out = h.release();

@@ -7,7 +7,9 @@
 // a dependency-free reader for exactly that schema.  Pure C++17, no CUDA.
 #include <cctype>
 #include <cerrno>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -70,8 +72,16 @@ struct JParser {
         ++i;
         return true;
     }
+    int depth = 0;
+    struct Nest {   // bounded nesting: a hostile file must not overflow the stack
+        int &d;
+        explicit Nest(int &dd) : d(dd) { ++d; }
+        ~Nest() { --d; }
+    };
     bool parse(JVal &v)
     {
+        Nest nest(depth);
+        if (depth > 64) return fail("nesting too deep");
         ws();
         if (i >= s.size()) return fail("unexpected end");
         const char ch = s[i];
@@ -141,6 +151,8 @@ struct PlyElem {
     std::vector<PlyProp> props;
 };
 
+constexpr long kMaxListLen = 1 << 16;   // the reference's lists hold 2 or 3 values (count type uchar)
+
 bool is_float_type(const std::string &t) { return t == "float" || t == "float32"; }
 
 // ASCII token -> value of the declared PLY type, widened to double
@@ -159,6 +171,11 @@ int load_ply_edge_mesh(const char *ply_path, Scenario &sc, std::string &msg)
 {
     std::ifstream in(ply_path);
     if (!in) { msg = std::string("Error: Unable to open ") + ply_path; return MBFEA_EIO; }
+    // every element row takes at least two bytes of text: a declared count beyond the file size is a
+    // corrupt header, not a reason to allocate
+    in.seekg(0, std::ios::end);
+    const int64_t file_bytes = (int64_t)in.tellg();
+    in.seekg(0, std::ios::beg);
     std::string line;
     if (!std::getline(in, line) || line.substr(0, 3) != "ply") { msg = "not a PLY file"; return MBFEA_EIO; }
     std::vector<PlyElem> elems;
@@ -173,7 +190,10 @@ int load_ply_edge_mesh(const char *ply_path, Scenario &sc, std::string &msg)
             ascii = (f == "ascii");
         } else if (kw == "element") {
             PlyElem el;
-            ls >> el.name >> el.count;
+            if (!(ls >> el.name >> el.count) || el.count < 0 || el.count > file_bytes) {
+                msg = "PLY: bad element count in '" + line + "'";
+                return MBFEA_EIO;
+            }
             elems.push_back(el);
         } else if (kw == "property") {
             if (elems.empty()) { msg = "PLY property before any element"; return MBFEA_EIO; }
@@ -204,6 +224,7 @@ int load_ply_edge_mesh(const char *ply_path, Scenario &sc, std::string &msg)
                     if (p.is_list) {
                         if (!next_token(tok)) { msg = "PLY truncated (vertex list)"; return MBFEA_EIO; }
                         const long n = std::strtol(tok.c_str(), nullptr, 10);
+                        if (n < 0 || n > kMaxListLen) { msg = "PLY: bad list length '" + tok + "'"; return MBFEA_EIO; }
                         for (long k = 0; k < n; ++k) if (!next_token(tok)) { msg = "PLY truncated"; return MBFEA_EIO; }
                         continue;
                     }
@@ -232,14 +253,20 @@ int load_ply_edge_mesh(const char *ply_path, Scenario &sc, std::string &msg)
                     bool ok = false;
                     if (!p.is_list) {
                         if (!next_token(tok)) { msg = "PLY truncated (edges)"; return MBFEA_EIO; }
-                        const long idx = std::strtol(tok.c_str(), nullptr, 10);
+                        char *end = nullptr;
+                        const long long idx = std::strtoll(tok.c_str(), &end, 10);
+                        if (end == tok.c_str() || idx < INT32_MIN || idx > INT32_MAX) {   // no silent wrap into range
+                            msg = "PLY: bad vertex index '" + tok + "'";
+                            return MBFEA_EIO;
+                        }
                         if (p.name == "vertex1") sc.elems_cm[(size_t)e] = (int32_t)idx;
                         else if (p.name == "vertex2") sc.elems_cm[(size_t)(E + e)] = (int32_t)idx;
                         continue;
                     }
                     if (!next_token(tok)) { msg = "PLY truncated (edge list)"; return MBFEA_EIO; }
                     const long n = std::strtol(tok.c_str(), nullptr, 10);
-                    std::vector<double> vals((size_t)std::max(0L, n));
+                    if (n < 0 || n > kMaxListLen) { msg = "PLY: bad list length '" + tok + "'"; return MBFEA_EIO; }
+                    std::vector<double> vals((size_t)n);
                     for (long k = 0; k < n; ++k) {
                         if (!next_token(tok)) { msg = "PLY truncated (edge list values)"; return MBFEA_EIO; }
                         vals[(size_t)k] = typed_value(tok, p.type, ok);
@@ -266,6 +293,7 @@ int load_ply_edge_mesh(const char *ply_path, Scenario &sc, std::string &msg)
                     if (!next_token(tok)) { msg = "PLY truncated"; return MBFEA_EIO; }
                     if (p.is_list) {
                         const long n = std::strtol(tok.c_str(), nullptr, 10);
+                        if (n < 0 || n > kMaxListLen) { msg = "PLY: bad list length '" + tok + "'"; return MBFEA_EIO; }
                         for (long k = 0; k < n; ++k) if (!next_token(tok)) { msg = "PLY truncated"; return MBFEA_EIO; }
                     }
                 }
@@ -300,7 +328,10 @@ int load_scenario_files(const char *json_path, const char *ply_override, Scenari
     if (fv != root.obj.end()) {
         if (fv->second.kind != JVal::Arr) { msg = "config.json: fixedVertices must be an array"; return MBFEA_EIO; }
         for (const JVal &v : fv->second.arr) {
-            if (v.kind != JVal::Num) { msg = "config.json: fixedVertices entries must be integers"; return MBFEA_EIO; }
+            if (v.kind != JVal::Num || !(std::fabs(v.num) <= (double)INT32_MAX)) {   // also rejects NaN
+                msg = "config.json: fixedVertices entries must be integers";
+                return MBFEA_EIO;
+            }
             sc.fixed.push_back((int32_t)v.num);
         }
     }
@@ -308,7 +339,11 @@ int load_scenario_files(const char *json_path, const char *ply_override, Scenari
     if (fo != root.obj.end()) {
         if (fo->second.kind != JVal::Arr) { msg = "config.json: forces must be an array"; return MBFEA_EIO; }
         for (const JVal &v : fo->second.arr) {
-            if (v.kind != JVal::Arr || v.arr.size() < 3) { msg = "config.json: a force is [node, dof, magnitude]"; return MBFEA_EIO; }
+            if (v.kind != JVal::Arr || v.arr.size() < 3 || v.arr[0].kind != JVal::Num || v.arr[1].kind != JVal::Num ||
+                v.arr[2].kind != JVal::Num || !(std::fabs(v.arr[0].num) < 9.0e18) || !(std::fabs(v.arr[1].num) < 9.0e18)) {
+                msg = "config.json: a force is [node, dof, magnitude]";
+                return MBFEA_EIO;
+            }
             const int64_t node = (int64_t)v.arr[0].num, dof = (int64_t)v.arr[1].num;
             const double mag = v.arr[2].num;
             // Expects(nf.dof >= 0 && nf.dof < 6 && nf.index >= 0 && nf.magnitude >= 0) [REF :77]

@@ -300,6 +300,41 @@ def test_scenario_reader_fixture_and_error_path(built, tmp_path):
         mb.read_scenario(cfg4)
 
 
+def test_scenario_reader_rejects_corrupt_files(built, tmp_path):
+    """Hostile or truncated inputs end in an IO error, never in a huge allocation, a wrapped index or a crash
+    (the readers were fuzzed under AddressSanitizer / UBSan; these are the cases that needed a guard)."""
+    from helpers import PLY_TWO_SEGMENTS
+    bad_plys = {
+        "huge_count": PLY_TWO_SEGMENTS.replace("element vertex 3", "element vertex 99999999999999"),
+        "negative_count": PLY_TWO_SEGMENTS.replace("element edge 2", "element edge -2"),
+        "no_count": PLY_TWO_SEGMENTS.replace("element edge 2", "element edge"),
+        "huge_list": PLY_TWO_SEGMENTS.replace("0 1 3 0.0 1.0 0.0", "0 1 4000000000 0.0 1.0 0.0"),
+        "index_wraps_int32": PLY_TWO_SEGMENTS.replace("1 2 3 0.0", "4294967297 2 3 0.0"),
+        "truncated": PLY_TWO_SEGMENTS[:-20],
+        "bad_number": PLY_TWO_SEGMENTS.replace("2 0 0", "2 zero 0"),
+    }
+    for name, text in bad_plys.items():
+        cfg, _ = write_scenario(tmp_path, [0], [[2, 1, 100]], ply_text=text, ply_name=name + ".ply")
+        with pytest.raises(OSError):
+            mb.read_scenario(cfg)
+    _, ply = write_scenario(tmp_path, [0], [[2, 1, 100]])
+    bad_json = {
+        "deep_nesting": "[" * 100000,
+        "fixed_not_integer": '{"plyFilename": "%s", "fixedVertices": [1e300], "forces": []}' % ply,
+        "fixed_nan_like": '{"plyFilename": "%s", "fixedVertices": ["0"], "forces": []}' % ply,
+        "force_not_numbers": '{"plyFilename": "%s", "fixedVertices": [0], "forces": [["a", 1, 2]]}' % ply,
+        "force_node_huge": '{"plyFilename": "%s", "fixedVertices": [0], "forces": [[1e30, 1, 2]]}' % ply,
+        "not_an_object": "[1, 2, 3]",
+        "unterminated": '{"plyFilename": "%s", "fixedVertices": [0' % ply,
+    }
+    for name, text in bad_json.items():
+        path = os.path.join(str(tmp_path), name + ".json")
+        with open(path, "w") as f:
+            f.write(text)
+        with pytest.raises(OSError):
+            mb.read_scenario(path)
+
+
 def test_ply_reader_defaults_and_double_types(built, tmp_path):
     ply = """ply
 format ascii 1.0
