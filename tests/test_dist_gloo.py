@@ -108,3 +108,19 @@ def test_partitioned_pcg_matches_single_rank(built, tmp_path, world):
     it, its = np.load(os.path.join(str(tmp_path), "its.npy"))
     assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-9
     assert abs(int(it) - int(its)) <= 3  # same Krylov process, partial sums regrouped
+
+
+def test_mailbox_protocol_simulation(tmp_path):
+    """Protocol-level model of the NVLink peer-memory CG exchange (csrc/kernels.cu: Mailbox::ll with slots
+    double-buffered by iteration parity, flag = epoch | iteration; neighbour halo tags): 8 ranks as host
+    threads with random delays; every value a rank consumes must be the one its peer published for that
+    iteration.  (With a single slot per rank the same model deadlocks -- the hang seen on 4 GPUs.)"""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = os.path.join(str(tmp_path), "mailbox_sim")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mailbox_protocol_sim.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", src, "-o", exe, "-lpthread"], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
+    assert "0 inconsistencies" in out
