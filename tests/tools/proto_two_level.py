@@ -46,7 +46,16 @@ bj = lambda r: np.einsum("rij,rj->ri", Dinv, r.reshape(nb, 6)).ravel()
 
 # aggregates: bricks of `agg` vertices per axis of the bounding box grid (mean spacing from the mesh)
 h = np.median(np.linalg.norm(O.nodes[O.elements[:, 0]] - O.nodes[O.elements[:, 1]], axis=1))
-cell = np.floor((X - X.min(0)) / (h * agg) + 1e-9).astype(np.int64)
+if agg > 0:
+    cell = np.floor((X - X.min(0)) / (h * agg) + 1e-9).astype(np.int64)
+else:
+    # agg = -N: a fixed budget of about N aggregates, bricks of the bounding box with near-cubic cells
+    ext = np.maximum(X.max(0) - X.min(0), 1e-12)
+    live = ext > 1e-3 * ext.max()
+    side = (np.prod(ext[live]) / (-agg)) ** (1.0 / live.sum())
+    counts = np.where(live, np.maximum(1, np.round(ext / side)), 1).astype(np.int64)
+    cell = np.minimum((np.floor((X - X.min(0)) / ext * counts)).astype(np.int64), counts - 1)
+    print("aggregate grid", counts)
 _, aid = np.unique(cell, axis=0, return_inverse=True)
 aid = aid.ravel(); na = aid.max() + 1
 cent = np.zeros((na, 3)); np.add.at(cent, aid, X); cent /= np.bincount(aid)[:, None]
