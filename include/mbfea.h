@@ -309,6 +309,27 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
                              int32_t *uptr, int32_t *ucol, int32_t *lptr, int32_t *lcol, int32_t *lofs,
                              int32_t *tile_base, int32_t *perm);
 
+/* hierarchy: host half of the multilevel (rigid-body aggregate) preconditioner that is the next
+ *           widening of the solver -- NOT used by mbfea_solve yet.  Builds, for a
+ *           one-rank job in the canonical reduced numbering, the chain of coarse levels: aggregates =
+ *           bricks of edge cell0 * ratio^l over the free vertices' bounding box, 6 rigid-body degrees of
+ *           freedom each.  cell0 <= 0 selects 4 x the mean beam length.
+ *  levels  : number of coarse levels built (0: nothing to coarsen).
+ *  sizes[6] of coarse level l (0-based): {fine rows, coarse rows, coarse blocks, fine blocks, 0, 0}.
+ *  copy    : agg[fine rows], off[3 * fine rows] (fine position - aggregate centroid, x y z per row),
+ *            rowptr[coarse rows + 1], colidx[coarse blocks], gal_ptr[coarse blocks + 1],
+ *            gal_src[fine blocks] (indices into the finer level's block pattern, ascending per coarse
+ *            block; level 0's finer pattern is mbfea_plan_partition's with world = 1).  Any may be NULL. */
+typedef struct mbfea_hierarchy mbfea_hierarchy;
+int mbfea_hierarchy_open(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
+                         const int32_t *fixed, double cell0, double ratio, int32_t max_levels,
+                         int64_t coarsest_rows, mbfea_hierarchy **out);
+int mbfea_hierarchy_levels(const mbfea_hierarchy *h);
+int mbfea_hierarchy_sizes(const mbfea_hierarchy *h, int32_t level, int64_t sizes[6]);
+int mbfea_hierarchy_copy(const mbfea_hierarchy *h, int32_t level, int32_t *agg, double *off, int32_t *rowptr,
+                         int32_t *colidx, int32_t *gal_ptr, int32_t *gal_src);
+void mbfea_hierarchy_close(mbfea_hierarchy *h);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

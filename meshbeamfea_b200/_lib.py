@@ -111,6 +111,12 @@ SIGNATURES = {
     "mbfea_host_free_map": (C.c_int, [_i64, _i64, _pi32, _pi32, _pi64]),
     "mbfea_host_renumber": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _pi32, _pi32]),
     "mbfea_host_contributors": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _i32, _pi64, _pi32, _pi32]),
+    "mbfea_hierarchy_open": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, C.c_double, C.c_double, _i32, _i64,
+                                       C.POINTER(C.c_void_p)]),
+    "mbfea_hierarchy_levels": (C.c_int, [C.c_void_p]),
+    "mbfea_hierarchy_sizes": (C.c_int, [C.c_void_p, _i32, _pi64]),
+    "mbfea_hierarchy_copy": (C.c_int, [C.c_void_p, _i32, _pi32, _pd, _pi32, _pi32, _pi32, _pi32]),
+    "mbfea_hierarchy_close": (None, [C.c_void_p]),
     "mbfea_host_solver_format": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, _i32, _i32, _i32, _pi64, _pi32, _pi32,
                                            _pi32, _pi32, _pi32, _pi32, _pi32]),
 }

@@ -1733,4 +1733,73 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
     return MBFEA_OK;
 }
 
+struct mbfea_hierarchy { Hierarchy H; };
+
+int mbfea_hierarchy_open(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
+                         const int32_t *fixed, double cell0, double ratio, int32_t max_levels,
+                         int64_t coarsest_rows, mbfea_hierarchy **out)
+{
+    if (V <= 0 || E <= 0 || !nodes_cm || !elems_cm || !out || (F > 0 && !fixed) || max_levels < 1 || !(ratio > 1.0)) return MBFEA_EARG;
+    *out = nullptr;
+    for (int64_t e = 0; e < 2 * E; ++e)
+        if (elems_cm[e] < 0 || elems_cm[e] >= V) return MBFEA_EPRECOND;
+    for (int64_t i = 0; i < F; ++i)
+        if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
+    try {
+        HostPlan P;
+        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, P);
+        const int64_t nb = P.nb();
+        std::vector<double> pos((size_t)3 * std::max<int64_t>(nb, 1));
+        for (int64_t v = 0; v < V; ++v)
+            if (P.free_index[(size_t)v] >= 0)
+                for (int a = 0; a < 3; ++a) pos[(size_t)3 * P.free_index[(size_t)v] + a] = nodes_cm[(size_t)a * V + v];
+        if (!(cell0 > 0.0)) {   // 4 x the mean beam length
+            double sum = 0.0;
+            for (int64_t e = 0; e < E; ++e) {
+                double d2 = 0.0;
+                for (int a = 0; a < 3; ++a) {
+                    const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                    d2 += d * d;
+                }
+                sum += std::sqrt(d2);
+            }
+            cell0 = 4.0 * sum / (double)E;
+        }
+        std::unique_ptr<mbfea_hierarchy> h(new mbfea_hierarchy);
+        if (cell0 > 0.0)
+            build_hierarchy(nb, P.rowptr.data(), P.colidx.data(), pos.data(), cell0, ratio, max_levels, coarsest_rows, h->H);
+        *out = h.release();
+    } catch (const std::bad_alloc &) {
+        return MBFEA_EARG;
+    }
+    return MBFEA_OK;
+}
+
+int mbfea_hierarchy_levels(const mbfea_hierarchy *h) { return h ? (int)h->H.levels.size() : 0; }
+
+int mbfea_hierarchy_sizes(const mbfea_hierarchy *h, int32_t level, int64_t sizes[6])
+{
+    if (!h || !sizes || level < 0 || level >= (int32_t)h->H.levels.size()) return MBFEA_EARG;
+    const HierLevel &L = h->H.levels[(size_t)level];
+    sizes[0] = L.n_fine; sizes[1] = L.n_coarse; sizes[2] = (int64_t)L.colidx.size(); sizes[3] = (int64_t)L.gal_src.size();
+    sizes[4] = sizes[5] = 0;
+    return MBFEA_OK;
+}
+
+int mbfea_hierarchy_copy(const mbfea_hierarchy *h, int32_t level, int32_t *agg, double *off, int32_t *rowptr,
+                         int32_t *colidx, int32_t *gal_ptr, int32_t *gal_src)
+{
+    if (!h || level < 0 || level >= (int32_t)h->H.levels.size()) return MBFEA_EARG;
+    const HierLevel &L = h->H.levels[(size_t)level];
+    if (agg) std::copy(L.agg.begin(), L.agg.end(), agg);
+    if (off) std::copy(L.off.begin(), L.off.end(), off);
+    if (rowptr) std::copy(L.rowptr.begin(), L.rowptr.end(), rowptr);
+    if (colidx) std::copy(L.colidx.begin(), L.colidx.end(), colidx);
+    if (gal_ptr) std::copy(L.gal_ptr.begin(), L.gal_ptr.end(), gal_ptr);
+    if (gal_src) std::copy(L.gal_src.begin(), L.gal_src.end(), gal_src);
+    return MBFEA_OK;
+}
+
+void mbfea_hierarchy_close(mbfea_hierarchy *h) { delete h; }
+
 }  // extern "C"

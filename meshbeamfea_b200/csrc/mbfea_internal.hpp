@@ -107,6 +107,24 @@ void find_components(HostPlan &plan, int32_t max_rows, int32_t min_components);
 void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
                  std::vector<int32_t> &tile_row);
 
+// ---------------------------------------------------------------------------
+// Aggregate hierarchy for the multilevel preconditioner (host half, see hierarchy.cpp)
+// ---------------------------------------------------------------------------
+struct HierLevel {
+    int64_t n_fine = 0, n_coarse = 0;
+    std::vector<int32_t> agg;                 // n_fine: aggregate (= coarse block row) of each fine row
+    std::vector<double> off;                  // 3 * n_fine: fine position minus the centroid of its aggregate
+    std::vector<double> centroid;             // 3 * n_coarse: positions of the coarse rows
+    std::vector<int32_t> agg_ptr, agg_rows;   // member rows of each aggregate, ascending
+    std::vector<int32_t> rowptr, colidx;      // coarse 6x6-block pattern (columns ascending, diagonal present)
+    std::vector<int32_t> gal_ptr, gal_src;    // per coarse block: the fine blocks summed into it, ascending
+};
+struct Hierarchy { std::vector<HierLevel> levels; };
+// nb block rows with pattern (rowptr, colidx < nb) and positions pos_rm[3 * row]; level l bricks have edge
+// cell0 * ratio^l; stops at max_levels levels (counting the fine one) or once a level has <= coarsest_rows rows.
+void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
+                     double ratio, int max_levels, int64_t coarsest_rows, Hierarchy &H);
+
 // Scenario files (config.json + ASCII PLY).
 struct Scenario {
     int64_t V = 0, E = 0;

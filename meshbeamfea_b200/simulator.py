@@ -421,6 +421,40 @@ def host_contributors(V: int, elements: np.ndarray, fixed: np.ndarray, rank: int
     return cptr, contrib[:int(sizes[1])]
 
 
+def host_hierarchy(nodes: np.ndarray, elements: np.ndarray, fixed: np.ndarray, cell0: float = 0.0, ratio: float = 2.0,
+                   max_levels: int = 8, coarsest_rows: int = 128) -> list:
+    """Aggregate hierarchy of the multilevel preconditioner (host half of SURVEY 8(f) rank 4; not used by the
+    solver yet): one dict per coarse level with agg, off, rowptr, colidx, gal_ptr, gal_src."""
+    lib = L.lib()
+    nodes = np.asarray(nodes, np.float64).reshape(-1, 3)
+    elements = np.asarray(elements, np.int32).reshape(-1, 2)
+    V = nodes.shape[0]
+    nodes_cm = np.ascontiguousarray(nodes.T).ravel()
+    elems_cm = np.ascontiguousarray(elements.T).ravel()
+    fixed = np.ascontiguousarray(np.asarray(fixed, np.int32).ravel())
+    h = C.c_void_p()
+    rc = lib.mbfea_hierarchy_open(V, elements.shape[0], ptr(nodes_cm, _pd), ptr(elems_cm, _pi32), fixed.size,
+                                  ptr(fixed, _pi32), cell0, ratio, max_levels, coarsest_rows, C.byref(h))
+    if rc != L.OK:
+        _raise(rc, lib.mbfea_status_string(rc).decode())
+    try:
+        out = []
+        for lvl in range(lib.mbfea_hierarchy_levels(h)):
+            sz = np.zeros(6, np.int64)
+            lib.mbfea_hierarchy_sizes(h, lvl, ptr(sz, _pi64))
+            nf, nc, bc, bf = (int(v) for v in sz[:4])
+            d = dict(agg=np.zeros(nf, np.int32), off=np.zeros(3 * nf), rowptr=np.zeros(nc + 1, np.int32),
+                     colidx=np.zeros(bc, np.int32), gal_ptr=np.zeros(bc + 1, np.int32), gal_src=np.zeros(bf, np.int32))
+            lib.mbfea_hierarchy_copy(h, lvl, ptr(d["agg"], _pi32), ptr(d["off"], _pd), ptr(d["rowptr"], _pi32),
+                                     ptr(d["colidx"], _pi32), ptr(d["gal_ptr"], _pi32), ptr(d["gal_src"], _pi32))
+            d["off"] = d["off"].reshape(nf, 3)
+            d.update(n_fine=nf, n_coarse=nc)
+            out.append(d)
+        return out
+    finally:
+        lib.mbfea_hierarchy_close(h)
+
+
 def host_solver_format(nodes: Optional[np.ndarray], elements: np.ndarray, fixed: np.ndarray, V: Optional[int] = None,
                        mode: int = 0, rank: int = 0, world: int = 1) -> dict:
     """The symmetric-half solver format set_job would build on one rank (host only, internal numbering,

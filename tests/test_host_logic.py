@@ -506,3 +506,60 @@ def test_solver_format_on_every_rank_of_a_partition(built, mode):
         assert all(where[(int(c), int(r))] == int(o) for r, c, o in zip(lrow, lcol, lofs))
         saw_balanced |= bool(fmt["balanced"]) and rank > 0
     assert saw_balanced
+
+
+@pytest.mark.parametrize("mesh", ["lattice", "gridshell"])
+def test_aggregate_hierarchy_matches_galerkin_products(built, mesh):
+    """Host half of the multilevel preconditioner: for every level the coarse pattern
+    is the pattern of P^T A P and the Galerkin contributor lists reproduce its values, with
+    P = rigid-body modes of the brick aggregates (built independently with scipy from agg / off)."""
+    import scipy.sparse as sp
+    job = syn.cubic_lattice(12) if mesh == "lattice" else syn.gridshell(30)
+    O = to_oracle(job)
+    V = O.nodes.shape[0]
+    fm = orc.free_map(V, O.fixed)
+    rp, col = orc.bsr_pattern(O, fm)
+    vals = orc.bsr_assemble(O, fm, rp, col)
+    nb = rp.size - 1
+    H = mb.host_hierarchy(job.nodes, job.elements, job.fixedNodes, ratio=2.0, max_levels=6, coarsest_rows=8)
+    assert len(H) >= 2 and H[0]["n_fine"] == nb
+    # the fine pattern the contributor lists of level 0 index into is the canonical reduced pattern
+    full = mb.plan_partition(V, job.elements, job.fixedNodes, 0, 1)
+    assert np.array_equal(full["rowptr"], rp) and np.array_equal(full["colidx"], col)
+    A = sp.bsr_matrix((vals.reshape(-1, 6, 6), col, rp), shape=(6 * nb, 6 * nb))
+    pos = O.nodes[fm >= 0]
+    blocks, bptr, bcol = vals.reshape(-1, 6, 6), rp, col
+    for lvl, L in enumerate(H):
+        nf, nc = L["n_fine"], L["n_coarse"]
+        assert nc < nf and (lvl == 0 or nf == H[lvl - 1]["n_coarse"])
+        agg, off = L["agg"], L["off"]
+        # centroids and offsets
+        cent = np.zeros((nc, 3)); np.add.at(cent, agg, pos); cent /= np.bincount(agg, minlength=nc)[:, None]
+        assert np.allclose(off, pos - cent[agg], rtol=0, atol=1e-12)
+        # B(d) = [[I, -[d]x], [0, I]]
+        B = np.tile(np.eye(6), (nf, 1, 1))
+        x, y, z = off[:, 0], off[:, 1], off[:, 2]
+        B[:, 0, 4], B[:, 0, 5], B[:, 1, 3], B[:, 1, 5], B[:, 2, 3], B[:, 2, 4] = z, -y, -z, x, y, -x
+        P = sp.bsr_matrix((B, agg, np.arange(nf + 1)), shape=(6 * nf, 6 * nc))
+        Ac = (P.T @ A @ P).tobsr(blocksize=(6, 6)); Ac.sort_indices()
+        # pattern: structural (a coarse block may be numerically zero), so compare with the aggregate graph
+        frow = np.repeat(np.arange(nf), np.diff(bptr))
+        want = np.unique(np.concatenate([agg[frow].astype(np.int64) * nc + agg[bcol], np.arange(nc) * (nc + 1)]))
+        crow = np.repeat(np.arange(nc), np.diff(L["rowptr"]))
+        assert np.array_equal(crow.astype(np.int64) * nc + L["colidx"], want)
+        # contributor lists: every fine block exactly once, ascending per coarse block, values = Galerkin product
+        gp, gs = L["gal_ptr"], L["gal_src"]
+        assert np.array_equal(np.sort(gs), np.arange(bcol.size))
+        seg = np.repeat(np.arange(gp.size - 1), np.diff(gp))
+        assert np.all(np.diff(gs)[seg[1:] == seg[:-1]] > 0)
+        assert np.array_equal(agg[frow[gs]], crow[seg]) and np.array_equal(agg[bcol[gs]], L["colidx"][seg])
+        contrib = np.einsum("kji,kjl,klm->kim", B[frow[gs]], blocks[gs], B[bcol[gs]])
+        mine = np.zeros((gp.size - 1, 6, 6)); np.add.at(mine, seg, contrib)
+        ref = np.zeros_like(mine)
+        Ad = Ac.tocsr()
+        for k in range(gp.size - 1):
+            I, J = crow[k], L["colidx"][k]
+            ref[k] = Ad[6 * I:6 * I + 6, 6 * J:6 * J + 6].toarray()
+        assert np.abs(mine - ref).max() <= 1e-9 * np.abs(ref).max()
+        # next level works on the coarse matrix
+        A, pos, blocks, bptr, bcol = sp.bsr_matrix((mine, L["colidx"], L["rowptr"]), shape=(6 * nc, 6 * nc)), cent, mine, L["rowptr"], L["colidx"]
