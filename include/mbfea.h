@@ -320,6 +320,9 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
  *            rowptr[coarse rows + 1], colidx[coarse blocks], gal_ptr[coarse blocks + 1],
  *            gal_src[fine blocks] (indices into the finer level's block pattern, ascending per coarse
  *            block; level 0's finer pattern is mbfea_plan_partition's with world = 1).  Any may be NULL. */
+/* spd_inverse: explicit inverse of a dense symmetric positive definite matrix (row-major n x n), the
+ *           coarsest-level solve of that preconditioner; MBFEA_ESINGULAR on a non-positive pivot.    */
+int mbfea_host_spd_inverse(int64_t n, const double *A, double *Ainv);
 typedef struct mbfea_hierarchy mbfea_hierarchy;
 int mbfea_hierarchy_open(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
                          const int32_t *fixed, double cell0, double ratio, int32_t max_levels,

@@ -8,9 +8,9 @@ The package is a thin ctypes face over ``libmbfea.so`` (C ABI in
 """
 from .simulator import (BeamDimensions, BeamMaterial, BeamSimulator, Context, ContractViolation, MbfeaError,
                         NodalForce, NotConverged, RangeError, SimulationJob, SimulationResults, SingularSystem,
-                        host_contributors, host_hierarchy, host_renumber, host_solver_format, plan_partition, read_scenario)
+                        host_contributors, host_hierarchy, host_renumber, host_spd_inverse, host_solver_format, plan_partition, read_scenario)
 from . import synthetic
 
 __all__ = ["BeamDimensions", "BeamMaterial", "BeamSimulator", "Context", "ContractViolation", "MbfeaError",
            "NodalForce", "NotConverged", "RangeError", "SimulationJob", "SimulationResults", "SingularSystem",
-           "host_contributors", "host_hierarchy", "host_renumber", "host_solver_format", "plan_partition", "read_scenario", "synthetic"]
+           "host_contributors", "host_hierarchy", "host_renumber", "host_spd_inverse", "host_solver_format", "plan_partition", "read_scenario", "synthetic"]

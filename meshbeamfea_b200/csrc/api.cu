@@ -1733,6 +1733,16 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
     return MBFEA_OK;
 }
 
+int mbfea_host_spd_inverse(int64_t n, const double *A, double *Ainv)
+{
+    if (n <= 0 || !A || !Ainv) return MBFEA_EARG;
+    try {
+        return dense_spd_inverse(n, A, Ainv) == 0 ? MBFEA_OK : MBFEA_ESINGULAR;
+    } catch (const std::bad_alloc &) {
+        return MBFEA_EARG;
+    }
+}
+
 struct mbfea_hierarchy { Hierarchy H; };
 
 int mbfea_hierarchy_open(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,

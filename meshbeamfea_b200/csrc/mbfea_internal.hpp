@@ -125,6 +125,10 @@ struct Hierarchy { std::vector<HierLevel> levels; };
 void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
                      double ratio, int max_levels, int64_t coarsest_rows, Hierarchy &H);
 
+// Explicit inverse of a dense SPD matrix (row-major n x n) for the coarsest level; 0, or 1 + the index of
+// the first non-positive pivot (dense.cpp).
+int dense_spd_inverse(int64_t n, const double *A, double *Ainv);
+
 // Scenario files (config.json + ASCII PLY).
 struct Scenario {
     int64_t V = 0, E = 0;

@@ -421,6 +421,18 @@ def host_contributors(V: int, elements: np.ndarray, fixed: np.ndarray, rank: int
     return cptr, contrib[:int(sizes[1])]
 
 
+def host_spd_inverse(A: np.ndarray) -> np.ndarray:
+    """Explicit inverse of a dense SPD matrix on the host (coarsest level of the multilevel preconditioner)."""
+    lib = L.lib()
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    out = np.empty_like(A)
+    rc = lib.mbfea_host_spd_inverse(n, ptr(A, _pd), ptr(out, _pd))
+    if rc != L.OK:
+        _raise(rc, lib.mbfea_status_string(rc).decode())
+    return out
+
+
 def host_hierarchy(nodes: np.ndarray, elements: np.ndarray, fixed: np.ndarray, cell0: float = 0.0, ratio: float = 2.0,
                    max_levels: int = 8, coarsest_rows: int = 128) -> list:
     """Aggregate hierarchy of the multilevel preconditioner (host half of SURVEY 8(f) rank 4; not used by the

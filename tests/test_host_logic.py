@@ -563,3 +563,19 @@ def test_aggregate_hierarchy_matches_galerkin_products(built, mesh):
         assert np.abs(mine - ref).max() <= 1e-9 * np.abs(ref).max()
         # next level works on the coarse matrix
         A, pos, blocks, bptr, bcol = sp.bsr_matrix((mine, L["colidx"], L["rowptr"]), shape=(6 * nc, 6 * nc)), cent, mine, L["rowptr"], L["colidx"]
+
+
+def test_dense_spd_inverse(built):
+    """Coarsest-level solve of the multilevel preconditioner: blocked Cholesky + explicit inverse on the host."""
+    rng = np.random.default_rng(2)
+    for n in (1, 6, 47, 48, 49, 300, 768):
+        M = rng.standard_normal((n, n))
+        A = M @ M.T + n * np.eye(n)
+        Ai = mb.host_spd_inverse(A)
+        assert np.abs(Ai @ A - np.eye(n)).max() < 1e-10
+        assert np.abs(Ai - Ai.T).max() < 1e-12 * np.abs(Ai).max() + 1e-15
+        assert np.abs(Ai - np.linalg.inv(A)).max() < 1e-10 * np.abs(Ai).max()
+    with pytest.raises(mb.SingularSystem):
+        mb.host_spd_inverse(np.array([[1.0, 2.0], [2.0, 1.0]]))          # indefinite
+    with pytest.raises(mb.SingularSystem):
+        mb.host_spd_inverse(np.zeros((3, 3)))
