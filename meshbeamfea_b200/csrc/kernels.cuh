@@ -168,4 +168,16 @@ int  force_minmax_parts(int64_t n);
 void launch_force_ranges(cudaStream_t st, int64_t n, const double *F, double *pmin, double *pmax, double *range);
 void launch_force_normalize(cudaStream_t st, int64_t n, const double *F, const double *range, double *out);
 
+
+// ---- multilevel preconditioner, device half (DRAFT, not called by the solver yet: see multilevel.cu) ----------
+void launch_ml_galerkin(cudaStream_t st, int64_t n_coarse_blocks, const int32_t *gal_ptr, const int32_t *gal_src,
+                        const int32_t *frow, const int32_t *fcol, const double *fvals, const double *off, double *cvals);
+void launch_ml_restrict(cudaStream_t st, int64_t n_agg, const int32_t *agg_ptr, const int32_t *agg_rows, const double *off,
+                        const double *lfac /* null: unscaled level */, const double *r, double *rc);
+void launch_ml_smooth(cudaStream_t st, int64_t n, const double *sinv, const double *r, double *z);
+void launch_ml_dense_matvec(cudaStream_t st, int64_t n, const double *Ainv, const double *r, double *z);
+void launch_ml_prolong(cudaStream_t st, int64_t n, const int32_t *agg, const double *off, const double *zc, double *z);
+void launch_ml_finish(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const double *off, const double *lfac,
+                      const double *rt, const double *z1, double *zt, double *part);
+
 }}  // namespace mbfea::dev

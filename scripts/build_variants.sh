@@ -12,6 +12,6 @@ for spec in "$@"; do
      -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -DMBFEA_SYM_MINB=$1 -DMBFEA_SYM_UNROLL=$2 -DMBFEA_SYM_PREFETCH=${3:-0} -DMBFEA_SYM_L2PF=${4:-1} \
      -c kernels.cu -o build/kernels_$name.o
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libmbfea_$name.so \
-     build/kernels_$name.o build/api.o build/host_prep.o build/hierarchy.o build/dense.o build/scenario.o build/nccl_dl.o -cudart static -ldl -lpthread
+     build/kernels_$name.o build/multilevel.o build/api.o build/host_prep.o build/hierarchy.o build/dense.o build/scenario.o build/nccl_dl.o -cudart static -ldl -lpthread
   echo "built variants/libmbfea_$name.so"
 done

@@ -579,3 +579,17 @@ def test_dense_spd_inverse(built):
         mb.host_spd_inverse(np.array([[1.0, 2.0], [2.0, 1.0]]))          # indefinite
     with pytest.raises(mb.SingularSystem):
         mb.host_spd_inverse(np.zeros((3, 3)))
+
+
+def test_multilevel_transfer_math(tmp_path):
+    """The rigid-body transfer arithmetic the (not yet wired) multilevel kernels share with the host:
+    B(d) c, B(d)^T r, entries of B(d) and the Galerkin block entry, against explicit 6x6 matrices."""
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(str(tmp_path), "mlmath")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(here, "..", "meshbeamfea_b200", "csrc"),
+                    os.path.join(here, "multilevel_math_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
