@@ -320,6 +320,12 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
  *            rowptr[coarse rows + 1], colidx[coarse blocks], gal_ptr[coarse blocks + 1],
  *            gal_src[fine blocks] (indices into the finer level's block pattern, ascending per coarse
  *            block; level 0's finer pattern is mbfea_plan_partition's with world = 1).  Any may be NULL. */
+/* EXPERIMENTAL and UNVALIDATED on hardware (see csrc/multilevel.cu): mbfea_solve with the additive multilevel
+ * preconditioner -- one rank, one mesh, after mbfea_assemble; results through the usual getters after
+ * mbfea_recover.  cell_beam_lengths: brick edge of the first coarse level in mean beam lengths (<= 0: 2);
+ * ratio: growth of the brick edge per level (<= 1: 2); coarsest_rows: stop coarsening at this many rows
+ * (<= 0: 128).  Not covered by any parity claim; mbfea_solve / mbfea_execute do not use it.            */
+int mbfea_solve_multilevel(mbfea_ctx *ctx, double cell_beam_lengths, double ratio, int64_t coarsest_rows);
 /* spd_inverse: explicit inverse of a dense symmetric positive definite matrix (row-major n x n), the
  *           coarsest-level solve of that preconditioner; MBFEA_ESINGULAR on a non-positive pivot.    */
 int mbfea_host_spd_inverse(int64_t n, const double *A, double *Ainv);
