@@ -12,11 +12,15 @@
 // The fine level lives in the block-Jacobi-scaled variables of the solver (y = L^T x): its transfer operators
 // are L_v^T B(d_v), with L_v the row's Cholesky factor (lfac, full 6x6 storage, zeros above the diagonal).
 // All sums run in a fixed order (member lists and contributor lists ascend): results are reproducible.
+#if !defined(MBFEA_HOST_EMULATION)   // tests/multilevel_emul.cpp compiles the kernel bodies for the CPU
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdint>
 
+#if !defined(MBFEA_HOST_EMULATION)
 #include "kernels.cuh"
+#endif
 #include "multilevel_math.hpp"
 
 namespace mbfea { namespace dev {
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(kMlThreads) k_ml_finish(int64_t nb, const int3
     }
 }
 
+#if !defined(MBFEA_HOST_EMULATION)
 // ---- launchers (no caller yet, see the header comment) -------------------------------------------------------
 void launch_ml_galerkin(cudaStream_t st, int64_t n_coarse_blocks, const int32_t *gal_ptr, const int32_t *gal_src,
                         const int32_t *frow, const int32_t *fcol, const double *fvals, const double *off, double *cvals)
@@ -239,5 +244,7 @@ void launch_ml_finish(cudaStream_t st, int grid, int64_t nb, const int32_t *agg,
     if (nb <= 0 || grid <= 0) return;
     k_ml_finish<<<(unsigned)grid, kMlThreads, 0, st>>>(nb, agg, off, lfac, rt, z1, zt, part);
 }
+
+#endif   // !MBFEA_HOST_EMULATION
 
 }}  // namespace mbfea::dev
