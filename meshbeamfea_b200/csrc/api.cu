@@ -18,6 +18,7 @@
 
 #include "kernels.cuh"
 #include "mbfea_internal.hpp"
+#include "multilevel_apply.hpp"
 #include "nccl_dl.hpp"
 
 using namespace mbfea;
@@ -1748,22 +1749,29 @@ struct MlLevel {
     DevBuf<double> off, vals, lfac, sinv, r, z;   // vals: coarse blocks; r, z: coarse vectors (6 per row)
 };
 
-// z~ (zt) = r~ + L^T B (sum over the coarse levels); partials of r~ . z~ into part[0 .. grid)
+// z~ (zt) = r~ + L^T B (sum over the coarse levels); partials of r~ . z~ into part[0 .. grid).  The level loop is
+// ml_apply_levels (multilevel_apply.hpp), shared with the CPU emulation test.
+struct MlStreamLauncher {
+    cudaStream_t st;
+    void restrict(int64_t n, const int32_t *ap, const int32_t *ar, const double *off, const double *lfac, const double *r, double *rc)
+    { launch_ml_restrict(st, n, ap, ar, off, lfac, r, rc); }
+    void smooth(int64_t n, const double *sinv, const double *r, double *z) { launch_ml_smooth(st, n, sinv, r, z); }
+    void dense_matvec(int64_t n, const double *Ai, const double *r, double *z) { launch_ml_dense_matvec(st, n, Ai, r, z); }
+    void prolong(int64_t n, const int32_t *agg, const double *off, const double *zc, double *z) { launch_ml_prolong(st, n, agg, off, zc, z); }
+    void finish(int grid, int64_t nb, const int32_t *agg, const double *off, const double *lfac, const double *rt, const double *z1,
+                double *zt, double *part)
+    { launch_ml_finish(st, grid, nb, agg, off, lfac, rt, z1, zt, part); }
+};
+
 void ml_apply(mbfea_ctx *c, std::vector<MlLevel> &lv, const DevBuf<double> &Ainv, const double *rt, double *zt,
               double *part, int grid)
 {
-    const int64_t nb = c->nb();
-    const size_t L = lv.size();
-    launch_ml_restrict(c->st, lv[0].n_coarse, lv[0].agg_ptr.p, lv[0].agg_rows.p, lv[0].off.p, c->lfac.p, rt, lv[0].r.p);
-    for (size_t l = 1; l < L; ++l)
-        launch_ml_restrict(c->st, lv[l].n_coarse, lv[l].agg_ptr.p, lv[l].agg_rows.p, lv[l].off.p, nullptr, lv[l - 1].r.p, lv[l].r.p);
-    launch_ml_dense_matvec(c->st, 6 * lv[L - 1].n_coarse, Ainv.p, lv[L - 1].r.p, lv[L - 1].z.p);
-    for (size_t l = L - 1; l >= 1; --l) {   // level l's rows are level l-1's aggregates
-        launch_ml_smooth(c->st, lv[l - 1].n_coarse, lv[l - 1].sinv.p, lv[l - 1].r.p, lv[l - 1].z.p);
-        launch_ml_prolong(c->st, lv[l - 1].n_coarse, lv[l].agg.p, lv[l].off.p, lv[l].z.p, lv[l - 1].z.p);
-    }
-    launch_ml_finish(c->st, grid, nb, lv[0].agg.p, lv[0].off.p, c->lfac.p, rt, lv[0].z.p, zt, part);
-    c->launches += (int64_t)(2 * L + 1 + 2 * (L - 1));
+    std::vector<MlLevelView> view(lv.size());
+    for (size_t l = 0; l < lv.size(); ++l)
+        view[l] = MlLevelView{lv[l].n_fine, lv[l].n_coarse, lv[l].agg.p, lv[l].agg_ptr.p, lv[l].agg_rows.p, lv[l].off.p,
+                              lv[l].sinv.p, lv[l].r.p, lv[l].z.p};
+    ml_apply_levels(MlStreamLauncher{c->st}, view.data(), view.size(), Ainv.p, c->nb(), c->lfac.p, rt, zt, part, grid);
+    c->launches += (int64_t)(4 * lv.size());
 }
 
 }  // namespace

@@ -67,6 +67,7 @@ static void emu_launch(void (*k)(A...), unsigned grid, unsigned block, B... args
 }
 
 #include "mbfea_internal.hpp"
+#include "multilevel_apply.hpp"
 using namespace mbfea;
 using namespace mbfea::dev;
 
@@ -104,9 +105,22 @@ int main()
     std::mt19937_64 g(9); std::uniform_real_distribution<double> U(-1, 1);
     const int64_t nnz = P.rowptr[(size_t)nb];
     std::vector<double> vals((size_t)nnz * 36);
-    for (double &x : vals) x = U(g);
     std::vector<int32_t> frow((size_t)nnz);
     for (int64_t r = 0; r < nb; ++r) for (int32_t k = P.rowptr[(size_t)r]; k < P.rowptr[(size_t)r + 1]; ++k) frow[(size_t)k] = (int32_t)r;
+    // symmetric and strongly diagonally dominant (=> SPD, so are its Galerkin products): A(b, a) = A(a, b)^T
+    for (int64_t r = 0; r < nb; ++r) for (int32_t k = P.rowptr[(size_t)r]; k < P.rowptr[(size_t)r + 1]; ++k) {
+        const int32_t cidx = P.colidx[(size_t)k];
+        if (cidx < r) continue;
+        double Bk[6][6];
+        for (auto &row : Bk) for (double &x : row) x = U(g);
+        if (cidx == r) { for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) Bk[i][j] = Bk[j][i]; for (int i = 0; i < 6; ++i) Bk[i][i] += 60.0; }
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) vals[(size_t)k * 36 + 6 * i + j] = Bk[i][j];
+        if (cidx != r) {
+            const int32_t *cb = P.colidx.data() + P.rowptr[(size_t)cidx], *ce = P.colidx.data() + P.rowptr[(size_t)cidx + 1];
+            const int64_t m = std::lower_bound(cb, ce, (int32_t)r) - P.colidx.data();
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) vals[(size_t)m * 36 + 6 * i + j] = Bk[j][i];
+        }
+    }
     // dense reference: P (6 nb x 6 nc) from agg / off, A dense
     const int64_t nc = L.n_coarse, nf = 6 * nb, nn = 6 * nc;
     std::vector<double> Pd((size_t)(nf * nn), 0.0), Ad((size_t)(nf * nf), 0.0);
@@ -181,6 +195,101 @@ int main()
     emu_launch(k_ml_finish, 2u, 256u, nb, L.agg.data(), L.off.data(), lfac.data(), r.data(), xc.data(), zt.data(), part.data());
     e = maxrel(zt, ztref); std::printf("finish        %.2e, dot %.2e\n", e, std::fabs(part[0] + part[1] - dotref) / std::fabs(dotref));
     bad += !(e < 1e-12) + !(std::fabs(part[0] + part[1] - dotref) <= 1e-12 * std::fabs(dotref));
+    // ---- the whole preconditioner through ml_apply_levels (the code the GPU driver runs), two coarse levels ----
+    if (H.levels.size() >= 2) {
+        const HierLevel &L1 = H.levels[1];
+        const int64_t n1 = L.n_coarse, n2 = L1.n_coarse, m1 = 6 * n1, m2 = 6 * n2;
+        // level-2 Galerkin matrix from the level-1 blocks (emulated kernel, as the driver does)
+        std::vector<int32_t> frow1((size_t)ncb);
+        for (int64_t I = 0; I < n1; ++I) for (int32_t k = L.rowptr[(size_t)I]; k < L.rowptr[(size_t)I + 1]; ++k) frow1[(size_t)k] = (int32_t)I;
+        const int64_t ncb2 = (int64_t)L1.colidx.size();
+        std::vector<double> cvals2((size_t)ncb2 * 36);
+        emu_launch(k_ml_galerkin, (unsigned)((ncb2 * 36 + 255) / 256), 256u, ncb2, L1.gal_ptr.data(), L1.gal_src.data(), frow1.data(),
+                   L.colidx.data(), cvals.data(), L1.off.data(), cvals2.data());
+        // dense P1, A1 (= Ac above), A2 = P1^T A1 P1 and its inverse (Gauss-Jordan, tiny)
+        std::vector<double> P1((size_t)(m1 * m2), 0.0);
+        for (int64_t v = 0; v < n1; ++v) {
+            const double *d = &L1.off[(size_t)3 * v];
+            double Bv[6][6] = {};
+            for (int i = 0; i < 6; ++i) Bv[i][i] = 1.0;
+            Bv[0][4] = d[2]; Bv[0][5] = -d[1]; Bv[1][3] = -d[2]; Bv[1][5] = d[0]; Bv[2][3] = d[1]; Bv[2][4] = -d[0];
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) P1[(size_t)((6 * v + i) * m2 + 6 * L1.agg[(size_t)v] + j)] = Bv[i][j];
+        }
+        std::vector<double> T((size_t)(m1 * m2), 0.0), A2((size_t)(m2 * m2), 0.0), A2k((size_t)(m2 * m2), 0.0);
+        for (int64_t i = 0; i < m1; ++i) for (int64_t k = 0; k < m1; ++k) { const double x = Ac[(size_t)(i * m1 + k)]; if (x != 0) for (int64_t j = 0; j < m2; ++j) T[(size_t)(i * m2 + j)] += x * P1[(size_t)(k * m2 + j)]; }
+        for (int64_t k = 0; k < m1; ++k) for (int64_t i = 0; i < m2; ++i) { const double x = P1[(size_t)(k * m2 + i)]; if (x != 0) for (int64_t j = 0; j < m2; ++j) A2[(size_t)(i * m2 + j)] += x * T[(size_t)(k * m2 + j)]; }
+        for (int64_t I = 0; I < n2; ++I) for (int32_t k = L1.rowptr[(size_t)I]; k < L1.rowptr[(size_t)I + 1]; ++k)
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) A2k[(size_t)((6 * I + i) * m2 + 6 * L1.colidx[(size_t)k] + j)] = cvals2[(size_t)k * 36 + 6 * i + j];
+        e = maxrel(A2k, A2); std::printf("galerkin lvl2 %.2e\n", e); bad += !(e < 1e-12);
+        std::vector<double> Ainv2((size_t)(m2 * m2), 0.0), G = A2;
+        for (int64_t i = 0; i < m2; ++i) Ainv2[(size_t)(i * m2 + i)] = 1.0;
+        for (int64_t cidx = 0; cidx < m2; ++cidx) {
+            const double pv = G[(size_t)(cidx * m2 + cidx)];
+            for (int64_t j = 0; j < m2; ++j) { G[(size_t)(cidx * m2 + j)] /= pv; Ainv2[(size_t)(cidx * m2 + j)] /= pv; }
+            for (int64_t i = 0; i < m2; ++i) if (i != cidx) {
+                const double fct = G[(size_t)(i * m2 + cidx)];
+                if (fct != 0) for (int64_t j = 0; j < m2; ++j) { G[(size_t)(i * m2 + j)] -= fct * G[(size_t)(cidx * m2 + j)]; Ainv2[(size_t)(i * m2 + j)] -= fct * Ainv2[(size_t)(cidx * m2 + j)]; }
+            }
+        }
+        // S of the level-1 diagonal blocks (what k_block_chol produces): D = Lc Lc^T, S = Lc^-1
+        std::vector<double> sinv1((size_t)n1 * 36, 0.0), D1inv((size_t)n1 * 36, 0.0);
+        for (int64_t I = 0; I < n1; ++I) {
+            double Dm[6][6], Lc[6][6] = {}, Sm[6][6] = {};
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Dm[i][j] = Ac[(size_t)((6 * I + i) * m1 + 6 * I + j)];
+            for (int j = 0; j < 6; ++j) {
+                double d = Dm[j][j]; for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
+                Lc[j][j] = std::sqrt(d);
+                for (int i = j + 1; i < 6; ++i) { double v = Dm[i][j]; for (int k = 0; k < j; ++k) v -= Lc[i][k] * Lc[j][k]; Lc[i][j] = v / Lc[j][j]; }
+            }
+            for (int j = 0; j < 6; ++j) for (int i = j; i < 6; ++i) {
+                if (i == j) { Sm[i][j] = 1.0 / Lc[j][j]; continue; }
+                double v = 0; for (int k = j; k < i; ++k) v -= Lc[i][k] * Sm[k][j];
+                Sm[i][j] = v / Lc[i][i];
+            }
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+                sinv1[(size_t)I * 36 + 6 * i + j] = Sm[i][j];
+                double v = 0; for (int k = 0; k < 6; ++k) v += Sm[k][i] * Sm[k][j];
+                D1inv[(size_t)I * 36 + 6 * i + j] = v;
+            }
+        }
+        // dense reference: z = r + L^T P0 ( D1^-1 r1 + P1 A2^-1 P1^T r1 ),  r1 = P0^T L r
+        std::vector<double> w0((size_t)nf), r1((size_t)m1, 0.0), r2((size_t)m2, 0.0), z2((size_t)m2, 0.0), z1v((size_t)m1, 0.0), zfull((size_t)nf);
+        for (int64_t v = 0; v < nb; ++v) for (int i = 0; i < 6; ++i) { double sacc = 0; for (int j = 0; j <= i; ++j) sacc += lfac[(size_t)v * 36 + 6 * i + j] * r[(size_t)(6 * v + j)]; w0[(size_t)(6 * v + i)] = sacc; }
+        for (int64_t k = 0; k < nf; ++k) for (int64_t j = 0; j < m1; ++j) r1[(size_t)j] += Pd[(size_t)(k * nn + j)] * w0[(size_t)k];
+        for (int64_t k = 0; k < m1; ++k) for (int64_t j = 0; j < m2; ++j) r2[(size_t)j] += P1[(size_t)(k * m2 + j)] * r1[(size_t)k];
+        for (int64_t i = 0; i < m2; ++i) for (int64_t j = 0; j < m2; ++j) z2[(size_t)i] += Ainv2[(size_t)(i * m2 + j)] * r2[(size_t)j];
+        for (int64_t I = 0; I < n1; ++I) for (int i = 0; i < 6; ++i) { double v = 0; for (int j = 0; j < 6; ++j) v += D1inv[(size_t)I * 36 + 6 * i + j] * r1[(size_t)(6 * I + j)]; z1v[(size_t)(6 * I + i)] = v; }
+        for (int64_t k = 0; k < m1; ++k) for (int64_t j = 0; j < m2; ++j) z1v[(size_t)k] += P1[(size_t)(k * m2 + j)] * z2[(size_t)j];
+        double dot2 = 0;
+        for (int64_t v = 0; v < nb; ++v) {
+            double t[6];
+            for (int i = 0; i < 6; ++i) { t[i] = 0; for (int64_t j = 0; j < m1; ++j) t[i] += Pd[(size_t)((6 * v + i) * nn + j)] * z1v[(size_t)j]; }
+            for (int i = 0; i < 6; ++i) { double sacc = r[(size_t)(6 * v + i)]; for (int j = i; j < 6; ++j) sacc += lfac[(size_t)v * 36 + 6 * j + i] * t[j]; zfull[(size_t)(6 * v + i)] = sacc; dot2 += r[(size_t)(6 * v + i)] * sacc; }
+        }
+        // the shared level loop with emulated launches
+        struct EmuLauncher {
+            void restrict(int64_t n, const int32_t *ap, const int32_t *ar, const double *off, const double *lf, const double *rr, double *rcv)
+            {
+                const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+                if (lf) emu_launch(k_ml_restrict<true>, grid, 256u, n, ap, ar, off, lf, rr, rcv);
+                else emu_launch(k_ml_restrict<false>, grid, 256u, n, ap, ar, off, lf, rr, rcv);
+            }
+            void smooth(int64_t n, const double *sv, const double *rr, double *zz) { emu_launch(k_ml_smooth, (unsigned)((n + 255) / 256), 256u, n, sv, rr, zz); }
+            void dense_matvec(int64_t n, const double *Ai, const double *rr, double *zz) { emu_launch(k_ml_dense_matvec, (unsigned)((n * 32 + 255) / 256), 256u, n, Ai, rr, zz); }
+            void prolong(int64_t n, const int32_t *ag, const double *off, const double *zc, double *zz) { emu_launch(k_ml_prolong, (unsigned)((n + 255) / 256), 256u, n, ag, off, zc, zz); }
+            void finish(int grid, int64_t nbb, const int32_t *ag, const double *off, const double *lf, const double *rtv, const double *z1p, double *ztv, double *pp)
+            { emu_launch(k_ml_finish, (unsigned)grid, 256u, nbb, ag, off, lf, rtv, z1p, ztv, pp); }
+        };
+        std::vector<double> rA((size_t)m1), zA((size_t)m1), rB((size_t)m2), zB((size_t)m2), ztl((size_t)nf), partl(3, 0.0);
+        mbfea::MlLevelView views[2] = {
+            {nb, n1, L.agg.data(), L.agg_ptr.data(), L.agg_rows.data(), L.off.data(), sinv1.data(), rA.data(), zA.data()},
+            {n1, n2, L1.agg.data(), L1.agg_ptr.data(), L1.agg_rows.data(), L1.off.data(), nullptr, rB.data(), zB.data()}};
+        mbfea::ml_apply_levels(EmuLauncher{}, views, 2, Ainv2.data(), nb, lfac.data(), r.data(), ztl.data(), partl.data(), 3);
+        e = maxrel(ztl, zfull);
+        const double de = std::fabs(partl[0] + partl[1] + partl[2] - dot2) / std::fabs(dot2);
+        std::printf("level loop    %.2e, dot %.2e  (rows %lld -> %lld -> %lld)\n", e, de, (long long)nb, (long long)n1, (long long)n2);
+        bad += !(e < 1e-11) + !(de < 1e-11);
+    } else { std::printf("only one coarse level\n"); bad += 1; }
     std::printf("%s\n", bad ? "MISMATCH" : "all kernels match");
     return bad != 0;
 }
