@@ -124,23 +124,32 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
         for (int64_t I = b0; I < b1; ++I) { row_of(I, tmp); std::copy(tmp.begin(), tmp.end(), L.colidx.begin() + L.rowptr[(size_t)I]); }
     });
     // Galerkin contributor lists: fine block k = (a, b) is summed into coarse block (agg a, agg b) as
-    // B(off a)^T A(a, b) B(off b); per coarse block the fine blocks are listed in ascending k
+    // B(off a)^T A(a, b) B(off b); per coarse block the fine blocks are listed in ascending k.  The lists of coarse
+    // row I come from I's member rows only (ascending rows => ascending k), so aggregates are independent: count,
+    // prefix, fill -- both passes parallel over aggregates.
     const int64_t nnz_f = rowptr[n], nnz_c = (int64_t)L.colidx.size();
-    std::vector<int32_t> target((size_t)nnz_f);
-    par_ranges(n, 1 << 14, [&](int64_t b0, int64_t b1) {
-        for (int64_t a = b0; a < b1; ++a) {
-            const int32_t I = L.agg[(size_t)a];
-            const int32_t *cb = L.colidx.data() + L.rowptr[(size_t)I], *ce = L.colidx.data() + L.rowptr[(size_t)I + 1];
-            for (int32_t k = rowptr[a]; k < rowptr[a + 1]; ++k)
-                target[(size_t)k] = (int32_t)(std::lower_bound(cb, ce, L.agg[(size_t)colidx[k]]) - L.colidx.data());
-        }
-    });
     L.gal_ptr.assign((size_t)nnz_c + 1, 0);
-    for (int64_t k = 0; k < nnz_f; ++k) L.gal_ptr[(size_t)target[(size_t)k] + 1]++;
+    auto for_blocks_of = [&](int64_t I, auto &&visit) {   // visit(coarse block index, fine block index), fine ascending
+        const int32_t *cb = L.colidx.data() + L.rowptr[(size_t)I], *ce = L.colidx.data() + L.rowptr[(size_t)I + 1];
+        for (int32_t q = L.agg_ptr[(size_t)I]; q < L.agg_ptr[(size_t)I + 1]; ++q) {
+            const int32_t v = L.agg_rows[(size_t)q];
+            for (int32_t k = rowptr[v]; k < rowptr[v + 1]; ++k)
+                visit((int32_t)(std::lower_bound(cb, ce, L.agg[(size_t)colidx[k]]) - L.colidx.data()), k);
+        }
+    };
+    par_ranges(na, 1 << 10, [&](int64_t b0, int64_t b1) {
+        for (int64_t I = b0; I < b1; ++I) for_blocks_of(I, [&](int32_t kc, int32_t) { L.gal_ptr[(size_t)kc + 1]++; });
+    });
     for (int64_t k = 0; k < nnz_c; ++k) L.gal_ptr[(size_t)k + 1] += L.gal_ptr[(size_t)k];
     L.gal_src.resize((size_t)nnz_f);
-    std::vector<int32_t> cur(L.gal_ptr.begin(), L.gal_ptr.end() - 1);
-    for (int64_t k = 0; k < nnz_f; ++k) L.gal_src[(size_t)cur[(size_t)target[(size_t)k]]++] = (int32_t)k;
+    par_ranges(na, 1 << 10, [&](int64_t b0, int64_t b1) {
+        std::vector<int32_t> cur;
+        for (int64_t I = b0; I < b1; ++I) {
+            const int32_t c0 = L.rowptr[(size_t)I], c1 = L.rowptr[(size_t)I + 1];
+            cur.assign(L.gal_ptr.begin() + c0, L.gal_ptr.begin() + c1);
+            for_blocks_of(I, [&](int32_t kc, int32_t k) { L.gal_src[(size_t)cur[(size_t)(kc - c0)]++] = k; });
+        }
+    });
 }
 
 void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
