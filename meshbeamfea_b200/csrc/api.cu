@@ -119,6 +119,7 @@ struct mbfea_ctx {
     nccl::Comm comm = nullptr;
     // NVLink peer-memory path (comm_mode 0/2): mailbox + ghost regions mapped through CUDA IPC
     bool p2p = false;
+    bool comm_broken = false;   // a peer stopped responding: no further collective is attempted (destroy skips its rendezvous)
     DevBuf<Mailbox> mailbox;
     DevBuf<PeerCtx> peerctx;
     DevBuf<unsigned int> tickets;
@@ -318,10 +319,9 @@ void setup_p2p_mailboxes(mbfea_ctx *c)
     }
     cudaGetLastError();
     CK(c->mailbox.alloc(1));
-    CK(c->tickets.alloc(4));
     CK(c->peerctx.alloc(1));
     CK(cudaMemsetAsync(c->mailbox.p, 0, sizeof(Mailbox), c->st));
-    CK(cudaMemsetAsync(c->tickets.p, 0, 4 * sizeof(unsigned int), c->st));
+    CK(cudaMemsetAsync(c->tickets.p, 0, 8 * sizeof(unsigned int), c->st));
     CK(cudaStreamSynchronize(c->st));
     struct Rec { cudaIpcMemHandle_t h; int64_t ok; };
     static_assert(sizeof(Rec) % 8 == 0, "IPC record must be a multiple of 8 bytes");
@@ -428,7 +428,7 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         launch_cg_update(c->st, nb, parity, PartialRef{c->part_a.p, gs, 1}, c->p.p, c->Ap.p, c->y.p, c->rt.p,
                          c->part_b.p, c->sc.p, c->peerctx.p);
         launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, c->rt.p, c->p.p, c->sc.p, c->peerctx.p,
-                          c->push_idx.p, c->push_dst.p);
+                          c->push_idx.p, c->push_dst.p, c->tickets.p + 2);
         c->launches += 2;
         return;
     }
@@ -449,7 +449,7 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         rho = PartialRef{c->gath.p + W, W, 1};
         c->launches++;
     }
-    launch_cg_pupdate(c->st, nb, parity, rho, c->rt.p, c->p.p, c->sc.p, nullptr, nullptr, nullptr);
+    launch_cg_pupdate(c->st, nb, parity, rho, c->rt.p, c->p.p, c->sc.p, nullptr, nullptr, nullptr, c->tickets.p + 2);
     c->launches += 2;
 }
 
@@ -482,7 +482,7 @@ void enqueue_iteration2(mbfea_ctx *c, int kernel)
     if (W > 1 && !c->p2p) { delta = PartialRef{c->gath.p, W, 2}; gamma = PartialRef{c->gath.p + 1, W, 2}; }
     launch_cg2_step(c->st, nb, delta, gamma, c->p.p, c->Ap.p, c->rt.p, c->sdir.p, c->y.p, c->sc.p,
                     c->p2p ? c->peerctx.p : nullptr, c->p2p ? c->push_idx.p : nullptr, c->p2p ? c->push_dst.p : nullptr,
-                    c->p2p ? c->push_rows.p : nullptr, c->p2p ? (int)c->push_rows.n : 0);
+                    c->p2p ? c->push_rows.p : nullptr, c->p2p ? (int)c->push_rows.n : 0, c->tickets.p + 2);
     c->launches++;
     enqueue_spmv2(c, kernel);
 }
@@ -551,12 +551,25 @@ void upload_forces(mbfea_ctx *c, int64_t nF, const int64_t *f_node, const int64_
     const int64_t nb = c->nb();
     CK(cudaMemsetAsync(c->f.p, 0, (size_t)std::max<int64_t>(1, 6 * nb) * sizeof(double), c->st));
     if (nF > 0) {
+        // one thread per force unless some (vertex, dof) is loaded twice: then the ordered one-thread kernel
+        // keeps the accumulation order of the input (a bitmap of 6V bits finds out; validated indices)
+        bool unique = true;
+        {
+            std::vector<uint64_t> seen(((size_t)6 * (size_t)c->V + 63) / 64, 0);
+            for (int64_t i = 0; i < nF && unique; ++i) {
+                const size_t bit = (size_t)6 * (size_t)f_node[i] + (size_t)f_dof[i];
+                uint64_t &w = seen[bit >> 6];
+                const uint64_t m = 1ull << (bit & 63);
+                if (w & m) unique = false;
+                w |= m;
+            }
+        }
         DevBuf<int64_t> dn, dd;
         DevBuf<double> dm;
         upload(c, dn, f_node, (size_t)nF);
         upload(c, dd, f_dof, (size_t)nF);
         upload(c, dm, f_mag, (size_t)nF);
-        launch_scatter_forces(c->st, nF, dn.p, dd.p, dm.p, c->free_index.p, c->plan.row_begin, nb, c->f.p);
+        launch_scatter_forces(c->st, nF, dn.p, dd.p, dm.p, c->free_index.p, c->plan.row_begin, nb, c->f.p, unique);
         CK(cudaStreamSynchronize(c->st));
     }
     c->solved = c->recovered = false;
@@ -645,8 +658,11 @@ int mbfea_create(mbfea_ctx **out, const mbfea_options *opts)
         CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
         for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
         CK(cudaMallocHost(reinterpret_cast<void **>(&c->sc_host), sizeof(PcgScalars)));
+        set_sm_count(c->sm_count);
         CK(c->sc.alloc(1));
         CK(c->flag.alloc(1));
+        CK(c->tickets.alloc(8));
+        CK(cudaMemsetAsync(c->tickets.p, 0, 8 * sizeof(unsigned int), c->st));
         CK(c->part_a.alloc(kMaxPartials));
         CK(c->part_b.alloc(kMaxPartials));
         CK(c->part_c.alloc(kMaxPartials));
@@ -668,6 +684,15 @@ void mbfea_destroy(mbfea_ctx *c)
     close_peer_vectors(c);
     for (size_t q = 0; q < c->peer_mailbox.size(); ++q)
         if ((int)q != c->opt.rank && c->peer_mailbox[q]) cudaIpcCloseMemHandle(c->peer_mailbox[q]);
+    if (c->p2p && c->comm && c->nc && !c->comm_broken) {
+        // rendezvous before the exported allocations (p, mailbox) are freed: every peer has unmapped them by
+        // the time the all-gather completes (all ranks destroy their contexts collectively, like set_job)
+        try {
+            int64_t token = 0;
+            std::vector<int64_t> tokens((size_t)c->world());
+            allgather_host(c, &token, tokens.data(), sizeof token);
+        } catch (...) { cudaGetLastError(); }
+    }
     if (c->comm && c->nc) c->nc->CommDestroy(c->comm);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -704,6 +729,22 @@ int mbfea_comm_init(mbfea_ctx *c, const uint8_t id128[128], int32_t rank, int32_
         c->opt.rank = rank; c->opt.world = world;
         CK(c->gath.alloc((size_t)8 * world));
         setup_p2p_mailboxes(c);
+        // warm the point-to-point connections now: the first ncclSend/Recv between two ranks sets up the
+        // channel (seconds on 8 GPUs), which otherwise lands inside the first timed assemble (ghost S factors)
+        if (world > 1) {
+            DevBuf<double> w;
+            CK(w.alloc((size_t)2 * world));
+            NK(c->nc->GroupStart());
+            for (int q = 0; q < world; ++q) {
+                if (q == rank) continue;
+                NK(c->nc->Send(w.p + rank, 1, nccl::kFloat64, q, c->comm, c->st));
+                NK(c->nc->Recv(w.p + world + q, 1, nccl::kFloat64, q, c->comm, c->st));
+            }
+            NK(c->nc->GroupEnd());
+            NK(c->nc->AllReduce(c->flag.p, c->flag.p, 1, nccl::kInt32, nccl::kMax, c->comm, c->st));
+            NK(c->nc->Broadcast(w.p, w.p, 1, nccl::kFloat64, 0, c->comm, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        }
         return MBFEA_OK;
     });
 }
@@ -889,6 +930,9 @@ int mbfea_assemble(mbfea_ctx *c)
         CK(cudaEventRecord(c->ev[1], c->st));
         do_precond(c);
         CK(cudaEventRecord(c->ev[2], c->st));
+        // every rank takes the same exit: a non-SPD block on one rank fails the job on all of them (otherwise
+        // the others would go on into the solve's collectives and hang)
+        if (c->world() > 1) NK(c->nc->AllReduce(c->flag.p, c->flag.p, 1, nccl::kInt32, nccl::kMax, c->comm, c->st));
         int flag = 0;
         CK(cudaMemcpyAsync(&flag, c->flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
@@ -912,6 +956,10 @@ int mbfea_solve(mbfea_ctx *c)
         const int kernel = c->p2p ? 1 : pick_spmv(c, 0);
         const int gv = vec_grid(nb);
         c->epoch++;
+        // a solve that ended abnormally (timeout, breakdown mid-kernel) must not leak its tickets or its
+        // timeout flag into this one
+        CK(cudaMemsetAsync(c->tickets.p, 0, 8 * sizeof(unsigned int), c->st));
+        if (c->p2p) peer_timeout_clear(c->st);
         long long max_iter = c->opt.max_iter;
         if (max_iter <= 0) max_iter = std::min<long long>(20LL * 6 * std::max<int64_t>(1, c->plan.nb_global), 5000000LL);
         int check = c->opt.check_every;
@@ -1052,8 +1100,10 @@ int mbfea_solve(mbfea_ctx *c)
                 CK(cudaMemcpyAsync(c->sc_host, c->sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->st));
                 CK(cudaStreamSynchronize(c->st));
                 if (c->sc_host->done != 0) break;
-                if (c->p2p && peer_timeout_flag())
+                if (c->p2p && peer_timeout_flag()) {
+                    c->comm_broken = true;
                     return fail(c, MBFEA_ECUDA, "a peer rank stopped signalling during the CG loop (NVLink mailbox wait timed out)");
+                }
             }
             // K~ y through the ghosted buffer (its previous content -- direction or residual -- is
             // rebuilt by the replacement below if the iteration resumes)
@@ -1122,8 +1172,10 @@ int mbfea_solve(mbfea_ctx *c)
                          c->plan.sym_half ? (c->plan.balanced ? "symmetric-half, balanced" : "symmetric-half") : "full-row", check);
         if (c->opt.verbose && restarts)
             std::fprintf(stderr, "[mbfea] rank %d: %d residual replacement(s)\n", c->opt.rank, restarts);
-        if (c->p2p && peer_timeout_flag())
+        if (c->p2p && peer_timeout_flag()) {
+            c->comm_broken = true;
             return fail(c, MBFEA_ECUDA, "a peer rank stopped signalling during the PCG loop (NVLink mailbox wait timed out)");
+        }
         if (h.done == 3) return fail(c, MBFEA_ESINGULAR, "CG breakdown: p.Ap <= 0 or non-finite (system not SPD: is any vertex fixed?)");
         if (diverged)
             return fail(c, MBFEA_ESINGULAR, "recomputed residual ||f - K u|| disagrees with the CG recurrence: the system is singular "
@@ -1884,7 +1936,7 @@ int mbfea_solve_multilevel(mbfea_ctx *c, double cell_beam_lengths, double ratio,
                                  c->sc.p, nullptr);
                 ml_apply(c, lv, Ainv, c->rt.p, c->sdir.p, c->part_b.p, gz);
                 launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gz, 1}, c->sdir.p, c->p.p, c->sc.p, nullptr, nullptr,
-                                  nullptr);
+                                  nullptr, c->tickets.p + 2);
                 c->launches += 2;
             }
             enqueue_check(c);

@@ -90,6 +90,11 @@ __device__ __forceinline__ void sum_partial_pairs(const double2 *pairs, int n, d
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// SM count of the device the context runs on (mbfea_create sets it): grids are sized in resident waves of it
+static int g_sm_count = 148;
+void set_sm_count(int n) { if (n > 0) g_sm_count = n; }
+int sm_count() { return g_sm_count; }
+
 static bool g_use_pdl = false;   // measured on B200 inside CUDA graphs: 304.8 vs 298.9 us/iteration -- no gain, off
 void set_pdl(bool on) { g_use_pdl = on; }
 
@@ -858,15 +863,16 @@ static int spmv_rows(int64_t nb, bool sym, bool peer)
     if (peer) return 32;
     if (forced == 16 || forced == 32) return forced;
     constexpr int64_t kHalfTileBelow = 12;
-    return (nb + 31) / 32 < (int64_t)148 * MBFEA_SYM_MINB * kHalfTileBelow ? 16 : 32;
+    return (nb + 31) / 32 < (int64_t)g_sm_count * MBFEA_SYM_MINB * kHalfTileBelow ? 16 : 32;
 }
 
-// one full wave: 148 SMs x resident CTAs per SM (8 at 40 registers, 6 at 56 for the symmetric variant)
+// one full wave: SMs x resident CTAs per SM (8 at 40 registers, 6 at 56 for the symmetric variant)
 int spmv_rowthread_grid(int64_t nb, bool sym, bool peer)
 {
     const int rows = spmv_rows(nb, sym, peer);
     const int64_t tiles = (nb + rows - 1) / rows;
-    const int64_t cap = (sym ? 148 * MBFEA_SYM_MINB : 148 * 8) * (32 / rows);
+    int64_t cap = (int64_t)(sym ? g_sm_count * MBFEA_SYM_MINB : g_sm_count * 8) * (32 / rows);
+    if (cap > kMaxPartials) cap = kMaxPartials;
     return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
@@ -1196,18 +1202,20 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
                                                        const double *__restrict__ rt, double *__restrict__ p,
                                                        PcgScalars *sc, const PeerCtx *pc,
                                                        const int32_t *__restrict__ push_idx,
-                                                       double *const *__restrict__ push_dst)
+                                                       double *const *__restrict__ push_dst, unsigned int *ticket)
 {
     __shared__ double red[33];
     pdl_wait();      // the previous kernel's results (and sc) are visible from here
     pdl_trigger();   // the next kernel may start launching
+    // No CTA of this grid writes a scalar another CTA reads at entry: iter / done / rz are advanced by the
+    // LAST CTA to retire (ticket), when every other CTA has finished -- no assumption about co-residency.
     if (sc->done != 0) return;
     const double pAp = sc->pAp;
     if (!(pAp > 0.0) || !isfinite(pAp)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->done = 3;
         return;
     }
-    const long long it0 = sc->iter;   // only block 0 stamps, and it bumps iter after this read
+    const long long it0 = sc->iter;   // advanced only by the last CTA to retire
     trace_stamp(sc, it0, 4);
     double rho_new;
     if (pc != nullptr) {
@@ -1239,23 +1247,21 @@ __global__ void __launch_bounds__(256, 4) k_cg_pupdate(int64_t n, int parity, Pa
             }
         }
     }
-    if (push_idx != nullptr) {
-        if (last_cta_done(pc->tickets + 2, pushed)) {   // peer stores land (system-scope fence) before the ticket
-            if ((int)threadIdx.x < pc->n_neighbors) {
-                // tag_cur = (epoch << 32 | k) + 1: exactly the halo tag iteration k+1 waits for
-                st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], sc->tag_cur);
-            }
+    if (last_cta_done(ticket, pushed)) {   // peer stores land (system-scope fence) before the ticket
+        if (push_idx != nullptr && (int)threadIdx.x < pc->n_neighbors) {
+            // tag_cur = (epoch << 32 | k) + 1: exactly the halo tag iteration k+1 waits for
+            st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], sc->tag_cur);
         }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->rz[parity ^ 1] = rho_new;
-        const long long it = sc->iter + 1;
-        sc->iter = it;
-        int done = 0;
-        if (!isfinite(rho_new)) done = 3;
-        else if (rho_new <= 1e-32 * sc->rho0) done = 1;   // below anything FP64 can resolve: exact convergence
-        else if (it >= sc->max_iter) done = 2;
-        sc->done = done;
+        if (threadIdx.x == 0) {
+            sc->rz[parity ^ 1] = rho_new;
+            const long long it = sc->iter + 1;
+            sc->iter = it;
+            int done = 0;
+            if (!isfinite(rho_new)) done = 3;
+            else if (rho_new <= 1e-32 * sc->rho0) done = 1;   // below anything FP64 can resolve: exact convergence
+            else if (it >= sc->max_iter) done = 2;
+            sc->done = done;
+        }
     }
 }
 
@@ -1297,14 +1303,14 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
     int64_t n, PartialRef delta_ref, PartialRef gamma_ref, double *__restrict__ r, const double *__restrict__ w,
     double *__restrict__ d, double *__restrict__ s, double *__restrict__ y, PcgScalars *sc, const PeerCtx *pc,
     const int32_t *__restrict__ push_idx, double *const *__restrict__ push_dst,
-    const int32_t *__restrict__ push_rows, int n_push)
+    const int32_t *__restrict__ push_rows, int n_push, unsigned int *ticket)
 {
     __shared__ double red[33];
     __shared__ double dots[2][kMaxWorld];
     pdl_wait();      // the previous kernel's results (and sc) are visible from here
     pdl_trigger();   // the next kernel may start launching
     if (sc->done != 0) return;
-    const long long it = sc->iter;    // stable: only block 0 bumps it, after its own reads
+    const long long it = sc->iter;    // stable: advanced only by the last CTA to retire (ticket), after every CTA's reads
     trace_stamp(sc, it, 2);
     double delta, gamma;
     unsigned long long tag = 0;
@@ -1371,25 +1377,25 @@ __global__ void __launch_bounds__(256, 4) k_cg2_step(
             step(j);
         }
     }
-    if (push_idx != nullptr) {   // the halo tag must be published even when nothing moved (peers wait on it)
-        if (last_cta_done(pc->tickets + 2, pushed)) {
+    if (last_cta_done(ticket, pushed)) {
+        if (push_idx != nullptr) {   // the halo tag must be published even when nothing moved (peers wait on it)
             if ((int)threadIdx.x < pc->n_neighbors) {
                 st_release_sys(&pc->peer[pc->neighbor[threadIdx.x]]->halo_tag[pc->rank], tag);
             }
             trace_stamp_cta(sc, it, 5);
         }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->rz[par] = gamma;
-        sc->alpha[par] = alpha;
-        sc->pAp = den;
-        if (it == 0) sc->rho0 = gamma;
-        sc->iter = it + 1;
-        int done = 0;
-        if (bad) done = 3;
-        else if (exact) done = 1;
-        else if (it + 1 >= sc->max_iter) done = 2;
-        sc->done = done;
+        if (threadIdx.x == 0) {
+            sc->rz[par] = gamma;
+            sc->alpha[par] = alpha;
+            sc->pAp = den;
+            if (it == 0) sc->rho0 = gamma;
+            sc->iter = it + 1;
+            int done = 0;
+            if (bad) done = 3;
+            else if (exact) done = 1;
+            else if (it + 1 >= sc->max_iter) done = 2;
+            sc->done = done;
+        }
     }
 }
 
@@ -1401,10 +1407,10 @@ void launch_cg2_init(cudaStream_t st, int64_t nb, const double *f, const double 
 
 void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef gamma, double *r, const double *w,
                      double *d, double *s, double *y, PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx,
-                     double *const *push_dst, const int32_t *push_rows, int n_push)
+                     double *const *push_dst, const int32_t *push_rows, int n_push, unsigned int *ticket)
 {
     launch_pdl(k_cg2_step, cg_vec_grid(nb), 256, 0, st, 6 * nb, delta, gamma, r, w, d, s, y, sc, pc, push_idx, push_dst,
-               push_rows, push_idx != nullptr ? n_push : 0);
+               push_rows, push_idx != nullptr ? n_push : 0, ticket);
 }
 
 // per batch: partial sums of ||L (a - b)||^2 (b may be null): the unscaled residual norm
@@ -1696,7 +1702,8 @@ void launch_cg_init_finish(cudaStream_t st, PartialRef rho, PartialRef ff, PcgSc
 int cg_vec_grid(int64_t nb)
 {
     const int64_t blocks = (3 * nb + 255) / 256;   // one double2 per thread and trip
-    const int64_t cap = 148 * 4;                    // one full wave at 4 CTAs of 256 threads per SM
+    int64_t cap = (int64_t)g_sm_count * 4;          // one full wave at 4 CTAs of 256 threads per SM
+    if (cap > kMaxPartials) cap = kMaxPartials;
     return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
@@ -1707,9 +1714,10 @@ void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, c
 }
 
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
-                       PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst)
+                       PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst,
+                       unsigned int *ticket)
 {
-    launch_pdl(k_cg_pupdate, cg_vec_grid(nb), 256, 0, st, 6 * nb, parity, rho, rt, p, sc, pc, push_idx, push_dst);
+    launch_pdl(k_cg_pupdate, cg_vec_grid(nb), 256, 0, st, 6 * nb, parity, rho, rt, p, sc, pc, push_idx, push_dst, ticket);
 }
 
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
@@ -1767,12 +1775,19 @@ int peer_timeout_flag()
     return v;
 }
 
+// start of every solve: a timeout of an earlier solve (or of another context) must not fail this one
+void peer_timeout_clear(cudaStream_t st)
+{
+    const int zero = 0;
+    cudaMemcpyToSymbolAsync(g_peer_timeout, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+}
+
 void launch_push_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, double *const *dst,
                       const double *x, const PcgScalars *sc, const PeerCtx *pc)
 {
     int64_t g = (n_send * 3 + 255) / 256;
     if (g < 1) g = 1;
-    if (g > 148) g = 148;
+    if (g > g_sm_count) g = g_sm_count;
     k_push_halo<<<(unsigned)g, 256, 0, st>>>(n_send, send_rows, dst, x, sc, pc);
 }
 
@@ -1827,9 +1842,9 @@ void launch_fill(cudaStream_t st, int64_t n, double *a, double v0, double dv, in
 }
 
 // load vector of the reduced system: f[6*free_index[node]+dof] += magnitude.
-// One thread, fixed order: duplicates accumulate in input order (deterministic)
-// and nF is tiny next to the mesh.  Forces on fixed vertices are dropped, as
-// elimination drops their equations.
+// Ordered variant (a job that loads some DOF more than once): one thread, fixed
+// order, so duplicates accumulate in input order (deterministic).  Forces on fixed
+// vertices are dropped, as elimination drops their equations.
 __global__ void k_scatter_forces(int64_t nF, const int64_t *__restrict__ node, const int64_t *__restrict__ dof,
                                  const double *__restrict__ mag, const int32_t *__restrict__ free_index,
                                  int64_t row_begin, int64_t nb, double *f)
@@ -1842,11 +1857,25 @@ __global__ void k_scatter_forces(int64_t nF, const int64_t *__restrict__ node, c
     }
 }
 
+// the same with one thread per force -- only valid when no two forces hit the same (vertex, dof), which the
+// host checks (upload_forces): then every destination is written once and the order does not matter
+__global__ void k_scatter_forces_unique(int64_t nF, const int64_t *__restrict__ node, const int64_t *__restrict__ dof,
+                                        const double *__restrict__ mag, const int32_t *__restrict__ free_index,
+                                        int64_t row_begin, int64_t nb, double *f)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nF) return;
+    const int64_t g = free_index[node[i]];
+    if (g < row_begin || g >= row_begin + nb) return;
+    f[(g - row_begin) * 6 + dof[i]] = mag[i];
+}
+
 void launch_scatter_forces(cudaStream_t st, int64_t nF, const int64_t *node, const int64_t *dof, const double *mag,
-                           const int32_t *free_index, int64_t row_begin, int64_t nb, double *f)
+                           const int32_t *free_index, int64_t row_begin, int64_t nb, double *f, bool unique)
 {
     if (nF <= 0) return;
-    k_scatter_forces<<<1, 32, 0, st>>>(nF, node, dof, mag, free_index, row_begin, nb, f);
+    if (unique) k_scatter_forces_unique<<<(unsigned)((nF + 255) / 256), 256, 0, st>>>(nF, node, dof, mag, free_index, row_begin, nb, f);
+    else k_scatter_forces<<<1, 32, 0, st>>>(nF, node, dof, mag, free_index, row_begin, nb, f);
 }
 
 // ---------------------------------------------------------------------------
@@ -1977,7 +2006,7 @@ __global__ void k_force_normalize(int64_t n, const double *__restrict__ F, const
 int force_minmax_parts(int64_t n)
 {
     const int64_t b = (n + 255) / 256;
-    return (int)(b < 1 ? 1 : (b > 148 ? 148 : b));
+    return (int)(b < 1 ? 1 : (b > g_sm_count ? g_sm_count : b));
 }
 
 void launch_force_ranges(cudaStream_t st, int64_t n, const double *F, double *pmin, double *pmax, double *range)

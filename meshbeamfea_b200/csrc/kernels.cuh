@@ -116,13 +116,14 @@ void launch_cg_init_finish(cudaStream_t st, PartialRef rho, PartialRef ff, PcgSc
 void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *p, const double *Ap,
                       double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc);
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
-                       PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst);
+                       PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst,
+                       unsigned int *ticket /* last-CTA ticket: the CTA that retires last advances the scalars */);
 // single-reduction (Chronopoulos-Gear) CG: SpMV on the residual yields r.r and r.K~r, one step kernel does the rest
 void launch_cg2_init(cudaStream_t st, int64_t nb, const double *f, const double *sinv, double *y, double *r, double *ft,
                      double *d, double *s, double *part_ff);
 void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef gamma, double *r, const double *w,
                      double *d, double *s, double *y, PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx,
-                     double *const *push_dst, const int32_t *push_rows, int n_push);
+                     double *const *push_dst, const int32_t *push_rows, int n_push, unsigned int *ticket);
 // unscaled residual norm ||L (a - b)||^2 (b may be null) -> partials; finish: total -> sc->rr, stop test
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
                      const PcgScalars *sc, const PeerCtx *pc);
@@ -141,6 +142,9 @@ void launch_cg_batched(cudaStream_t st, int ncomp, size_t smem_bytes, const int3
 void launch_unscale(cudaStream_t st, int64_t nb, const double *sinv, const double *y, double *x);
 void set_pdl(bool on);    // programmatic dependent launch of the CG-loop kernels (default off; MBFEA_PDL=1 turns it on)
 int peer_timeout_flag();  // 1 once any peer wait gave up (a rank died)
+void peer_timeout_clear(cudaStream_t st);
+void set_sm_count(int n); // grids are sized in resident waves of the device's SM count
+int  sm_count();
 // P2P halo: owned boundary x-blocks -> the neighbours' ghost slots (peer stores), then the tag
 void launch_push_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows, double *const *dst,
                       const double *x, const PcgScalars *sc, const PeerCtx *pc);
@@ -154,7 +158,8 @@ void launch_pack_halo(cudaStream_t st, int64_t n_send, const int32_t *send_rows,
 void launch_fill(cudaStream_t st, int64_t n, double *a, double v0, double dv, int period);
 // load vector of the reduced system (owned rows), duplicates accumulate in input order
 void launch_scatter_forces(cudaStream_t st, int64_t nF, const int64_t *node, const int64_t *dof, const double *mag,
-                           const int32_t *free_index, int64_t row_begin, int64_t nb, double *f);
+                           const int32_t *free_index, int64_t row_begin, int64_t nb, double *f,
+                           bool unique /* no destination is hit twice: one thread per force */);
 // results
 void launch_expand(cudaStream_t st, int64_t V, const int32_t *free_index, const double *x_global,
                    double *U_cm, double *U_rm);

@@ -12,7 +12,7 @@ namespace mbfea { namespace nccl {
 struct UniqueId { char internal[128]; };  // == ncclUniqueId
 typedef struct ncclComm *Comm;
 enum DataType { kInt32 = 2, kInt64 = 4, kFloat64 = 8 };  // ncclInt32, ncclInt64, ncclFloat64
-enum RedOp { kSum = 0 };
+enum RedOp { kSum = 0, kMax = 2 };  // ncclSum, ncclMax
 
 struct Api {
     int (*GetUniqueId)(UniqueId *);
