@@ -91,7 +91,15 @@ typedef struct mbfea_options {
                               the input vertex order has no locality), 1 never, 2 always,
                               3 Morton (Z-order) numbering from the vertex coordinates: 32-row
                               tiles become compact bricks of the mesh                          */
-    int32_t reserved[2];
+    int32_t precond;       /* preconditioner of the CG solve: 0 auto (multilevel on one rank for a single mesh of
+                              >= 4096 free vertices, block-Jacobi otherwise), 1 6x6 block-Jacobi (the north-star
+                              configuration the SpMV roofline is quoted on), 2 additive multilevel: block-Jacobi plus a
+                              hierarchy of rigid-body aggregate coarse spaces                 */
+    int32_t ml_smooth_from;/* multilevel: first coarse level whose prolongator to the next level is smoothed,
+                              P = (I - w D^-1 A) T (0 = default 1; large = tentative prolongators everywhere)       */
+    double  ml_cell;       /* multilevel: brick edge of the first coarse level in mean beam lengths (<= 0: 2)      */
+    double  ml_ratio;      /* multilevel: growth of the brick edge per level (<= 1: 2)                              */
+    int64_t ml_coarsest_rows; /* multilevel: stop coarsening at this many rows (<= 0: 64; dense inverse there)      */
 } mbfea_options;
 
 typedef struct mbfea_stats {
@@ -118,7 +126,12 @@ typedef struct mbfea_stats {
     int32_t restarts;           /* residual replacements done by the solve             */
     int32_t n_components;       /* > 0: batched solve, one CTA per mesh; iterations = the
                                    slowest mesh's count                                 */
-    int32_t reserved[3];
+    int32_t precond;            /* preconditioner the last solve used: 1 block-Jacobi, 2 multilevel */
+    int32_t ml_levels;          /* multilevel: coarse levels below the fine one                      */
+    int32_t reserved;
+    double  ms_ml_symbolic;     /* multilevel: host hierarchy build + uploads inside set_job (wall)  */
+    double  ms_ml_setup;        /* multilevel: Galerkin products, smoothers, coarsest inverse (device time, part of ms_precond) */
+    double  bytes_ml_apply;     /* multilevel: algorithmic bytes of the two fine-level transfer kernels per apply */
 } mbfea_stats;
 
 int          mbfea_version(void);
@@ -326,6 +339,14 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
  * ratio: growth of the brick edge per level (<= 1: 2); coarsest_rows: stop coarsening at this many rows
  * (<= 0: 128).  Not covered by any parity claim; mbfea_solve / mbfea_execute do not use it.            */
 int mbfea_solve_multilevel(mbfea_ctx *ctx, double cell_beam_lengths, double ratio, int64_t coarsest_rows);
+/* ml_hierarchy: the level hierarchy mbfea_set_job builds for the multilevel preconditioner (options.precond = 2) of a
+ *           one-rank job, sizes only (host-only; CPU tests and set_job timing).  *n_levels: coarse levels; sizes[6 * l ..]
+ *           for the transfer from level l to l + 1: {rows of level l, rows of level l + 1, 6x6 blocks of level l + 1's
+ *           matrix, blocks of the prolongator, blocks of A P (0 on the fine level: contributor lists), smoothed 0/1}.
+ *           Arguments <= 0 select the defaults of mbfea_options.                                                        */
+int mbfea_host_ml_hierarchy(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
+                            const int32_t *fixed, double cell_beam_lengths, double ratio, int64_t coarsest_rows,
+                            int32_t smooth_from, int32_t max_levels, int32_t *n_levels, int64_t *sizes);
 /* spd_inverse: explicit inverse of a dense symmetric positive definite matrix (row-major n x n), the
  *           coarsest-level solve of that preconditioner; MBFEA_ESINGULAR on a non-positive pivot.    */
 int mbfea_host_spd_inverse(int64_t n, const double *A, double *Ainv);

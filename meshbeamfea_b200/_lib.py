@@ -24,7 +24,8 @@ class Options(C.Structure):
         ("check_every", C.c_int32), ("spmv_kernel", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("use_graph", C.c_int32), ("comm_mode", C.c_int32), ("storage", C.c_int32),
         ("cg_variant", C.c_int32), ("batch_mode", C.c_int32), ("reorder", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("precond", C.c_int32), ("ml_smooth_from", C.c_int32), ("ml_cell", C.c_double), ("ml_ratio", C.c_double),
+        ("ml_coarsest_rows", C.c_int64),
     ]
 
 
@@ -41,7 +42,8 @@ class Stats(C.Structure):
         ("bytes_spmv", C.c_double), ("bytes_pcg_iter", C.c_double), ("bytes_assemble", C.c_double),
         ("bytes_recover", C.c_double),
         ("kernel_launches", C.c_int64), ("converged", C.c_int32), ("restarts", C.c_int32),
-        ("n_components", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("n_components", C.c_int32), ("precond", C.c_int32), ("ml_levels", C.c_int32), ("reserved", C.c_int32),
+        ("ms_ml_symbolic", C.c_double), ("ms_ml_setup", C.c_double), ("bytes_ml_apply", C.c_double),
     ]
 
     def as_dict(self):
@@ -112,6 +114,8 @@ SIGNATURES = {
     "mbfea_host_renumber": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _pi32, _pi32]),
     "mbfea_host_contributors": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _i32, _pi64, _pi32, _pi32]),
     "mbfea_solve_multilevel": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _i64]),
+    "mbfea_host_ml_hierarchy": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, C.c_double, C.c_double, _i64, _i32, _i32,
+                                          _pi32, _pi64]),
     "mbfea_host_spd_inverse": (C.c_int, [_i64, _pd, _pd]),
     "mbfea_hierarchy_open": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, C.c_double, C.c_double, _i32, _i64,
                                        C.POINTER(C.c_void_p)]),

@@ -16,8 +16,10 @@
 #include <string>
 #include <vector>
 
+#include "devbuf.hpp"
 #include "kernels.cuh"
 #include "mbfea_internal.hpp"
+#include "mlprec.hpp"
 #include "multilevel_apply.hpp"
 #include "nccl_dl.hpp"
 
@@ -33,46 +35,6 @@ double now_ms()
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
-
-template <class T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0, cap = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { release(); }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr; n = 0; cap = 0;
-    }
-    // keeps the allocation when it is large enough (and not wastefully so): a second
-    // set_job on a same-sized mesh costs no cudaFree/cudaMalloc round trips
-    cudaError_t alloc(size_t count)
-    {
-        if (count == 0) count = 1;
-        if (p && cap >= count && cap <= 2 * count + 1024) { n = count; return cudaSuccess; }
-        release();
-        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
-        if (e == cudaSuccess) { n = count; cap = count; } else p = nullptr;
-        return e;
-    }
-};
-
-struct CudaFail { cudaError_t e; const char *what; int line; };
-struct NcclFail { int e; const char *what; int line; };
-
-#define CK(call)                                                        \
-    do {                                                                \
-        cudaError_t _e = (call);                                        \
-        if (_e != cudaSuccess) throw CudaFail{_e, #call, __LINE__};     \
-    } while (0)
-#define NK(call)                                                        \
-    do {                                                                \
-        int _e = (call);                                                \
-        if (_e != 0) throw NcclFail{_e, #call, __LINE__};               \
-    } while (0)
 
 }  // namespace
 
@@ -134,6 +96,10 @@ struct mbfea_ctx {
     DevBuf<int32_t> comp_ptr, comp_iters, comp_status;
     DevBuf<double> comp_rr, comp_ff;
     DevBuf<unsigned long long> trace;  // MBFEA_TRACE=1: globaltimer stamps of the first iterations
+
+    // multilevel preconditioner (options.precond): hierarchy built in set_job, numeric setup in assemble
+    MlPrec ml;
+    bool use_ml = false;
 
     // PCG graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -250,6 +216,7 @@ void run_spmv(mbfea_ctx *c, int kernel, const double *x, double *y, double *part
 // (one cross-GPU exchange and two kernels per iteration instead of two and three: -10 % at 4 GPUs)
 int cg_variant(const mbfea_ctx *c)
 {
+    if (c->use_ml) return 1;   // the preconditioned recurrence is the classic one (z~ = M r~ between update and p-update)
     if (c->opt.cg_variant == 1 || c->opt.cg_variant == 2) return c->opt.cg_variant;
     return c->opt.world > 1 ? 2 : 1;
 }
@@ -442,6 +409,14 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
         c->launches++;
     }
     launch_cg_update(c->st, nb, parity, pAp, c->p.p, c->Ap.p, c->y.p, c->rt.p, c->part_b.p, c->sc.p, nullptr);
+    if (c->use_ml) {
+        // z~ = M r~ (into sdir), rho = r~ . z~; the direction update takes z~ where plain CG takes r~
+        c->ml.apply(c->st, c->rt.p, c->sdir.p, c->part_b.p, gv);
+        launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, c->sdir.p, c->p.p, c->sc.p, nullptr, nullptr, nullptr,
+                          c->tickets.p + 2);
+        c->launches += 2 + c->ml.kernels_per_apply();
+        return;
+    }
     PartialRef rho{c->part_b.p, gv, 1};
     if (W > 1) {
         launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, nullptr, nullptr, c->sc.p);
@@ -605,6 +580,11 @@ void mbfea_options_default(mbfea_options *o)
     o->rank = 0;
     o->world = 1;
     o->use_graph = 1;
+    o->precond = 0;
+    o->ml_smooth_from = 0;
+    o->ml_cell = 0.0;
+    o->ml_ratio = 0.0;
+    o->ml_coarsest_rows = 0;
 }
 
 const char *mbfea_status_string(int s)
@@ -789,6 +769,11 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
         const bool half = !batched && (c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2));
         build_solver_format(c->plan, half);
+        // preconditioner: multilevel on one rank for a single large mesh (auto) or on request
+        c->use_ml = false;
+        c->ml.reset();
+        const bool ml_possible = c->opt.world == 1 && !batched && c->plan.nb_global >= 64;
+        const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
         build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
         build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
         c->tma_ok = true;
@@ -883,6 +868,34 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         upload_forces(c, nF, f_node, f_dof, f_mag);
         CK(cudaStreamSynchronize(c->st));
         lap("load vector");
+        if (ml_possible && ml_wanted) {
+            // positions of the block rows (internal numbering) and the mean beam length: the aggregates are bricks
+            std::vector<double> pos((size_t)3 * nb);
+            for (int64_t v = 0; v < V; ++v) {
+                const int32_t r = c->plan.free_index[(size_t)v];
+                if (r >= 0) for (int a = 0; a < 3; ++a) pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
+            }
+            double len = 0.0;
+            for (int64_t e = 0; e < E; ++e) {
+                double d2 = 0.0;
+                for (int a = 0; a < 3; ++a) {
+                    const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                    d2 += d * d;
+                }
+                len += std::sqrt(d2);
+            }
+            MlParams mp;
+            if (c->opt.ml_cell > 0.0) mp.cell = c->opt.ml_cell;
+            if (c->opt.ml_ratio > 1.0) mp.ratio = c->opt.ml_ratio;
+            if (c->opt.ml_coarsest_rows > 0) mp.coarsest_rows = std::min<int64_t>(c->opt.ml_coarsest_rows, 256);
+            if (c->opt.ml_smooth_from > 0) mp.smooth_from = c->opt.ml_smooth_from;
+            c->ml.par = mp;
+            c->use_ml = c->ml.build_symbolic(c->st, nb, c->plan.rowptr.data(), c->plan.colidx.data(), pos.data(), len / (double)E);
+            if (!c->use_ml && c->opt.precond == 2 && c->opt.verbose)
+                std::fprintf(stderr, "[mbfea] multilevel preconditioner requested but the mesh does not coarsen: block-Jacobi\n");
+            c->stats.ms_ml_symbolic = c->ml.ms_symbolic;
+            lap("multilevel hierarchy");
+        }
         setup_p2p_halo(c);
         c->stats.ms_h2d = now_ms() - t1;
 
@@ -896,6 +909,12 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         // a CG iteration adds 9 vector passes of 48 B per row
         s.bytes_spmv = 292.0 * (double)c->plan.ucol.size() + 8.0 * (double)c->plan.lcol.size() + 104.0 * (double)nb;
         s.bytes_pcg_iter = s.bytes_spmv + 432.0 * (double)nb;
+        // multilevel: restriction reads r~ (48) + T (144, FP32) + member id (4); prolongation reads r~, T, aggregate id and
+        // writes z~ (48); the p-update reads z~ in place of r~ (no change)
+        s.bytes_ml_apply = c->use_ml ? 440.0 * (double)nb : 0.0;
+        if (c->use_ml) s.bytes_pcg_iter += s.bytes_ml_apply;
+        s.precond = c->use_ml ? 2 : 1;
+        s.ml_levels = c->use_ml ? (int32_t)c->ml.levels() : 0;
         s.bytes_assemble = 112.0 * (double)E + 288.0 * (double)nnzb;
         s.bytes_recover = 208.0 * (double)E + 96.0 * (double)E;
         c->have_job = true;
@@ -903,6 +922,11 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             std::fprintf(stderr, "[mbfea] rank %d/%d: V=%lld E=%lld free=%lld rows=%lld blocks=%lld ghosts=%lld prep=%.1f ms h2d=%.1f ms\n",
                          c->opt.rank, c->opt.world, (long long)V, (long long)E, (long long)c->plan.nb_global,
                          (long long)nb, (long long)nnzb, (long long)ng, s.ms_host_prep, s.ms_h2d);
+        if (c->opt.verbose && c->use_ml) {
+            std::string rows;
+            for (int64_t r : c->ml.rows) rows += " " + std::to_string(r);
+            std::fprintf(stderr, "[mbfea] multilevel preconditioner: rows per level%s (hierarchy %.1f ms)\n", rows.c_str(), c->ml.ms_symbolic);
+        }
         return MBFEA_OK;
     });
 }
@@ -929,6 +953,11 @@ int mbfea_assemble(mbfea_ctx *c)
         do_assemble(c);
         CK(cudaEventRecord(c->ev[1], c->st));
         do_precond(c);
+        CK(cudaEventRecord(c->ev[6], c->st));
+        if (c->use_ml) {
+            c->ml.build_numeric(c->st, c->rowptr.p, c->colidx.p, c->vals.p, c->lfac.p, c->flag.p);
+            c->launches += c->ml.setup_launches;
+        }
         CK(cudaEventRecord(c->ev[2], c->st));
         // every rank takes the same exit: a non-SPD block on one rank fails the job on all of them (otherwise
         // the others would go on into the solve's collectives and hang)
@@ -938,9 +967,11 @@ int mbfea_assemble(mbfea_ctx *c)
         CK(cudaStreamSynchronize(c->st));
         c->stats.ms_assemble = elapsed(c, 0, 1);
         c->stats.ms_precond = elapsed(c, 1, 2);
+        c->stats.ms_ml_setup = c->use_ml ? elapsed(c, 6, 2) : 0.0;
         c->assembled = true; c->solved = c->recovered = false;
-        if (flag) return fail(c, MBFEA_ESINGULAR,
-                              "a diagonal 6x6 block is not positive definite (isolated vertex, zero-length or zero-stiffness beam)");
+        if (flag & 1) return fail(c, MBFEA_ESINGULAR,
+                                  "a diagonal 6x6 block is not positive definite (isolated vertex, zero-length or zero-stiffness beam)");
+        if (flag & 2) return fail(c, MBFEA_ESINGULAR, "the coarsest matrix of the multilevel preconditioner is not positive definite");
         return MBFEA_OK;
     });
 }
@@ -1032,6 +1063,11 @@ int mbfea_solve(mbfea_ctx *c)
             CK(cudaMemsetAsync(c->part_b.p, 0, sizeof(double) * kMaxPartials, c->st));
         } else {
             launch_cg_init(c->st, nb, c->f.p, c->sinv.p, c->y.p, c->rt.p, c->ft.p, c->p.p, c->part_b.p, c->part_c.p);
+            if (c->use_ml) {   // p0 = z~0 = M r~0, rho0 = r~0 . z~0
+                c->ml.apply(c->st, c->rt.p, c->sdir.p, c->part_b.p, gv);
+                CK(cudaMemcpyAsync(c->p.p, c->sdir.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+                c->launches += c->ml.kernels_per_apply();
+            }
         }
         PartialRef rho{c->part_b.p, gv, 1}, ff{c->part_c.p, gv, 1};
         if (W > 1) {
@@ -1135,6 +1171,12 @@ int mbfea_solve(mbfea_ctx *c)
             prev_true = rr_true;
             ++restarts;
             c->epoch++;
+            if (c->use_ml) {   // resume from the replaced residual: p = z~ = M r~, rho = r~ . z~
+                c->ml.apply(c->st, c->rt.p, c->sdir.p, c->part_b.p, gv);
+                CK(cudaMemcpyAsync(c->p.p, c->sdir.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+                launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 1, nullptr, nullptr, nullptr);
+                c->launches += 1 + c->ml.kernels_per_apply();
+            }
             launch_cg_restart_finish(c->st, trr, trho, c->sc.p, c->epoch, 1);
             c->launches++;
             if (c->p2p) {
@@ -1167,8 +1209,8 @@ int mbfea_solve(mbfea_ctx *c)
         s.restarts = restarts;
         c->solved = true; c->recovered = false;
         if (c->opt.verbose)
-            std::fprintf(stderr, "[mbfea] rank %d: CG %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d (%s storage), batch %d\n",
-                         c->opt.rank, (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel,
+            std::fprintf(stderr, "[mbfea] rank %d: %s %lld its, rel res %.3e (true %.3e), %.2f ms, spmv kernel %d (%s storage), batch %d\n",
+                         c->opt.rank, c->use_ml ? "multilevel PCG" : "CG", (long long)h.iter, s.rel_residual, s.true_rel_residual, s.ms_pcg, kernel,
                          c->plan.sym_half ? (c->plan.balanced ? "symmetric-half, balanced" : "symmetric-half") : "full-row", check);
         if (c->opt.verbose && restarts)
             std::fprintf(stderr, "[mbfea] rank %d: %d residual replacement(s)\n", c->opt.rank, restarts);
@@ -1963,6 +2005,56 @@ int mbfea_solve_multilevel(mbfea_ctx *c, double cell_beam_lengths, double ratio,
         if (h.done == 2) return fail(c, MBFEA_ENOCONV, "multilevel PCG reached max_iter before the requested tolerance");
         return MBFEA_OK;
     });
+}
+
+int mbfea_host_ml_hierarchy(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
+                            const int32_t *fixed, double cell_beam_lengths, double ratio, int64_t coarsest_rows,
+                            int32_t smooth_from, int32_t max_levels, int32_t *n_levels, int64_t *sizes)
+{
+    if (V <= 0 || E <= 0 || !nodes_cm || !elems_cm || !n_levels || (F > 0 && !fixed) || max_levels < 1) return MBFEA_EARG;
+    for (int64_t e = 0; e < 2 * E; ++e)
+        if (elems_cm[e] < 0 || elems_cm[e] >= V) return MBFEA_EPRECOND;
+    for (int64_t i = 0; i < F; ++i)
+        if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
+    try {
+        HostPlan P;
+        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, P);
+        const int64_t nb = P.nb();
+        std::vector<double> pos((size_t)3 * std::max<int64_t>(nb, 1));
+        for (int64_t v = 0; v < V; ++v)
+            if (P.free_index[(size_t)v] >= 0)
+                for (int a = 0; a < 3; ++a) pos[(size_t)3 * P.free_index[(size_t)v] + a] = nodes_cm[(size_t)a * V + v];
+        double sum = 0.0;
+        for (int64_t e = 0; e < E; ++e) {
+            double d2 = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                d2 += d * d;
+            }
+            sum += std::sqrt(d2);
+        }
+        MlParams mp;
+        if (cell_beam_lengths > 0.0) mp.cell = cell_beam_lengths;
+        if (ratio > 1.0) mp.ratio = ratio;
+        if (coarsest_rows > 0) mp.coarsest_rows = coarsest_rows;
+        if (smooth_from > 0) mp.smooth_from = smooth_from;
+        MlHierarchy H;
+        build_ml_hierarchy(nb, P.rowptr.data(), P.colidx.data(), pos.data(), mp.cell * sum / (double)E, mp.ratio, mp.max_levels,
+                           mp.coarsest_rows, mp.smooth_from, H);
+        *n_levels = (int32_t)H.levels();
+        for (size_t l = 0; l < H.levels() && (int32_t)l < max_levels && sizes; ++l) {
+            const bool gen = l >= 1;
+            sizes[6 * l + 0] = H.agg[l].n_fine;
+            sizes[6 * l + 1] = H.agg[l].n_coarse;
+            sizes[6 * l + 2] = gen ? (int64_t)H.xfer[l].ccol.size() : (int64_t)H.agg[l].colidx.size();   // blocks of the next level's matrix
+            sizes[6 * l + 3] = gen ? (int64_t)H.xfer[l].pcol.size() : H.agg[l].n_fine;                    // blocks of P
+            sizes[6 * l + 4] = gen ? (int64_t)H.xfer[l].apcol.size() : 0;                                 // blocks of A P
+            sizes[6 * l + 5] = gen && H.xfer[l].smoothed ? 1 : 0;
+        }
+    } catch (const std::bad_alloc &) {
+        return MBFEA_EARG;
+    }
+    return MBFEA_OK;
 }
 
 int mbfea_host_spd_inverse(int64_t n, const double *A, double *Ainv)

@@ -9,7 +9,10 @@
 // rigid-body modes of its members about their centroid: a member at offset d = x - centroid moves by
 // u = t + w x d, theta = w, i.e. its 6x6 prolongation block is B(d) = [[I, -[d]x], [0, I]].
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -17,6 +20,21 @@
 #include "mbfea_internal.hpp"
 
 namespace mbfea {
+
+namespace {
+struct Lap {   // MBFEA_PREP_TRACE=1: wall time of the passes of the hierarchy build
+    bool on = std::getenv("MBFEA_PREP_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void operator()(const char *what, int64_t n)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mbfea hierarchy] n=%-9lld %-28s %8.2f ms\n", (long long)n, what,
+                     std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
 
 template <class Fn>
 static void par_ranges(int64_t n, int64_t min_per_thread, Fn fn)
@@ -30,8 +48,9 @@ static void par_ranges(int64_t n, int64_t min_per_thread, Fn fn)
 }
 
 static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *pos, double cell,
-                        HierLevel &L)
+                        HierLevel &L, bool with_galerkin_lists = true)
 {
+    Lap lap;
     L.n_fine = n;
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int64_t v = 0; v < n; ++v)
@@ -49,6 +68,7 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
             brick[(size_t)v] = (c[0] * cnt[1] + c[1]) * cnt[2] + c[2];
         }
     });
+    lap("bricks", n);
     L.agg.assign((size_t)n, 0);
     L.agg_ptr.clear(); L.agg_rows.resize((size_t)n);
     int32_t na = 0;
@@ -85,6 +105,7 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
     }
     L.agg_ptr.push_back((int32_t)n);
     L.n_coarse = na;
+    lap("aggregate lists", n);
     L.centroid.assign((size_t)3 * na, 0.0);
     par_ranges(na, 1 << 12, [&](int64_t b0, int64_t b1) {
         for (int64_t I = b0; I < b1; ++I) {
@@ -100,6 +121,8 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
         for (int64_t v = b0; v < b1; ++v)
             for (int a = 0; a < 3; ++a) L.off[(size_t)3 * v + a] = pos[3 * v + a] - L.centroid[(size_t)3 * L.agg[(size_t)v] + a];
     });
+    lap("centroids + offsets", n);
+    if (!with_galerkin_lists) return;   // coarse-to-coarse transfers build their own patterns (build_transfer)
     // coarse pattern: aggregate I couples to agg(col) of every block of its member rows.  Two passes (count,
     // fill) over ranges of aggregates, each thread with its own scratch.
     L.rowptr.assign((size_t)na + 1, 0);
@@ -127,6 +150,7 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
     // B(off a)^T A(a, b) B(off b); per coarse block the fine blocks are listed in ascending k.  The lists of coarse
     // row I come from I's member rows only (ascending rows => ascending k), so aggregates are independent: count,
     // prefix, fill -- both passes parallel over aggregates.
+    lap("coarse pattern", n);
     const int64_t nnz_f = rowptr[n], nnz_c = (int64_t)L.colidx.size();
     L.gal_ptr.assign((size_t)nnz_c + 1, 0);
     auto for_blocks_of = [&](int64_t I, auto &&visit) {   // visit(coarse block index, fine block index), fine ascending
@@ -150,6 +174,121 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
             for_blocks_of(I, [&](int32_t kc, int32_t k) { L.gal_src[(size_t)cur[(size_t)(kc - c0)]++] = k; });
         }
     });
+    lap("galerkin lists", n);
+}
+
+// Symbolic structures of one coarse-to-coarse transfer (see MlTransfer).  (rowptr, colidx): pattern of level l's
+// matrix (diagonal present), L: its aggregates.
+static void build_transfer(int64_t n, const int32_t *rowptr, const int32_t *colidx, const HierLevel &L, bool smoothed,
+                           MlTransfer &T)
+{
+    Lap lap;
+    const int64_t nc = L.n_coarse;
+    T.smoothed = smoothed; T.n_fine = n; T.n_coarse = nc;
+    // rows of a pattern built in two parallel passes (count, fill) from a per-row generator that pushes candidate
+    // columns through `add` (a per-thread marker array removes duplicates before the row is sorted)
+    struct Dedup {
+        std::vector<int32_t> mark, out;
+        int32_t stamp = 0;
+        void begin(int32_t row) { stamp = row; out.clear(); }
+        void add(int32_t c) { if (mark[(size_t)c] != stamp) { mark[(size_t)c] = stamp; out.push_back(c); } }
+    };
+    auto build_rows = [&](int64_t rows, int64_t ncols, int64_t min_per_thread, std::vector<int32_t> &rp, std::vector<int32_t> &ci, auto &&gen) {
+        rp.assign((size_t)rows + 1, 0);
+        std::vector<std::vector<int32_t>> keep((size_t)rows);   // rows are generated once; the fill pass only copies
+        par_ranges(rows, min_per_thread, [&](int64_t b0, int64_t b1) {
+            Dedup d;
+            d.mark.assign((size_t)ncols, -1);
+            for (int64_t i = b0; i < b1; ++i) {
+                d.begin((int32_t)i);
+                gen(i, d);
+                std::sort(d.out.begin(), d.out.end());
+                rp[(size_t)i + 1] = (int32_t)d.out.size();
+                keep[(size_t)i] = d.out;
+            }
+        });
+        for (int64_t i = 0; i < rows; ++i) rp[(size_t)i + 1] += rp[(size_t)i];
+        ci.resize((size_t)rp[(size_t)rows]);
+        par_ranges(rows, 1 << 12, [&](int64_t b0, int64_t b1) {
+            for (int64_t i = b0; i < b1; ++i) std::copy(keep[(size_t)i].begin(), keep[(size_t)i].end(), ci.begin() + rp[(size_t)i]);
+        });
+    };
+    // P: row i couples to agg(j) of every block (i, j) when smoothed, to agg(i) alone otherwise
+    build_rows(n, nc, 1 << 10, T.prow, T.pcol, [&](int64_t i, Dedup &d) {
+        d.add(L.agg[(size_t)i]);
+        if (smoothed)
+            for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) d.add(L.agg[(size_t)colidx[k]]);
+    });
+    T.pown.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i)
+        T.pown[(size_t)i] = (int32_t)(std::lower_bound(T.pcol.begin() + T.prow[(size_t)i], T.pcol.begin() + T.prow[(size_t)i + 1],
+                                                       L.agg[(size_t)i]) - T.pcol.begin());
+    lap("P pattern", n);
+    // transpose structure (counting sort by column keeps block indices, hence fine rows, ascending)
+    const int64_t nnzp = (int64_t)T.pcol.size();
+    T.rrow.assign((size_t)nc + 1, 0);
+    for (int64_t b = 0; b < nnzp; ++b) T.rrow[(size_t)T.pcol[(size_t)b] + 1]++;
+    for (int64_t I = 0; I < nc; ++I) T.rrow[(size_t)I + 1] += T.rrow[(size_t)I];
+    T.rblk.resize((size_t)nnzp); T.rfine.resize((size_t)nnzp);
+    {
+        std::vector<int32_t> cur(T.rrow.begin(), T.rrow.end() - 1);
+        for (int64_t i = 0; i < n; ++i)
+            for (int32_t b = T.prow[(size_t)i]; b < T.prow[(size_t)i + 1]; ++b) {
+                const int32_t slot = cur[(size_t)T.pcol[(size_t)b]]++;
+                T.rblk[(size_t)slot] = b; T.rfine[(size_t)slot] = (int32_t)i;
+            }
+    }
+    lap("P transpose", n);
+    // A P: row i couples to the P columns of every k with a block (i, k)
+    build_rows(n, nc, 64, T.aprow, T.apcol, [&](int64_t i, Dedup &d) {
+        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int32_t j = colidx[k];
+            for (int32_t b = T.prow[(size_t)j]; b < T.prow[(size_t)j + 1]; ++b) d.add(T.pcol[(size_t)b]);
+        }
+    });
+    lap("A P pattern", n);
+    // P^T (A P): coarse row I couples to the A P columns of every fine row with a P block in column I
+    build_rows(nc, nc, 8, T.crow, T.ccol, [&](int64_t I, Dedup &d) {
+        d.add((int32_t)I);
+        for (int32_t e = T.rrow[(size_t)I]; e < T.rrow[(size_t)I + 1]; ++e) {
+            const int32_t i = T.rfine[(size_t)e];
+            for (int32_t b = T.aprow[(size_t)i]; b < T.aprow[(size_t)i + 1]; ++b) d.add(T.apcol[(size_t)b]);
+        }
+    });
+    lap("P^T A P pattern", n);
+    T.cdiag.resize((size_t)nc);
+    for (int64_t I = 0; I < nc; ++I)
+        T.cdiag[(size_t)I] = (int32_t)(std::lower_bound(T.ccol.begin() + T.crow[(size_t)I], T.ccol.begin() + T.crow[(size_t)I + 1],
+                                                        (int32_t)I) - T.ccol.begin());
+}
+
+void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
+                        double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H)
+{
+    H.agg.clear(); H.xfer.clear();
+    if (nb <= 0 || !(cell0 > 0.0) || !(ratio > 1.0)) return;
+    std::vector<double> pos(pos_rm, pos_rm + 3 * nb);
+    std::vector<int32_t> rp, ci;                      // pattern of the current level (level 0: the caller's arrays)
+    const int32_t *crp = rowptr, *cci = colidx;
+    double cell = cell0;
+    int64_t n = nb;
+    for (int l = 0; l + 1 < max_levels && n > coarsest_rows; ++l) {
+        HierLevel L;
+        build_level(n, crp, cci, pos.data(), cell, L, /*with_galerkin_lists=*/l == 0);
+        if (L.n_coarse >= n) break;   // no coarsening at this cell size: stop
+        MlTransfer T;
+        if (l >= 1) {
+            build_transfer(n, crp, cci, L, l >= smooth_from, T);
+            rp = T.crow; ci = T.ccol;
+        } else {
+            rp = L.rowptr; ci = L.colidx;
+        }
+        crp = rp.data(); cci = ci.data();
+        pos = L.centroid; n = L.n_coarse;
+        H.agg.push_back(std::move(L));
+        H.xfer.push_back(std::move(T));
+        cell *= ratio;
+    }
 }
 
 void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,

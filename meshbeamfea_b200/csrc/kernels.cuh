@@ -185,4 +185,29 @@ void launch_ml_prolong(cudaStream_t st, int64_t n, const int32_t *agg, const dou
 void launch_ml_finish(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const double *off, const double *lfac,
                       const double *rt, const double *z1, double *zt, double *part);
 
+// ---- multilevel preconditioner, production kernels (mlprec.cu) ----------------------------------------------
+void launch_ml_make_t0(cudaStream_t st, int64_t nb, const double *lfac, const double *off, float *t0);
+void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv);
+void launch_ml_row_of(cudaStream_t st, int64_t n, const int32_t *rowptr, int32_t *row_of);
+void launch_ml_make_p(cudaStream_t st, int64_t n, int64_t nnzp, const int32_t *prow, const int32_t *pcol, const int32_t *prow_of,
+                      const int32_t *arow, const int32_t *acol, const double *avals, const int32_t *agg, const double *off,
+                      const double *dinv, double omega, double *pval);
+void launch_ml_ap(cudaStream_t st, int64_t n, int64_t nnzc, const int32_t *crow, const int32_t *ccol, const int32_t *crow_of,
+                  const int32_t *arow, const int32_t *acol, const double *avals, const int32_t *prow, const int32_t *pcol,
+                  const double *pval, double *cval);
+void launch_ml_rap(cudaStream_t st, int64_t nc, int64_t nnzg, const int32_t *grow, const int32_t *gcol, const int32_t *grow_of,
+                   const int32_t *rrow, const int32_t *rblk, const int32_t *rfine, const double *pval, const int32_t *crow,
+                   const int32_t *ccol, const double *cval, double *gval);
+void launch_ml_blocks_to_dense(cudaStream_t st, int64_t nrows, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
+                               const int32_t *row_of, const double *vals, double *dense);
+void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, int *flag);
+void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_t *agg_ptr, const int32_t *agg_rows,
+                         const float *t0, const double *r, double *rc);
+void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
+                       const double *z1, double *zt, double *part);
+void launch_ml_restrict(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
+                        const double *pval, const double *r, double *rc);
+void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const double *dinv, const int32_t *prow, const int32_t *pcol,
+                              const double *pval, const double *r, const double *zc, double *z);
+
 }}  // namespace mbfea::dev

@@ -125,6 +125,33 @@ struct Hierarchy { std::vector<HierLevel> levels; };
 void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
                      double ratio, int max_levels, int64_t coarsest_rows, Hierarchy &H);
 
+// ---------------------------------------------------------------------------
+// Multilevel preconditioner, symbolic half (host, once per set_job; hierarchy.cpp).
+// Level 0 is the reduced system; level l+1 rows are brick aggregates of level l carrying 6 rigid-body
+// unknowns.  The transfer from the fine level is the TENTATIVE prolongator (one rigid block per row) and its
+// Galerkin product runs over HierLevel's contributor lists.  Transfers between coarse levels are general
+// 6x6-block sparse matrices P (tentative, or smoothed: P = (I - w D^-1 A) T, pattern = A's pattern mapped
+// through the aggregates) with the structures the device kernels walk: P's transpose (restriction as a
+// gather), the pattern of A P and of the next level's matrix P^T A P.  Columns ascend in every row.
+// ---------------------------------------------------------------------------
+struct MlTransfer {
+    bool smoothed = false;
+    int64_t n_fine = 0, n_coarse = 0;
+    std::vector<int32_t> prow, pcol;           // P: n_fine rows
+    std::vector<int32_t> pown;                 // n_fine: index in pcol of the block (i, agg i)
+    std::vector<int32_t> rrow, rblk, rfine;    // per coarse row: the P blocks of that column (ascending) and their fine rows
+    std::vector<int32_t> aprow, apcol;         // A P: n_fine rows
+    std::vector<int32_t> crow, ccol, cdiag;    // next level's matrix: n_coarse rows, diagonal position per row
+};
+struct MlHierarchy {
+    std::vector<HierLevel> agg;       // agg[l]: aggregates of level l (l = 0: fine level, with Galerkin contributor lists)
+    std::vector<MlTransfer> xfer;     // xfer[l] for l >= 1 (xfer[0] unused: the fine transfer is implicit in agg[0])
+    size_t levels() const { return agg.size(); }   // number of coarse levels
+};
+// smooth_from: first level whose prolongator is smoothed (1 = every coarse-to-coarse transfer; large = none)
+void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
+                        double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H);
+
 // Explicit inverse of a dense SPD matrix (row-major n x n) for the coarsest level; 0, or 1 + the index of
 // the first non-positive pivot (dense.cpp).
 int dense_spd_inverse(int64_t n, const double *A, double *Ainv);

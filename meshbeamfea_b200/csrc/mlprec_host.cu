@@ -1,0 +1,145 @@
+// Host driver of the multilevel preconditioner (see mlprec.hpp).
+#include "mlprec.hpp"
+
+#include <algorithm>
+#include <chrono>
+
+#include "kernels.cuh"
+
+namespace mbfea {
+
+using namespace mbfea::dev;
+
+namespace {
+template <class T>
+void up(cudaStream_t st, DevBuf<T> &d, const std::vector<T> &h)
+{
+    CK(d.alloc(h.size()));
+    if (!h.empty()) CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+double wall_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+void MlPrec::reset()
+{
+    symbolic_ok = numeric_ok = false;
+    lv.clear();
+    rows.clear();
+    nb = 0;
+}
+
+bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
+                            double mean_len)
+{
+    const double t0w = wall_ms();
+    reset();
+    nb = nb_;
+    if (nb <= 0 || !(mean_len > 0.0)) return false;
+    MlHierarchy H;
+    build_ml_hierarchy(nb, h_rowptr, h_colidx, pos_rm, par.cell * mean_len, par.ratio, par.max_levels, par.coarsest_rows,
+                       std::max(1, par.smooth_from), H);
+    const size_t L = H.levels();
+    if (L == 0) return false;
+    if (6 * H.agg[L - 1].n_coarse > 2048) return false;   // the chain stopped early (max_levels): no dense inverse that large
+    // level 0 -> 1
+    const HierLevel &h0 = H.agg[0];
+    up(st, agg0, h0.agg); up(st, agg_ptr0, h0.agg_ptr); up(st, agg_rows0, h0.agg_rows);
+    up(st, gal_ptr0, h0.gal_ptr); up(st, gal_src0, h0.gal_src); up(st, off0, h0.off);
+    CK(frow0.alloc((size_t)h_rowptr[nb]));
+    CK(t0.alloc((size_t)nb * 36));
+    int32_t biggest = 0;
+    for (int64_t I = 0; I < h0.n_coarse; ++I) biggest = std::max(biggest, h0.agg_ptr[(size_t)I + 1] - h0.agg_ptr[(size_t)I]);
+    group0 = biggest <= 8 ? 8 : 32;
+    rows.push_back(nb);
+    for (size_t m = 0; m < L; ++m) {
+        std::unique_ptr<MlCoarse> c(new MlCoarse);
+        const std::vector<int32_t> &rp = m == 0 ? h0.rowptr : H.xfer[m].crow;
+        const std::vector<int32_t> &ci = m == 0 ? h0.colidx : H.xfer[m].ccol;
+        c->n = (int64_t)rp.size() - 1;
+        c->nnz = (int64_t)ci.size();
+        rows.push_back(c->n);
+        up(st, c->rowptr, rp); up(st, c->colidx, ci);
+        std::vector<int32_t> diag((size_t)c->n);
+        for (int64_t I = 0; I < c->n; ++I)
+            diag[(size_t)I] = (int32_t)(std::lower_bound(ci.begin() + rp[(size_t)I], ci.begin() + rp[(size_t)I + 1], (int32_t)I) - ci.begin());
+        up(st, c->diag_idx, diag);
+        CK(c->row_of.alloc((size_t)c->nnz));
+        CK(c->vals.alloc((size_t)c->nnz * 36));
+        CK(c->r.alloc((size_t)c->n * 6)); CK(c->z.alloc((size_t)c->n * 6));
+        launch_ml_row_of(st, c->n, c->rowptr.p, c->row_of.p);
+        if (m + 1 < L) {   // transfer from level m + 1 to level m + 2
+            const HierLevel &h = H.agg[m + 1];
+            const MlTransfer &T = H.xfer[m + 1];
+            c->has_next = true; c->smoothed = T.smoothed; c->n_next = T.n_coarse;
+            c->nnzp = (int64_t)T.pcol.size(); c->nnzap = (int64_t)T.apcol.size();
+            up(st, c->agg, h.agg); up(st, c->off, h.off);
+            up(st, c->prow, T.prow); up(st, c->pcol, T.pcol);
+            up(st, c->rrow, T.rrow); up(st, c->rblk, T.rblk); up(st, c->rfine, T.rfine);
+            up(st, c->aprow, T.aprow); up(st, c->apcol, T.apcol);
+            CK(c->prow_of.alloc((size_t)c->nnzp)); CK(c->aprow_of.alloc((size_t)c->nnzap));
+            launch_ml_row_of(st, c->n, c->prow.p, c->prow_of.p);
+            launch_ml_row_of(st, c->n, c->aprow.p, c->aprow_of.p);
+            CK(c->pval.alloc((size_t)c->nnzp * 36)); CK(c->apval.alloc((size_t)c->nnzap * 36));
+            CK(c->lfac.alloc((size_t)c->n * 36)); CK(c->sinv.alloc((size_t)c->n * 36)); CK(c->dinv.alloc((size_t)c->n * 36));
+        }
+        lv.push_back(std::move(c));
+    }
+    n_dense = 6 * lv.back()->n;
+    CK(dense.alloc((size_t)(n_dense * n_dense)));
+    CK(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+    symbolic_ok = true;
+    ms_symbolic = wall_ms() - t0w;
+    return true;
+}
+
+void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_vals,
+                           const double *d_lfac, int *d_flag)
+{
+    numeric_ok = false;
+    if (!symbolic_ok) return;
+    int64_t k = 0;
+    launch_ml_row_of(st, nb, d_rowptr, frow0.p);
+    launch_ml_make_t0(st, nb, d_lfac, off0.p, t0.p);
+    launch_ml_galerkin(st, lv[0]->nnz, gal_ptr0.p, gal_src0.p, frow0.p, d_colidx, d_vals, off0.p, lv[0]->vals.p);
+    k += 3;
+    for (size_t m = 0; m < lv.size(); ++m) {
+        MlCoarse &c = *lv[m];
+        if (!c.has_next) break;
+        MlCoarse &nx = *lv[m + 1];
+        launch_block_chol(st, c.n, c.diag_idx.p, c.vals.p, c.lfac.p, c.sinv.p, d_flag);
+        launch_ml_diag_inv(st, c.n, c.sinv.p, c.dinv.p);
+        launch_ml_make_p(st, c.n, c.nnzp, c.prow.p, c.pcol.p, c.prow_of.p, c.rowptr.p, c.colidx.p, c.vals.p, c.agg.p, c.off.p,
+                         c.dinv.p, c.smoothed ? par.omega : 0.0, c.pval.p);
+        launch_ml_ap(st, c.n, c.nnzap, c.aprow.p, c.apcol.p, c.aprow_of.p, c.rowptr.p, c.colidx.p, c.vals.p, c.prow.p, c.pcol.p,
+                     c.pval.p, c.apval.p);
+        launch_ml_rap(st, nx.n, nx.nnz, nx.rowptr.p, nx.colidx.p, nx.row_of.p, c.rrow.p, c.rblk.p, c.rfine.p, c.pval.p, c.aprow.p,
+                      c.apcol.p, c.apval.p, nx.vals.p);
+        k += 5;
+    }
+    MlCoarse &last = *lv.back();
+    CK(cudaMemsetAsync(dense.p, 0, (size_t)(n_dense * n_dense) * sizeof(double), st));
+    launch_ml_blocks_to_dense(st, last.n, last.nnz, last.rowptr.p, last.colidx.p, last.row_of.p, last.vals.p, dense.p);
+    launch_ml_dense_inverse(st, (int)n_dense, dense.p, d_flag);
+    k += 2;
+    setup_launches = k;
+    numeric_ok = true;
+}
+
+void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, int grid)
+{
+    const size_t L = lv.size();
+    launch_ml_restrict0(st, lv[0]->n, group0, agg_ptr0.p, agg_rows0.p, t0.p, rt, lv[0]->r.p);
+    for (size_t m = 0; m + 1 < L; ++m)
+        launch_ml_restrict(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->pval.p, lv[m]->r.p, lv[m + 1]->r.p);
+    launch_ml_dense_matvec(st, n_dense, dense.p, lv[L - 1]->r.p, lv[L - 1]->z.p);
+    for (size_t m = L - 1; m-- > 0;)
+        launch_ml_smooth_prolong(st, lv[m]->n, lv[m]->dinv.p, lv[m]->prow.p, lv[m]->pcol.p, lv[m]->pval.p, lv[m]->r.p,
+                                 lv[m + 1]->z.p, lv[m]->z.p);
+    launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part);
+}
+
+}  // namespace mbfea

@@ -141,7 +141,8 @@ class Context:
     """One ``mbfea_ctx``: device buffers, stream, PCG graph, optional NCCL comm."""
 
     def __init__(self, device: int = -1, tol: float = 1e-8, max_iter: int = 0, verbose: bool = False,
-                 spmv_kernel: int = 0, check_every: int = 0, use_graph: bool = True, comm_mode: int = 0, storage: int = 0, cg_variant: int = 0, batch_mode: int = 0, reorder: int = 0):
+                 spmv_kernel: int = 0, check_every: int = 0, use_graph: bool = True, comm_mode: int = 0, storage: int = 0, cg_variant: int = 0, batch_mode: int = 0, reorder: int = 0,
+                 precond: int = 0, ml_cell: float = 0.0, ml_ratio: float = 0.0, ml_coarsest_rows: int = 0, ml_smooth_from: int = 0):
         self._lib = L.lib()
         o = Options()
         self._lib.mbfea_options_default(C.byref(o))
@@ -152,6 +153,7 @@ class Context:
         o.cg_variant = cg_variant
         o.batch_mode = batch_mode
         o.reorder = reorder
+        o.precond, o.ml_cell, o.ml_ratio, o.ml_coarsest_rows, o.ml_smooth_from = precond, ml_cell, ml_ratio, ml_coarsest_rows, ml_smooth_from
         self._h = C.c_void_p()
         rc = self._lib.mbfea_create(C.byref(self._h), C.byref(o))
         if rc != L.OK:

@@ -200,6 +200,62 @@ def _lu_solve(A, rhs, refine: int):
     return x
 
 
+def residual_dd(A_csr, x_hi, x_lo, f) -> np.ndarray:
+    """r = f - A (x_hi + x_lo) with double-double products and sums (orc_csr_residual_dd), rounded to double."""
+    A = A_csr.tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    rp = np.ascontiguousarray(A.indptr, np.int64); ci = np.ascontiguousarray(A.indices, np.int32)
+    va = np.ascontiguousarray(A.data, np.float64)
+    xh = np.ascontiguousarray(x_hi, np.float64)
+    xl = None if x_lo is None else np.ascontiguousarray(x_lo, np.float64)
+    ff = np.ascontiguousarray(f, np.float64)
+    r = np.empty(n)
+    L = lib()
+    L.orc_csr_residual_dd.restype = None
+    L.orc_csr_residual_dd(C.c_int64(n), _p(rp, _pi64), _p(ci, _pi32), _p(va, _pd), _p(xh, _pd),
+                          _p(xl, _pd) if xl is not None else None, _p(ff, _pd), _p(r, _pd))
+    return r
+
+
+def solve_dd(job: Job, steps: int = 6):
+    """Higher-precision reference: SuperLU factors of the eliminated system + iterative refinement whose residual
+    and solution update are carried in double-double.  Each step gains ~ -log10(kappa * 1e-16) digits, so a few
+    steps reach the exact solution of the FP64-represented system to far below 1e-8 even at kappa ~ 1e10
+    (planar 100 x 100 cantilever).  Returns (U (V,6) rounded to double, edge forces from it, history of
+    ||f - K x|| / ||f|| per step)."""
+    import scipy.sparse.linalg as spla
+    V = job.nodes.shape[0]
+    props = beam_props(job.dims, job.material)
+    K = assemble_full(job, props)
+    f = load_vector(V, job.forces)
+    fm = free_map(V, job.fixed)
+    free_dofs = (6 * np.nonzero(fm >= 0)[0][:, None] + np.arange(6)[None, :]).ravel()
+    Kr = K[free_dofs][:, free_dofs].tocsr()
+    fr = np.ascontiguousarray(f[free_dofs])
+    lu = spla.splu(Kr.tocsc())
+    xh = lu.solve(fr)
+    xl = np.zeros_like(xh)
+    nf = np.linalg.norm(fr)
+    hist = []
+    for _ in range(steps):
+        r = residual_dd(Kr, xh, xl, fr)
+        hist.append(float(np.linalg.norm(r) / nf))
+        d = lu.solve(r)
+        s = xh + d
+        bb = s - xh
+        e = (xh - (s - bb)) + (d - bb)
+        xl = xl + e
+        xh = s + xl
+        xl = xl - (xh - s)
+    hist.append(float(np.linalg.norm(residual_dd(Kr, xh, xl, fr)) / nf))
+    u = np.zeros(6 * V)
+    u[free_dofs] = xh
+    U = u.reshape(V, 6)
+    F, _ = element_forces(job, U, props)
+    return U, F, hist
+
+
 def solve(job: Job, form: str = "eliminate", refine: int = 2):
     """Full pipeline with a sparse direct solve.
 
