@@ -99,7 +99,7 @@ typedef struct mbfea_options {
                               P = (I - w D^-1 A) T (0 = default 1; large = tentative prolongators everywhere)       */
     double  ml_cell;       /* multilevel: brick edge of the first coarse level in mean beam lengths (<= 0: 2)      */
     double  ml_ratio;      /* multilevel: growth of the brick edge per level (<= 1: 2)                              */
-    int64_t ml_coarsest_rows; /* multilevel: stop coarsening at this many rows (<= 0: 64; dense inverse there)      */
+    int64_t ml_coarsest_rows; /* multilevel: stop coarsening at this many rows (<= 0: 512; dense inverse there)      */
 } mbfea_options;
 
 typedef struct mbfea_stats {
@@ -322,8 +322,8 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
                              int32_t *uptr, int32_t *ucol, int32_t *lptr, int32_t *lcol, int32_t *lofs,
                              int32_t *tile_base, int32_t *perm);
 
-/* hierarchy: host half of the multilevel (rigid-body aggregate) preconditioner that is the next
- *           widening of the solver -- NOT used by mbfea_solve yet.  Builds, for a
+/* hierarchy: aggregates and tentative Galerkin structures of the multilevel (rigid-body aggregate) preconditioner
+ *           (options.precond = 2), exposed for the CPU tests.  Builds, for a
  *           one-rank job in the canonical reduced numbering, the chain of coarse levels: aggregates =
  *           bricks of edge cell0 * ratio^l over the free vertices' bounding box, 6 rigid-body degrees of
  *           freedom each.  cell0 <= 0 selects 4 x the mean beam length.
@@ -333,12 +333,6 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
  *            rowptr[coarse rows + 1], colidx[coarse blocks], gal_ptr[coarse blocks + 1],
  *            gal_src[fine blocks] (indices into the finer level's block pattern, ascending per coarse
  *            block; level 0's finer pattern is mbfea_plan_partition's with world = 1).  Any may be NULL. */
-/* EXPERIMENTAL and UNVALIDATED on hardware (see csrc/multilevel.cu): mbfea_solve with the additive multilevel
- * preconditioner -- one rank, one mesh, after mbfea_assemble; results through the usual getters after
- * mbfea_recover.  cell_beam_lengths: brick edge of the first coarse level in mean beam lengths (<= 0: 2);
- * ratio: growth of the brick edge per level (<= 1: 2); coarsest_rows: stop coarsening at this many rows
- * (<= 0: 128).  Not covered by any parity claim; mbfea_solve / mbfea_execute do not use it.            */
-int mbfea_solve_multilevel(mbfea_ctx *ctx, double cell_beam_lengths, double ratio, int64_t coarsest_rows);
 /* ml_hierarchy: the level hierarchy mbfea_set_job builds for the multilevel preconditioner (options.precond = 2) of a
  *           one-rank job, sizes only (host-only; CPU tests and set_job timing).  *n_levels: coarse levels; sizes[6 * l ..]
  *           for the transfer from level l to l + 1: {rows of level l, rows of level l + 1, 6x6 blocks of level l + 1's

@@ -1451,11 +1451,13 @@ __global__ void __launch_bounds__(kSpmvThreads) k_cg_check(int64_t nb, const dou
     }
 }
 
-// Residual replacement (restart): r~ := f~ - K~ y (the recomputed residual), direction := r~ (classic)
-// or 0 (single-reduction); partials of ||L r~||^2 and of rho = r~.r~
-__global__ void __launch_bounds__(kSpmvThreads) k_cg_restart(int64_t nb, const double *__restrict__ lfac,
-                                                             const double *__restrict__ ft,
-                                                             const double *__restrict__ Ky, double *__restrict__ res,
+// Residual replacement (restart) from the ASSEMBLED matrix: w = f - K x (x = S^T y, K the unscaled full-pattern
+// matrix exactly as assembled -- not the scaled, symmetrised K~ the iteration multiplies with, whose entries carry
+// a few ulp of rounding that an ill-conditioned system amplifies into the solution), r~ := S w, direction := r~
+// (classic) or 0 (single-reduction); partials of ||w||^2 = ||f - K x||^2 and of rho = r~.r~
+__global__ void __launch_bounds__(kSpmvThreads) k_cg_restart(int64_t nb, const double *__restrict__ sinv,
+                                                             const double *__restrict__ f,
+                                                             const double *__restrict__ Kx, double *__restrict__ res,
                                                              double *__restrict__ dir, double dir_scale,
                                                              double *__restrict__ aux_zero,
                                                              double *__restrict__ part_rr, double *__restrict__ part_rho)
@@ -1467,14 +1469,14 @@ __global__ void __launch_bounds__(kSpmvThreads) k_cg_restart(int64_t nb, const d
     for (int64_t r0 = (int64_t)blockIdx.x * kRowsPerCta; r0 < nb; r0 += (int64_t)gridDim.x * kRowsPerCta) {
         const int64_t row = r0 + lr;
         const bool live = row < nb;
-        double v = 0.0;
-        if (live) v = ft[row * 6 + i] - Ky[row * 6 + i];
+        double w = 0.0;
+        if (live) w = f[row * 6 + i] - Kx[row * 6 + i];
         __syncthreads();
-        vs[threadIdx.x] = v;
+        vs[threadIdx.x] = w;
         __syncthreads();
         if (live) {
-            const double t = lower_row_times(lfac, row, i, vs + lr * 6);
-            rr = fma(t, t, rr);
+            const double v = lower_row_times(sinv, row, i, vs + lr * 6);
+            rr = fma(w, w, rr);
             rho = fma(v, v, rho);
             if (res != nullptr) res[row * 6 + i] = v;
             if (dir != nullptr) dir[row * 6 + i] = dir_scale * v;
@@ -1504,10 +1506,10 @@ __global__ void __launch_bounds__(256) k_cg_restart_finish(PartialRef rr, Partia
     }
 }
 
-void launch_cg_restart(cudaStream_t st, int64_t nb, const double *lfac, const double *ft, const double *Ky, double *res,
+void launch_cg_restart(cudaStream_t st, int64_t nb, const double *sinv, const double *f, const double *Kx, double *res,
                        double *dir, double dir_scale, double *aux_zero, double *part_rr, double *part_rho)
 {
-    k_cg_restart<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, lfac, ft, Ky, res, dir, dir_scale, aux_zero, part_rr, part_rho);
+    k_cg_restart<<<vec_grid(nb), kSpmvThreads, 0, st>>>(nb, sinv, f, Kx, res, dir, dir_scale, aux_zero, part_rr, part_rho);
 }
 
 void launch_cg_restart_finish(cudaStream_t st, PartialRef rr, PartialRef rho, PcgScalars *sc, unsigned long long epoch,

@@ -128,8 +128,9 @@ void launch_cg2_step(cudaStream_t st, int64_t nb, PartialRef delta, PartialRef g
 void launch_cg_check(cudaStream_t st, int64_t nb, const double *lfac, const double *a, const double *b, double *part,
                      const PcgScalars *sc, const PeerCtx *pc);
 void launch_cg_check_finish(cudaStream_t st, PartialRef part, PcgScalars *sc, const PeerCtx *pc);
-// residual replacement: res := ft - Ky, dir := dir_scale * res, aux_zero := 0; partials of ||L res||^2 and res.res
-void launch_cg_restart(cudaStream_t st, int64_t nb, const double *lfac, const double *ft, const double *Ky, double *res,
+// residual replacement from the assembled matrix: res := S (f - Kx), dir := dir_scale * res, aux_zero := 0;
+// partials of ||f - Kx||^2 and res.res
+void launch_cg_restart(cudaStream_t st, int64_t nb, const double *sinv, const double *f, const double *Kx, double *res,
                        double *dir, double dir_scale, double *aux_zero, double *part_rr, double *part_rho);
 void launch_cg_restart_finish(cudaStream_t st, PartialRef rr, PartialRef rho, PcgScalars *sc, unsigned long long epoch,
                               int clear_done);
@@ -174,20 +175,18 @@ void launch_force_ranges(cudaStream_t st, int64_t n, const double *F, double *pm
 void launch_force_normalize(cudaStream_t st, int64_t n, const double *F, const double *range, double *out);
 
 
-// ---- multilevel preconditioner, device half (DRAFT, not called by the solver yet: see multilevel.cu) ----------
-void launch_ml_galerkin(cudaStream_t st, int64_t n_coarse_blocks, const int32_t *gal_ptr, const int32_t *gal_src,
-                        const int32_t *frow, const int32_t *fcol, const double *fvals, const double *off, double *cvals);
-void launch_ml_restrict(cudaStream_t st, int64_t n_agg, const int32_t *agg_ptr, const int32_t *agg_rows, const double *off,
-                        const double *lfac /* null: unscaled level */, const double *r, double *rc);
-void launch_ml_smooth(cudaStream_t st, int64_t n, const double *sinv, const double *r, double *z);
-void launch_ml_dense_matvec(cudaStream_t st, int64_t n, const double *Ainv, const double *r, double *z);
-void launch_ml_prolong(cudaStream_t st, int64_t n, const int32_t *agg, const double *off, const double *zc, double *z);
-void launch_ml_finish(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const double *off, const double *lfac,
-                      const double *rt, const double *z1, double *zt, double *part);
-
 // ---- multilevel preconditioner, production kernels (mlprec.cu) ----------------------------------------------
 void launch_ml_make_t0(cudaStream_t st, int64_t nb, const double *lfac, const double *off, float *t0);
-void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv);
+void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv, float *dinv32);
+void launch_ml_galerkin0(cudaStream_t st, int64_t n_coarse_blocks, const int32_t *gal_ptr, const int32_t *gal_src,
+                         const int32_t *frow, const int32_t *fcol, const double *fvals, const double *off, double *cvals);
+void launch_ml_dense_to_f32(cudaStream_t st, int n, const double *a, float *out);
+void launch_ml_dense_matvec(cudaStream_t st, int n, const float *ainv, const double *r, double *z);
+void launch_ml_to_f32(cudaStream_t st, int64_t n, const double *a, float *out);
+void launch_ml_restrict_tent(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rfine, const double *off,
+                             const double *r, double *rc);
+void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t n, const float *dinv, const int32_t *agg, const double *off,
+                                   const double *r, const double *zc, double *z);
 void launch_ml_row_of(cudaStream_t st, int64_t n, const int32_t *rowptr, int32_t *row_of);
 void launch_ml_make_p(cudaStream_t st, int64_t n, int64_t nnzp, const int32_t *prow, const int32_t *pcol, const int32_t *prow_of,
                       const int32_t *arow, const int32_t *acol, const double *avals, const int32_t *agg, const double *off,
@@ -200,14 +199,14 @@ void launch_ml_rap(cudaStream_t st, int64_t nc, int64_t nnzg, const int32_t *gro
                    const int32_t *ccol, const double *cval, double *gval);
 void launch_ml_blocks_to_dense(cudaStream_t st, int64_t nrows, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
                                const int32_t *row_of, const double *vals, double *dense);
-void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, int *flag);
+void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, double *colk, int *flag);
 void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_t *agg_ptr, const int32_t *agg_rows,
                          const float *t0, const double *r, double *rc);
 void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
                        const double *z1, double *zt, double *part);
 void launch_ml_restrict(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
-                        const double *pval, const double *r, double *rc);
-void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const double *dinv, const int32_t *prow, const int32_t *pcol,
-                              const double *pval, const double *r, const double *zc, double *z);
+                        const float *pval, const double *r, double *rc);
+void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const float *dinv, const int32_t *prow, const int32_t *pcol,
+                              const float *pval, const double *r, const double *zc, double *z);
 
 }}  // namespace mbfea::dev

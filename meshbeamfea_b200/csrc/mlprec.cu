@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kT) k_ml_make_t0(int64_t nb, const double *__r
 }
 
 // D^-1 = S^T S per row (S = L^-1 lower triangular, full 6x6 storage), one thread per (row, entry)
-__global__ void __launch_bounds__(kT) k_ml_diag_inv(int64_t n, const double *__restrict__ sinv, double *__restrict__ dinv)
+__global__ void __launch_bounds__(kT) k_ml_diag_inv(int64_t n, const double *__restrict__ sinv, double *__restrict__ dinv,
+                                                    float *__restrict__ dinv32)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t v = t / 36;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kT) k_ml_diag_inv(int64_t n, const double *__r
 #pragma unroll
     for (int k = 0; k < 6; ++k) s = fma(__ldg(S + 6 * k + i), __ldg(S + 6 * k + j), s);
     dinv[t] = s;
+    dinv32[t] = (float)s;
 }
 
 // P = T - w D^-1 A T on the pattern (prow, pcol): one thread per P block (i, I).
@@ -194,6 +196,161 @@ __global__ void __launch_bounds__(128) k_ml_rap(int64_t nc, const int32_t *__res
     for (int e = 0; e < 36; ++e) out[e] = acc[e];
 }
 
+// ---------------------------------------------------------------------------
+// Galerkin matrix of level 1 with the tentative fine prolongator:  coarse block k = sum over its contributor list
+// (ascending fine blocks q) of B(d_a)^T A_q B(d_b), a = frow[q], b = fcol[q]  (A = the assembled, unscaled K).
+// EIGHT lanes per coarse block: lanes take contributors round-robin (each reads its own 288-byte block: whole
+// sectors), keep the 6x6 partial sum in registers, then a fixed shuffle tree over the 8 lanes; lane 0 stores.
+// Diagonal coarse blocks have ~30 contributors, off-diagonal ones ~4: eight lanes keep both busy.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void rigid_sandwich(const double *__restrict__ A, const double *da, const double *db, double *acc)
+{
+    double M[36];
+    const double bx = db[0], by = db[1], bz = db[2];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {   // M = A B(db)
+        const double2 a01 = __ldg(reinterpret_cast<const double2 *>(A + 6 * r)), a23 = __ldg(reinterpret_cast<const double2 *>(A + 6 * r + 2)),
+                      a45 = __ldg(reinterpret_cast<const double2 *>(A + 6 * r + 4));
+        M[6 * r + 0] = a01.x; M[6 * r + 1] = a01.y; M[6 * r + 2] = a23.x;
+        M[6 * r + 3] = a23.y + (-a01.y * bz + a23.x * by);
+        M[6 * r + 4] = a45.x + (a01.x * bz - a23.x * bx);
+        M[6 * r + 5] = a45.y + (-a01.x * by + a01.y * bx);
+    }
+    const double ax = da[0], ay = da[1], az = da[2];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {   // acc += B(da)^T M: rows 0..2 unchanged, row 3+r += ([da]x M[0..2, :])_r
+        const double m0 = M[c], m1 = M[6 + c], m2 = M[12 + c];
+        acc[c] += m0; acc[6 + c] += m1; acc[12 + c] += m2;
+        acc[18 + c] += M[18 + c] + (ay * m2 - az * m1);
+        acc[24 + c] += M[24 + c] + (az * m0 - ax * m2);
+        acc[30 + c] += M[30 + c] + (ax * m1 - ay * m0);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_ml_galerkin0(int64_t n_coarse_blocks, const int32_t *__restrict__ gal_ptr,
+                                                      const int32_t *__restrict__ gal_src, const int32_t *__restrict__ frow,
+                                                      const int32_t *__restrict__ fcol, const double *__restrict__ fvals,
+                                                      const double *__restrict__ off, double *__restrict__ cvals)
+{
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;
+    double acc[36];
+#pragma unroll
+    for (int e = 0; e < 36; ++e) acc[e] = 0.0;
+    if (k < n_coarse_blocks) {
+        for (int32_t s = __ldg(gal_ptr + k) + lane; s < __ldg(gal_ptr + k + 1); s += 8) {
+            const int32_t q = __ldg(gal_src + s);
+            const double *da = off + 3 * (int64_t)__ldg(frow + q), *db = off + 3 * (int64_t)__ldg(fcol + q);
+            const double dav[3] = {__ldg(da), __ldg(da + 1), __ldg(da + 2)}, dbv[3] = {__ldg(db), __ldg(db + 1), __ldg(db + 2)};
+            rigid_sandwich(fvals + (int64_t)q * 36, dav, dbv, acc);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 36; ++e)
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) acc[e] += __shfl_down_sync(0xffffffffu, acc[e], o, 8);
+    if (k < n_coarse_blocks && lane == 0) {
+        double2 *out = reinterpret_cast<double2 *>(cvals + k * 36);
+#pragma unroll
+        for (int e = 0; e < 18; ++e) out[e] = make_double2(acc[2 * e], acc[2 * e + 1]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Explicit inverse of the coarsest matrix (dense n x n, n = 6 m, SPD): block Gauss-Jordan with 6x6 pivots, two
+// launches per pivot step (no pivot search: SPD).  Step k:
+//   pivot : Pinv = (A_kk)^-1; column block k saved; block row k := Pinv A_k,: (A_kk := Pinv)        -- one CTA
+//   update: A_ij -= C_i A_kj for i != k, j != k;  A_ik := -C_i Pinv   (C_i: the saved column block)   -- n^2 threads
+// *flag |= 2 on a non-positive pivot.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ml_gj_pivot(int n, int k, double *__restrict__ a, double *__restrict__ colk, int *flag)
+{
+    __shared__ double P[36];
+    const int k6 = 6 * k;
+    if (threadIdx.x < 36) P[threadIdx.x] = a[(size_t)(k6 + threadIdx.x / 6) * n + k6 + threadIdx.x % 6];
+    __syncthreads();
+    if (threadIdx.x == 0) {   // in-place Gauss-Jordan of the 6x6 pivot block
+        bool bad = false;
+        for (int p = 0; p < 6; ++p) {
+            double d = P[7 * p];
+            if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+            const double inv = 1.0 / d;
+            for (int j = 0; j < 6; ++j) P[6 * p + j] = (j == p) ? inv : P[6 * p + j] * inv;
+            for (int i = 0; i < 6; ++i) {
+                if (i == p) continue;
+                const double f = P[6 * i + p];
+                for (int j = 0; j < 6; ++j) P[6 * i + j] = (j == p) ? -f * inv : P[6 * i + j] - f * P[6 * p + j];
+            }
+        }
+        if (bad) atomicOr(flag, 2);
+    }
+    // save the column block (old values), all rows
+    for (int t = threadIdx.x; t < n * 6; t += blockDim.x) colk[t] = a[(size_t)(t / 6) * n + k6 + t % 6];
+    __syncthreads();
+    // new block row k: for every column j the 6 old values of the pivot rows -> Pinv times them
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double v[6], w[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] = a[(size_t)(k6 + c) * n + j];
+        const bool in = j >= k6 && j < k6 + 6;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = 0.0;
+            if (in) s = P[6 * r + (j - k6)];
+            else
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s = fma(P[6 * r + c], v[c], s);
+            w[r] = s;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) a[(size_t)(k6 + r) * n + j] = w[r];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ml_gj_update(int n, int k, double *__restrict__ a, const double *__restrict__ colk)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * n) return;
+    const int i = (int)(t / n), j = (int)(t - (int64_t)i * n), k6 = 6 * k;
+    if (i >= k6 && i < k6 + 6) return;
+    const double *c = colk + (size_t)i * 6;
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) s = fma(c[m], a[(size_t)(k6 + m) * n + j], s);   // block row k holds Pinv A_k,: (Pinv in the pivot columns)
+    a[t] = (j >= k6 && j < k6 + 6) ? -s : a[t] - s;
+}
+
+// symmetrised FP32 copy of the inverse for the apply (rounding the same double for (i, j) and (j, i) keeps it symmetric)
+__global__ void __launch_bounds__(256) k_ml_dense_to_f32(int n, const double *__restrict__ a, float *__restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * n) return;
+    const int i = (int)(t / n), j = (int)(t - (int64_t)i * n);
+    out[t] = (float)(0.5 * (a[t] + a[(size_t)j * n + i]));
+}
+
+// coarsest level: z = Ainv r, Ainv dense n x n FP32 (L2-resident); one warp per row
+__global__ void __launch_bounds__(kT) k_ml_dense_matvec(int n, const float *__restrict__ ainv, const double *__restrict__ r,
+                                                        double *__restrict__ z)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n) return;
+    const float *A = ainv + (size_t)row * n;
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s = fma((double)__ldg(A + j), r[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) z[row] = s;
+}
+
+// FP32 copies for the apply: the same rounded values serve restriction and prolongation
+__global__ void __launch_bounds__(kT) k_ml_to_f32(int64_t n, const double *__restrict__ a, float *__restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = (float)a[t];
+}
+
 // row index of every block of a CSR pattern (setup helper): row_of[k] = i for k in [rowptr[i], rowptr[i+1])
 __global__ void __launch_bounds__(kT) k_ml_row_of(int64_t n, const int32_t *__restrict__ rowptr, int32_t *__restrict__ row_of)
 {
@@ -214,35 +371,6 @@ __global__ void __launch_bounds__(kT) k_ml_blocks_to_dense(int64_t nrows, const 
     const int e = (int)(t - k * 36), r = e / 6, c = e - 6 * r;
     const int64_t n = 6 * nrows;
     dense[(6 * (int64_t)__ldg(row_of + k) + r) * n + 6 * (int64_t)__ldg(colidx + k) + c] = vals[t];
-}
-
-// In-place Gauss-Jordan inverse of a dense SPD matrix (no pivoting needed), ONE CTA of 1024 threads, the matrix
-// (<= a few MB) stays L2-resident.  *flag |= 2 on a non-positive pivot.  Step k:
-//   p = 1 / a_kk;  row k *= p (a_kk := p);  for i != k: f = a_ik, a_ik := 0, row i -= f * row k.
-__global__ void __launch_bounds__(1024) k_ml_dense_inverse(int n, double *__restrict__ a, int *flag)
-{
-    __shared__ double piv;
-    extern __shared__ double colk[];   // n doubles: column k before the step
-    for (int k = 0; k < n; ++k) {
-        if (threadIdx.x == 0) {
-            const double d = a[(size_t)k * n + k];
-            if (!(d > 0.0) || !isfinite(d)) { atomicOr(flag, 2); piv = 1.0; } else piv = 1.0 / d;
-        }
-        for (int i = threadIdx.x; i < n; i += blockDim.x) colk[i] = a[(size_t)i * n + k];
-        __syncthreads();
-        const double p = piv;
-        // row k
-        for (int j = threadIdx.x; j < n; j += blockDim.x) a[(size_t)k * n + j] = (j == k) ? p : a[(size_t)k * n + j] * p;
-        __syncthreads();
-        // every other row: a_ij -= f_i * a_kj (j != k), a_ik = -f_i * p
-        for (int64_t t = threadIdx.x; t < (int64_t)n * n; t += blockDim.x) {
-            const int i = (int)(t / n), j = (int)(t - (int64_t)i * n);
-            if (i == k) continue;
-            const double f = colk[i];
-            a[t] = (j == k) ? -f * p : fma(-f, a[(size_t)k * n + j], a[t]);
-        }
-        __syncthreads();
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -319,10 +447,11 @@ __global__ void __launch_bounds__(kT, 4) k_ml_finish0(int64_t nb, const int32_t 
     }
 }
 
-// coarse restriction: rc[I] = sum over the P blocks (i, I) of column I (ascending) of P_iI^T r_i; one warp per coarse row
+// coarse restriction, general P (FP32 blocks): rc[I] = sum over the P blocks (i, I) of column I (ascending) of
+// P_iI^T r_i; one warp per coarse row, lanes over the entries, fixed shuffle tree
 __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *__restrict__ rrow,
                                                     const int32_t *__restrict__ rblk, const int32_t *__restrict__ rfine,
-                                                    const double *__restrict__ pval, const double *__restrict__ r,
+                                                    const float *__restrict__ pval, const double *__restrict__ r,
                                                     double *__restrict__ rc)
 {
     const int lane = threadIdx.x & 31;
@@ -330,13 +459,16 @@ __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *_
     if (I >= nc) return;   // whole warps leave together
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int32_t e = __ldg(rrow + I) + lane; e < __ldg(rrow + I + 1); e += 32) {
-        const double *P = pval + (int64_t)__ldg(rblk + e) * 36;
+        const float4 *P = reinterpret_cast<const float4 *>(pval + (int64_t)__ldg(rblk + e) * 36);
         const double *rv = r + (int64_t)__ldg(rfine + e) * 6;
+        float pp[36];
+#pragma unroll
+        for (int x = 0; x < 9; ++x) { const float4 f = __ldg(P + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const double ri = rv[i];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) acc[j] = fma(__ldg(P + 6 * i + j), ri, acc[j]);
+            for (int j = 0; j < 6; ++j) acc[j] = fma((double)pp[6 * i + j], ri, acc[j]);
         }
     }
 #pragma unroll
@@ -348,26 +480,85 @@ __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *_
         for (int j = 0; j < 6; ++j) rc[I * 6 + j] = acc[j];
 }
 
-// coarse level on the way down: z_i = D_i^-1 r_i + sum over row i of P of P_iJ zc_J; thread = (row, scalar)
-__global__ void __launch_bounds__(kT) k_ml_smooth_prolong(int64_t n, const double *__restrict__ dinv,
+// coarse restriction, TENTATIVE P (one rigid block per row, generated from the offsets: 24 bytes per member instead
+// of a 6x6 block): rc[I] = sum over the members i of aggregate I (ascending) of B(off_i)^T r_i; 8 lanes per aggregate
+__global__ void __launch_bounds__(kT) k_ml_restrict_tent(int64_t nc, const int32_t *__restrict__ rrow,
+                                                         const int32_t *__restrict__ rfine, const double *__restrict__ off,
+                                                         const double *__restrict__ r, double *__restrict__ rc)
+{
+    const int lane = threadIdx.x & 7;
+    const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (I < nc) {
+        for (int32_t e = __ldg(rrow + I) + lane; e < __ldg(rrow + I + 1); e += 8) {
+            const int64_t i = __ldg(rfine + e);
+            double w[6], t[6];
+#pragma unroll
+            for (int x = 0; x < 6; ++x) w[x] = r[i * 6 + x];
+            const double d[3] = {__ldg(off + 3 * i), __ldg(off + 3 * i + 1), __ldg(off + 3 * i + 2)};
+            rigid_apply_t(d, w, t);
+#pragma unroll
+            for (int x = 0; x < 6; ++x) acc[x] += t[x];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], o, 8);
+    if (I < nc && lane == 0)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) rc[I * 6 + j] = acc[j];
+}
+
+// coarse level on the way down: z_i = D_i^-1 r_i + sum over row i of P of P_iJ zc_J; thread = (row, scalar); FP32 D^-1, P
+__global__ void __launch_bounds__(kT) k_ml_smooth_prolong(int64_t n, const float *__restrict__ dinv,
                                                           const int32_t *__restrict__ prow, const int32_t *__restrict__ pcol,
-                                                          const double *__restrict__ pval, const double *__restrict__ r,
+                                                          const float *__restrict__ pval, const double *__restrict__ r,
                                                           const double *__restrict__ zc, double *__restrict__ z)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t v = t / 6;
     if (v >= n) return;
     const int i = (int)(t - v * 6);
-    const double *D = dinv + v * 36 + 6 * i, *rv = r + v * 6;
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) s = fma(__ldg(D + j), rv[j], s);
+    const float2 *D = reinterpret_cast<const float2 *>(dinv + v * 36 + 6 * i);
+    const double *rv = r + v * 6;
+    const float2 d0 = __ldg(D), d1 = __ldg(D + 1), d2 = __ldg(D + 2);
+    double s = (double)d0.x * rv[0];
+    s = fma((double)d0.y, rv[1], s); s = fma((double)d1.x, rv[2], s); s = fma((double)d1.y, rv[3], s);
+    s = fma((double)d2.x, rv[4], s); s = fma((double)d2.y, rv[5], s);
     for (int32_t b = __ldg(prow + v); b < __ldg(prow + v + 1); ++b) {
-        const double *P = pval + (int64_t)b * 36 + 6 * i, *c = zc + (int64_t)__ldg(pcol + b) * 6;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) s = fma(__ldg(P + j), c[j], s);
+        const float2 *P = reinterpret_cast<const float2 *>(pval + (int64_t)b * 36 + 6 * i);
+        const double *c = zc + (int64_t)__ldg(pcol + b) * 6;
+        const float2 p0 = __ldg(P), p1 = __ldg(P + 1), p2 = __ldg(P + 2);
+        s = fma((double)p0.x, c[0], s); s = fma((double)p0.y, c[1], s); s = fma((double)p1.x, c[2], s);
+        s = fma((double)p1.y, c[3], s); s = fma((double)p2.x, c[4], s); s = fma((double)p2.y, c[5], s);
     }
     z[t] = s;
+}
+
+// the same for a TENTATIVE P: z_i = D_i^-1 r_i + B(off_i) zc[agg i]
+__global__ void __launch_bounds__(kT) k_ml_smooth_prolong_tent(int64_t n, const float *__restrict__ dinv,
+                                                               const int32_t *__restrict__ agg, const double *__restrict__ off,
+                                                               const double *__restrict__ r, const double *__restrict__ zc,
+                                                               double *__restrict__ z)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t v = t / 6;
+    if (v >= n) return;
+    const int i = (int)(t - v * 6);
+    const float2 *D = reinterpret_cast<const float2 *>(dinv + v * 36 + 6 * i);
+    const double *rv = r + v * 6;
+    const float2 d0 = __ldg(D), d1 = __ldg(D + 1), d2 = __ldg(D + 2);
+    double s = (double)d0.x * rv[0];
+    s = fma((double)d0.y, rv[1], s); s = fma((double)d1.x, rv[2], s); s = fma((double)d1.y, rv[3], s);
+    s = fma((double)d2.x, rv[4], s); s = fma((double)d2.y, rv[5], s);
+    const double *c = zc + (int64_t)__ldg(agg + v) * 6;
+    const double d[3] = {__ldg(off + 3 * v), __ldg(off + 3 * v + 1), __ldg(off + 3 * v + 2)};
+    double cc[6], tt[6];
+#pragma unroll
+    for (int x = 0; x < 6; ++x) cc[x] = c[x];
+    rigid_apply(d, cc, tt);
+    z[t] = s + tt[i];
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------------
@@ -375,9 +566,9 @@ void launch_ml_make_t0(cudaStream_t st, int64_t nb, const double *lfac, const do
 {
     if (nb > 0) k_ml_make_t0<<<blocks_for(nb * 36), kT, 0, st>>>(nb, lfac, off, t0);
 }
-void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv)
+void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv, float *dinv32)
 {
-    if (n > 0) k_ml_diag_inv<<<blocks_for(n * 36), kT, 0, st>>>(n, sinv, dinv);
+    if (n > 0) k_ml_diag_inv<<<blocks_for(n * 36), kT, 0, st>>>(n, sinv, dinv, dinv32);
 }
 void launch_ml_row_of(cudaStream_t st, int64_t n, const int32_t *rowptr, int32_t *row_of)
 {
@@ -406,13 +597,33 @@ void launch_ml_blocks_to_dense(cudaStream_t st, int64_t nrows, int64_t nnz, cons
 {
     if (nnz > 0) k_ml_blocks_to_dense<<<blocks_for(nnz * 36), kT, 0, st>>>(nrows, rowptr, colidx, row_of, vals, dense);
 }
-int ml_dense_inverse_prepare(int n)
+void launch_ml_galerkin0(cudaStream_t st, int64_t n_coarse_blocks, const int32_t *gal_ptr, const int32_t *gal_src,
+                         const int32_t *frow, const int32_t *fcol, const double *fvals, const double *off, double *cvals)
 {
-    return (int)cudaFuncSetAttribute(k_ml_dense_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * sizeof(double)));
+    if (n_coarse_blocks > 0)
+        k_ml_galerkin0<<<blocks_for(n_coarse_blocks * 8, 128), 128, 0, st>>>(n_coarse_blocks, gal_ptr, gal_src, frow, fcol, fvals, off, cvals);
 }
-void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, int *flag)
+// a: n x n (n = 6 m) overwritten by its inverse; colk: n * 6 doubles of scratch; 2 m launches
+void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, double *colk, int *flag)
 {
-    if (n > 0) k_ml_dense_inverse<<<1, 1024, (size_t)n * sizeof(double), st>>>(n, a, flag);
+    if (n <= 0) return;
+    const unsigned grid = blocks_for((int64_t)n * n, 256);
+    for (int k = 0; k < n / 6; ++k) {
+        k_ml_gj_pivot<<<1, 256, 0, st>>>(n, k, a, colk, flag);
+        k_ml_gj_update<<<grid, 256, 0, st>>>(n, k, a, colk);
+    }
+}
+void launch_ml_dense_to_f32(cudaStream_t st, int n, const double *a, float *out)
+{
+    if (n > 0) k_ml_dense_to_f32<<<blocks_for((int64_t)n * n, 256), 256, 0, st>>>(n, a, out);
+}
+void launch_ml_dense_matvec(cudaStream_t st, int n, const float *ainv, const double *r, double *z)
+{
+    if (n > 0) k_ml_dense_matvec<<<blocks_for((int64_t)n * 32), kT, 0, st>>>(n, ainv, r, z);
+}
+void launch_ml_to_f32(cudaStream_t st, int64_t n, const double *a, float *out)
+{
+    if (n > 0) k_ml_to_f32<<<blocks_for(n), kT, 0, st>>>(n, a, out);
 }
 void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_t *agg_ptr, const int32_t *agg_rows,
                          const float *t0, const double *r, double *rc)
@@ -427,14 +638,24 @@ void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg
     if (nb > 0 && grid > 0) k_ml_finish0<<<(unsigned)grid, kT, 0, st>>>(nb, agg, t0, rt, z1, zt, part);
 }
 void launch_ml_restrict(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
-                        const double *pval, const double *r, double *rc)
+                        const float *pval, const double *r, double *rc)
 {
     if (nc > 0) k_ml_restrict<<<blocks_for(nc * 32), kT, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc);
 }
-void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const double *dinv, const int32_t *prow, const int32_t *pcol,
-                              const double *pval, const double *r, const double *zc, double *z)
+void launch_ml_restrict_tent(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rfine, const double *off,
+                             const double *r, double *rc)
+{
+    if (nc > 0) k_ml_restrict_tent<<<blocks_for(nc * 8), kT, 0, st>>>(nc, rrow, rfine, off, r, rc);
+}
+void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const float *dinv, const int32_t *prow, const int32_t *pcol,
+                              const float *pval, const double *r, const double *zc, double *z)
 {
     if (n > 0) k_ml_smooth_prolong<<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z);
+}
+void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t n, const float *dinv, const int32_t *agg, const double *off,
+                                   const double *r, const double *zc, double *z)
+{
+    if (n > 0) k_ml_smooth_prolong_tent<<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, agg, off, r, zc, z);
 }
 
 }}  // namespace mbfea::dev

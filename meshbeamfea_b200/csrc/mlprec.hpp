@@ -16,8 +16,8 @@ namespace mbfea {
 struct MlParams {
     double cell = 2.0;            // brick edge of the first coarse level, in mean beam lengths
     double ratio = 2.0;           // growth of the brick edge per level
-    int64_t coarsest_rows = 64;   // stop coarsening at this many block rows (dense inverse of <= 6 x that)
-    int smooth_from = 2;          // first level whose prolongator to the next level is smoothed (>= 1)
+    int64_t coarsest_rows = 512;  // stop coarsening at this many block rows (dense inverse of <= 6 x that)
+    int smooth_from = 1;          // first level whose prolongator to the next level is smoothed (>= 1)
     int max_levels = 12;
     double omega = 0.6;           // damping of the prolongator smoother, P = (I - omega D^-1 A) T
 };
@@ -30,6 +30,7 @@ struct MlCoarse {                 // one coarse level (l >= 1) and its transfer 
     int64_t n_next = 0, nnzp = 0, nnzap = 0;
     DevBuf<int32_t> agg, prow, pcol, prow_of, rrow, rblk, rfine, aprow, apcol, aprow_of;
     DevBuf<double> off, pval, apval;
+    DevBuf<float> pval32, dinv32;   // what the apply reads: the same rounded values in restriction and prolongation
 };
 
 class MlPrec {
@@ -61,7 +62,8 @@ private:
     DevBuf<float> t0;
     int group0 = 32;
     std::vector<std::unique_ptr<MlCoarse>> lv;   // lv[m]: level m + 1
-    DevBuf<double> dense;                        // explicit inverse of the coarsest matrix
+    DevBuf<double> dense, gj_col;                // explicit inverse of the coarsest matrix (+ Gauss-Jordan scratch)
+    DevBuf<float> dense32;                       // its symmetrised FP32 copy: what the apply multiplies with
     int64_t n_dense = 0;
 };
 

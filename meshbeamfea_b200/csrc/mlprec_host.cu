@@ -44,7 +44,7 @@ bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowpt
                        std::max(1, par.smooth_from), H);
     const size_t L = H.levels();
     if (L == 0) return false;
-    if (6 * H.agg[L - 1].n_coarse > 2048) return false;   // the chain stopped early (max_levels): no dense inverse that large
+    if (6 * H.agg[L - 1].n_coarse > 3072) return false;   // the chain stopped early (max_levels): no dense inverse that large
     // level 0 -> 1
     const HierLevel &h0 = H.agg[0];
     up(st, agg0, h0.agg); up(st, agg_ptr0, h0.agg_ptr); up(st, agg_rows0, h0.agg_rows);
@@ -84,12 +84,16 @@ bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowpt
             launch_ml_row_of(st, c->n, c->prow.p, c->prow_of.p);
             launch_ml_row_of(st, c->n, c->aprow.p, c->aprow_of.p);
             CK(c->pval.alloc((size_t)c->nnzp * 36)); CK(c->apval.alloc((size_t)c->nnzap * 36));
+            if (c->smoothed) CK(c->pval32.alloc((size_t)c->nnzp * 36));
             CK(c->lfac.alloc((size_t)c->n * 36)); CK(c->sinv.alloc((size_t)c->n * 36)); CK(c->dinv.alloc((size_t)c->n * 36));
+            CK(c->dinv32.alloc((size_t)c->n * 36));
         }
         lv.push_back(std::move(c));
     }
     n_dense = 6 * lv.back()->n;
     CK(dense.alloc((size_t)(n_dense * n_dense)));
+    CK(dense32.alloc((size_t)(n_dense * n_dense)));
+    CK(gj_col.alloc((size_t)n_dense * 6));
     CK(cudaStreamSynchronize(st));   // the host vectors above go out of scope
     symbolic_ok = true;
     ms_symbolic = wall_ms() - t0w;
@@ -104,16 +108,17 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
     int64_t k = 0;
     launch_ml_row_of(st, nb, d_rowptr, frow0.p);
     launch_ml_make_t0(st, nb, d_lfac, off0.p, t0.p);
-    launch_ml_galerkin(st, lv[0]->nnz, gal_ptr0.p, gal_src0.p, frow0.p, d_colidx, d_vals, off0.p, lv[0]->vals.p);
+    launch_ml_galerkin0(st, lv[0]->nnz, gal_ptr0.p, gal_src0.p, frow0.p, d_colidx, d_vals, off0.p, lv[0]->vals.p);
     k += 3;
     for (size_t m = 0; m < lv.size(); ++m) {
         MlCoarse &c = *lv[m];
         if (!c.has_next) break;
         MlCoarse &nx = *lv[m + 1];
         launch_block_chol(st, c.n, c.diag_idx.p, c.vals.p, c.lfac.p, c.sinv.p, d_flag);
-        launch_ml_diag_inv(st, c.n, c.sinv.p, c.dinv.p);
+        launch_ml_diag_inv(st, c.n, c.sinv.p, c.dinv.p, c.dinv32.p);
         launch_ml_make_p(st, c.n, c.nnzp, c.prow.p, c.pcol.p, c.prow_of.p, c.rowptr.p, c.colidx.p, c.vals.p, c.agg.p, c.off.p,
                          c.dinv.p, c.smoothed ? par.omega : 0.0, c.pval.p);
+        if (c.smoothed) { launch_ml_to_f32(st, c.nnzp * 36, c.pval.p, c.pval32.p); ++k; }
         launch_ml_ap(st, c.n, c.nnzap, c.aprow.p, c.apcol.p, c.aprow_of.p, c.rowptr.p, c.colidx.p, c.vals.p, c.prow.p, c.pcol.p,
                      c.pval.p, c.apval.p);
         launch_ml_rap(st, nx.n, nx.nnz, nx.rowptr.p, nx.colidx.p, nx.row_of.p, c.rrow.p, c.rblk.p, c.rfine.p, c.pval.p, c.aprow.p,
@@ -123,8 +128,9 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
     MlCoarse &last = *lv.back();
     CK(cudaMemsetAsync(dense.p, 0, (size_t)(n_dense * n_dense) * sizeof(double), st));
     launch_ml_blocks_to_dense(st, last.n, last.nnz, last.rowptr.p, last.colidx.p, last.row_of.p, last.vals.p, dense.p);
-    launch_ml_dense_inverse(st, (int)n_dense, dense.p, d_flag);
-    k += 2;
+    launch_ml_dense_inverse(st, (int)n_dense, dense.p, gj_col.p, d_flag);
+    launch_ml_dense_to_f32(st, (int)n_dense, dense.p, dense32.p);
+    k += 2 + 2 * (n_dense / 6);
     setup_launches = k;
     numeric_ok = true;
 }
@@ -133,12 +139,21 @@ void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, 
 {
     const size_t L = lv.size();
     launch_ml_restrict0(st, lv[0]->n, group0, agg_ptr0.p, agg_rows0.p, t0.p, rt, lv[0]->r.p);
-    for (size_t m = 0; m + 1 < L; ++m)
-        launch_ml_restrict(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->pval.p, lv[m]->r.p, lv[m + 1]->r.p);
-    launch_ml_dense_matvec(st, n_dense, dense.p, lv[L - 1]->r.p, lv[L - 1]->z.p);
-    for (size_t m = L - 1; m-- > 0;)
-        launch_ml_smooth_prolong(st, lv[m]->n, lv[m]->dinv.p, lv[m]->prow.p, lv[m]->pcol.p, lv[m]->pval.p, lv[m]->r.p,
-                                 lv[m + 1]->z.p, lv[m]->z.p);
+    for (size_t m = 0; m + 1 < L; ++m) {
+        if (lv[m]->smoothed)
+            launch_ml_restrict(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->pval32.p, lv[m]->r.p, lv[m + 1]->r.p);
+        else
+            launch_ml_restrict_tent(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rfine.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->r.p);
+    }
+    launch_ml_dense_matvec(st, (int)n_dense, dense32.p, lv[L - 1]->r.p, lv[L - 1]->z.p);
+    for (size_t m = L - 1; m-- > 0;) {
+        if (lv[m]->smoothed)
+            launch_ml_smooth_prolong(st, lv[m]->n, lv[m]->dinv32.p, lv[m]->prow.p, lv[m]->pcol.p, lv[m]->pval32.p, lv[m]->r.p,
+                                     lv[m + 1]->z.p, lv[m]->z.p);
+        else
+            launch_ml_smooth_prolong_tent(st, lv[m]->n, lv[m]->dinv32.p, lv[m]->agg.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->z.p,
+                                          lv[m]->z.p);
+    }
     launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part);
 }
 

@@ -249,11 +249,6 @@ class Context:
         allow = (L.ENOCONV,) if allow_unconverged else ()
         return self._ck(self._lib.mbfea_solve(self._h), allow)
 
-    def solve_multilevel(self, cell_beam_lengths: float = 2.0, ratio: float = 2.0, coarsest_rows: int = 128) -> int:
-        """EXPERIMENTAL, unvalidated on hardware: PCG with the additive multilevel preconditioner
-        (mbfea_solve_multilevel); after assemble(), followed by recover()."""
-        return self._ck(self._lib.mbfea_solve_multilevel(self._h, cell_beam_lengths, ratio, coarsest_rows))
-
     def recover(self):
         self._ck(self._lib.mbfea_recover(self._h))
 

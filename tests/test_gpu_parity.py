@@ -517,20 +517,3 @@ def _as_arrays(job):
     return mb.SimulationJob(np.asarray(job.nodes, np.float64), np.asarray(job.elements, np.int32),
                             np.asarray(job.elementalNormals, np.float64), np.asarray(job.fixedNodes, np.int32),
                             job.nodalForces, dims, mat)
-
-
-@pytest.mark.skip(reason="draft of the next round: mbfea_solve_multilevel has never run on a GPU; enable once validated")
-def test_multilevel_preconditioner_matches_the_plain_solve(built):
-    """Intended validation of the experimental multilevel PCG: same displacements and forces as the
-    block-Jacobi solve within the parity bar, in several times fewer iterations (CPU prototype on the same
-    hierarchy: tests/tools/proto_hierarchy_pcg.py)."""
-    job = syn.cubic_lattice(20)
-    U, F = orc.solve(to_oracle(job))
-    with ctx_for(job) as c:
-        c.execute()
-        its_plain = c.stats()["iterations"]
-        c.assemble()
-        c.solve_multilevel(2.0, 2.0, 128)
-        c.recover()
-        assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U
-        assert c.stats()["iterations"] * 2 < its_plain

@@ -582,7 +582,7 @@ def test_dense_spd_inverse(built):
 
 
 def test_multilevel_transfer_math(tmp_path):
-    """The rigid-body transfer arithmetic the (not yet wired) multilevel kernels share with the host:
+    """The rigid-body transfer arithmetic the multilevel kernels share with the host:
     B(d) c, B(d)^T r, entries of B(d) and the Galerkin block entry, against explicit 6x6 matrices."""
     import shutil
     if shutil.which("g++") is None:
@@ -593,21 +593,3 @@ def test_multilevel_transfer_math(tmp_path):
                     os.path.join(here, "multilevel_math_check.cpp"), "-o", exe], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stdout + out.stderr
-
-
-def test_multilevel_kernels_under_thread_level_emulation(tmp_path):
-    """The draft multilevel kernels (csrc/multilevel.cu, not yet run on a GPU) executed on the CPU with one host
-    thread per CUDA thread -- __syncthreads / __shfl_down_sync as barriers -- against dense P^T A P, P^T r, P z
-    arithmetic on a small lattice: Galerkin assembly, both restrictions, smoother, dense matvec, prolongation and
-    the fine-level finish with its dot-product partials."""
-    import shutil
-    if shutil.which("g++") is None:
-        pytest.skip("no g++")
-    here = os.path.dirname(os.path.abspath(__file__))
-    csrc = os.path.join(here, "..", "meshbeamfea_b200", "csrc")
-    exe = os.path.join(str(tmp_path), "mlemul")
-    subprocess.run(["g++", "-O1", "-std=c++20", "-I", csrc, "-I", os.path.join(here, "..", "include"),
-                    os.path.join(here, "multilevel_emul.cpp"), os.path.join(csrc, "host_prep.cpp"),
-                    os.path.join(csrc, "hierarchy.cpp"), "-o", exe, "-lpthread"], check=True)
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "all kernels match" in out.stdout, out.stdout + out.stderr
