@@ -452,6 +452,11 @@ ORC_API void orc_bsr_spmv(int64_t nb, const int64_t *rowptr, const int32_t *coli
 
 /* Block-Jacobi PCG; returns iterations done.  stop: ||r|| <= tol*||f||.
  * max_iter bounds the work (the bench uses it to time a fixed sample).      */
+/* optional wall-clock budget of orc_pcg_bj (seconds; <= 0: none): the bench's reference arm runs the CPU solve
+ * to completion but must not hold the box for ever if the host is slow */
+static double g_pcg_budget_s = 0.0;
+ORC_API void orc_set_pcg_budget(double seconds) { g_pcg_budget_s = seconds; }
+
 ORC_API int64_t orc_pcg_bj(int64_t nb, const int64_t *rowptr, const int32_t *colidx,
                            const double *vals, const double *f, double *x,
                            double tol, int64_t max_iter, double *rel_res_out)
@@ -480,7 +485,9 @@ ORC_API int64_t orc_pcg_bj(int64_t nb, const int64_t *rowptr, const int32_t *col
     int64_t it = 0;
     double rr = ff;
     if (ff == 0) { if (rel_res_out) *rel_res_out = 0; goto done; }
+    const double t_start = omp_get_wtime();
     while (it < max_iter && rr > tol * tol * ff) {
+        if (g_pcg_budget_s > 0.0 && omp_get_wtime() - t_start > g_pcg_budget_s) break;
         orc_bsr_spmv(nb, rowptr, colidx, vals, p, Ap);
         double pAp = 0;
 #pragma omp parallel for schedule(static) reduction(+ : pAp)

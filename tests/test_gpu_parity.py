@@ -517,3 +517,99 @@ def _as_arrays(job):
     return mb.SimulationJob(np.asarray(job.nodes, np.float64), np.asarray(job.elements, np.int32),
                             np.asarray(job.elementalNormals, np.float64), np.asarray(job.fixedNodes, np.int32),
                             job.nodalForces, dims, mat)
+
+
+# ---- multilevel preconditioner (options.precond) ---------------------------------------
+@pytest.mark.parametrize("name,make", [("lattice_14", lambda: syn.cubic_lattice(14)), ("gridshell_80", lambda: syn.gridshell(80)),
+                                       ("planar_grid_70", lambda: syn.planar_grid(70))])
+def test_multilevel_preconditioner_matches_the_direct_solve(built, name, make):
+    """The multilevel-preconditioned solve (the default above 4096 free vertices) against the oracle's sparse direct
+    solve, for smoothed and tentative coarse prolongators, and against the block-Jacobi solve of the same job: same
+    displacements and forces within the parity bar, in fewer iterations."""
+    job = make()
+    U, F = orc.solve(to_oracle(job))
+    its = {}
+    for label, kw in (("default", dict(precond=2)), ("tentative", dict(precond=2, ml_smooth_from=99)),
+                      ("smoothed_small_coarsest", dict(precond=2, ml_smooth_from=1, ml_coarsest_rows=8)),
+                      ("block_jacobi", dict(precond=1))):
+        with ctx_for(job, **kw) as c:
+            c.execute()
+            st = c.stats()
+            its[label] = st["iterations"]
+            assert st["precond"] == (1 if label == "block_jacobi" else 2), (label, st["precond"])
+            assert st["converged"] in (1, 2)
+            assert rel_l2(c.displacements(), U) < TOL_U and rel_l2(c.edge_forces(), F) < TOL_U, label
+    assert its["default"] * 1.5 < its["block_jacobi"], its
+    with ctx_for(job) as c:   # auto: multilevel from 4096 free vertices on
+        assert c.stats()["precond"] == (2 if c.stats()["n_block_rows_global"] >= 4096 else 1)
+
+
+def test_multilevel_is_bitwise_reproducible_and_graph_independent(built):
+    job = syn.cubic_lattice(14)
+    outs = []
+    for use_graph in (True, True, False):
+        with ctx_for(job, tol=1e-10, precond=2, use_graph=use_graph, check_every=10) as c:
+            c.execute()
+            outs.append((c.displacements().copy(), c.stats()["iterations"]))
+    assert outs[0][1] == outs[1][1] == outs[2][1]
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
+
+
+@pytest.mark.parametrize("name,make", [("lattice_40", lambda: syn.cubic_lattice(40)), ("gridshell_240", lambda: syn.gridshell(240))])
+def test_mid_size_parity_against_the_double_double_reference(built, name, make):
+    """Mid-size meshes (374 k / 340 k DOF) where the sparse direct solve no longer finishes in test time (SuperLU on
+    the 24^3 lattice runs for minutes): the reference is the oracle's own CPU PCG inside an iterative refinement
+    with double-double residuals (oracle.solve_dd_pcg), converged to ~1e-18.  Every storage format, CG variant and
+    preconditioner must agree with it within the 1e-8 parity bar."""
+    job = make()
+    U, F, hist = orc.solve_dd_pcg(to_oracle(job), passes=2)
+    assert hist[-1] < 1e-15, hist
+    combos = [dict(), dict(precond=2, ml_smooth_from=99), dict(precond=1, storage=2, cg_variant=1), dict(precond=1, storage=1, cg_variant=1),
+              dict(precond=1, storage=2, cg_variant=2), dict(precond=1, storage=1, spmv_kernel=2)]
+    for kw in combos:
+        with ctx_for(job, **kw) as c:
+            c.execute()
+            assert c.stats()["converged"] in (1, 2), kw
+            eu, ef = rel_l2(c.displacements(), U), rel_l2(c.edge_forces(), F)
+            assert eu < TOL_U and ef < TOL_U, (kw, eu, ef)
+
+
+def test_config2_full_size_against_the_double_double_reference(built):
+    """BASELINE config 2 at full size: planar 100 x 100 cantilevered grid, 59 400 free DOF, kappa ~ 1e10.  The
+    reference is the SuperLU solve refined with double-double residuals (oracle.solve_dd, residual 7e-25): the
+    plain oracle sits 2.8e-10 from it, the raw KKT SuperLU solve the reference's call amounts to 5e-9 in u and
+    3e-4 in the forces.  Round 1's GPU solve was 4.0e-8 off whatever the tolerance: the rounding of the scaled
+    matrix K~ = S K S^T amplified by kappa.  With the residual replacement evaluated against the assembled K the
+    solve meets the 1e-8 bar at the bench tolerance, with either preconditioner."""
+    job = syn.planar_grid(100)
+    O = to_oracle(job)
+    U, F, hist = orc.solve_dd(O)
+    assert hist[-1] < 1e-20, hist
+    U2, F2 = orc.solve(O)
+    assert rel_l2(U2, U) < 1e-9 and rel_l2(F2, F) < 1e-9     # the plain oracle is on the right side too
+    for kw in (dict(), dict(precond=1)):
+        with ctx_for(job, tol=1e-8, **kw) as c:
+            c.execute()
+            eu, ef = rel_l2(c.displacements(), U), rel_l2(c.edge_forces(), F)
+            assert eu < TOL_U and ef < TOL_U, (kw, eu, ef)
+
+
+def test_config5_full_size_batch_sampled_against_the_oracle(built):
+    """BASELINE config 5 at full size: 4096 independent ~500-beam random meshes as one job (one CTA per mesh); every
+    16th mesh (256 of them) is solved by the oracle's direct solver on its own and compared."""
+    jobs = [syn.random_mesh(1234 + m) for m in range(4096)]
+    merged = syn.merge_jobs(jobs)
+    with ctx_for(merged, tol=1e-12) as c:
+        c.execute()
+        st = c.stats()
+        assert st["n_components"] == 4096 and st["converged"] == 1
+        U, F = c.displacements(), c.edge_forces()
+    voff = np.concatenate([[0], np.cumsum([j.nodes.shape[0] for j in jobs])])
+    eoff = np.concatenate([[0], np.cumsum([j.elements.shape[0] for j in jobs])])
+    worst = 0.0
+    for m in range(0, 4096, 16):
+        Uo, Fo = orc.solve(to_oracle(jobs[m]))
+        eu = rel_l2(U[voff[m]:voff[m + 1]], Uo)
+        ef = rel_l2(F[:, 2 * eoff[m]:2 * eoff[m + 1]], Fo)
+        worst = max(worst, eu, ef)
+        assert eu < TOL_U and ef < TOL_U, (m, eu, ef)
