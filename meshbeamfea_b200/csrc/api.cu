@@ -392,8 +392,14 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
     if (c->p2p) {
         run_spmv(c, 1, c->p.p, c->Ap.p, c->part_a.p, c->sc.p, c->peerctx.p);
         launch_cg_update(c->st, nb, parity, PartialRef{c->part_a.p, gs, 1}, c->p.p, c->Ap.p, c->y.p, c->rt.p,
-                         c->part_b.p, c->sc.p, c->peerctx.p);
-        launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, c->rt.p, c->p.p, c->sc.p, c->peerctx.p,
+                         c->part_b.p, c->sc.p, c->peerctx.p, c->use_ml ? 0 : 1);
+        const double *zdir = c->rt.p;
+        if (c->use_ml) {   // z~ = M r~; its last kernel all-gathers r~.z~ through the mailboxes in place of r~.r~
+            c->ml.apply(c->st, c->rt.p, c->sdir.p, c->part_b.p, gv, c->sc.p, c->peerctx.p);
+            c->launches += c->ml.kernels_per_apply();
+            zdir = c->sdir.p;
+        }
+        launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, zdir, c->p.p, c->sc.p, c->peerctx.p,
                           c->push_idx.p, c->push_dst.p, c->tickets.p + 2);
         c->launches += 2;
         return;
@@ -411,8 +417,14 @@ void enqueue_iteration(mbfea_ctx *c, int kernel, int parity)
     if (c->use_ml) {
         // z~ = M r~ (into sdir), rho = r~ . z~; the direction update takes z~ where plain CG takes r~
         c->ml.apply(c->st, c->rt.p, c->sdir.p, c->part_b.p, gv);
-        launch_cg_pupdate(c->st, nb, parity, PartialRef{c->part_b.p, gv, 1}, c->sdir.p, c->p.p, c->sc.p, nullptr, nullptr, nullptr,
-                          c->tickets.p + 2);
+        PartialRef rz{c->part_b.p, gv, 1};
+        if (W > 1) {
+            launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 2, nullptr, nullptr, c->sc.p);
+            NK(c->nc->AllGather(c->red.p + 2, c->gath.p + W, 1, nccl::kFloat64, c->comm, c->st));
+            rz = PartialRef{c->gath.p + W, W, 1};
+            c->launches++;
+        }
+        launch_cg_pupdate(c->st, nb, parity, rz, c->sdir.p, c->p.p, c->sc.p, nullptr, nullptr, nullptr, c->tickets.p + 2);
         c->launches += 2 + c->ml.kernels_per_apply();
         return;
     }
@@ -771,7 +783,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         // preconditioner: multilevel on one rank for a single large mesh (auto) or on request
         c->use_ml = false;
         c->ml.reset();
-        const bool ml_possible = c->opt.world == 1 && !batched && c->plan.nb_global >= 64;
+        const bool ml_possible = !batched && c->plan.nb_global >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
         const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
         build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
         build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
@@ -868,8 +880,10 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         CK(cudaStreamSynchronize(c->st));
         lap("load vector");
         if (ml_possible && ml_wanted) {
-            // positions of the block rows (internal numbering) and the mean beam length: the aggregates are bricks
-            std::vector<double> pos((size_t)3 * nb);
+            // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
+            // mean beam length: the aggregates are bricks of a few beam lengths
+            const int64_t nbg = c->plan.nb_global;
+            std::vector<double> pos((size_t)3 * nbg);
             for (int64_t v = 0; v < V; ++v) {
                 const int32_t r = c->plan.free_index[(size_t)v];
                 if (r >= 0) for (int a = 0; a < 3; ++a) pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
@@ -889,7 +903,21 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             if (c->opt.ml_coarsest_rows > 0) mp.coarsest_rows = std::min<int64_t>(c->opt.ml_coarsest_rows, 512);
             if (c->opt.ml_smooth_from > 0) mp.smooth_from = c->opt.ml_smooth_from;
             c->ml.par = mp;
-            c->use_ml = c->ml.build_symbolic(c->st, nb, c->plan.rowptr.data(), c->plan.colidx.data(), pos.data(), len / (double)E);
+            if (c->opt.world == 1) {
+                c->use_ml = c->ml.build_symbolic(c->st, nb, c->plan.rowptr.data(), c->plan.colidx.data(), pos.data(), len / (double)E);
+            } else {
+                // several ranks: the hierarchy is built on the GLOBAL pattern (every rank holds the whole mesh anyway), with
+                // aggregates that never straddle a rank; only the rank's own share of level 0 goes to its device
+                HostPlan G;
+                build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
+                MlDist dist;
+                dist.rank = c->opt.rank; dist.world = c->opt.world;
+                dist.row_begin = c->plan.row_begin; dist.row_end = c->plan.row_end;
+                dist.ghost_global = &c->plan.ghost_global;
+                dist.loc_rowptr = c->plan.rowptr.data(); dist.loc_colidx = c->plan.colidx.data();
+                dist.nc = c->nc; dist.comm = c->comm;
+                c->use_ml = c->ml.build_symbolic(c->st, nbg, G.rowptr.data(), G.colidx.data(), pos.data(), len / (double)E, &dist);
+            }
             if (!c->use_ml && c->opt.precond == 2 && c->opt.verbose)
                 std::fprintf(stderr, "[mbfea] multilevel preconditioner requested but the mesh does not coarsen: block-Jacobi\n");
             c->stats.ms_ml_symbolic = c->ml.ms_symbolic;
@@ -1178,6 +1206,7 @@ int mbfea_solve(mbfea_ctx *c)
                 c->ml.apply(c->st, c->rt.p, c->sdir.p, c->part_b.p, gv);
                 CK(cudaMemcpyAsync(c->p.p, c->sdir.p, (size_t)6 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
                 launch_reduce_partials(c->st, c->part_b.p, gv, c->red.p + 1, nullptr, nullptr, nullptr);
+                if (W > 1) NK(c->nc->AllGather(c->red.p, c->gath.p, 2, nccl::kFloat64, c->comm, c->st));   // trr unchanged, trho = r~.z~
                 c->launches += 1 + c->ml.kernels_per_apply();
             }
             launch_cg_restart_finish(c->st, trr, trho, c->sc.p, c->epoch, 1);

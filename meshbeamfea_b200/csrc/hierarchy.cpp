@@ -47,8 +47,11 @@ static void par_ranges(int64_t n, int64_t min_per_thread, Fn fn)
     for (auto &x : th) x.join();
 }
 
+// part_bounds (optional, nparts + 1 ascending row bounds): aggregates never straddle a part -- a brick cut by a
+// partition boundary becomes one aggregate per part -- and are numbered part-major, so that every part owns a
+// contiguous range of aggregates (multi-GPU: the fine-level transfer is then local to a rank).
 static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *pos, double cell,
-                        HierLevel &L, bool with_galerkin_lists = true)
+                        HierLevel &L, bool with_galerkin_lists = true, const int64_t *part_bounds = nullptr, int nparts = 1)
 {
     Lap lap;
     L.n_fine = n;
@@ -68,14 +71,21 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
             brick[(size_t)v] = (c[0] * cnt[1] + c[1]) * cnt[2] + c[2];
         }
     });
+    int64_t n_keys = cnt[0] * cnt[1] * cnt[2];
+    if (part_bounds != nullptr && nparts > 1) {
+        const int64_t per_part = n_keys;
+        for (int q = 0; q < nparts; ++q)
+            for (int64_t v = part_bounds[q]; v < part_bounds[q + 1]; ++v) brick[(size_t)v] += (int64_t)q * per_part;
+        n_keys *= nparts;
+    }
     lap("bricks", n);
     L.agg.assign((size_t)n, 0);
     L.agg_ptr.clear(); L.agg_rows.resize((size_t)n);
     int32_t na = 0;
-    const double n_bricks = (double)cnt[0] * (double)cnt[1] * (double)cnt[2];
+    const double n_bricks = (double)cnt[0] * (double)cnt[1] * (double)cnt[2] * (double)((part_bounds && nparts > 1) ? nparts : 1);
     if (n_bricks <= 8.0 * (double)n + 1024.0) {
         // counting sort by brick (stable: rows stay ascending inside a brick)
-        const int64_t nbk = cnt[0] * cnt[1] * cnt[2];
+        const int64_t nbk = n_keys;
         std::vector<int32_t> start((size_t)nbk + 1, 0);
         for (int64_t v = 0; v < n; ++v) start[(size_t)brick[(size_t)v] + 1]++;
         std::vector<int32_t> id((size_t)nbk, -1);
@@ -263,7 +273,8 @@ static void build_transfer(int64_t n, const int32_t *rowptr, const int32_t *coli
 }
 
 void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
-                        double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H)
+                        double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H,
+                        const int64_t *part_bounds, int nparts)
 {
     H.agg.clear(); H.xfer.clear();
     if (nb <= 0 || !(cell0 > 0.0) || !(ratio > 1.0)) return;
@@ -274,7 +285,7 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
     int64_t n = nb;
     for (int l = 0; l + 1 < max_levels && n > coarsest_rows; ++l) {
         HierLevel L;
-        build_level(n, crp, cci, pos.data(), cell, L, /*with_galerkin_lists=*/l == 0);
+        build_level(n, crp, cci, pos.data(), cell, L, /*with_galerkin_lists=*/l == 0, l == 0 ? part_bounds : nullptr, l == 0 ? nparts : 1);
         if (L.n_coarse >= n) break;   // no coarsening at this cell size: stop
         MlTransfer T;
         if (l >= 1) {

@@ -1148,7 +1148,7 @@ __global__ void __launch_bounds__(256) k_cg_init_finish(PartialRef rho, PartialR
 __global__ void __launch_bounds__(256, 4) k_cg_update(
     int64_t n, int parity, PartialRef pAp_ref, const double *__restrict__ p, const double *__restrict__ Ap,
     double *__restrict__ y, double *__restrict__ rt, double *__restrict__ part_rho, PcgScalars *sc,
-    const PeerCtx *pc)
+    const PeerCtx *pc, int publish_rho)
 {
     __shared__ double red[33];
     pdl_wait();      // the previous kernel's results (and sc) are visible from here
@@ -1184,7 +1184,8 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
     }
     const double a = block_sum<false>(rho, red);
     if (threadIdx.x == 0) part_rho[blockIdx.x] = a;
-    if (pc != nullptr && last_cta_done(pc->tickets + 1, false)) {
+    // (with a preconditioner rho = r~.z~ comes from its last kernel, k_ml_finish0, which publishes it instead)
+    if (pc != nullptr && publish_rho && last_cta_done(pc->tickets + 1, false)) {
         const double sa = sum_partials(PartialRef{part_rho, (int)gridDim.x, 1}, red);
         if ((int)threadIdx.x < pc->world) {
             Mailbox *m = pc->peer[threadIdx.x];
@@ -1192,6 +1193,51 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
             st_release_sys(&m->dot_tag[1][pc->rank], tag);
         }
     }
+}
+
+// Multilevel preconditioner, last kernel of the apply (fine prolongation + dot): z~_v = r~_v + T_v z1[agg v] with
+// T_v = L_v^T B(d_v) in FP32 (see mlprec.cu); part[blockIdx] = sum of r~ . z~ over the CTA's entries.
+// Thread = (row, scalar i): reads row i of T_v (24 B, consecutive threads -> consecutive addresses).
+// Multi-GPU (pc != null, inside the CG iteration): the last CTA sums the partials and all-gathers this rank's
+// r~.z~ through the NVLink mailboxes -- the slot and tag k_cg_update would have used for r~.r~.
+__global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t *__restrict__ agg, const float *__restrict__ t0,
+                                                       const double *__restrict__ rt, const double *__restrict__ z1,
+                                                       double *__restrict__ zt, double *__restrict__ part,
+                                                       const PcgScalars *sc, const PeerCtx *pc)
+{
+    __shared__ double red[33];
+    if (sc != nullptr && sc->done != 0) return;
+    double dot = 0.0;
+    const int64_t n = 6 * nb;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = t / 6;
+        const double *zc = z1 + (int64_t)__ldg(agg + v) * 6;
+        const float2 *T = reinterpret_cast<const float2 *>(t0 + t * 6);
+        const float2 a = __ldg(T), b = __ldg(T + 1), c = __ldg(T + 2);
+        const double ri = rt[t];
+        double s = ri;
+        s = fma((double)a.x, zc[0], s); s = fma((double)a.y, zc[1], s);
+        s = fma((double)b.x, zc[2], s); s = fma((double)b.y, zc[3], s);
+        s = fma((double)c.x, zc[4], s); s = fma((double)c.y, zc[5], s);
+        zt[t] = s;
+        dot = fma(ri, s, dot);
+    }
+    const double a = block_sum<false>(dot, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = a;
+    if (pc != nullptr && last_cta_done(pc->tickets + 1, false)) {
+        const double sa = sum_partials(PartialRef{part, (int)gridDim.x, 1}, red);
+        if ((int)threadIdx.x < pc->world) {
+            Mailbox *m = pc->peer[threadIdx.x];
+            m->dot_val[1][pc->rank] = sa;
+            st_release_sys(&m->dot_tag[1][pc->rank], sc->tag_cur);
+        }
+    }
+}
+
+void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
+                       const double *z1, double *zt, double *part, const PcgScalars *sc, const PeerCtx *pc)
+{
+    if (nb > 0 && grid > 0) k_ml_finish0<<<(unsigned)grid, 256, 0, st>>>(nb, agg, t0, rt, z1, zt, part, sc, pc);
 }
 
 // p = r~ + beta p.  Multi-GPU: the thread that produces a boundary block's entries also stores
@@ -1710,9 +1756,9 @@ int cg_vec_grid(int64_t nb)
 }
 
 void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *p, const double *Ap,
-                      double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc)
+                      double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc, int publish_rho)
 {
-    launch_pdl(k_cg_update, cg_vec_grid(nb), 256, 0, st, 6 * nb, parity, pAp, p, Ap, y, rt, part_rho, sc, pc);
+    launch_pdl(k_cg_update, cg_vec_grid(nb), 256, 0, st, 6 * nb, parity, pAp, p, Ap, y, rt, part_rho, sc, pc, publish_rho);
 }
 
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,

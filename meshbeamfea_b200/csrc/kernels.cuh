@@ -114,7 +114,8 @@ void launch_cg_init(cudaStream_t st, int64_t nb, const double *f, const double *
 void launch_cg_init_finish(cudaStream_t st, PartialRef rho, PartialRef ff, PcgScalars *sc, double tol,
                            long long max_iter, unsigned long long epoch, unsigned long long *trace);
 void launch_cg_update(cudaStream_t st, int64_t nb, int parity, PartialRef pAp, const double *p, const double *Ap,
-                      double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc);
+                      double *y, double *rt, double *part_rho, PcgScalars *sc, const PeerCtx *pc,
+                      int publish_rho = 1 /* peer path: the last CTA all-gathers r~.r~ (0: a preconditioner's rho follows) */);
 void launch_cg_pupdate(cudaStream_t st, int64_t nb, int parity, PartialRef rho, const double *rt, double *p,
                        PcgScalars *sc, const PeerCtx *pc, const int32_t *push_idx, double *const *push_dst,
                        unsigned int *ticket /* last-CTA ticket: the CTA that retires last advances the scalars */);
@@ -203,7 +204,8 @@ void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, double *colk, in
 void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_t *agg_ptr, const int32_t *agg_rows,
                          const float *t0, const double *r, double *rc);
 void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
-                       const double *z1, double *zt, double *part);
+                       const double *z1, double *zt, double *part, const PcgScalars *sc = nullptr,
+                       const PeerCtx *pc = nullptr /* kernels.cu: peer path publishes r~.z~ through the mailboxes */);
 void launch_ml_restrict(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
                         const float *pval, const double *r, double *rc);
 void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const float *dinv, const int32_t *prow, const int32_t *pcol,

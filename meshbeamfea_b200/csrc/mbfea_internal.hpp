@@ -149,8 +149,11 @@ struct MlHierarchy {
     size_t levels() const { return agg.size(); }   // number of coarse levels
 };
 // smooth_from: first level whose prolongator is smoothed (1 = every coarse-to-coarse transfer; large = none)
+// part_bounds / nparts (multi-GPU): row ranges of the ranks; fine-level aggregates then never straddle a rank and are
+// numbered rank-major (every rank owns a contiguous range of level-1 rows)
 void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
-                        double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H);
+                        double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H,
+                        const int64_t *part_bounds = nullptr, int nparts = 1);
 
 // Explicit inverse of a dense SPD matrix (row-major n x n) for the coarsest level; 0, or 1 + the index of
 // the first non-positive pivot (dense.cpp).

@@ -413,40 +413,6 @@ __global__ void __launch_bounds__(kT) k_ml_restrict0(int64_t n_agg, const int32_
     }
 }
 
-// fine prolongation + dot: z~_v = r~_v + T_v z1[agg v]; part[blockIdx] = sum of r~ . z~ over the CTA's entries.
-// Thread = (row, scalar i): reads row i of T_v (24 B, consecutive threads -> consecutive addresses).
-__global__ void __launch_bounds__(kT, 4) k_ml_finish0(int64_t nb, const int32_t *__restrict__ agg, const float *__restrict__ t0,
-                                                      const double *__restrict__ rt, const double *__restrict__ z1,
-                                                      double *__restrict__ zt, double *__restrict__ part)
-{
-    __shared__ double red[kT / 32];
-    double dot = 0.0;
-    const int64_t n = 6 * nb;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t v = t / 6;
-        const double *zc = z1 + (int64_t)__ldg(agg + v) * 6;
-        const float2 *T = reinterpret_cast<const float2 *>(t0 + t * 6);
-        const float2 a = __ldg(T), b = __ldg(T + 1), c = __ldg(T + 2);
-        const double ri = rt[t];
-        double s = ri;
-        s = fma((double)a.x, zc[0], s); s = fma((double)a.y, zc[1], s);
-        s = fma((double)b.x, zc[2], s); s = fma((double)b.y, zc[3], s);
-        s = fma((double)c.x, zc[4], s); s = fma((double)c.y, zc[5], s);
-        zt[t] = s;
-        dot = fma(ri, s, dot);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dot += __shfl_down_sync(0xffffffffu, dot, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kT / 32; ++w) s += red[w];
-        part[blockIdx.x] = s;
-    }
-}
-
 // coarse restriction, general P (FP32 blocks): rc[I] = sum over the P blocks (i, I) of column I (ascending) of
 // P_iI^T r_i; one warp per coarse row, lanes over the entries, fixed shuffle tree
 __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *__restrict__ rrow,
@@ -631,11 +597,6 @@ void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_
     if (n_agg <= 0) return;
     if (group == 8) k_ml_restrict0<8><<<blocks_for(n_agg * 8), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
     else k_ml_restrict0<32><<<blocks_for(n_agg * 32), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
-}
-void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
-                       const double *z1, double *zt, double *part)
-{
-    if (nb > 0 && grid > 0) k_ml_finish0<<<(unsigned)grid, kT, 0, st>>>(nb, agg, t0, rt, z1, zt, part);
 }
 void launch_ml_restrict(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
                         const float *pval, const double *r, double *rc)

@@ -9,7 +9,9 @@
 #include <vector>
 
 #include "devbuf.hpp"
+#include "kernels.cuh"
 #include "mbfea_internal.hpp"
+#include "nccl_dl.hpp"
 
 namespace mbfea {
 
@@ -33,6 +35,20 @@ struct MlCoarse {                 // one coarse level (l >= 1) and its transfer 
     DevBuf<float> pval32, dinv32;   // what the apply reads: the same rounded values in restriction and prolongation
 };
 
+// Several ranks (vertex-block partition): the fine-level transfer is LOCAL to a rank -- aggregates never straddle a
+// rank, every rank restricts / prolongs its own rows -- while the coarse levels (1 ..) are REPLICATED: each rank
+// assembles its own rows of the level-1 matrix and its slice of the level-1 residual, the slices are exchanged over
+// NCCL (matrix: once per assembly; residual: 48 B per aggregate per apply), and every rank then runs the identical
+// coarse chain (same kernels, same inputs => same bits, so alpha / beta stay identical across ranks).
+struct MlDist {
+    int rank = 0, world = 1;
+    int64_t row_begin = 0, row_end = 0;                   // own rows in the global internal numbering
+    const std::vector<int64_t> *ghost_global = nullptr;   // global rows of the ghost columns (local id nb + g)
+    const int32_t *loc_rowptr = nullptr, *loc_colidx = nullptr;   // the rank's local pattern (host; local column ids)
+    const nccl::Api *nc = nullptr;
+    nccl::Comm comm = nullptr;
+};
+
 class MlPrec {
 public:
     MlParams par;
@@ -45,18 +61,27 @@ public:
     void reset();
     // Level hierarchy of a one-rank job from the full block pattern (host arrays, local ids) and the positions of
     // the block rows; uploads every index array.  Returns false (and stays unusable) when the mesh does not coarsen.
+    // dist != null: (h_rowptr, h_colidx, pos_rm) describe the GLOBAL reduced system (nb = global rows), dist the rank's share.
     bool build_symbolic(cudaStream_t st, int64_t nb, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
-                        double mean_beam_length);
+                        double mean_beam_length, const MlDist *dist = nullptr);
     // Galerkin matrices, smoothers, prolongators, coarsest inverse from the assembled K (full pattern, unscaled) and
     // the Cholesky factors of its diagonal blocks.  *d_flag |= 1/2 on a non-SPD coarse block / coarsest pivot.
     void build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_vals,
                        const double *d_lfac, int *d_flag);
     // zt = M rt, part[0 .. grid) = partials of rt . zt
-    void apply(cudaStream_t st, const double *rt, double *zt, double *part, int grid);
-    int kernels_per_apply() const { return lv.empty() ? 0 : (int)(2 * lv.size() + 1); }
+    // sc / pc (multi-GPU peer path, inside the CG iteration): the last kernel publishes this rank's r~.z~ through the mailboxes
+    void apply(cudaStream_t st, const double *rt, double *zt, double *part, int grid, const dev::PcgScalars *sc = nullptr,
+               const dev::PeerCtx *pc = nullptr);
+    int kernels_per_apply() const { return lv.empty() ? 0 : (int)(2 * lv.size() + 1 + (world > 1 ? 1 : 0)); }
     size_t levels() const { return lv.size(); }
 
 private:
+    // multi-rank: own slice of level 1 (aggregates [agg_begin[rank], agg_begin[rank + 1]), their matrix blocks)
+    int rank = 0, world = 1;
+    const nccl::Api *nc = nullptr;
+    nccl::Comm comm = nullptr;
+    std::vector<int64_t> agg_begin, blk_begin;   // per rank: first level-1 row / first level-1 matrix block (world + 1 entries)
+    void exchange_slices(cudaStream_t st, double *buf, const std::vector<int64_t> &begin, int width);
     DevBuf<int32_t> agg0, agg_ptr0, agg_rows0, gal_ptr0, gal_src0, frow0;
     DevBuf<double> off0;
     DevBuf<float> t0;

@@ -33,27 +33,87 @@ void MlPrec::reset()
 }
 
 bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
-                            double mean_len)
+                            double mean_len, const MlDist *dist)
 {
     const double t0w = wall_ms();
     reset();
-    nb = nb_;
-    if (nb <= 0 || !(mean_len > 0.0)) return false;
+    if (nb_ <= 0 || !(mean_len > 0.0)) return false;
+    rank = dist ? dist->rank : 0; world = dist ? dist->world : 1;
+    nc = dist ? dist->nc : nullptr; comm = dist ? dist->comm : nullptr;
+    const int64_t nbg = nb_;   // rows of the (global) system the hierarchy is built on
+    std::vector<int64_t> bounds((size_t)world + 1);
+    for (int q = 0; q <= world; ++q) bounds[(size_t)q] = nbg * q / world;
     MlHierarchy H;
-    build_ml_hierarchy(nb, h_rowptr, h_colidx, pos_rm, par.cell * mean_len, par.ratio, par.max_levels, par.coarsest_rows,
-                       std::max(1, par.smooth_from), H);
+    build_ml_hierarchy(nbg, h_rowptr, h_colidx, pos_rm, par.cell * mean_len, par.ratio, par.max_levels, par.coarsest_rows,
+                       std::max(1, par.smooth_from), H, world > 1 ? bounds.data() : nullptr, world);
     const size_t L = H.levels();
     if (L == 0) return false;
     if (6 * H.agg[L - 1].n_coarse > 3072) return false;   // the chain stopped early (max_levels): no dense inverse that large
     // level 0 -> 1
     const HierLevel &h0 = H.agg[0];
-    up(st, agg0, h0.agg); up(st, agg_ptr0, h0.agg_ptr); up(st, agg_rows0, h0.agg_rows);
-    up(st, gal_ptr0, h0.gal_ptr); up(st, gal_src0, h0.gal_src); up(st, off0, h0.off);
-    CK(frow0.alloc((size_t)h_rowptr[nb]));
-    CK(t0.alloc((size_t)nb * 36));
     int32_t biggest = 0;
     for (int64_t I = 0; I < h0.n_coarse; ++I) biggest = std::max(biggest, h0.agg_ptr[(size_t)I + 1] - h0.agg_ptr[(size_t)I]);
     group0 = biggest <= 8 ? 8 : 32;
+    agg_begin.assign((size_t)world + 1, 0); blk_begin.assign((size_t)world + 1, 0);
+    for (int q = 0; q < world; ++q) {   // aggregates are numbered rank-major: rank q owns [agg of its first row .. )
+        int32_t hi = -1;
+        for (int64_t v = bounds[(size_t)q]; v < bounds[(size_t)q + 1]; ++v) hi = std::max(hi, h0.agg[(size_t)v]);
+        agg_begin[(size_t)q + 1] = std::max<int64_t>(agg_begin[(size_t)q], (int64_t)hi + 1);
+    }
+    for (int q = 0; q <= world; ++q) blk_begin[(size_t)q] = h0.rowptr[(size_t)agg_begin[(size_t)q]];
+    if (world == 1) {
+        nb = nbg;
+        up(st, agg0, h0.agg); up(st, agg_ptr0, h0.agg_ptr); up(st, agg_rows0, h0.agg_rows);
+        up(st, gal_ptr0, h0.gal_ptr); up(st, gal_src0, h0.gal_src); up(st, off0, h0.off);
+        CK(frow0.alloc((size_t)h_rowptr[nbg]));
+    } else {
+        // the rank's share of level 0: own rows (local ids), own aggregates, own rows of the level-1 matrix
+        const int64_t r0 = dist->row_begin, nbl = dist->row_end - dist->row_begin;
+        const int64_t ng = (int64_t)dist->ghost_global->size();
+        const int64_t a0 = agg_begin[(size_t)rank], a1 = agg_begin[(size_t)rank + 1];
+        nb = nbl;
+        std::vector<int32_t> agg_l((size_t)nbl), ptr_l((size_t)(a1 - a0) + 1), rows_l;
+        std::vector<double> off_l((size_t)3 * (size_t)(nbl + ng));
+        for (int64_t i = 0; i < nbl; ++i) {
+            agg_l[(size_t)i] = h0.agg[(size_t)(r0 + i)];
+            for (int a = 0; a < 3; ++a) off_l[(size_t)3 * i + a] = h0.off[(size_t)3 * (r0 + i) + a];
+        }
+        for (int64_t g = 0; g < ng; ++g)
+            for (int a = 0; a < 3; ++a) off_l[(size_t)3 * (nbl + g) + a] = h0.off[(size_t)3 * (*dist->ghost_global)[(size_t)g] + a];
+        rows_l.reserve((size_t)nbl);
+        for (int64_t I = a0; I < a1; ++I) {
+            ptr_l[(size_t)(I - a0)] = (int32_t)rows_l.size();
+            for (int32_t q = h0.agg_ptr[(size_t)I]; q < h0.agg_ptr[(size_t)I + 1]; ++q) rows_l.push_back((int32_t)(h0.agg_rows[(size_t)q] - r0));
+        }
+        ptr_l[(size_t)(a1 - a0)] = (int32_t)rows_l.size();
+        // contributor lists of the own level-1 blocks, fine blocks renumbered from the global to the local pattern
+        const int64_t b0 = blk_begin[(size_t)rank], b1 = blk_begin[(size_t)rank + 1];
+        std::vector<int32_t> gp((size_t)(b1 - b0) + 1), gs;
+        gs.reserve((size_t)(h0.gal_ptr[(size_t)b1] - h0.gal_ptr[(size_t)b0]));
+        // global fine block k of own row r -> local block: same row, column found in the local row
+        std::vector<int32_t> row_of_blk;   // row of every global block of the own rows
+        const int32_t k_lo = h_rowptr[r0], k_hi = h_rowptr[r0 + nbl];
+        std::vector<int32_t> g2l((size_t)(k_hi - k_lo));
+        for (int64_t i = 0; i < nbl; ++i) {
+            const int32_t *lb = dist->loc_colidx + dist->loc_rowptr[i], *le = dist->loc_colidx + dist->loc_rowptr[i + 1];
+            for (int32_t k = h_rowptr[r0 + i]; k < h_rowptr[r0 + i + 1]; ++k) {
+                const int64_t cg = h_colidx[k];
+                int32_t lc;
+                if (cg >= r0 && cg < r0 + nbl) lc = (int32_t)(cg - r0);
+                else lc = (int32_t)(nbl + (std::lower_bound(dist->ghost_global->begin(), dist->ghost_global->end(), cg) - dist->ghost_global->begin()));
+                g2l[(size_t)(k - k_lo)] = (int32_t)(std::lower_bound(lb, le, lc) - dist->loc_colidx);
+            }
+        }
+        for (int64_t k = b0; k < b1; ++k) {
+            gp[(size_t)(k - b0)] = (int32_t)gs.size();
+            for (int32_t s2 = h0.gal_ptr[(size_t)k]; s2 < h0.gal_ptr[(size_t)k + 1]; ++s2) gs.push_back(g2l[(size_t)(h0.gal_src[(size_t)s2] - k_lo)]);
+        }
+        gp[(size_t)(b1 - b0)] = (int32_t)gs.size();
+        up(st, agg0, agg_l); up(st, agg_ptr0, ptr_l); up(st, agg_rows0, rows_l);
+        up(st, gal_ptr0, gp); up(st, gal_src0, gs); up(st, off0, off_l);
+        CK(frow0.alloc((size_t)dist->loc_rowptr[nbl]));
+    }
+    CK(t0.alloc((size_t)nb * 36));
     rows.push_back(nb);
     for (size_t m = 0; m < L; ++m) {
         std::unique_ptr<MlCoarse> c(new MlCoarse);
@@ -108,8 +168,11 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
     int64_t k = 0;
     launch_ml_row_of(st, nb, d_rowptr, frow0.p);
     launch_ml_make_t0(st, nb, d_lfac, off0.p, t0.p);
-    launch_ml_galerkin0(st, lv[0]->nnz, gal_ptr0.p, gal_src0.p, frow0.p, d_colidx, d_vals, off0.p, lv[0]->vals.p);
+    // level-1 matrix: the own block rows (all of them on one rank), then the slices of the other ranks
+    launch_ml_galerkin0(st, blk_begin[(size_t)rank + 1] - blk_begin[(size_t)rank], gal_ptr0.p, gal_src0.p, frow0.p, d_colidx, d_vals,
+                        off0.p, lv[0]->vals.p + 36 * blk_begin[(size_t)rank]);
     k += 3;
+    if (world > 1) { exchange_slices(st, lv[0]->vals.p, blk_begin, 36); ++k; }
     for (size_t m = 0; m < lv.size(); ++m) {
         MlCoarse &c = *lv[m];
         if (!c.has_next) break;
@@ -135,10 +198,27 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
     numeric_ok = true;
 }
 
-void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, int grid)
+// every rank sends its slice [begin[rank], begin[rank + 1]) (x width doubles) of `buf` to every other rank: one grouped
+// NCCL send / receive (a single fused kernel; capturable in the CG graph)
+void MlPrec::exchange_slices(cudaStream_t st, double *buf, const std::vector<int64_t> &begin, int width)
+{
+    const size_t mine = (size_t)(width * (begin[(size_t)rank + 1] - begin[(size_t)rank]));
+    NK(nc->GroupStart());
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        const size_t theirs = (size_t)(width * (begin[(size_t)q + 1] - begin[(size_t)q]));
+        if (mine) NK(nc->Send(buf + width * begin[(size_t)rank], mine, nccl::kFloat64, q, comm, st));
+        if (theirs) NK(nc->Recv(buf + width * begin[(size_t)q], theirs, nccl::kFloat64, q, comm, st));
+    }
+    NK(nc->GroupEnd());
+}
+
+void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, int grid, const PcgScalars *sc, const PeerCtx *pc)
 {
     const size_t L = lv.size();
-    launch_ml_restrict0(st, lv[0]->n, group0, agg_ptr0.p, agg_rows0.p, t0.p, rt, lv[0]->r.p);
+    launch_ml_restrict0(st, agg_begin[(size_t)rank + 1] - agg_begin[(size_t)rank], group0, agg_ptr0.p, agg_rows0.p, t0.p, rt,
+                        lv[0]->r.p + 6 * agg_begin[(size_t)rank]);
+    if (world > 1) exchange_slices(st, lv[0]->r.p, agg_begin, 6);
     for (size_t m = 0; m + 1 < L; ++m) {
         if (lv[m]->smoothed)
             launch_ml_restrict(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->pval32.p, lv[m]->r.p, lv[m + 1]->r.p);
@@ -154,7 +234,7 @@ void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, 
             launch_ml_smooth_prolong_tent(st, lv[m]->n, lv[m]->dinv32.p, lv[m]->agg.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->z.p,
                                           lv[m]->z.p);
     }
-    launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part);
+    launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part, sc, pc);
 }
 
 }  // namespace mbfea
