@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -90,23 +93,13 @@ bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowpt
         const int64_t b0 = blk_begin[(size_t)rank], b1 = blk_begin[(size_t)rank + 1];
         std::vector<int32_t> gp((size_t)(b1 - b0) + 1), gs;
         gs.reserve((size_t)(h0.gal_ptr[(size_t)b1] - h0.gal_ptr[(size_t)b0]));
-        // global fine block k of own row r -> local block: same row, column found in the local row
-        std::vector<int32_t> row_of_blk;   // row of every global block of the own rows
-        const int32_t k_lo = h_rowptr[r0], k_hi = h_rowptr[r0 + nbl];
-        std::vector<int32_t> g2l((size_t)(k_hi - k_lo));
-        for (int64_t i = 0; i < nbl; ++i) {
-            const int32_t *lb = dist->loc_colidx + dist->loc_rowptr[i], *le = dist->loc_colidx + dist->loc_rowptr[i + 1];
-            for (int32_t k = h_rowptr[r0 + i]; k < h_rowptr[r0 + i + 1]; ++k) {
-                const int64_t cg = h_colidx[k];
-                int32_t lc;
-                if (cg >= r0 && cg < r0 + nbl) lc = (int32_t)(cg - r0);
-                else lc = (int32_t)(nbl + (std::lower_bound(dist->ghost_global->begin(), dist->ghost_global->end(), cg) - dist->ghost_global->begin()));
-                g2l[(size_t)(k - k_lo)] = (int32_t)(std::lower_bound(lb, le, lc) - dist->loc_colidx);
-            }
-        }
+        // the rank's local pattern keeps the blocks of a row in GLOBAL column order (build_plan only renames the column
+        // ids), so the local index of global fine block k of an own row is k - (first block of the first own row)
+        const int32_t k_lo = h_rowptr[r0];
+        if (h_rowptr[r0 + nbl] - k_lo != dist->loc_rowptr[nbl]) return false;   // the two plans disagree: stay with block-Jacobi
         for (int64_t k = b0; k < b1; ++k) {
             gp[(size_t)(k - b0)] = (int32_t)gs.size();
-            for (int32_t s2 = h0.gal_ptr[(size_t)k]; s2 < h0.gal_ptr[(size_t)k + 1]; ++s2) gs.push_back(g2l[(size_t)(h0.gal_src[(size_t)s2] - k_lo)]);
+            for (int32_t s2 = h0.gal_ptr[(size_t)k]; s2 < h0.gal_ptr[(size_t)k + 1]; ++s2) gs.push_back(h0.gal_src[(size_t)s2] - k_lo);
         }
         gp[(size_t)(b1 - b0)] = (int32_t)gs.size();
         up(st, agg0, agg_l); up(st, agg_ptr0, ptr_l); up(st, agg_rows0, rows_l);
@@ -173,6 +166,38 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
                         off0.p, lv[0]->vals.p + 36 * blk_begin[(size_t)rank]);
     k += 3;
     if (world > 1) { exchange_slices(st, lv[0]->vals.p, blk_begin, 36); ++k; }
+    if (std::getenv("MBFEA_ML_DEBUG")) {   // level-1 matrix after the exchange: zero blocks and asymmetry per owner rank
+        MlCoarse &c1 = *lv[0];
+        std::vector<double> v((size_t)c1.nnz * 36);
+        std::vector<int32_t> rp((size_t)c1.n + 1), ci((size_t)c1.nnz);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(v.data(), c1.vals.p, v.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rp.data(), c1.rowptr.p, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ci.data(), c1.colidx.p, ci.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int q = 0; q < world; ++q) {
+            int64_t zero = 0, nonfinite = 0, badsym = 0, neg_diag = 0;
+            double worst = 0.0;
+            for (int64_t I = agg_begin[(size_t)q]; I < agg_begin[(size_t)q + 1]; ++I)
+                for (int32_t kk = rp[(size_t)I]; kk < rp[(size_t)I + 1]; ++kk) {
+                    const double *B = v.data() + (size_t)kk * 36;
+                    double mx = 0.0; bool fin = true;
+                    for (int e = 0; e < 36; ++e) { mx = std::max(mx, std::fabs(B[e])); fin = fin && std::isfinite(B[e]); }
+                    if (!fin) { ++nonfinite; continue; }
+                    if (mx == 0.0) ++zero;
+                    const int32_t J = ci[(size_t)kk];
+                    if (J == I) { for (int d = 0; d < 6; ++d) if (!(B[7 * d] > 0.0)) { ++neg_diag; break; } }
+                    const int32_t *jb = ci.data() + rp[(size_t)J], *je = ci.data() + rp[(size_t)J + 1];
+                    const int32_t *pos = std::lower_bound(jb, je, (int32_t)I);
+                    if (pos == je || *pos != I) { ++badsym; continue; }
+                    const double *T = v.data() + (size_t)(pos - ci.data()) * 36;
+                    for (int r = 0; r < 6; ++r) for (int cc = 0; cc < 6; ++cc) worst = std::max(worst, std::fabs(B[6 * r + cc] - T[6 * cc + r]) / (mx + 1e-300));
+                }
+            std::fprintf(stderr, "[mbfea ml debug] rank %d sees level-1 rows of rank %d: aggregates [%lld, %lld) blocks [%lld, %lld): zero blocks %lld, non-finite %lld, "
+                                 "missing transposes %lld, non-positive diagonals %lld, worst asymmetry %.2e\n", rank, q,
+                         (long long)agg_begin[(size_t)q], (long long)agg_begin[(size_t)q + 1], (long long)blk_begin[(size_t)q],
+                         (long long)blk_begin[(size_t)q + 1], (long long)zero, (long long)nonfinite, (long long)badsym, (long long)neg_diag, worst);
+        }
+    }
     for (size_t m = 0; m < lv.size(); ++m) {
         MlCoarse &c = *lv[m];
         if (!c.has_next) break;

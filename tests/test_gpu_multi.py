@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, uid_path, out_dir, n, comm_mode, variant):
+def _worker(rank, world, uid_path, out_dir, n, comm_mode, variant, precond):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import time
     import meshbeamfea_b200 as mb
@@ -31,7 +31,7 @@ def _worker(rank, world, uid_path, out_dir, n, comm_mode, variant):
             time.sleep(0.05)
         uid = open(uid_path, "rb").read()
     job = syn.cubic_lattice(n)
-    c = mb.Context(device=rank, tol=1e-12, comm_mode=comm_mode, cg_variant=variant)
+    c = mb.Context(device=rank, tol=1e-12, comm_mode=comm_mode, cg_variant=variant, precond=precond)
     c.comm_init(uid, rank, world)
     c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job.beamMaterial,
               job.fixedNodes, job.nodalForces)
@@ -43,10 +43,11 @@ def _worker(rank, world, uid_path, out_dir, n, comm_mode, variant):
     c.close()
 
 
-@pytest.mark.parametrize("comm_mode,variant", [(0, 1), (1, 1), (0, 2), (1, 2)],
-                         ids=["nvlink_peer_memory", "nccl", "nvlink_single_reduction_cg", "nccl_single_reduction_cg"])
+@pytest.mark.parametrize("comm_mode,variant,precond", [(0, 1, 1), (1, 1, 1), (0, 2, 1), (1, 2, 1), (0, 1, 2), (1, 1, 2)],
+                         ids=["nvlink_peer_memory", "nccl", "nvlink_single_reduction_cg", "nccl_single_reduction_cg",
+                              "nvlink_multilevel", "nccl_multilevel"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_two_rank_solve_matches_single_and_oracle(built, tmp_path, world, comm_mode, variant):
+def test_two_rank_solve_matches_single_and_oracle(built, tmp_path, world, comm_mode, variant, precond):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import meshbeamfea_b200 as mb
@@ -54,13 +55,14 @@ def test_two_rank_solve_matches_single_and_oracle(built, tmp_path, world, comm_m
     from oracle import oracle as orc
     from helpers import to_oracle, rel_l2
     n = 14
-    mp.spawn(_worker, args=(world, os.path.join(str(tmp_path), "uid"), str(tmp_path), n, comm_mode, variant), nprocs=world,
-             join=True)
+    mp.spawn(_worker, args=(world, os.path.join(str(tmp_path), "uid"), str(tmp_path), n, comm_mode, variant, precond),
+             nprocs=world, join=True)
     job = syn.cubic_lattice(n)
-    with mb.Context(device=0, tol=1e-12) as c:
+    with mb.Context(device=0, tol=1e-12, precond=precond) as c:
         c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job.beamMaterial,
                   job.fixedNodes, job.nodalForces)
         c.execute()
+        assert c.stats()["precond"] == precond
         U1, F1 = c.displacements(), c.edge_forces()
         rp1, col1, vals1, _ = c.bsr()
         its1 = c.stats()["iterations"]

@@ -21,10 +21,10 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 
-def run(n, tol, use_graph=True, max_iter=0, comm_mode=0):
+def run(n, tol, use_graph=True, max_iter=0, comm_mode=0, precond=1, cg_variant=0):
     job = syn.cubic_lattice(n)
     c = mb.Context(device=local, tol=tol, verbose=(rank == 0), use_graph=use_graph, max_iter=max_iter,
-                   comm_mode=comm_mode)
+                   comm_mode=comm_mode, precond=precond, cg_variant=cg_variant)
     uid = [mb.Context.comm_unique_id() if rank == 0 else None]   # one fresh NCCL id per communicator
     dist.broadcast_object_list(uid, src=0)
     c.comm_init(uid[0], rank, world)
@@ -36,24 +36,31 @@ def run(n, tol, use_graph=True, max_iter=0, comm_mode=0):
     return job, c, dt
 
 
+PN = int(os.environ.get("MBFEA_PARITY_N", "14"))
 for mode in (0, 1):
-    job, c, dt = run(12, 1e-12, comm_mode=mode)
-    U, F = c.displacements(), c.edge_forces()
-    if rank == 0:
-        from oracle import oracle as orc
-        from helpers import to_oracle, rel_l2
-        Uo, Fo = orc.solve(to_oracle(job))
-        print(f"[multi] world={world} comm_mode={mode} lattice12: its={c.stats()['iterations']} "
-              f"err u={rel_l2(U, Uo):.2e} F={rel_l2(F, Fo):.2e}", flush=True)
-    c.close()
-for mode, graph in ((0, True), (0, False), (1, True)):
-    job, c, dt = run(int(os.environ.get("MBFEA_N", "100")), 1e-8, use_graph=graph, comm_mode=mode)
+    for precond, variant in ((1, 1), (1, 2), (2, 1)):
+        job, c, dt = run(PN, 1e-12, comm_mode=mode, precond=precond, cg_variant=variant)
+        U, F = c.displacements(), c.edge_forces()
+        st = c.stats()
+        if rank == 0:
+            from oracle import oracle as orc
+            from helpers import to_oracle, rel_l2
+            Uo, Fo = orc.solve(to_oracle(job))
+            print(f"[multi] PARITY world={world} comm_mode={mode} ({'NVLink peer memory' if mode == 0 else 'NCCL'}) precond={st['precond']} "
+                  f"cg_variant={variant} lattice{PN}: its={st['iterations']} err vs oracle u={rel_l2(U, Uo):.2e} F={rel_l2(F, Fo):.2e} "
+                  f"{'OK' if max(rel_l2(U, Uo), rel_l2(F, Fo)) < 1e-8 else 'FAIL'}", flush=True)
+        c.close()
+N = int(os.environ.get("MBFEA_N", "100"))
+for mode, graph, precond in ((0, True, 1), (0, True, 2), (1, True, 2), (0, False, 2)):
+    if N <= 0:
+        break
+    job, c, dt = run(N, 1e-8, use_graph=graph, comm_mode=mode, precond=precond)
     st = c.stats()
     if rank == 0:
-        print(f"[multi] world={world} comm_mode={mode} graph={graph} lattice: its={st['iterations']} relres={st['rel_residual']:.2e} "
-              f"true={st['true_rel_residual']:.2e} pcg={st['ms_pcg']:.1f} ms "
-              f"({st['ms_pcg'] / max(1, st['iterations']):.4f} ms/it) asm={st['ms_assemble']:.2f} wall={dt:.3f}s "
-              f"ghosts={st['n_ghost_blocks']}", flush=True)
+        print(f"[multi] TIMED world={world} comm_mode={mode} graph={graph} precond={st['precond']} lattice{N}: its={st['iterations']} "
+              f"relres={st['rel_residual']:.2e} true={st['true_rel_residual']:.2e} pcg={st['ms_pcg']:.1f} ms "
+              f"({st['ms_pcg'] / max(1, st['iterations']):.4f} ms/it) asm={st['ms_assemble']:.2f} precond={st['ms_precond']:.2f} "
+              f"ml_setup={st['ms_ml_setup']:.2f} symbolic={st['ms_ml_symbolic']:.0f} wall={dt:.3f}s ghosts={st['n_ghost_blocks']}", flush=True)
     c.close()
 dist.barrier()
 dist.destroy_process_group()
