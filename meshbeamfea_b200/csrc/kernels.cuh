@@ -184,9 +184,10 @@ void launch_ml_galerkin0(cudaStream_t st, int64_t n_coarse_blocks, const int32_t
 void launch_ml_dense_to_f32(cudaStream_t st, int n, const double *a, float *out);
 void launch_ml_dense_matvec(cudaStream_t st, int n, const float *ainv, const double *r, double *z);
 void launch_ml_to_f32(cudaStream_t st, int64_t n, const double *a, float *out);
+// restrictions: only the fine rows [fine_lo, fine_hi) contribute; prolongations: rows [row0, row0 + n)
 void launch_ml_restrict_tent(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rfine, const double *off,
-                             const double *r, double *rc);
-void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t n, const float *dinv, const int32_t *agg, const double *off,
+                             const double *r, double *rc, int64_t fine_lo, int64_t fine_hi);
+void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t row0, int64_t n, const float *dinv, const int32_t *agg, const double *off,
                                    const double *r, const double *zc, double *z);
 void launch_ml_row_of(cudaStream_t st, int64_t n, const int32_t *rowptr, int32_t *row_of);
 void launch_ml_make_p(cudaStream_t st, int64_t n, int64_t nnzp, const int32_t *prow, const int32_t *pcol, const int32_t *prow_of,
@@ -206,9 +207,10 @@ void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_
 void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
                        const double *z1, double *zt, double *part, const PcgScalars *sc = nullptr,
                        const PeerCtx *pc = nullptr /* kernels.cu: peer path publishes r~.z~ through the mailboxes */);
-void launch_ml_restrict(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
-                        const float *pval, const double *r, double *rc);
-void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const float *dinv, const int32_t *prow, const int32_t *pcol,
-                              const float *pval, const double *r, const double *zc, double *z);
+void launch_ml_restrict(cudaStream_t st, int64_t nc, int64_t nnzp, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
+                        const float *pval, const double *r, double *rc, int64_t fine_lo, int64_t fine_hi);
+void launch_ml_smooth_prolong(cudaStream_t st, int64_t row0, int64_t n, int64_t n_level, int64_t nnzp, const float *dinv,
+                              const int32_t *prow, const int32_t *pcol, const float *pval, const double *r, const double *zc,
+                              double *z);
 
 }}  // namespace mbfea::dev

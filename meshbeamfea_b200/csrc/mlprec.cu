@@ -263,11 +263,22 @@ __global__ void __launch_bounds__(128) k_ml_galerkin0(int64_t n_coarse_blocks, c
 //   update: A_ij -= C_i A_kj for i != k, j != k;  A_ik := -C_i Pinv   (C_i: the saved column block)   -- n^2 threads
 // *flag |= 2 on a non-positive pivot.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ml_gj_pivot(int n, int k, double *__restrict__ a, double *__restrict__ colk, int *flag)
+__global__ void __launch_bounds__(1024) k_ml_gj_pivot(int n, int k, double *__restrict__ a, double *__restrict__ colk, int *flag)
 {
     __shared__ double P[36];
     const int k6 = 6 * k;
     if (threadIdx.x < 36) P[threadIdx.x] = a[(size_t)(k6 + threadIdx.x / 6) * n + k6 + threadIdx.x % 6];
+    // save the column block (old values), all rows: independent loads, issued before anyone waits for the pivot
+    for (int t = threadIdx.x; t < n * 6; t += blockDim.x) colk[t] = a[(size_t)(t / 6) * n + k6 + t % 6];
+    // the 6 old values of the pivot rows in this thread's columns
+    double v[2][6];
+    int jj[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        jj[u] = threadIdx.x + u * 1024;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[u][c] = jj[u] < n ? a[(size_t)(k6 + c) * n + jj[u]] : 0.0;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {   // in-place Gauss-Jordan of the 6x6 pivot block
         bool bad = false;
@@ -284,23 +295,24 @@ __global__ void __launch_bounds__(256) k_ml_gj_pivot(int n, int k, double *__res
         }
         if (bad) atomicOr(flag, 2);
     }
-    // save the column block (old values), all rows
-    for (int t = threadIdx.x; t < n * 6; t += blockDim.x) colk[t] = a[(size_t)(t / 6) * n + k6 + t % 6];
     __syncthreads();
-    // new block row k: for every column j the 6 old values of the pivot rows -> Pinv times them
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        double v[6], w[6];
+    // new block row k: Pinv times the old pivot rows (Pinv itself in the pivot columns); n <= 3072 = 3 x 1024 columns
+    for (int u = 0; u < 3; ++u) {
+        const int j = threadIdx.x + u * 1024;
+        if (j >= n) break;
+        double vv[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) v[c] = a[(size_t)(k6 + c) * n + j];
+        for (int c = 0; c < 6; ++c) vv[c] = u < 2 ? v[u][c] : a[(size_t)(k6 + c) * n + j];
         const bool in = j >= k6 && j < k6 + 6;
+        double w[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-            double s = 0.0;
-            if (in) s = P[6 * r + (j - k6)];
+            double s2 = 0.0;
+            if (in) s2 = P[6 * r + (j - k6)];
             else
 #pragma unroll
-                for (int c = 0; c < 6; ++c) s = fma(P[6 * r + c], v[c], s);
-            w[r] = s;
+                for (int c = 0; c < 6; ++c) s2 = fma(P[6 * r + c], vv[c], s2);
+            w[r] = s2;
         }
 #pragma unroll
         for (int r = 0; r < 6; ++r) a[(size_t)(k6 + r) * n + j] = w[r];
@@ -415,18 +427,22 @@ __global__ void __launch_bounds__(kT) k_ml_restrict0(int64_t n_agg, const int32_
 
 // coarse restriction, general P (FP32 blocks): rc[I] = sum over the P blocks (i, I) of column I (ascending) of
 // P_iI^T r_i; one warp per coarse row, lanes over the entries, fixed shuffle tree
+// [fine_lo, fine_hi): only the fine rows of this window contribute (several ranks: each rank sums over its own rows of the
+// finer level and the partial results are all-reduced)
 __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *__restrict__ rrow,
                                                     const int32_t *__restrict__ rblk, const int32_t *__restrict__ rfine,
                                                     const float *__restrict__ pval, const double *__restrict__ r,
-                                                    double *__restrict__ rc)
+                                                    double *__restrict__ rc, int32_t fine_lo, int32_t fine_hi)
 {
     const int lane = threadIdx.x & 31;
     const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (I >= nc) return;   // whole warps leave together
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int32_t e = __ldg(rrow + I) + lane; e < __ldg(rrow + I + 1); e += 32) {
+        const int32_t fi = __ldg(rfine + e);
+        if (fi < fine_lo || fi >= fine_hi) continue;
         const float4 *P = reinterpret_cast<const float4 *>(pval + (int64_t)__ldg(rblk + e) * 36);
-        const double *rv = r + (int64_t)__ldg(rfine + e) * 6;
+        const double *rv = r + (int64_t)fi * 6;
         float pp[36];
 #pragma unroll
         for (int x = 0; x < 9; ++x) { const float4 f = __ldg(P + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
@@ -446,11 +462,49 @@ __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *_
         for (int j = 0; j < 6; ++j) rc[I * 6 + j] = acc[j];
 }
 
+// the same for coarse levels whose rows are long (smoothed prolongators between small levels: hundreds of P blocks per
+// coarse row, a few hundred rows): one CTA of 128 threads per coarse row, one entry per thread and pass, fixed-order
+// CTA reduction -- the warp-per-row kernel above is latency-bound there (7 dependent passes per warp, 216 warps)
+__global__ void __launch_bounds__(128) k_ml_restrict_wide(int64_t nc, const int32_t *__restrict__ rrow,
+                                                          const int32_t *__restrict__ rblk, const int32_t *__restrict__ rfine,
+                                                          const float *__restrict__ pval, const double *__restrict__ r,
+                                                          double *__restrict__ rc, int32_t fine_lo, int32_t fine_hi)
+{
+    __shared__ double red[4][6];
+    const int64_t I = blockIdx.x;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int32_t e = __ldg(rrow + I) + threadIdx.x; e < __ldg(rrow + I + 1); e += 128) {
+        const int32_t fi = __ldg(rfine + e);
+        if (fi < fine_lo || fi >= fine_hi) continue;
+        const float4 *P = reinterpret_cast<const float4 *>(pval + (int64_t)__ldg(rblk + e) * 36);
+        const double *rv = r + (int64_t)fi * 6;
+        float pp[36];
+#pragma unroll
+        for (int x = 0; x < 9; ++x) { const float4 f = __ldg(P + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double ri = rv[i];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[j] = fma((double)pp[6 * i + j], ri, acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], o);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) red[threadIdx.x >> 5][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 6) rc[I * 6 + threadIdx.x] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
 // coarse restriction, TENTATIVE P (one rigid block per row, generated from the offsets: 24 bytes per member instead
 // of a 6x6 block): rc[I] = sum over the members i of aggregate I (ascending) of B(off_i)^T r_i; 8 lanes per aggregate
 __global__ void __launch_bounds__(kT) k_ml_restrict_tent(int64_t nc, const int32_t *__restrict__ rrow,
                                                          const int32_t *__restrict__ rfine, const double *__restrict__ off,
-                                                         const double *__restrict__ r, double *__restrict__ rc)
+                                                         const double *__restrict__ r, double *__restrict__ rc,
+                                                         int32_t fine_lo, int32_t fine_hi)
 {
     const int lane = threadIdx.x & 7;
     const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -458,6 +512,7 @@ __global__ void __launch_bounds__(kT) k_ml_restrict_tent(int64_t nc, const int32
     if (I < nc) {
         for (int32_t e = __ldg(rrow + I) + lane; e < __ldg(rrow + I + 1); e += 8) {
             const int64_t i = __ldg(rfine + e);
+            if (i < fine_lo || i >= fine_hi) continue;
             double w[6], t[6];
 #pragma unroll
             for (int x = 0; x < 6; ++x) w[x] = r[i * 6 + x];
@@ -480,11 +535,11 @@ __global__ void __launch_bounds__(kT) k_ml_restrict_tent(int64_t nc, const int32
 __global__ void __launch_bounds__(kT) k_ml_smooth_prolong(int64_t n, const float *__restrict__ dinv,
                                                           const int32_t *__restrict__ prow, const int32_t *__restrict__ pcol,
                                                           const float *__restrict__ pval, const double *__restrict__ r,
-                                                          const double *__restrict__ zc, double *__restrict__ z)
+                                                          const double *__restrict__ zc, double *__restrict__ z, int64_t row0)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t v = t / 6;
-    if (v >= n) return;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 / 6 >= n) return;
+    const int64_t t = t0 + 6 * row0, v = t / 6;   // rows [row0, row0 + n)
     const int i = (int)(t - v * 6);
     const float2 *D = reinterpret_cast<const float2 *>(dinv + v * 36 + 6 * i);
     const double *rv = r + v * 6;
@@ -502,15 +557,58 @@ __global__ void __launch_bounds__(kT) k_ml_smooth_prolong(int64_t n, const float
     z[t] = s;
 }
 
+// the same with one WARP per row, lanes over the row's P blocks (rows of smoothed prolongators between small levels hold
+// tens of blocks: the thread-per-scalar kernel above walks them one dependent gather after the other)
+__global__ void __launch_bounds__(kT) k_ml_smooth_prolong_warp(int64_t n, const float *__restrict__ dinv,
+                                                               const int32_t *__restrict__ prow, const int32_t *__restrict__ pcol,
+                                                               const float *__restrict__ pval, const double *__restrict__ r,
+                                                               const double *__restrict__ zc, double *__restrict__ z, int64_t row0)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;   // whole warps leave together
+    const int64_t v = w + row0;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int32_t b = __ldg(prow + v) + lane; b < __ldg(prow + v + 1); b += 32) {
+        const float4 *P = reinterpret_cast<const float4 *>(pval + (int64_t)b * 36);
+        const double *c = zc + (int64_t)__ldg(pcol + b) * 6;
+        float pp[36];
+#pragma unroll
+        for (int x = 0; x < 9; ++x) { const float4 f = __ldg(P + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
+        const double cc[6] = {c[0], c[1], c[2], c[3], c[4], c[5]};
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[i] = fma((double)pp[6 * i + j], cc[j], acc[i]);
+    }
+    if (lane < 6) {   // D^-1 r: lane i adds row i
+        const float2 *D = reinterpret_cast<const float2 *>(dinv + v * 36 + 6 * lane);
+        const double *rv = r + v * 6;
+        const float2 d0 = __ldg(D), d1 = __ldg(D + 1), d2 = __ldg(D + 2);
+        double s = (double)d0.x * rv[0];
+        s = fma((double)d0.y, rv[1], s); s = fma((double)d1.x, rv[2], s); s = fma((double)d1.y, rv[3], s);
+        s = fma((double)d2.x, rv[4], s); s = fma((double)d2.y, rv[5], s);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (i == lane) acc[i] += s;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) z[v * 6 + i] = acc[i];
+}
+
 // the same for a TENTATIVE P: z_i = D_i^-1 r_i + B(off_i) zc[agg i]
 __global__ void __launch_bounds__(kT) k_ml_smooth_prolong_tent(int64_t n, const float *__restrict__ dinv,
                                                                const int32_t *__restrict__ agg, const double *__restrict__ off,
                                                                const double *__restrict__ r, const double *__restrict__ zc,
-                                                               double *__restrict__ z)
+                                                               double *__restrict__ z, int64_t row0)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t v = t / 6;
-    if (v >= n) return;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 / 6 >= n) return;
+    const int64_t t = t0 + 6 * row0, v = t / 6;   // rows [row0, row0 + n)
     const int i = (int)(t - v * 6);
     const float2 *D = reinterpret_cast<const float2 *>(dinv + v * 36 + 6 * i);
     const double *rv = r + v * 6;
@@ -575,7 +673,7 @@ void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, double *colk, in
     if (n <= 0) return;
     const unsigned grid = blocks_for((int64_t)n * n, 256);
     for (int k = 0; k < n / 6; ++k) {
-        k_ml_gj_pivot<<<1, 256, 0, st>>>(n, k, a, colk, flag);
+        k_ml_gj_pivot<<<1, 1024, 0, st>>>(n, k, a, colk, flag);
         k_ml_gj_update<<<grid, 256, 0, st>>>(n, k, a, colk);
     }
 }
@@ -598,25 +696,34 @@ void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_
     if (group == 8) k_ml_restrict0<8><<<blocks_for(n_agg * 8), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
     else k_ml_restrict0<32><<<blocks_for(n_agg * 32), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
 }
-void launch_ml_restrict(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
-                        const float *pval, const double *r, double *rc)
+void launch_ml_restrict(cudaStream_t st, int64_t nc, int64_t nnzp, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
+                        const float *pval, const double *r, double *rc, int64_t fine_lo, int64_t fine_hi)
 {
-    if (nc > 0) k_ml_restrict<<<blocks_for(nc * 32), kT, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc);
+    if (nc <= 0) return;
+    if (nnzp > 48 * nc && nc <= 65535)   // long rows on a small level
+        k_ml_restrict_wide<<<(unsigned)nc, 128, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, (int32_t)fine_lo, (int32_t)fine_hi);
+    else
+        k_ml_restrict<<<blocks_for(nc * 32), kT, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, (int32_t)fine_lo, (int32_t)fine_hi);
 }
 void launch_ml_restrict_tent(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rfine, const double *off,
-                             const double *r, double *rc)
+                             const double *r, double *rc, int64_t fine_lo, int64_t fine_hi)
 {
-    if (nc > 0) k_ml_restrict_tent<<<blocks_for(nc * 8), kT, 0, st>>>(nc, rrow, rfine, off, r, rc);
+    if (nc > 0) k_ml_restrict_tent<<<blocks_for(nc * 8), kT, 0, st>>>(nc, rrow, rfine, off, r, rc, (int32_t)fine_lo, (int32_t)fine_hi);
 }
-void launch_ml_smooth_prolong(cudaStream_t st, int64_t n, const float *dinv, const int32_t *prow, const int32_t *pcol,
-                              const float *pval, const double *r, const double *zc, double *z)
+void launch_ml_smooth_prolong(cudaStream_t st, int64_t row0, int64_t n, int64_t n_level, int64_t nnzp, const float *dinv,
+                              const int32_t *prow, const int32_t *pcol, const float *pval, const double *r, const double *zc,
+                              double *z)
 {
-    if (n > 0) k_ml_smooth_prolong<<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z);
+    if (n <= 0) return;
+    if (nnzp > 6 * n_level)   // rows of many blocks: a warp per row
+        k_ml_smooth_prolong_warp<<<blocks_for(n * 32), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
+    else
+        k_ml_smooth_prolong<<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
 }
-void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t n, const float *dinv, const int32_t *agg, const double *off,
+void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t row0, int64_t n, const float *dinv, const int32_t *agg, const double *off,
                                    const double *r, const double *zc, double *z)
 {
-    if (n > 0) k_ml_smooth_prolong_tent<<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, agg, off, r, zc, z);
+    if (n > 0) k_ml_smooth_prolong_tent<<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, agg, off, r, zc, z, row0);
 }
 
 }}  // namespace mbfea::dev

@@ -243,20 +243,28 @@ void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, 
     const size_t L = lv.size();
     launch_ml_restrict0(st, agg_begin[(size_t)rank + 1] - agg_begin[(size_t)rank], group0, agg_ptr0.p, agg_rows0.p, t0.p, rt,
                         lv[0]->r.p + 6 * agg_begin[(size_t)rank]);
-    if (world > 1) exchange_slices(st, lv[0]->r.p, agg_begin, 6);
+    // several ranks: level 1 stays DISTRIBUTED in the apply -- every rank restricts its own level-1 rows to level 2 (partial
+    // sums, all-reduced: 48 B per level-2 row) and prolongs back onto its own level-1 rows only, which is all the fine
+    // prolongation needs; levels >= 2 are replicated.  With a single coarse level the dense solve needs all of r1.
+    const bool split1 = world > 1 && L >= 2;
+    if (world > 1 && !split1) exchange_slices(st, lv[0]->r.p, agg_begin, 6);
     for (size_t m = 0; m + 1 < L; ++m) {
+        const int64_t lo = (m == 0 && split1) ? agg_begin[(size_t)rank] : 0, hi = (m == 0 && split1) ? agg_begin[(size_t)rank + 1] : lv[m]->n;
         if (lv[m]->smoothed)
-            launch_ml_restrict(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->pval32.p, lv[m]->r.p, lv[m + 1]->r.p);
+            launch_ml_restrict(st, lv[m + 1]->n, lv[m]->nnzp, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->pval32.p, lv[m]->r.p, lv[m + 1]->r.p, lo, hi);
         else
-            launch_ml_restrict_tent(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rfine.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->r.p);
+            launch_ml_restrict_tent(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rfine.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->r.p, lo, hi);
+        if (m == 0 && split1) NK(nc->AllReduce(lv[1]->r.p, lv[1]->r.p, (size_t)(6 * lv[1]->n), nccl::kFloat64, nccl::kSum, comm, st));
     }
     launch_ml_dense_matvec(st, (int)n_dense, dense32.p, lv[L - 1]->r.p, lv[L - 1]->z.p);
     for (size_t m = L - 1; m-- > 0;) {
+        const int64_t row0 = (m == 0 && split1) ? agg_begin[(size_t)rank] : 0;
+        const int64_t cnt = (m == 0 && split1) ? agg_begin[(size_t)rank + 1] - row0 : lv[m]->n;
         if (lv[m]->smoothed)
-            launch_ml_smooth_prolong(st, lv[m]->n, lv[m]->dinv32.p, lv[m]->prow.p, lv[m]->pcol.p, lv[m]->pval32.p, lv[m]->r.p,
+            launch_ml_smooth_prolong(st, row0, cnt, lv[m]->n, lv[m]->nnzp, lv[m]->dinv32.p, lv[m]->prow.p, lv[m]->pcol.p, lv[m]->pval32.p, lv[m]->r.p,
                                      lv[m + 1]->z.p, lv[m]->z.p);
         else
-            launch_ml_smooth_prolong_tent(st, lv[m]->n, lv[m]->dinv32.p, lv[m]->agg.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->z.p,
+            launch_ml_smooth_prolong_tent(st, row0, cnt, lv[m]->dinv32.p, lv[m]->agg.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->z.p,
                                           lv[m]->z.p);
     }
     launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part, sc, pc);
