@@ -14,6 +14,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "devbuf.hpp"
@@ -785,6 +786,28 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         c->ml.reset();
         const bool ml_possible = !batched && c->plan.nb_global >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
         const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
+        // The host half of the multilevel hierarchy needs only the block pattern and the vertex positions: it runs on its own
+        // thread while this one builds the solver format and uploads the mesh and the plan.  (Several ranks: rank 0 builds it
+        // for everybody -- the ranks of a box share the host cores, W redundant builds would each get 1 / W of them.)
+        struct MlHostJob {
+            std::vector<double> pos;
+            double mean_len = 0.0;
+            MlHierarchy H;
+            std::vector<unsigned char> img;   // several ranks, rank 0: flat image for the broadcast
+            bool failed = false;
+            double ms = 0.0;
+        } mlh;
+        std::thread ml_thread;
+        const bool ml_build_here = ml_possible && ml_wanted && (c->opt.world == 1 || c->opt.rank == 0);
+        if (ml_possible && ml_wanted) {
+            MlParams mp;
+            if (c->opt.ml_cell > 0.0) mp.cell = c->opt.ml_cell;
+            if (c->opt.ml_ratio > 1.0) mp.ratio = c->opt.ml_ratio;
+            if (c->opt.ml_coarsest_rows > 0) mp.coarsest_rows = std::min<int64_t>(c->opt.ml_coarsest_rows, 512);
+            if (c->opt.ml_smooth_from > 0) mp.smooth_from = c->opt.ml_smooth_from;
+            c->ml.par = mp;
+        }
+        struct JoinGuard { std::thread &t; ~JoinGuard() { if (t.joinable()) t.join(); } } ml_join{ml_thread};
         build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
         build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
         c->tma_ok = true;
@@ -803,6 +826,62 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             tl = n;
         };
 
+        // (started after the host prep: both allocate and first-touch hundreds of MB, and concurrent page faults from two
+        // thread pools serialise on the process' mmap lock -- measured 300 ms of stall; the device uploads below do not)
+        if (ml_build_here) {
+            ml_thread = std::thread([&, V, E, F]() {
+                try {
+                    const double tw = now_ms();
+                    const int64_t nbg = c->plan.nb_global;
+                    const int W = c->opt.world;
+                    // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
+                    // mean beam length: the aggregates are bricks of a few beam lengths
+                    mlh.pos.resize((size_t)3 * nbg);
+                    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, E >> 16));
+                    std::vector<double> part((size_t)nt, 0.0);
+                    std::vector<std::thread> th;
+                    for (int t = 0; t < nt; ++t)
+                        th.emplace_back([&, t]() {
+                            for (int64_t v = V * t / nt; v < V * (t + 1) / nt; ++v) {
+                                const int32_t r = c->plan.free_index[(size_t)v];
+                                if (r >= 0) for (int a = 0; a < 3; ++a) mlh.pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
+                            }
+                            double len = 0.0;   // fixed chunks, summed in chunk order below: reproducible
+                            for (int64_t e = E * t / nt; e < E * (t + 1) / nt; ++e) {
+                                double d2 = 0.0;
+                                for (int a = 0; a < 3; ++a) {
+                                    const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                                    d2 += d * d;
+                                }
+                                len += std::sqrt(d2);
+                            }
+                            part[(size_t)t] = len;
+                        });
+                    for (auto &x : th) x.join();
+                    double len = 0.0;
+                    for (int t = 0; t < nt; ++t) len += part[(size_t)t];
+                    mlh.mean_len = len / (double)E;
+                    if (W == 1) {
+                        c->ml.build_hierarchy_host(nbg, c->plan.rowptr.data(), c->plan.colidx.data(), mlh.pos.data(), mlh.mean_len, 1, mlh.H);
+                    } else {
+                        HostPlan G;
+                        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
+                        c->ml.build_hierarchy_host(nbg, G.rowptr.data(), G.colidx.data(), mlh.pos.data(), mlh.mean_len, W, mlh.H);
+                        std::vector<unsigned char> body;
+                        ml_hierarchy_pack(mlh.H, body);
+                        const size_t head = (size_t)(W + 2) * sizeof(int64_t);
+                        mlh.img.resize(head + ((body.size() + 7) & ~(size_t)7));
+                        int64_t *hd = reinterpret_cast<int64_t *>(mlh.img.data());
+                        for (int q = 0; q <= W; ++q) hd[q] = G.rowptr[(size_t)(nbg * q / W)];   // first block of every rank's rows
+                        hd[W + 1] = (int64_t)body.size();
+                        std::memcpy(mlh.img.data() + head, body.data(), body.size());
+                    }
+                    mlh.ms = now_ms() - tw;
+                } catch (...) {
+                    mlh.failed = true;
+                }
+            });
+        }
         const int64_t nb = c->nb(), ng = c->ng(), nnzb = c->plan.nnzb();
         // mesh -> device, repacked into aligned records
         {
@@ -880,44 +959,55 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         CK(cudaStreamSynchronize(c->st));
         lap("load vector");
         if (ml_possible && ml_wanted) {
-            // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
-            // mean beam length: the aggregates are bricks of a few beam lengths
+            const double tw = now_ms();
             const int64_t nbg = c->plan.nb_global;
-            std::vector<double> pos((size_t)3 * nbg);
-            for (int64_t v = 0; v < V; ++v) {
-                const int32_t r = c->plan.free_index[(size_t)v];
-                if (r >= 0) for (int a = 0; a < 3; ++a) pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
-            }
-            double len = 0.0;
-            for (int64_t e = 0; e < E; ++e) {
-                double d2 = 0.0;
-                for (int a = 0; a < 3; ++a) {
-                    const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
-                    d2 += d * d;
-                }
-                len += std::sqrt(d2);
-            }
-            MlParams mp;
-            if (c->opt.ml_cell > 0.0) mp.cell = c->opt.ml_cell;
-            if (c->opt.ml_ratio > 1.0) mp.ratio = c->opt.ml_ratio;
-            if (c->opt.ml_coarsest_rows > 0) mp.coarsest_rows = std::min<int64_t>(c->opt.ml_coarsest_rows, 512);
-            if (c->opt.ml_smooth_from > 0) mp.smooth_from = c->opt.ml_smooth_from;
-            c->ml.par = mp;
+            if (ml_thread.joinable()) ml_thread.join();
             if (c->opt.world == 1) {
-                c->use_ml = c->ml.build_symbolic(c->st, nb, c->plan.rowptr.data(), c->plan.colidx.data(), pos.data(), len / (double)E);
+                c->use_ml = !mlh.failed && c->ml.upload_hierarchy(c->st, mlh.H, nbg, (int64_t)c->plan.rowptr[(size_t)nb], 0, nullptr);
             } else {
-                // several ranks: the hierarchy is built on the GLOBAL pattern (every rank holds the whole mesh anyway), with
-                // aggregates that never straddle a rank; only the rank's own share of level 0 goes to its device
-                HostPlan G;
-                build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
-                MlDist dist;
-                dist.rank = c->opt.rank; dist.world = c->opt.world;
-                dist.row_begin = c->plan.row_begin; dist.row_end = c->plan.row_end;
-                dist.ghost_global = &c->plan.ghost_global;
-                dist.loc_rowptr = c->plan.rowptr.data(); dist.loc_colidx = c->plan.colidx.data();
-                dist.nc = c->nc; dist.comm = c->comm;
-                c->use_ml = c->ml.build_symbolic(c->st, nbg, G.rowptr.data(), G.colidx.data(), pos.data(), len / (double)E, &dist);
+                // rank 0's flat image goes through the GPUs to everybody; each rank then uploads its own share of level 0 and
+                // the replicated coarse levels
+                const int W = c->opt.world;
+                std::vector<unsigned char> &img = mlh.img;
+                const size_t head = (size_t)(W + 2) * sizeof(int64_t);
+                int64_t bytes = mlh.failed ? 0 : (int64_t)img.size();
+                std::vector<int64_t> all((size_t)W);
+                allgather_host(c, &bytes, all.data(), sizeof bytes);
+                bytes = all[0];
+                if (bytes > 0) {
+                    DevBuf<unsigned char> dimg;
+                    CK(dimg.alloc((size_t)bytes));
+                    if (c->opt.rank == 0) CK(cudaMemcpyAsync(dimg.p, img.data(), (size_t)bytes, cudaMemcpyHostToDevice, c->st));
+                    NK(c->nc->Broadcast(dimg.p, dimg.p, (size_t)bytes / 8, nccl::kInt64, 0, c->comm, c->st));
+                    MlHierarchy Hrecv;
+                    const MlHierarchy *H = &mlh.H;
+                    if (c->opt.rank != 0) {
+                        img.resize((size_t)bytes);
+                        CK(cudaMemcpyAsync(img.data(), dimg.p, (size_t)bytes, cudaMemcpyDeviceToHost, c->st));
+                    }
+                    CK(cudaStreamSynchronize(c->st));
+                    const int64_t *hd = reinterpret_cast<const int64_t *>(img.data());
+                    if (c->opt.rank != 0) {
+                        if (!ml_hierarchy_unpack(img.data() + head, (size_t)hd[W + 1], Hrecv))
+                            return fail(c, MBFEA_ECUDA, "multilevel hierarchy: malformed image from rank 0");
+                        H = &Hrecv;
+                    }
+                    MlDist dist;
+                    dist.rank = c->opt.rank; dist.world = W;
+                    dist.row_begin = c->plan.row_begin; dist.row_end = c->plan.row_end;
+                    dist.ghost_global = &c->plan.ghost_global;
+                    dist.loc_rowptr = c->plan.rowptr.data(); dist.loc_colidx = c->plan.colidx.data();
+                    dist.nc = c->nc; dist.comm = c->comm;
+                    if (hd[c->opt.rank + 1] - hd[c->opt.rank] != (int64_t)c->plan.rowptr[(size_t)nb])
+                        return fail(c, MBFEA_ECUDA, "multilevel hierarchy: the global and the rank's block patterns disagree");
+                    c->use_ml = c->ml.upload_hierarchy(c->st, *H, nbg, hd[W], hd[c->opt.rank], &dist);
+                }
+                // every rank must take the same path
+                int64_t ok = c->use_ml ? 1 : 0;
+                allgather_host(c, &ok, all.data(), sizeof ok);
+                for (int q = 0; q < W; ++q) if (!all[(size_t)q]) c->use_ml = false;
             }
+            c->ml.ms_symbolic = mlh.ms + (now_ms() - tw);
             if (!c->use_ml && c->opt.precond == 2 && c->opt.verbose)
                 std::fprintf(stderr, "[mbfea] multilevel preconditioner requested but the mesh does not coarsen: block-Jacobi\n");
             c->stats.ms_ml_symbolic = c->ml.ms_symbolic;

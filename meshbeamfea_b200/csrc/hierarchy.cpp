@@ -302,6 +302,78 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
     }
 }
 
+// ---- flat image of a hierarchy (several ranks: rank 0 builds it with every host core, the others receive it) ----
+namespace {
+template <class T>
+void put_vec(std::vector<unsigned char> &out, const std::vector<T> &v)
+{
+    const uint64_t n = v.size();
+    const size_t at = out.size();
+    out.resize(at + sizeof n + n * sizeof(T));
+    std::memcpy(out.data() + at, &n, sizeof n);
+    if (n) std::memcpy(out.data() + at + sizeof n, v.data(), n * sizeof(T));
+}
+template <class T>
+bool get_vec(const unsigned char *&p, const unsigned char *end, std::vector<T> &v)
+{
+    uint64_t n = 0;
+    if ((size_t)(end - p) < sizeof n) return false;
+    std::memcpy(&n, p, sizeof n); p += sizeof n;
+    if ((uint64_t)(end - p) < n * sizeof(T)) return false;
+    v.resize((size_t)n);
+    if (n) std::memcpy(v.data(), p, (size_t)n * sizeof(T));
+    p += n * sizeof(T);
+    return true;
+}
+}  // namespace
+
+void ml_hierarchy_pack(const MlHierarchy &H, std::vector<unsigned char> &out)
+{
+    out.clear();
+    const uint64_t L = H.levels();
+    out.resize(sizeof L);
+    std::memcpy(out.data(), &L, sizeof L);
+    for (size_t l = 0; l < L; ++l) {
+        const HierLevel &a = H.agg[l];
+        const MlTransfer &t = H.xfer[l];
+        const int64_t head[6] = {a.n_fine, a.n_coarse, t.n_fine, t.n_coarse, t.smoothed ? 1 : 0, 0};
+        const size_t at = out.size();
+        out.resize(at + sizeof head);
+        std::memcpy(out.data() + at, head, sizeof head);
+        put_vec(out, a.agg); put_vec(out, a.off); put_vec(out, a.agg_ptr); put_vec(out, a.agg_rows);
+        put_vec(out, a.rowptr); put_vec(out, a.colidx); put_vec(out, a.gal_ptr); put_vec(out, a.gal_src);
+        put_vec(out, t.prow); put_vec(out, t.pcol); put_vec(out, t.pown); put_vec(out, t.rrow); put_vec(out, t.rblk);
+        put_vec(out, t.rfine); put_vec(out, t.aprow); put_vec(out, t.apcol); put_vec(out, t.crow); put_vec(out, t.ccol);
+        put_vec(out, t.cdiag);
+    }
+}
+
+bool ml_hierarchy_unpack(const unsigned char *data, size_t bytes, MlHierarchy &H)
+{
+    H.agg.clear(); H.xfer.clear();
+    const unsigned char *p = data, *end = data + bytes;
+    uint64_t L = 0;
+    if (bytes < sizeof L) return false;
+    std::memcpy(&L, p, sizeof L); p += sizeof L;
+    if (L > 64) return false;
+    H.agg.resize((size_t)L); H.xfer.resize((size_t)L);
+    for (size_t l = 0; l < L; ++l) {
+        HierLevel &a = H.agg[l];
+        MlTransfer &t = H.xfer[l];
+        int64_t head[6];
+        if ((size_t)(end - p) < sizeof head) return false;
+        std::memcpy(head, p, sizeof head); p += sizeof head;
+        a.n_fine = head[0]; a.n_coarse = head[1]; t.n_fine = head[2]; t.n_coarse = head[3]; t.smoothed = head[4] != 0;
+        if (!(get_vec(p, end, a.agg) && get_vec(p, end, a.off) && get_vec(p, end, a.agg_ptr) && get_vec(p, end, a.agg_rows) &&
+              get_vec(p, end, a.rowptr) && get_vec(p, end, a.colidx) && get_vec(p, end, a.gal_ptr) && get_vec(p, end, a.gal_src) &&
+              get_vec(p, end, t.prow) && get_vec(p, end, t.pcol) && get_vec(p, end, t.pown) && get_vec(p, end, t.rrow) &&
+              get_vec(p, end, t.rblk) && get_vec(p, end, t.rfine) && get_vec(p, end, t.aprow) && get_vec(p, end, t.apcol) &&
+              get_vec(p, end, t.crow) && get_vec(p, end, t.ccol) && get_vec(p, end, t.cdiag)))
+            return false;
+    }
+    return p == end;
+}
+
 void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
                      double ratio, int max_levels, int64_t coarsest_rows, Hierarchy &H)
 {

@@ -155,6 +155,11 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
                         double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H,
                         const int64_t *part_bounds = nullptr, int nparts = 1);
 
+// flat byte image of a hierarchy and back (several ranks: one rank builds, the others receive); unpack returns false on a
+// malformed image
+void ml_hierarchy_pack(const MlHierarchy &H, std::vector<unsigned char> &out);
+bool ml_hierarchy_unpack(const unsigned char *data, size_t bytes, MlHierarchy &H);
+
 // Explicit inverse of a dense SPD matrix (row-major n x n) for the coarsest level; 0, or 1 + the index of
 // the first non-positive pivot (dense.cpp).
 int dense_spd_inverse(int64_t n, const double *A, double *Ainv);

@@ -64,6 +64,13 @@ public:
     // dist != null: (h_rowptr, h_colidx, pos_rm) describe the GLOBAL reduced system (nb = global rows), dist the rank's share.
     bool build_symbolic(cudaStream_t st, int64_t nb, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
                         double mean_beam_length, const MlDist *dist = nullptr);
+    // the host half alone (what rank 0 runs for everybody on several ranks) ...
+    void build_hierarchy_host(int64_t nb, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
+                              double mean_beam_length, int world, MlHierarchy &H) const;
+    // ... and the device half from a prebuilt hierarchy: fine_nnz = blocks of the (global) fine pattern, own_first_block =
+    // index of the first block of the rank's first row in it (0 on one rank)
+    bool upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nb_global, int64_t fine_nnz, int64_t own_first_block,
+                          const MlDist *dist);
     // Galerkin matrices, smoothers, prolongators, coarsest inverse from the assembled K (full pattern, unscaled) and
     // the Cholesky factors of its diagonal blocks.  *d_flag |= 1/2 on a non-SPD coarse block / coarsest pivot.
     void build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_vals,

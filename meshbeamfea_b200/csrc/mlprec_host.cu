@@ -35,20 +35,37 @@ void MlPrec::reset()
     nb = 0;
 }
 
+void MlPrec::build_hierarchy_host(int64_t nbg, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
+                                  double mean_len, int world_, MlHierarchy &H) const
+{
+    std::vector<int64_t> bounds((size_t)world_ + 1);
+    for (int q = 0; q <= world_; ++q) bounds[(size_t)q] = nbg * q / world_;
+    build_ml_hierarchy(nbg, h_rowptr, h_colidx, pos_rm, par.cell * mean_len, par.ratio, par.max_levels, par.coarsest_rows,
+                       std::max(1, par.smooth_from), H, world_ > 1 ? bounds.data() : nullptr, world_);
+}
+
 bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
                             double mean_len, const MlDist *dist)
 {
+    if (nb_ <= 0 || !(mean_len > 0.0)) { reset(); return false; }
+    const double t0w = wall_ms();
+    MlHierarchy H;
+    build_hierarchy_host(nb_, h_rowptr, h_colidx, pos_rm, mean_len, dist ? dist->world : 1, H);
+    const bool ok = upload_hierarchy(st, H, nb_, h_rowptr[nb_], dist ? h_rowptr[dist->row_begin] : 0, dist);
+    ms_symbolic = wall_ms() - t0w;
+    return ok;
+}
+
+bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg, int64_t fine_nnz, int64_t own_first_block,
+                              const MlDist *dist)
+{
     const double t0w = wall_ms();
     reset();
-    if (nb_ <= 0 || !(mean_len > 0.0)) return false;
+    if (nbg <= 0) return false;
     rank = dist ? dist->rank : 0; world = dist ? dist->world : 1;
     nc = dist ? dist->nc : nullptr; comm = dist ? dist->comm : nullptr;
-    const int64_t nbg = nb_;   // rows of the (global) system the hierarchy is built on
     std::vector<int64_t> bounds((size_t)world + 1);
     for (int q = 0; q <= world; ++q) bounds[(size_t)q] = nbg * q / world;
-    MlHierarchy H;
-    build_ml_hierarchy(nbg, h_rowptr, h_colidx, pos_rm, par.cell * mean_len, par.ratio, par.max_levels, par.coarsest_rows,
-                       std::max(1, par.smooth_from), H, world > 1 ? bounds.data() : nullptr, world);
     const size_t L = H.levels();
     if (L == 0) return false;
     if (6 * H.agg[L - 1].n_coarse > 3072) return false;   // the chain stopped early (max_levels): no dense inverse that large
@@ -68,7 +85,7 @@ bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowpt
         nb = nbg;
         up(st, agg0, h0.agg); up(st, agg_ptr0, h0.agg_ptr); up(st, agg_rows0, h0.agg_rows);
         up(st, gal_ptr0, h0.gal_ptr); up(st, gal_src0, h0.gal_src); up(st, off0, h0.off);
-        CK(frow0.alloc((size_t)h_rowptr[nbg]));
+        CK(frow0.alloc((size_t)fine_nnz));
     } else {
         // the rank's share of level 0: own rows (local ids), own aggregates, own rows of the level-1 matrix
         const int64_t r0 = dist->row_begin, nbl = dist->row_end - dist->row_begin;
@@ -95,8 +112,7 @@ bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowpt
         gs.reserve((size_t)(h0.gal_ptr[(size_t)b1] - h0.gal_ptr[(size_t)b0]));
         // the rank's local pattern keeps the blocks of a row in GLOBAL column order (build_plan only renames the column
         // ids), so the local index of global fine block k of an own row is k - (first block of the first own row)
-        const int32_t k_lo = h_rowptr[r0];
-        if (h_rowptr[r0 + nbl] - k_lo != dist->loc_rowptr[nbl]) return false;   // the two plans disagree: stay with block-Jacobi
+        const int32_t k_lo = (int32_t)own_first_block;
         for (int64_t k = b0; k < b1; ++k) {
             gp[(size_t)(k - b0)] = (int32_t)gs.size();
             for (int32_t s2 = h0.gal_ptr[(size_t)k]; s2 < h0.gal_ptr[(size_t)k + 1]; ++s2) gs.push_back(h0.gal_src[(size_t)s2] - k_lo);
