@@ -867,14 +867,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                         HostPlan G;
                         build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
                         c->ml.build_hierarchy_host(nbg, G.rowptr.data(), G.colidx.data(), mlh.pos.data(), mlh.mean_len, W, mlh.H);
-                        std::vector<unsigned char> body;
-                        ml_hierarchy_pack(mlh.H, body);
-                        const size_t head = (size_t)(W + 2) * sizeof(int64_t);
-                        mlh.img.resize(head + ((body.size() + 7) & ~(size_t)7));
-                        int64_t *hd = reinterpret_cast<int64_t *>(mlh.img.data());
-                        for (int q = 0; q <= W; ++q) hd[q] = G.rowptr[(size_t)(nbg * q / W)];   // first block of every rank's rows
-                        hd[W + 1] = (int64_t)body.size();
-                        std::memcpy(mlh.img.data() + head, body.data(), body.size());
+                        if (!ml_image_pack(mlh.H, W, nbg, G.rowptr.data(), mlh.img)) mlh.failed = true;
                     }
                     mlh.ms = now_ms() - tw;
                 } catch (...) {
@@ -968,39 +961,28 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                 // rank 0's flat image goes through the GPUs to everybody; each rank then uploads its own share of level 0 and
                 // the replicated coarse levels
                 const int W = c->opt.world;
-                std::vector<unsigned char> &img = mlh.img;
-                const size_t head = (size_t)(W + 2) * sizeof(int64_t);
-                int64_t bytes = mlh.failed ? 0 : (int64_t)img.size();
+                int64_t bytes = mlh.failed ? 0 : (int64_t)mlh.img.size();
                 std::vector<int64_t> all((size_t)W);
                 allgather_host(c, &bytes, all.data(), sizeof bytes);
                 bytes = all[0];
                 if (bytes > 0) {
                     DevBuf<unsigned char> dimg;
                     CK(dimg.alloc((size_t)bytes));
-                    if (c->opt.rank == 0) CK(cudaMemcpyAsync(dimg.p, img.data(), (size_t)bytes, cudaMemcpyHostToDevice, c->st));
+                    if (c->opt.rank == 0) CK(cudaMemcpyAsync(dimg.p, mlh.img.data(), (size_t)bytes, cudaMemcpyHostToDevice, c->st));
                     NK(c->nc->Broadcast(dimg.p, dimg.p, (size_t)bytes / 8, nccl::kInt64, 0, c->comm, c->st));
-                    MlHierarchy Hrecv;
-                    const MlHierarchy *H = &mlh.H;
-                    if (c->opt.rank != 0) {
-                        img.resize((size_t)bytes);
-                        CK(cudaMemcpyAsync(img.data(), dimg.p, (size_t)bytes, cudaMemcpyDeviceToHost, c->st));
-                    }
+                    MlImageHeader hd;
+                    CK(cudaMemcpyAsync(&hd, dimg.p, sizeof hd, cudaMemcpyDeviceToHost, c->st));
                     CK(cudaStreamSynchronize(c->st));
-                    const int64_t *hd = reinterpret_cast<const int64_t *>(img.data());
-                    if (c->opt.rank != 0) {
-                        if (!ml_hierarchy_unpack(img.data() + head, (size_t)hd[W + 1], Hrecv))
-                            return fail(c, MBFEA_ECUDA, "multilevel hierarchy: malformed image from rank 0");
-                        H = &Hrecv;
-                    }
                     MlDist dist;
                     dist.rank = c->opt.rank; dist.world = W;
                     dist.row_begin = c->plan.row_begin; dist.row_end = c->plan.row_end;
                     dist.ghost_global = &c->plan.ghost_global;
                     dist.loc_rowptr = c->plan.rowptr.data(); dist.loc_colidx = c->plan.colidx.data();
                     dist.nc = c->nc; dist.comm = c->comm;
-                    if (hd[c->opt.rank + 1] - hd[c->opt.rank] != (int64_t)c->plan.rowptr[(size_t)nb])
-                        return fail(c, MBFEA_ECUDA, "multilevel hierarchy: the global and the rank's block patterns disagree");
-                    c->use_ml = c->ml.upload_hierarchy(c->st, *H, nbg, hd[W], hd[c->opt.rank], &dist);
+                    if (hd.magic != kMlImageMagic || hd.world != W ||
+                        hd.own_first[c->opt.rank + 1] - hd.own_first[c->opt.rank] != (int64_t)c->plan.rowptr[(size_t)nb])
+                        return fail(c, MBFEA_ECUDA, "multilevel hierarchy: the image of rank 0 does not match this rank's block pattern");
+                    c->use_ml = c->ml.upload_from_image(c->st, dimg.p, hd, dist);
                 }
                 // every rank must take the same path
                 int64_t ok = c->use_ml ? 1 : 0;

@@ -303,75 +303,67 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
 }
 
 // ---- flat image of a hierarchy (several ranks: rank 0 builds it with every host core, the others receive it) ----
-namespace {
-template <class T>
-void put_vec(std::vector<unsigned char> &out, const std::vector<T> &v)
+bool ml_image_pack(const MlHierarchy &H, int world, int64_t nbg, const int32_t *fine_rowptr, std::vector<unsigned char> &out)
 {
-    const uint64_t n = v.size();
-    const size_t at = out.size();
-    out.resize(at + sizeof n + n * sizeof(T));
-    std::memcpy(out.data() + at, &n, sizeof n);
-    if (n) std::memcpy(out.data() + at + sizeof n, v.data(), n * sizeof(T));
-}
-template <class T>
-bool get_vec(const unsigned char *&p, const unsigned char *end, std::vector<T> &v)
-{
-    uint64_t n = 0;
-    if ((size_t)(end - p) < sizeof n) return false;
-    std::memcpy(&n, p, sizeof n); p += sizeof n;
-    if ((uint64_t)(end - p) < n * sizeof(T)) return false;
-    v.resize((size_t)n);
-    if (n) std::memcpy(v.data(), p, (size_t)n * sizeof(T));
-    p += n * sizeof(T);
-    return true;
-}
-}  // namespace
-
-void ml_hierarchy_pack(const MlHierarchy &H, std::vector<unsigned char> &out)
-{
-    out.clear();
-    const uint64_t L = H.levels();
-    out.resize(sizeof L);
-    std::memcpy(out.data(), &L, sizeof L);
-    for (size_t l = 0; l < L; ++l) {
+    const size_t L = H.levels();
+    if (L == 0 || L > (size_t)kMlImageMaxLevels || world < 1 || world > kMlImageMaxWorld) return false;
+    MlImageHeader hd;
+    std::memset(&hd, 0, sizeof hd);
+    hd.magic = kMlImageMagic; hd.levels = (int64_t)L; hd.world = world; hd.nbg = nbg; hd.fine_nnz = fine_rowptr[nbg];
+    const HierLevel &h0 = H.agg[0];
+    int32_t biggest = 0;
+    for (int64_t I = 0; I < h0.n_coarse; ++I) biggest = std::max(biggest, h0.agg_ptr[(size_t)I + 1] - h0.agg_ptr[(size_t)I]);
+    hd.group0 = biggest <= 8 ? 8 : 32;
+    for (int q = 0; q < world; ++q) {   // aggregates are numbered rank-major
+        const int64_t lo = nbg * q / world, hi = nbg * (q + 1) / world;
+        int32_t top = -1;
+        for (int64_t v = lo; v < hi; ++v) top = std::max(top, h0.agg[(size_t)v]);
+        hd.agg_begin[q + 1] = std::max<int64_t>(hd.agg_begin[q], (int64_t)top + 1);
+    }
+    for (int q = 0; q <= world; ++q) {
+        hd.own_first[q] = fine_rowptr[nbg * q / world];
+        hd.blk_begin[q] = h0.rowptr[(size_t)hd.agg_begin[q]];
+        hd.aggptr_at[q] = h0.agg_ptr[(size_t)hd.agg_begin[q]];
+        hd.galptr_at[q] = h0.gal_ptr[(size_t)hd.blk_begin[q]];
+    }
+    // diagonal positions of the level-1 pattern
+    std::vector<int32_t> diag1((size_t)h0.n_coarse);
+    for (int64_t I = 0; I < h0.n_coarse; ++I)
+        diag1[(size_t)I] = (int32_t)(std::lower_bound(h0.colidx.begin() + h0.rowptr[(size_t)I], h0.colidx.begin() + h0.rowptr[(size_t)I + 1],
+                                                      (int32_t)I) - h0.colidx.begin());
+    struct Src { const void *p; size_t bytes; int64_t cnt; };
+    std::vector<std::vector<Src>> src(L);
+    auto vi = [](const std::vector<int32_t> &v) { return Src{v.data(), v.size() * sizeof(int32_t), (int64_t)v.size()}; };
+    auto vd = [](const std::vector<double> &v) { return Src{v.data(), v.size() * sizeof(double), (int64_t)v.size()}; };
+    src[0] = {vi(h0.agg), vd(h0.off), vi(h0.agg_ptr), vi(h0.agg_rows), vi(h0.rowptr), vi(h0.colidx), vi(diag1), vi(h0.gal_ptr), vi(h0.gal_src)};
+    for (size_t l = 1; l < L; ++l) {
         const HierLevel &a = H.agg[l];
         const MlTransfer &t = H.xfer[l];
-        const int64_t head[6] = {a.n_fine, a.n_coarse, t.n_fine, t.n_coarse, t.smoothed ? 1 : 0, 0};
-        const size_t at = out.size();
-        out.resize(at + sizeof head);
-        std::memcpy(out.data() + at, head, sizeof head);
-        put_vec(out, a.agg); put_vec(out, a.off); put_vec(out, a.agg_ptr); put_vec(out, a.agg_rows);
-        put_vec(out, a.rowptr); put_vec(out, a.colidx); put_vec(out, a.gal_ptr); put_vec(out, a.gal_src);
-        put_vec(out, t.prow); put_vec(out, t.pcol); put_vec(out, t.pown); put_vec(out, t.rrow); put_vec(out, t.rblk);
-        put_vec(out, t.rfine); put_vec(out, t.aprow); put_vec(out, t.apcol); put_vec(out, t.crow); put_vec(out, t.ccol);
-        put_vec(out, t.cdiag);
+        src[l] = {vi(a.agg), vd(a.off), vi(t.prow), vi(t.pcol), vi(t.rrow), vi(t.rblk), vi(t.rfine), vi(t.aprow), vi(t.apcol),
+                  vi(t.crow), vi(t.ccol), vi(t.cdiag)};
     }
-}
-
-bool ml_hierarchy_unpack(const unsigned char *data, size_t bytes, MlHierarchy &H)
-{
-    H.agg.clear(); H.xfer.clear();
-    const unsigned char *p = data, *end = data + bytes;
-    uint64_t L = 0;
-    if (bytes < sizeof L) return false;
-    std::memcpy(&L, p, sizeof L); p += sizeof L;
-    if (L > 64) return false;
-    H.agg.resize((size_t)L); H.xfer.resize((size_t)L);
+    size_t at = (sizeof(MlImageHeader) + 15) & ~(size_t)15;
     for (size_t l = 0; l < L; ++l) {
-        HierLevel &a = H.agg[l];
-        MlTransfer &t = H.xfer[l];
-        int64_t head[6];
-        if ((size_t)(end - p) < sizeof head) return false;
-        std::memcpy(head, p, sizeof head); p += sizeof head;
-        a.n_fine = head[0]; a.n_coarse = head[1]; t.n_fine = head[2]; t.n_coarse = head[3]; t.smoothed = head[4] != 0;
-        if (!(get_vec(p, end, a.agg) && get_vec(p, end, a.off) && get_vec(p, end, a.agg_ptr) && get_vec(p, end, a.agg_rows) &&
-              get_vec(p, end, a.rowptr) && get_vec(p, end, a.colidx) && get_vec(p, end, a.gal_ptr) && get_vec(p, end, a.gal_src) &&
-              get_vec(p, end, t.prow) && get_vec(p, end, t.pcol) && get_vec(p, end, t.pown) && get_vec(p, end, t.rrow) &&
-              get_vec(p, end, t.rblk) && get_vec(p, end, t.rfine) && get_vec(p, end, t.aprow) && get_vec(p, end, t.apcol) &&
-              get_vec(p, end, t.crow) && get_vec(p, end, t.ccol) && get_vec(p, end, t.cdiag)))
-            return false;
+        hd.lv[l].n_fine = H.agg[l].n_fine; hd.lv[l].n_coarse = H.agg[l].n_coarse;
+        hd.lv[l].smoothed = (l >= 1 && H.xfer[l].smoothed) ? 1 : 0;
+        for (size_t k = 0; k < src[l].size(); ++k) {
+            hd.lv[l].off[k] = (int64_t)at; hd.lv[l].cnt[k] = src[l][k].cnt;
+            at += (src[l][k].bytes + 15) & ~(size_t)15;
+        }
     }
-    return p == end;
+    hd.total_bytes = (int64_t)at;
+    out.resize(at);   // one allocation, every array copied once (in parallel)
+    std::memcpy(out.data(), &hd, sizeof hd);
+    std::vector<std::thread> th;
+    for (size_t l = 0; l < L; ++l)
+        for (size_t k = 0; k < src[l].size(); ++k) {
+            const Src sk = src[l][k];
+            unsigned char *dst = out.data() + hd.lv[l].off[k];
+            if (sk.bytes > (size_t)(8 << 20)) th.emplace_back([=] { std::memcpy(dst, sk.p, sk.bytes); });
+            else if (sk.bytes) std::memcpy(dst, sk.p, sk.bytes);
+        }
+    for (auto &x : th) x.join();
+    return true;
 }
 
 void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,

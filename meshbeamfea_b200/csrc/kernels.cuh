@@ -190,6 +190,8 @@ void launch_ml_restrict_tent(cudaStream_t st, int64_t nc, const int32_t *rrow, c
 void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t row0, int64_t n, const float *dinv, const int32_t *agg, const double *off,
                                    const double *r, const double *zc, double *z);
 void launch_ml_row_of(cudaStream_t st, int64_t n, const int32_t *rowptr, int32_t *row_of);
+void launch_ml_shift_i32(cudaStream_t st, int64_t n, const int32_t *src, int32_t delta, int32_t *dst);
+void launch_ml_gather3(cudaStream_t st, int64_t n, const double *src, const int64_t *idx, double *dst);
 void launch_ml_make_p(cudaStream_t st, int64_t n, int64_t nnzp, const int32_t *prow, const int32_t *pcol, const int32_t *prow_of,
                       const int32_t *arow, const int32_t *acol, const double *avals, const int32_t *agg, const double *off,
                       const double *dinv, double omega, double *pval);

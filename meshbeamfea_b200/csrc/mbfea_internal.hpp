@@ -155,10 +155,25 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
                         double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H,
                         const int64_t *part_bounds = nullptr, int nparts = 1);
 
-// flat byte image of a hierarchy and back (several ranks: one rank builds, the others receive); unpack returns false on a
-// malformed image
-void ml_hierarchy_pack(const MlHierarchy &H, std::vector<unsigned char> &out);
-bool ml_hierarchy_unpack(const unsigned char *data, size_t bytes, MlHierarchy &H);
+// Flat image of a hierarchy for several ranks: rank 0 builds the hierarchy with every host core, packs it once, the
+// image travels H2D + one NCCL broadcast, and every rank fills its device arrays straight from the device copy
+// (device-to-device slices: no host unpacking on the receivers).  Header first (host-readable), then the arrays,
+// 16-byte aligned.  Level 0 arrays: agg, off, agg_ptr, agg_rows, level-1 rowptr / colidx / diagonal positions, gal_ptr,
+// gal_src.  Level l >= 1 (transfer l -> l + 1): agg, off, prow, pcol, rrow, rblk, rfine, aprow, apcol, crow, ccol, cdiag.
+constexpr int kMlImageMaxLevels = 16, kMlImageMaxWorld = 16, kMlImageArrays = 12;
+struct MlImageHeader {
+    int64_t magic, levels, world, group0, nbg, fine_nnz, total_bytes, pad;
+    // per rank (world + 1 entries): first fine block of its rows, first level-1 row / block, agg_ptr / gal_ptr at those
+    int64_t own_first[kMlImageMaxWorld + 1], agg_begin[kMlImageMaxWorld + 1], blk_begin[kMlImageMaxWorld + 1],
+        aggptr_at[kMlImageMaxWorld + 1], galptr_at[kMlImageMaxWorld + 1];
+    struct Level {
+        int64_t n_fine, n_coarse, smoothed, pad;
+        int64_t off[kMlImageArrays], cnt[kMlImageArrays];   // byte offset in the image, element count
+    } lv[kMlImageMaxLevels];
+};
+constexpr int64_t kMlImageMagic = 0x6d6c696d67303031LL;
+// fine_rowptr: block row pointer of the GLOBAL fine pattern (nbg + 1); false when the hierarchy does not fit the header
+bool ml_image_pack(const MlHierarchy &H, int world, int64_t nbg, const int32_t *fine_rowptr, std::vector<unsigned char> &out);
 
 // Explicit inverse of a dense SPD matrix (row-major n x n) for the coarsest level; 0, or 1 + the index of
 // the first non-positive pivot (dense.cpp).

@@ -363,6 +363,19 @@ __global__ void __launch_bounds__(kT) k_ml_to_f32(int64_t n, const double *__res
     if (t < n) out[t] = (float)a[t];
 }
 
+// slices of the hierarchy image (several ranks): dst[i] = src[i] - delta, and the offsets of the ghost rows
+__global__ void __launch_bounds__(kT) k_ml_shift_i32(int64_t n, const int32_t *__restrict__ src, int32_t delta, int32_t *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] - delta;
+}
+__global__ void __launch_bounds__(kT) k_ml_gather3(int64_t n, const double *__restrict__ src, const int64_t *__restrict__ idx,
+                                                   double *__restrict__ dst)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 3 * n) dst[t] = src[3 * idx[t / 3] + t % 3];
+}
+
 // row index of every block of a CSR pattern (setup helper): row_of[k] = i for k in [rowptr[i], rowptr[i+1])
 __global__ void __launch_bounds__(kT) k_ml_row_of(int64_t n, const int32_t *__restrict__ rowptr, int32_t *__restrict__ row_of)
 {
@@ -633,6 +646,14 @@ void launch_ml_make_t0(cudaStream_t st, int64_t nb, const double *lfac, const do
 void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv, float *dinv32)
 {
     if (n > 0) k_ml_diag_inv<<<blocks_for(n * 36), kT, 0, st>>>(n, sinv, dinv, dinv32);
+}
+void launch_ml_shift_i32(cudaStream_t st, int64_t n, const int32_t *src, int32_t delta, int32_t *dst)
+{
+    if (n > 0) k_ml_shift_i32<<<blocks_for(n), kT, 0, st>>>(n, src, delta, dst);
+}
+void launch_ml_gather3(cudaStream_t st, int64_t n, const double *src, const int64_t *idx, double *dst)
+{
+    if (n > 0) k_ml_gather3<<<blocks_for(3 * n), kT, 0, st>>>(n, src, idx, dst);
 }
 void launch_ml_row_of(cudaStream_t st, int64_t n, const int32_t *rowptr, int32_t *row_of)
 {

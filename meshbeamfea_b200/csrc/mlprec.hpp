@@ -71,6 +71,9 @@ public:
     // index of the first block of the rank's first row in it (0 on one rank)
     bool upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nb_global, int64_t fine_nnz, int64_t own_first_block,
                           const MlDist *dist);
+    // several ranks: the device arrays straight from the device copy of rank 0's image (ml_image_pack): device-to-device
+    // slices of level 0 (own rows, own aggregates, own level-1 block rows) and copies of the replicated coarse levels
+    bool upload_from_image(cudaStream_t st, const unsigned char *d_img, const MlImageHeader &hd, const MlDist &dist);
     // Galerkin matrices, smoothers, prolongators, coarsest inverse from the assembled K (full pattern, unscaled) and
     // the Cholesky factors of its diagonal blocks.  *d_flag |= 1/2 on a non-SPD coarse block / coarsest pivot.
     void build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_vals,
@@ -83,6 +86,7 @@ public:
     size_t levels() const { return lv.size(); }
 
 private:
+    void alloc_level_buffers(cudaStream_t st, MlCoarse &c, bool has_next);
     // multi-rank: own slice of level 1 (aggregates [agg_begin[rank], agg_begin[rank + 1]), their matrix blocks)
     int rank = 0, world = 1;
     const nccl::Api *nc = nullptr;

@@ -136,10 +136,6 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
         for (int64_t I = 0; I < c->n; ++I)
             diag[(size_t)I] = (int32_t)(std::lower_bound(ci.begin() + rp[(size_t)I], ci.begin() + rp[(size_t)I + 1], (int32_t)I) - ci.begin());
         up(st, c->diag_idx, diag);
-        CK(c->row_of.alloc((size_t)c->nnz));
-        CK(c->vals.alloc((size_t)c->nnz * 36));
-        CK(c->r.alloc((size_t)c->n * 6)); CK(c->z.alloc((size_t)c->n * 6));
-        launch_ml_row_of(st, c->n, c->rowptr.p, c->row_of.p);
         if (m + 1 < L) {   // transfer from level m + 1 to level m + 2
             const HierLevel &h = H.agg[m + 1];
             const MlTransfer &T = H.xfer[m + 1];
@@ -149,14 +145,8 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
             up(st, c->prow, T.prow); up(st, c->pcol, T.pcol);
             up(st, c->rrow, T.rrow); up(st, c->rblk, T.rblk); up(st, c->rfine, T.rfine);
             up(st, c->aprow, T.aprow); up(st, c->apcol, T.apcol);
-            CK(c->prow_of.alloc((size_t)c->nnzp)); CK(c->aprow_of.alloc((size_t)c->nnzap));
-            launch_ml_row_of(st, c->n, c->prow.p, c->prow_of.p);
-            launch_ml_row_of(st, c->n, c->aprow.p, c->aprow_of.p);
-            CK(c->pval.alloc((size_t)c->nnzp * 36)); CK(c->apval.alloc((size_t)c->nnzap * 36));
-            if (c->smoothed) CK(c->pval32.alloc((size_t)c->nnzp * 36));
-            CK(c->lfac.alloc((size_t)c->n * 36)); CK(c->sinv.alloc((size_t)c->n * 36)); CK(c->dinv.alloc((size_t)c->n * 36));
-            CK(c->dinv32.alloc((size_t)c->n * 36));
         }
+        alloc_level_buffers(st, *c, m + 1 < L);
         lv.push_back(std::move(c));
     }
     n_dense = 6 * lv.back()->n;
@@ -164,6 +154,102 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
     CK(dense32.alloc((size_t)(n_dense * n_dense)));
     CK(gj_col.alloc((size_t)n_dense * 6));
     CK(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+    symbolic_ok = true;
+    ms_symbolic = wall_ms() - t0w;
+    return true;
+}
+
+// value / work arrays of a coarse level whose index arrays are in place
+void MlPrec::alloc_level_buffers(cudaStream_t st, MlCoarse &c, bool has_next)
+{
+    CK(c.row_of.alloc((size_t)c.nnz));
+    CK(c.vals.alloc((size_t)c.nnz * 36));
+    CK(c.r.alloc((size_t)c.n * 6)); CK(c.z.alloc((size_t)c.n * 6));
+    launch_ml_row_of(st, c.n, c.rowptr.p, c.row_of.p);
+    if (!has_next) return;
+    CK(c.prow_of.alloc((size_t)c.nnzp)); CK(c.aprow_of.alloc((size_t)c.nnzap));
+    launch_ml_row_of(st, c.n, c.prow.p, c.prow_of.p);
+    launch_ml_row_of(st, c.n, c.aprow.p, c.aprow_of.p);
+    CK(c.pval.alloc((size_t)c.nnzp * 36)); CK(c.apval.alloc((size_t)c.nnzap * 36));
+    if (c.smoothed) CK(c.pval32.alloc((size_t)c.nnzp * 36));
+    CK(c.lfac.alloc((size_t)c.n * 36)); CK(c.sinv.alloc((size_t)c.n * 36)); CK(c.dinv.alloc((size_t)c.n * 36));
+    CK(c.dinv32.alloc((size_t)c.n * 36));
+}
+
+bool MlPrec::upload_from_image(cudaStream_t st, const unsigned char *d_img, const MlImageHeader &hd, const MlDist &dist)
+{
+    const double t0w = wall_ms();
+    reset();
+    if (hd.magic != kMlImageMagic || hd.levels < 1 || hd.levels > kMlImageMaxLevels || hd.world != dist.world) return false;
+    rank = dist.rank; world = dist.world; nc = dist.nc; comm = dist.comm;
+    const size_t L = (size_t)hd.levels;
+    if (6 * hd.lv[L - 1].n_coarse > 3072) return false;
+    group0 = (int)hd.group0;
+    agg_begin.assign(hd.agg_begin, hd.agg_begin + world + 1);
+    blk_begin.assign(hd.blk_begin, hd.blk_begin + world + 1);
+    auto src_i = [&](size_t l, int k) { return reinterpret_cast<const int32_t *>(d_img + hd.lv[l].off[k]); };
+    auto src_d = [&](size_t l, int k) { return reinterpret_cast<const double *>(d_img + hd.lv[l].off[k]); };
+    auto copy_i = [&](DevBuf<int32_t> &dst, size_t l, int k) {
+        CK(dst.alloc((size_t)hd.lv[l].cnt[k]));
+        if (hd.lv[l].cnt[k]) CK(cudaMemcpyAsync(dst.p, src_i(l, k), (size_t)hd.lv[l].cnt[k] * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    };
+    auto copy_d = [&](DevBuf<double> &dst, size_t l, int k) {
+        CK(dst.alloc((size_t)hd.lv[l].cnt[k]));
+        if (hd.lv[l].cnt[k]) CK(cudaMemcpyAsync(dst.p, src_d(l, k), (size_t)hd.lv[l].cnt[k] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    };
+    // ---- level 0: the rank's own rows, aggregates and level-1 block rows
+    const int64_t r0 = dist.row_begin, nbl = dist.row_end - dist.row_begin, ng = (int64_t)dist.ghost_global->size();
+    const int64_t a0 = agg_begin[(size_t)rank], a1 = agg_begin[(size_t)rank + 1];
+    const int64_t b0 = blk_begin[(size_t)rank], b1 = blk_begin[(size_t)rank + 1];
+    const int64_t m0 = hd.aggptr_at[rank], m1 = hd.aggptr_at[rank + 1];   // member-list range of the own aggregates
+    const int64_t g0 = hd.galptr_at[rank], g1 = hd.galptr_at[rank + 1];   // contributor-list range of the own level-1 blocks
+    nb = nbl;
+    CK(agg0.alloc((size_t)nbl));
+    CK(cudaMemcpyAsync(agg0.p, src_i(0, 0) + r0, (size_t)nbl * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    CK(off0.alloc((size_t)3 * (size_t)(nbl + ng)));
+    CK(cudaMemcpyAsync(off0.p, src_d(0, 1) + 3 * r0, (size_t)3 * nbl * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    DevBuf<int64_t> d_ghost;
+    if (ng > 0) {
+        CK(d_ghost.alloc((size_t)ng));
+        CK(cudaMemcpyAsync(d_ghost.p, dist.ghost_global->data(), (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        launch_ml_gather3(st, ng, src_d(0, 1), d_ghost.p, off0.p + 3 * nbl);
+    }
+    CK(agg_ptr0.alloc((size_t)(a1 - a0) + 1));
+    launch_ml_shift_i32(st, a1 - a0 + 1, src_i(0, 2) + a0, (int32_t)m0, agg_ptr0.p);
+    CK(agg_rows0.alloc((size_t)(m1 - m0)));
+    launch_ml_shift_i32(st, m1 - m0, src_i(0, 3) + m0, (int32_t)r0, agg_rows0.p);
+    CK(gal_ptr0.alloc((size_t)(b1 - b0) + 1));
+    launch_ml_shift_i32(st, b1 - b0 + 1, src_i(0, 7) + b0, (int32_t)g0, gal_ptr0.p);
+    CK(gal_src0.alloc((size_t)(g1 - g0)));
+    // the rank's local pattern keeps the blocks of a row in GLOBAL column order, so global fine block k of an own row is
+    // local block k - (first block of the rank's first row)
+    launch_ml_shift_i32(st, g1 - g0, src_i(0, 8) + g0, (int32_t)hd.own_first[rank], gal_src0.p);
+    CK(frow0.alloc((size_t)dist.loc_rowptr[nbl]));
+    CK(t0.alloc((size_t)nb * 36));
+    rows.push_back(nb);
+    // ---- coarse levels: replicated
+    for (size_t m = 0; m < L; ++m) {
+        std::unique_ptr<MlCoarse> c(new MlCoarse);
+        c->n = hd.lv[m].n_coarse;
+        if (m == 0) { copy_i(c->rowptr, 0, 4); copy_i(c->colidx, 0, 5); copy_i(c->diag_idx, 0, 6); c->nnz = hd.lv[0].cnt[5]; }
+        else { copy_i(c->rowptr, m, 9); copy_i(c->colidx, m, 10); copy_i(c->diag_idx, m, 11); c->nnz = hd.lv[m].cnt[10]; }
+        rows.push_back(c->n);
+        const bool has_next = m + 1 < L;
+        if (has_next) {   // transfer from level m + 1 to level m + 2: image level m + 1
+            const size_t l = m + 1;
+            c->has_next = true; c->smoothed = hd.lv[l].smoothed != 0; c->n_next = hd.lv[l].n_coarse;
+            c->nnzp = hd.lv[l].cnt[3]; c->nnzap = hd.lv[l].cnt[8];
+            copy_i(c->agg, l, 0); copy_d(c->off, l, 1); copy_i(c->prow, l, 2); copy_i(c->pcol, l, 3);
+            copy_i(c->rrow, l, 4); copy_i(c->rblk, l, 5); copy_i(c->rfine, l, 6); copy_i(c->aprow, l, 7); copy_i(c->apcol, l, 8);
+        }
+        alloc_level_buffers(st, *c, has_next);
+        lv.push_back(std::move(c));
+    }
+    n_dense = 6 * lv.back()->n;
+    CK(dense.alloc((size_t)(n_dense * n_dense)));
+    CK(dense32.alloc((size_t)(n_dense * n_dense)));
+    CK(gj_col.alloc((size_t)n_dense * 6));
+    CK(cudaStreamSynchronize(st));   // d_ghost and the image may go away
     symbolic_ok = true;
     ms_symbolic = wall_ms() - t0w;
     return true;
