@@ -341,6 +341,11 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
 int mbfea_host_ml_hierarchy(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
                             const int32_t *fixed, double cell_beam_lengths, double ratio, int64_t coarsest_rows,
                             int32_t smooth_from, int32_t max_levels, int32_t *n_levels, int64_t *sizes);
+/* ml_image: the flat image of the hierarchy that rank 0 of a `world`-rank job builds and broadcasts (mbfea_set_job with
+ *           options.precond = 2 on several ranks; csrc/mbfea_internal.hpp: MlImageHeader followed by the arrays).  Host-only,
+ *           for the CPU tests of the multi-rank slicing.  Call with image = NULL to get *n_bytes, then with a buffer.     */
+int mbfea_host_ml_image(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
+                        const int32_t *fixed, int32_t world, int32_t smooth_from, int64_t *n_bytes, unsigned char *image);
 /* spd_inverse: explicit inverse of a dense symmetric positive definite matrix (row-major n x n), the
  *           coarsest-level solve of that preconditioner; MBFEA_ESINGULAR on a non-positive pivot.    */
 int mbfea_host_spd_inverse(int64_t n, const double *A, double *Ainv);

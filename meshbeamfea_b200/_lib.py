@@ -115,6 +115,7 @@ SIGNATURES = {
     "mbfea_host_contributors": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _i32, _pi64, _pi32, _pi32]),
     "mbfea_host_ml_hierarchy": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, C.c_double, C.c_double, _i64, _i32, _i32,
                                           _pi32, _pi64]),
+    "mbfea_host_ml_image": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, _i32, _i32, _pi64, C.c_void_p]),
     "mbfea_host_spd_inverse": (C.c_int, [_i64, _pd, _pd]),
     "mbfea_hierarchy_open": (C.c_int, [_i64, _i64, _pd, _pi32, _i64, _pi32, C.c_double, C.c_double, _i32, _i64,
                                        C.POINTER(C.c_void_p)]),

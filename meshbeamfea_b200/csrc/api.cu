@@ -805,6 +805,8 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             if (c->opt.ml_ratio > 1.0) mp.ratio = c->opt.ml_ratio;
             if (c->opt.ml_coarsest_rows > 0) mp.coarsest_rows = std::min<int64_t>(c->opt.ml_coarsest_rows, 512);
             if (c->opt.ml_smooth_from > 0) mp.smooth_from = c->opt.ml_smooth_from;
+            if (const char *e = std::getenv("MBFEA_ML_OMEGA")) { const double v = std::atof(e); if (v > 0.0 && v < 2.0) mp.omega = v; }
+            if (const char *e = std::getenv("MBFEA_ML_THETA")) { const double v = std::atof(e); if (v > 0.0) mp.theta = v; }
             c->ml.par = mp;
         }
         struct JoinGuard { std::thread &t; ~JoinGuard() { if (t.joinable()) t.join(); } } ml_join{ml_thread};
@@ -1976,6 +1978,45 @@ int mbfea_host_ml_hierarchy(int64_t V, int64_t E, const double *nodes_cm, const 
             sizes[6 * l + 4] = gen ? (int64_t)H.xfer[l].apcol.size() : 0;                                 // blocks of A P
             sizes[6 * l + 5] = gen && H.xfer[l].smoothed ? 1 : 0;
         }
+    } catch (const std::bad_alloc &) {
+        return MBFEA_EARG;
+    }
+    return MBFEA_OK;
+}
+
+int mbfea_host_ml_image(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm, int64_t F,
+                        const int32_t *fixed, int32_t world, int32_t smooth_from, int64_t *n_bytes, unsigned char *image)
+{
+    if (V <= 0 || E <= 0 || !nodes_cm || !elems_cm || !n_bytes || (F > 0 && !fixed) || world < 1 || world > kMlImageMaxWorld) return MBFEA_EARG;
+    for (int64_t e = 0; e < 2 * E; ++e)
+        if (elems_cm[e] < 0 || elems_cm[e] >= V) return MBFEA_EPRECOND;
+    for (int64_t i = 0; i < F; ++i)
+        if (fixed[i] < 0 || fixed[i] >= V) return MBFEA_ERANGE_FIXED;
+    try {
+        HostPlan P;
+        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, P);
+        const int64_t nb = P.nb();
+        std::vector<double> pos((size_t)3 * std::max<int64_t>(nb, 1));
+        for (int64_t v = 0; v < V; ++v)
+            if (P.free_index[(size_t)v] >= 0)
+                for (int a = 0; a < 3; ++a) pos[(size_t)3 * P.free_index[(size_t)v] + a] = nodes_cm[(size_t)a * V + v];
+        double sum = 0.0;
+        for (int64_t e = 0; e < E; ++e) {
+            double d2 = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                d2 += d * d;
+            }
+            sum += std::sqrt(d2);
+        }
+        MlPrec ml;
+        if (smooth_from > 0) ml.par.smooth_from = smooth_from;
+        MlHierarchy H;
+        ml.build_hierarchy_host(nb, P.rowptr.data(), P.colidx.data(), pos.data(), sum / (double)E, world, H);
+        std::vector<unsigned char> img;
+        if (!ml_image_pack(H, world, nb, P.rowptr.data(), img)) return MBFEA_ESTATE;
+        if (image && *n_bytes >= (int64_t)img.size()) std::memcpy(image, img.data(), img.size());
+        *n_bytes = (int64_t)img.size();
     } catch (const std::bad_alloc &) {
         return MBFEA_EARG;
     }

@@ -1203,7 +1203,7 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
 __global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t *__restrict__ agg, const float *__restrict__ t0,
                                                        const double *__restrict__ rt, const double *__restrict__ z1,
                                                        double *__restrict__ zt, double *__restrict__ part,
-                                                       const PcgScalars *sc, const PeerCtx *pc)
+                                                       const PcgScalars *sc, const PeerCtx *pc, double theta)
 {
     __shared__ double red[33];
     if (sc != nullptr && sc->done != 0) return;
@@ -1215,10 +1215,11 @@ __global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t
         const float2 *T = reinterpret_cast<const float2 *>(t0 + t * 6);
         const float2 a = __ldg(T), b = __ldg(T + 1), c = __ldg(T + 2);
         const double ri = rt[t];
-        double s = ri;
-        s = fma((double)a.x, zc[0], s); s = fma((double)a.y, zc[1], s);
+        double s = (double)a.x * zc[0];
+        s = fma((double)a.y, zc[1], s);
         s = fma((double)b.x, zc[2], s); s = fma((double)b.y, zc[3], s);
         s = fma((double)c.x, zc[4], s); s = fma((double)c.y, zc[5], s);
+        s = fma(theta, s, ri);   // theta: weight of the coarse correction against the block-Jacobi term
         zt[t] = s;
         dot = fma(ri, s, dot);
     }
@@ -1235,9 +1236,9 @@ __global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t
 }
 
 void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
-                       const double *z1, double *zt, double *part, const PcgScalars *sc, const PeerCtx *pc)
+                       const double *z1, double *zt, double *part, const PcgScalars *sc, const PeerCtx *pc, double theta)
 {
-    if (nb > 0 && grid > 0) k_ml_finish0<<<(unsigned)grid, 256, 0, st>>>(nb, agg, t0, rt, z1, zt, part, sc, pc);
+    if (nb > 0 && grid > 0) k_ml_finish0<<<(unsigned)grid, 256, 0, st>>>(nb, agg, t0, rt, z1, zt, part, sc, pc, theta);
 }
 
 // p = r~ + beta p.  Multi-GPU: the thread that produces a boundary block's entries also stores

@@ -208,7 +208,8 @@ void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_
                          const float *t0, const double *r, double *rc);
 void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
                        const double *z1, double *zt, double *part, const PcgScalars *sc = nullptr,
-                       const PeerCtx *pc = nullptr /* kernels.cu: peer path publishes r~.z~ through the mailboxes */);
+                       const PeerCtx *pc = nullptr /* kernels.cu: peer path publishes r~.z~ through the mailboxes */,
+                       double theta = 1.0 /* weight of the coarse correction */);
 void launch_ml_restrict(cudaStream_t st, int64_t nc, int64_t nnzp, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
                         const float *pval, const double *r, double *rc, int64_t fine_lo, int64_t fine_hi);
 void launch_ml_smooth_prolong(cudaStream_t st, int64_t row0, int64_t n, int64_t n_level, int64_t nnzp, const float *dinv,

@@ -22,6 +22,7 @@ struct MlParams {
     int smooth_from = 1;          // first level whose prolongator to the next level is smoothed (>= 1)
     int max_levels = 12;
     double omega = 0.6;           // damping of the prolongator smoother, P = (I - omega D^-1 A) T
+    double theta = 1.0;           // weight of the coarse correction against the block-Jacobi term, z~ = r~ + theta P0~ (...)
 };
 
 struct MlCoarse {                 // one coarse level (l >= 1) and its transfer to level l + 1

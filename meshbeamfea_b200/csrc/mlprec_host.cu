@@ -369,7 +369,7 @@ void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, 
             launch_ml_smooth_prolong_tent(st, row0, cnt, lv[m]->dinv32.p, lv[m]->agg.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->z.p,
                                           lv[m]->z.p);
     }
-    launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part, sc, pc);
+    launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part, sc, pc, par.theta);
 }
 
 }  // namespace mbfea

@@ -593,3 +593,72 @@ def test_multilevel_transfer_math(tmp_path):
                     os.path.join(here, "multilevel_math_check.cpp"), "-o", exe], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def _ml_image(job, world, smooth_from=0):
+    """(header dict, arrays per level) of the hierarchy image rank 0 broadcasts on `world` ranks."""
+    import ctypes as C
+    from meshbeamfea_b200 import _lib as L
+    lib = L.lib()
+    nodes = np.ascontiguousarray(np.asarray(job.nodes, np.float64).T.ravel())
+    el = np.ascontiguousarray(np.asarray(job.elements, np.int32).T.ravel())
+    fx = np.ascontiguousarray(job.fixedNodes, np.int32)
+    n = C.c_int64(0)
+    args = (job.nodes.shape[0], job.elements.shape[0], L.ptr(nodes, L._pd), L.ptr(el, L._pi32), fx.size, L.ptr(fx, L._pi32), world, smooth_from)
+    assert lib.mbfea_host_ml_image(*args, C.byref(n), None) == 0
+    buf = np.zeros(n.value, np.uint8)
+    assert lib.mbfea_host_ml_image(*args, C.byref(n), buf.ctypes.data_as(C.c_void_p)) == 0
+    w = buf[:8 * 8].view(np.int64)
+    hd = dict(magic=int(w[0]), levels=int(w[1]), world=int(w[2]), group0=int(w[3]), nbg=int(w[4]), fine_nnz=int(w[5]), total=int(w[6]))
+    per_rank = buf[64:64 + 5 * 17 * 8].view(np.int64).reshape(5, 17)
+    for k, name in enumerate(("own_first", "agg_begin", "blk_begin", "aggptr_at", "galptr_at")):
+        hd[name] = per_rank[k, :world + 1].copy()
+    base = 64 + 5 * 17 * 8
+    levels = []
+    for l in range(hd["levels"]):
+        rec = buf[base + l * (4 + 24) * 8: base + (l + 1) * (4 + 24) * 8].view(np.int64)
+        off, cnt = rec[4:16], rec[16:28]
+        is_f64 = {1}   # array 1 of every level is the offsets (double), the rest are int32
+        arrs = []
+        for k in range(12):
+            dt = np.float64 if k in is_f64 else np.int32
+            arrs.append(buf[off[k]: off[k] + cnt[k] * np.dtype(dt).itemsize].view(dt) if cnt[k] else np.zeros(0, dt))
+        levels.append(dict(n_fine=int(rec[0]), n_coarse=int(rec[1]), smoothed=int(rec[2]), arrays=arrs))
+    return hd, levels
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_multilevel_hierarchy_image_is_sliceable_by_rank(world):
+    """Several ranks: rank 0 builds the multilevel hierarchy and broadcasts one flat image; every rank slices its share of level
+    0 out of it on the device.  That only works if fine-level aggregates never straddle a rank and are numbered rank-major,
+    and if the member / contributor lists of a rank's aggregates and level-1 block rows reference its own rows and blocks
+    only -- checked here on the image itself, against the partition of mbfea_plan_partition."""
+    job = syn.cubic_lattice(9)
+    hd, lv = _ml_image(job, world)
+    assert hd["magic"] == 0x6d6c696d67303031 and hd["world"] == world and hd["levels"] >= 1
+    nbg = hd["nbg"]
+    agg, off, agg_ptr, agg_rows, rp1, ci1, diag1, gal_ptr, gal_src = lv[0]["arrays"][:9]
+    assert agg.size == nbg and off.size == 3 * nbg and lv[0]["n_fine"] == nbg
+    bounds = [nbg * q // world for q in range(world + 1)]
+    for q in range(world):
+        plan = mb.plan_partition(job.nodes.shape[0], job.elements, job.fixedNodes, q, world)
+        assert (plan["row_begin"], plan["row_end"]) == (bounds[q], bounds[q + 1])
+        # the image's block offsets are those of the rank's own local pattern (same block order, see build_plan)
+        assert hd["own_first"][q + 1] - hd["own_first"][q] == plan["rowptr"][-1]
+        a0, a1 = hd["agg_begin"][q], hd["agg_begin"][q + 1]
+        mine = agg[bounds[q]:bounds[q + 1]]
+        assert mine.min() >= a0 and mine.max() < a1                       # rank-major, no straddling
+        members = agg_rows[agg_ptr[a0]:agg_ptr[a1]]
+        assert members.min() >= bounds[q] and members.max() < bounds[q + 1]
+        assert hd["aggptr_at"][q] == agg_ptr[a0] and hd["blk_begin"][q] == rp1[a0]
+        b0, b1 = hd["blk_begin"][q], hd["blk_begin"][q + 1]
+        src = gal_src[gal_ptr[b0]:gal_ptr[b1]]
+        assert hd["galptr_at"][q] == gal_ptr[b0]
+        assert src.min() >= hd["own_first"][q] and src.max() < hd["own_first"][q + 1]   # fine blocks of the rank's own rows only
+    assert hd["agg_begin"][world] == lv[0]["n_coarse"] and gal_src.size == hd["fine_nnz"]
+    assert np.array_equal(np.sort(gal_src), np.arange(hd["fine_nnz"]))   # every fine block contributes exactly once
+    # diagonal positions of the level-1 pattern
+    assert all(ci1[diag1[i]] == i for i in range(lv[0]["n_coarse"]))
+    # the one-rank image of the same mesh has fewer (unsplit) aggregates
+    hd1, lv1 = _ml_image(job, 1)
+    assert lv1[0]["n_coarse"] <= lv[0]["n_coarse"]
