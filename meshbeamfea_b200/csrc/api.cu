@@ -100,6 +100,8 @@ struct mbfea_ctx {
     // multilevel preconditioner (options.precond): hierarchy built in set_job, numeric setup in assemble
     MlPrec ml;
     bool use_ml = false;
+    MlHierarchy ml_host;   // host half of the hierarchy, kept between jobs: its arrays keep their capacity
+    std::vector<double> ml_pos;
 
     // PCG graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -790,9 +792,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         // thread while this one builds the solver format and uploads the mesh and the plan.  (Several ranks: rank 0 builds it
         // for everybody -- the ranks of a box share the host cores, W redundant builds would each get 1 / W of them.)
         struct MlHostJob {
-            std::vector<double> pos;
             double mean_len = 0.0;
-            MlHierarchy H;
             std::vector<unsigned char> img;   // several ranks, rank 0: flat image for the broadcast
             bool failed = false;
             double ms = 0.0;
@@ -810,6 +810,60 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             c->ml.par = mp;
         }
         struct JoinGuard { std::thread &t; ~JoinGuard() { if (t.joinable()) t.join(); } } ml_join{ml_thread};
+        auto start_ml_thread = [&]() {
+        if (ml_build_here) {
+                ml_thread = std::thread([&, V, E, F]() {
+                    try {
+                        const double tw = now_ms();
+                        const int64_t nbg = c->plan.nb_global;
+                        const int W = c->opt.world;
+                        // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
+                        // mean beam length: the aggregates are bricks of a few beam lengths
+                        c->ml_pos.resize((size_t)3 * nbg);
+                        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, E >> 16));
+                        std::vector<double> part((size_t)nt, 0.0);
+                        std::vector<std::thread> th;
+                        for (int t = 0; t < nt; ++t)
+                            th.emplace_back([&, t]() {
+                                for (int64_t v = V * t / nt; v < V * (t + 1) / nt; ++v) {
+                                    const int32_t r = c->plan.free_index[(size_t)v];
+                                    if (r >= 0) for (int a = 0; a < 3; ++a) c->ml_pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
+                                }
+                                double len = 0.0;   // fixed chunks, summed in chunk order below: reproducible
+                                for (int64_t e = E * t / nt; e < E * (t + 1) / nt; ++e) {
+                                    double d2 = 0.0;
+                                    for (int a = 0; a < 3; ++a) {
+                                        const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                                        d2 += d * d;
+                                    }
+                                    len += std::sqrt(d2);
+                                }
+                                part[(size_t)t] = len;
+                            });
+                        for (auto &x : th) x.join();
+                        double len = 0.0;
+                        for (int t = 0; t < nt; ++t) len += part[(size_t)t];
+                        mlh.mean_len = len / (double)E;
+                        if (W == 1) {
+                            c->ml.build_hierarchy_host(nbg, c->plan.rowptr.data(), c->plan.colidx.data(), c->ml_pos.data(), mlh.mean_len, 1, c->ml_host);
+                        } else {
+                            HostPlan G;
+                            build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
+                            c->ml.build_hierarchy_host(nbg, G.rowptr.data(), G.colidx.data(), c->ml_pos.data(), mlh.mean_len, W, c->ml_host);
+                            if (!ml_image_pack(c->ml_host, W, nbg, G.rowptr.data(), mlh.img)) mlh.failed = true;
+                        }
+                        mlh.ms = now_ms() - tw;
+                    } catch (...) {
+                        mlh.failed = true;
+                    }
+                });
+            }
+        };
+        // started here, next to the rest of the host prep (MBFEA_ML_THREAD_LATE=1: only after it, next to the device uploads).
+        // Measured on the 119^3 lattice: set_job 180 ms against 280 ms, once the hierarchy arrays keep their capacity
+        // between jobs -- with fresh allocations on both sides the two thread pools serialised on page faults instead.
+        const bool ml_early = [] { const char *e = std::getenv("MBFEA_ML_THREAD_LATE"); return !(e && *e == '1'); }();
+        if (ml_early) start_ml_thread();
         build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
         build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
         c->tma_ok = true;
@@ -828,55 +882,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             tl = n;
         };
 
-        // (started after the host prep: both allocate and first-touch hundreds of MB, and concurrent page faults from two
-        // thread pools serialise on the process' mmap lock -- measured 300 ms of stall; the device uploads below do not)
-        if (ml_build_here) {
-            ml_thread = std::thread([&, V, E, F]() {
-                try {
-                    const double tw = now_ms();
-                    const int64_t nbg = c->plan.nb_global;
-                    const int W = c->opt.world;
-                    // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
-                    // mean beam length: the aggregates are bricks of a few beam lengths
-                    mlh.pos.resize((size_t)3 * nbg);
-                    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, E >> 16));
-                    std::vector<double> part((size_t)nt, 0.0);
-                    std::vector<std::thread> th;
-                    for (int t = 0; t < nt; ++t)
-                        th.emplace_back([&, t]() {
-                            for (int64_t v = V * t / nt; v < V * (t + 1) / nt; ++v) {
-                                const int32_t r = c->plan.free_index[(size_t)v];
-                                if (r >= 0) for (int a = 0; a < 3; ++a) mlh.pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
-                            }
-                            double len = 0.0;   // fixed chunks, summed in chunk order below: reproducible
-                            for (int64_t e = E * t / nt; e < E * (t + 1) / nt; ++e) {
-                                double d2 = 0.0;
-                                for (int a = 0; a < 3; ++a) {
-                                    const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
-                                    d2 += d * d;
-                                }
-                                len += std::sqrt(d2);
-                            }
-                            part[(size_t)t] = len;
-                        });
-                    for (auto &x : th) x.join();
-                    double len = 0.0;
-                    for (int t = 0; t < nt; ++t) len += part[(size_t)t];
-                    mlh.mean_len = len / (double)E;
-                    if (W == 1) {
-                        c->ml.build_hierarchy_host(nbg, c->plan.rowptr.data(), c->plan.colidx.data(), mlh.pos.data(), mlh.mean_len, 1, mlh.H);
-                    } else {
-                        HostPlan G;
-                        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
-                        c->ml.build_hierarchy_host(nbg, G.rowptr.data(), G.colidx.data(), mlh.pos.data(), mlh.mean_len, W, mlh.H);
-                        if (!ml_image_pack(mlh.H, W, nbg, G.rowptr.data(), mlh.img)) mlh.failed = true;
-                    }
-                    mlh.ms = now_ms() - tw;
-                } catch (...) {
-                    mlh.failed = true;
-                }
-            });
-        }
+        if (!ml_early) start_ml_thread();
         const int64_t nb = c->nb(), ng = c->ng(), nnzb = c->plan.nnzb();
         // mesh -> device, repacked into aligned records
         {
@@ -958,7 +964,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             const int64_t nbg = c->plan.nb_global;
             if (ml_thread.joinable()) ml_thread.join();
             if (c->opt.world == 1) {
-                c->use_ml = !mlh.failed && c->ml.upload_hierarchy(c->st, mlh.H, nbg, (int64_t)c->plan.rowptr[(size_t)nb], 0, nullptr);
+                c->use_ml = !mlh.failed && c->ml.upload_hierarchy(c->st, c->ml_host, nbg, (int64_t)c->plan.rowptr[(size_t)nb], 0, nullptr);
             } else {
                 // rank 0's flat image goes through the GPUs to everybody; each rank then uploads its own share of level 0 and
                 // the replicated coarse levels

@@ -50,6 +50,24 @@ static void par_ranges(int64_t n, int64_t min_per_thread, Fn fn)
 // part_bounds (optional, nparts + 1 ascending row bounds): aggregates never straddle a part -- a brick cut by a
 // partition boundary becomes one aggregate per part -- and are numbered part-major, so that every part owns a
 // contiguous range of aggregates (multi-GPU: the fine-level transfer is then local to a rank).
+// the same with the thread's index and the number of ranges actually used (per-thread scratch)
+template <class Fn>
+static int64_t par_ranges_t(int64_t n, int64_t min_per_thread, Fn fn)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int64_t nt = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 32), n / std::max<int64_t>(1, min_per_thread)));
+    if (nt <= 1) { fn((int64_t)0, n, (int64_t)0); return 1; }
+    std::vector<std::thread> th;
+    for (int64_t t = 0; t < nt; ++t) th.emplace_back([=] { fn(n * t / nt, n * (t + 1) / nt, t); });
+    for (auto &x : th) x.join();
+    return nt;
+}
+static int64_t par_ranges_count(int64_t n, int64_t min_per_thread)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 32), n / std::max<int64_t>(1, min_per_thread)));
+}
+
 static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *pos, double cell,
                         HierLevel &L, bool with_galerkin_lists = true, const int64_t *part_bounds = nullptr, int nparts = 1)
 {
@@ -132,7 +150,10 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
             for (int a = 0; a < 3; ++a) L.off[(size_t)3 * v + a] = pos[3 * v + a] - L.centroid[(size_t)3 * L.agg[(size_t)v] + a];
     });
     lap("centroids + offsets", n);
-    if (!with_galerkin_lists) return;   // coarse-to-coarse transfers build their own patterns (build_transfer)
+    if (!with_galerkin_lists) {   // coarse-to-coarse transfers build their own patterns (build_transfer)
+        L.rowptr.clear(); L.colidx.clear(); L.gal_ptr.clear(); L.gal_src.clear();
+        return;
+    }
     // coarse pattern: aggregate I couples to agg(col) of every block of its member rows.  Two passes (count,
     // fill) over ranges of aggregates, each thread with its own scratch.
     L.rowptr.assign((size_t)na + 1, 0);
@@ -205,22 +226,26 @@ static void build_transfer(int64_t n, const int32_t *rowptr, const int32_t *coli
     };
     auto build_rows = [&](int64_t rows, int64_t ncols, int64_t min_per_thread, std::vector<int32_t> &rp, std::vector<int32_t> &ci, auto &&gen) {
         rp.assign((size_t)rows + 1, 0);
-        std::vector<std::vector<int32_t>> keep((size_t)rows);   // rows are generated once; the fill pass only copies
-        par_ranges(rows, min_per_thread, [&](int64_t b0, int64_t b1) {
+        // every thread generates the rows of its contiguous range once, into one flat buffer; after the prefix sum the
+        // buffer is exactly the slice [rp[first row], rp[last row + 1]) of the column array
+        const int64_t nt = par_ranges_count(rows, min_per_thread);
+        std::vector<std::vector<int32_t>> flat((size_t)nt);
+        par_ranges_t(rows, min_per_thread, [&](int64_t b0, int64_t b1, int64_t t) {
             Dedup d;
             d.mark.assign((size_t)ncols, -1);
+            std::vector<int32_t> &mine = flat[(size_t)t];
             for (int64_t i = b0; i < b1; ++i) {
                 d.begin((int32_t)i);
                 gen(i, d);
                 std::sort(d.out.begin(), d.out.end());
                 rp[(size_t)i + 1] = (int32_t)d.out.size();
-                keep[(size_t)i] = d.out;
+                mine.insert(mine.end(), d.out.begin(), d.out.end());
             }
         });
         for (int64_t i = 0; i < rows; ++i) rp[(size_t)i + 1] += rp[(size_t)i];
         ci.resize((size_t)rp[(size_t)rows]);
-        par_ranges(rows, 1 << 12, [&](int64_t b0, int64_t b1) {
-            for (int64_t i = b0; i < b1; ++i) std::copy(keep[(size_t)i].begin(), keep[(size_t)i].end(), ci.begin() + rp[(size_t)i]);
+        par_ranges_t(rows, min_per_thread, [&](int64_t b0, int64_t, int64_t t) {
+            if (!flat[(size_t)t].empty()) std::memcpy(ci.data() + rp[(size_t)b0], flat[(size_t)t].data(), flat[(size_t)t].size() * sizeof(int32_t));
         });
     };
     // P: row i couples to agg(j) of every block (i, j) when smoothed, to agg(i) alone otherwise
@@ -276,30 +301,34 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
                         double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H,
                         const int64_t *part_bounds, int nparts)
 {
-    H.agg.clear(); H.xfer.clear();
-    if (nb <= 0 || !(cell0 > 0.0) || !(ratio > 1.0)) return;
-    std::vector<double> pos(pos_rm, pos_rm + 3 * nb);
-    std::vector<int32_t> rp, ci;                      // pattern of the current level (level 0: the caller's arrays)
-    const int32_t *crp = rowptr, *cci = colidx;
-    double cell = cell0;
-    int64_t n = nb;
-    for (int l = 0; l + 1 < max_levels && n > coarsest_rows; ++l) {
-        HierLevel L;
-        build_level(n, crp, cci, pos.data(), cell, L, /*with_galerkin_lists=*/l == 0, l == 0 ? part_bounds : nullptr, l == 0 ? nparts : 1);
-        if (L.n_coarse >= n) break;   // no coarsening at this cell size: stop
-        MlTransfer T;
-        if (l >= 1) {
-            build_transfer(n, crp, cci, L, l >= smooth_from, T);
-            rp = T.crow; ci = T.ccol;
-        } else {
-            rp = L.rowptr; ci = L.colidx;
+    // Built IN PLACE: a hierarchy object that is handed in again (the next set_job of the same context) keeps the
+    // capacity of every array, so a re-submitted mesh of similar size touches no fresh pages (first-touch page faults of
+    // several hundred MB were a third of the build).
+    size_t used = 0;
+    if (nb > 0 && cell0 > 0.0 && ratio > 1.0) {
+        const double *pos = pos_rm;
+        const int32_t *crp = rowptr, *cci = colidx;
+        double cell = cell0;
+        int64_t n = nb;
+        for (int l = 0; l + 1 < max_levels && n > coarsest_rows; ++l) {
+            if (H.agg.size() <= used) { H.agg.emplace_back(); H.xfer.emplace_back(); }
+            HierLevel &L = H.agg[used];
+            MlTransfer &T = H.xfer[used];
+            build_level(n, crp, cci, pos, cell, L, /*with_galerkin_lists=*/l == 0, l == 0 ? part_bounds : nullptr, l == 0 ? nparts : 1);
+            if (L.n_coarse >= n) break;   // no coarsening at this cell size: stop
+            if (l >= 1) {
+                build_transfer(n, crp, cci, L, l >= smooth_from, T);
+                crp = T.crow.data(); cci = T.ccol.data();
+            } else {
+                T = MlTransfer();
+                crp = L.rowptr.data(); cci = L.colidx.data();
+            }
+            pos = L.centroid.data(); n = L.n_coarse;
+            ++used;
+            cell *= ratio;
         }
-        crp = rp.data(); cci = ci.data();
-        pos = L.centroid; n = L.n_coarse;
-        H.agg.push_back(std::move(L));
-        H.xfer.push_back(std::move(T));
-        cell *= ratio;
     }
+    H.agg.resize(used); H.xfer.resize(used);
 }
 
 // ---- flat image of a hierarchy (several ranks: rank 0 builds it with every host core, the others receive it) ----

@@ -10,7 +10,7 @@ job = bench.make_job(wl)
 A = bench.flat_arrays(job, pin=True)
 V, E = job.nodes.shape[0], job.elements.shape[0]
 with mb.Context(device=0, tol=1e-8) as c:
-    for i in range(3):
+    for i in range(int(os.environ.get("MBFEA_SETJOBS", "3"))):
         print(f"===== set_job #{i}", file=sys.stderr, flush=True)
         t = time.perf_counter()
         c.set_job_raw(V, E, A["nodes_cm"], A["elems_cm"], A["normals_cm"], A["dims"], A["mat"], A["fixed"], A["fn"], A["fd"], A["fm"])
