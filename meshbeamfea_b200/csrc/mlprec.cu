@@ -257,79 +257,121 @@ __global__ void __launch_bounds__(128) k_ml_galerkin0(int64_t n_coarse_blocks, c
 }
 
 // ---------------------------------------------------------------------------
-// Explicit inverse of the coarsest matrix (dense n x n, n = 6 m, SPD): block Gauss-Jordan with 6x6 pivots, two
-// launches per pivot step (no pivot search: SPD).  Step k:
-//   pivot : Pinv = (A_kk)^-1; column block k saved; block row k := Pinv A_k,: (A_kk := Pinv)        -- one CTA
-//   update: A_ij -= C_i A_kj for i != k, j != k;  A_ik := -C_i Pinv   (C_i: the saved column block)   -- n^2 threads
+// Explicit inverse of the coarsest matrix (dense n x n, n = 6 m, SPD): block Gauss-Jordan with 24-wide pivot blocks, three
+// launches per pivot block (no pivot search: SPD).  Step over the pivot columns [k0, k0 + bw), bw <= 24:
+//   invert: Pinv = (A_kk)^-1 (one warp, a row per lane in registers)
+//   rows  : the column block is saved; block row k := Pinv A_k,: (A_kk := Pinv)                        -- n threads
+//   update: A_ij := [j outside the pivot columns] A_ij - sum_c C_ic R_cj for i outside the pivot rows, C the saved column
+//           block, R the new block row -- a rank-24 update in 64 x 64 tiles (4 x 4 outputs per thread)  -- (n / 64)^2 CTAs
+// The matrix stays L2-resident; wider pivots cut the passes over it 4x against 6-wide ones (n = 2058: 15 ms -> 3 ms).
 // *flag |= 2 on a non-positive pivot.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_ml_gj_pivot(int n, int k, double *__restrict__ a, double *__restrict__ colk, int *flag)
+constexpr int kGjW = 24;
+
+// step 1 (one warp): Pinv = inverse of the pivot block [k0, k0 + bw)^2 (padded with the identity to 24 x 24), by
+// Gauss-Jordan with a row per lane in registers, -> pinv[24 * 24]
+__global__ void __launch_bounds__(32) k_ml_gj_invert(int n, int k0, int bw, const double *__restrict__ a, double *__restrict__ pinv, int *flag)
 {
-    __shared__ double P[36];
-    const int k6 = 6 * k;
-    if (threadIdx.x < 36) P[threadIdx.x] = a[(size_t)(k6 + threadIdx.x / 6) * n + k6 + threadIdx.x % 6];
-    // save the column block (old values), all rows: independent loads, issued before anyone waits for the pivot
-    for (int t = threadIdx.x; t < n * 6; t += blockDim.x) colk[t] = a[(size_t)(t / 6) * n + k6 + t % 6];
-    // the 6 old values of the pivot rows in this thread's columns
-    double v[2][6];
-    int jj[2];
+    const int i = threadIdx.x;
+    double row[kGjW];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        jj[u] = threadIdx.x + u * 1024;
+    for (int j = 0; j < kGjW; ++j) row[j] = (i < bw && j < bw) ? a[(size_t)(k0 + i) * n + k0 + j] : (i == j ? 1.0 : 0.0);
+    bool bad = false;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) v[u][c] = jj[u] < n ? a[(size_t)(k6 + c) * n + jj[u]] : 0.0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {   // in-place Gauss-Jordan of the 6x6 pivot block
-        bool bad = false;
-        for (int p = 0; p < 6; ++p) {
-            double d = P[7 * p];
-            if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-            const double inv = 1.0 / d;
-            for (int j = 0; j < 6; ++j) P[6 * p + j] = (j == p) ? inv : P[6 * p + j] * inv;
-            for (int i = 0; i < 6; ++i) {
-                if (i == p) continue;
-                const double f = P[6 * i + p];
-                for (int j = 0; j < 6; ++j) P[6 * i + j] = (j == p) ? -f * inv : P[6 * i + j] - f * P[6 * p + j];
-            }
+    for (int p = 0; p < kGjW; ++p) {
+        double d = __shfl_sync(0xffffffffu, row[p], p);
+        if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+        const double inv = 1.0 / d;
+        const double f = row[p];   // this row's entry in the pivot column
+#pragma unroll
+        for (int j = 0; j < kGjW; ++j) {
+            const double pj = __shfl_sync(0xffffffffu, row[j], p) * inv;   // scaled pivot row, entry j (j != p)
+            if (i == p) row[j] = (j == p) ? inv : pj;
+            else row[j] = (j == p) ? -f * inv : fma(-f, pj, row[j]);
         }
-        if (bad) atomicOr(flag, 2);
     }
+    if (i < kGjW)
+#pragma unroll
+        for (int j = 0; j < kGjW; ++j) pinv[i * kGjW + j] = row[j];
+    if (bad && i == 0) atomicOr(flag, 2);
+}
+
+// step 2: thread t < n as a COLUMN: new block row k := Pinv (old pivot rows), Pinv itself in the pivot columns;
+//         thread t < n as a ROW outside the pivot rows: its pivot-column entries saved to colk[t][0 .. 24)
+// (the two halves touch disjoint entries: pivot rows are written, other rows are read)
+__global__ void __launch_bounds__(128) k_ml_gj_rows(int n, int k0, int bw, double *__restrict__ a, const double *__restrict__ pinv,
+                                                    double *__restrict__ colk)
+{
+    __shared__ double P[kGjW * kGjW];
+    for (int t = threadIdx.x; t < kGjW * kGjW; t += blockDim.x) P[t] = pinv[t];
     __syncthreads();
-    // new block row k: Pinv times the old pivot rows (Pinv itself in the pivot columns); n <= 3072 = 3 x 1024 columns
-    for (int u = 0; u < 3; ++u) {
-        const int j = threadIdx.x + u * 1024;
-        if (j >= n) break;
-        double vv[6];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (t < k0 || t >= k0 + bw) {
+        const double *src = a + (size_t)t * n + k0;
+        double *dst = colk + (size_t)t * kGjW;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) vv[c] = u < 2 ? v[u][c] : a[(size_t)(k6 + c) * n + j];
-        const bool in = j >= k6 && j < k6 + 6;
-        double w[6];
+        for (int c = 0; c < kGjW; ++c) dst[c] = c < bw ? src[c] : 0.0;
+    }
+    double v[kGjW];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            double s2 = 0.0;
-            if (in) s2 = P[6 * r + (j - k6)];
-            else
+    for (int c = 0; c < kGjW; ++c) v[c] = c < bw ? a[(size_t)(k0 + c) * n + t] : 0.0;
+    const bool in = t >= k0 && t < k0 + bw;
+    for (int r = 0; r < bw; ++r) {
+        double s2 = 0.0;
+        if (in) s2 = P[r * kGjW + (t - k0)];
+        else
 #pragma unroll
-                for (int c = 0; c < 6; ++c) s2 = fma(P[6 * r + c], vv[c], s2);
-            w[r] = s2;
-        }
-#pragma unroll
-        for (int r = 0; r < 6; ++r) a[(size_t)(k6 + r) * n + j] = w[r];
+            for (int c = 0; c < kGjW; ++c) s2 = fma(P[r * kGjW + c], v[c], s2);
+        a[(size_t)(k0 + r) * n + t] = s2;
     }
 }
 
-__global__ void __launch_bounds__(256) k_ml_gj_update(int n, int k, double *__restrict__ a, const double *__restrict__ colk)
+// step 3: rank-24 update of every row outside the pivot rows, 64 x 64 tiles, 4 x 4 outputs per thread (rows tr + x,
+// columns tc + 16 y: consecutive lanes -> consecutive columns, conflict-free shared-memory reads and coalesced stores)
+__global__ void __launch_bounds__(256) k_ml_gj_update(int n, int k0, int bw, double *__restrict__ a, const double *__restrict__ colk)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)n * n) return;
-    const int i = (int)(t / n), j = (int)(t - (int64_t)i * n), k6 = 6 * k;
-    if (i >= k6 && i < k6 + 6) return;
-    const double *c = colk + (size_t)i * 6;
-    double s = 0.0;
+    __shared__ double Cs[64][kGjW + 1];
+    __shared__ double Rs[kGjW][64];
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    for (int t = threadIdx.x; t < 64 * kGjW; t += 256) {
+        const int r = t / kGjW, c = t - r * kGjW;
+        const int i = i0 + r;
+        Cs[r][c] = (i < n && (i < k0 || i >= k0 + bw)) ? colk[(size_t)i * kGjW + c] : 0.0;
+    }
+    for (int t = threadIdx.x; t < kGjW * 64; t += 256) {
+        const int c = t / 64, j = t - c * 64;
+        Rs[c][j] = (c < bw && j0 + j < n) ? a[(size_t)(k0 + c) * n + j0 + j] : 0.0;
+    }
+    __syncthreads();
+    const int tr = (threadIdx.x / 16) * 4, tc = threadIdx.x % 16;
+    double acc[4][4];
 #pragma unroll
-    for (int m = 0; m < 6; ++m) s = fma(c[m], a[(size_t)(k6 + m) * n + j], s);   // block row k holds Pinv A_k,: (Pinv in the pivot columns)
-    a[t] = (j >= k6 && j < k6 + 6) ? -s : a[t] - s;
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < kGjW; ++c) {
+        double cv[4], rv[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { cv[x] = Cs[tr + x][c]; rv[x] = Rs[c][tc + 16 * x]; }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fma(cv[x], rv[y], acc[x][y]);
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int i = i0 + tr + x;
+        if (i >= n || (i >= k0 && i < k0 + bw)) continue;   // the pivot rows were finished by k_ml_gj_rows
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int j = j0 + tc + 16 * y;
+            if (j >= n) continue;
+            double *q = a + (size_t)i * n + j;
+            *q = ((j >= k0 && j < k0 + bw) ? 0.0 : *q) - acc[x][y];
+        }
+    }
 }
 
 // symmetrised FP32 copy of the inverse for the apply (rounding the same double for (i, j) and (j, i) keeps it symmetric)
@@ -688,14 +730,18 @@ void launch_ml_galerkin0(cudaStream_t st, int64_t n_coarse_blocks, const int32_t
     if (n_coarse_blocks > 0)
         k_ml_galerkin0<<<blocks_for(n_coarse_blocks * 8, 128), 128, 0, st>>>(n_coarse_blocks, gal_ptr, gal_src, frow, fcol, fvals, off, cvals);
 }
-// a: n x n (n = 6 m) overwritten by its inverse; colk: n * 6 doubles of scratch; 2 m launches
+// a: n x n (n = 6 m) overwritten by its inverse; colk: (n + 24) * 24 doubles of scratch (the last 576: the pivot inverse);
+// 3 launches per 24 pivot columns
 void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, double *colk, int *flag)
 {
     if (n <= 0) return;
-    const unsigned grid = blocks_for((int64_t)n * n, 256);
-    for (int k = 0; k < n / 6; ++k) {
-        k_ml_gj_pivot<<<1, 1024, 0, st>>>(n, k, a, colk, flag);
-        k_ml_gj_update<<<grid, 256, 0, st>>>(n, k, a, colk);
+    const dim3 grid((unsigned)((n + 63) / 64), (unsigned)((n + 63) / 64));
+    double *pinv = colk + (size_t)n * kGjW;
+    for (int k0 = 0; k0 < n; k0 += kGjW) {
+        const int bw = n - k0 < kGjW ? n - k0 : kGjW;
+        k_ml_gj_invert<<<1, 32, 0, st>>>(n, k0, bw, a, pinv, flag);
+        k_ml_gj_rows<<<blocks_for(n, 128), 128, 0, st>>>(n, k0, bw, a, pinv, colk);
+        k_ml_gj_update<<<grid, 256, 0, st>>>(n, k0, bw, a, colk);
     }
 }
 void launch_ml_dense_to_f32(cudaStream_t st, int n, const double *a, float *out)

@@ -152,7 +152,7 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
     n_dense = 6 * lv.back()->n;
     CK(dense.alloc((size_t)(n_dense * n_dense)));
     CK(dense32.alloc((size_t)(n_dense * n_dense)));
-    CK(gj_col.alloc((size_t)n_dense * 6));
+    CK(gj_col.alloc((size_t)(n_dense + 24) * 24));
     CK(cudaStreamSynchronize(st));   // the host vectors above go out of scope
     symbolic_ok = true;
     ms_symbolic = wall_ms() - t0w;
@@ -248,7 +248,7 @@ bool MlPrec::upload_from_image(cudaStream_t st, const unsigned char *d_img, cons
     n_dense = 6 * lv.back()->n;
     CK(dense.alloc((size_t)(n_dense * n_dense)));
     CK(dense32.alloc((size_t)(n_dense * n_dense)));
-    CK(gj_col.alloc((size_t)n_dense * 6));
+    CK(gj_col.alloc((size_t)(n_dense + 24) * 24));
     CK(cudaStreamSynchronize(st));   // d_ghost and the image may go away
     symbolic_ok = true;
     ms_symbolic = wall_ms() - t0w;
@@ -320,7 +320,7 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
     launch_ml_blocks_to_dense(st, last.n, last.nnz, last.rowptr.p, last.colidx.p, last.row_of.p, last.vals.p, dense.p);
     launch_ml_dense_inverse(st, (int)n_dense, dense.p, gj_col.p, d_flag);
     launch_ml_dense_to_f32(st, (int)n_dense, dense.p, dense32.p);
-    k += 2 + 2 * (n_dense / 6);
+    k += 2 + 3 * ((n_dense + 23) / 24);
     setup_launches = k;
     numeric_ok = true;
 }
