@@ -372,22 +372,6 @@ def main():
                 "traffic": traffic, "algorithmic_bytes_per_launch": st["bytes_spmv"], "ms_per_launch": ms_spmv,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
-    # ---- the same SpMV family on the full-row format (every block in its own row): more bytes, higher
-    #      fraction of peak, slower in wall time -- reported beside the production format for context ----
-    roofline_alt = None
-    if world == 1 and rank == 0 and not args.no_alt_roofline:
-        alt = mb.Context(device=local, tol=args.tol, storage=1)
-        alt.set_job_raw(V, E, A["nodes_cm"], A["elems_cm"], A["normals_cm"], A["dims"], A["mat"], A["fixed"],
-                        A["fn"], A["fd"], A["fm"])
-        if alt.stats()["n_components"] == 0:
-            alt.assemble()
-            ms_alt = alt.time_spmv(kernel=1, warmup=3, reps=50)
-            b_alt = alt.stats()["bytes_spmv"]
-            roofline_alt = {"format": "full rows (storage=1), k_spmv_rowthread<false>", "achieved": b_alt / (ms_alt * 1e-3) / 1e9,
-                            "peak": peak, "unit": "GB/s", "frac": b_alt / (ms_alt * 1e-3) / 1e9 / peak,
-                            "algorithmic_bytes_per_launch": b_alt, "ms_per_launch": ms_alt}
-        alt.close()
-
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -418,6 +402,23 @@ def main():
                "ms_set_job": 1e3 * parts[0] / args.steps, "ms_execute": 1e3 * parts[1] / args.steps,
                "ms_fetch_results": 1e3 * parts[2] / args.steps,
                "ms_host_prep": s2["ms_host_prep"], "ms_h2d_incl_plan": s2["ms_h2d"], "ms_d2h": s2["ms_d2h"]}
+
+    # (after the end-to-end loop: a second context's host allocations in between slowed the next set_job by 200 ms)
+    # ---- the same SpMV family on the full-row format (every block in its own row): more bytes, higher
+    #      fraction of peak, slower in wall time -- reported beside the production format for context ----
+    roofline_alt = None
+    if world == 1 and rank == 0 and not args.no_alt_roofline:
+        alt = mb.Context(device=local, tol=args.tol, storage=1)
+        alt.set_job_raw(V, E, A["nodes_cm"], A["elems_cm"], A["normals_cm"], A["dims"], A["mat"], A["fixed"],
+                        A["fn"], A["fd"], A["fm"])
+        if alt.stats()["n_components"] == 0:
+            alt.assemble()
+            ms_alt = alt.time_spmv(kernel=1, warmup=3, reps=50)
+            b_alt = alt.stats()["bytes_spmv"]
+            roofline_alt = {"format": "full rows (storage=1), k_spmv_rowthread<false>", "achieved": b_alt / (ms_alt * 1e-3) / 1e9,
+                            "peak": peak, "unit": "GB/s", "frac": b_alt / (ms_alt * 1e-3) / 1e9 / peak,
+                            "algorithmic_bytes_per_launch": b_alt, "ms_per_launch": ms_alt}
+        alt.close()
 
     # ---- side records: the same job with block-Jacobi alone, and round 1's headline mesh ----
     def side_run(job2, A2, **kw):
