@@ -1078,15 +1078,39 @@ int mbfea_assemble(mbfea_ctx *c)
         c->assembled = true; c->solved = c->recovered = false;
         if (flag & 1) return fail(c, MBFEA_ESINGULAR,
                                   "a diagonal 6x6 block is not positive definite (isolated vertex, zero-length or zero-stiffness beam)");
-        if (flag & 2) return fail(c, MBFEA_ESINGULAR, "the coarsest matrix of the multilevel preconditioner is not positive definite");
+        if (flag & 2) {
+            if (c->opt.precond != 0)
+                return fail(c, MBFEA_ESINGULAR, "the coarsest matrix of the multilevel preconditioner is not positive definite");
+            c->use_ml = false;   // auto: block-Jacobi for this job (the flag was all-reduced: every rank decides alike)
+            c->stats.precond = 1; c->stats.ml_levels = 0;
+            drop_graph(c);
+        }
         return MBFEA_OK;
     });
 }
+
+static int solve_once(mbfea_ctx *c);
 
 int mbfea_solve(mbfea_ctx *c)
 {
     if (int rc = need_job(c)) return rc;
     if (!c->assembled) return fail(c, MBFEA_ESTATE, "solve before assemble");
+    int rc = solve_once(c);
+    // options.precond = 0 (auto) promised a solve, not a particular preconditioner: if the multilevel-preconditioned
+    // iteration breaks down or stalls (every rank sees the same scalars, so every rank decides alike), fall back to the
+    // block-Jacobi iteration once
+    if ((rc == MBFEA_ESINGULAR || rc == MBFEA_ENOCONV) && c->use_ml && c->opt.precond == 0) {
+        if (c->opt.verbose) std::fprintf(stderr, "[mbfea] rank %d: multilevel PCG failed (%s); retrying with block-Jacobi\n", c->opt.rank, c->err.c_str());
+        c->use_ml = false;
+        c->stats.precond = 1; c->stats.ml_levels = 0;
+        drop_graph(c);
+        rc = solve_once(c);
+    }
+    return rc;
+}
+
+static int solve_once(mbfea_ctx *c)
+{
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         const int64_t nb = c->nb();

@@ -453,11 +453,10 @@ __global__ void __launch_bounds__(128) k_assemble(int64_t nnzb, const int32_t *_
                                                   const ElemGeom *__restrict__ geom, double *__restrict__ vals)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nnzb) return;
     double acc[36];
 #pragma unroll
     for (int j = 0; j < 36; ++j) acc[j] = 0.0;
-    const int32_t c0 = __ldg(contrib_ptr + k), c1 = __ldg(contrib_ptr + k + 1);
+    const int32_t c0 = k < nnzb ? __ldg(contrib_ptr + k) : 0, c1 = k < nnzb ? __ldg(contrib_ptr + k + 1) : 0;
     for (int32_t c = c0; c < c1; ++c) {
         const int32_t code = __ldg(contrib + c);
         Frame f; Stiff s;
@@ -471,9 +470,24 @@ __global__ void __launch_bounds__(128) k_assemble(int64_t nnzb, const int32_t *_
             for (int j = 0; j < 6; ++j) acc[6 * r + j] = ADD(acc[6 * r + j], row[j]);
         }
     }
-    double2 *o = reinterpret_cast<double2 *>(vals + k * 36);
+    // the CTA's 128 blocks are one contiguous 36 KB span of `vals`: stage them in shared memory (row stride 37: no bank
+    // conflicts) and store the span with consecutive threads on consecutive 16-byte chunks -- a thread storing its own
+    // 288 bytes touches 32 different sectors per store instruction of the warp
+    __shared__ double stage[128 * 37];
+    if (k < nnzb) {
 #pragma unroll
-    for (int j = 0; j < 18; ++j) o[j] = make_double2(acc[2 * j], acc[2 * j + 1]);
+        for (int j = 0; j < 36; ++j) stage[threadIdx.x * 37 + j] = acc[j];
+    }
+    __syncthreads();
+    const int64_t k0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t live = nnzb - k0 < 128 ? nnzb - k0 : 128;   // blocks of this CTA
+    double2 *o = reinterpret_cast<double2 *>(vals + k0 * 36);
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+        const int c = threadIdx.x + 128 * j;          // 16-byte chunk of the span
+        const int b = c / 18, w = (c - b * 18) * 2;   // block, first of its two entries
+        if (b < live) o[c] = make_double2(stage[b * 37 + w], stage[b * 37 + w + 1]);
+    }
 }
 
 void launch_assemble(cudaStream_t st, int64_t nnzb, const int32_t *contrib_ptr, const int32_t *contrib,
