@@ -49,9 +49,9 @@ struct mbfea_ctx {
     bool have_job = false, assembled = false, solved = false, recovered = false;
     int64_t V = 0, E = 0, F = 0;
     HostPlan plan;
-    std::vector<double> props_host;
-    std::vector<int32_t> tile_row_host;    // TMA tiles over the full pattern (K, parity tap)
-    std::vector<int32_t> tile_row_s_host;  // TMA tiles over the solver format (full-row storage only)
+    hvec<float> props_host;              // EA, EIz, EIy, GJ per beam: float values in the reference, uploaded as such
+    hvec<int32_t> tile_row_host;    // TMA tiles over the full pattern (K, parity tap)
+    hvec<int32_t> tile_row_s_host;  // TMA tiles over the solver format (full-row storage only)
     bool tma_ok = false;       // pattern fits the TMA tile geometry
     bool tma_prepared = false;
 
@@ -61,7 +61,8 @@ struct mbfea_ctx {
     DevBuf<ElemGeom> geom;
     DevBuf<int32_t> free_index, free_canon, fixed;   // free_canon: the K3 scan (canonical); free_index: composed with the internal renumbering
     // staging for set_job (kept: a re-submitted mesh of the same size costs no cudaMalloc/cudaFree)
-    DevBuf<double> stg_nodes, stg_normals, stg_props;
+    DevBuf<double> stg_nodes, stg_normals;
+    DevBuf<float> stg_props;
     DevBuf<int32_t> stg_elems, stg_scratch;
     // device: pattern
     DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, tile_row_s, send_rows;
@@ -101,6 +102,9 @@ struct mbfea_ctx {
     MlPrec ml;
     bool use_ml = false;
     MlHierarchy ml_host;   // host half of the hierarchy, kept between jobs: its arrays keep their capacity
+    HostPlan ml_gplan;                // several ranks, rank 0: pattern of the whole reduced system (the hierarchy is global)
+    MlImageLayout ml_layout;          // several ranks, rank 0: where every hierarchy array sits in the broadcast image
+    DevBuf<unsigned char> ml_dimg;    // several ranks: the device image
     std::vector<double> ml_pos;
 
     // PCG graph cache
@@ -152,8 +156,8 @@ void upload(mbfea_ctx *c, DevBuf<T> &d, const T *h, size_t n)
     if (n) CK(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, c->st));
 }
 
-template <class T>
-void upload(mbfea_ctx *c, DevBuf<T> &d, const std::vector<T> &h) { upload(c, d, h.data(), h.size()); }
+template <class T, class A>
+void upload(mbfea_ctx *c, DevBuf<T> &d, const std::vector<T, A> &h) { upload(c, d, h.data(), h.size()); }
 
 void drop_graph(mbfea_ctx *c)
 {
@@ -665,6 +669,7 @@ int mbfea_create(mbfea_ctx **out, const mbfea_options *opts)
         return MBFEA_OK;
     });
     if (rc != MBFEA_OK) return rc;
+    host_arrays_pin_on(c->device);   // from now on the host arrays that travel are page-locked (hostmem.cpp)
     *out = c.release();
     return MBFEA_OK;
 }
@@ -771,29 +776,58 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         std::memset(&c->stats, 0, sizeof c->stats);
         const double t0 = now_ms();
         c->V = V; c->E = E; c->F = F;
+        const bool ptrace = std::getenv("MBFEA_PREP_TRACE") != nullptr;
+        double tl = t0, host_ms = 0.0;
+        auto lap = [&](const char *what) {
+            if (!ptrace) return;
+            cudaStreamSynchronize(c->st);
+            const double n = now_ms();
+            std::fprintf(stderr, "[mbfea set_job] %-28s %8.2f ms\n", what, n - tl);
+            tl = n;
+        };
+        // The host arrays that travel are page-locked (hostmem.cpp), so every upload below is asynchronous: the device
+        // copies one array while the host builds the next.
         c->props_host.resize((size_t)4 * E);
         derive_props(E, dims_bh, mat_nuE, c->props_host.data());
+        host_ms += now_ms() - t0;
+        // mesh -> device, repacked into aligned records; K3 (canonical map)
+        {
+            DevBuf<double> &d_nodes = c->stg_nodes, &d_normals = c->stg_normals;
+            DevBuf<float> &d_props = c->stg_props;
+            DevBuf<int32_t> &d_elems = c->stg_elems, &d_scratch = c->stg_scratch;
+            upload(c, d_nodes, nodes_cm, (size_t)3 * V);
+            upload(c, d_elems, elems_cm, (size_t)2 * E);
+            upload(c, d_normals, normals_cm, (size_t)3 * E);
+            upload(c, d_props, c->props_host);
+            upload(c, c->fixed, fixed, (size_t)F);
+            CK(c->node4.alloc((size_t)V));
+            CK(c->rec.alloc((size_t)E));
+            CK(c->geom.alloc((size_t)E));
+            CK(c->free_index.alloc((size_t)V));
+            CK(c->free_canon.alloc((size_t)V));
+            CK(d_scratch.alloc((size_t)V + (size_t)V / 1024 + 2));
+            launch_pack_nodes(c->st, V, d_nodes.p, c->node4.p);
+            launch_pack_elems(c->st, E, d_elems.p, d_normals.p, d_props.p, c->rec.p);
+            launch_free_map(c->st, V, F, c->fixed.p, c->free_canon.p, d_scratch.p);
+            lap("mesh upload + pack + K3");
+        }
+        const double tp0 = now_ms();
         // internal renumbering: 0 auto (only when the input vertex order has no locality), 1 never, 2 always
         const int reorder = c->opt.reorder == 1 ? 0 : (c->opt.reorder == 2 ? 2 : (c->opt.reorder == 3 ? 3 : 1));
         build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan, reorder, nodes_cm);
-        // solver format: symmetric-half storage unless full rows are asked for (the TMA kernel
-        // streams whole rows and has no transposed-reference path)
+        // preconditioner: multilevel on one rank for a single large mesh (auto) or on request
         if (c->opt.batch_mode != 1) find_components(c->plan, 1024, 32);
         else { c->plan.comp_ptr.clear(); c->plan.comp_max_rows = 0; }
         const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
-        const bool half = !batched && (c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2));
-        build_solver_format(c->plan, half);
-        // preconditioner: multilevel on one rank for a single large mesh (auto) or on request
         c->use_ml = false;
         c->ml.reset();
         const bool ml_possible = !batched && c->plan.nb_global >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
         const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
         // The host half of the multilevel hierarchy needs only the block pattern and the vertex positions: it runs on its own
-        // thread while this one builds the solver format and uploads the mesh and the plan.  (Several ranks: rank 0 builds it
+        // thread while this one builds the solver format and uploads the plan.  (Several ranks: rank 0 builds it
         // for everybody -- the ranks of a box share the host cores, W redundant builds would each get 1 / W of them.)
         struct MlHostJob {
             double mean_len = 0.0;
-            std::vector<unsigned char> img;   // several ranks, rank 0: flat image for the broadcast
             bool failed = false;
             double ms = 0.0;
         } mlh;
@@ -814,6 +848,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         if (ml_build_here) {
                 ml_thread = std::thread([&, V, E, F]() {
                     try {
+                        cudaSetDevice(c->device);   // page-locked allocations of this thread belong to this context's device
                         const double tw = now_ms();
                         const int64_t nbg = c->plan.nb_global;
                         const int W = c->opt.world;
@@ -847,10 +882,10 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                         if (W == 1) {
                             c->ml.build_hierarchy_host(nbg, c->plan.rowptr.data(), c->plan.colidx.data(), c->ml_pos.data(), mlh.mean_len, 1, c->ml_host);
                         } else {
-                            HostPlan G;
+                            HostPlan &G = c->ml_gplan;   // kept between jobs (page-locked arrays: allocation is expensive)
                             build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
                             c->ml.build_hierarchy_host(nbg, G.rowptr.data(), G.colidx.data(), c->ml_pos.data(), mlh.mean_len, W, c->ml_host);
-                            if (!ml_image_pack(c->ml_host, W, nbg, G.rowptr.data(), mlh.img)) mlh.failed = true;
+                            if (!ml_image_layout(c->ml_host, W, nbg, G.rowptr.data(), c->ml_layout)) mlh.failed = true;
                         }
                         mlh.ms = now_ms() - tw;
                     } catch (...) {
@@ -859,68 +894,36 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                 });
             }
         };
-        // started here, next to the rest of the host prep (MBFEA_ML_THREAD_LATE=1: only after it, next to the device uploads).
-        // Measured on the 119^3 lattice: set_job 180 ms against 280 ms, once the hierarchy arrays keep their capacity
-        // between jobs -- with fresh allocations on both sides the two thread pools serialised on page faults instead.
+        // started as soon as the block pattern exists, next to the rest of the host prep (MBFEA_ML_THREAD_LATE=1: only
+        // after the solver format).  The hierarchy arrays keep their capacity between jobs; with fresh allocations on
+        // both sides the two thread pools serialised on page faults instead.
         const bool ml_early = [] { const char *e = std::getenv("MBFEA_ML_THREAD_LATE"); return !(e && *e == '1'); }();
         if (ml_early) start_ml_thread();
-        build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
-        build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
-        c->tma_ok = true;
-        for (size_t t = 0; t + 1 < c->tile_row_host.size(); ++t)
-            if (c->plan.rowptr[c->tile_row_host[t + 1]] - c->plan.rowptr[c->tile_row_host[t]] > kTmaCapBlocks)
-                c->tma_ok = false;  // a single row longer than a stage: row-thread kernel only
-        const double t1 = now_ms();
-        c->stats.ms_host_prep = t1 - t0;
-        const bool ptrace = std::getenv("MBFEA_PREP_TRACE") != nullptr;
-        double tl = t1;
-        auto lap = [&](const char *what) {
-            if (!ptrace) return;
-            cudaStreamSynchronize(c->st);
-            const double n = now_ms();
-            std::fprintf(stderr, "[mbfea set_job] %-28s %8.2f ms\n", what, n - tl);
-            tl = n;
-        };
-
-        if (!ml_early) start_ml_thread();
+        host_ms += now_ms() - tp0;
         const int64_t nb = c->nb(), ng = c->ng(), nnzb = c->plan.nnzb();
-        // mesh -> device, repacked into aligned records
-        {
-            DevBuf<double> &d_nodes = c->stg_nodes, &d_normals = c->stg_normals, &d_props = c->stg_props;
-            DevBuf<int32_t> &d_elems = c->stg_elems, &d_scratch = c->stg_scratch;
-            upload(c, d_nodes, nodes_cm, (size_t)3 * V);
-            upload(c, d_elems, elems_cm, (size_t)2 * E);
-            upload(c, d_normals, normals_cm, (size_t)3 * E);
-            upload(c, d_props, c->props_host);
-            upload(c, c->fixed, fixed, (size_t)F);
-            CK(c->node4.alloc((size_t)V));
-            CK(c->rec.alloc((size_t)E));
-            CK(c->geom.alloc((size_t)E));
-            CK(c->free_index.alloc((size_t)V));
-            CK(c->free_canon.alloc((size_t)V));
-            CK(d_scratch.alloc((size_t)V + (size_t)V / 1024 + 2));
-            launch_pack_nodes(c->st, V, d_nodes.p, c->node4.p);
-            launch_pack_elems(c->st, E, d_elems.p, d_normals.p, d_props.p, c->rec.p);
-            launch_free_map(c->st, V, F, c->fixed.p, c->free_canon.p, d_scratch.p);  // K3 (canonical map)
-            if (c->plan.perm.empty()) {
-                CK(cudaMemcpyAsync(c->free_index.p, c->free_canon.p, (size_t)V * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->st));
-            } else {
-                DevBuf<int32_t> d_perm;
-                upload(c, d_perm, c->plan.perm);
-                launch_apply_perm(c->st, V, c->free_canon.p, d_perm.p, c->free_index.p);
-                CK(cudaStreamSynchronize(c->st));
-            }
+        // the reduced numbering the kernels use: K3's map, composed with the internal renumbering when there is one
+        if (c->plan.perm.empty()) {
+            CK(cudaMemcpyAsync(c->free_index.p, c->free_canon.p, (size_t)V * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->st));
+        } else {
+            DevBuf<int32_t> d_perm;
+            upload(c, d_perm, c->plan.perm);
+            launch_apply_perm(c->st, V, c->free_canon.p, d_perm.p, c->free_index.p);
             CK(cudaStreamSynchronize(c->st));
-            lap("mesh upload + pack + K3");
         }
-        lap("free temporaries");
         upload(c, c->rowptr, c->plan.rowptr);
         upload(c, c->colidx, c->plan.colidx);
         upload(c, c->diag_idx, c->plan.diag_idx);
         upload(c, c->contrib_ptr, c->plan.contrib_ptr);
         upload(c, c->contrib, c->plan.contrib);
-        upload(c, c->tile_row, c->tile_row_host);
-        upload(c, c->tile_row_s, c->tile_row_s_host);
+        upload(c, c->send_rows, c->plan.send_rows);
+        lap("pattern upload");
+        // solver format: symmetric-half storage unless full rows are asked for (the TMA kernel
+        // streams whole rows and has no transposed-reference path)
+        const double tp1 = now_ms();
+        const bool half = !batched && (c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2));
+        build_solver_format(c->plan, half);
+        if (!ml_early) start_ml_thread();
+        host_ms += now_ms() - tp1;
         upload(c, c->uptr, c->plan.uptr);
         upload(c, c->ucol, c->plan.ucol);
         upload(c, c->usrc, c->plan.usrc);
@@ -928,14 +931,25 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         upload(c, c->lcol, c->plan.lcol);
         upload(c, c->lofs, c->plan.lofs);
         upload(c, c->ilv_base, c->plan.tile_base);
-        upload(c, c->send_rows, c->plan.send_rows);
+        const double tp2 = now_ms();
+        build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
+        build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
+        c->tma_ok = true;
+        for (size_t t = 0; t + 1 < c->tile_row_host.size(); ++t)
+            if (c->plan.rowptr[c->tile_row_host[t + 1]] - c->plan.rowptr[c->tile_row_host[t]] > kTmaCapBlocks)
+                c->tma_ok = false;  // a single row longer than a stage: row-thread kernel only
+        host_ms += now_ms() - tp2;
+        upload(c, c->tile_row, c->tile_row_host);
+        upload(c, c->tile_row_s, c->tile_row_s_host);
         if (batched) {
             const size_t nc = c->plan.comp_ptr.size() - 1;
             upload(c, c->comp_ptr, c->plan.comp_ptr);
             CK(c->comp_iters.alloc(nc)); CK(c->comp_status.alloc(nc));
             CK(c->comp_rr.alloc(nc)); CK(c->comp_ff.alloc(nc));
         }
-        lap("plan upload");
+        lap("solver format upload");
+        c->stats.ms_host_prep = host_ms;
+        const double t1 = t0 + host_ms;   // ms_h2d below = everything that is not host preparation
         CK(c->sendbuf.alloc((size_t)36 * c->plan.send_rows.size()));
         CK(c->vals.alloc((size_t)nnzb * 36));
         // symmetric-half: interleaved tiles (16-byte units, padded to the longest row of each tile)
@@ -969,14 +983,19 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                 // rank 0's flat image goes through the GPUs to everybody; each rank then uploads its own share of level 0 and
                 // the replicated coarse levels
                 const int W = c->opt.world;
-                int64_t bytes = mlh.failed ? 0 : (int64_t)mlh.img.size();
+                int64_t bytes = (mlh.failed || c->opt.rank != 0) ? 0 : c->ml_layout.hd.total_bytes;
                 std::vector<int64_t> all((size_t)W);
                 allgather_host(c, &bytes, all.data(), sizeof bytes);
                 bytes = all[0];
                 if (bytes > 0) {
-                    DevBuf<unsigned char> dimg;
+                    DevBuf<unsigned char> &dimg = c->ml_dimg;   // kept between jobs
                     CK(dimg.alloc((size_t)bytes));
-                    if (c->opt.rank == 0) CK(cudaMemcpyAsync(dimg.p, mlh.img.data(), (size_t)bytes, cudaMemcpyHostToDevice, c->st));
+                    if (c->opt.rank == 0) {
+                        // the image is assembled on the device: header + every (page-locked) hierarchy array at its offset
+                        CK(cudaMemcpyAsync(dimg.p, &c->ml_layout.hd, sizeof(MlImageHeader), cudaMemcpyHostToDevice, c->st));
+                        for (const MlImageLayout::Part &pt : c->ml_layout.parts)
+                            CK(cudaMemcpyAsync(dimg.p + pt.at, pt.p, pt.bytes, cudaMemcpyHostToDevice, c->st));
+                    }
                     NK(c->nc->Broadcast(dimg.p, dimg.p, (size_t)bytes / 8, nccl::kInt64, 0, c->comm, c->st));
                     MlImageHeader hd;
                     CK(cudaMemcpyAsync(&hd, dimg.p, sizeof hd, cudaMemcpyDeviceToHost, c->st));
@@ -1550,7 +1569,7 @@ int mbfea_get_props(mbfea_ctx *c, double *props4)
 {
     if (int rc = need_job(c)) return rc;
     if (!props4) return fail(c, MBFEA_EARG, "NULL");
-    std::memcpy(props4, c->props_host.data(), c->props_host.size() * sizeof(double));
+    for (size_t i = 0; i < c->props_host.size(); ++i) props4[i] = (double)c->props_host[i];
     return MBFEA_OK;
 }
 
@@ -1617,7 +1636,7 @@ int mbfea_get_bsr(mbfea_ctx *c, int64_t *rowptr, int32_t *colidx, double *vals, 
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         const int64_t nb = c->nb(), nnzb = c->plan.nnzb(), r0 = c->plan.row_begin;
-        const std::vector<int32_t> &rp = c->plan.rowptr, &ci = c->plan.colidx;
+        const hvec<int32_t> &rp = c->plan.rowptr, &ci = c->plan.colidx;
         std::vector<double> v;
         if (vals) {
             v.resize((size_t)nnzb * 36);
@@ -1899,7 +1918,9 @@ int mbfea_host_validate(int64_t V, int64_t E, const int32_t *elems_cm, const flo
 int mbfea_host_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4)
 {
     if (E < 0 || (E > 0 && (!dims_bh || !mat_nuE || !props4))) return MBFEA_EARG;
-    derive_props(E, dims_bh, mat_nuE, props4);
+    std::vector<float> pf((size_t)4 * (size_t)E);
+    derive_props(E, dims_bh, mat_nuE, pf.data());
+    for (size_t i = 0; i < pf.size(); ++i) props4[i] = (double)pf[i];
     return MBFEA_OK;
 }
 
@@ -1958,7 +1979,7 @@ int mbfea_host_solver_format(int64_t V, int64_t E, const double *nodes_cm, const
     sizes[4] = P.tile_base.empty() ? 0 : P.tile_base.back(); sizes[5] = P.balanced ? 1 : 0; sizes[6] = longest;
     sizes[7] = P.perm.empty() ? 0 : 1;
     if (!P.sym_half) return MBFEA_EARG;   // value array beyond 2^31 units: full rows (not reachable at host-test sizes)
-    auto put = [](int32_t *dst, const std::vector<int32_t> &src) { if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(int32_t)); };
+    auto put = [](int32_t *dst, const auto &src) { if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(int32_t)); };
     put(uptr, P.uptr); put(ucol, P.ucol); put(lptr, P.lptr); put(lcol, P.lcol); put(lofs, P.lofs); put(tile_base, P.tile_base);
     if (perm) for (int64_t i = 0; i < P.nb_global; ++i) perm[i] = P.perm.empty() ? (int32_t)i : P.perm[(size_t)i];
     return MBFEA_OK;

@@ -224,7 +224,7 @@ static void build_transfer(int64_t n, const int32_t *rowptr, const int32_t *coli
         void begin(int32_t row) { stamp = row; out.clear(); }
         void add(int32_t c) { if (mark[(size_t)c] != stamp) { mark[(size_t)c] = stamp; out.push_back(c); } }
     };
-    auto build_rows = [&](int64_t rows, int64_t ncols, int64_t min_per_thread, std::vector<int32_t> &rp, std::vector<int32_t> &ci, auto &&gen) {
+    auto build_rows = [&](int64_t rows, int64_t ncols, int64_t min_per_thread, hvec<int32_t> &rp, hvec<int32_t> &ci, auto &&gen) {
         rp.assign((size_t)rows + 1, 0);
         // every thread generates the rows of its contiguous range once, into one flat buffer; after the prefix sum the
         // buffer is exactly the slice [rp[first row], rp[last row + 1]) of the column array
@@ -332,11 +332,11 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
 }
 
 // ---- flat image of a hierarchy (several ranks: rank 0 builds it with every host core, the others receive it) ----
-bool ml_image_pack(const MlHierarchy &H, int world, int64_t nbg, const int32_t *fine_rowptr, std::vector<unsigned char> &out)
+bool ml_image_layout(const MlHierarchy &H, int world, int64_t nbg, const int32_t *fine_rowptr, MlImageLayout &lay)
 {
     const size_t L = H.levels();
     if (L == 0 || L > (size_t)kMlImageMaxLevels || world < 1 || world > kMlImageMaxWorld) return false;
-    MlImageHeader hd;
+    MlImageHeader &hd = lay.hd;
     std::memset(&hd, 0, sizeof hd);
     hd.magic = kMlImageMagic; hd.levels = (int64_t)L; hd.world = world; hd.nbg = nbg; hd.fine_nnz = fine_rowptr[nbg];
     const HierLevel &h0 = H.agg[0];
@@ -356,14 +356,15 @@ bool ml_image_pack(const MlHierarchy &H, int world, int64_t nbg, const int32_t *
         hd.galptr_at[q] = h0.gal_ptr[(size_t)hd.blk_begin[q]];
     }
     // diagonal positions of the level-1 pattern
-    std::vector<int32_t> diag1((size_t)h0.n_coarse);
+    hvec<int32_t> &diag1 = lay.diag1;
+    diag1.resize((size_t)h0.n_coarse);
     for (int64_t I = 0; I < h0.n_coarse; ++I)
         diag1[(size_t)I] = (int32_t)(std::lower_bound(h0.colidx.begin() + h0.rowptr[(size_t)I], h0.colidx.begin() + h0.rowptr[(size_t)I + 1],
                                                       (int32_t)I) - h0.colidx.begin());
     struct Src { const void *p; size_t bytes; int64_t cnt; };
     std::vector<std::vector<Src>> src(L);
-    auto vi = [](const std::vector<int32_t> &v) { return Src{v.data(), v.size() * sizeof(int32_t), (int64_t)v.size()}; };
-    auto vd = [](const std::vector<double> &v) { return Src{v.data(), v.size() * sizeof(double), (int64_t)v.size()}; };
+    auto vi = [](const auto &v) { return Src{v.data(), v.size() * sizeof(int32_t), (int64_t)v.size()}; };
+    auto vd = [](const auto &v) { return Src{v.data(), v.size() * sizeof(double), (int64_t)v.size()}; };
     src[0] = {vi(h0.agg), vd(h0.off), vi(h0.agg_ptr), vi(h0.agg_rows), vi(h0.rowptr), vi(h0.colidx), vi(diag1), vi(h0.gal_ptr), vi(h0.gal_src)};
     for (size_t l = 1; l < L; ++l) {
         const HierLevel &a = H.agg[l];
@@ -372,25 +373,32 @@ bool ml_image_pack(const MlHierarchy &H, int world, int64_t nbg, const int32_t *
                   vi(t.crow), vi(t.ccol), vi(t.cdiag)};
     }
     size_t at = (sizeof(MlImageHeader) + 15) & ~(size_t)15;
+    lay.parts.clear();
     for (size_t l = 0; l < L; ++l) {
         hd.lv[l].n_fine = H.agg[l].n_fine; hd.lv[l].n_coarse = H.agg[l].n_coarse;
         hd.lv[l].smoothed = (l >= 1 && H.xfer[l].smoothed) ? 1 : 0;
         for (size_t k = 0; k < src[l].size(); ++k) {
             hd.lv[l].off[k] = (int64_t)at; hd.lv[l].cnt[k] = src[l][k].cnt;
+            if (src[l][k].bytes) lay.parts.push_back(MlImageLayout::Part{src[l][k].p, src[l][k].bytes, at});
             at += (src[l][k].bytes + 15) & ~(size_t)15;
         }
     }
     hd.total_bytes = (int64_t)at;
-    out.resize(at);   // one allocation, every array copied once (in parallel)
-    std::memcpy(out.data(), &hd, sizeof hd);
+    return true;
+}
+
+bool ml_image_pack(const MlHierarchy &H, int world, int64_t nbg, const int32_t *fine_rowptr, std::vector<unsigned char> &out)
+{
+    MlImageLayout lay;
+    if (!ml_image_layout(H, world, nbg, fine_rowptr, lay)) return false;
+    out.resize((size_t)lay.hd.total_bytes);   // one allocation, every array copied once (in parallel)
+    std::memcpy(out.data(), &lay.hd, sizeof lay.hd);
     std::vector<std::thread> th;
-    for (size_t l = 0; l < L; ++l)
-        for (size_t k = 0; k < src[l].size(); ++k) {
-            const Src sk = src[l][k];
-            unsigned char *dst = out.data() + hd.lv[l].off[k];
-            if (sk.bytes > (size_t)(8 << 20)) th.emplace_back([=] { std::memcpy(dst, sk.p, sk.bytes); });
-            else if (sk.bytes) std::memcpy(dst, sk.p, sk.bytes);
-        }
+    for (const MlImageLayout::Part &pt : lay.parts) {
+        unsigned char *dst = out.data() + pt.at;
+        if (pt.bytes > (size_t)(8 << 20)) th.emplace_back([=] { std::memcpy(dst, pt.p, pt.bytes); });
+        else std::memcpy(dst, pt.p, pt.bytes);
+    }
     for (auto &x : th) x.join();
     return true;
 }
@@ -408,7 +416,7 @@ void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, c
         HierLevel L;
         build_level(n, rp.data(), ci.data(), pos.data(), cell, L);
         if (L.n_coarse >= n) break;   // no coarsening at this cell size (isolated points): stop
-        pos = L.centroid; rp = L.rowptr; ci = L.colidx; n = L.n_coarse;
+        pos = L.centroid; rp.assign(L.rowptr.begin(), L.rowptr.end()); ci.assign(L.colidx.begin(), L.colidx.end()); n = L.n_coarse;
         H.levels.push_back(std::move(L));
         cell *= ratio;
     }

@@ -96,7 +96,7 @@ int validate_job(int64_t V, int64_t E, const int32_t *elems_cm, const float *dim
 // promotions: std::pow(float,int) -> double, float*double -> double, result
 // narrowed to float on assignment [REF src/beamsimulator.cpp:173-188].
 // ---------------------------------------------------------------------------
-static inline void props_one(float b, float h, float nu, float Egpa, double *out)
+static inline void props_one(float b, float h, float nu, float Egpa, float *out)
 {
     const float crossArea = b * h;
     const float I2 = static_cast<float>(b * std::pow(static_cast<double>(h), 3) / 12);
@@ -141,12 +141,12 @@ static void parallel_ranges(int64_t n, int64_t min_per_thread, Fn fn)
     for (auto &x : th) x.join();
 }
 
-void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4)
+void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, float *props4)
 {
     parallel_ranges(E, 1 << 16, [=](int64_t lo, int64_t hi, int) {
         // most meshes repeat one section: memoise the last one
         float lb = NAN, lh = NAN, ln = NAN, le = NAN;
-        double last[4] = {0, 0, 0, 0};
+        float last[4] = {0, 0, 0, 0};
         for (int64_t e = lo; e < hi; ++e) {
             const float b = dims_bh[2 * e], h = dims_bh[2 * e + 1], nu = mat_nuE[2 * e], Eg = mat_nuE[2 * e + 1];
             if (!(b == lb && h == lh && nu == ln && Eg == le)) {
@@ -684,8 +684,8 @@ void find_components(HostPlan &P, int32_t max_rows, int32_t min_components)
     P.comp_max_rows = mx;
 }
 
-void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
-                 std::vector<int32_t> &tile_row)
+void build_tiles(const hvec<int32_t> &rowptr, int cap_blocks, int max_rows,
+                 hvec<int32_t> &tile_row)
 {
     const int64_t nb = (int64_t)rowptr.size() - 1;
     tile_row.clear();

@@ -232,12 +232,14 @@ __global__ void k_pack_nodes(int64_t V, const double *__restrict__ nodes_cm, Nod
 }
 
 __global__ void k_pack_elems(int64_t E, const int32_t *__restrict__ elems_cm,
-                             const double *__restrict__ normals_cm, const double *__restrict__ props4,
+                             const double *__restrict__ normals_cm, const float *__restrict__ props4,
                              ElemRec *__restrict__ rec)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const double2 p01 = ldg2(props4 + 4 * e), p23 = ldg2(props4 + 4 * e + 2);
+    // EA, EIz, EIy, GJ are float values in the reference [REF src/beamsimulator.cpp:173-188]; the widening is exact
+    const float4 pf = __ldg(reinterpret_cast<const float4 *>(props4) + e);
+    const double2 p01 = make_double2((double)pf.x, (double)pf.y), p23 = make_double2((double)pf.z, (double)pf.w);
     const uint32_t a = (uint32_t)elems_cm[e], b = (uint32_t)elems_cm[E + e];
     const long long ab = (long long)(((unsigned long long)b << 32) | a);
     double2 *o = reinterpret_cast<double2 *>(rec + e);
@@ -254,7 +256,7 @@ void launch_pack_nodes(cudaStream_t st, int64_t V, const double *nodes_cm, Node4
 }
 
 void launch_pack_elems(cudaStream_t st, int64_t E, const int32_t *elems_cm, const double *normals_cm,
-                       const double *props4, ElemRec *rec)
+                       const float *props4, ElemRec *rec)
 {
     if (E <= 0) return;
     k_pack_elems<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(E, elems_cm, normals_cm, props4, rec);

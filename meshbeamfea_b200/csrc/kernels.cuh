@@ -74,7 +74,7 @@ struct PartialRef { const double *buf; int n; int stride; };
 
 void launch_pack_nodes(cudaStream_t st, int64_t V, const double *nodes_cm, Node4 *node4);
 void launch_pack_elems(cudaStream_t st, int64_t E, const int32_t *elems_cm, const double *normals_cm,
-                       const double *props4, ElemRec *rec);
+                       const float *props4, ElemRec *rec);
 // K3: device constraint map (flags -> exclusive scan)
 void launch_free_map(cudaStream_t st, int64_t V, int64_t F, const int32_t *fixed, int32_t *free_index,
                      int32_t *scratch /* >= V + V/1024 + 1 ints */);

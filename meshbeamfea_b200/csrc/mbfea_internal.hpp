@@ -2,6 +2,7 @@
 // translation units of libmbfea.so.  Not installed; the public surface is
 // include/mbfea.h.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -9,6 +10,25 @@
 #include "../../include/mbfea.h"
 
 namespace mbfea {
+
+// ---------------------------------------------------------------------------
+// Host arrays that are uploaded (hostmem.cpp): page-locked once mbfea_create has found a device, plain heap otherwise.
+// ---------------------------------------------------------------------------
+void host_arrays_pin_on(int device);
+void *host_array_alloc(size_t bytes);
+void host_array_free(void *p) noexcept;
+bool host_array_is_pinned(const void *p);
+template <class T>
+struct HostAlloc {
+    using value_type = T;
+    HostAlloc() = default;
+    template <class U> HostAlloc(const HostAlloc<U> &) {}
+    T *allocate(size_t n) { return static_cast<T *>(host_array_alloc(n * sizeof(T))); }
+    void deallocate(T *p, size_t) noexcept { host_array_free(p); }
+    template <class U> bool operator==(const HostAlloc<U> &) const { return true; }
+    template <class U> bool operator!=(const HostAlloc<U> &) const { return false; }
+};
+template <class T> using hvec = std::vector<T, HostAlloc<T>>;
 
 // ---------------------------------------------------------------------------
 // Host-side plan: everything derived from connectivity + fixed set.  Pure C++,
@@ -32,18 +52,19 @@ struct HostPlan {
     // first renumbering instead: perm[canonical] = internal row, inv[internal] = canonical.  Purely
     // internal: every tap and result is reported in canonical / vertex numbering.
     std::vector<int32_t> perm, inv;
-    std::vector<int32_t> rowptr;      // nb+1
-    std::vector<int32_t> colidx;      // nnzb, LOCAL ids: owned [0,nb), ghosts after
-    std::vector<int32_t> diag_idx;    // nb: position of the diagonal block
-    std::vector<int32_t> contrib_ptr; // nnzb+1
-    std::vector<int32_t> contrib;     // (element<<2)|which, ascending element per block
+    hvec<int32_t> rowptr;      // nb+1
+    hvec<int32_t> colidx;      // nnzb, LOCAL ids: owned [0,nb), ghosts after
+    hvec<int32_t> diag_idx;    // nb: position of the diagonal block
+    hvec<int32_t> contrib_ptr; // nnzb+1
+    hvec<int32_t> contrib;     // (element<<2)|which, ascending element per block
     // Solver format (off-diagonal blocks of the block-Jacobi-scaled matrix, unit diagonal implied):
     // row r stores the blocks [uptr[r], uptr[r+1]) itself -- its ghost columns and, with
     // symmetric-half storage, one of every local pair {r, c} (the upper one, c > r, unless
     // `balanced`) -- and reaches the remaining local
     // columns as TRANSPOSED references [lptr[r], lptr[r+1]) into row c's stored blocks.
-    std::vector<int32_t> uptr, ucol, usrc;  // usrc: index of the block in the full pattern
-    std::vector<int32_t> lptr, lcol, lblk;  // lblk: stored-block index holding (lcol, r)
+    hvec<int32_t> uptr, ucol, usrc;  // usrc: index of the block in the full pattern
+    hvec<int32_t> lptr, lcol;
+    std::vector<int32_t> lblk;       // lblk: stored-block index holding (lcol, r)
     bool sym_half = false;
     // build_plan scratch, kept between jobs: re-submitting a mesh of the same size then touches no fresh pages
     std::vector<int64_t> scratch_ent, scratch_start, scratch_pos;
@@ -55,8 +76,8 @@ struct HostPlan {
     // 16-byte unit  tile_base[tile] + (3k + m) * 192 + 6 lr + i,  so the 192 threads of a CTA
     // read 192 consecutive chunks per load instruction.  lofs[l] = unit of (m = 0, i = 0) of the
     // block a transposed reference points to.  Plain BSR order is kept for full-row storage.
-    std::vector<int32_t> tile_base;         // #tiles + 1, in 16-byte units
-    std::vector<int32_t> lofs;
+    hvec<int32_t> tile_base;         // #tiles + 1, in 16-byte units
+    hvec<int32_t> lofs;
     // Connected components of the reduced system when each occupies a contiguous range of block
     // rows (a batch of independent meshes submitted as one job): comp_ptr[b]..comp_ptr[b+1].
     // Empty when the job is one mesh, the ranges interleave, or a component is too large.
@@ -82,7 +103,8 @@ int validate_forces(int64_t V, int64_t nF, const int64_t *f_node, const int64_t 
                     std::string &msg);
 
 // float-quirk section properties [REF src/beamsimulator.cpp:173-188]
-void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, double *props4);
+// (the four products are float values in the reference; they are kept and uploaded as floats)
+void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, float *props4);
 
 // free_index + nb_global.  fixed must be validated already.
 int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<int32_t> &free_index);
@@ -104,20 +126,20 @@ void build_solver_format(HostPlan &plan, bool half);
 void find_components(HostPlan &plan, int32_t max_rows, int32_t min_components);
 
 // Row tiles for the TMA-staged SpMV: tile t covers rows [tile_row[t], tile_row[t+1]).
-void build_tiles(const std::vector<int32_t> &rowptr, int cap_blocks, int max_rows,
-                 std::vector<int32_t> &tile_row);
+void build_tiles(const hvec<int32_t> &rowptr, int cap_blocks, int max_rows,
+                 hvec<int32_t> &tile_row);
 
 // ---------------------------------------------------------------------------
 // Aggregate hierarchy for the multilevel preconditioner (host half, see hierarchy.cpp)
 // ---------------------------------------------------------------------------
 struct HierLevel {
     int64_t n_fine = 0, n_coarse = 0;
-    std::vector<int32_t> agg;                 // n_fine: aggregate (= coarse block row) of each fine row
-    std::vector<double> off;                  // 3 * n_fine: fine position minus the centroid of its aggregate
-    std::vector<double> centroid;             // 3 * n_coarse: positions of the coarse rows
-    std::vector<int32_t> agg_ptr, agg_rows;   // member rows of each aggregate, ascending
-    std::vector<int32_t> rowptr, colidx;      // coarse 6x6-block pattern (columns ascending, diagonal present)
-    std::vector<int32_t> gal_ptr, gal_src;    // per coarse block: the fine blocks summed into it, ascending
+    hvec<int32_t> agg;                 // n_fine: aggregate (= coarse block row) of each fine row
+    hvec<double> off;                  // 3 * n_fine: fine position minus the centroid of its aggregate
+    std::vector<double> centroid;      // 3 * n_coarse: positions of the coarse rows
+    hvec<int32_t> agg_ptr, agg_rows;   // member rows of each aggregate, ascending
+    hvec<int32_t> rowptr, colidx;      // coarse 6x6-block pattern (columns ascending, diagonal present)
+    hvec<int32_t> gal_ptr, gal_src;    // per coarse block: the fine blocks summed into it, ascending
 };
 struct Hierarchy { std::vector<HierLevel> levels; };
 // nb block rows with pattern (rowptr, colidx < nb) and positions pos_rm[3 * row]; level l bricks have edge
@@ -137,11 +159,11 @@ void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, c
 struct MlTransfer {
     bool smoothed = false;
     int64_t n_fine = 0, n_coarse = 0;
-    std::vector<int32_t> prow, pcol;           // P: n_fine rows
-    std::vector<int32_t> pown;                 // n_fine: index in pcol of the block (i, agg i)
-    std::vector<int32_t> rrow, rblk, rfine;    // per coarse row: the P blocks of that column (ascending) and their fine rows
-    std::vector<int32_t> aprow, apcol;         // A P: n_fine rows
-    std::vector<int32_t> crow, ccol, cdiag;    // next level's matrix: n_coarse rows, diagonal position per row
+    hvec<int32_t> prow, pcol;           // P: n_fine rows
+    std::vector<int32_t> pown;          // n_fine: index in pcol of the block (i, agg i)
+    hvec<int32_t> rrow, rblk, rfine;    // per coarse row: the P blocks of that column (ascending) and their fine rows
+    hvec<int32_t> aprow, apcol;         // A P: n_fine rows
+    hvec<int32_t> crow, ccol, cdiag;    // next level's matrix: n_coarse rows, diagonal position per row
 };
 struct MlHierarchy {
     std::vector<HierLevel> agg;       // agg[l]: aggregates of level l (l = 0: fine level, with Galerkin contributor lists)
@@ -174,6 +196,15 @@ struct MlImageHeader {
 constexpr int64_t kMlImageMagic = 0x6d6c696d67303031LL;
 // fine_rowptr: block row pointer of the GLOBAL fine pattern (nbg + 1); false when the hierarchy does not fit the header
 bool ml_image_pack(const MlHierarchy &H, int world, int64_t nbg, const int32_t *fine_rowptr, std::vector<unsigned char> &out);
+// The same image as a layout: the header plus (source array, bytes, offset in the image) of every part -- rank 0 copies the
+// (page-locked) hierarchy arrays straight into the device image, without assembling it on the host first.
+struct MlImageLayout {
+    struct Part { const void *p; size_t bytes; size_t at; };
+    MlImageHeader hd;
+    std::vector<Part> parts;
+    hvec<int32_t> diag1;   // diagonal positions of the level-1 pattern (computed here; must outlive the copies)
+};
+bool ml_image_layout(const MlHierarchy &H, int world, int64_t nbg, const int32_t *fine_rowptr, MlImageLayout &lay);
 
 // Explicit inverse of a dense SPD matrix (row-major n x n) for the coarsest level; 0, or 1 + the index of
 // the first non-positive pivot (dense.cpp).

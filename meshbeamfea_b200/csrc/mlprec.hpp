@@ -99,6 +99,8 @@ private:
     DevBuf<float> t0;
     int group0 = 32;
     std::vector<std::unique_ptr<MlCoarse>> lv;   // lv[m]: level m + 1
+    std::vector<std::unique_ptr<MlCoarse>> spare; // level objects of the previous job, in level order (buffers keep their capacity)
+    std::unique_ptr<MlCoarse> take_level();
     DevBuf<double> dense, gj_col;                // explicit inverse of the coarsest matrix (+ Gauss-Jordan scratch)
     DevBuf<float> dense32;                       // its symmetrised FP32 copy: what the apply multiplies with
     int64_t n_dense = 0;

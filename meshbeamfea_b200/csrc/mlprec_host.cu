@@ -14,8 +14,8 @@ namespace mbfea {
 using namespace mbfea::dev;
 
 namespace {
-template <class T>
-void up(cudaStream_t st, DevBuf<T> &d, const std::vector<T> &h)
+template <class T, class A>
+void up(cudaStream_t st, DevBuf<T> &d, const std::vector<T, A> &h)
 {
     CK(d.alloc(h.size()));
     if (!h.empty()) CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
@@ -30,9 +30,24 @@ double wall_ms()
 void MlPrec::reset()
 {
     symbolic_ok = numeric_ok = false;
+    // the level objects (and their device buffers) are kept for the next job: a re-submitted mesh of the same size then
+    // costs no cudaFree / cudaMalloc round trips (about a hundred buffers, 1 GB on the 119^3 lattice)
+    for (auto &s : spare) lv.push_back(std::move(s));
+    spare.swap(lv);
     lv.clear();
     rows.clear();
     nb = 0;
+}
+
+std::unique_ptr<MlCoarse> MlPrec::take_level()
+{
+    if (spare.empty()) return std::unique_ptr<MlCoarse>(new MlCoarse);
+    std::unique_ptr<MlCoarse> c = std::move(spare.front());
+    spare.erase(spare.begin());
+    c->n = c->nnz = 0;
+    c->has_next = c->smoothed = false;
+    c->n_next = c->nnzp = c->nnzap = 0;
+    return c;
 }
 
 void MlPrec::build_hierarchy_host(int64_t nbg, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
@@ -125,9 +140,9 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
     CK(t0.alloc((size_t)nb * 36));
     rows.push_back(nb);
     for (size_t m = 0; m < L; ++m) {
-        std::unique_ptr<MlCoarse> c(new MlCoarse);
-        const std::vector<int32_t> &rp = m == 0 ? h0.rowptr : H.xfer[m].crow;
-        const std::vector<int32_t> &ci = m == 0 ? h0.colidx : H.xfer[m].ccol;
+        std::unique_ptr<MlCoarse> c = take_level();
+        const hvec<int32_t> &rp = m == 0 ? h0.rowptr : H.xfer[m].crow;
+        const hvec<int32_t> &ci = m == 0 ? h0.colidx : H.xfer[m].ccol;
         c->n = (int64_t)rp.size() - 1;
         c->nnz = (int64_t)ci.size();
         rows.push_back(c->n);
@@ -229,7 +244,7 @@ bool MlPrec::upload_from_image(cudaStream_t st, const unsigned char *d_img, cons
     rows.push_back(nb);
     // ---- coarse levels: replicated
     for (size_t m = 0; m < L; ++m) {
-        std::unique_ptr<MlCoarse> c(new MlCoarse);
+        std::unique_ptr<MlCoarse> c = take_level();
         c->n = hd.lv[m].n_coarse;
         if (m == 0) { copy_i(c->rowptr, 0, 4); copy_i(c->colidx, 0, 5); copy_i(c->diag_idx, 0, 6); c->nnz = hd.lv[0].cnt[5]; }
         else { copy_i(c->rowptr, m, 9); copy_i(c->colidx, m, 10); copy_i(c->diag_idx, m, 11); c->nnz = hd.lv[m].cnt[10]; }
