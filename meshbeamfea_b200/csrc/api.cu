@@ -14,6 +14,9 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -63,7 +66,9 @@ struct mbfea_ctx {
     // staging for set_job (kept: a re-submitted mesh of the same size costs no cudaMalloc/cudaFree)
     DevBuf<double> stg_nodes, stg_normals;
     DevBuf<float> stg_props;
-    DevBuf<int32_t> stg_elems, stg_scratch;
+    DevBuf<int32_t> stg_elems, stg_scratch, stg_perm;
+    DevBuf<int64_t> stg_fnode, stg_fdof;
+    DevBuf<double> stg_fmag;
     // device: pattern
     DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, tile_row_s, send_rows;
     DevBuf<int32_t> uptr, ucol, usrc, lptr, lcol, lofs, ilv_base;   // solver format (HostPlan::uptr ...)
@@ -557,8 +562,8 @@ void upload_forces(mbfea_ctx *c, int64_t nF, const int64_t *f_node, const int64_
                 w |= m;
             }
         }
-        DevBuf<int64_t> dn, dd;
-        DevBuf<double> dm;
+        DevBuf<int64_t> &dn = c->stg_fnode, &dd = c->stg_fdof;   // staging kept between jobs (no cudaMalloc / cudaFree per call)
+        DevBuf<double> &dm = c->stg_fmag;
         upload(c, dn, f_node, (size_t)nF);
         upload(c, dd, f_dof, (size_t)nF);
         upload(c, dm, f_mag, (size_t)nF);
@@ -814,26 +819,32 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         const double tp0 = now_ms();
         // internal renumbering: 0 auto (only when the input vertex order has no locality), 1 never, 2 always
         const int reorder = c->opt.reorder == 1 ? 0 : (c->opt.reorder == 2 ? 2 : (c->opt.reorder == 3 ? 3 : 1));
-        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan, reorder, nodes_cm);
-        // preconditioner: multilevel on one rank for a single large mesh (auto) or on request
-        if (c->opt.batch_mode != 1) find_components(c->plan, 1024, 32);
-        else { c->plan.comp_ptr.clear(); c->plan.comp_max_rows = 0; }
-        const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
+        // The host half of the multilevel hierarchy runs on its own thread, next to the pattern build: its first phase
+        // (positions of the block rows, brick aggregates, centroids) needs the free map only and starts as soon as
+        // build_plan has it; the thread then waits at the gate for the block pattern.  (Several ranks: rank 0 builds the
+        // hierarchy for everybody -- the ranks of a box share the host cores, W redundant builds would each get 1 / W of
+        // them -- from its own pattern of the whole system.)
         c->use_ml = false;
         c->ml.reset();
-        const bool ml_possible = !batched && c->plan.nb_global >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
-        const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
-        // The host half of the multilevel hierarchy needs only the block pattern and the vertex positions: it runs on its own
-        // thread while this one builds the solver format and uploads the plan.  (Several ranks: rank 0 builds it
-        // for everybody -- the ranks of a box share the host cores, W redundant builds would each get 1 / W of them.)
         struct MlHostJob {
             double mean_len = 0.0;
             bool failed = false;
             double ms = 0.0;
+            std::mutex m;
+            std::condition_variable cv;
+            int pattern_state = 0;   // 0 under construction, 1 ready, 2 abandoned (batched job, or set_job failed)
+            void signal(int st) { { std::lock_guard<std::mutex> g(m); if (pattern_state == 0) pattern_state = st; } cv.notify_all(); }
         } mlh;
         std::thread ml_thread;
-        const bool ml_build_here = ml_possible && ml_wanted && (c->opt.world == 1 || c->opt.rank == 0);
-        if (ml_possible && ml_wanted) {
+        bool ml_started = false;
+        // destruction order: the gate is released first (an exception on this thread must not leave the other one waiting), then joined
+        struct JoinGuard { std::thread &t; ~JoinGuard() { if (t.joinable()) t.join(); } } ml_join{ml_thread};
+        struct GateGuard { MlHostJob &j; ~GateGuard() { j.signal(2); } } ml_gate{mlh};
+        const std::function<void()> start_ml_thread = [&]() {
+            const int64_t nbg = c->plan.nb_global;
+            const bool wanted = c->opt.precond == 2 || (c->opt.precond == 0 && nbg >= 4096);
+            const bool possible = nbg >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
+            if (!wanted || !possible || !(c->opt.world == 1 || c->opt.rank == 0)) return;
             MlParams mp;
             if (c->opt.ml_cell > 0.0) mp.cell = c->opt.ml_cell;
             if (c->opt.ml_ratio > 1.0) mp.ratio = c->opt.ml_ratio;
@@ -842,70 +853,76 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             if (const char *e = std::getenv("MBFEA_ML_OMEGA")) { const double v = std::atof(e); if (v > 0.0 && v < 2.0) mp.omega = v; }
             if (const char *e = std::getenv("MBFEA_ML_THETA")) { const double v = std::atof(e); if (v > 0.0) mp.theta = v; }
             c->ml.par = mp;
-        }
-        struct JoinGuard { std::thread &t; ~JoinGuard() { if (t.joinable()) t.join(); } } ml_join{ml_thread};
-        auto start_ml_thread = [&]() {
-        if (ml_build_here) {
-                ml_thread = std::thread([&, V, E, F]() {
-                    try {
-                        cudaSetDevice(c->device);   // page-locked allocations of this thread belong to this context's device
-                        const double tw = now_ms();
-                        const int64_t nbg = c->plan.nb_global;
-                        const int W = c->opt.world;
-                        // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
-                        // mean beam length: the aggregates are bricks of a few beam lengths
-                        c->ml_pos.resize((size_t)3 * nbg);
-                        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, E >> 16));
-                        std::vector<double> part((size_t)nt, 0.0);
-                        std::vector<std::thread> th;
-                        for (int t = 0; t < nt; ++t)
-                            th.emplace_back([&, t]() {
-                                for (int64_t v = V * t / nt; v < V * (t + 1) / nt; ++v) {
-                                    const int32_t r = c->plan.free_index[(size_t)v];
-                                    if (r >= 0) for (int a = 0; a < 3; ++a) c->ml_pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
+            ml_started = true;
+            ml_thread = std::thread([&, V, E, F, nbg]() {
+                try {
+                    cudaSetDevice(c->device);   // page-locked allocations of this thread belong to this context's device
+                    const double tw = now_ms();
+                    const int W = c->opt.world;
+                    // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
+                    // mean beam length: the aggregates are bricks of a few beam lengths
+                    c->ml_pos.resize((size_t)3 * nbg);
+                    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, E >> 16));
+                    std::vector<double> part((size_t)nt, 0.0);
+                    std::vector<std::thread> th;
+                    for (int t = 0; t < nt; ++t)
+                        th.emplace_back([&, t]() {
+                            for (int64_t v = V * t / nt; v < V * (t + 1) / nt; ++v) {
+                                const int32_t r = c->plan.free_index[(size_t)v];
+                                if (r >= 0) for (int a = 0; a < 3; ++a) c->ml_pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
+                            }
+                            double len = 0.0;   // fixed chunks, summed in chunk order below: reproducible
+                            for (int64_t e = E * t / nt; e < E * (t + 1) / nt; ++e) {
+                                double d2 = 0.0;
+                                for (int a = 0; a < 3; ++a) {
+                                    const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                                    d2 += d * d;
                                 }
-                                double len = 0.0;   // fixed chunks, summed in chunk order below: reproducible
-                                for (int64_t e = E * t / nt; e < E * (t + 1) / nt; ++e) {
-                                    double d2 = 0.0;
-                                    for (int a = 0; a < 3; ++a) {
-                                        const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
-                                        d2 += d * d;
-                                    }
-                                    len += std::sqrt(d2);
-                                }
-                                part[(size_t)t] = len;
-                            });
-                        for (auto &x : th) x.join();
-                        double len = 0.0;
-                        for (int t = 0; t < nt; ++t) len += part[(size_t)t];
-                        mlh.mean_len = len / (double)E;
-                        if (W == 1) {
-                            c->ml.build_hierarchy_host(nbg, c->plan.rowptr.data(), c->plan.colidx.data(), c->ml_pos.data(), mlh.mean_len, 1, c->ml_host);
-                        } else {
-                            HostPlan &G = c->ml_gplan;   // kept between jobs (page-locked arrays: allocation is expensive)
-                            build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
-                            c->ml.build_hierarchy_host(nbg, G.rowptr.data(), G.colidx.data(), c->ml_pos.data(), mlh.mean_len, W, c->ml_host);
-                            if (!ml_image_layout(c->ml_host, W, nbg, G.rowptr.data(), c->ml_layout)) mlh.failed = true;
-                        }
-                        mlh.ms = now_ms() - tw;
-                    } catch (...) {
-                        mlh.failed = true;
+                                len += std::sqrt(d2);
+                            }
+                            part[(size_t)t] = len;
+                        });
+                    for (auto &x : th) x.join();
+                    double len = 0.0;
+                    for (int t = 0; t < nt; ++t) len += part[(size_t)t];
+                    mlh.mean_len = len / (double)E;
+                    if (W == 1) {
+                        const FinePatternGate gate = [&](const int32_t *&rp, const int32_t *&ci) {
+                            std::unique_lock<std::mutex> g(mlh.m);
+                            mlh.cv.wait(g, [&] { return mlh.pattern_state != 0; });
+                            if (mlh.pattern_state != 1) return false;
+                            rp = c->plan.rowptr.data(); ci = c->plan.colidx.data();
+                            return true;
+                        };
+                        c->ml.build_hierarchy_host(nbg, nullptr, nullptr, c->ml_pos.data(), mlh.mean_len, 1, c->ml_host, &gate);
+                        if (c->ml_host.levels() == 0) mlh.failed = true;
+                    } else {
+                        HostPlan &G = c->ml_gplan;   // kept between jobs (page-locked arrays: allocation is expensive)
+                        build_plan(V, E, elems_cm, F, fixed, 0, 1, false, G, reorder, nodes_cm);
+                        c->ml.build_hierarchy_host(nbg, G.rowptr.data(), G.colidx.data(), c->ml_pos.data(), mlh.mean_len, W, c->ml_host);
+                        if (!ml_image_layout(c->ml_host, W, nbg, G.rowptr.data(), c->ml_layout)) mlh.failed = true;
                     }
-                });
-            }
+                    mlh.ms = now_ms() - tw;
+                } catch (...) {
+                    mlh.failed = true;
+                }
+            });
         };
-        // started as soon as the block pattern exists, next to the rest of the host prep (MBFEA_ML_THREAD_LATE=1: only
-        // after the solver format).  The hierarchy arrays keep their capacity between jobs; with fresh allocations on
-        // both sides the two thread pools serialised on page faults instead.
-        const bool ml_early = [] { const char *e = std::getenv("MBFEA_ML_THREAD_LATE"); return !(e && *e == '1'); }();
-        if (ml_early) start_ml_thread();
+        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan, reorder, nodes_cm, &start_ml_thread);
+        if (c->opt.batch_mode != 1) find_components(c->plan, 1024, 32);
+        else { c->plan.comp_ptr.clear(); c->plan.comp_max_rows = 0; }
+        const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
+        mlh.signal(batched ? 2 : 1);   // the hierarchy thread may read the block pattern now (a batch has no use for it)
+        // preconditioner: multilevel for a single large mesh (auto) or on request
+        const bool ml_possible = !batched && c->plan.nb_global >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
+        const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
         host_ms += now_ms() - tp0;
         const int64_t nb = c->nb(), ng = c->ng(), nnzb = c->plan.nnzb();
         // the reduced numbering the kernels use: K3's map, composed with the internal renumbering when there is one
         if (c->plan.perm.empty()) {
             CK(cudaMemcpyAsync(c->free_index.p, c->free_canon.p, (size_t)V * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->st));
         } else {
-            DevBuf<int32_t> d_perm;
+            DevBuf<int32_t> &d_perm = c->stg_perm;
             upload(c, d_perm, c->plan.perm);
             launch_apply_perm(c->st, V, c->free_canon.p, d_perm.p, c->free_index.p);
             CK(cudaStreamSynchronize(c->st));
@@ -922,7 +939,6 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         const double tp1 = now_ms();
         const bool half = !batched && (c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2));
         build_solver_format(c->plan, half);
-        if (!ml_early) start_ml_thread();
         host_ms += now_ms() - tp1;
         upload(c, c->uptr, c->plan.uptr);
         upload(c, c->ucol, c->plan.ucol);
@@ -978,7 +994,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             const int64_t nbg = c->plan.nb_global;
             if (ml_thread.joinable()) ml_thread.join();
             if (c->opt.world == 1) {
-                c->use_ml = !mlh.failed && c->ml.upload_hierarchy(c->st, c->ml_host, nbg, (int64_t)c->plan.rowptr[(size_t)nb], 0, nullptr);
+                c->use_ml = ml_started && !mlh.failed && c->ml.upload_hierarchy(c->st, c->ml_host, nbg, (int64_t)c->plan.rowptr[(size_t)nb], 0, nullptr);
             } else {
                 // rank 0's flat image goes through the GPUs to everybody; each rank then uploads its own share of level 0 and
                 // the replicated coarse levels
@@ -1037,7 +1053,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         s.bytes_pcg_iter = s.bytes_spmv + 432.0 * (double)nb;
         // multilevel: restriction reads r~ (48) + T (144, FP32) + member id (4); prolongation reads r~, T, aggregate id and
         // writes z~ (48); the p-update reads z~ in place of r~ (no change)
-        s.bytes_ml_apply = c->use_ml ? 440.0 * (double)nb : 0.0;
+        s.bytes_ml_apply = c->use_ml ? (c->ml.half16 ? 312.0 : 440.0) * (double)nb : 0.0;   // T blocks: 80 B (16-bit + scale) or 144 B (FP32)
         if (c->use_ml) s.bytes_pcg_iter += s.bytes_ml_apply;
         s.precond = c->use_ml ? 2 : 1;
         s.ml_levels = c->use_ml ? (int32_t)c->ml.levels() : 0;

@@ -68,14 +68,25 @@ static int64_t par_ranges_count(int64_t n, int64_t min_per_thread)
     return std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 32), n / std::max<int64_t>(1, min_per_thread)));
 }
 
-static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx, const double *pos, double cell,
-                        HierLevel &L, bool with_galerkin_lists = true, const int64_t *part_bounds = nullptr, int nparts = 1)
+// First half of a level: the aggregates (needs the positions only, not the pattern).
+static void build_level_aggregates(int64_t n, const double *pos, double cell, HierLevel &L, const int64_t *part_bounds = nullptr,
+                                   int nparts = 1)
 {
     Lap lap;
     L.n_fine = n;
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int64_t v = 0; v < n; ++v)
-        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], pos[3 * v + a]); hi[a] = std::max(hi[a], pos[3 * v + a]); }
+    {   // bounding box: per-thread boxes, merged (min / max: the result does not depend on the split)
+        const int64_t nt = par_ranges_count(n, 1 << 16);
+        std::vector<double> box((size_t)nt * 6);
+        par_ranges_t(n, 1 << 16, [&](int64_t b0, int64_t b1, int64_t t) {
+            double l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int64_t v = b0; v < b1; ++v)
+                for (int a = 0; a < 3; ++a) { l[a] = std::min(l[a], pos[3 * v + a]); h[a] = std::max(h[a], pos[3 * v + a]); }
+            for (int a = 0; a < 3; ++a) { box[(size_t)t * 6 + a] = l[a]; box[(size_t)t * 6 + 3 + a] = h[a]; }
+        });
+        for (int64_t t = 0; t < nt; ++t)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], box[(size_t)t * 6 + a]); hi[a] = std::max(hi[a], box[(size_t)t * 6 + 3 + a]); }
+    }
     int64_t cnt[3];
     for (int a = 0; a < 3; ++a) cnt[a] = std::max<int64_t>(1, (int64_t)std::floor((hi[a] - lo[a]) / cell + 1e-9) + 1);
     // brick of every row; aggregates numbered in ascending (i, j, k) order of the occupied bricks, members in
@@ -150,10 +161,14 @@ static void build_level(int64_t n, const int32_t *rowptr, const int32_t *colidx,
             for (int a = 0; a < 3; ++a) L.off[(size_t)3 * v + a] = pos[3 * v + a] - L.centroid[(size_t)3 * L.agg[(size_t)v] + a];
     });
     lap("centroids + offsets", n);
-    if (!with_galerkin_lists) {   // coarse-to-coarse transfers build their own patterns (build_transfer)
-        L.rowptr.clear(); L.colidx.clear(); L.gal_ptr.clear(); L.gal_src.clear();
-        return;
-    }
+}
+
+// Second half (fine level only; coarse-to-coarse transfers build their own patterns in build_transfer): the coarse
+// pattern and the Galerkin contributor lists from the fine pattern.
+static void build_level_pattern(int64_t n, const int32_t *rowptr, const int32_t *colidx, HierLevel &L)
+{
+    Lap lap;
+    const int64_t na = L.n_coarse;
     // coarse pattern: aggregate I couples to agg(col) of every block of its member rows.  Two passes (count,
     // fill) over ranges of aggregates, each thread with its own scratch.
     L.rowptr.assign((size_t)na + 1, 0);
@@ -299,7 +314,7 @@ static void build_transfer(int64_t n, const int32_t *rowptr, const int32_t *coli
 
 void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
                         double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H,
-                        const int64_t *part_bounds, int nparts)
+                        const int64_t *part_bounds, int nparts, const FinePatternGate *fine_pattern)
 {
     // Built IN PLACE: a hierarchy object that is handed in again (the next set_job of the same context) keeps the
     // capacity of every array, so a re-submitted mesh of similar size touches no fresh pages (first-touch page faults of
@@ -314,7 +329,15 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
             if (H.agg.size() <= used) { H.agg.emplace_back(); H.xfer.emplace_back(); }
             HierLevel &L = H.agg[used];
             MlTransfer &T = H.xfer[used];
-            build_level(n, crp, cci, pos, cell, L, /*with_galerkin_lists=*/l == 0, l == 0 ? part_bounds : nullptr, l == 0 ? nparts : 1);
+            build_level_aggregates(n, pos, cell, L, l == 0 ? part_bounds : nullptr, l == 0 ? nparts : 1);
+            if (l == 0) {
+                // the aggregates needed the positions only; the fine pattern may still be under construction on the
+                // caller's side (set_job builds it on another thread): wait for it here
+                if (fine_pattern && !(*fine_pattern)(crp, cci)) { used = 0; break; }
+                build_level_pattern(n, crp, cci, L);
+            } else {
+                L.rowptr.clear(); L.colidx.clear(); L.gal_ptr.clear(); L.gal_src.clear();
+            }
             if (L.n_coarse >= n) break;   // no coarsening at this cell size: stop
             if (l >= 1) {
                 build_transfer(n, crp, cci, L, l >= smooth_from, T);
@@ -414,7 +437,8 @@ void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, c
     int64_t n = nb;
     for (int l = 1; l < max_levels && n > coarsest_rows; ++l) {
         HierLevel L;
-        build_level(n, rp.data(), ci.data(), pos.data(), cell, L);
+        build_level_aggregates(n, pos.data(), cell, L);
+        build_level_pattern(n, rp.data(), ci.data(), L);
         if (L.n_coarse >= n) break;   // no coarsening at this cell size (isolated points): stop
         pos = L.centroid; rp.assign(L.rowptr.begin(), L.rowptr.end()); ci.assign(L.colidx.begin(), L.colidx.end()); n = L.n_coarse;
         H.levels.push_back(std::move(L));

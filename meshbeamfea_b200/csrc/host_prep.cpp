@@ -164,12 +164,36 @@ void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, float *
 // ---------------------------------------------------------------------------
 int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<int32_t> &fm)
 {
-    fm.assign((size_t)V, 0);
-    for (int64_t i = 0; i < F; ++i) fm[fixed[i]] = -1;
-    int32_t k = 0;
-    for (int64_t v = 0; v < V; ++v)
-        if (fm[v] == 0) fm[v] = k++;
-    return k;
+    fm.resize((size_t)V);
+    int32_t *m = fm.data();
+    const int64_t nt = std::max<int64_t>(1, std::min<int64_t>(host_threads(), V >> 16));
+    if (nt <= 1) {
+        std::fill(m, m + V, 0);
+        for (int64_t i = 0; i < F; ++i) m[fixed[i]] = -1;
+        int32_t k = 0;
+        for (int64_t v = 0; v < V; ++v)
+            if (m[v] == 0) m[v] = k++;
+        return k;
+    }
+    // chunked: clear, mark (duplicates store the same value), count the free vertices per chunk, rank them from the
+    // chunk's prefix -- the same map as the serial scan above
+    parallel_ranges(V, 1 << 16, [=](int64_t lo, int64_t hi, int) { std::fill(m + lo, m + hi, 0); });
+    if (F >= (1 << 18)) parallel_ranges(F, 1 << 16, [=](int64_t lo, int64_t hi, int) { for (int64_t i = lo; i < hi; ++i) __atomic_store_n(&m[fixed[i]], -1, __ATOMIC_RELAXED); });
+    else for (int64_t i = 0; i < F; ++i) m[fixed[i]] = -1;
+    std::vector<int64_t> first((size_t)nt + 1, 0);
+    int64_t *fp = first.data();
+    parallel_ranges(V, 1 << 16, [=](int64_t lo, int64_t hi, int t) {
+        int64_t k = 0;
+        for (int64_t v = lo; v < hi; ++v) k += m[v] == 0;
+        fp[t + 1] = k;
+    });
+    for (int64_t t = 0; t < nt; ++t) first[(size_t)t + 1] += first[(size_t)t];
+    parallel_ranges(V, 1 << 16, [=](int64_t lo, int64_t hi, int t) {
+        int32_t k = (int32_t)fp[t];
+        for (int64_t v = lo; v < hi; ++v)
+            if (m[v] == 0) m[v] = k++;
+    });
+    return first[(size_t)nt];
 }
 
 static inline int32_t owner_of(int64_t g, int64_t nb_global, int32_t world)
@@ -314,7 +338,8 @@ static bool bfs_renumber(int64_t V, int64_t E, const int32_t *elems_cm, const st
 }
 
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
-                int32_t rank, int32_t world, bool with_contrib, HostPlan &P, int reorder, const double *nodes_cm)
+                int32_t rank, int32_t world, bool with_contrib, HostPlan &P, int reorder, const double *nodes_cm,
+                const std::function<void()> *after_free_map)
 {
     PrepTrace tr;
     RankShare share(world);
@@ -331,6 +356,7 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     const int64_t r0 = P.row_begin, nb = P.row_end - P.row_begin;
     const int32_t *fm = P.free_index.data();
     tr.lap("free map");
+    if (after_free_map && *after_free_map) (*after_free_map)();
 
     // pass 1: entries per owned row (diagonal contributions + off-diagonal ones).  The owned rows are
     // split into one range per thread.  Every end point that falls into an owned row is first dropped

@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "kernels.cuh"
+#include "multilevel_math.hpp"
 
 namespace mbfea { namespace dev {
 
@@ -688,6 +689,16 @@ constexpr int kSpmvThreads = kRowsPerCta * 6;
 #ifndef MBFEA_SYM_PREFETCH
 #define MBFEA_SYM_PREFETCH 0  // fetch the next tile's row pointers while working on this one
 #endif
+#ifndef MBFEA_SYM_STREAM
+#define MBFEA_SYM_STREAM 0    // value loads that bypass L1 allocation (ld.global.nc.L1::no_allocate): 1 the row's own blocks,
+                              // 2 the transposed references too -- the values are read once per CTA, the x-blocks are reused
+#endif
+__device__ __forceinline__ double2 ldg_stream(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 
 // ROWS (32 or 16) block rows per CTA: the symmetric variant runs half-tiles on small systems (a rank's
 // share on 8 GPUs is ~4 tiles per resident CTA: whole tiles quantise the makespan to 5 and leave too few
@@ -765,7 +776,8 @@ __global__ void __launch_bounds__(ROWS * 6, (SYM ? MBFEA_SYM_MINB : 8) * (32 / R
                 double2 v0, v1, v2;
                 if (SYM) {
                     const double2 *v = vt + (int64_t)(k - kb) * 576;
-                    v0 = __ldg(v); v1 = __ldg(v + 192); v2 = __ldg(v + 384);
+                    if (MBFEA_SYM_STREAM >= 1) { v0 = ldg_stream(v); v1 = ldg_stream(v + 192); v2 = ldg_stream(v + 384); }
+                    else { v0 = __ldg(v); v1 = __ldg(v + 192); v2 = __ldg(v + 384); }
                 } else {
                     const double *v = vals + (int64_t)k * 36 + i * 6;
                     v0 = ldg2(v); v1 = ldg2(v + 2); v2 = ldg2(v + 4);
@@ -794,7 +806,9 @@ MBFEA_UNROLL(MBFEA_SYM_UNROLL)
                 for (int32_t l = lb; l < le; ++l) {
                     const double2 *v = reinterpret_cast<const double2 *>(vals) + __ldg(lofs + l) + i;
                     const double xj = __ldg(x + (int64_t)__ldg(lcol + l) * 6 + i);
-                    const double2 v0 = __ldg(v), v1 = __ldg(v + 192), v2 = __ldg(v + 384);
+                    double2 v0, v1, v2;
+                    if (MBFEA_SYM_STREAM >= 2) { v0 = ldg_stream(v); v1 = ldg_stream(v + 192); v2 = ldg_stream(v + 384); }
+                    else { v0 = __ldg(v); v1 = __ldg(v + 192); v2 = __ldg(v + 384); }
                     t0 = fma(v0.x, xj, t0); t1 = fma(v0.y, xj, t1);
                     t2 = fma(v1.x, xj, t2); t3 = fma(v1.y, xj, t3);
                     t4 = fma(v2.x, xj, t4); t5 = fma(v2.y, xj, t5);
@@ -1216,7 +1230,8 @@ __global__ void __launch_bounds__(256, 4) k_cg_update(
 // Thread = (row, scalar i): reads row i of T_v (24 B, consecutive threads -> consecutive addresses).
 // Multi-GPU (pc != null, inside the CG iteration): the last CTA sums the partials and all-gathers this rank's
 // r~.z~ through the NVLink mailboxes -- the slot and tag k_cg_update would have used for r~.r~.
-__global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t *__restrict__ agg, const float *__restrict__ t0,
+template <bool H16>
+__global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t *__restrict__ agg, const void *__restrict__ t0,
                                                        const double *__restrict__ rt, const double *__restrict__ z1,
                                                        double *__restrict__ zt, double *__restrict__ part,
                                                        const PcgScalars *sc, const PeerCtx *pc, double theta)
@@ -1228,14 +1243,15 @@ __global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t v = t / 6;
         const double *zc = z1 + (int64_t)__ldg(agg + v) * 6;
-        const float2 *T = reinterpret_cast<const float2 *>(t0 + t * 6);
-        const float2 a = __ldg(T), b = __ldg(T + 1), c = __ldg(T + 2);
+        float tr[6];
+        double tsc;
+        tblock_load_row<H16>(t0, v, (int)(t - v * 6), tr, tsc);
         const double ri = rt[t];
-        double s = (double)a.x * zc[0];
-        s = fma((double)a.y, zc[1], s);
-        s = fma((double)b.x, zc[2], s); s = fma((double)b.y, zc[3], s);
-        s = fma((double)c.x, zc[4], s); s = fma((double)c.y, zc[5], s);
-        s = fma(theta, s, ri);   // theta: weight of the coarse correction against the block-Jacobi term
+        double s = (double)tr[0] * zc[0];
+        s = fma((double)tr[1], zc[1], s);
+        s = fma((double)tr[2], zc[2], s); s = fma((double)tr[3], zc[3], s);
+        s = fma((double)tr[4], zc[4], s); s = fma((double)tr[5], zc[5], s);
+        s = fma(theta * tsc, s, ri);   // theta: weight of the coarse correction against the block-Jacobi term
         zt[t] = s;
         dot = fma(ri, s, dot);
     }
@@ -1251,10 +1267,12 @@ __global__ void __launch_bounds__(256, 4) k_ml_finish0(int64_t nb, const int32_t
     }
 }
 
-void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
+void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const void *t0, bool half, const double *rt,
                        const double *z1, double *zt, double *part, const PcgScalars *sc, const PeerCtx *pc, double theta)
 {
-    if (nb > 0 && grid > 0) k_ml_finish0<<<(unsigned)grid, 256, 0, st>>>(nb, agg, t0, rt, z1, zt, part, sc, pc, theta);
+    if (nb <= 0 || grid <= 0) return;
+    if (half) k_ml_finish0<true><<<(unsigned)grid, 256, 0, st>>>(nb, agg, t0, rt, z1, zt, part, sc, pc, theta);
+    else k_ml_finish0<false><<<(unsigned)grid, 256, 0, st>>>(nb, agg, t0, rt, z1, zt, part, sc, pc, theta);
 }
 
 // p = r~ + beta p.  Multi-GPU: the thread that produces a boundary block's entries also stores

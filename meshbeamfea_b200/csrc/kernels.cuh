@@ -18,6 +18,7 @@ constexpr int kTmaMaxRows = 32;     // block rows per tile  -> 192 consumer thre
 constexpr int kTmaStages = 3;
 
 constexpr int kMaxWorld = 16;
+constexpr int kTBlock16Bytes = 80;   // 16-bit transfer block of the multilevel apply (multilevel_math.hpp)
 
 // ---- multi-GPU over NVLink peer memory (no NCCL on the PCG data path) --------
 // One Mailbox per rank, in device memory that every peer maps through CUDA IPC.
@@ -204,16 +205,19 @@ void launch_ml_rap(cudaStream_t st, int64_t nc, int64_t nnzg, const int32_t *gro
 void launch_ml_blocks_to_dense(cudaStream_t st, int64_t nrows, int64_t nnz, const int32_t *rowptr, const int32_t *colidx,
                                const int32_t *row_of, const double *vals, double *dense);
 void launch_ml_dense_inverse(cudaStream_t st, int n, double *a, double *colk, int *flag);
+// transfer blocks (t0, pval): half = 80-byte blocks of 16-bit floats + scale (launch_ml_pack16), else 144-byte FP32 blocks
+void launch_ml_pack16(cudaStream_t st, int64_t nblk, const float *src, void *dst);
+void launch_ml_pack16(cudaStream_t st, int64_t nblk, const double *src, void *dst);
 void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_t *agg_ptr, const int32_t *agg_rows,
-                         const float *t0, const double *r, double *rc);
-void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const float *t0, const double *rt,
+                         const void *t0, bool half, const double *r, double *rc);
+void launch_ml_finish0(cudaStream_t st, int grid, int64_t nb, const int32_t *agg, const void *t0, bool half, const double *rt,
                        const double *z1, double *zt, double *part, const PcgScalars *sc = nullptr,
                        const PeerCtx *pc = nullptr /* kernels.cu: peer path publishes r~.z~ through the mailboxes */,
                        double theta = 1.0 /* weight of the coarse correction */);
 void launch_ml_restrict(cudaStream_t st, int64_t nc, int64_t nnzp, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
-                        const float *pval, const double *r, double *rc, int64_t fine_lo, int64_t fine_hi);
+                        const void *pval, bool half, const double *r, double *rc, int64_t fine_lo, int64_t fine_hi);
 void launch_ml_smooth_prolong(cudaStream_t st, int64_t row0, int64_t n, int64_t n_level, int64_t nnzp, const float *dinv,
-                              const int32_t *prow, const int32_t *pcol, const float *pval, const double *r, const double *zc,
+                              const int32_t *prow, const int32_t *pcol, const void *pval, bool half, const double *r, const double *zc,
                               double *z);
 
 }}  // namespace mbfea::dev

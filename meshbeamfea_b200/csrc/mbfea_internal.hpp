@@ -4,6 +4,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -113,9 +114,10 @@ int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<i
 // with_contrib=false skips the contributor lists (plan-only callers).
 // reorder: 0 never, 1 breadth-first when the canonical numbering has poor locality (auto), 2 breadth-first
 // always, 3 Morton order of the vertex coordinates (needs nodes_cm; falls back to 2 without)
+// after_free_map (optional): called once free_index, nb_global and the row range are final, before the pattern passes
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                 int32_t rank, int32_t world, bool with_contrib, HostPlan &plan, int reorder = 0,
-                const double *nodes_cm = nullptr);
+                const double *nodes_cm = nullptr, const std::function<void()> *after_free_map = nullptr);
 
 // Solver format from the full pattern (see HostPlan::uptr).  half=false keeps every
 // off-diagonal block in its own row (no transposed references).
@@ -173,9 +175,13 @@ struct MlHierarchy {
 // smooth_from: first level whose prolongator is smoothed (1 = every coarse-to-coarse transfer; large = none)
 // part_bounds / nparts (multi-GPU): row ranges of the ranks; fine-level aggregates then never straddle a rank and are
 // numbered rank-major (every rank owns a contiguous range of level-1 rows)
+// fine_pattern (optional): the fine aggregates need the positions only, so the build may start before the fine block
+// pattern exists; the gate is called once, when the pattern is first needed -- it blocks until the pattern is there,
+// stores its arrays (which then replace rowptr / colidx) and returns true, or returns false to abandon the build.
+using FinePatternGate = std::function<bool(const int32_t *&rowptr, const int32_t *&colidx)>;
 void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, const double *pos_rm, double cell0,
                         double ratio, int max_levels, int64_t coarsest_rows, int smooth_from, MlHierarchy &H,
-                        const int64_t *part_bounds = nullptr, int nparts = 1);
+                        const int64_t *part_bounds = nullptr, int nparts = 1, const FinePatternGate *fine_pattern = nullptr);
 
 // Flat image of a hierarchy for several ranks: rank 0 builds the hierarchy with every host core, packs it once, the
 // image travels H2D + one NCCL broadcast, and every rank fills its device arrays straight from the device copy

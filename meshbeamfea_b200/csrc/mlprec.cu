@@ -405,6 +405,29 @@ __global__ void __launch_bounds__(kT) k_ml_to_f32(int64_t n, const double *__res
     if (t < n) out[t] = (float)a[t];
 }
 
+// 16-bit transfer blocks (multilevel_math.hpp): 36 values / largest magnitude as halfs, + that magnitude; thread per block
+template <class S>
+__global__ void __launch_bounds__(kT) k_ml_pack16(int64_t nblk, const S *__restrict__ src, unsigned char *__restrict__ dst)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    float v[36];
+    float m = 0.0f;
+#pragma unroll
+    for (int x = 0; x < 36; ++x) { v[x] = (float)src[b * 36 + x]; m = fmaxf(m, fabsf(v[x])); }
+    const float inv = m > 0.0f ? 1.0f / m : 0.0f;
+    uint32_t w[20];
+#pragma unroll
+    for (int x = 0; x < 18; ++x) {
+        const __half2 h = __floats2half2_rn(v[2 * x] * inv, v[2 * x + 1] * inv);
+        w[x] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    w[18] = __float_as_uint(m); w[19] = 0u;
+    uint4 *o = reinterpret_cast<uint4 *>(dst + b * kTBlock16Bytes);
+#pragma unroll
+    for (int x = 0; x < 5; ++x) o[x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
+}
+
 // slices of the hierarchy image (several ranks): dst[i] = src[i] - delta, and the offsets of the ghost rows
 __global__ void __launch_bounds__(kT) k_ml_shift_i32(int64_t n, const int32_t *__restrict__ src, int32_t delta, int32_t *__restrict__ dst)
 {
@@ -446,9 +469,9 @@ __global__ void __launch_bounds__(kT) k_ml_blocks_to_dense(int64_t nrows, const 
 // fine restriction: rc[I] = sum over the members v of aggregate I (ascending) of T_v^T r~_v.  G lanes per
 // aggregate (8 when no aggregate has more than 8 members, else 32); lanes take members round-robin, then a
 // shuffle tree in a fixed pattern within the group.
-template <int G>
+template <int G, bool H16>
 __global__ void __launch_bounds__(kT) k_ml_restrict0(int64_t n_agg, const int32_t *__restrict__ agg_ptr,
-                                                     const int32_t *__restrict__ agg_rows, const float *__restrict__ t0,
+                                                     const int32_t *__restrict__ agg_rows, const void *__restrict__ t0,
                                                      const double *__restrict__ r, double *__restrict__ rc)
 {
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -457,13 +480,12 @@ __global__ void __launch_bounds__(kT) k_ml_restrict0(int64_t n_agg, const int32_
     if (gid < n_agg) {
         for (int32_t q = __ldg(agg_ptr + gid) + lane; q < __ldg(agg_ptr + gid + 1); q += G) {
             const int64_t v = __ldg(agg_rows + q);
-            const float4 *T = reinterpret_cast<const float4 *>(t0 + v * 36);
             float tt[36];
-#pragma unroll
-            for (int x = 0; x < 9; ++x) { const float4 f = __ldg(T + x); tt[4 * x] = f.x; tt[4 * x + 1] = f.y; tt[4 * x + 2] = f.z; tt[4 * x + 3] = f.w; }
+            double sc;
+            tblock_load<H16>(t0, v, tt, sc);
             const double2 r0 = *reinterpret_cast<const double2 *>(r + v * 6), r1 = *reinterpret_cast<const double2 *>(r + v * 6 + 2),
                           r2 = *reinterpret_cast<const double2 *>(r + v * 6 + 4);
-            const double rv[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
+            const double rv[6] = {sc * r0.x, sc * r0.y, sc * r1.x, sc * r1.y, sc * r2.x, sc * r2.y};
 #pragma unroll
             for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -484,9 +506,10 @@ __global__ void __launch_bounds__(kT) k_ml_restrict0(int64_t n_agg, const int32_
 // P_iI^T r_i; one warp per coarse row, lanes over the entries, fixed shuffle tree
 // [fine_lo, fine_hi): only the fine rows of this window contribute (several ranks: each rank sums over its own rows of the
 // finer level and the partial results are all-reduced)
+template <bool H16>
 __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *__restrict__ rrow,
                                                     const int32_t *__restrict__ rblk, const int32_t *__restrict__ rfine,
-                                                    const float *__restrict__ pval, const double *__restrict__ r,
+                                                    const void *__restrict__ pval, const double *__restrict__ r,
                                                     double *__restrict__ rc, int32_t fine_lo, int32_t fine_hi)
 {
     const int lane = threadIdx.x & 31;
@@ -496,14 +519,13 @@ __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *_
     for (int32_t e = __ldg(rrow + I) + lane; e < __ldg(rrow + I + 1); e += 32) {
         const int32_t fi = __ldg(rfine + e);
         if (fi < fine_lo || fi >= fine_hi) continue;
-        const float4 *P = reinterpret_cast<const float4 *>(pval + (int64_t)__ldg(rblk + e) * 36);
         const double *rv = r + (int64_t)fi * 6;
         float pp[36];
-#pragma unroll
-        for (int x = 0; x < 9; ++x) { const float4 f = __ldg(P + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
+        double sc;
+        tblock_load<H16>(pval, (int64_t)__ldg(rblk + e), pp, sc);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const double ri = rv[i];
+            const double ri = sc * rv[i];
 #pragma unroll
             for (int j = 0; j < 6; ++j) acc[j] = fma((double)pp[6 * i + j], ri, acc[j]);
         }
@@ -520,9 +542,10 @@ __global__ void __launch_bounds__(kT) k_ml_restrict(int64_t nc, const int32_t *_
 // the same for coarse levels whose rows are long (smoothed prolongators between small levels: hundreds of P blocks per
 // coarse row, a few hundred rows): one CTA of 128 threads per coarse row, one entry per thread and pass, fixed-order
 // CTA reduction -- the warp-per-row kernel above is latency-bound there (7 dependent passes per warp, 216 warps)
+template <bool H16>
 __global__ void __launch_bounds__(128) k_ml_restrict_wide(int64_t nc, const int32_t *__restrict__ rrow,
                                                           const int32_t *__restrict__ rblk, const int32_t *__restrict__ rfine,
-                                                          const float *__restrict__ pval, const double *__restrict__ r,
+                                                          const void *__restrict__ pval, const double *__restrict__ r,
                                                           double *__restrict__ rc, int32_t fine_lo, int32_t fine_hi)
 {
     __shared__ double red[4][6];
@@ -531,14 +554,13 @@ __global__ void __launch_bounds__(128) k_ml_restrict_wide(int64_t nc, const int3
     for (int32_t e = __ldg(rrow + I) + threadIdx.x; e < __ldg(rrow + I + 1); e += 128) {
         const int32_t fi = __ldg(rfine + e);
         if (fi < fine_lo || fi >= fine_hi) continue;
-        const float4 *P = reinterpret_cast<const float4 *>(pval + (int64_t)__ldg(rblk + e) * 36);
         const double *rv = r + (int64_t)fi * 6;
         float pp[36];
-#pragma unroll
-        for (int x = 0; x < 9; ++x) { const float4 f = __ldg(P + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
+        double sc;
+        tblock_load<H16>(pval, (int64_t)__ldg(rblk + e), pp, sc);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const double ri = rv[i];
+            const double ri = sc * rv[i];
 #pragma unroll
             for (int j = 0; j < 6; ++j) acc[j] = fma((double)pp[6 * i + j], ri, acc[j]);
         }
@@ -587,9 +609,10 @@ __global__ void __launch_bounds__(kT) k_ml_restrict_tent(int64_t nc, const int32
 }
 
 // coarse level on the way down: z_i = D_i^-1 r_i + sum over row i of P of P_iJ zc_J; thread = (row, scalar); FP32 D^-1, P
+template <bool H16>
 __global__ void __launch_bounds__(kT) k_ml_smooth_prolong(int64_t n, const float *__restrict__ dinv,
                                                           const int32_t *__restrict__ prow, const int32_t *__restrict__ pcol,
-                                                          const float *__restrict__ pval, const double *__restrict__ r,
+                                                          const void *__restrict__ pval, const double *__restrict__ r,
                                                           const double *__restrict__ zc, double *__restrict__ z, int64_t row0)
 {
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -603,20 +626,24 @@ __global__ void __launch_bounds__(kT) k_ml_smooth_prolong(int64_t n, const float
     s = fma((double)d0.y, rv[1], s); s = fma((double)d1.x, rv[2], s); s = fma((double)d1.y, rv[3], s);
     s = fma((double)d2.x, rv[4], s); s = fma((double)d2.y, rv[5], s);
     for (int32_t b = __ldg(prow + v); b < __ldg(prow + v + 1); ++b) {
-        const float2 *P = reinterpret_cast<const float2 *>(pval + (int64_t)b * 36 + 6 * i);
         const double *c = zc + (int64_t)__ldg(pcol + b) * 6;
-        const float2 p0 = __ldg(P), p1 = __ldg(P + 1), p2 = __ldg(P + 2);
-        s = fma((double)p0.x, c[0], s); s = fma((double)p0.y, c[1], s); s = fma((double)p1.x, c[2], s);
-        s = fma((double)p1.y, c[3], s); s = fma((double)p2.x, c[4], s); s = fma((double)p2.y, c[5], s);
+        float pr[6];
+        double sc;
+        tblock_load_row<H16>(pval, b, i, pr, sc);
+        double a = (double)pr[0] * c[0];
+        a = fma((double)pr[1], c[1], a); a = fma((double)pr[2], c[2], a);
+        a = fma((double)pr[3], c[3], a); a = fma((double)pr[4], c[4], a); a = fma((double)pr[5], c[5], a);
+        s = fma(sc, a, s);
     }
     z[t] = s;
 }
 
 // the same with one WARP per row, lanes over the row's P blocks (rows of smoothed prolongators between small levels hold
 // tens of blocks: the thread-per-scalar kernel above walks them one dependent gather after the other)
+template <bool H16>
 __global__ void __launch_bounds__(kT) k_ml_smooth_prolong_warp(int64_t n, const float *__restrict__ dinv,
                                                                const int32_t *__restrict__ prow, const int32_t *__restrict__ pcol,
-                                                               const float *__restrict__ pval, const double *__restrict__ r,
+                                                               const void *__restrict__ pval, const double *__restrict__ r,
                                                                const double *__restrict__ zc, double *__restrict__ z, int64_t row0)
 {
     const int lane = threadIdx.x & 31;
@@ -625,12 +652,11 @@ __global__ void __launch_bounds__(kT) k_ml_smooth_prolong_warp(int64_t n, const 
     const int64_t v = w + row0;
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int32_t b = __ldg(prow + v) + lane; b < __ldg(prow + v + 1); b += 32) {
-        const float4 *P = reinterpret_cast<const float4 *>(pval + (int64_t)b * 36);
         const double *c = zc + (int64_t)__ldg(pcol + b) * 6;
         float pp[36];
-#pragma unroll
-        for (int x = 0; x < 9; ++x) { const float4 f = __ldg(P + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
-        const double cc[6] = {c[0], c[1], c[2], c[3], c[4], c[5]};
+        double sc;
+        tblock_load<H16>(pval, b, pp, sc);
+        const double cc[6] = {sc * c[0], sc * c[1], sc * c[2], sc * c[3], sc * c[4], sc * c[5]};
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -756,21 +782,38 @@ void launch_ml_to_f32(cudaStream_t st, int64_t n, const double *a, float *out)
 {
     if (n > 0) k_ml_to_f32<<<blocks_for(n), kT, 0, st>>>(n, a, out);
 }
+void launch_ml_pack16(cudaStream_t st, int64_t nblk, const float *src, void *dst)
+{
+    if (nblk > 0) k_ml_pack16<float><<<blocks_for(nblk), kT, 0, st>>>(nblk, src, static_cast<unsigned char *>(dst));
+}
+void launch_ml_pack16(cudaStream_t st, int64_t nblk, const double *src, void *dst)
+{
+    if (nblk > 0) k_ml_pack16<double><<<blocks_for(nblk), kT, 0, st>>>(nblk, src, static_cast<unsigned char *>(dst));
+}
 void launch_ml_restrict0(cudaStream_t st, int64_t n_agg, int group, const int32_t *agg_ptr, const int32_t *agg_rows,
-                         const float *t0, const double *r, double *rc)
+                         const void *t0, bool half, const double *r, double *rc)
 {
     if (n_agg <= 0) return;
-    if (group == 8) k_ml_restrict0<8><<<blocks_for(n_agg * 8), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
-    else k_ml_restrict0<32><<<blocks_for(n_agg * 32), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
+    if (group == 8) {
+        if (half) k_ml_restrict0<8, true><<<blocks_for(n_agg * 8), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
+        else k_ml_restrict0<8, false><<<blocks_for(n_agg * 8), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
+    } else {
+        if (half) k_ml_restrict0<32, true><<<blocks_for(n_agg * 32), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
+        else k_ml_restrict0<32, false><<<blocks_for(n_agg * 32), kT, 0, st>>>(n_agg, agg_ptr, agg_rows, t0, r, rc);
+    }
 }
 void launch_ml_restrict(cudaStream_t st, int64_t nc, int64_t nnzp, const int32_t *rrow, const int32_t *rblk, const int32_t *rfine,
-                        const float *pval, const double *r, double *rc, int64_t fine_lo, int64_t fine_hi)
+                        const void *pval, bool half, const double *r, double *rc, int64_t fine_lo, int64_t fine_hi)
 {
     if (nc <= 0) return;
-    if (nnzp > 48 * nc && nc <= 65535)   // long rows on a small level
-        k_ml_restrict_wide<<<(unsigned)nc, 128, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, (int32_t)fine_lo, (int32_t)fine_hi);
-    else
-        k_ml_restrict<<<blocks_for(nc * 32), kT, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, (int32_t)fine_lo, (int32_t)fine_hi);
+    const int32_t lo = (int32_t)fine_lo, hi = (int32_t)fine_hi;
+    if (nnzp > 48 * nc && nc <= 65535) {   // long rows on a small level
+        if (half) k_ml_restrict_wide<true><<<(unsigned)nc, 128, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, lo, hi);
+        else k_ml_restrict_wide<false><<<(unsigned)nc, 128, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, lo, hi);
+    } else {
+        if (half) k_ml_restrict<true><<<blocks_for(nc * 32), kT, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, lo, hi);
+        else k_ml_restrict<false><<<blocks_for(nc * 32), kT, 0, st>>>(nc, rrow, rblk, rfine, pval, r, rc, lo, hi);
+    }
 }
 void launch_ml_restrict_tent(cudaStream_t st, int64_t nc, const int32_t *rrow, const int32_t *rfine, const double *off,
                              const double *r, double *rc, int64_t fine_lo, int64_t fine_hi)
@@ -778,14 +821,17 @@ void launch_ml_restrict_tent(cudaStream_t st, int64_t nc, const int32_t *rrow, c
     if (nc > 0) k_ml_restrict_tent<<<blocks_for(nc * 8), kT, 0, st>>>(nc, rrow, rfine, off, r, rc, (int32_t)fine_lo, (int32_t)fine_hi);
 }
 void launch_ml_smooth_prolong(cudaStream_t st, int64_t row0, int64_t n, int64_t n_level, int64_t nnzp, const float *dinv,
-                              const int32_t *prow, const int32_t *pcol, const float *pval, const double *r, const double *zc,
+                              const int32_t *prow, const int32_t *pcol, const void *pval, bool half, const double *r, const double *zc,
                               double *z)
 {
     if (n <= 0) return;
-    if (nnzp > 6 * n_level)   // rows of many blocks: a warp per row
-        k_ml_smooth_prolong_warp<<<blocks_for(n * 32), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
-    else
-        k_ml_smooth_prolong<<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
+    if (nnzp > 6 * n_level) {   // rows of many blocks: a warp per row
+        if (half) k_ml_smooth_prolong_warp<true><<<blocks_for(n * 32), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
+        else k_ml_smooth_prolong_warp<false><<<blocks_for(n * 32), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
+    } else {
+        if (half) k_ml_smooth_prolong<true><<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
+        else k_ml_smooth_prolong<false><<<blocks_for(n * 6), kT, 0, st>>>(n, dinv, prow, pcol, pval, r, zc, z, row0);
+    }
 }
 void launch_ml_smooth_prolong_tent(cudaStream_t st, int64_t row0, int64_t n, const float *dinv, const int32_t *agg, const double *off,
                                    const double *r, const double *zc, double *z)

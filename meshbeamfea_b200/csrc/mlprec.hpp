@@ -34,6 +34,8 @@ struct MlCoarse {                 // one coarse level (l >= 1) and its transfer 
     DevBuf<int32_t> agg, prow, pcol, prow_of, rrow, rblk, rfine, aprow, apcol, aprow_of;
     DevBuf<double> off, pval, apval;
     DevBuf<float> pval32, dinv32;   // what the apply reads: the same rounded values in restriction and prolongation
+    DevBuf<unsigned char> pvalh;    // P as 80-byte blocks of 16-bit floats + scale (multilevel_math.hpp), in place of pval32
+    const void *p_apply(bool half16) const { return half16 ? (const void *)pvalh.p : (const void *)pval32.p; }
 };
 
 // Several ranks (vertex-block partition): the fine-level transfer is LOCAL to a rank -- aggregates never straddle a
@@ -54,6 +56,11 @@ class MlPrec {
 public:
     MlParams par;
     bool symbolic_ok = false, numeric_ok = false;
+    // Transfer blocks of the apply in the 16-bit scaled format (MBFEA_ML_HALF=1).  OFF by default: measured on the 119^3
+    // lattice it saves 6 % of the solve at an unchanged iteration count (354), but on the thin gridshell (n = 1826) the
+    // preconditioner stops working -- the coarse spaces must hold the rigid-body modes to ~1e-7: a relative error eps in T
+    // adds eps^2 |K| of spurious energy to modes whose true energy is |K| / kappa, and kappa is 1e9 there.
+    bool half16 = false;
     int64_t nb = 0;
     std::vector<int64_t> rows;    // rows of every level, fine first
     double ms_symbolic = 0.0;     // host wall time of the last build_symbolic (hierarchy + uploads)
@@ -67,7 +74,7 @@ public:
                         double mean_beam_length, const MlDist *dist = nullptr);
     // the host half alone (what rank 0 runs for everybody on several ranks) ...
     void build_hierarchy_host(int64_t nb, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
-                              double mean_beam_length, int world, MlHierarchy &H) const;
+                              double mean_beam_length, int world, MlHierarchy &H, const FinePatternGate *fine_pattern = nullptr) const;
     // ... and the device half from a prebuilt hierarchy: fine_nnz = blocks of the (global) fine pattern, own_first_block =
     // index of the first block of the rank's first row in it (0 on one rank)
     bool upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nb_global, int64_t fine_nnz, int64_t own_first_block,
@@ -96,7 +103,10 @@ private:
     void exchange_slices(cudaStream_t st, double *buf, const std::vector<int64_t> &begin, int width);
     DevBuf<int32_t> agg0, agg_ptr0, agg_rows0, gal_ptr0, gal_src0, frow0;
     DevBuf<double> off0;
-    DevBuf<float> t0;
+    DevBuf<int64_t> ghost_stage;
+    DevBuf<float> t0;              // fine transfer T_v = L_v^T B(d_v), FP32 (with half16: scratch of the packing pass)
+    DevBuf<unsigned char> t0h;     // the same as 80-byte 16-bit blocks: what the apply reads
+    const void *t0_apply() const { return half16 ? (const void *)t0h.p : (const void *)t0.p; }
     int group0 = 32;
     std::vector<std::unique_ptr<MlCoarse>> lv;   // lv[m]: level m + 1
     std::vector<std::unique_ptr<MlCoarse>> spare; // level objects of the previous job, in level order (buffers keep their capacity)

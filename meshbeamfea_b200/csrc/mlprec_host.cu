@@ -51,12 +51,12 @@ std::unique_ptr<MlCoarse> MlPrec::take_level()
 }
 
 void MlPrec::build_hierarchy_host(int64_t nbg, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
-                                  double mean_len, int world_, MlHierarchy &H) const
+                                  double mean_len, int world_, MlHierarchy &H, const FinePatternGate *fine_pattern) const
 {
     std::vector<int64_t> bounds((size_t)world_ + 1);
     for (int q = 0; q <= world_; ++q) bounds[(size_t)q] = nbg * q / world_;
     build_ml_hierarchy(nbg, h_rowptr, h_colidx, pos_rm, par.cell * mean_len, par.ratio, par.max_levels, par.coarsest_rows,
-                       std::max(1, par.smooth_from), H, world_ > 1 ? bounds.data() : nullptr, world_);
+                       std::max(1, par.smooth_from), H, world_ > 1 ? bounds.data() : nullptr, world_, fine_pattern);
 }
 
 bool MlPrec::build_symbolic(cudaStream_t st, int64_t nb_, const int32_t *h_rowptr, const int32_t *h_colidx, const double *pos_rm,
@@ -77,6 +77,7 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
     const double t0w = wall_ms();
     reset();
     if (nbg <= 0) return false;
+    half16 = [] { const char *e = std::getenv("MBFEA_ML_HALF"); return e && *e == '1'; }();
     rank = dist ? dist->rank : 0; world = dist ? dist->world : 1;
     nc = dist ? dist->nc : nullptr; comm = dist ? dist->comm : nullptr;
     std::vector<int64_t> bounds((size_t)world + 1);
@@ -138,6 +139,7 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
         CK(frow0.alloc((size_t)dist->loc_rowptr[nbl]));
     }
     CK(t0.alloc((size_t)nb * 36));
+    if (half16) CK(t0h.alloc((size_t)nb * kTBlock16Bytes));
     rows.push_back(nb);
     for (size_t m = 0; m < L; ++m) {
         std::unique_ptr<MlCoarse> c = take_level();
@@ -186,7 +188,7 @@ void MlPrec::alloc_level_buffers(cudaStream_t st, MlCoarse &c, bool has_next)
     launch_ml_row_of(st, c.n, c.prow.p, c.prow_of.p);
     launch_ml_row_of(st, c.n, c.aprow.p, c.aprow_of.p);
     CK(c.pval.alloc((size_t)c.nnzp * 36)); CK(c.apval.alloc((size_t)c.nnzap * 36));
-    if (c.smoothed) CK(c.pval32.alloc((size_t)c.nnzp * 36));
+    if (c.smoothed) { if (half16) CK(c.pvalh.alloc((size_t)c.nnzp * kTBlock16Bytes)); else CK(c.pval32.alloc((size_t)c.nnzp * 36)); }
     CK(c.lfac.alloc((size_t)c.n * 36)); CK(c.sinv.alloc((size_t)c.n * 36)); CK(c.dinv.alloc((size_t)c.n * 36));
     CK(c.dinv32.alloc((size_t)c.n * 36));
 }
@@ -196,6 +198,7 @@ bool MlPrec::upload_from_image(cudaStream_t st, const unsigned char *d_img, cons
     const double t0w = wall_ms();
     reset();
     if (hd.magic != kMlImageMagic || hd.levels < 1 || hd.levels > kMlImageMaxLevels || hd.world != dist.world) return false;
+    half16 = [] { const char *e = std::getenv("MBFEA_ML_HALF"); return e && *e == '1'; }();
     rank = dist.rank; world = dist.world; nc = dist.nc; comm = dist.comm;
     const size_t L = (size_t)hd.levels;
     if (6 * hd.lv[L - 1].n_coarse > 3072) return false;
@@ -223,7 +226,7 @@ bool MlPrec::upload_from_image(cudaStream_t st, const unsigned char *d_img, cons
     CK(cudaMemcpyAsync(agg0.p, src_i(0, 0) + r0, (size_t)nbl * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     CK(off0.alloc((size_t)3 * (size_t)(nbl + ng)));
     CK(cudaMemcpyAsync(off0.p, src_d(0, 1) + 3 * r0, (size_t)3 * nbl * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    DevBuf<int64_t> d_ghost;
+    DevBuf<int64_t> &d_ghost = ghost_stage;   // kept between jobs
     if (ng > 0) {
         CK(d_ghost.alloc((size_t)ng));
         CK(cudaMemcpyAsync(d_ghost.p, dist.ghost_global->data(), (size_t)ng * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -241,6 +244,7 @@ bool MlPrec::upload_from_image(cudaStream_t st, const unsigned char *d_img, cons
     launch_ml_shift_i32(st, g1 - g0, src_i(0, 8) + g0, (int32_t)hd.own_first[rank], gal_src0.p);
     CK(frow0.alloc((size_t)dist.loc_rowptr[nbl]));
     CK(t0.alloc((size_t)nb * 36));
+    if (half16) CK(t0h.alloc((size_t)nb * kTBlock16Bytes));
     rows.push_back(nb);
     // ---- coarse levels: replicated
     for (size_t m = 0; m < L; ++m) {
@@ -278,6 +282,7 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
     int64_t k = 0;
     launch_ml_row_of(st, nb, d_rowptr, frow0.p);
     launch_ml_make_t0(st, nb, d_lfac, off0.p, t0.p);
+    if (half16) { launch_ml_pack16(st, nb, t0.p, t0h.p); ++k; }
     // level-1 matrix: the own block rows (all of them on one rank), then the slices of the other ranks
     launch_ml_galerkin0(st, blk_begin[(size_t)rank + 1] - blk_begin[(size_t)rank], gal_ptr0.p, gal_src0.p, frow0.p, d_colidx, d_vals,
                         off0.p, lv[0]->vals.p + 36 * blk_begin[(size_t)rank]);
@@ -323,7 +328,11 @@ void MlPrec::build_numeric(cudaStream_t st, const int32_t *d_rowptr, const int32
         launch_ml_diag_inv(st, c.n, c.sinv.p, c.dinv.p, c.dinv32.p);
         launch_ml_make_p(st, c.n, c.nnzp, c.prow.p, c.pcol.p, c.prow_of.p, c.rowptr.p, c.colidx.p, c.vals.p, c.agg.p, c.off.p,
                          c.dinv.p, c.smoothed ? par.omega : 0.0, c.pval.p);
-        if (c.smoothed) { launch_ml_to_f32(st, c.nnzp * 36, c.pval.p, c.pval32.p); ++k; }
+        if (c.smoothed) {
+            if (half16) launch_ml_pack16(st, c.nnzp, c.pval.p, c.pvalh.p);
+            else launch_ml_to_f32(st, c.nnzp * 36, c.pval.p, c.pval32.p);
+            ++k;
+        }
         launch_ml_ap(st, c.n, c.nnzap, c.aprow.p, c.apcol.p, c.aprow_of.p, c.rowptr.p, c.colidx.p, c.vals.p, c.prow.p, c.pcol.p,
                      c.pval.p, c.apval.p);
         launch_ml_rap(st, nx.n, nx.nnz, nx.rowptr.p, nx.colidx.p, nx.row_of.p, c.rrow.p, c.rblk.p, c.rfine.p, c.pval.p, c.aprow.p,
@@ -358,7 +367,7 @@ void MlPrec::exchange_slices(cudaStream_t st, double *buf, const std::vector<int
 void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, int grid, const PcgScalars *sc, const PeerCtx *pc)
 {
     const size_t L = lv.size();
-    launch_ml_restrict0(st, agg_begin[(size_t)rank + 1] - agg_begin[(size_t)rank], group0, agg_ptr0.p, agg_rows0.p, t0.p, rt,
+    launch_ml_restrict0(st, agg_begin[(size_t)rank + 1] - agg_begin[(size_t)rank], group0, agg_ptr0.p, agg_rows0.p, t0_apply(), half16, rt,
                         lv[0]->r.p + 6 * agg_begin[(size_t)rank]);
     // several ranks: level 1 stays DISTRIBUTED in the apply -- every rank restricts its own level-1 rows to level 2 (partial
     // sums, all-reduced: 48 B per level-2 row) and prolongs back onto its own level-1 rows only, which is all the fine
@@ -368,7 +377,7 @@ void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, 
     for (size_t m = 0; m + 1 < L; ++m) {
         const int64_t lo = (m == 0 && split1) ? agg_begin[(size_t)rank] : 0, hi = (m == 0 && split1) ? agg_begin[(size_t)rank + 1] : lv[m]->n;
         if (lv[m]->smoothed)
-            launch_ml_restrict(st, lv[m + 1]->n, lv[m]->nnzp, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->pval32.p, lv[m]->r.p, lv[m + 1]->r.p, lo, hi);
+            launch_ml_restrict(st, lv[m + 1]->n, lv[m]->nnzp, lv[m]->rrow.p, lv[m]->rblk.p, lv[m]->rfine.p, lv[m]->p_apply(half16), half16, lv[m]->r.p, lv[m + 1]->r.p, lo, hi);
         else
             launch_ml_restrict_tent(st, lv[m + 1]->n, lv[m]->rrow.p, lv[m]->rfine.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->r.p, lo, hi);
         if (m == 0 && split1) NK(nc->AllReduce(lv[1]->r.p, lv[1]->r.p, (size_t)(6 * lv[1]->n), nccl::kFloat64, nccl::kSum, comm, st));
@@ -378,13 +387,13 @@ void MlPrec::apply(cudaStream_t st, const double *rt, double *zt, double *part, 
         const int64_t row0 = (m == 0 && split1) ? agg_begin[(size_t)rank] : 0;
         const int64_t cnt = (m == 0 && split1) ? agg_begin[(size_t)rank + 1] - row0 : lv[m]->n;
         if (lv[m]->smoothed)
-            launch_ml_smooth_prolong(st, row0, cnt, lv[m]->n, lv[m]->nnzp, lv[m]->dinv32.p, lv[m]->prow.p, lv[m]->pcol.p, lv[m]->pval32.p, lv[m]->r.p,
+            launch_ml_smooth_prolong(st, row0, cnt, lv[m]->n, lv[m]->nnzp, lv[m]->dinv32.p, lv[m]->prow.p, lv[m]->pcol.p, lv[m]->p_apply(half16), half16, lv[m]->r.p,
                                      lv[m + 1]->z.p, lv[m]->z.p);
         else
             launch_ml_smooth_prolong_tent(st, row0, cnt, lv[m]->dinv32.p, lv[m]->agg.p, lv[m]->off.p, lv[m]->r.p, lv[m + 1]->z.p,
                                           lv[m]->z.p);
     }
-    launch_ml_finish0(st, grid, nb, agg0.p, t0.p, rt, lv[0]->z.p, zt, part, sc, pc, par.theta);
+    launch_ml_finish0(st, grid, nb, agg0.p, t0_apply(), half16, rt, lv[0]->z.p, zt, part, sc, pc, par.theta);
 }
 
 }  // namespace mbfea

@@ -2,6 +2,11 @@
 // that the arithmetic is unit-tested on the CPU (tests/test_host_logic.py::test_multilevel_transfer_math).
 #pragma once
 #if defined(__CUDACC__)
+#include <cuda_fp16.h>
+
+#include <cstdint>
+
+#include "kernels.cuh"
 #define MBFEA_HD __host__ __device__ __forceinline__
 #else
 #define MBFEA_HD inline
@@ -53,5 +58,64 @@ MBFEA_HD double galerkin_entry(const double *da, const double *db, const double 
     }
     return v;
 }
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// Transfer blocks of the multilevel apply (fine T_v, coarse P_iJ).  The apply is bandwidth-bound and needs no more than
+// ~3 digits of the transfer entries (the preconditioner only has to stay symmetric: restriction and prolongation read
+// the SAME rounded values), so a block is stored as 36 16-bit floats normalised by the block's largest magnitude plus
+// that magnitude as a float: 80 bytes, 16-byte aligned, instead of 144 (FP32).  The per-block scale makes the format
+// independent of the units of the mesh (FP16 alone would overflow on L_v^T entries above 65504).
+// H16 = false: plain FP32 blocks of 144 bytes -- the DEFAULT: the 16-bit format is an opt-in experiment (MBFEA_ML_HALF=1),
+// fine on stiff 3-D lattices, not accurate enough for thin shells (see MlPrec::half16).
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ float2 tb_half2(uint32_t u)
+{
+    return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+}
+// whole block -> pp[36] (row-major), scale
+template <bool H16>
+__device__ __forceinline__ void tblock_load(const void *base, int64_t b, float (&pp)[36], double &scale)
+{
+    if (H16) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(base) + b * kTBlock16Bytes);
+        uint4 w[5];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) w[x] = __ldg(q + x);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const float2 a = tb_half2(w[x].x), c = tb_half2(w[x].y), d = tb_half2(w[x].z), e = tb_half2(w[x].w);
+            pp[8 * x] = a.x; pp[8 * x + 1] = a.y; pp[8 * x + 2] = c.x; pp[8 * x + 3] = c.y;
+            pp[8 * x + 4] = d.x; pp[8 * x + 5] = d.y; pp[8 * x + 6] = e.x; pp[8 * x + 7] = e.y;
+        }
+        const float2 a = tb_half2(w[4].x), c = tb_half2(w[4].y);
+        pp[32] = a.x; pp[33] = a.y; pp[34] = c.x; pp[35] = c.y;
+        scale = (double)__uint_as_float(w[4].z);
+    } else {
+        const float4 *q = reinterpret_cast<const float4 *>(static_cast<const float *>(base) + b * 36);
+#pragma unroll
+        for (int x = 0; x < 9; ++x) { const float4 f = __ldg(q + x); pp[4 * x] = f.x; pp[4 * x + 1] = f.y; pp[4 * x + 2] = f.z; pp[4 * x + 3] = f.w; }
+        scale = 1.0;
+    }
+}
+// row i of a block -> row[6], scale
+template <bool H16>
+__device__ __forceinline__ void tblock_load_row(const void *base, int64_t b, int i, float (&row)[6], double &scale)
+{
+    if (H16) {
+        const unsigned char *p = static_cast<const unsigned char *>(base) + b * kTBlock16Bytes;
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p + 12 * i);
+        const float2 a = tb_half2(__ldg(q)), c = tb_half2(__ldg(q + 1)), d = tb_half2(__ldg(q + 2));
+        row[0] = a.x; row[1] = a.y; row[2] = c.x; row[3] = c.y; row[4] = d.x; row[5] = d.y;
+        scale = (double)__ldg(reinterpret_cast<const float *>(p + 72));
+    } else {
+        const float2 *q = reinterpret_cast<const float2 *>(static_cast<const float *>(base) + b * 36 + 6 * i);
+        const float2 a = __ldg(q), c = __ldg(q + 1), d = __ldg(q + 2);
+        row[0] = a.x; row[1] = a.y; row[2] = c.x; row[3] = c.y; row[4] = d.x; row[5] = d.y;
+        scale = 1.0;
+    }
+}
+#endif
 
 }}  // namespace mbfea::dev
