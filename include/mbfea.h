@@ -243,6 +243,14 @@ int mbfea_time_assemble(mbfea_ctx *ctx, int32_t warmup, int32_t reps, double *ms
  * Slots 1,3,5,6,7 are only written on the multi-GPU peer-memory path.            */
 int mbfea_debug_trace(mbfea_ctx *ctx, uint64_t *stamps, int64_t max_iters, int64_t *slots_per_iter);
 
+/* Parity tap of the set-up path.  On one rank the block pattern, the contributor lists of the assembly and the
+ * solver format are built on the device; several ranks (and internally renumbered or irregular jobs) use the host
+ * builders.  This call rebuilds all of them with the HOST builders from the mesh the device holds and compares them
+ * with the device arrays, entry for entry.  mismatches[k] = number of differing entries (-1: different length) of
+ * 0 rowptr, 1 colidx, 2 diag_idx, 3 contrib_ptr, 4 contrib, 5 uptr, 6 ucol, 7 usrc, 8 lptr, 9 lcol, 10 lofs,
+ * 11 tile_base.  *built_on_device: 1 pattern on the device, 2 pattern and solver format on the device, 0 neither. */
+int mbfea_debug_compare_plan(mbfea_ctx *ctx, int64_t mismatches[12], int32_t *built_on_device);
+
 /* ---- multi-GPU (one process per GPU; vertex-block partition) -------------
  * Rank 0 makes an id, the launcher broadcasts the 128 bytes (torch.distributed
  * in bench.py), every rank calls comm_init before set_job.  Collectives on the

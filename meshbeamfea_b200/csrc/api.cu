@@ -72,6 +72,11 @@ struct mbfea_ctx {
     // device: pattern
     DevBuf<int32_t> rowptr, colidx, diag_idx, contrib_ptr, contrib, tile_row, tile_row_s, send_rows;
     DevBuf<int32_t> uptr, ucol, usrc, lptr, lcol, lofs, ilv_base;   // solver format (HostPlan::uptr ...)
+    int64_t n_stored = 0, n_refs = 0, tile_units = 0;   // stored blocks, transposed references, 16-byte units of the interleaved value array
+    // pattern / contributor lists / solver format built on the device (plan_dev.cu): scratch, kept between jobs
+    bool device_plan = false;
+    DevBuf<int32_t> pd_cnt, pd_cur, pd_start, pd_scan;
+    DevBuf<unsigned long long> pd_ent, pd_tot;
     // device: matrix + vectors.  vals = assembled K (full pattern); vals_s = stored blocks of
     // K~ = S K S^T; lfac/sinv = Cholesky factor of the diagonal blocks and its inverse
     DevBuf<double> vals, vals_s, lfac, sinv, f, ft, x, y, rt, p, Ap, sdir, sendbuf;
@@ -908,7 +913,55 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                 }
             });
         };
-        build_plan(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, true, c->plan, reorder, nodes_cm, &start_ml_thread);
+        build_plan_begin(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, c->plan, reorder, nodes_cm);
+        start_ml_thread();
+        // One rank, canonical numbering: the block pattern, the contributor lists and the solver format are built on the
+        // DEVICE (plan_dev.cu) from the mesh that is already there -- the same arrays as the host builders', entry for
+        // entry -- and only the pattern comes back (the hierarchy build and the taps read it).  Several ranks, an
+        // internally renumbered job or MBFEA_HOST_PLAN=1: the host builders and an upload.
+        static const bool force_host_plan = [] { const char *e = std::getenv("MBFEA_HOST_PLAN"); return e && *e == '1'; }();
+        const bool device_plan = !force_host_plan && c->opt.world == 1 && c->plan.perm.empty() && c->plan.nb_global > 0 &&
+                                 4 * E < (int64_t)INT32_MAX - 8;
+        c->device_plan = device_plan;
+        const int64_t nb = c->nb(), ng_dev = 0;
+        (void)ng_dev;
+        int64_t nnzb_dev = 0;
+        if (device_plan) {
+            HostPlan &P = c->plan;
+            // scratch: entries per row / cursor, entry start, blocks per row, scan scratch, 64-bit entries
+            CK(c->pd_cnt.alloc((size_t)nb + 1)); CK(c->pd_cur.alloc((size_t)nb + 1)); CK(c->pd_start.alloc((size_t)nb + 1));
+            CK(c->pd_scan.alloc((size_t)scan_i32_scratch(nb + 1)));
+            CK(cudaMemsetAsync(c->pd_cnt.p, 0, ((size_t)nb + 1) * sizeof(int32_t), c->st));
+            CK(cudaMemsetAsync(c->pd_cur.p, 0, ((size_t)nb + 1) * sizeof(int32_t), c->st));
+            launch_pd_count(c->st, E, c->stg_elems.p, c->free_canon.p, c->pd_cnt.p);
+            launch_scan_i32(c->st, nb, c->pd_cnt.p, c->pd_start.p, c->pd_scan.p);
+            int32_t nent = 0;
+            CK(cudaMemcpyAsync(&nent, c->pd_start.p + nb, sizeof nent, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            CK(c->pd_ent.alloc((size_t)nent + 1));
+            launch_pd_fill(c->st, E, c->stg_elems.p, c->free_canon.p, c->pd_start.p, c->pd_cur.p, c->pd_ent.p);
+            launch_pd_sort(c->st, nb, c->pd_start.p, c->pd_ent.p, c->pd_cnt.p);   // pd_cnt now: blocks per row
+            CK(c->rowptr.alloc((size_t)nb + 1));
+            launch_scan_i32(c->st, nb, c->pd_cnt.p, c->rowptr.p, c->pd_scan.p);
+            int32_t nnz32 = 0;
+            CK(cudaMemcpyAsync(&nnz32, c->rowptr.p + nb, sizeof nnz32, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            nnzb_dev = nnz32;
+            CK(c->colidx.alloc((size_t)nnzb_dev)); CK(c->diag_idx.alloc((size_t)nb));
+            CK(c->contrib_ptr.alloc((size_t)nnzb_dev + 1)); CK(c->contrib.alloc((size_t)nent));
+            launch_pd_emit(c->st, nb, c->pd_start.p, c->pd_ent.p, c->rowptr.p, c->colidx.p, c->diag_idx.p, c->contrib_ptr.p, c->contrib.p);
+            // the pattern on the host: hierarchy build, component detection, taps
+            P.rowptr.resize((size_t)nb + 1); P.colidx.resize((size_t)nnzb_dev);
+            CK(cudaMemcpyAsync(P.rowptr.data(), c->rowptr.p, ((size_t)nb + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(P.colidx.data(), c->colidx.p, (size_t)nnzb_dev * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            P.diag_idx.clear(); P.contrib_ptr.clear(); P.contrib.clear();
+            P.ghost_global.clear(); P.ghost_owner.clear(); P.send_rows.clear(); P.send_dest.clear(); P.neighbors.clear();
+            CK(c->send_rows.alloc(0));
+            lap("pattern on the device + download");
+        } else {
+            build_plan_pattern(E, elems_cm, true, c->plan);
+        }
         if (c->opt.batch_mode != 1) find_components(c->plan, 1024, 32);
         else { c->plan.comp_ptr.clear(); c->plan.comp_max_rows = 0; }
         const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
@@ -917,7 +970,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         const bool ml_possible = !batched && c->plan.nb_global >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
         const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
         host_ms += now_ms() - tp0;
-        const int64_t nb = c->nb(), ng = c->ng(), nnzb = c->plan.nnzb();
+        const int64_t ng = c->ng(), nnzb = c->plan.nnzb();
         // the reduced numbering the kernels use: K3's map, composed with the internal renumbering when there is one
         if (c->plan.perm.empty()) {
             CK(cudaMemcpyAsync(c->free_index.p, c->free_canon.p, (size_t)V * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->st));
@@ -927,29 +980,71 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             launch_apply_perm(c->st, V, c->free_canon.p, d_perm.p, c->free_index.p);
             CK(cudaStreamSynchronize(c->st));
         }
-        upload(c, c->rowptr, c->plan.rowptr);
-        upload(c, c->colidx, c->plan.colidx);
-        upload(c, c->diag_idx, c->plan.diag_idx);
-        upload(c, c->contrib_ptr, c->plan.contrib_ptr);
-        upload(c, c->contrib, c->plan.contrib);
-        upload(c, c->send_rows, c->plan.send_rows);
-        lap("pattern upload");
+        if (!device_plan) {
+            upload(c, c->rowptr, c->plan.rowptr);
+            upload(c, c->colidx, c->plan.colidx);
+            upload(c, c->diag_idx, c->plan.diag_idx);
+            upload(c, c->contrib_ptr, c->plan.contrib_ptr);
+            upload(c, c->contrib, c->plan.contrib);
+            upload(c, c->send_rows, c->plan.send_rows);
+            lap("pattern upload");
+        }
         // solver format: symmetric-half storage unless full rows are asked for (the TMA kernel
         // streams whole rows and has no transposed-reference path)
         const double tp1 = now_ms();
         const bool half = !batched && (c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2));
-        build_solver_format(c->plan, half);
+        bool format_on_device = false;
+        if (device_plan && half) {
+            // upper rule on the device; an irregular numbering that pads the 32-row tiles by more than 5 % under it
+            // (or a value array beyond 2^31 units) goes to the host builder, which balances the pair orientation
+            const int64_t ntiles = (nb + 31) / 32;
+            CK(c->uptr.alloc((size_t)nb + 1)); CK(c->lptr.alloc((size_t)nb + 1)); CK(c->ilv_base.alloc((size_t)ntiles + 1));
+            CK(c->pd_tot.alloc(2));
+            CK(cudaMemsetAsync(c->pd_tot.p, 0, 2 * sizeof(unsigned long long), c->st));
+            int32_t *nu = c->pd_cnt.p, *nl = c->pd_cur.p, *tunits = c->pd_start.p;   // scratch of the pattern pass, free again
+            launch_pf_count(c->st, nb, c->rowptr.p, c->diag_idx.p, nu, nl);
+            launch_pf_tiles(c->st, nb, nu, tunits, c->pd_tot.p);
+            unsigned long long tot[2] = {0, 0};
+            CK(cudaMemcpyAsync(tot, c->pd_tot.p, sizeof tot, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            static const bool no_balance = std::getenv("MBFEA_NO_BALANCE") != nullptr;
+            const bool pads = tot[1] * 20 > tot[0] * 21 && !no_balance;
+            if (!pads && tot[1] * 18 <= (unsigned long long)INT32_MAX) {
+                launch_scan_i32(c->st, nb, nu, c->uptr.p, c->pd_scan.p);
+                launch_scan_i32(c->st, nb, nl, c->lptr.p, c->pd_scan.p);
+                launch_scan_i32(c->st, ntiles, tunits, c->ilv_base.p, c->pd_scan.p);
+                c->n_stored = (int64_t)tot[0];
+                c->n_refs = nnzb - nb - c->n_stored;
+                c->tile_units = (int64_t)(tot[1] * 18);
+                CK(c->ucol.alloc((size_t)c->n_stored)); CK(c->usrc.alloc((size_t)c->n_stored));
+                CK(c->lcol.alloc((size_t)c->n_refs)); CK(c->lofs.alloc((size_t)c->n_refs));
+                launch_pf_fill(c->st, nb, c->rowptr.p, c->colidx.p, c->diag_idx.p, c->uptr.p, c->lptr.p, c->ilv_base.p, c->ucol.p, c->usrc.p,
+                               c->lcol.p, c->lofs.p);
+                HostPlan &P = c->plan;
+                P.sym_half = true; P.balanced = false;
+                P.uptr.clear(); P.ucol.clear(); P.usrc.clear(); P.lptr.clear(); P.lcol.clear(); P.lblk.clear(); P.lofs.clear(); P.tile_base.clear();
+                format_on_device = true;
+                lap("solver format on the device");
+            }
+        }
+        if (!format_on_device) {
+            build_solver_format(c->plan, half);
+            c->n_stored = (int64_t)c->plan.ucol.size();
+            c->n_refs = (int64_t)c->plan.lcol.size();
+            c->tile_units = c->plan.sym_half ? (int64_t)c->plan.tile_base.back() : 0;
+            upload(c, c->uptr, c->plan.uptr);
+            upload(c, c->ucol, c->plan.ucol);
+            upload(c, c->usrc, c->plan.usrc);
+            upload(c, c->lptr, c->plan.lptr);
+            upload(c, c->lcol, c->plan.lcol);
+            upload(c, c->lofs, c->plan.lofs);
+            upload(c, c->ilv_base, c->plan.tile_base);
+        }
         host_ms += now_ms() - tp1;
-        upload(c, c->uptr, c->plan.uptr);
-        upload(c, c->ucol, c->plan.ucol);
-        upload(c, c->usrc, c->plan.usrc);
-        upload(c, c->lptr, c->plan.lptr);
-        upload(c, c->lcol, c->plan.lcol);
-        upload(c, c->lofs, c->plan.lofs);
-        upload(c, c->ilv_base, c->plan.tile_base);
         const double tp2 = now_ms();
         build_tiles(c->plan.rowptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_host);
-        build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
+        if (!format_on_device) build_tiles(c->plan.uptr, kTmaCapBlocks, kTmaMaxRows, c->tile_row_s_host);
+        else c->tile_row_s_host.clear();   // (tiles over the solver format serve the full-row TMA kernel only)
         c->tma_ok = true;
         for (size_t t = 0; t + 1 < c->tile_row_host.size(); ++t)
             if (c->plan.rowptr[c->tile_row_host[t + 1]] - c->plan.rowptr[c->tile_row_host[t]] > kTmaCapBlocks)
@@ -969,7 +1064,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         CK(c->sendbuf.alloc((size_t)36 * c->plan.send_rows.size()));
         CK(c->vals.alloc((size_t)nnzb * 36));
         // symmetric-half: interleaved tiles (16-byte units, padded to the longest row of each tile)
-        CK(c->vals_s.alloc(c->plan.sym_half ? (size_t)c->plan.tile_base.back() * 2 : (size_t)c->plan.ucol.size() * 36));
+        CK(c->vals_s.alloc(c->plan.sym_half ? (size_t)c->tile_units * 2 : (size_t)c->n_stored * 36));
         CK(c->lfac.alloc((size_t)nb * 36));
         CK(c->sinv.alloc((size_t)(nb + ng) * 36));
         CK(c->f.alloc((size_t)6 * nb));
@@ -1049,7 +1144,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         // algorithmic bytes: the solver SpMV streams 288 B + a 4 B column id per STORED
         // block, 8 B per transposed reference, and per row 48 B x + 48 B y + two 4 B row pointers;
         // a CG iteration adds 9 vector passes of 48 B per row
-        s.bytes_spmv = 292.0 * (double)c->plan.ucol.size() + 8.0 * (double)c->plan.lcol.size() + 104.0 * (double)nb;
+        s.bytes_spmv = 292.0 * (double)c->n_stored + 8.0 * (double)c->n_refs + 104.0 * (double)nb;
         s.bytes_pcg_iter = s.bytes_spmv + 432.0 * (double)nb;
         // multilevel: restriction reads r~ (48) + T (144, FP32) + member id (4); prolongation reads r~, T, aggregate id and
         // writes z~ (48); the p-update reads z~ in place of r~ (no change)
@@ -1802,6 +1897,54 @@ int mbfea_debug_trace(mbfea_ctx *c, uint64_t *stamps, int64_t max_iters, int64_t
 }
 
 // ---- host-only partition plan --------------------------------------------------
+int mbfea_debug_compare_plan(mbfea_ctx *c, int64_t mismatches[12], int32_t *built_on_device)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!mismatches) return fail(c, MBFEA_EARG, "NULL");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->st));
+        std::vector<int32_t> elems((size_t)2 * (size_t)c->E), fixed((size_t)c->F);
+        if (c->E) CK(cudaMemcpy(elems.data(), c->stg_elems.p, elems.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (c->F) CK(cudaMemcpy(fixed.data(), c->fixed.p, fixed.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        HostPlan H;
+        H.perm = c->plan.perm; H.inv = c->plan.inv;
+        // same numbering as the job: the renumbering decision is not repeated (it needs the coordinates), its result is reused
+        build_plan_begin(c->V, c->E, elems.data(), c->F, fixed.data(), c->opt.rank, c->opt.world, H, 0, nullptr);
+        if (!c->plan.perm.empty()) {
+            H.perm = c->plan.perm; H.inv = c->plan.inv;
+            for (int64_t v = 0; v < c->V; ++v)
+                if (H.free_index[(size_t)v] >= 0) H.free_index[(size_t)v] = H.perm[(size_t)H.free_index[(size_t)v]];
+        }
+        build_plan_pattern(c->E, elems.data(), true, H);
+        build_solver_format(H, c->plan.sym_half);
+        auto cmp = [&](const DevBuf<int32_t> &d, const hvec<int32_t> &h, size_t n_dev) -> int64_t {
+            if (n_dev != h.size()) return -1;
+            std::vector<int32_t> t(h.size());
+            if (!t.empty()) CK(cudaMemcpy(t.data(), d.p, t.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            int64_t bad = 0;
+            for (size_t i = 0; i < t.size(); ++i) bad += t[i] != h[i];
+            return bad;
+        };
+        const size_t nb = (size_t)c->nb(), nnzb = (size_t)c->plan.nnzb();
+        const size_t ntile1 = c->plan.sym_half ? (nb + 31) / 32 + 1 : 0;
+        mismatches[0] = cmp(c->rowptr, H.rowptr, nb + 1);
+        mismatches[1] = cmp(c->colidx, H.colidx, nnzb);
+        mismatches[2] = cmp(c->diag_idx, H.diag_idx, nb);
+        mismatches[3] = cmp(c->contrib_ptr, H.contrib_ptr, nnzb + 1);
+        mismatches[4] = cmp(c->contrib, H.contrib, H.contrib.size());
+        mismatches[5] = cmp(c->uptr, H.uptr, nb + 1);
+        mismatches[6] = cmp(c->ucol, H.ucol, (size_t)c->n_stored);
+        mismatches[7] = cmp(c->usrc, H.usrc, (size_t)c->n_stored);
+        mismatches[8] = cmp(c->lptr, H.lptr, nb + 1);
+        mismatches[9] = cmp(c->lcol, H.lcol, (size_t)c->n_refs);
+        mismatches[10] = cmp(c->lofs, H.lofs, c->plan.sym_half ? (size_t)c->n_refs : 0);
+        mismatches[11] = cmp(c->ilv_base, H.tile_base, ntile1);
+        if (built_on_device) *built_on_device = c->device_plan ? (c->plan.uptr.empty() && c->n_stored > 0 ? 2 : 1) : 0;
+        return MBFEA_OK;
+    });
+}
+
 int mbfea_plan_partition(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                          int32_t rank, int32_t world, mbfea_plan_sizes *sizes, int64_t *rowptr, int32_t *colidx,
                          int64_t *ghost_global, int32_t *ghost_owner, int64_t *send_local_rows, int32_t *send_dest)

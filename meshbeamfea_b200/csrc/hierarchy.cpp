@@ -169,34 +169,49 @@ static void build_level_pattern(int64_t n, const int32_t *rowptr, const int32_t 
 {
     Lap lap;
     const int64_t na = L.n_coarse;
-    // coarse pattern: aggregate I couples to agg(col) of every block of its member rows.  Two passes (count,
-    // fill) over ranges of aggregates, each thread with its own scratch.
+    // coarse pattern: aggregate I couples to agg(col) of every block of its member rows.  Every thread generates the
+    // rows of its contiguous range of aggregates once, into one flat buffer; after the prefix sum the buffer is exactly
+    // the slice [rowptr[first], rowptr[last + 1]) of the column array.
     L.rowptr.assign((size_t)na + 1, 0);
-    auto row_of = [&](int64_t I, std::vector<int32_t> &tmp) {
-        tmp.clear();
-        tmp.push_back((int32_t)I);
-        for (int32_t q = L.agg_ptr[(size_t)I]; q < L.agg_ptr[(size_t)I + 1]; ++q) {
-            const int32_t v = L.agg_rows[(size_t)q];
-            for (int32_t k = rowptr[v]; k < rowptr[v + 1]; ++k) tmp.push_back(L.agg[(size_t)colidx[k]]);
-        }
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-    };
-    par_ranges(na, 1 << 10, [&](int64_t b0, int64_t b1) {
-        std::vector<int32_t> tmp;
-        for (int64_t I = b0; I < b1; ++I) { row_of(I, tmp); L.rowptr[(size_t)I + 1] = (int32_t)tmp.size(); }
-    });
-    for (int64_t I = 0; I < na; ++I) L.rowptr[(size_t)I + 1] += L.rowptr[(size_t)I];
-    L.colidx.resize((size_t)L.rowptr[(size_t)na]);
-    par_ranges(na, 1 << 10, [&](int64_t b0, int64_t b1) {
-        std::vector<int32_t> tmp;
-        for (int64_t I = b0; I < b1; ++I) { row_of(I, tmp); std::copy(tmp.begin(), tmp.end(), L.colidx.begin() + L.rowptr[(size_t)I]); }
-    });
-    // Galerkin contributor lists: fine block k = (a, b) is summed into coarse block (agg a, agg b) as
-    // B(off a)^T A(a, b) B(off b); per coarse block the fine blocks are listed in ascending k.  The lists of coarse
-    // row I come from I's member rows only (ascending rows => ascending k), so aggregates are independent: count,
-    // prefix, fill -- both passes parallel over aggregates.
+    {
+        const int64_t nt = par_ranges_count(na, 1 << 10);
+        std::vector<std::vector<int32_t>> flat((size_t)nt);
+        par_ranges_t(na, 1 << 10, [&](int64_t b0, int64_t b1, int64_t t) {
+            std::vector<int32_t> tmp;
+            std::vector<int32_t> &mine = flat[(size_t)t];
+            mine.reserve((size_t)(b1 - b0) * 28);
+            for (int64_t I = b0; I < b1; ++I) {
+                tmp.clear();
+                tmp.push_back((int32_t)I);
+                for (int32_t q = L.agg_ptr[(size_t)I]; q < L.agg_ptr[(size_t)I + 1]; ++q) {
+                    const int32_t v = L.agg_rows[(size_t)q];
+                    for (int32_t k = rowptr[v]; k < rowptr[v + 1]; ++k) tmp.push_back(L.agg[(size_t)colidx[k]]);
+                }
+                std::sort(tmp.begin(), tmp.end());
+                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                L.rowptr[(size_t)I + 1] = (int32_t)tmp.size();
+                mine.insert(mine.end(), tmp.begin(), tmp.end());
+            }
+        });
+        for (int64_t I = 0; I < na; ++I) L.rowptr[(size_t)I + 1] += L.rowptr[(size_t)I];
+        L.colidx.resize((size_t)L.rowptr[(size_t)na]);
+        par_ranges_t(na, 1 << 10, [&](int64_t b0, int64_t, int64_t t) {
+            if (!flat[(size_t)t].empty())
+                std::memcpy(L.colidx.data() + L.rowptr[(size_t)b0], flat[(size_t)t].data(), flat[(size_t)t].size() * sizeof(int32_t));
+        });
+    }
     lap("coarse pattern", n);
+}
+
+// Galerkin contributor lists of the fine level: fine block k = (a, b) is summed into coarse block (agg a, agg b) as
+// B(off a)^T A(a, b) B(off b); per coarse block the fine blocks are listed in ascending k.  The lists of coarse
+// row I come from I's member rows only (ascending rows => ascending k), so aggregates are independent: count,
+// prefix, fill -- both passes parallel over aggregates.  Needs the coarse pattern; nothing below level 1 needs the
+// lists, so build_ml_hierarchy runs this next to the coarser levels.
+static void build_level_galerkin_lists(int64_t n, const int32_t *rowptr, const int32_t *colidx, HierLevel &L)
+{
+    Lap lap;
+    const int64_t na = L.n_coarse;
     const int64_t nnz_f = rowptr[n], nnz_c = (int64_t)L.colidx.size();
     L.gal_ptr.assign((size_t)nnz_c + 1, 0);
     auto for_blocks_of = [&](int64_t I, auto &&visit) {   // visit(coarse block index, fine block index), fine ascending
@@ -320,13 +335,15 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
     // capacity of every array, so a re-submitted mesh of similar size touches no fresh pages (first-touch page faults of
     // several hundred MB were a third of the build).
     size_t used = 0;
+    std::thread galerkin_job;
+    struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_galerkin{galerkin_job};
+    if (H.agg.size() < (size_t)std::max(1, max_levels)) { H.agg.resize((size_t)max_levels); H.xfer.resize((size_t)max_levels); }
     if (nb > 0 && cell0 > 0.0 && ratio > 1.0) {
         const double *pos = pos_rm;
         const int32_t *crp = rowptr, *cci = colidx;
         double cell = cell0;
         int64_t n = nb;
         for (int l = 0; l + 1 < max_levels && n > coarsest_rows; ++l) {
-            if (H.agg.size() <= used) { H.agg.emplace_back(); H.xfer.emplace_back(); }
             HierLevel &L = H.agg[used];
             MlTransfer &T = H.xfer[used];
             build_level_aggregates(n, pos, cell, L, l == 0 ? part_bounds : nullptr, l == 0 ? nparts : 1);
@@ -335,6 +352,9 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
                 // caller's side (set_job builds it on another thread): wait for it here
                 if (fine_pattern && !(*fine_pattern)(crp, cci)) { used = 0; break; }
                 build_level_pattern(n, crp, cci, L);
+                // the contributor lists of the fine level are needed by nobody below: built next to the coarser levels
+                // (H.agg was sized for every level up front, so `L` stays where it is)
+                galerkin_job = std::thread([n, crp, cci, &L] { build_level_galerkin_lists(n, crp, cci, L); });
             } else {
                 L.rowptr.clear(); L.colidx.clear(); L.gal_ptr.clear(); L.gal_src.clear();
             }
@@ -351,6 +371,7 @@ void build_ml_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx
             cell *= ratio;
         }
     }
+    if (galerkin_job.joinable()) galerkin_job.join();
     H.agg.resize(used); H.xfer.resize(used);
 }
 
@@ -439,6 +460,7 @@ void build_hierarchy(int64_t nb, const int32_t *rowptr, const int32_t *colidx, c
         HierLevel L;
         build_level_aggregates(n, pos.data(), cell, L);
         build_level_pattern(n, rp.data(), ci.data(), L);
+        build_level_galerkin_lists(n, rp.data(), ci.data(), L);
         if (L.n_coarse >= n) break;   // no coarsening at this cell size (isolated points): stop
         pos = L.centroid; rp.assign(L.rowptr.begin(), L.rowptr.end()); ci.assign(L.colidx.begin(), L.colidx.end()); n = L.n_coarse;
         H.levels.push_back(std::move(L));

@@ -291,14 +291,22 @@ static bool bfs_renumber(int64_t V, int64_t E, const int32_t *elems_cm, const st
         // the value stream (~900 B per row)
         const int64_t window = std::max<int64_t>(4096, (int64_t)(16e6 / 900.0));
         auto poor = [&](const int32_t *pm) {
+            int64_t cnt[64] = {0};   // per thread: far, total (integer counts: the split does not change the result)
+            int64_t *cp = cnt;
+            const int32_t *fcp = fc.data();
+            parallel_ranges(E, 1 << 16, [=](int64_t lo, int64_t hi, int t) {
+                int64_t far = 0, tot = 0;
+                for (int64_t e = lo; e < hi; ++e) {
+                    int32_t a = fcp[elems_cm[e]], b = fcp[elems_cm[E + e]];
+                    if (a < 0 || b < 0) continue;
+                    if (pm) { a = pm[a]; b = pm[b]; }
+                    ++tot;
+                    far += std::llabs((long long)a - (long long)b) > window;
+                }
+                cp[2 * t] = far; cp[2 * t + 1] = tot;
+            });
             int64_t far = 0, tot = 0;
-            for (int64_t e = 0; e < E; ++e) {
-                int32_t a = fc[elems_cm[e]], b = fc[elems_cm[E + e]];
-                if (a < 0 || b < 0) continue;
-                if (pm) { a = pm[a]; b = pm[b]; }
-                ++tot;
-                far += std::llabs((long long)a - (long long)b) > window;
-            }
+            for (int t = 0; t < 32; ++t) { far += cnt[2 * t]; tot += cnt[2 * t + 1]; }
             return tot != 0 && far * 20 >= tot;   // >= 5 % far pairs
         };
         if (!poor(nullptr)) return false;   // keep the input order
@@ -337,11 +345,9 @@ static bool bfs_renumber(int64_t V, int64_t E, const int32_t *elems_cm, const st
     return true;
 }
 
-void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
-                int32_t rank, int32_t world, bool with_contrib, HostPlan &P, int reorder, const double *nodes_cm,
-                const std::function<void()> *after_free_map)
+void build_plan_begin(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed, int32_t rank, int32_t world,
+                      HostPlan &P, int reorder, const double *nodes_cm)
 {
-    PrepTrace tr;
     RankShare share(world);
     P.V = V; P.E = E; P.rank = rank; P.world = world;
     P.nb_global = build_free_map(V, F, fixed, P.free_index);
@@ -349,14 +355,30 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
     if (bfs_renumber(V, E, elems_cm, P.free_index, nbg, reorder, nodes_cm, P.perm, P.inv)) {
         for (int64_t v = 0; v < V; ++v)
             if (P.free_index[v] >= 0) P.free_index[v] = P.perm[P.free_index[v]];
-        tr.lap("internal renumbering");
     }
     P.row_begin = nbg * rank / world;
     P.row_end = nbg * (rank + 1) / world;
-    const int64_t r0 = P.row_begin, nb = P.row_end - P.row_begin;
-    const int32_t *fm = P.free_index.data();
+}
+
+void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
+                int32_t rank, int32_t world, bool with_contrib, HostPlan &P, int reorder, const double *nodes_cm,
+                const std::function<void()> *after_free_map)
+{
+    PrepTrace tr;
+    build_plan_begin(V, E, elems_cm, F, fixed, rank, world, P, reorder, nodes_cm);
     tr.lap("free map");
     if (after_free_map && *after_free_map) (*after_free_map)();
+    build_plan_pattern(E, elems_cm, with_contrib, P);
+}
+
+void build_plan_pattern(int64_t E, const int32_t *elems_cm, bool with_contrib, HostPlan &P)
+{
+    PrepTrace tr;
+    const int32_t rank = P.rank, world = P.world;
+    RankShare share(world);
+    const int64_t nbg = P.nb_global;
+    const int64_t r0 = P.row_begin, nb = P.row_end - P.row_begin;
+    const int32_t *fm = P.free_index.data();
 
     // pass 1: entries per owned row (diagonal contributions + off-diagonal ones).  The owned rows are
     // split into one range per thread.  Every end point that falls into an owned row is first dropped

@@ -177,6 +177,22 @@ void launch_force_ranges(cudaStream_t st, int64_t n, const double *F, double *pm
 void launch_force_normalize(cudaStream_t st, int64_t n, const double *F, const double *range, double *out);
 
 
+// ---- block pattern, contributor lists and solver format built on the device (plan_dev.cu) -------------------
+// exclusive scan of n int32 values: out[0 .. n] (out[n] = total); tsum: scan_i32_scratch(n) ints of scratch
+void launch_scan_i32(cudaStream_t st, int64_t n, const int32_t *in, int32_t *out, int32_t *tsum);
+int64_t scan_i32_scratch(int64_t n);
+void launch_pd_count(cudaStream_t st, int64_t E, const int32_t *elems_cm, const int32_t *fm, int32_t *cnt);
+void launch_pd_fill(cudaStream_t st, int64_t E, const int32_t *elems_cm, const int32_t *fm, const int32_t *start, int32_t *cur,
+                    unsigned long long *ent);
+void launch_pd_sort(cudaStream_t st, int64_t nb, const int32_t *start, unsigned long long *ent, int32_t *nblk);
+void launch_pd_emit(cudaStream_t st, int64_t nb, const int32_t *start, const unsigned long long *ent, const int32_t *rowptr,
+                    int32_t *colidx, int32_t *diag_idx, int32_t *contrib_ptr, int32_t *contrib);
+void launch_pf_count(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *diag_idx, int32_t *nu, int32_t *nl);
+void launch_pf_tiles(cudaStream_t st, int64_t nb, const int32_t *nu, int32_t *tunits, unsigned long long *totals);
+void launch_pf_fill(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx, const int32_t *diag_idx,
+                    const int32_t *uptr, const int32_t *lptr, const int32_t *tile_base, int32_t *ucol, int32_t *usrc, int32_t *lcol,
+                    int32_t *lofs);
+
 // ---- multilevel preconditioner, production kernels (mlprec.cu) ----------------------------------------------
 void launch_ml_make_t0(cudaStream_t st, int64_t nb, const double *lfac, const double *off, float *t0);
 void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv, float *dinv32);

@@ -114,6 +114,11 @@ int64_t build_free_map(int64_t V, int64_t F, const int32_t *fixed, std::vector<i
 // with_contrib=false skips the contributor lists (plan-only callers).
 // reorder: 0 never, 1 breadth-first when the canonical numbering has poor locality (auto), 2 breadth-first
 // always, 3 Morton order of the vertex coordinates (needs nodes_cm; falls back to 2 without)
+// The first part alone: free map, internal renumbering (perm / inv, empty = identity) and the rank's row range.
+void build_plan_begin(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed, int32_t rank, int32_t world,
+                      HostPlan &plan, int reorder = 0, const double *nodes_cm = nullptr);
+// The second part: block pattern, contributor lists and halo plan of the rank, from the state build_plan_begin left.
+void build_plan_pattern(int64_t E, const int32_t *elems_cm, bool with_contrib, HostPlan &plan);
 // after_free_map (optional): called once free_index, nb_global and the row range are final, before the pattern passes
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                 int32_t rank, int32_t world, bool with_contrib, HostPlan &plan, int reorder = 0,

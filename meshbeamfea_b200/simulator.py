@@ -348,6 +348,13 @@ class Context:
         self._ck(self._lib.mbfea_debug_trace(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), iters, C.byref(n)))
         return out
 
+    def compare_plan(self):
+        """(mismatch counts of the 12 set-up arrays against the host builders, 0 / 1 / 2: what was built on the device)"""
+        bad = np.zeros(12, np.int64)
+        where = C.c_int32()
+        self._ck(self._lib.mbfea_debug_compare_plan(self._h, bad.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(where)))
+        return bad, int(where.value)
+
     def time_spmv(self, kernel: int = 0, warmup: int = 3, reps: int = 20) -> float:
         ms = C.c_double()
         self._ck(self._lib.mbfea_time_spmv(self._h, kernel, warmup, reps, C.byref(ms)))
