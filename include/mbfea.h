@@ -250,6 +250,13 @@ int mbfea_debug_trace(mbfea_ctx *ctx, uint64_t *stamps, int64_t max_iters, int64
  * 0 rowptr, 1 colidx, 2 diag_idx, 3 contrib_ptr, 4 contrib, 5 uptr, 6 ucol, 7 usrc, 8 lptr, 9 lcol, 10 lofs,
  * 11 tile_base.  *built_on_device: 1 pattern on the device, 2 pattern and solver format on the device, 0 neither. */
 int mbfea_debug_compare_plan(mbfea_ctx *ctx, int64_t mismatches[12], int32_t *built_on_device);
+/* The same for the symbolic half of the multilevel preconditioner (one rank): rebuilds the level hierarchy with the HOST
+ * builder (same parameters, same mean beam length) and compares it with the device arrays.  16 counters per level,
+ * *levels levels (capacity: 16 * 16 entries): level 0: agg, off, agg_ptr, agg_rows, level-1 rowptr, colidx, diagonal
+ * positions, gal_ptr, gal_src; level l >= 1: agg, off, prow, pcol, rrow, rblk, rfine, aprow, apcol, next level's rowptr,
+ * colidx, diagonal positions, smoothed flag.  Counter = differing entries, -1 different length, -2 level count differs.
+ * *built_on_device: 1 when the hierarchy of the current job was built on the device.  MBFEA_ESTATE without a hierarchy. */
+int mbfea_debug_compare_hierarchy(mbfea_ctx *ctx, int64_t mismatches[256], int32_t *levels, int32_t *built_on_device);
 
 /* ---- multi-GPU (one process per GPU; vertex-block partition) -------------
  * Rank 0 makes an id, the launcher broadcasts the 128 bytes (torch.distributed

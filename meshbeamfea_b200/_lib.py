@@ -100,6 +100,7 @@ SIGNATURES = {
     "mbfea_time_assemble": (C.c_int, [_vp, _i32, _i32, _pd]),
     "mbfea_debug_trace": (C.c_int, [_vp, C.POINTER(C.c_uint64), _i64, _pi64]),
     "mbfea_debug_compare_plan": (C.c_int, [_vp, _pi64, _pi32]),
+    "mbfea_debug_compare_hierarchy": (C.c_int, [_vp, _pi64, _pi32, _pi32]),
     "mbfea_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "mbfea_comm_init": (C.c_int, [_vp, C.POINTER(C.c_uint8), _i32, _i32]),
     "mbfea_plan_partition": (C.c_int, [_i64, _i64, _pi32, _i64, _pi32, _i32, _i32, C.POINTER(PlanSizes),

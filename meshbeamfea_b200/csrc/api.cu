@@ -111,6 +111,8 @@ struct mbfea_ctx {
     // multilevel preconditioner (options.precond): hierarchy built in set_job, numeric setup in assemble
     MlPrec ml;
     bool use_ml = false;
+    bool ml_on_device = false;   // the hierarchy of the current job was built on the device
+    double ml_mean_len = 0.0;
     MlHierarchy ml_host;   // host half of the hierarchy, kept between jobs: its arrays keep their capacity
     HostPlan ml_gplan;                // several ranks, rank 0: pattern of the whole reduced system (the hierarchy is global)
     MlImageLayout ml_layout;          // several ranks, rank 0: where every hierarchy array sits in the broadcast image
@@ -578,6 +580,48 @@ void upload_forces(mbfea_ctx *c, int64_t nF, const int64_t *f_node, const int64_
     c->solved = c->recovered = false;
 }
 
+// mean beam length (the brick aggregates of the multilevel hierarchy are a few beam lengths wide): fixed chunks,
+// summed in chunk order -- reproducible, and the same value on the host and the device path of the hierarchy
+double mean_beam_length(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm)
+{
+    if (E <= 0) return 0.0;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, E >> 16));
+    std::vector<double> part((size_t)nt, 0.0);
+    std::vector<std::thread> th;
+    auto body = [&](int t) {
+        double len = 0.0;
+        for (int64_t e = E * t / nt; e < E * (t + 1) / nt; ++e) {
+            double d2 = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
+                d2 += d * d;
+            }
+            len += std::sqrt(d2);
+        }
+        part[(size_t)t] = len;
+    };
+    if (nt == 1) body(0);
+    else {
+        for (int t = 0; t < nt; ++t) th.emplace_back(body, t);
+        for (auto &x : th) x.join();
+    }
+    double len = 0.0;
+    for (int t = 0; t < nt; ++t) len += part[(size_t)t];
+    return len / (double)E;
+}
+
+MlParams ml_params_of(const mbfea_ctx *c)
+{
+    MlParams mp;
+    if (c->opt.ml_cell > 0.0) mp.cell = c->opt.ml_cell;
+    if (c->opt.ml_ratio > 1.0) mp.ratio = c->opt.ml_ratio;
+    if (c->opt.ml_coarsest_rows > 0) mp.coarsest_rows = std::min<int64_t>(c->opt.ml_coarsest_rows, 512);
+    if (c->opt.ml_smooth_from > 0) mp.smooth_from = c->opt.ml_smooth_from;
+    if (const char *e = std::getenv("MBFEA_ML_OMEGA")) { const double v = std::atof(e); if (v > 0.0 && v < 2.0) mp.omega = v; }
+    if (const char *e = std::getenv("MBFEA_ML_THETA")) { const double v = std::atof(e); if (v > 0.0) mp.theta = v; }
+    return mp;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -797,18 +841,13 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         };
         // The host arrays that travel are page-locked (hostmem.cpp), so every upload below is asynchronous: the device
         // copies one array while the host builds the next.
-        c->props_host.resize((size_t)4 * E);
-        derive_props(E, dims_bh, mat_nuE, c->props_host.data());
-        host_ms += now_ms() - t0;
         // mesh -> device, repacked into aligned records; K3 (canonical map)
         {
             DevBuf<double> &d_nodes = c->stg_nodes, &d_normals = c->stg_normals;
-            DevBuf<float> &d_props = c->stg_props;
             DevBuf<int32_t> &d_elems = c->stg_elems, &d_scratch = c->stg_scratch;
             upload(c, d_nodes, nodes_cm, (size_t)3 * V);
             upload(c, d_elems, elems_cm, (size_t)2 * E);
             upload(c, d_normals, normals_cm, (size_t)3 * E);
-            upload(c, d_props, c->props_host);
             upload(c, c->fixed, fixed, (size_t)F);
             CK(c->node4.alloc((size_t)V));
             CK(c->rec.alloc((size_t)E));
@@ -817,7 +856,6 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             CK(c->free_canon.alloc((size_t)V));
             CK(d_scratch.alloc((size_t)V + (size_t)V / 1024 + 2));
             launch_pack_nodes(c->st, V, d_nodes.p, c->node4.p);
-            launch_pack_elems(c->st, E, d_elems.p, d_normals.p, d_props.p, c->rec.p);
             launch_free_map(c->st, V, F, c->fixed.p, c->free_canon.p, d_scratch.p);
             lap("mesh upload + pack + K3");
         }
@@ -830,6 +868,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         // hierarchy for everybody -- the ranks of a box share the host cores, W redundant builds would each get 1 / W of
         // them -- from its own pattern of the whole system.)
         c->use_ml = false;
+        c->ml_on_device = false;
         c->ml.reset();
         struct MlHostJob {
             double mean_len = 0.0;
@@ -850,14 +889,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             const bool wanted = c->opt.precond == 2 || (c->opt.precond == 0 && nbg >= 4096);
             const bool possible = nbg >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
             if (!wanted || !possible || !(c->opt.world == 1 || c->opt.rank == 0)) return;
-            MlParams mp;
-            if (c->opt.ml_cell > 0.0) mp.cell = c->opt.ml_cell;
-            if (c->opt.ml_ratio > 1.0) mp.ratio = c->opt.ml_ratio;
-            if (c->opt.ml_coarsest_rows > 0) mp.coarsest_rows = std::min<int64_t>(c->opt.ml_coarsest_rows, 512);
-            if (c->opt.ml_smooth_from > 0) mp.smooth_from = c->opt.ml_smooth_from;
-            if (const char *e = std::getenv("MBFEA_ML_OMEGA")) { const double v = std::atof(e); if (v > 0.0 && v < 2.0) mp.omega = v; }
-            if (const char *e = std::getenv("MBFEA_ML_THETA")) { const double v = std::atof(e); if (v > 0.0) mp.theta = v; }
-            c->ml.par = mp;
+            c->ml.par = ml_params_of(c);
             ml_started = true;
             ml_thread = std::thread([&, V, E, F, nbg]() {
                 try {
@@ -867,8 +899,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                     // positions of the block rows (internal numbering; all of them: the coarse levels are global) and the
                     // mean beam length: the aggregates are bricks of a few beam lengths
                     c->ml_pos.resize((size_t)3 * nbg);
-                    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, E >> 16));
-                    std::vector<double> part((size_t)nt, 0.0);
+                    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(16, V >> 16));
                     std::vector<std::thread> th;
                     for (int t = 0; t < nt; ++t)
                         th.emplace_back([&, t]() {
@@ -876,21 +907,9 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                                 const int32_t r = c->plan.free_index[(size_t)v];
                                 if (r >= 0) for (int a = 0; a < 3; ++a) c->ml_pos[(size_t)3 * r + a] = nodes_cm[(size_t)a * V + v];
                             }
-                            double len = 0.0;   // fixed chunks, summed in chunk order below: reproducible
-                            for (int64_t e = E * t / nt; e < E * (t + 1) / nt; ++e) {
-                                double d2 = 0.0;
-                                for (int a = 0; a < 3; ++a) {
-                                    const double d = nodes_cm[(size_t)a * V + elems_cm[e]] - nodes_cm[(size_t)a * V + elems_cm[E + e]];
-                                    d2 += d * d;
-                                }
-                                len += std::sqrt(d2);
-                            }
-                            part[(size_t)t] = len;
                         });
                     for (auto &x : th) x.join();
-                    double len = 0.0;
-                    for (int t = 0; t < nt; ++t) len += part[(size_t)t];
-                    mlh.mean_len = len / (double)E;
+                    mlh.mean_len = mean_beam_length(V, E, nodes_cm, elems_cm);
                     if (W == 1) {
                         const FinePatternGate gate = [&](const int32_t *&rp, const int32_t *&ci) {
                             std::unique_lock<std::mutex> g(mlh.m);
@@ -914,7 +933,11 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             });
         };
         build_plan_begin(V, E, elems_cm, F, fixed, c->opt.rank, c->opt.world, c->plan, reorder, nodes_cm);
-        start_ml_thread();
+        // section properties (float arithmetic of the reference, on the host) -> beam records
+        c->props_host.resize((size_t)4 * E);
+        derive_props(E, dims_bh, mat_nuE, c->props_host.data());
+        upload(c, c->stg_props, c->props_host);
+        launch_pack_elems(c->st, E, c->stg_elems.p, c->stg_normals.p, c->stg_props.p, c->rec.p);
         // One rank, canonical numbering: the block pattern, the contributor lists and the solver format are built on the
         // DEVICE (plan_dev.cu) from the mesh that is already there -- the same arrays as the host builders', entry for
         // entry -- and only the pattern comes back (the hierarchy build and the taps read it).  Several ranks, an
@@ -923,6 +946,11 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         const bool device_plan = !force_host_plan && c->opt.world == 1 && c->plan.perm.empty() && c->plan.nb_global > 0 &&
                                  4 * E < (int64_t)INT32_MAX - 8;
         c->device_plan = device_plan;
+        // ... and so is the symbolic half of the multilevel preconditioner (hier_dev.cu; MBFEA_HOST_HIER=1: host thread)
+        static const bool force_host_hier = [] { const char *e = std::getenv("MBFEA_HOST_HIER"); return e && *e == '1'; }();
+        const bool ml_dev_try = device_plan && !force_host_hier && c->plan.nb_global >= 64 &&
+                                (c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096));
+        if (!ml_dev_try) start_ml_thread();
         const int64_t nb = c->nb(), ng_dev = 0;
         (void)ng_dev;
         int64_t nnzb_dev = 0;
@@ -966,6 +994,15 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         else { c->plan.comp_ptr.clear(); c->plan.comp_max_rows = 0; }
         const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
         mlh.signal(batched ? 2 : 1);   // the hierarchy thread may read the block pattern now (a batch has no use for it)
+        bool ml_on_device = false;
+        if (ml_dev_try && !batched) {
+            c->ml.par = ml_params_of(c);
+            const double ml_len = mean_beam_length(V, E, nodes_cm, elems_cm);
+            ml_on_device = c->ml.build_hierarchy_device(c->st, V, c->node4.p, c->free_canon.p, nb, c->rowptr.p, c->colidx.p, nnzb_dev, ml_len);
+            c->ml_mean_len = ml_len;
+            lap("multilevel hierarchy on the device");
+            if (!ml_on_device) start_ml_thread();   // (does not coarsen on the device's terms: the host builder decides)
+        }
         // preconditioner: multilevel for a single large mesh (auto) or on request
         const bool ml_possible = !batched && c->plan.nb_global >= 64 && (c->opt.world == 1 || c->plan.nb() > 0);
         const bool ml_wanted = c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096);
@@ -1088,7 +1125,10 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             const double tw = now_ms();
             const int64_t nbg = c->plan.nb_global;
             if (ml_thread.joinable()) ml_thread.join();
-            if (c->opt.world == 1) {
+            c->ml_on_device = ml_on_device;
+            if (ml_on_device) {
+                c->use_ml = true;
+            } else if (c->opt.world == 1) {
                 c->use_ml = ml_started && !mlh.failed && c->ml.upload_hierarchy(c->st, c->ml_host, nbg, (int64_t)c->plan.rowptr[(size_t)nb], 0, nullptr);
             } else {
                 // rank 0's flat image goes through the GPUs to everybody; each rank then uploads its own share of level 0 and
@@ -1127,7 +1167,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                 allgather_host(c, &ok, all.data(), sizeof ok);
                 for (int q = 0; q < W; ++q) if (!all[(size_t)q]) c->use_ml = false;
             }
-            c->ml.ms_symbolic = mlh.ms + (now_ms() - tw);
+            if (!ml_on_device) { c->ml.ms_symbolic = mlh.ms + (now_ms() - tw); c->ml_mean_len = mlh.mean_len; }
             if (!c->use_ml && c->opt.precond == 2 && c->opt.verbose)
                 std::fprintf(stderr, "[mbfea] multilevel preconditioner requested but the mesh does not coarsen: block-Jacobi\n");
             c->stats.ms_ml_symbolic = c->ml.ms_symbolic;
@@ -1941,6 +1981,33 @@ int mbfea_debug_compare_plan(mbfea_ctx *c, int64_t mismatches[12], int32_t *buil
         mismatches[10] = cmp(c->lofs, H.lofs, c->plan.sym_half ? (size_t)c->n_refs : 0);
         mismatches[11] = cmp(c->ilv_base, H.tile_base, ntile1);
         if (built_on_device) *built_on_device = c->device_plan ? (c->plan.uptr.empty() && c->n_stored > 0 ? 2 : 1) : 0;
+        return MBFEA_OK;
+    });
+}
+
+int mbfea_debug_compare_hierarchy(mbfea_ctx *c, int64_t mismatches[256], int32_t *levels, int32_t *built_on_device)
+{
+    if (int rc = need_job(c)) return rc;
+    if (!mismatches || !levels) return fail(c, MBFEA_EARG, "NULL");
+    if (!c->use_ml || c->opt.world != 1) return fail(c, MBFEA_ESTATE, "no multilevel hierarchy on this (one-rank) job");
+    return guarded(c, [&]() -> int {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->st));
+        const int64_t V = c->V, nbg = c->plan.nb_global;
+        std::vector<double> nodes((size_t)3 * (size_t)V), pos((size_t)3 * (size_t)nbg);
+        CK(cudaMemcpy(nodes.data(), c->stg_nodes.p, nodes.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t v = 0; v < V; ++v) {
+            const int32_t r = c->plan.free_index[(size_t)v];
+            if (r >= 0) for (int a = 0; a < 3; ++a) pos[(size_t)3 * r + a] = nodes[(size_t)a * V + v];
+        }
+        MlHierarchy H;
+        c->ml.build_hierarchy_host(nbg, c->plan.rowptr.data(), c->plan.colidx.data(), pos.data(), c->ml_mean_len, 1, H);
+        std::vector<int64_t> bad;
+        c->ml.compare_with_host(c->st, H, (int64_t)c->plan.rowptr[(size_t)nbg], bad);
+        std::memset(mismatches, 0, 256 * sizeof(int64_t));
+        for (size_t i = 0; i < bad.size() && i < 256; ++i) mismatches[i] = bad[i];
+        *levels = (int32_t)std::min<size_t>(16, bad.size() / 16);
+        if (built_on_device) *built_on_device = c->ml_on_device ? 1 : 0;
         return MBFEA_OK;
     });
 }

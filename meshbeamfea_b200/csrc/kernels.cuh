@@ -193,6 +193,39 @@ void launch_pf_fill(cudaStream_t st, int64_t nb, const int32_t *rowptr, const in
                     const int32_t *uptr, const int32_t *lptr, const int32_t *tile_base, int32_t *ucol, int32_t *usrc, int32_t *lcol,
                     int32_t *lofs);
 
+// ---- symbolic half of the multilevel preconditioner built on the device (hier_dev.cu) ------------------------
+void launch_h_pos(cudaStream_t st, int64_t V, const Node4 *node4, const int32_t *fm, double *pos);
+void launch_h_box(cudaStream_t st, int64_t n, const double *pos, double *part /* 6 * 256 */, double *box /* min[3], max[3] */);
+void launch_h_brick(cudaStream_t st, int64_t n, const double *pos, const double lo[3], double cell, const int64_t cnt[3], int32_t *key,
+                    int32_t *bcnt);
+void launch_h_occ(cudaStream_t st, int64_t nk, const int32_t *bcnt, int32_t *occ);
+void launch_h_assign(cudaStream_t st, int64_t n, const int32_t *key, const int32_t *aggid, const int32_t *bstart, int32_t *bcur,
+                     int32_t *agg, int32_t *agg_rows);
+void launch_h_aggptr(cudaStream_t st, int64_t nk, const int32_t *bcnt, const int32_t *aggid, const int32_t *bstart, int32_t *agg_ptr,
+                     int64_t n, int64_t na);
+void launch_h_sort_members(cudaStream_t st, int64_t na, const int32_t *agg_ptr, int32_t *agg_rows, int32_t *maxsz);
+void launch_h_centroid_off(cudaStream_t st, int64_t n, int64_t na, const int32_t *agg_ptr, const int32_t *agg_rows, const int32_t *agg,
+                           const double *pos, double *centroid, double *off);
+void launch_h0_ub(cudaStream_t st, int64_t na, const int32_t *agg_ptr, const int32_t *agg_rows, const int32_t *rowptr, int32_t *ub);
+void launch_h0_cand(cudaStream_t st, int64_t na, const int32_t *agg_ptr, const int32_t *agg_rows, const int32_t *rowptr,
+                    const int32_t *colidx, const int32_t *agg, const int32_t *cstart, int32_t *cand, int32_t *nuniq);
+void launch_h0_emit(cudaStream_t st, int64_t na, const int32_t *cstart, const int32_t *cand, const int32_t *rowptr1, int32_t *colidx1,
+                    int32_t *diag1);
+void launch_h0_gal(cudaStream_t st, bool fill, int64_t na, const int32_t *agg_ptr, const int32_t *agg_rows, const int32_t *rowptr,
+                   const int32_t *colidx, const int32_t *agg, const int32_t *rowptr1, const int32_t *colidx1, int32_t *cnt_or_cur,
+                   const int32_t *gal_ptr, int32_t *gal_src);
+// rows of P / A P / P^T A P as sorted unique unions (fill = false: row lengths; true: columns at rowptr)
+void launch_hx_p_rows(cudaStream_t st, bool fill, int64_t n, int64_t ncols, bool smoothed, const int32_t *arow, const int32_t *acol,
+                      const int32_t *agg, int32_t *rowlen, const int32_t *prow, int32_t *pcol);
+void launch_hx_ap_rows(cudaStream_t st, bool fill, int64_t n, int64_t ncols, const int32_t *arow, const int32_t *acol, const int32_t *prow,
+                       const int32_t *pcol, int32_t *rowlen, const int32_t *aprow, int32_t *apcol);
+void launch_hx_rap_rows(cudaStream_t st, bool fill, int64_t nc, const int32_t *rrow, const int32_t *rfine, const int32_t *aprow,
+                        const int32_t *apcol, int32_t *rowlen, const int32_t *crow, int32_t *ccol);
+// phase 0: entries per column (rcnt), 1: block ids into the columns' segments (cursor), 2: sort each segment, fine rows
+void launch_hx_transpose(cudaStream_t st, int phase, int64_t nnzp, int64_t nc, const int32_t *pcol, const int32_t *prow_of,
+                         int32_t *rcnt_or_cur, const int32_t *rrow, int32_t *rblk, int32_t *rfine);
+void launch_h_diag(cudaStream_t st, int64_t n, const int32_t *rowptr, const int32_t *colidx, int32_t *diag);
+
 // ---- multilevel preconditioner, production kernels (mlprec.cu) ----------------------------------------------
 void launch_ml_make_t0(cudaStream_t st, int64_t nb, const double *lfac, const double *off, float *t0);
 void launch_ml_diag_inv(cudaStream_t st, int64_t n, const double *sinv, double *dinv, float *dinv32);

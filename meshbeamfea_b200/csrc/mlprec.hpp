@@ -79,6 +79,15 @@ public:
     // index of the first block of the rank's first row in it (0 on one rank)
     bool upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nb_global, int64_t fine_nnz, int64_t own_first_block,
                           const MlDist *dist);
+    // One rank: the whole symbolic half built ON THE DEVICE (hier_dev.cu) from the mesh and the fine pattern that are
+    // already there -- the same arrays as build_hierarchy_host + upload_hierarchy, entry for entry.  node4 / fm: vertex
+    // records and the vertex -> block row map (-1 fixed); (d_rowptr, d_colidx): fine pattern, fine_nnz blocks.
+    // false: nothing usable was built (mesh does not coarsen, brick grid too sparse for the counting sort, coarsest
+    // level too large) -- the caller falls back to the host builder.
+    bool build_hierarchy_device(cudaStream_t st, int64_t V, const dev::Node4 *d_node4, const int32_t *d_fm, int64_t nb,
+                                const int32_t *d_rowptr, const int32_t *d_colidx, int64_t fine_nnz, double mean_beam_length);
+    // parity tap: the device arrays of the current hierarchy against a host hierarchy (mismatch counts per array, see api.cu)
+    void compare_with_host(cudaStream_t st, const MlHierarchy &H, int64_t fine_nnz, std::vector<int64_t> &bad) const;
     // several ranks: the device arrays straight from the device copy of rank 0's image (ml_image_pack): device-to-device
     // slices of level 0 (own rows, own aggregates, own level-1 block rows) and copies of the replicated coarse levels
     bool upload_from_image(cudaStream_t st, const unsigned char *d_img, const MlImageHeader &hd, const MlDist &dist);
@@ -104,6 +113,9 @@ private:
     DevBuf<int32_t> agg0, agg_ptr0, agg_rows0, gal_ptr0, gal_src0, frow0;
     DevBuf<double> off0;
     DevBuf<int64_t> ghost_stage;
+    // scratch of build_hierarchy_device, kept between jobs
+    DevBuf<double> hd_pos[2], hd_part, hd_box;
+    DevBuf<int32_t> hd_key, hd_bcnt, hd_bcur, hd_occ, hd_aggid, hd_bstart, hd_scan, hd_len, hd_aggptr, hd_aggrows, hd_cand, hd_small;
     DevBuf<float> t0;              // fine transfer T_v = L_v^T B(d_v), FP32 (with half16: scratch of the packing pass)
     DevBuf<unsigned char> t0h;     // the same as 80-byte 16-bit blocks: what the apply reads
     const void *t0_apply() const { return half16 ? (const void *)t0h.p : (const void *)t0.p; }

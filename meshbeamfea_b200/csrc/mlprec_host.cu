@@ -176,6 +176,221 @@ bool MlPrec::upload_hierarchy(cudaStream_t st, const MlHierarchy &H, int64_t nbg
     return true;
 }
 
+// ---- the symbolic half on the device (one rank) --------------------------------------------------------------
+namespace {
+template <class T>
+T fetch(cudaStream_t st, const T *d)   // one scalar back from the device (synchronises the stream)
+{
+    T v;
+    CK(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return v;
+}
+}  // namespace
+
+bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_node4, const int32_t *d_fm, int64_t nb_,
+                                    const int32_t *d_rowptr, const int32_t *d_colidx, int64_t fine_nnz, double mean_len)
+{
+    const double t0w = wall_ms();
+    reset();
+    if (nb_ <= 0 || !(mean_len > 0.0) || !(par.cell > 0.0) || !(par.ratio > 1.0)) return false;
+    half16 = [] { const char *e = std::getenv("MBFEA_ML_HALF"); return e && *e == '1'; }();
+    rank = 0; world = 1; nc = nullptr; comm = nullptr;
+    nb = nb_;
+    CK(hd_pos[0].alloc((size_t)3 * nb)); CK(hd_pos[1].alloc((size_t)3 * nb));
+    CK(hd_part.alloc(6 * 256)); CK(hd_box.alloc(6));
+    CK(hd_key.alloc((size_t)nb)); CK(hd_len.alloc((size_t)nb + 2)); CK(hd_small.alloc(8));
+    CK(hd_scan.alloc((size_t)scan_i32_scratch(std::max<int64_t>(fine_nnz, 9 * nb + 2048) + 2)));
+    launch_h_pos(st, V, d_node4, d_fm, hd_pos[0].p);
+    const double *pos = hd_pos[0].p;
+    int cur_pos = 0;
+    const int32_t *crp = d_rowptr, *cci = d_colidx;
+    double cell = par.cell * mean_len;
+    int64_t n = nb;
+    const int smooth_from = std::max(1, par.smooth_from);
+    bool ok = true;
+    int64_t nk0 = 0, na0 = 0;
+    for (int l = 0; l + 1 < par.max_levels && n > par.coarsest_rows; ++l) {
+        // ---- aggregates of level l: bricks of edge `cell` over the bounding box ----
+        launch_h_box(st, n, pos, hd_part.p, hd_box.p);
+        double box[6];
+        CK(cudaMemcpyAsync(box, hd_box.p, sizeof box, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int64_t cnt[3];
+        double nk_d = 1.0;
+        for (int a = 0; a < 3; ++a) {
+            cnt[a] = std::max<int64_t>(1, (int64_t)std::floor((box[3 + a] - box[a]) / cell + 1e-9) + 1);
+            nk_d *= (double)cnt[a];
+        }
+        if (!(nk_d <= 8.0 * (double)n + 1024.0)) { ok = false; break; }   // sparse brick grid: the host builder sorts instead
+        const int64_t nk = cnt[0] * cnt[1] * cnt[2];
+        if (l == 0) {   // the brick grids of the coarser levels are smaller: one allocation serves every level
+            nk0 = nk;
+            CK(hd_bcnt.alloc((size_t)nk + 3)); CK(hd_bcur.alloc((size_t)nk + 3)); CK(hd_occ.alloc((size_t)nk + 3));
+            CK(hd_aggid.alloc((size_t)nk + 3)); CK(hd_bstart.alloc((size_t)nk + 3));
+        } else if (nk > nk0) { ok = false; break; }
+        CK(cudaMemsetAsync(hd_bcnt.p, 0, ((size_t)nk + 1) * sizeof(int32_t), st));
+        CK(cudaMemsetAsync(hd_bcur.p, 0, ((size_t)nk + 1) * sizeof(int32_t), st));
+        launch_h_brick(st, n, pos, box, cell, cnt, hd_key.p, hd_bcnt.p);
+        launch_h_occ(st, nk, hd_bcnt.p, hd_occ.p);
+        launch_scan_i32(st, nk, hd_occ.p, hd_aggid.p, hd_scan.p);
+        launch_scan_i32(st, nk, hd_bcnt.p, hd_bstart.p, hd_scan.p);
+        const int64_t na = fetch(st, hd_aggid.p + nk);
+        if (na >= n) break;   // no coarsening at this cell size: stop
+        MlCoarse *cur = l >= 1 ? lv[(size_t)l - 1].get() : nullptr;   // level l (l >= 1) and its transfer to level l + 1
+        DevBuf<int32_t> &agg = l == 0 ? agg0 : cur->agg;
+        DevBuf<double> &off = l == 0 ? off0 : cur->off;
+        DevBuf<int32_t> &aptr = l == 0 ? agg_ptr0 : hd_aggptr, &arows = l == 0 ? agg_rows0 : hd_aggrows;
+        CK(agg.alloc((size_t)n)); CK(off.alloc((size_t)3 * n));
+        if (l == 0) {
+            na0 = na;
+            CK(agg_ptr0.alloc((size_t)na + 1)); CK(agg_rows0.alloc((size_t)n));
+            CK(hd_aggptr.alloc((size_t)na + 2)); CK(hd_aggrows.alloc((size_t)na + 2));   // member lists of the coarser levels (n <= na0)
+        } else if (na + 1 > na0 + 2 || n > na0 + 2) { ok = false; break; }
+        double *centroid = hd_pos[cur_pos ^ 1].p;
+        launch_h_assign(st, n, hd_key.p, hd_aggid.p, hd_bstart.p, hd_bcur.p, agg.p, arows.p);
+        launch_h_aggptr(st, nk, hd_bcnt.p, hd_aggid.p, hd_bstart.p, aptr.p, n, na);
+        CK(cudaMemsetAsync(hd_small.p, 0, 8 * sizeof(int32_t), st));
+        launch_h_sort_members(st, na, aptr.p, arows.p, hd_small.p);
+        launch_h_centroid_off(st, n, na, aptr.p, arows.p, agg.p, pos, centroid, off.p);
+        std::unique_ptr<MlCoarse> next = take_level();
+        next->n = na;
+        CK(next->rowptr.alloc((size_t)na + 1)); CK(next->diag_idx.alloc((size_t)na));
+        if (l == 0) {
+            group0 = fetch(st, hd_small.p) <= 8 ? 8 : 32;
+            agg_begin.assign({0, na});
+            // level-1 pattern: candidates per aggregate -> sorted unique
+            launch_h0_ub(st, na, aptr.p, arows.p, crp, hd_len.p);
+            // (hd_aggptr is free on level 0: start of every aggregate's candidate segment)
+            launch_scan_i32(st, na, hd_len.p, hd_aggptr.p, hd_scan.p);
+            const int64_t ncand = fetch(st, hd_aggptr.p + na);
+            CK(hd_cand.alloc((size_t)ncand + 1));
+            launch_h0_cand(st, na, aptr.p, arows.p, crp, cci, agg.p, hd_aggptr.p, hd_cand.p, hd_len.p);
+            launch_scan_i32(st, na, hd_len.p, next->rowptr.p, hd_scan.p);
+            next->nnz = fetch(st, next->rowptr.p + na);
+            CK(next->colidx.alloc((size_t)next->nnz));
+            launch_h0_emit(st, na, hd_aggptr.p, hd_cand.p, next->rowptr.p, next->colidx.p, next->diag_idx.p);
+            blk_begin.assign({0, next->nnz});
+            // Galerkin contributor lists (counts, prefix, fill; the counters live in the candidate scratch)
+            CK(hd_cand.alloc((size_t)std::max<int64_t>(ncand, next->nnz) + 1));
+            CK(gal_ptr0.alloc((size_t)next->nnz + 1)); CK(gal_src0.alloc((size_t)fine_nnz));
+            CK(cudaMemsetAsync(hd_cand.p, 0, ((size_t)next->nnz + 1) * sizeof(int32_t), st));
+            launch_h0_gal(st, false, na, aptr.p, arows.p, crp, cci, agg.p, next->rowptr.p, next->colidx.p, hd_cand.p, nullptr, nullptr);
+            launch_scan_i32(st, next->nnz, hd_cand.p, gal_ptr0.p, hd_scan.p);
+            CK(cudaMemsetAsync(hd_cand.p, 0, ((size_t)next->nnz + 1) * sizeof(int32_t), st));
+            launch_h0_gal(st, true, na, aptr.p, arows.p, crp, cci, agg.p, next->rowptr.p, next->colidx.p, hd_cand.p, gal_ptr0.p, gal_src0.p);
+            CK(frow0.alloc((size_t)fine_nnz));
+            CK(t0.alloc((size_t)nb * 36));
+            if (half16) CK(t0h.alloc((size_t)nb * kTBlock16Bytes));
+            rows.push_back(nb);
+        } else {
+            // transfer from level l to level l + 1: P, P^T, A P, P^T A P (patterns)
+            cur->has_next = true; cur->smoothed = l >= smooth_from; cur->n_next = na;
+            if (na > 200 * 1024 * 8) { ok = false; break; }   // bitmap of a row beyond the shared memory of an SM: host builder
+            CK(cur->prow.alloc((size_t)n + 1));
+            launch_hx_p_rows(st, false, n, na, cur->smoothed, crp, cci, agg.p, hd_len.p, nullptr, nullptr);
+            launch_scan_i32(st, n, hd_len.p, cur->prow.p, hd_scan.p);
+            cur->nnzp = fetch(st, cur->prow.p + n);
+            CK(cur->pcol.alloc((size_t)cur->nnzp));
+            launch_hx_p_rows(st, true, n, na, cur->smoothed, crp, cci, agg.p, nullptr, cur->prow.p, cur->pcol.p);
+            CK(cur->prow_of.alloc((size_t)cur->nnzp));
+            launch_ml_row_of(st, n, cur->prow.p, cur->prow_of.p);
+            // P^T
+            CK(cur->rrow.alloc((size_t)na + 1)); CK(cur->rblk.alloc((size_t)cur->nnzp)); CK(cur->rfine.alloc((size_t)cur->nnzp));
+            int32_t *tcnt = hd_bcur.p;   // free again after the member fill (na <= nk)
+            CK(cudaMemsetAsync(tcnt, 0, ((size_t)na + 2) * sizeof(int32_t), st));
+            launch_hx_transpose(st, 0, cur->nnzp, na, cur->pcol.p, nullptr, tcnt, nullptr, nullptr, nullptr);
+            launch_scan_i32(st, na, tcnt, cur->rrow.p, hd_scan.p);
+            CK(cudaMemsetAsync(tcnt, 0, ((size_t)na + 2) * sizeof(int32_t), st));
+            launch_hx_transpose(st, 1, cur->nnzp, na, cur->pcol.p, nullptr, tcnt, cur->rrow.p, cur->rblk.p, nullptr);
+            launch_hx_transpose(st, 2, cur->nnzp, na, nullptr, cur->prow_of.p, nullptr, cur->rrow.p, cur->rblk.p, cur->rfine.p);
+            // A P
+            CK(cur->aprow.alloc((size_t)n + 1));
+            launch_hx_ap_rows(st, false, n, na, crp, cci, cur->prow.p, cur->pcol.p, hd_len.p, nullptr, nullptr);
+            launch_scan_i32(st, n, hd_len.p, cur->aprow.p, hd_scan.p);
+            cur->nnzap = fetch(st, cur->aprow.p + n);
+            CK(cur->apcol.alloc((size_t)cur->nnzap));
+            launch_hx_ap_rows(st, true, n, na, crp, cci, cur->prow.p, cur->pcol.p, nullptr, cur->aprow.p, cur->apcol.p);
+            // P^T (A P): the next level's matrix
+            launch_hx_rap_rows(st, false, na, cur->rrow.p, cur->rfine.p, cur->aprow.p, cur->apcol.p, hd_len.p, nullptr, nullptr);
+            launch_scan_i32(st, na, hd_len.p, next->rowptr.p, hd_scan.p);
+            next->nnz = fetch(st, next->rowptr.p + na);
+            CK(next->colidx.alloc((size_t)next->nnz));
+            launch_hx_rap_rows(st, true, na, cur->rrow.p, cur->rfine.p, cur->aprow.p, cur->apcol.p, nullptr, next->rowptr.p, next->colidx.p);
+            launch_h_diag(st, na, next->rowptr.p, next->colidx.p, next->diag_idx.p);
+        }
+        rows.push_back(na);
+        crp = next->rowptr.p; cci = next->colidx.p;
+        lv.push_back(std::move(next));
+        cur_pos ^= 1;
+        pos = hd_pos[cur_pos].p;
+        n = na;
+        cell *= par.ratio;
+    }
+    if (!ok || lv.empty() || 6 * lv.back()->n > 3072) { reset(); return false; }
+    const size_t L = lv.size();
+    for (size_t m = 0; m < L; ++m) alloc_level_buffers(st, *lv[m], m + 1 < L);
+    n_dense = 6 * lv.back()->n;
+    CK(dense.alloc((size_t)(n_dense * n_dense)));
+    CK(dense32.alloc((size_t)(n_dense * n_dense)));
+    CK(gj_col.alloc((size_t)(n_dense + 24) * 24));
+    CK(cudaStreamSynchronize(st));
+    symbolic_ok = true;
+    ms_symbolic = wall_ms() - t0w;
+    return true;
+}
+
+// parity tap: device arrays of the current hierarchy against a host hierarchy.  bad: per level 16 counters --
+// level 0: agg, off, agg_ptr, agg_rows, rowptr1, colidx1, diag1, gal_ptr, gal_src; level l >= 1: agg, off, prow, pcol,
+// rrow, rblk, rfine, aprow, apcol, crow, ccol, cdiag  (-1: different length, -2: level missing)
+void MlPrec::compare_with_host(cudaStream_t st, const MlHierarchy &H, int64_t fine_nnz, std::vector<int64_t> &bad) const
+{
+    CK(cudaStreamSynchronize(st));
+    const size_t L = std::max(H.levels(), lv.size());
+    bad.assign(16 * std::max<size_t>(L, 1), 0);
+    auto cmp_i = [&](const DevBuf<int32_t> &d, size_t n_dev, const auto &h) -> int64_t {
+        if (n_dev != h.size()) return -1;
+        std::vector<int32_t> t(h.size());
+        if (!t.empty()) CK(cudaMemcpy(t.data(), d.p, t.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        int64_t b = 0;
+        for (size_t i = 0; i < t.size(); ++i) b += t[i] != h[i];
+        return b;
+    };
+    auto cmp_d = [&](const DevBuf<double> &d, size_t n_dev, const auto &h) -> int64_t {
+        if (n_dev != h.size()) return -1;
+        std::vector<double> t(h.size());
+        if (!t.empty()) CK(cudaMemcpy(t.data(), d.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        int64_t b = 0;
+        for (size_t i = 0; i < t.size(); ++i) b += !(t[i] == h[i]);
+        return b;
+    };
+    if (H.levels() != lv.size()) { for (auto &x : bad) x = -2; return; }
+    if (L == 0) return;
+    const HierLevel &h0 = H.agg[0];
+    const MlCoarse &c0 = *lv[0];
+    std::vector<int32_t> diag1((size_t)h0.n_coarse);
+    for (int64_t I = 0; I < h0.n_coarse; ++I)
+        diag1[(size_t)I] = (int32_t)(std::lower_bound(h0.colidx.begin() + h0.rowptr[(size_t)I], h0.colidx.begin() + h0.rowptr[(size_t)I + 1],
+                                                      (int32_t)I) - h0.colidx.begin());
+    bad[0] = cmp_i(agg0, (size_t)nb, h0.agg); bad[1] = cmp_d(off0, (size_t)3 * nb, h0.off);
+    bad[2] = cmp_i(agg_ptr0, (size_t)c0.n + 1, h0.agg_ptr); bad[3] = cmp_i(agg_rows0, (size_t)nb, h0.agg_rows);
+    bad[4] = cmp_i(c0.rowptr, (size_t)c0.n + 1, h0.rowptr); bad[5] = cmp_i(c0.colidx, (size_t)c0.nnz, h0.colidx);
+    bad[6] = cmp_i(c0.diag_idx, (size_t)c0.n, diag1);
+    bad[7] = cmp_i(gal_ptr0, (size_t)c0.nnz + 1, h0.gal_ptr); bad[8] = cmp_i(gal_src0, (size_t)fine_nnz, h0.gal_src);
+    for (size_t l = 1; l < L; ++l) {
+        const HierLevel &a = H.agg[l];
+        const MlTransfer &T = H.xfer[l];
+        const MlCoarse &c = *lv[l - 1], &nx = *lv[l];
+        int64_t *b = bad.data() + 16 * l;
+        b[0] = cmp_i(c.agg, (size_t)c.n, a.agg); b[1] = cmp_d(c.off, (size_t)3 * c.n, a.off);
+        b[2] = cmp_i(c.prow, (size_t)c.n + 1, T.prow); b[3] = cmp_i(c.pcol, (size_t)c.nnzp, T.pcol);
+        b[4] = cmp_i(c.rrow, (size_t)nx.n + 1, T.rrow); b[5] = cmp_i(c.rblk, (size_t)c.nnzp, T.rblk); b[6] = cmp_i(c.rfine, (size_t)c.nnzp, T.rfine);
+        b[7] = cmp_i(c.aprow, (size_t)c.n + 1, T.aprow); b[8] = cmp_i(c.apcol, (size_t)c.nnzap, T.apcol);
+        b[9] = cmp_i(nx.rowptr, (size_t)nx.n + 1, T.crow); b[10] = cmp_i(nx.colidx, (size_t)nx.nnz, T.ccol); b[11] = cmp_i(nx.diag_idx, (size_t)nx.n, T.cdiag);
+        b[12] = (c.smoothed == T.smoothed) ? 0 : 1;
+    }
+}
+
 // value / work arrays of a coarse level whose index arrays are in place
 void MlPrec::alloc_level_buffers(cudaStream_t st, MlCoarse &c, bool has_next)
 {

@@ -355,6 +355,13 @@ class Context:
         self._ck(self._lib.mbfea_debug_compare_plan(self._h, bad.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(where)))
         return bad, int(where.value)
 
+    def compare_hierarchy(self):
+        """(mismatch counters [levels, 16] of the multilevel hierarchy against the host builder, built on the device?)"""
+        bad = np.zeros(256, np.int64)
+        levels, where = C.c_int32(), C.c_int32()
+        self._ck(self._lib.mbfea_debug_compare_hierarchy(self._h, bad.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(levels), C.byref(where)))
+        return bad.reshape(16, 16)[:levels.value], int(where.value)
+
     def time_spmv(self, kernel: int = 0, warmup: int = 3, reps: int = 20) -> float:
         ms = C.c_double()
         self._ck(self._lib.mbfea_time_spmv(self._h, kernel, warmup, reps, C.byref(ms)))

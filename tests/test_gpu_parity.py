@@ -668,3 +668,28 @@ def test_device_built_plan_equals_the_host_builders(built, name):
     with ctx_for(job, reorder=2) as c:
         bad, where = c.compare_plan()
         assert where == 0 and not bad.any(), {n: int(b) for n, b in zip(names, bad) if b}
+
+
+@pytest.mark.parametrize("name,make", [("lattice_24", lambda: syn.cubic_lattice(24)), ("lattice_45", lambda: syn.cubic_lattice(45)),
+                                       ("gridshell_150", lambda: syn.gridshell(150)), ("planar_grid_90", lambda: syn.planar_grid(90)),
+                                       ("random_3000", lambda: syn.random_mesh(11, V=3000, k=6))])
+def test_device_built_hierarchy_equals_the_host_builder(built, name, make):
+    """One rank: the symbolic half of the multilevel preconditioner (aggregates of every level, level-1 pattern, Galerkin
+    contributor lists, P / P^T / A P / P^T A P patterns) is built on the device (hier_dev.cu).  Every array must equal
+    the host builder's -- the one the CPU suite pins against scipy's P^T K P -- entry for entry, offsets included."""
+    job = _as_arrays(make())
+    with ctx_for(job, precond=2) as c:
+        assert c.stats()["precond"] == 2
+        bad, on_device = c.compare_hierarchy()
+        assert on_device == 1 and bad.shape[0] >= 1
+        assert not bad.any(), bad
+        c.execute()
+        U = c.displacements()
+        its = c.stats()["iterations"]
+    # and the solve is the same as with the host-built hierarchy of a renumbered submission (reorder=2 takes the host
+    # builders; different internal numbering, same mathematics)
+    with ctx_for(job, precond=2, reorder=2) as c:
+        bad, on_device = c.compare_hierarchy()
+        assert on_device == 0 and not bad.any(), bad
+        c.execute()
+        assert rel_l2(c.displacements(), U) < 1e-9 and abs(c.stats()["iterations"] - its) <= max(8, its // 5)
