@@ -200,7 +200,7 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
     CK(hd_pos[0].alloc((size_t)3 * nb)); CK(hd_pos[1].alloc((size_t)3 * nb));
     CK(hd_part.alloc(6 * 256)); CK(hd_box.alloc(6));
     CK(hd_key.alloc((size_t)nb)); CK(hd_len.alloc((size_t)nb + 2)); CK(hd_small.alloc(8));
-    CK(hd_scan.alloc((size_t)scan_i32_scratch(std::max<int64_t>(fine_nnz, 9 * nb + 2048) + 2)));
+    CK(hd_scan.alloc((size_t)scan_i32_scratch(std::max<int64_t>(fine_nnz, std::min<int64_t>(65 * nb + 2048, 268435456 + 8)) + 2)));
     launch_h_pos(st, V, d_node4, d_fm, hd_pos[0].p);
     const double *pos = hd_pos[0].p;
     int cur_pos = 0;
@@ -210,6 +210,11 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
     const int smooth_from = std::max(1, par.smooth_from);
     bool ok = true;
     int64_t nk0 = 0, na0 = 0;
+    const bool trace = std::getenv("MBFEA_PREP_TRACE") != nullptr;
+    auto give_up = [&](const char *why, int l, int64_t a, int64_t b) {
+        if (trace) std::fprintf(stderr, "[mbfea hierarchy] device build gives up at level %d: %s (%lld, %lld)\n", l, why, (long long)a, (long long)b);
+        ok = false;
+    };
     for (int l = 0; l + 1 < par.max_levels && n > par.coarsest_rows; ++l) {
         // ---- aggregates of level l: bricks of edge `cell` over the bounding box ----
         launch_h_box(st, n, pos, hd_part.p, hd_box.p);
@@ -222,13 +227,15 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
             cnt[a] = std::max<int64_t>(1, (int64_t)std::floor((box[3 + a] - box[a]) / cell + 1e-9) + 1);
             nk_d *= (double)cnt[a];
         }
-        if (!(nk_d <= 8.0 * (double)n + 1024.0)) { ok = false; break; }   // sparse brick grid: the host builder sorts instead
+        // (the host builder switches from its counting sort to a comparison sort above 8 n bricks -- same numbering either
+        //  way; here the counting arrays may be far sparser before they stop paying: 64 n bricks, at most 2^28)
+        if (!(nk_d <= 64.0 * (double)n + 1024.0) || nk_d > 268435456.0) { give_up("sparse brick grid", l, (int64_t)nk_d, n); break; }
         const int64_t nk = cnt[0] * cnt[1] * cnt[2];
         if (l == 0) {   // the brick grids of the coarser levels are smaller: one allocation serves every level
             nk0 = nk;
             CK(hd_bcnt.alloc((size_t)nk + 3)); CK(hd_bcur.alloc((size_t)nk + 3)); CK(hd_occ.alloc((size_t)nk + 3));
             CK(hd_aggid.alloc((size_t)nk + 3)); CK(hd_bstart.alloc((size_t)nk + 3));
-        } else if (nk > nk0) { ok = false; break; }
+        } else if (nk > nk0) { give_up("brick grid grew", l, nk, nk0); break; }
         CK(cudaMemsetAsync(hd_bcnt.p, 0, ((size_t)nk + 1) * sizeof(int32_t), st));
         CK(cudaMemsetAsync(hd_bcur.p, 0, ((size_t)nk + 1) * sizeof(int32_t), st));
         launch_h_brick(st, n, pos, box, cell, cnt, hd_key.p, hd_bcnt.p);
@@ -246,7 +253,7 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
             na0 = na;
             CK(agg_ptr0.alloc((size_t)na + 1)); CK(agg_rows0.alloc((size_t)n));
             CK(hd_aggptr.alloc((size_t)na + 2)); CK(hd_aggrows.alloc((size_t)na + 2));   // member lists of the coarser levels (n <= na0)
-        } else if (na + 1 > na0 + 2 || n > na0 + 2) { ok = false; break; }
+        } else if (na + 1 > na0 + 2 || n > na0 + 2) { give_up("member scratch", l, na, n); break; }
         double *centroid = hd_pos[cur_pos ^ 1].p;
         launch_h_assign(st, n, hd_key.p, hd_aggid.p, hd_bstart.p, hd_bcur.p, agg.p, arows.p);
         launch_h_aggptr(st, nk, hd_bcnt.p, hd_aggid.p, hd_bstart.p, aptr.p, n, na);
@@ -286,7 +293,7 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
         } else {
             // transfer from level l to level l + 1: P, P^T, A P, P^T A P (patterns)
             cur->has_next = true; cur->smoothed = l >= smooth_from; cur->n_next = na;
-            if (na > 200 * 1024 * 8) { ok = false; break; }   // bitmap of a row beyond the shared memory of an SM: host builder
+            if (na > 200 * 1024 * 8) { give_up("row bitmap beyond shared memory", l, na, 0); break; }   // host builder
             CK(cur->prow.alloc((size_t)n + 1));
             launch_hx_p_rows(st, false, n, na, cur->smoothed, crp, cci, agg.p, hd_len.p, nullptr, nullptr);
             launch_scan_i32(st, n, hd_len.p, cur->prow.p, hd_scan.p);
@@ -327,7 +334,8 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
         n = na;
         cell *= par.ratio;
     }
-    if (!ok || lv.empty() || 6 * lv.back()->n > 3072) { reset(); return false; }
+    if (ok && !lv.empty() && 6 * lv.back()->n > 3072) give_up("coarsest level too large", (int)lv.size(), lv.back()->n, 0);
+    if (!ok || lv.empty()) { reset(); return false; }
     const size_t L = lv.size();
     for (size_t m = 0; m < L; ++m) alloc_level_buffers(st, *lv[m], m + 1 < L);
     n_dense = 6 * lv.back()->n;

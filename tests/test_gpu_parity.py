@@ -670,9 +670,19 @@ def test_device_built_plan_equals_the_host_builders(built, name):
         assert where == 0 and not bad.any(), {n: int(b) for n, b in zip(names, bad) if b}
 
 
+def _tilted_plane(n):
+    """a planar grid tilted into space: the rows occupy a thin slab of the bounding box, so the brick grid is sparse
+    (the host builder takes its comparison-sort path there, the device keeps the counting sort)"""
+    j = _as_arrays(syn.planar_grid(n))
+    nodes = j.nodes.copy()
+    nodes[:, 2] = 0.9 * nodes[:, 0] + 1.1 * nodes[:, 1]
+    return mb.SimulationJob(nodes, j.elements, j.elementalNormals, j.fixedNodes, j.nodalForces, j.beamDimensions, j.beamMaterial)
+
+
 @pytest.mark.parametrize("name,make", [("lattice_24", lambda: syn.cubic_lattice(24)), ("lattice_45", lambda: syn.cubic_lattice(45)),
                                        ("gridshell_150", lambda: syn.gridshell(150)), ("planar_grid_90", lambda: syn.planar_grid(90)),
-                                       ("random_3000", lambda: syn.random_mesh(11, V=3000, k=6))])
+                                       ("random_3000", lambda: syn.random_mesh(11, V=3000, k=6)),
+                                       ("tilted_plane_90", lambda: _tilted_plane(90))])
 def test_device_built_hierarchy_equals_the_host_builder(built, name, make):
     """One rank: the symbolic half of the multilevel preconditioner (aggregates of every level, level-1 pattern, Galerkin
     contributor lists, P / P^T / A P / P^T A P patterns) is built on the device (hier_dev.cu).  Every array must equal
@@ -683,6 +693,8 @@ def test_device_built_hierarchy_equals_the_host_builder(built, name, make):
         bad, on_device = c.compare_hierarchy()
         assert on_device == 1 and bad.shape[0] >= 1
         assert not bad.any(), bad
+        if name.startswith("tilted"):   # (a geometry made up for the sparse brick grid: the structures are the point)
+            return
         c.execute()
         U = c.displacements()
         its = c.stats()["iterations"]
