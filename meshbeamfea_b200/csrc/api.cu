@@ -76,6 +76,7 @@ struct mbfea_ctx {
     // pattern / contributor lists / solver format built on the device (plan_dev.cu): scratch, kept between jobs
     bool device_plan = false;
     DevBuf<int32_t> pd_cnt, pd_cur, pd_start, pd_scan;
+    DevBuf<int32_t> g_rowptr, g_colidx, g_diag, g_cptr, g_contrib;   // several ranks, rank 0: pattern of the whole system (hierarchy build)
     DevBuf<unsigned long long> pd_ent, pd_tot;
     // device: matrix + vectors.  vals = assembled K (full pattern); vals_s = stored blocks of
     // K~ = S K S^T; lfac/sinv = Cholesky factor of the diagonal blocks and its inverse
@@ -580,6 +581,35 @@ void upload_forces(mbfea_ctx *c, int64_t nF, const int64_t *f_node, const int64_
     c->solved = c->recovered = false;
 }
 
+// Block pattern (and, when asked, the contributor lists) of the WHOLE reduced system on the device (plan_dev.cu), from
+// the mesh that is already there; fm = vertex -> block row (-1 fixed), nb rows.  Returns the number of blocks.
+int64_t device_pattern(mbfea_ctx *c, int64_t E, const int32_t *fm, int64_t nb, DevBuf<int32_t> &rowptr, DevBuf<int32_t> &colidx,
+                       DevBuf<int32_t> &diag_idx, DevBuf<int32_t> &contrib_ptr, DevBuf<int32_t> &contrib)
+{
+    // scratch: entries per row / cursor, entry start, blocks per row, scan scratch, 64-bit entries
+    CK(c->pd_cnt.alloc((size_t)nb + 1)); CK(c->pd_cur.alloc((size_t)nb + 1)); CK(c->pd_start.alloc((size_t)nb + 1));
+    CK(c->pd_scan.alloc((size_t)scan_i32_scratch(nb + 1)));
+    CK(cudaMemsetAsync(c->pd_cnt.p, 0, ((size_t)nb + 1) * sizeof(int32_t), c->st));
+    CK(cudaMemsetAsync(c->pd_cur.p, 0, ((size_t)nb + 1) * sizeof(int32_t), c->st));
+    launch_pd_count(c->st, E, c->stg_elems.p, fm, c->pd_cnt.p);
+    launch_scan_i32(c->st, nb, c->pd_cnt.p, c->pd_start.p, c->pd_scan.p);
+    int32_t nent = 0;
+    CK(cudaMemcpyAsync(&nent, c->pd_start.p + nb, sizeof nent, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    CK(c->pd_ent.alloc((size_t)nent + 1));
+    launch_pd_fill(c->st, E, c->stg_elems.p, fm, c->pd_start.p, c->pd_cur.p, c->pd_ent.p);
+    launch_pd_sort(c->st, nb, c->pd_start.p, c->pd_ent.p, c->pd_cnt.p);   // pd_cnt now: blocks per row
+    CK(rowptr.alloc((size_t)nb + 1));
+    launch_scan_i32(c->st, nb, c->pd_cnt.p, rowptr.p, c->pd_scan.p);
+    int32_t nnz32 = 0;
+    CK(cudaMemcpyAsync(&nnz32, rowptr.p + nb, sizeof nnz32, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    CK(colidx.alloc((size_t)nnz32)); CK(diag_idx.alloc((size_t)nb));
+    CK(contrib_ptr.alloc((size_t)nnz32 + 1)); CK(contrib.alloc((size_t)nent));
+    launch_pd_emit(c->st, nb, c->pd_start.p, c->pd_ent.p, rowptr.p, colidx.p, diag_idx.p, contrib_ptr.p, contrib.p);
+    return nnz32;
+}
+
 // mean beam length (the brick aggregates of the multilevel hierarchy are a few beam lengths wide): fixed chunks,
 // summed in chunk order -- reproducible, and the same value on the host and the device path of the hierarchy
 double mean_beam_length(int64_t V, int64_t E, const double *nodes_cm, const int32_t *elems_cm)
@@ -950,34 +980,18 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         static const bool force_host_hier = [] { const char *e = std::getenv("MBFEA_HOST_HIER"); return e && *e == '1'; }();
         const bool ml_dev_try = device_plan && !force_host_hier && c->plan.nb_global >= 64 &&
                                 (c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096));
-        if (!ml_dev_try) start_ml_thread();
+        // several ranks: rank 0 builds the hierarchy of the WHOLE system for everybody -- on its device too (global pattern,
+        // hierarchy with rank-local fine aggregates, flat image assembled device-to-device), else on the host thread
+        const bool ml_dev_multi = c->opt.world > 1 && c->opt.rank == 0 && !force_host_plan && !force_host_hier && c->plan.perm.empty() &&
+                                  c->plan.nb_global >= 64 && c->plan.nb() > 0 && 4 * E < (int64_t)INT32_MAX - 8 &&
+                                  (c->opt.precond == 2 || (c->opt.precond == 0 && c->plan.nb_global >= 4096));
+        if (!ml_dev_try && !ml_dev_multi) start_ml_thread();
         const int64_t nb = c->nb(), ng_dev = 0;
         (void)ng_dev;
         int64_t nnzb_dev = 0;
         if (device_plan) {
             HostPlan &P = c->plan;
-            // scratch: entries per row / cursor, entry start, blocks per row, scan scratch, 64-bit entries
-            CK(c->pd_cnt.alloc((size_t)nb + 1)); CK(c->pd_cur.alloc((size_t)nb + 1)); CK(c->pd_start.alloc((size_t)nb + 1));
-            CK(c->pd_scan.alloc((size_t)scan_i32_scratch(nb + 1)));
-            CK(cudaMemsetAsync(c->pd_cnt.p, 0, ((size_t)nb + 1) * sizeof(int32_t), c->st));
-            CK(cudaMemsetAsync(c->pd_cur.p, 0, ((size_t)nb + 1) * sizeof(int32_t), c->st));
-            launch_pd_count(c->st, E, c->stg_elems.p, c->free_canon.p, c->pd_cnt.p);
-            launch_scan_i32(c->st, nb, c->pd_cnt.p, c->pd_start.p, c->pd_scan.p);
-            int32_t nent = 0;
-            CK(cudaMemcpyAsync(&nent, c->pd_start.p + nb, sizeof nent, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            CK(c->pd_ent.alloc((size_t)nent + 1));
-            launch_pd_fill(c->st, E, c->stg_elems.p, c->free_canon.p, c->pd_start.p, c->pd_cur.p, c->pd_ent.p);
-            launch_pd_sort(c->st, nb, c->pd_start.p, c->pd_ent.p, c->pd_cnt.p);   // pd_cnt now: blocks per row
-            CK(c->rowptr.alloc((size_t)nb + 1));
-            launch_scan_i32(c->st, nb, c->pd_cnt.p, c->rowptr.p, c->pd_scan.p);
-            int32_t nnz32 = 0;
-            CK(cudaMemcpyAsync(&nnz32, c->rowptr.p + nb, sizeof nnz32, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            nnzb_dev = nnz32;
-            CK(c->colidx.alloc((size_t)nnzb_dev)); CK(c->diag_idx.alloc((size_t)nb));
-            CK(c->contrib_ptr.alloc((size_t)nnzb_dev + 1)); CK(c->contrib.alloc((size_t)nent));
-            launch_pd_emit(c->st, nb, c->pd_start.p, c->pd_ent.p, c->rowptr.p, c->colidx.p, c->diag_idx.p, c->contrib_ptr.p, c->contrib.p);
+            nnzb_dev = device_pattern(c, E, c->free_canon.p, nb, c->rowptr, c->colidx, c->diag_idx, c->contrib_ptr, c->contrib);
             // the pattern on the host: hierarchy build, component detection, taps
             P.rowptr.resize((size_t)nb + 1); P.colidx.resize((size_t)nnzb_dev);
             CK(cudaMemcpyAsync(P.rowptr.data(), c->rowptr.p, ((size_t)nb + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
@@ -994,7 +1008,19 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         else { c->plan.comp_ptr.clear(); c->plan.comp_max_rows = 0; }
         const bool batched = !c->plan.comp_ptr.empty();   // the batched kernel streams full plain rows
         mlh.signal(batched ? 2 : 1);   // the hierarchy thread may read the block pattern now (a batch has no use for it)
-        bool ml_on_device = false;
+        bool ml_on_device = false, ml_image_on_device = false;
+        if (ml_dev_multi) {
+            const int64_t nbg = c->plan.nb_global;
+            const int64_t g_nnz = device_pattern(c, E, c->free_canon.p, nbg, c->g_rowptr, c->g_colidx, c->g_diag, c->g_cptr, c->g_contrib);
+            c->ml.par = ml_params_of(c);
+            const double ml_len = mean_beam_length(V, E, nodes_cm, elems_cm);
+            ml_image_on_device = c->ml.build_hierarchy_device(c->st, V, c->node4.p, c->free_canon.p, nbg, c->g_rowptr.p, c->g_colidx.p, g_nnz,
+                                                              ml_len, c->opt.world) &&
+                                 c->ml.pack_image_device(c->st, c->opt.world, nbg, c->g_rowptr.p, g_nnz, c->ml_dimg, c->ml_layout.hd);
+            c->ml_mean_len = ml_len;
+            lap("global hierarchy + image on the device");
+            if (!ml_image_on_device) start_ml_thread();
+        }
         if (ml_dev_try && !batched) {
             c->ml.par = ml_params_of(c);
             const double ml_len = mean_beam_length(V, E, nodes_cm, elems_cm);
@@ -1141,7 +1167,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
                 if (bytes > 0) {
                     DevBuf<unsigned char> &dimg = c->ml_dimg;   // kept between jobs
                     CK(dimg.alloc((size_t)bytes));
-                    if (c->opt.rank == 0) {
+                    if (c->opt.rank == 0 && !ml_image_on_device) {
                         // the image is assembled on the device: header + every (page-locked) hierarchy array at its offset
                         CK(cudaMemcpyAsync(dimg.p, &c->ml_layout.hd, sizeof(MlImageHeader), cudaMemcpyHostToDevice, c->st));
                         for (const MlImageLayout::Part &pt : c->ml_layout.parts)

@@ -64,7 +64,9 @@ __global__ void k_h_box_fin(int nparts, const double *__restrict__ part, double 
     box[threadIdx.x] = r;
 }
 
-struct BrickGrid { double lo[3]; double cell; int64_t cnt[3]; };
+// parts (several ranks, fine level only): rows [bound[q], bound[q + 1]) belong to part q; a brick cut by a part boundary
+// becomes one aggregate per part and the aggregates are numbered part-major (key += q * bricks of the grid)
+struct BrickGrid { double lo[3]; double cell; int64_t cnt[3]; int32_t nparts; int64_t bound[kMaxWorld + 1]; };
 
 // brick of every row (the host's formula, operation for operation) + rows per brick
 __global__ void __launch_bounds__(kT) k_h_brick(int64_t n, const double *__restrict__ pos, BrickGrid g, int32_t *__restrict__ key,
@@ -80,7 +82,13 @@ __global__ void __launch_bounds__(kT) k_h_brick(int64_t n, const double *__restr
         k = k < 0 ? 0 : k;
         c[a] = k > g.cnt[a] - 1 ? g.cnt[a] - 1 : k;
     }
-    const int32_t b = (int32_t)((c[0] * g.cnt[1] + c[1]) * g.cnt[2] + c[2]);
+    int64_t b64 = (c[0] * g.cnt[1] + c[1]) * g.cnt[2] + c[2];
+    if (g.nparts > 1) {
+        int q = 0;
+        while (q + 1 < g.nparts && v >= g.bound[q + 1]) ++q;
+        b64 += (int64_t)q * (g.cnt[0] * g.cnt[1] * g.cnt[2]);
+    }
+    const int32_t b = (int32_t)b64;
     key[v] = b;
     atomicAdd(bcnt + b, 1);
 }
@@ -363,11 +371,13 @@ void launch_h_box(cudaStream_t st, int64_t n, const double *pos, double *part, d
     k_h_box_fin<<<1, 32, 0, st>>>(grid < 1 ? 1 : grid, part, box);
 }
 void launch_h_brick(cudaStream_t st, int64_t n, const double *pos, const double lo[3], double cell, const int64_t cnt[3], int32_t *key,
-                    int32_t *bcnt)
+                    int32_t *bcnt, const int64_t *part_bounds, int nparts)
 {
     BrickGrid g;
     for (int a = 0; a < 3; ++a) { g.lo[a] = lo[a]; g.cnt[a] = cnt[a]; }
     g.cell = cell;
+    g.nparts = (part_bounds != nullptr && nparts > 1) ? nparts : 1;
+    for (int q = 0; q <= kMaxWorld; ++q) g.bound[q] = (g.nparts > 1 && q <= nparts) ? part_bounds[q] : 0;
     if (n > 0) k_h_brick<<<blocks_for(n), kT, 0, st>>>(n, pos, g, key, bcnt);
 }
 void launch_h_occ(cudaStream_t st, int64_t nk, const int32_t *bcnt, int32_t *occ)

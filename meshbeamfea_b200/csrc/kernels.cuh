@@ -197,7 +197,7 @@ void launch_pf_fill(cudaStream_t st, int64_t nb, const int32_t *rowptr, const in
 void launch_h_pos(cudaStream_t st, int64_t V, const Node4 *node4, const int32_t *fm, double *pos);
 void launch_h_box(cudaStream_t st, int64_t n, const double *pos, double *part /* 6 * 256 */, double *box /* min[3], max[3] */);
 void launch_h_brick(cudaStream_t st, int64_t n, const double *pos, const double lo[3], double cell, const int64_t cnt[3], int32_t *key,
-                    int32_t *bcnt);
+                    int32_t *bcnt, const int64_t *part_bounds = nullptr, int nparts = 1);
 void launch_h_occ(cudaStream_t st, int64_t nk, const int32_t *bcnt, int32_t *occ);
 void launch_h_assign(cudaStream_t st, int64_t n, const int32_t *key, const int32_t *aggid, const int32_t *bstart, int32_t *bcur,
                      int32_t *agg, int32_t *agg_rows);

@@ -85,7 +85,12 @@ public:
     // false: nothing usable was built (mesh does not coarsen, brick grid too sparse for the counting sort, coarsest
     // level too large) -- the caller falls back to the host builder.
     bool build_hierarchy_device(cudaStream_t st, int64_t V, const dev::Node4 *d_node4, const int32_t *d_fm, int64_t nb,
-                                const int32_t *d_rowptr, const int32_t *d_colidx, int64_t fine_nnz, double mean_beam_length);
+                                const int32_t *d_rowptr, const int32_t *d_colidx, int64_t fine_nnz, double mean_beam_length,
+                                int nparts = 1);
+    // Several ranks, rank 0: after build_hierarchy_device(.., nparts = world) on the GLOBAL system, the flat image of
+    // ml_image_pack assembled from the device arrays (device-to-device) for the broadcast; hd: its header (host copy)
+    bool pack_image_device(cudaStream_t st, int world_, int64_t nbg, const int32_t *d_fine_rowptr, int64_t fine_nnz,
+                           DevBuf<unsigned char> &dimg, MlImageHeader &hd);
     // parity tap: the device arrays of the current hierarchy against a host hierarchy (mismatch counts per array, see api.cu)
     void compare_with_host(cudaStream_t st, const MlHierarchy &H, int64_t fine_nnz, std::vector<int64_t> &bad) const;
     // several ranks: the device arrays straight from the device copy of rank 0's image (ml_image_pack): device-to-device

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels.cuh"
 
@@ -189,7 +190,7 @@ T fetch(cudaStream_t st, const T *d)   // one scalar back from the device (synch
 }  // namespace
 
 bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_node4, const int32_t *d_fm, int64_t nb_,
-                                    const int32_t *d_rowptr, const int32_t *d_colidx, int64_t fine_nnz, double mean_len)
+                                    const int32_t *d_rowptr, const int32_t *d_colidx, int64_t fine_nnz, double mean_len, int nparts)
 {
     const double t0w = wall_ms();
     reset();
@@ -222,15 +223,18 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
         CK(cudaMemcpyAsync(box, hd_box.p, sizeof box, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         int64_t cnt[3];
-        double nk_d = 1.0;
+        const int parts = (l == 0 && nparts > 1) ? nparts : 1;   // several ranks: fine-level aggregates never straddle a rank
+        double nk_d = (double)parts;
         for (int a = 0; a < 3; ++a) {
             cnt[a] = std::max<int64_t>(1, (int64_t)std::floor((box[3 + a] - box[a]) / cell + 1e-9) + 1);
             nk_d *= (double)cnt[a];
         }
+        int64_t bounds[kMaxWorld + 1] = {0};
+        if (parts > 1) { if (parts > kMaxWorld) { give_up("too many parts", l, parts, 0); break; } for (int q = 0; q <= parts; ++q) bounds[q] = nb * q / parts; }
         // (the host builder switches from its counting sort to a comparison sort above 8 n bricks -- same numbering either
         //  way; here the counting arrays may be far sparser before they stop paying: 64 n bricks, at most 2^28)
         if (!(nk_d <= 64.0 * (double)n + 1024.0) || nk_d > 268435456.0) { give_up("sparse brick grid", l, (int64_t)nk_d, n); break; }
-        const int64_t nk = cnt[0] * cnt[1] * cnt[2];
+        const int64_t nk = cnt[0] * cnt[1] * cnt[2] * parts;
         if (l == 0) {   // the brick grids of the coarser levels are smaller: one allocation serves every level
             nk0 = nk;
             CK(hd_bcnt.alloc((size_t)nk + 3)); CK(hd_bcur.alloc((size_t)nk + 3)); CK(hd_occ.alloc((size_t)nk + 3));
@@ -238,7 +242,7 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
         } else if (nk > nk0) { give_up("brick grid grew", l, nk, nk0); break; }
         CK(cudaMemsetAsync(hd_bcnt.p, 0, ((size_t)nk + 1) * sizeof(int32_t), st));
         CK(cudaMemsetAsync(hd_bcur.p, 0, ((size_t)nk + 1) * sizeof(int32_t), st));
-        launch_h_brick(st, n, pos, box, cell, cnt, hd_key.p, hd_bcnt.p);
+        launch_h_brick(st, n, pos, box, cell, cnt, hd_key.p, hd_bcnt.p, bounds, parts);
         launch_h_occ(st, nk, hd_bcnt.p, hd_occ.p);
         launch_scan_i32(st, nk, hd_occ.p, hd_aggid.p, hd_scan.p);
         launch_scan_i32(st, nk, hd_bcnt.p, hd_bstart.p, hd_scan.p);
@@ -265,7 +269,9 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
         CK(next->rowptr.alloc((size_t)na + 1)); CK(next->diag_idx.alloc((size_t)na));
         if (l == 0) {
             group0 = fetch(st, hd_small.p) <= 8 ? 8 : 32;
-            agg_begin.assign({0, na});
+            agg_begin.assign((size_t)parts + 1, 0);
+            agg_begin[(size_t)parts] = na;
+            for (int q = 1; q < parts; ++q) agg_begin[(size_t)q] = fetch(st, hd_aggid.p + (int64_t)q * (nk / parts));   // occupied bricks before part q
             // level-1 pattern: candidates per aggregate -> sorted unique
             launch_h0_ub(st, na, aptr.p, arows.p, crp, hd_len.p);
             // (hd_aggptr is free on level 0: start of every aggregate's candidate segment)
@@ -277,7 +283,9 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
             next->nnz = fetch(st, next->rowptr.p + na);
             CK(next->colidx.alloc((size_t)next->nnz));
             launch_h0_emit(st, na, hd_aggptr.p, hd_cand.p, next->rowptr.p, next->colidx.p, next->diag_idx.p);
-            blk_begin.assign({0, next->nnz});
+            blk_begin.assign((size_t)parts + 1, 0);
+            blk_begin[(size_t)parts] = next->nnz;
+            for (int q = 1; q < parts; ++q) blk_begin[(size_t)q] = fetch(st, next->rowptr.p + agg_begin[(size_t)q]);
             // Galerkin contributor lists (counts, prefix, fill; the counters live in the candidate scratch)
             CK(hd_cand.alloc((size_t)std::max<int64_t>(ncand, next->nnz) + 1));
             CK(gal_ptr0.alloc((size_t)next->nnz + 1)); CK(gal_src0.alloc((size_t)fine_nnz));
@@ -345,6 +353,54 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
     CK(cudaStreamSynchronize(st));
     symbolic_ok = true;
     ms_symbolic = wall_ms() - t0w;
+    return true;
+}
+
+bool MlPrec::pack_image_device(cudaStream_t st, int world_, int64_t nbg, const int32_t *d_fine_rowptr, int64_t fine_nnz,
+                               DevBuf<unsigned char> &dimg, MlImageHeader &hd)
+{
+    const size_t L = lv.size();
+    if (!symbolic_ok || L == 0 || L > (size_t)kMlImageMaxLevels || world_ < 1 || world_ > kMlImageMaxWorld) return false;
+    if ((int)agg_begin.size() != world_ + 1 || (int)blk_begin.size() != world_ + 1) return false;
+    std::memset(&hd, 0, sizeof hd);
+    hd.magic = kMlImageMagic; hd.levels = (int64_t)L; hd.world = world_; hd.nbg = nbg; hd.fine_nnz = fine_nnz; hd.group0 = group0;
+    for (int q = 0; q <= world_; ++q) {
+        hd.agg_begin[q] = agg_begin[(size_t)q];
+        hd.blk_begin[q] = blk_begin[(size_t)q];
+        hd.own_first[q] = fetch(st, d_fine_rowptr + nbg * q / world_);
+        hd.aggptr_at[q] = fetch(st, agg_ptr0.p + agg_begin[(size_t)q]);
+        hd.galptr_at[q] = fetch(st, gal_ptr0.p + blk_begin[(size_t)q]);
+    }
+    struct Part { const void *p; size_t bytes; int64_t cnt; };
+    std::vector<std::vector<Part>> src(L);
+    auto pi = [](const DevBuf<int32_t> &d, int64_t n) { return Part{d.p, (size_t)n * sizeof(int32_t), n}; };
+    auto pd = [](const DevBuf<double> &d, int64_t n) { return Part{d.p, (size_t)n * sizeof(double), n}; };
+    const MlCoarse &c0 = *lv[0];
+    src[0] = {pi(agg0, nb), pd(off0, 3 * nb), pi(agg_ptr0, c0.n + 1), pi(agg_rows0, nb), pi(c0.rowptr, c0.n + 1), pi(c0.colidx, c0.nnz),
+              pi(c0.diag_idx, c0.n), pi(gal_ptr0, c0.nnz + 1), pi(gal_src0, fine_nnz)};
+    for (size_t l = 1; l < L; ++l) {
+        const MlCoarse &c = *lv[l - 1], &nx = *lv[l];
+        src[l] = {pi(c.agg, c.n), pd(c.off, 3 * c.n), pi(c.prow, c.n + 1), pi(c.pcol, c.nnzp), pi(c.rrow, nx.n + 1), pi(c.rblk, c.nnzp),
+                  pi(c.rfine, c.nnzp), pi(c.aprow, c.n + 1), pi(c.apcol, c.nnzap), pi(nx.rowptr, nx.n + 1), pi(nx.colidx, nx.nnz),
+                  pi(nx.diag_idx, nx.n)};
+    }
+    size_t at = (sizeof(MlImageHeader) + 15) & ~(size_t)15;
+    for (size_t l = 0; l < L; ++l) {
+        hd.lv[l].n_fine = l == 0 ? nb : lv[l - 1]->n; hd.lv[l].n_coarse = lv[l]->n;
+        hd.lv[l].smoothed = (l >= 1 && lv[l - 1]->smoothed) ? 1 : 0;
+        for (size_t k = 0; k < src[l].size(); ++k) {
+            hd.lv[l].off[k] = (int64_t)at; hd.lv[l].cnt[k] = src[l][k].cnt;
+            at += (src[l][k].bytes + 15) & ~(size_t)15;
+        }
+    }
+    hd.total_bytes = (int64_t)at;
+    CK(dimg.alloc(at));
+    CK(cudaMemcpyAsync(dimg.p, &hd, sizeof hd, cudaMemcpyHostToDevice, st));
+    for (size_t l = 0; l < L; ++l)
+        for (size_t k = 0; k < src[l].size(); ++k)
+            if (src[l][k].bytes)
+                CK(cudaMemcpyAsync(dimg.p + hd.lv[l].off[k], src[l][k].p, src[l][k].bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));   // (hd is the caller's: the header copy above has been staged)
     return true;
 }
 
