@@ -76,7 +76,8 @@ struct mbfea_ctx {
     // pattern / contributor lists / solver format built on the device (plan_dev.cu): scratch, kept between jobs
     bool device_plan = false;
     DevBuf<int32_t> pd_cnt, pd_cur, pd_start, pd_scan;
-    DevBuf<int32_t> g_rowptr, g_colidx, g_diag, g_cptr, g_contrib;   // several ranks, rank 0: pattern of the whole system (hierarchy build)
+    DevBuf<int32_t> g_rowptr, g_colidx, g_diag, g_cptr, g_contrib;   // several ranks: pattern of the whole system (the rank's share is cut from it; rank 0: hierarchy build)
+    DevBuf<long long> ghost_dev;
     DevBuf<unsigned long long> pd_ent, pd_tot;
     // device: matrix + vectors.  vals = assembled K (full pattern); vals_s = stored blocks of
     // K~ = S K S^T; lfac/sinv = Cholesky factor of the diagonal blocks and its inverse
@@ -845,7 +846,9 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
     if (c->world() > 1 && !c->comm) return fail(c, MBFEA_ESTATE, "world > 1 requires mbfea_comm_init first");
     c->have_job = c->assembled = c->solved = c->recovered = false;
     std::string msg;
+    const double tv0 = now_ms();
     if (int rc = validate_job(V, E, elems_cm, dims_bh, mat_nuE, F, fixed, nF, f_node, f_dof, msg)) return fail(c, rc, msg);
+    if (std::getenv("MBFEA_PREP_TRACE")) std::fprintf(stderr, "[mbfea set_job] %-28s %8.2f ms\n", "validation", now_ms() - tv0);
 
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
@@ -858,6 +861,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             allgather_host(c, &token, tokens.data(), sizeof token);
         }
         std::memset(&c->stats, 0, sizeof c->stats);
+        if (std::getenv("MBFEA_PREP_TRACE")) std::fprintf(stderr, "[mbfea set_job] %-28s %8.2f ms\n", "peer unmap + rendezvous", now_ms() - tv0);
         const double t0 = now_ms();
         c->V = V; c->E = E; c->F = F;
         const bool ptrace = std::getenv("MBFEA_PREP_TRACE") != nullptr;
@@ -975,7 +979,10 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         static const bool force_host_plan = [] { const char *e = std::getenv("MBFEA_HOST_PLAN"); return e && *e == '1'; }();
         const bool device_plan = !force_host_plan && c->opt.world == 1 && c->plan.perm.empty() && c->plan.nb_global > 0 &&
                                  4 * E < (int64_t)INT32_MAX - 8;
-        c->device_plan = device_plan;
+        const bool device_plan_multi = !force_host_plan && c->opt.world > 1 && c->plan.perm.empty() && c->plan.nb_global > 0 && c->plan.nb() > 0 &&
+                                       4 * E < (int64_t)INT32_MAX - 8;
+        int64_t g_nnz = -1;   // several ranks: blocks of the global pattern once it is on the device
+        c->device_plan = device_plan || device_plan_multi;
         // ... and so is the symbolic half of the multilevel preconditioner (hier_dev.cu; MBFEA_HOST_HIER=1: host thread)
         static const bool force_host_hier = [] { const char *e = std::getenv("MBFEA_HOST_HIER"); return e && *e == '1'; }();
         const bool ml_dev_try = device_plan && !force_host_hier && c->plan.nb_global >= 64 &&
@@ -1001,6 +1008,47 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             P.ghost_global.clear(); P.ghost_owner.clear(); P.send_rows.clear(); P.send_dest.clear(); P.neighbors.clear();
             CK(c->send_rows.alloc(0));
             lap("pattern on the device + download");
+        } else if (device_plan_multi) {
+            // several ranks: every rank builds the pattern of the WHOLE system on its device (it holds the whole mesh; a few
+            // milliseconds) and takes its share: own block rows, local column ids (ghosts after the owned columns, ascending
+            // global order), own contributor lists.  Rank 0 keeps the global pattern for the hierarchy.
+            HostPlan &P = c->plan;
+            const int64_t nbg = P.nb_global, r0 = P.row_begin, r1 = P.row_end;
+            g_nnz = device_pattern(c, E, c->free_canon.p, nbg, c->g_rowptr, c->g_colidx, c->g_diag, c->g_cptr, c->g_contrib);
+            int32_t k0 = 0, k1 = 0, c0 = 0, c1 = 0;
+            CK(cudaMemcpyAsync(&k0, c->g_rowptr.p + r0, sizeof k0, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(&k1, c->g_rowptr.p + r1, sizeof k1, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            CK(cudaMemcpyAsync(&c0, c->g_cptr.p + k0, sizeof c0, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(&c1, c->g_cptr.p + k1, sizeof c1, cudaMemcpyDeviceToHost, c->st));
+            int32_t *mark = c->pd_cnt.p, *gidx = c->pd_start.p;   // scratch of the pattern pass (nbg + 1 entries), free again
+            CK(cudaMemsetAsync(mark, 0, ((size_t)nbg + 1) * sizeof(int32_t), c->st));
+            launch_pl_mark(c->st, k0, k1, c->g_colidx.p, r0, r1, mark);
+            launch_scan_i32(c->st, nbg, mark, gidx, c->pd_scan.p);
+            int32_t ng32 = 0;
+            CK(cudaMemcpyAsync(&ng32, gidx + nbg, sizeof ng32, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            nnzb_dev = (int64_t)k1 - k0;
+            CK(c->ghost_dev.alloc((size_t)ng32));
+            launch_pl_ghosts(c->st, nbg, mark, gidx, c->ghost_dev.p);
+            CK(c->rowptr.alloc((size_t)nb + 1)); CK(c->diag_idx.alloc((size_t)nb)); CK(c->colidx.alloc((size_t)nnzb_dev));
+            CK(c->contrib_ptr.alloc((size_t)nnzb_dev + 1)); CK(c->contrib.alloc((size_t)(c1 - c0)));
+            launch_pl_shift(c->st, nb + 1, c->g_rowptr.p + r0, k0, c->rowptr.p);
+            launch_pl_shift(c->st, nb, c->g_diag.p + r0, k0, c->diag_idx.p);
+            launch_pl_localize(c->st, k0, k1, c->g_colidx.p, r0, r1, gidx, c->colidx.p);
+            launch_pl_shift(c->st, nnzb_dev + 1, c->g_cptr.p + k0, c0, c->contrib_ptr.p);
+            if (c1 > c0) CK(cudaMemcpyAsync(c->contrib.p, c->g_contrib.p + c0, (size_t)(c1 - c0) * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->st));
+            // the local pattern and the ghost list on the host: halo plan, hierarchy slices, taps
+            P.rowptr.resize((size_t)nb + 1); P.colidx.resize((size_t)nnzb_dev); P.ghost_global.resize((size_t)ng32);
+            static_assert(sizeof(long long) == sizeof(int64_t), "ghost list is copied as is");
+            CK(cudaMemcpyAsync(P.rowptr.data(), c->rowptr.p, ((size_t)nb + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(P.colidx.data(), c->colidx.p, (size_t)nnzb_dev * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+            if (ng32) CK(cudaMemcpyAsync(P.ghost_global.data(), c->ghost_dev.p, (size_t)ng32 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            P.diag_idx.clear(); P.contrib_ptr.clear(); P.contrib.clear();
+            build_halo_lists(P);
+            upload(c, c->send_rows, P.send_rows);
+            lap("pattern on the device (rank's share) + download");
         } else {
             build_plan_pattern(E, elems_cm, true, c->plan);
         }
@@ -1011,7 +1059,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         bool ml_on_device = false, ml_image_on_device = false;
         if (ml_dev_multi) {
             const int64_t nbg = c->plan.nb_global;
-            const int64_t g_nnz = device_pattern(c, E, c->free_canon.p, nbg, c->g_rowptr, c->g_colidx, c->g_diag, c->g_cptr, c->g_contrib);
+            if (g_nnz < 0) g_nnz = device_pattern(c, E, c->free_canon.p, nbg, c->g_rowptr, c->g_colidx, c->g_diag, c->g_cptr, c->g_contrib);
             c->ml.par = ml_params_of(c);
             const double ml_len = mean_beam_length(V, E, nodes_cm, elems_cm);
             ml_image_on_device = c->ml.build_hierarchy_device(c->st, V, c->node4.p, c->free_canon.p, nbg, c->g_rowptr.p, c->g_colidx.p, g_nnz,
@@ -1043,7 +1091,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             launch_apply_perm(c->st, V, c->free_canon.p, d_perm.p, c->free_index.p);
             CK(cudaStreamSynchronize(c->st));
         }
-        if (!device_plan) {
+        if (!device_plan && !device_plan_multi) {
             upload(c, c->rowptr, c->plan.rowptr);
             upload(c, c->colidx, c->plan.colidx);
             upload(c, c->diag_idx, c->plan.diag_idx);
@@ -1057,7 +1105,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         const double tp1 = now_ms();
         const bool half = !batched && (c->opt.storage == 2 || (c->opt.storage == 0 && c->opt.spmv_kernel != 2));
         bool format_on_device = false;
-        if (device_plan && half) {
+        if ((device_plan || device_plan_multi) && half) {
             // upper rule on the device; an irregular numbering that pads the 32-row tiles by more than 5 % under it
             // (or a value array beyond 2^31 units) goes to the host builder, which balances the pair orientation
             const int64_t ntiles = (nb + 31) / 32;
@@ -1065,7 +1113,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             CK(c->pd_tot.alloc(2));
             CK(cudaMemsetAsync(c->pd_tot.p, 0, 2 * sizeof(unsigned long long), c->st));
             int32_t *nu = c->pd_cnt.p, *nl = c->pd_cur.p, *tunits = c->pd_start.p;   // scratch of the pattern pass, free again
-            launch_pf_count(c->st, nb, c->rowptr.p, c->diag_idx.p, nu, nl);
+            launch_pf_count(c->st, nb, c->rowptr.p, c->colidx.p, nu, nl);
             launch_pf_tiles(c->st, nb, nu, tunits, c->pd_tot.p);
             unsigned long long tot[2] = {0, 0};
             CK(cudaMemcpyAsync(tot, c->pd_tot.p, sizeof tot, cudaMemcpyDeviceToHost, c->st));
@@ -1200,6 +1248,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
             lap("multilevel hierarchy");
         }
         setup_p2p_halo(c);
+        lap("peer mappings + push lists");
         c->stats.ms_h2d = now_ms() - t1;
 
         mbfea_stats &s = c->stats;

@@ -22,6 +22,9 @@ namespace mbfea {
 // setNodes() -> setFixedNodes() -> setNodalForces()
 // [REF src/beamsimulator.cpp:107-111].
 // ---------------------------------------------------------------------------
+template <class Fn>
+static void parallel_ranges(int64_t n, int64_t min_per_thread, Fn fn);   // (defined below)
+
 int validate_forces(int64_t V, int64_t nF, const int64_t *f_node, const int64_t *f_dof,
                     std::string &msg)
 {
@@ -56,30 +59,37 @@ int validate_job(int64_t V, int64_t E, const int32_t *elems_cm, const float *dim
         msg = "job too large for 32-bit block indices";
         return MBFEA_EARG;
     }
-    for (int64_t e = 0; e < E; ++e) {
+    // per beam, in the reference's order of checks; chunks are scanned in parallel and the FIRST offending beam decides
+    // the message, as in a serial scan
+    //   1 the reference's range check [REF :81-83] compares against 3V and lets negatives through; anything it would
+    //     let through out of [0,V) is UB there, so this build rejects it as the same class of error
+    //   3, 4 BeamDimensions / BeamMaterial constructors [REF src/beam.hpp:14,25]
+    auto check = [=](int64_t e) -> int {
         const int32_t a = elems_cm[e], b = elems_cm[E + e];
-        // the reference's range check [REF :81-83] compares against 3V and lets
-        // negatives through; anything it would let through out of [0,V) is UB
-        // there, so this build rejects it as the same class of error.
-        if (a < 0 || b < 0 || a >= V || b >= V) {
-            msg = "precondition violated: element node index out of range";
-            return MBFEA_EPRECOND;
-        }
-        if (a == b) {
-            msg = "precondition violated: zero-length beam (both ends on one vertex)";
-            return MBFEA_EPRECOND;
-        }
-        // BeamDimensions / BeamMaterial constructors [REF src/beam.hpp:14,25]
+        if (a < 0 || b < 0 || a >= V || b >= V) return 1;
+        if (a == b) return 2;
         const float bb = dims_bh[2 * e], hh = dims_bh[2 * e + 1];
         const float nu = mat_nuE[2 * e];
-        if (!(bb > 0 && hh > 0)) {
-            msg = "precondition violated: beam dimensions must be positive";
-            return MBFEA_EPRECOND;
-        }
-        if (!(nu <= 0.5f && nu >= -1.0f)) {
-            msg = "precondition violated: Poisson's ratio outside [-1, 0.5]";
-            return MBFEA_EPRECOND;
-        }
+        if (!(bb > 0 && hh > 0)) return 3;
+        if (!(nu <= 0.5f && nu >= -1.0f)) return 4;
+        return 0;
+    };
+    int64_t first_bad[32];
+    for (auto &x : first_bad) x = -1;
+    int64_t *fbp = first_bad;
+    parallel_ranges(E, 1 << 16, [=](int64_t lo, int64_t hi, int t) {
+        for (int64_t e = lo; e < hi; ++e)
+            if (check(e) != 0) { fbp[t] = e; return; }
+    });
+    int64_t bad = -1;
+    for (int64_t x : first_bad) if (x >= 0 && (bad < 0 || x < bad)) bad = x;
+    if (bad >= 0) {
+        static const char *const what[] = {"", "precondition violated: element node index out of range",
+                                           "precondition violated: zero-length beam (both ends on one vertex)",
+                                           "precondition violated: beam dimensions must be positive",
+                                           "precondition violated: Poisson's ratio outside [-1, 0.5]"};
+        msg = what[check(bad)];
+        return MBFEA_EPRECOND;
     }
     for (int64_t i = 0; i < F; ++i) {
         if (fixed[i] < 0 || (int64_t)fixed[i] > V - 1) {
@@ -374,9 +384,8 @@ void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const 
 void build_plan_pattern(int64_t E, const int32_t *elems_cm, bool with_contrib, HostPlan &P)
 {
     PrepTrace tr;
-    const int32_t rank = P.rank, world = P.world;
+    const int32_t world = P.world;
     RankShare share(world);
-    const int64_t nbg = P.nb_global;
     const int64_t r0 = P.row_begin, nb = P.row_end - P.row_begin;
     const int32_t *fm = P.free_index.data();
 
@@ -534,9 +543,6 @@ void build_plan_pattern(int64_t E, const int32_t *elems_cm, bool with_contrib, H
             if (gcol[k] < r0 || gcol[k] >= r0 + nb) P.ghost_global.push_back(gcol[k]);
     std::sort(P.ghost_global.begin(), P.ghost_global.end());
     P.ghost_global.erase(std::unique(P.ghost_global.begin(), P.ghost_global.end()), P.ghost_global.end());
-    const int64_t ng = (int64_t)P.ghost_global.size();
-    P.ghost_owner.resize((size_t)ng);
-    for (int64_t i = 0; i < ng; ++i) P.ghost_owner[i] = owner_of(P.ghost_global[i], nbg, world);
     parallel_ranges(nnzb, 1 << 18, [&](int64_t lo, int64_t hi, int) {
         for (int64_t k = lo; k < hi; ++k) {
             const int64_t g = gcol[k];
@@ -548,6 +554,20 @@ void build_plan_pattern(int64_t E, const int32_t *elems_cm, bool with_contrib, H
         }
     });
     tr.lap("ghosts + local column ids");
+    build_halo_lists(P);
+    tr.lap("send lists");
+}
+
+// Owners of the ghost columns, send lists and neighbour table of a rank from its local pattern (rowptr, colidx with
+// local ids) and its ascending ghost list -- the last step of build_plan_pattern, also used when the pattern was
+// built on the device.
+void build_halo_lists(HostPlan &P)
+{
+    const int32_t rank = P.rank, world = P.world;
+    const int64_t nbg = P.nb_global, nb = P.row_end - P.row_begin;
+    const int64_t ng = (int64_t)P.ghost_global.size();
+    P.ghost_owner.resize((size_t)ng);
+    for (int64_t i = 0; i < ng; ++i) P.ghost_owner[i] = owner_of(P.ghost_global[i], nbg, world);
     // sends: the pattern is symmetric, so rank q needs owned row i from us iff
     // row i has a column owned by q.  Sorted by (dest, row) == the order in which
     // q lists them among its ghosts (ascending global id).
@@ -577,7 +597,6 @@ void build_plan_pattern(int64_t E, const int32_t *elems_cm, bool with_contrib, H
         nbq.send_offset = sl - P.send_dest.begin(); nbq.send_count = sh - sl;
         if (nbq.recv_count || nbq.send_count) P.neighbors.push_back(nbq);
     }
-    tr.lap("send lists");
 }
 
 void build_solver_format(HostPlan &P, bool half)

@@ -187,7 +187,13 @@ void launch_pd_fill(cudaStream_t st, int64_t E, const int32_t *elems_cm, const i
 void launch_pd_sort(cudaStream_t st, int64_t nb, const int32_t *start, unsigned long long *ent, int32_t *nblk);
 void launch_pd_emit(cudaStream_t st, int64_t nb, const int32_t *start, const unsigned long long *ent, const int32_t *rowptr,
                     int32_t *colidx, int32_t *diag_idx, int32_t *contrib_ptr, int32_t *contrib);
-void launch_pf_count(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *diag_idx, int32_t *nu, int32_t *nl);
+void launch_pf_count(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx, int32_t *nu, int32_t *nl);
+// the rank's share [r0, r1) of a pattern of the whole system: ghost marks over the blocks [k0, k1), ghost list, local ids
+void launch_pl_mark(cudaStream_t st, int64_t k0, int64_t k1, const int32_t *gcol, int64_t r0, int64_t r1, int32_t *mark);
+void launch_pl_ghosts(cudaStream_t st, int64_t nbg, const int32_t *mark, const int32_t *gidx, long long *ghost_global);
+void launch_pl_localize(cudaStream_t st, int64_t k0, int64_t k1, const int32_t *gcol, int64_t r0, int64_t r1, const int32_t *gidx,
+                        int32_t *colidx_l);
+void launch_pl_shift(cudaStream_t st, int64_t n, const int32_t *src, int32_t delta, int32_t *dst);
 void launch_pf_tiles(cudaStream_t st, int64_t nb, const int32_t *nu, int32_t *tunits, unsigned long long *totals);
 void launch_pf_fill(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx, const int32_t *diag_idx,
                     const int32_t *uptr, const int32_t *lptr, const int32_t *tile_base, int32_t *ucol, int32_t *usrc, int32_t *lcol,

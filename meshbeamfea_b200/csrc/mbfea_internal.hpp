@@ -119,6 +119,8 @@ void build_plan_begin(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, 
                       HostPlan &plan, int reorder = 0, const double *nodes_cm = nullptr);
 // The second part: block pattern, contributor lists and halo plan of the rank, from the state build_plan_begin left.
 void build_plan_pattern(int64_t E, const int32_t *elems_cm, bool with_contrib, HostPlan &plan);
+// Ghost owners, send lists and neighbour table from the rank's local pattern and its ascending ghost list.
+void build_halo_lists(HostPlan &plan);
 // after_free_map (optional): called once free_index, nb_global and the row range are final, before the pattern passes
 void build_plan(int64_t V, int64_t E, const int32_t *elems_cm, int64_t F, const int32_t *fixed,
                 int32_t rank, int32_t world, bool with_contrib, HostPlan &plan, int reorder = 0,

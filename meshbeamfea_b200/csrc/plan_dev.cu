@@ -201,15 +201,19 @@ __global__ void __launch_bounds__(128) k_pd_emit(int64_t nb, const int32_t *__re
 }
 
 // ---- solver format, upper rule ----
-// stored / referenced blocks per row (columns ascend and the diagonal is present: the stored ones follow it)
-__global__ void __launch_bounds__(kT) k_pf_count(int64_t nb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ diag_idx,
+// stored / referenced blocks per row: a row stores its ghost columns (local ids >= nb; several ranks) and its local
+// columns above the diagonal; the local columns below it are transposed references
+__global__ void __launch_bounds__(kT) k_pf_count(int64_t nb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                                                  int32_t *__restrict__ nu, int32_t *__restrict__ nl)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
-    const int32_t d = diag_idx[r];
-    nu[r] = rowptr[r + 1] - 1 - d;
-    nl[r] = d - rowptr[r];
+    int32_t u = 0, l = 0;
+    for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        const int32_t c = colidx[k];
+        if (c >= nb || c > (int32_t)r) ++u; else if (c < (int32_t)r) ++l;
+    }
+    nu[r] = u; nl[r] = l;
 }
 
 // per tile of 32 rows: 16-byte units of the interleaved layout (longest row x 3 chunks x 192 threads); totals of
@@ -235,19 +239,53 @@ __global__ void __launch_bounds__(128) k_pf_fill(int64_t nb, const int32_t *__re
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nb) return;
-    const int32_t d = diag_idx[r];
-    int32_t u = uptr[r];
-    for (int32_t k = d + 1; k < rowptr[r + 1]; ++k, ++u) { ucol[u] = colidx[k]; usrc[u] = k; }
-    int32_t l = lptr[r];
-    for (int32_t k = rowptr[r]; k < d; ++k, ++l) {
+    int32_t u = uptr[r], l = lptr[r];
+    for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
         const int32_t c = colidx[k];
-        // the slot of (c, r) inside row c's stored list (present by symmetry of the pattern)
-        int32_t lo = diag_idx[c] + 1, hi = rowptr[c + 1];
-        const int32_t first = lo;
+        if (c == (int32_t)r) continue;
+        if (c >= nb || c > (int32_t)r) { ucol[u] = c; usrc[u] = k; ++u; continue; }
+        // transposed reference: the slot of (c, r) inside row c's stored list (present by symmetry of the local pattern).
+        // Row c lists [ghosts of lower ranks][local columns below c][c][local columns above c][ghosts of higher ranks]
+        // (ascending GLOBAL ids); it stores the ghosts and the local columns above c, in that order.
+        int32_t low = rowptr[c];
+        while (colidx[low] >= nb) ++low;             // leading ghost columns (the diagonal ends the scan at the latest)
+        const int32_t first = diag_idx[c] + 1;
+        int32_t lo = first, hi = rowptr[c + 1];      // ascending local ids behind the diagonal (ghost ids are >= nb)
         while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (colidx[mid] < (int32_t)r) lo = mid + 1; else hi = mid; }
         lcol[l] = c;
-        lofs[l] = tile_base[c >> 5] + (lo - first) * 3 * 192 + (c & 31) * 6;
+        lofs[l] = tile_base[c >> 5] + ((low - rowptr[c]) + (lo - first)) * 3 * 192 + (c & 31) * 6;
+        ++l;
     }
+}
+
+// ---- the rank's share of a pattern built for the whole system (several ranks) ----
+// ghost columns of the rows [r0, r1): global columns outside the range, marked (then ranked by a scan: ascending order)
+__global__ void __launch_bounds__(kT) k_pl_mark(int64_t k0, int64_t k1, const int32_t *__restrict__ gcol, int32_t r0, int32_t r1, int32_t *mark)
+{
+    const int64_t k = k0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const int32_t g = gcol[k];
+    if (g < r0 || g >= r1) mark[g] = 1;   // (every writer stores the same value)
+}
+__global__ void __launch_bounds__(kT) k_pl_ghosts(int64_t nbg, const int32_t *__restrict__ mark, const int32_t *__restrict__ gidx,
+                                                  long long *__restrict__ ghost_global)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nbg && mark[g]) ghost_global[gidx[g]] = g;
+}
+// local column ids: owned [0, nb), ghosts after (in ascending global order); the blocks of a row keep their global order
+__global__ void __launch_bounds__(kT) k_pl_localize(int64_t k0, int64_t k1, const int32_t *__restrict__ gcol, int32_t r0, int32_t r1,
+                                                    const int32_t *__restrict__ gidx, int32_t *__restrict__ colidx_l)
+{
+    const int64_t k = k0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const int32_t g = gcol[k];
+    colidx_l[k - k0] = (g >= r0 && g < r1) ? g - r0 : (r1 - r0) + gidx[g];
+}
+__global__ void __launch_bounds__(kT) k_pl_shift(int64_t n, const int32_t *__restrict__ src, int32_t delta, int32_t *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] - delta;
 }
 }  // namespace
 
@@ -278,9 +316,26 @@ void launch_pd_emit(cudaStream_t st, int64_t nb, const int32_t *start, const uns
 {
     if (nb > 0) k_pd_emit<<<blocks_for(nb, 128), 128, 0, st>>>(nb, start, ent, rowptr, colidx, diag_idx, contrib_ptr, contrib);
 }
-void launch_pf_count(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *diag_idx, int32_t *nu, int32_t *nl)
+void launch_pf_count(cudaStream_t st, int64_t nb, const int32_t *rowptr, const int32_t *colidx, int32_t *nu, int32_t *nl)
 {
-    if (nb > 0) k_pf_count<<<blocks_for(nb), kT, 0, st>>>(nb, rowptr, diag_idx, nu, nl);
+    if (nb > 0) k_pf_count<<<blocks_for(nb), kT, 0, st>>>(nb, rowptr, colidx, nu, nl);
+}
+void launch_pl_mark(cudaStream_t st, int64_t k0, int64_t k1, const int32_t *gcol, int64_t r0, int64_t r1, int32_t *mark)
+{
+    if (k1 > k0) k_pl_mark<<<blocks_for(k1 - k0), kT, 0, st>>>(k0, k1, gcol, (int32_t)r0, (int32_t)r1, mark);
+}
+void launch_pl_ghosts(cudaStream_t st, int64_t nbg, const int32_t *mark, const int32_t *gidx, long long *ghost_global)
+{
+    if (nbg > 0) k_pl_ghosts<<<blocks_for(nbg), kT, 0, st>>>(nbg, mark, gidx, ghost_global);
+}
+void launch_pl_localize(cudaStream_t st, int64_t k0, int64_t k1, const int32_t *gcol, int64_t r0, int64_t r1, const int32_t *gidx,
+                        int32_t *colidx_l)
+{
+    if (k1 > k0) k_pl_localize<<<blocks_for(k1 - k0), kT, 0, st>>>(k0, k1, gcol, (int32_t)r0, (int32_t)r1, gidx, colidx_l);
+}
+void launch_pl_shift(cudaStream_t st, int64_t n, const int32_t *src, int32_t delta, int32_t *dst)
+{
+    if (n > 0) k_pl_shift<<<blocks_for(n), kT, 0, st>>>(n, src, delta, dst);
 }
 void launch_pf_tiles(cudaStream_t st, int64_t nb, const int32_t *nu, int32_t *tunits, unsigned long long *totals)
 {

@@ -35,6 +35,9 @@ def _worker(rank, world, uid_path, out_dir, n, comm_mode, variant, precond):
     c.comm_init(uid, rank, world)
     c.set_job(job.nodes, job.elements, job.elementalNormals, job.beamDimensions, job.beamMaterial,
               job.fixedNodes, job.nodalForces)
+    # the rank's plan is cut from a pattern built on the device: every array equals the host builders' for this rank
+    bad, where = c.compare_plan()
+    assert where >= 1 and not bad.any(), (rank, where, bad)
     c.execute()
     rp, col, vals, rows = c.bsr()
     st = c.stats()
