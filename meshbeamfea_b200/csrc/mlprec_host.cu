@@ -211,6 +211,8 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
     const int smooth_from = std::max(1, par.smooth_from);
     bool ok = true;
     int64_t nk0 = 0, na0 = 0;
+    // experiment: a different brick growth between the coarse levels (fewer, smaller levels in the replicated tail)
+    const double ratio_coarse = [] { const char *e = std::getenv("MBFEA_ML_RATIO_COARSE"); return e ? std::atof(e) : 0.0; }();
     const bool trace = std::getenv("MBFEA_PREP_TRACE") != nullptr;
     auto give_up = [&](const char *why, int l, int64_t a, int64_t b) {
         if (trace) std::fprintf(stderr, "[mbfea hierarchy] device build gives up at level %d: %s (%lld, %lld)\n", l, why, (long long)a, (long long)b);
@@ -340,7 +342,7 @@ bool MlPrec::build_hierarchy_device(cudaStream_t st, int64_t V, const Node4 *d_n
         cur_pos ^= 1;
         pos = hd_pos[cur_pos].p;
         n = na;
-        cell *= par.ratio;
+        cell *= (l >= 1 && ratio_coarse > 1.0) ? ratio_coarse : par.ratio;
     }
     if (ok && !lv.empty() && 6 * lv.back()->n > 3072) give_up("coarsest level too large", (int)lv.size(), lv.back()->n, 0);
     if (!ok || lv.empty()) { reset(); return false; }
