@@ -389,12 +389,14 @@ def main():
         barrier()
         t0 = time.perf_counter()
         parts = [0.0, 0.0, 0.0]
+        per_step = []
         for _ in range(args.steps):
             ta = time.perf_counter(); set_job()
             tb = time.perf_counter(); ctx.execute()
             tc = time.perf_counter(); fetch()
             td = time.perf_counter()
             parts[0] += tb - ta; parts[1] += tc - tb; parts[2] += td - tc
+            per_step.append([round(1e3 * (tb - ta), 2), round(1e3 * (tc - tb), 2), round(1e3 * (td - tc), 2)])
         barrier()
         dte = time.perf_counter() - t0
         if world > 1:
@@ -406,7 +408,8 @@ def main():
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dte / args.steps,
                "ms_set_job": 1e3 * parts[0] / args.steps, "ms_execute": 1e3 * parts[1] / args.steps,
                "ms_fetch_results": 1e3 * parts[2] / args.steps,
-               "ms_host_prep": s2["ms_host_prep"], "ms_h2d_incl_plan": s2["ms_h2d"], "ms_d2h": s2["ms_d2h"]}
+               "ms_host_prep": s2["ms_host_prep"], "ms_h2d_incl_plan": s2["ms_h2d"], "ms_d2h": s2["ms_d2h"],
+               "ms_per_step_parts": per_step}   # rank 0: [set_job, execute, fetch] of every timed step
 
     # (after the end-to-end loop: a second context's host allocations in between slowed the next set_job by 200 ms)
     # ---- the same SpMV family on the full-row format (every block in its own row): more bytes, higher

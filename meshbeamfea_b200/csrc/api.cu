@@ -112,6 +112,7 @@ struct mbfea_ctx {
 
     // multilevel preconditioner (options.precond): hierarchy built in set_job, numeric setup in assemble
     MlPrec ml;
+    MlPrec ml_global;   // several ranks, rank 0: builder of the hierarchy of the whole system (device path)
     bool use_ml = false;
     bool ml_on_device = false;   // the hierarchy of the current job was built on the device
     double ml_mean_len = 0.0;
@@ -356,12 +357,14 @@ void setup_p2p_halo(mbfea_ctx *c)
     for (const Neighbor &n : c->plan.neighbors) r.recv_off[n.rank] = n.recv_offset;
     std::vector<Rec> all((size_t)W);
     allgather_host(c, &r, all.data(), sizeof(Rec));
-    c->peer_p.assign((size_t)W, nullptr);
-    for (int q = 0; q < W; ++q) {
-        if (q == me) { c->peer_p[q] = c->p.p; continue; }
-        void *ptr = nullptr;
-        CK(cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess));
-        c->peer_p[q] = static_cast<double *>(ptr);
+    if (c->peer_p.empty()) {   // (else: the mappings of the previous job are still valid, see set_job)
+        c->peer_p.assign((size_t)W, nullptr);
+        for (int q = 0; q < W; ++q) {
+            if (q == me) { c->peer_p[q] = c->p.p; continue; }
+            void *ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_p[q] = static_cast<double *>(ptr);
+        }
     }
     // what rank q receives from me occupies q's ghost slots [recv_off_q[me], ...) in my send order
     std::vector<double *> dst(c->plan.send_rows.size());
@@ -846,6 +849,9 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
     if (c->world() > 1 && !c->comm) return fail(c, MBFEA_ESTATE, "world > 1 requires mbfea_comm_init first");
     c->have_job = c->assembled = c->solved = c->recovered = false;
     std::string msg;
+    // one process per GPU on one node: each rank's host passes take their share of the cores (8 ranks x 16 threads on
+    // 16 cores only thrash)
+    struct Share { explicit Share(int w) { host_threads_share(w); } ~Share() { host_threads_share(1); } } share(c->opt.world);
     const double tv0 = now_ms();
     if (int rc = validate_job(V, E, elems_cm, dims_bh, mat_nuE, F, fixed, nF, f_node, f_dof, msg)) return fail(c, rc, msg);
     if (std::getenv("MBFEA_PREP_TRACE")) std::fprintf(stderr, "[mbfea set_job] %-28s %8.2f ms\n", "validation", now_ms() - tv0);
@@ -853,15 +859,7 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
     return guarded(c, [&]() -> int {
         CK(cudaSetDevice(c->device));
         drop_graph(c);
-        if (c->p2p) {
-            // peers unmap my old p before I free it (the all-gather is the rendezvous)
-            close_peer_vectors(c);
-            int64_t token = 0;
-            std::vector<int64_t> tokens((size_t)c->world());
-            allgather_host(c, &token, tokens.data(), sizeof token);
-        }
         std::memset(&c->stats, 0, sizeof c->stats);
-        if (std::getenv("MBFEA_PREP_TRACE")) std::fprintf(stderr, "[mbfea set_job] %-28s %8.2f ms\n", "peer unmap + rendezvous", now_ms() - tv0);
         const double t0 = now_ms();
         c->V = V; c->E = E; c->F = F;
         const bool ptrace = std::getenv("MBFEA_PREP_TRACE") != nullptr;
@@ -1060,11 +1058,14 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         if (ml_dev_multi) {
             const int64_t nbg = c->plan.nb_global;
             if (g_nnz < 0) g_nnz = device_pattern(c, E, c->free_canon.p, nbg, c->g_rowptr, c->g_colidx, c->g_diag, c->g_cptr, c->g_contrib);
+            // (a builder object of its own: the global arrays are W times the size of the rank's share that c->ml holds
+            //  afterwards -- one object for both would free and reallocate every level buffer twice per job)
             c->ml.par = ml_params_of(c);
+            c->ml_global.par = c->ml.par;
             const double ml_len = mean_beam_length(V, E, nodes_cm, elems_cm);
-            ml_image_on_device = c->ml.build_hierarchy_device(c->st, V, c->node4.p, c->free_canon.p, nbg, c->g_rowptr.p, c->g_colidx.p, g_nnz,
-                                                              ml_len, c->opt.world) &&
-                                 c->ml.pack_image_device(c->st, c->opt.world, nbg, c->g_rowptr.p, g_nnz, c->ml_dimg, c->ml_layout.hd);
+            ml_image_on_device = c->ml_global.build_hierarchy_device(c->st, V, c->node4.p, c->free_canon.p, nbg, c->g_rowptr.p, c->g_colidx.p,
+                                                                     g_nnz, ml_len, c->opt.world) &&
+                                 c->ml_global.pack_image_device(c->st, c->opt.world, nbg, c->g_rowptr.p, g_nnz, c->ml_dimg, c->ml_layout.hd);
             c->ml_mean_len = ml_len;
             lap("global hierarchy + image on the device");
             if (!ml_image_on_device) start_ml_thread();
@@ -1185,6 +1186,23 @@ int mbfea_set_job(mbfea_ctx *c, int64_t V, int64_t E, const double *nodes_cm, co
         CK(c->ft.alloc((size_t)6 * nb));
         CK(c->sdir.alloc((size_t)6 * nb));
         CK(c->Ap.alloc((size_t)6 * nb));
+        if (c->p2p) {
+            // The peers map my p (CUDA IPC) and I map theirs.  The mappings are KEPT from job to job as long as nobody's p
+            // has to be reallocated (a re-submitted mesh: cudaIpcOpen/CloseMemHandle cost ~5 ms per peer, 35 ms on eight
+            // ranks); when any rank must reallocate, everybody unmaps first -- the second all-gather is the rendezvous
+            // that lets the owners free -- and setup_p2p_halo maps afresh.
+            const int W = c->world();
+            int64_t flag = (c->p.fits((size_t)6 * (size_t)(nb + ng)) && !c->peer_p.empty()) ? 0 : 1;
+            std::vector<int64_t> flags((size_t)W);
+            allgather_host(c, &flag, flags.data(), sizeof flag);
+            bool any = false;
+            for (int q = 0; q < W; ++q) any = any || flags[(size_t)q] != 0;
+            if (any) {
+                close_peer_vectors(c);
+                int64_t token = 0;
+                allgather_host(c, &token, flags.data(), sizeof token);
+            }
+        }
         CK(c->p.alloc((size_t)6 * (nb + ng)));
         CK(cudaMemsetAsync(c->p.p, 0, (size_t)std::max<int64_t>(1, 6 * (nb + ng)) * sizeof(double), c->st));
         CK(c->xg.alloc((size_t)6 * c->plan.nb_global));

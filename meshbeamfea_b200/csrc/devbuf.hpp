@@ -21,10 +21,16 @@ struct DevBuf {
     }
     // keeps the allocation when it is large enough (and not wastefully so): a second
     // set_job on a same-sized mesh costs no cudaFree/cudaMalloc round trips
+    // would alloc(count) keep the current allocation?
+    bool fits(size_t count) const
+    {
+        if (count == 0) count = 1;
+        return p && cap >= count && cap <= 2 * count + 1024;
+    }
     cudaError_t alloc(size_t count)
     {
         if (count == 0) count = 1;
-        if (p && cap >= count && cap <= 2 * count + 1024) { n = count; return cudaSuccess; }
+        if (fits(count)) { n = count; return cudaSuccess; }
         release();
         cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
         if (e == cudaSuccess) { n = count; cap = count; } else p = nullptr;

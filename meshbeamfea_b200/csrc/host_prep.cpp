@@ -132,6 +132,8 @@ struct RankShare {
     explicit RankShare(int world) : saved(tl_rank_share) { tl_rank_share = std::max(1, world); }
     ~RankShare() { tl_rank_share = saved; }
 };
+// the calling thread's passes share the node's cores with `world` ranks from here on (set_job; 1 = all cores)
+void host_threads_share(int world) { tl_rank_share = std::max(1, world); }
 static int64_t host_threads()
 {
     static const int forced = [] { const char *e = std::getenv("MBFEA_HOST_THREADS"); return e ? std::atoi(e) : 0; }();

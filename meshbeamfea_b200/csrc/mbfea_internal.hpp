@@ -103,6 +103,9 @@ int validate_job(int64_t V, int64_t E, const int32_t *elems_cm, const float *dim
 int validate_forces(int64_t V, int64_t nF, const int64_t *f_node, const int64_t *f_dof,
                     std::string &msg);
 
+// Host threads of the calling thread's parallel passes: the node's cores divided by `world` ranks that share them.
+void host_threads_share(int world);
+
 // float-quirk section properties [REF src/beamsimulator.cpp:173-188]
 // (the four products are float values in the reference; they are kept and uploaded as floats)
 void derive_props(int64_t E, const float *dims_bh, const float *mat_nuE, float *props4);

@@ -42,6 +42,12 @@ for mode in (0, 1):
         job, c, dt = run(PN, 1e-12, comm_mode=mode, precond=precond, cg_variant=variant)
         U, F = c.displacements(), c.edge_forces()
         st = c.stats()
+        bad, where = c.compare_plan()   # this rank's device-built plan against the host builders
+        flags = [None] * world
+        dist.all_gather_object(flags, (int(where), int(abs(bad).sum())))
+        if rank == 0:
+            print(f"[multi] PLAN world={world}: per rank (built on device: 0 no / 1 pattern / 2 pattern + solver format, mismatching entries "
+                  f"vs host builders) = {flags} {'OK' if all(f[1] == 0 for f in flags) else 'FAIL'}", flush=True)
         if rank == 0:
             from oracle import oracle as orc
             from helpers import to_oracle, rel_l2
