@@ -104,6 +104,26 @@ def test_validation_error_conventions(built):
     assert (mb.BeamMaterial().poissonsRatio, mb.BeamMaterial().youngsModulusGPascal) == (0.3, 210.0)  # [:27]
 
 
+def test_validation_of_a_large_job_reports_the_first_offending_beam(built):
+    """The per-beam checks run in parallel chunks of >= 65536 beams; the message must still be the one a serial scan in
+    the reference's order gives: the FIRST offending beam decides [REF src/beamsimulator.cpp:71-94, src/beam.hpp:14,25]."""
+    job = syn.cubic_lattice(42)          # 215 k beams: several chunks
+    E = job.elements.shape[0]
+    F1 = [(1, 2, -5.0)]
+    assert E > 3 * 65536 and _validate(job, forces=F1) == (L.OK, "")
+    late, early = E - 5, 70000            # different chunks
+    bad = syn.cubic_lattice(42)
+    bad.beamMaterial = np.array(bad.beamMaterial, np.float32); bad.beamDimensions = np.array(bad.beamDimensions, np.float32)
+    bad.beamMaterial[late, 0] = 0.9                                   # Poisson's ratio, late beam
+    assert _validate(bad, forces=F1) == (L.EPRECOND, "precondition violated: Poisson's ratio outside [-1, 0.5]")
+    bad.beamDimensions[early, 1] = -1.0                               # dimensions, earlier beam: wins
+    assert _validate(bad, forces=F1) == (L.EPRECOND, "precondition violated: beam dimensions must be positive")
+    bad.elements = np.array(bad.elements, np.int32); bad.elements[early - 1000, 0] = bad.elements[early - 1000, 1]
+    assert _validate(bad, forces=F1) == (L.EPRECOND, "precondition violated: zero-length beam (both ends on one vertex)")
+    bad.elements[5, 1] = job.nodes.shape[0]                           # out of range, first chunk: wins over everything
+    assert _validate(bad, forces=F1) == (L.EPRECOND, "precondition violated: element node index out of range")
+
+
 def test_host_props_bit_exact_vs_oracle(built):
     rng = np.random.default_rng(5)
     E = 20000
@@ -120,7 +140,9 @@ def test_host_props_bit_exact_vs_oracle(built):
 
 def test_host_free_map_bit_exact_vs_oracle(built):
     rng = np.random.default_rng(3)
-    for V, F in ((3, 1), (1000, 17), (50000, 7000)):
+    # (the last two sizes take the chunked, multi-threaded scan: several chunks of 65536 vertices; 300000 fixed entries
+    #  also mark in parallel)
+    for V, F in ((3, 1), (1000, 17), (50000, 7000), (400001, 90000), (700000, 300000)):
         fixed = rng.integers(0, V, F).astype(np.int32)  # duplicates on purpose
         fm = np.empty(V, np.int32); n = C.c_int64()
         assert L.lib().mbfea_host_free_map(V, F, L.ptr(fixed, L._pi32), L.ptr(fm, L._pi32), C.byref(n)) == L.OK
