@@ -154,9 +154,16 @@ const char  *mbfea_status_string(int status);
  * mat_nuE    2E floats   {nu,E_GPa} per beam     (std::vector<BeamMaterial>)
  * fixed      F  int32                            (Eigen::VectorXi fixedNodes)
  * f_node/f_dof/f_mag  nF entries                 (std::vector<NodalForce>)
- * All inputs are copied; the caller may free them on return.
+ * All inputs are copied; the caller may free them on return.  (Page-locked
+ * input arrays make the uploads asynchronous to the host work; pageable ones work.)
  * Section properties EA,EIz,EIy,GJ are derived here, on the host, in IEEE
  * float with the reference's promotion rules [REF src/beamsimulator.cpp:173-188].
+ * Everything else that is derived from the connectivity -- the block pattern of K,
+ * the assembly's contributor lists in the element order of the reference's triplets
+ * [REF :71-94], the solver format, the level hierarchy of the multilevel
+ * preconditioner -- is built on the device from the uploaded mesh (the host
+ * builders remain as reference and fallback: mbfea_debug_compare_plan /
+ * mbfea_debug_compare_hierarchy compare the two, entry for entry).
  */
 int mbfea_set_job(mbfea_ctx *ctx, int64_t V, int64_t E,
                   const double *nodes_cm, const int32_t *elems_cm,
