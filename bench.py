@@ -409,7 +409,8 @@ def main():
                "ms_set_job": 1e3 * parts[0] / args.steps, "ms_execute": 1e3 * parts[1] / args.steps,
                "ms_fetch_results": 1e3 * parts[2] / args.steps,
                "ms_host_prep": s2["ms_host_prep"], "ms_h2d_incl_plan": s2["ms_h2d"], "ms_d2h": s2["ms_d2h"],
-               "ms_per_step_parts": per_step}   # rank 0: [set_job, execute, fetch] of every timed step
+               "ms_per_step_parts": per_step,   # rank 0: [set_job, execute, fetch] of every timed step
+               "ms_per_step_median_rank0": statistics.median(sum(p3) for p3 in per_step) if per_step else None}
 
     # (after the end-to-end loop: a second context's host allocations in between slowed the next set_job by 200 ms)
     # ---- the same SpMV family on the full-row format (every block in its own row): more bytes, higher
