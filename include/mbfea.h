@@ -161,9 +161,10 @@ const char  *mbfea_status_string(int status);
  * Everything else that is derived from the connectivity -- the block pattern of K,
  * the assembly's contributor lists in the element order of the reference's triplets
  * [REF :71-94], the solver format, the level hierarchy of the multilevel
- * preconditioner -- is built on the device from the uploaded mesh (the host
- * builders remain as reference and fallback: mbfea_debug_compare_plan /
- * mbfea_debug_compare_hierarchy compare the two, entry for entry).
+ * preconditioner -- is built on the device from the uploaded mesh (host builders
+ * of the same index structures serve internally renumbered jobs and are the
+ * reference: mbfea_debug_compare_plan / mbfea_debug_compare_hierarchy compare the
+ * two, entry for entry).  No arithmetic of the path runs on the CPU.
  */
 int mbfea_set_job(mbfea_ctx *ctx, int64_t V, int64_t E,
                   const double *nodes_cm, const int32_t *elems_cm,
